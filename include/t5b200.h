@@ -1,0 +1,174 @@
+/* t5b200.h — C ABI of the B200-native batched fixed-dimension linear-algebra
+ * backend for the Haskell `tensor` library (tensor5/tensor).
+ *
+ * This is the drop-in boundary: the entry points below are exactly what a
+ * `foreign import ccall safe` binding in a device-backed sibling of
+ * Data.Tensor.Vector would bind (see INTEGRATION.md for the Haskell stubs).
+ * The reference has no FFI today; each entry cites the
+ * reference interface (file:line under the reference tree) whose job it takes
+ * over on the device.
+ *
+ * Conventions
+ *   - Every tensor of a batch is row-major, last index fastest — the reference's
+ *     wire order (src/Data/Tensor/Vector.hs:150-158 linearize, :360-367
+ *     fromList/toList).  A batch is `batch` such tensors.
+ *   - Host data is always AoS (tensors concatenated).  A device buffer is either
+ *     T5_AOS (same order) or T5_SOA (element-major: element e of item b of a
+ *     shard lives at [e * shard_capacity + b]).
+ *   - The batch axis is sharded over the context's devices by contiguous ranges
+ *     (t5_partition).  No collective runs on any path except t5_dot_sum.
+ *   - Every entry returns an int status (T5_OK == 0).  Nothing aborts, no C++
+ *     exception crosses the boundary, and there is NO CPU fallback: an
+ *     unsupported (dtype, shape, layout) is T5_ERR_UNSUPPORTED.
+ *   - Launches are asynchronous on the context's per-device streams;
+ *     t5_download, t5_sync, t5_dot_sum and t5_timer_end synchronise.
+ *   - Inputs are never written.  Outputs must be distinct buffers.
+ *   - Thread safety: a context serialises its entries with an internal mutex and
+ *     sets the current device at the top of every entry, so `ccall safe` callers
+ *     on several OS threads (GHC -threaded) and ForeignPtr finalizers running
+ *     t5_free on arbitrary threads are legal.
+ */
+#ifndef T5B200_H
+#define T5B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct t5_ctx t5_ctx;
+typedef struct t5_buf t5_buf;
+
+/* Element types.  Double / Float / Int of the reference's element parameter `e`
+ * (src/Data/Tensor/Vector.hs:121-124 `content :: V.Vector e`); T5_U8 is used
+ * only for the per-item status bytes of inverse / solve (the `Maybe` result). */
+enum { T5_F64 = 0, T5_F32 = 1, T5_I64 = 2, T5_U8 = 3 };
+enum { T5_AOS = 0, T5_SOA = 1 };
+
+enum {
+    T5_OK = 0,
+    T5_ERR_SHAPE = 1,       /* length / shape mismatch  <-> TensorException WrongListLength (src/Data/Tensor.hs:96-100) */
+    T5_ERR_UNSUPPORTED = 2, /* (dtype, shape, layout) has no device kernel; never falls back to the CPU */
+    T5_ERR_CUDA = 3,
+    T5_ERR_NCCL = 4,
+    T5_ERR_OOM = 5,
+    T5_ERR_INVALID = 6      /* NULL handle, buffers of different contexts / batch counts, aliasing output */
+};
+
+const char* t5_strerror(int code);
+/* Last CUDA / NCCL error text seen by this context (empty string when none). */
+const char* t5_last_error(t5_ctx* ctx);
+/* Library build tag, e.g. "t5b200 sm_100a r1". */
+const char* t5_version(void);
+
+/* ---- context ------------------------------------------------------------- */
+/* devices == NULL && ndev == 0: every visible device.  One stream per device. */
+int t5_init(const int* devices, int ndev, t5_ctx** out);
+int t5_shutdown(t5_ctx* ctx);
+int t5_ndev(t5_ctx* ctx);
+int t5_sync(t5_ctx* ctx);
+
+/* Batch partitioner (pure function, no device needed): shard `g` of `ndev` owns
+ * items [first, first + count) of a batch of `batch` items.  Contiguous split,
+ * per-device share rounded up to a multiple of 256 items. */
+int t5_partition(size_t batch, int ndev, int g, size_t* first, size_t* count);
+
+/* ---- buffers --------------------------------------------------------------
+ * A buffer holds `batch` items of `elems_per_item` elements of `dtype`
+ * (the flat `content` vector of src/Data/Tensor/Vector.hs:121-124, unboxed),
+ * sharded by t5_partition.  Haskell owns it through a ForeignPtr whose
+ * finalizer is t5_free. */
+int t5_alloc(t5_ctx* ctx, int dtype, size_t elems_per_item, size_t batch, int layout, t5_buf** out);
+int t5_free(t5_buf* buf);
+/* host is AoS; bytes must equal batch * elems_per_item * sizeof(dtype), else
+ * T5_ERR_SHAPE (fromList's length check, src/Data/Tensor/Vector.hs:362-366). */
+int t5_upload(t5_buf* buf, const void* host, size_t bytes);
+int t5_download(t5_buf* buf, void* host, size_t bytes); /* toList, Vector.hs:367 */
+/* AoS <-> SoA re-layout on the device (dst and src differ only in layout). */
+int t5_relayout(t5_buf* dst, const t5_buf* src);
+void* t5_pinned_alloc(size_t bytes);
+void t5_pinned_free(void* p);
+/* introspection used by the tests */
+size_t t5_buf_batch(const t5_buf* buf);
+size_t t5_buf_elems(const t5_buf* buf);
+int t5_buf_dtype(const t5_buf* buf);
+int t5_buf_layout(const t5_buf* buf);
+
+/* ---- operations -----------------------------------------------------------
+ * All operands of one call must belong to the same context and have the same
+ * batch count and layout. */
+
+/* MatrixProduct (.*.): C[i,c] = fold_{j ascending} (acc + A[i,j]*B[j,c]), acc0 = 0,
+ * multiply then add, never fused.  A is m x k, B is k x n, C is m x n.  n == 1 is
+ * matrix . vector, m == 1 vector . matrix.  Int64 wraps.  (Absent from the
+ * reference checkout — CHANGELOG.md:24-25; specified in SURVEY.md §8a a6.) */
+int t5_matmul(t5_ctx* ctx, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C);
+
+/* DotProduct (dot): OUT[b] = fold_{i ascending} (acc + X[b,i]*Y[b,i]).  §8a a7. */
+int t5_dot(t5_ctx* ctx, int dtype, int n, const t5_buf* X, const t5_buf* Y, t5_buf* OUT);
+
+/* sum_b dot(X_b, Y_b) -> *host_scalar (of dtype).  The only entry with a
+ * cross-device exchange: per-device partials are summed with a 1-element
+ * ncclAllReduce(ncclSum) when NCCL can be loaded, else (and always when
+ * ndev == 1) in fixed device order on the host.  Float/Double partials are
+ * accumulated in double.  Synchronises. */
+int t5_dot_sum(t5_ctx* ctx, int dtype, int n, const t5_buf* X, const t5_buf* Y, void* host_scalar);
+/* 1 when the last multi-device t5_dot_sum went through NCCL, 0 host-sum. */
+int t5_dot_sum_used_nccl(t5_ctx* ctx);
+
+/* TensorProduct / prod n: contract the last `ncontract` indices of A with the
+ * first `ncontract` of B (dims must agree, else T5_ERR_SHAPE).  ncontract == 0 is
+ * the outer product, one multiply per output.  §8a a8. */
+int t5_prod(t5_ctx* ctx, int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB,
+            int ncontract, const t5_buf* A, const t5_buf* B, t5_buf* C);
+
+/* transpose = unRev . t0: full index reversal, shape reversed
+ * (src/Data/Indexable.hs:101-102; src/Data/Tensor/Vector.hs:295-301, :306-307).
+ * Pure permutation, bit-exact for every dtype. */
+int t5_transpose(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, const t5_buf* A, t5_buf* OUT);
+
+/* SquareMatrix det / inverse and LinearSystem solve by Gaussian elimination
+ * with the first-non-zero pivot rule of SURVEY.md §8a (a9-a11).  Double and
+ * Float only (T5_I64 -> T5_ERR_UNSUPPORTED: needs Fractional).  STATUS is a
+ * T5_U8 buffer with one byte per item: 0 = Just, 1 = Nothing (singular; the
+ * item's output is zero-filled). */
+int t5_det(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
+int t5_inverse(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* STATUS);
+int t5_solve(t5_ctx* ctx, int dtype, int n, int nrhs, const t5_buf* A, const t5_buf* B, t5_buf* X, t5_buf* STATUS);
+
+/* Element-wise vector-space operations (Functor/Applicative instances,
+ * src/Data/Tensor/Vector.hs:180-190, :250-251: liftA2 (+), liftA2 (-), scalar *).
+ * op: 0 = a + b, 1 = a - b, 2 = a * b (Hadamard); t5_scale multiplies by *scalar. */
+int t5_zip(t5_ctx* ctx, int dtype, int op, const t5_buf* A, const t5_buf* B, t5_buf* C);
+int t5_scale(t5_ctx* ctx, int dtype, const void* scalar, const t5_buf* A, t5_buf* C);
+
+/* ---- host-buffer (end-to-end) entries --------------------------------------
+ * Same operations on HOST AoS arrays: the call uploads chunks, runs the kernel
+ * and downloads results, overlapping the three on separate streams.  This is
+ * what a Haskell instance method on an ordinary (host) tensor batch calls.
+ * Pinned host memory (t5_pinned_alloc) gives full PCIe speed. */
+int t5_matmul_host(t5_ctx* ctx, int dtype, int m, int k, int n, size_t batch,
+                   const void* A, const void* B, void* C);
+
+/* ---- measurement helpers ---------------------------------------------------
+ * CUDA events on the context's own streams (the streams the kernels run on);
+ * t5_timer_end synchronises and returns the MAX over devices in milliseconds. */
+int t5_timer_begin(t5_ctx* ctx);
+int t5_timer_end(t5_ctx* ctx, float* ms_max);
+/* Overwrite a > L2-sized scratch buffer on every device (L2 flush between timed
+ * iterations of small workloads). */
+int t5_flush_l2(t5_ctx* ctx);
+/* Counter-based synthetic inputs generated on the device:
+ * element i of the GLOBAL batch stream = f(splitmix64((seed ^ (op_id << 56)) + i)). */
+int t5_fill_synthetic(t5_buf* buf, uint64_t seed, uint64_t op_id);
+/* Every swap_every-th matrix gets A[1,1] := 0, every sing_every-th row 2 := row 1. */
+int t5_plant_specials(t5_buf* buf, int n, uint64_t swap_every, uint64_t sing_every);
+/* Number of kernels this context has launched since t5_init. */
+uint64_t t5_launch_count(t5_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T5B200_H */

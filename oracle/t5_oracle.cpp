@@ -1,0 +1,394 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// CPU restatement of the reference's (tensor5/tensor) storage / index
+// conventions and of the batched linear-algebra hot path that SURVEY.md §8a
+// specifies.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// `--impl reference` leg may load this library; the product (tensor_b200/) never
+// does and fails loudly when its CUDA library is missing.
+//
+// PARITY STATUS
+//   * transpose / linearize / unlinearize follow reference code that exists
+//     (src/Data/Tensor/Vector.hs:150-168, :295-301, :306-307,
+//      src/Data/Indexable.hs:101-102) and are pinned in tests/ against the
+//     hand-derived known answers of SURVEY.md §3a and against an independent
+//     restatement of the GADT backend's unRev/unConcat
+//     (src/Data/Tensor.hs:229-255; the reference's own tests
+//      tests/Tensor.hs:62-79 tie unRev to unConcat).
+//   * matmul (.*.), dot, prod n, det, inverse, solve: the reference checkout
+//     has NO implementation (CHANGELOG.md:24-29 is the only trace; SURVEY.md
+//     §0 F1).  Their arithmetic is the specification of SURVEY.md §8a.
+//     **PARITY UNPINNED** for these: the oracle is the specification.
+//   * No Haskell toolchain exists in this image, so oracle/_ref cannot be built.
+//
+// Build:  g++ -O2 -ffp-contract=off -fno-fast-math  (see oracle/build.sh)
+// -ffp-contract=off is REQUIRED: the specification is "multiply, round, add,
+// round" (GHC primops on Double/Float never fuse).
+//
+// Element types: 0 = Double (f64), 1 = Float (f32), 2 = Int (i64, two's
+// complement wrap-around like GHC's Int).
+
+#include <cstdint>
+#include <cstring>
+#include <cstddef>
+#include <vector>
+#include <thread>
+#include <algorithm>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Index conventions.  Vector.hs:150-158 `linearize ds is`: 1-based multi-index
+// -> 0-based row-major offset; Vector.hs:160-168 `unlinearize ds i`: inverse.
+// ---------------------------------------------------------------------------
+static inline uint64_t product_tail(const uint64_t* ds, int r, int from) {
+    uint64_t p = 1;
+    for (int a = from; a < r; ++a) p *= ds[a];
+    return p;
+}
+
+// go es js acc = acc + (head js - 1) * product (tail es)        (Vector.hs:158)
+static uint64_t linearize(const uint64_t* ds, const uint64_t* is, int r) {
+    uint64_t acc = 0;
+    for (int a = 0; a < r; ++a) acc += (is[a] - 1) * product_tail(ds, r, a + 1);
+    return acc;
+}
+
+// (q,r) = quotRem j (product t); emit q+1                       (Vector.hs:167-168)
+static void unlinearize(const uint64_t* ds, int r, uint64_t i, uint64_t* out) {
+    uint64_t j = i;
+    for (int a = 0; a < r; ++a) {
+        uint64_t p = product_tail(ds, r, a + 1);
+        out[a] = j / p + 1;
+        j = j % p;
+    }
+}
+
+// transposeV ds = linearize ds . reverse . unlinearize (reverse ds)  (Vector.hs:306-307)
+static uint64_t transposeV(const uint64_t* ds, int r, uint64_t i) {
+    uint64_t rd[16], ix[16], rix[16];
+    for (int a = 0; a < r; ++a) rd[a] = ds[r - 1 - a];
+    unlinearize(rd, r, i, ix);
+    for (int a = 0; a < r; ++a) rix[a] = ix[r - 1 - a];
+    return linearize(ds, rix, r);
+}
+
+// ---------------------------------------------------------------------------
+// Element arithmetic.  Int = wrap-around (computed in uint64_t).
+// ---------------------------------------------------------------------------
+template <class T> struct Arith {
+    static inline T zero() { return T(0); }
+    static inline T one() { return T(1); }
+    static inline T mul(T a, T b) { return a * b; }
+    static inline T add(T a, T b) { return a + b; }
+    static inline T sub(T a, T b) { return a - b; }
+};
+template <> struct Arith<int64_t> {
+    static inline int64_t zero() { return 0; }
+    static inline int64_t one() { return 1; }
+    static inline int64_t mul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
+    static inline int64_t add(int64_t a, int64_t b) { return (int64_t)((uint64_t)a + (uint64_t)b); }
+    static inline int64_t sub(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
+};
+
+// C[i,k] = fold_{j ascending} (acc + A[i,j]*B[j,k]), acc0 = 0.
+template <class T>
+static void matmul_item(const T* A, const T* B, T* C, int m, int k, int n) {
+    using R = Arith<T>;
+    for (int i = 0; i < m; ++i)
+        for (int c = 0; c < n; ++c) {
+            T acc = R::zero();
+            for (int j = 0; j < k; ++j) acc = R::add(acc, R::mul(A[i * k + j], B[j * n + c]));
+            C[i * n + c] = acc;
+        }
+}
+
+// contract the last nc indices of A with the first nc of B.
+// nc = 0: one multiply per output, no add.
+template <class T>
+static void prod_item(const T* A, const T* B, T* C, int P, int K, int Q, int nc) {
+    using R = Arith<T>;
+    if (nc == 0) {
+        for (int p = 0; p < P; ++p)
+            for (int q = 0; q < Q; ++q) C[(size_t)p * Q + q] = R::mul(A[p], B[q]);
+    } else {
+        matmul_item(A, B, C, P, K, Q);
+    }
+}
+
+// SURVEY §8a "Pivot rule": in column k the pivot is the FIRST row r >= k with
+// W[r,k] != 0 (exact compare); swap rows k and r; for i > k:
+// f = W[i,k] / W[k,k]; W[i,j] -= f*W[k,j] for j = k+1..n-1 then the augmented
+// columns; W[i,k] = 0.  W is n x (n+nrhs) row-major.  Returns false when some
+// column has no non-zero pivot.  *swaps counts row exchanges.
+template <class T>
+static bool forward_eliminate(T* W, int n, int nrhs, int* swaps) {
+    const int w = n + nrhs;
+    *swaps = 0;
+    for (int k = 0; k < n; ++k) {
+        int r = k;
+        while (r < n && W[r * w + k] == T(0)) ++r;
+        if (r == n) return false;
+        if (r != k) {
+            for (int j = 0; j < w; ++j) std::swap(W[k * w + j], W[r * w + j]);
+            ++*swaps;
+        }
+        for (int i = k + 1; i < n; ++i) {
+            T f = W[i * w + k] / W[k * w + k];
+            for (int j = k + 1; j < w; ++j) W[i * w + j] = W[i * w + j] - f * W[k * w + j];
+            W[i * w + k] = T(0);
+        }
+    }
+    return true;
+}
+
+// a9: det = (-1)^swaps * prod_{k ascending} pivot_k, product folded from 1;
+// singular -> exact +0.
+template <class T>
+static T det_item(const T* A, int n) {
+    T W[16 * 16];
+    std::memcpy(W, A, sizeof(T) * n * n);
+    int swaps;
+    if (!forward_eliminate(W, n, 0, &swaps)) return T(0);
+    T acc = T(1);
+    for (int k = 0; k < n; ++k) acc = acc * W[k * n + k];
+    return (swaps & 1) ? -acc : acc;
+}
+
+// a11: forward elimination on [A | B] then back-substitution, k = n-1..0,
+// s = fold_{j = k+1..n-1 ascending} (s + U[k,j]*X[j,c]) from 0,
+// X[k,c] = (Y[k,c] - s) / U[k,k].   status 1 (and zero-filled X) when singular.
+template <class T>
+static uint8_t solve_item(const T* A, const T* B, T* X, int n, int nrhs) {
+    T W[16 * 32];
+    const int w = n + nrhs;
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) W[i * w + j] = A[i * n + j];
+        for (int c = 0; c < nrhs; ++c) W[i * w + n + c] = B[i * nrhs + c];
+    }
+    int swaps;
+    if (!forward_eliminate(W, n, nrhs, &swaps)) {
+        for (int i = 0; i < n * nrhs; ++i) X[i] = T(0);
+        return 1;
+    }
+    for (int k = n - 1; k >= 0; --k)
+        for (int c = 0; c < nrhs; ++c) {
+            T s = T(0);
+            for (int j = k + 1; j < n; ++j) s = s + W[k * w + j] * X[j * nrhs + c];
+            X[k * nrhs + c] = (W[k * w + n + c] - s) / W[k * w + k];
+        }
+    return 0;
+}
+
+// a10: inverse(A) = solve(A, I) (Gauss-Jordan on [A | I] carried out as forward
+// elimination + back-substitution, every arithmetic step performed even on the
+// structural zeros of I so that the GPU kernel can share one code path).
+template <class T>
+static uint8_t inverse_item(const T* A, T* X, int n) {
+    T I[16 * 16];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) I[i * n + j] = (i == j) ? T(1) : T(0);
+    return solve_item(A, I, X, n, n);
+}
+
+// Run f(b0, b1) over contiguous chunks of [0, batch) on `threads` std::threads.
+template <class F>
+static void par_chunks(size_t batch, int threads, F f) {
+    if (threads <= 1 || batch < 1024) { f(size_t(0), batch); return; }
+    std::vector<std::thread> th;
+    size_t per = (batch + threads - 1) / threads;
+    for (int t = 0; t < threads; ++t) {
+        size_t b0 = std::min(batch, per * t), b1 = std::min(batch, per * (t + 1));
+        if (b0 < b1) th.emplace_back([=] { f(b0, b1); });
+    }
+    for (auto& x : th) x.join();
+}
+
+template <class T>
+static void matmul_batch(const void* A, const void* B, void* C, int m, int k, int n, size_t batch, int threads) {
+    const T* a = (const T*)A; const T* b = (const T*)B; T* c = (T*)C;
+    par_chunks(batch, threads, [=](size_t b0, size_t b1) {
+        for (size_t i = b0; i < b1; ++i)
+            matmul_item<T>(a + i * m * k, b + i * k * n, c + i * m * n, m, k, n);
+    });
+}
+template <class T>
+static void prod_batch(const void* A, const void* B, void* C, int P, int K, int Q, int nc, size_t batch, int threads) {
+    const T* a = (const T*)A; const T* b = (const T*)B; T* c = (T*)C;
+    par_chunks(batch, threads, [=](size_t b0, size_t b1) {
+        for (size_t i = b0; i < b1; ++i)
+            prod_item<T>(a + i * (size_t)P * K, b + i * (size_t)K * Q, c + i * (size_t)P * Q, P, K, Q, nc);
+    });
+}
+
+static inline uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- index conventions (Vector.hs:150-168, :306-307) ----------------------
+uint64_t t5o_linearize(const uint64_t* ds, const uint64_t* is, int r) { return linearize(ds, is, r); }
+void t5o_unlinearize(const uint64_t* ds, int r, uint64_t i, uint64_t* out) { unlinearize(ds, r, i, out); }
+uint64_t t5o_transposeV(const uint64_t* ds, int r, uint64_t i) { return transposeV(ds, r, i); }
+
+// ---- transpose = unRev . t0  (Indexable.hs:101-102, Vector.hs:295-301) ------
+// unRev with sh = [] : zh = reverse rh; out[i] = content ! transposeV rh i.
+// Pure permutation: elem_bytes in {4, 8}.
+int t5o_transpose(int elem_bytes, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT) {
+    if (rank < 0 || rank > 16) return 1;
+    uint64_t d = 1;
+    for (int a = 0; a < rank; ++a) d *= dims[a];
+    std::vector<uint64_t> perm(d);
+    for (uint64_t i = 0; i < d; ++i) perm[i] = transposeV(dims, rank, i);
+    const char* in = (const char*)A; char* out = (char*)OUT;
+    for (size_t b = 0; b < batch; ++b)
+        for (uint64_t i = 0; i < d; ++i)
+            std::memcpy(out + (b * d + i) * elem_bytes, in + (b * d + perm[i]) * elem_bytes, elem_bytes);
+    return 0;
+}
+
+// ---- .*. (a6) -------------------------------------------------------------
+int t5o_matmul(int dtype, int m, int k, int n, size_t batch, const void* A, const void* B, void* C, int threads) {
+    switch (dtype) {
+        case 0: matmul_batch<double>(A, B, C, m, k, n, batch, threads); return 0;
+        case 1: matmul_batch<float>(A, B, C, m, k, n, batch, threads); return 0;
+        case 2: matmul_batch<int64_t>(A, B, C, m, k, n, batch, threads); return 0;
+    }
+    return 2;
+}
+
+// ---- dot (a7): one scalar per pair ------------------------------------------
+int t5o_dot(int dtype, int n, size_t batch, const void* X, const void* Y, void* OUT, int threads) {
+    return t5o_matmul(dtype, 1, n, 1, batch, X, Y, OUT, threads);
+}
+
+// ---- batch-sum of dot (a7, H4): Float/Double partial dots are accumulated in
+// double (the stated comparison target for the GPU tree reduction); Int wraps.
+int t5o_dot_sum(int dtype, int n, size_t batch, const void* X, const void* Y, void* out_scalar) {
+    if (dtype == 2) {
+        const int64_t* x = (const int64_t*)X; const int64_t* y = (const int64_t*)Y;
+        uint64_t s = 0;
+        for (size_t b = 0; b < batch; ++b) {
+            int64_t d; matmul_item<int64_t>(x + b * n, y + b * n, &d, 1, n, 1);
+            s += (uint64_t)d;
+        }
+        *(int64_t*)out_scalar = (int64_t)s;
+        return 0;
+    }
+    // Neumaier-compensated double accumulation of the per-pair dots.
+    double s = 0.0, comp = 0.0;
+    for (size_t b = 0; b < batch; ++b) {
+        double d;
+        if (dtype == 0) { matmul_item<double>((const double*)X + b * n, (const double*)Y + b * n, &d, 1, n, 1); }
+        else if (dtype == 1) { float f; matmul_item<float>((const float*)X + b * n, (const float*)Y + b * n, &f, 1, n, 1); d = f; }
+        else return 2;
+        double t = s + d;
+        if ((s >= 0 ? s : -s) >= (d >= 0 ? d : -d)) comp += (s - t) + d; else comp += (d - t) + s;
+        s = t;
+    }
+    s += comp;
+    if (dtype == 0) *(double*)out_scalar = s; else *(float*)out_scalar = (float)s;
+    return 0;
+}
+
+// ---- prod n (a8) ------------------------------------------------------------
+int t5o_prod(int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int ncontract,
+             size_t batch, const void* A, const void* B, void* C, int threads) {
+    if (ncontract < 0 || ncontract > rankA || ncontract > rankB) return 1;
+    uint64_t P = 1, K = 1, Q = 1;
+    for (int a = 0; a < rankA - ncontract; ++a) P *= dimsA[a];
+    for (int a = 0; a < ncontract; ++a) {
+        if (dimsA[rankA - ncontract + a] != dimsB[a]) return 1;
+        K *= dimsB[a];
+    }
+    for (int a = ncontract; a < rankB; ++a) Q *= dimsB[a];
+    switch (dtype) {
+        case 0: prod_batch<double>(A, B, C, (int)P, (int)K, (int)Q, ncontract, batch, threads); return 0;
+        case 1: prod_batch<float>(A, B, C, (int)P, (int)K, (int)Q, ncontract, batch, threads); return 0;
+        case 2: prod_batch<int64_t>(A, B, C, (int)P, (int)K, (int)Q, ncontract, batch, threads); return 0;
+    }
+    return 2;
+}
+
+// ---- det / inverse / solve (a9-a11): Fractional element types only ---------
+int t5o_det(int dtype, int n, size_t batch, const void* A, void* OUT, int threads) {
+    if (n < 1 || n > 16) return 1;
+    if (dtype == 0) {
+        const double* a = (const double*)A; double* o = (double*)OUT;
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) o[b] = det_item<double>(a + b * n * n, n); });
+        return 0;
+    }
+    if (dtype == 1) {
+        const float* a = (const float*)A; float* o = (float*)OUT;
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) o[b] = det_item<float>(a + b * n * n, n); });
+        return 0;
+    }
+    return 2;
+}
+int t5o_inverse(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* status, int threads) {
+    if (n < 1 || n > 16) return 1;
+    if (dtype == 0) {
+        const double* a = (const double*)A; double* o = (double*)OUT;
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = inverse_item<double>(a + b * n * n, o + b * n * n, n); });
+        return 0;
+    }
+    if (dtype == 1) {
+        const float* a = (const float*)A; float* o = (float*)OUT;
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = inverse_item<float>(a + b * n * n, o + b * n * n, n); });
+        return 0;
+    }
+    return 2;
+}
+int t5o_solve(int dtype, int n, int nrhs, size_t batch, const void* A, const void* B, void* X, uint8_t* status, int threads) {
+    if (n < 1 || n > 16 || nrhs < 1 || nrhs > 16) return 1;
+    if (dtype == 0) {
+        const double* a = (const double*)A; const double* bb = (const double*)B; double* x = (double*)X;
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = solve_item<double>(a + b * n * n, bb + b * n * nrhs, x + b * n * nrhs, n, nrhs); });
+        return 0;
+    }
+    if (dtype == 1) {
+        const float* a = (const float*)A; const float* bb = (const float*)B; float* x = (float*)X;
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = solve_item<float>(a + b * n * n, bb + b * n * nrhs, x + b * n * nrhs, n, nrhs); });
+        return 0;
+    }
+    return 2;
+}
+
+// ---- synthetic inputs -----------------------------------------
+// x = splitmix64(seed ^ (op_id << 56) + global_element_index); Double =
+// ((x >> 11) * 2^-53) * 2 - 1; Float = ((x >> 40) * 2^-24) * 2 - 1; Int = x.
+// `first_elem` lets a shard generate its slice of the global stream.
+int t5o_fill(int dtype, uint64_t seed, uint64_t op_id, uint64_t first_elem, size_t count, void* out) {
+    const uint64_t base = seed ^ (op_id << 56);
+    for (size_t i = 0; i < count; ++i) {
+        uint64_t x = splitmix64(base + first_elem + i);
+        if (dtype == 0) ((double*)out)[i] = ((double)(x >> 11) * 0x1.0p-53) * 2.0 - 1.0;
+        else if (dtype == 1) ((float*)out)[i] = ((float)(x >> 40) * 0x1.0p-24f) * 2.0f - 1.0f;
+        else if (dtype == 2) ((int64_t*)out)[i] = (int64_t)x;
+        else return 2;
+    }
+    return 0;
+}
+
+// elimination configs — every `swap_every`-th matrix gets
+// A[1,1] := 0 (forces a row swap), every `sing_every`-th gets row 2 := row 1
+// (exactly singular).  first_item = global index of matrix 0 of this slice.
+int t5o_plant_specials(int dtype, int n, uint64_t first_item, size_t batch, void* A, uint64_t swap_every, uint64_t sing_every) {
+    if (dtype != 0 && dtype != 1) return 2;
+    const size_t es = dtype == 0 ? 8 : 4;
+    char* a = (char*)A;
+    for (size_t b = 0; b < batch; ++b) {
+        uint64_t g = first_item + b;
+        char* m = a + b * (size_t)n * n * es;
+        if (swap_every && g % swap_every == 0) std::memset(m, 0, es);
+        if (sing_every && g % sing_every == 0 && n >= 2) std::memcpy(m + (size_t)n * es, m, (size_t)n * es);
+    }
+    return 0;
+}
+
+}  // extern "C"

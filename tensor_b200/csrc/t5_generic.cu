@@ -1,0 +1,470 @@
+// Any-shape kernels: the general form of every operation (so that the C ABI is a
+// drop-in for arbitrary fixed dimensions, not just the benchmarked ones), plus
+// the utility kernels (synthetic fill, re-layout, reductions, element-wise ops).
+// Compiled with -fmad=false (bit-exact against the oracle's multiply-round-add).
+#include "t5_device.cuh"
+#include "t5_internal.h"
+
+namespace t5 {
+
+static inline int sm_count() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : T5_SM_COUNT_FALLBACK;
+}
+static inline int ok() { return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA; }
+
+// =====================================================================================
+// prod n: per item C[P x Q] = A[P x K] . B[K x Q]; consecutive threads
+// own consecutive output vectors (coalesced stores, B rows coalesced, A broadcast).
+// =====================================================================================
+template <class T, int VEC> struct VecT;
+template <> struct VecT<double, 2> { using type = double2; };
+template <> struct VecT<long long, 2> { using type = longlong2; };
+template <> struct VecT<float, 4> { using type = float4; };
+template <class T> struct VecT<T, 1> { using type = T; };
+
+template <class T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+prod_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int K, int Q, int nc,
+            unsigned long long count, int G) {
+    using R = Arith<T>;
+    using V = typename VecT<T, VEC>::type;
+    const int PQ = P * Q;
+    const int PQv = PQ / VEC;
+    const size_t strideA = (size_t)P * K, strideB = (size_t)K * Q;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const int gc = left < (unsigned long long)G ? (int)left : G;
+        const int total = gc * PQv;
+        for (int l = threadIdx.x; l < total; l += THREADS) {
+            const int il = l / PQv;
+            const int e = (l - il * PQv) * VEC;
+            const int p = e / Q;
+            const int q = e - p * Q;
+            const T* a = A + (g0 + il) * strideA + (size_t)p * K;
+            const T* b = B + (g0 + il) * strideB + q;
+            T acc[VEC];
+            if (nc == 0) {
+                const T av = __ldg(a);
+                V bv = __ldg(reinterpret_cast<const V*>(b));
+                #pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = R::mul(av, reinterpret_cast<const T*>(&bv)[j]);
+            } else {
+                #pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = R::zero();
+                for (int k = 0; k < K; ++k) {
+                    const T av = __ldg(a + k);
+                    V bv = __ldg(reinterpret_cast<const V*>(b + (size_t)k * Q));
+                    #pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[j] = R::add(acc[j], R::mul(av, reinterpret_cast<const T*>(&bv)[j]));
+                }
+            }
+            V out;
+            #pragma unroll
+            for (int j = 0; j < VEC; ++j) reinterpret_cast<T*>(&out)[j] = acc[j];
+            *reinterpret_cast<V*>(C + (g0 + il) * (size_t)PQ + e) = out;
+        }
+    }
+}
+
+template <class T, int VEC>
+static int prod_launch(const Shard& s, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
+    constexpr int THREADS = 256;
+    if (s.count == 0) return T5I_OK;
+    const long long PQv = (long long)P * Q / VEC;
+    int G = (int)((THREADS * 8 + PQv - 1) / PQv);
+    if (G < 1) G = 1;
+    if ((long long)G * PQv > 0x3fffffff) return T5I_UNSUPPORTED;
+    size_t units = (s.count + G - 1) / G;
+    size_t cap = (size_t)sm_count() * 8;
+    int grid = (int)(units < cap ? units : cap);
+    prod_kernel<T, VEC, THREADS><<<grid, THREADS, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, K, Q, nc,
+                                                                 (unsigned long long)s.count, G);
+    return ok();
+}
+
+int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
+    if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
+    if ((long long)P * Q > (1 << 28) || (long long)P * K > (1 << 28) || (long long)K * Q > (1 << 28)) return T5I_UNSUPPORTED;
+    switch (dtype) {
+        case T5D_F64: return (Q % 2 == 0) ? prod_launch<double, 2>(s, P, K, Q, nc, A, B, C) : prod_launch<double, 1>(s, P, K, Q, nc, A, B, C);
+        case T5D_I64: return (Q % 2 == 0) ? prod_launch<long long, 2>(s, P, K, Q, nc, A, B, C) : prod_launch<long long, 1>(s, P, K, Q, nc, A, B, C);
+        case T5D_F32: return (Q % 4 == 0) ? prod_launch<float, 4>(s, P, K, Q, nc, A, B, C) : prod_launch<float, 1>(s, P, K, Q, nc, A, B, C);
+    }
+    return T5I_UNSUPPORTED;
+}
+
+// =====================================================================================
+// transpose, any rank: out[b][i] = in[b][perm[i]] with perm = transposeV dims
+// (src/Data/Tensor/Vector.hs:306-307) tabulated once per shape by the host layer.
+// =====================================================================================
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+permute_kernel(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ perm, unsigned d,
+               unsigned long long count, int G) {
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
+        const unsigned total = gc * d;
+        for (unsigned l = threadIdx.x; l < total; l += THREADS) {
+            const unsigned il = l / d;
+            const unsigned i = l - il * d;
+            const size_t base = (size_t)(g0 + il) * d;
+            out[base + i] = __ldg(in + base + __ldg(perm + i));
+        }
+    }
+}
+
+int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O) {
+    constexpr int THREADS = 256;
+    if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    if (d > (1u << 28)) return T5I_UNSUPPORTED;
+    int G = (int)((THREADS * 16 + d - 1) / d);
+    if (G < 1) G = 1;
+    size_t units = (s.count + G - 1) / G;
+    size_t cap = (size_t)sm_count() * 8;
+    int grid = (int)(units < cap ? units : cap);
+    if (elem_bytes == 8)
+        permute_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (unsigned long long*)O, perm_dev, (unsigned)d, s.count, G);
+    else if (elem_bytes == 4)
+        permute_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)A, (unsigned*)O, perm_dev, (unsigned)d, s.count, G);
+    else
+        return T5I_UNSUPPORTED;
+    return ok();
+}
+
+// =====================================================================================
+// Gaussian elimination for 5 <= n <= 8 (and any n <= 8 / nrhs <= 8 not specialised in
+// t5_small_ops.cu): thread per item, working matrix in local memory.  Same pivot rule
+// and operation order as the specialised kernels and the oracle.
+// =====================================================================================
+constexpr int GEN_MAXN = 8;
+
+template <class T>
+__device__ bool gen_eliminate(T* w, int n, int wd, int* swaps) {
+    *swaps = 0;
+    for (int k = 0; k < n; ++k) {
+        int r = k;
+        while (r < n && w[r * wd + k] == T(0)) ++r;
+        if (r == n) return false;
+        if (r != k) {
+            for (int j = 0; j < wd; ++j) { T t = w[k * wd + j]; w[k * wd + j] = w[r * wd + j]; w[r * wd + j] = t; }
+            ++*swaps;
+        }
+        for (int i = k + 1; i < n; ++i) {
+            const T f = w[i * wd + k] / w[k * wd + k];
+            for (int j = k + 1; j < wd; ++j) w[i * wd + j] = w[i * wd + j] - f * w[k * wd + j];
+            w[i * wd + k] = T(0);
+        }
+    }
+    return true;
+}
+
+template <class T>
+__global__ void gen_det_kernel(const T* __restrict__ A, T* __restrict__ out, int n, unsigned long long count) {
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        T w[GEN_MAXN * GEN_MAXN];
+        const T* a = A + b * (size_t)(n * n);
+        for (int i = 0; i < n * n; ++i) w[i] = a[i];
+        int swaps;
+        T res = T(0);
+        if (gen_eliminate(w, n, n, &swaps)) {
+            T acc = T(1);
+            for (int k = 0; k < n; ++k) acc = acc * w[k * n + k];
+            res = (swaps & 1) ? -acc : acc;
+        }
+        out[b] = res;
+    }
+}
+
+template <class T>
+__global__ void gen_solve_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ X,
+                                 unsigned char* __restrict__ status, int n, int nrhs, bool identity_rhs,
+                                 unsigned long long count) {
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        T w[GEN_MAXN * 2 * GEN_MAXN];
+        T xs[GEN_MAXN * GEN_MAXN];
+        const int wd = n + nrhs;
+        const T* a = A + b * (size_t)(n * n);
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j < n; ++j) w[i * wd + j] = a[i * n + j];
+            for (int c = 0; c < nrhs; ++c)
+                w[i * wd + n + c] = identity_rhs ? (i == c ? T(1) : T(0)) : B[b * (size_t)(n * nrhs) + i * nrhs + c];
+        }
+        int swaps;
+        T* x = X + b * (size_t)(n * nrhs);
+        if (!gen_eliminate(w, n, wd, &swaps)) {
+            for (int i = 0; i < n * nrhs; ++i) x[i] = T(0);
+            status[b] = 1;
+            continue;
+        }
+        for (int k = n - 1; k >= 0; --k)
+            for (int c = 0; c < nrhs; ++c) {
+                T s = T(0);
+                for (int j = k + 1; j < n; ++j) s = s + w[k * wd + j] * xs[j * nrhs + c];
+                xs[k * nrhs + c] = (w[k * wd + n + c] - s) / w[k * wd + k];
+            }
+        for (int i = 0; i < n * nrhs; ++i) x[i] = xs[i];
+        status[b] = 0;
+    }
+}
+
+static inline int flat_grid(size_t n, int threads) {
+    size_t blocks = (n + threads - 1) / threads;
+    size_t cap = (size_t)sm_count() * 16;
+    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+int generic_det(const Shard& s, int dtype, int n, const void* A, void* O) {
+    if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    if (dtype == T5D_F64) gen_det_kernel<double><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const double*)A, (double*)O, n, s.count);
+    else if (dtype == T5D_F32) gen_det_kernel<float><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const float*)A, (float*)O, n, s.count);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs, const void* A, const void* B, void* X, void* status) {
+    if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN || nrhs < 1 || nrhs > GEN_MAXN) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    if (dtype == T5D_F64)
+        gen_solve_kernel<double><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const double*)A, (const double*)B, (double*)X, (unsigned char*)status, n, nrhs, identity_rhs, s.count);
+    else if (dtype == T5D_F32)
+        gen_solve_kernel<float><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const float*)A, (const float*)B, (float*)X, (unsigned char*)status, n, nrhs, identity_rhs, s.count);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+// =====================================================================================
+// Element-wise vector-space operations (Functor/Applicative, Vector.hs:180-190,
+// :250-251).  Layout-agnostic: they act on the flat element array of a shard.
+// =====================================================================================
+template <class T, int OP>
+__global__ void zip_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ c, unsigned long long n) {
+    using R = Arith<T>;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        T x = a[i], y = b[i];
+        c[i] = OP == 0 ? R::add(x, y) : (OP == 1 ? R::sub(x, y) : R::mul(x, y));
+    }
+}
+template <class T>
+__global__ void scale_kernel(const T* __restrict__ a, T* __restrict__ c, T k, unsigned long long n) {
+    using R = Arith<T>;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        c[i] = R::mul(k, a[i]);
+}
+
+template <class T>
+static int zip_t(const Shard& s, int op, size_t n, const void* A, const void* B, void* C) {
+    int g = flat_grid(n, 256);
+    if (op == 0) zip_kernel<T, 0><<<g, 256, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, n);
+    else if (op == 1) zip_kernel<T, 1><<<g, 256, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, n);
+    else if (op == 2) zip_kernel<T, 2><<<g, 256, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, n);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+// `elems` = number of stored elements of the shard (count*d for AoS, stride*d for SoA)
+int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, const void* B, void* C) {
+    if (elems == 0) return T5I_OK;
+    switch (dtype) {
+        case T5D_F64: return zip_t<double>(s, op, elems, A, B, C);
+        case T5D_F32: return zip_t<float>(s, op, elems, A, B, C);
+        case T5D_I64: return zip_t<long long>(s, op, elems, A, B, C);
+    }
+    return T5I_UNSUPPORTED;
+}
+
+int generic_scale(const Shard& s, int dtype, const void* k, size_t elems, const void* A, void* C) {
+    if (elems == 0) return T5I_OK;
+    int g = flat_grid(elems, 256);
+    switch (dtype) {
+        case T5D_F64: scale_kernel<double><<<g, 256, 0, s.stream>>>((const double*)A, (double*)C, *(const double*)k, elems); break;
+        case T5D_F32: scale_kernel<float><<<g, 256, 0, s.stream>>>((const float*)A, (float*)C, *(const float*)k, elems); break;
+        case T5D_I64: scale_kernel<long long><<<g, 256, 0, s.stream>>>((const long long*)A, (long long*)C, *(const long long*)k, elems); break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
+}
+
+// =====================================================================================
+// sum_b dot(x_b, y_b): a flat reduction of x[i]*y[i] (the product is rounded in the
+// element type, the sum is carried in double / wrapping int64).  Deterministic:
+// fixed grid, per-block partials reduced by one block in index order.
+// =====================================================================================
+template <class Acc> __device__ __forceinline__ Acc warp_sum(Acc v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+constexpr int DS_THREADS = 256;
+constexpr int DS_MAX_BLOCKS = 148 * 8;
+
+template <class T, class Acc>
+__global__ void __launch_bounds__(DS_THREADS)
+dot_sum_stage1(const T* __restrict__ x, const T* __restrict__ y, Acc* __restrict__ partials, unsigned long long n) {
+    using R = Arith<T>;
+    Acc acc = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * DS_THREADS + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * DS_THREADS)
+        acc += (Acc)R::mul(x[i], y[i]);
+    __shared__ Acc sm[DS_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Acc v = threadIdx.x < DS_THREADS / 32 ? sm[threadIdx.x] : Acc(0);
+        v = warp_sum(v);
+        if (threadIdx.x == 0) partials[blockIdx.x] = v;
+    }
+}
+template <class Acc>
+__global__ void __launch_bounds__(DS_THREADS) dot_sum_stage2(const Acc* __restrict__ partials, int nblocks, Acc* __restrict__ out) {
+    Acc acc = 0;
+    for (int i = threadIdx.x; i < nblocks; i += DS_THREADS) acc += partials[i];
+    __shared__ Acc sm[DS_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Acc v = threadIdx.x < DS_THREADS / 32 ? sm[threadIdx.x] : Acc(0);
+        v = warp_sum(v);
+        if (threadIdx.x == 0) *out = v;
+    }
+}
+
+// scratch_dev: >= DS_MAX_BLOCKS * 8 bytes.  SoA shards pass elems = stride*d with
+// zero padding (allocation is zero-initialised), so the flat form is layout-agnostic.
+int dot_sum_partial(const Shard& s, int dtype, size_t elems, const void* X, const void* Y, void* scratch, void* partial) {
+    size_t blocks = (elems + DS_THREADS - 1) / DS_THREADS;
+    int grid = (int)(blocks < (size_t)DS_MAX_BLOCKS ? (blocks ? blocks : 1) : DS_MAX_BLOCKS);
+    switch (dtype) {
+        case T5D_F64:
+            dot_sum_stage1<double, double><<<grid, DS_THREADS, 0, s.stream>>>((const double*)X, (const double*)Y, (double*)scratch, elems);
+            dot_sum_stage2<double><<<1, DS_THREADS, 0, s.stream>>>((const double*)scratch, grid, (double*)partial);
+            break;
+        case T5D_F32:
+            dot_sum_stage1<float, double><<<grid, DS_THREADS, 0, s.stream>>>((const float*)X, (const float*)Y, (double*)scratch, elems);
+            dot_sum_stage2<double><<<1, DS_THREADS, 0, s.stream>>>((const double*)scratch, grid, (double*)partial);
+            break;
+        case T5D_I64:
+            dot_sum_stage1<long long, unsigned long long><<<grid, DS_THREADS, 0, s.stream>>>((const long long*)X, (const long long*)Y, (unsigned long long*)scratch, elems);
+            dot_sum_stage2<unsigned long long><<<1, DS_THREADS, 0, s.stream>>>((const unsigned long long*)scratch, grid, (unsigned long long*)partial);
+            break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
+}
+
+// =====================================================================================
+// Synthetic inputs, generated where they are consumed.
+// =====================================================================================
+template <class T> __device__ __forceinline__ T synth(uint64_t x);
+template <> __device__ __forceinline__ double synth<double>(uint64_t x) { return ((double)(x >> 11) * 0x1.0p-53) * 2.0 - 1.0; }
+template <> __device__ __forceinline__ float synth<float>(uint64_t x) { return ((float)(x >> 40) * 0x1.0p-24f) * 2.0f - 1.0f; }
+template <> __device__ __forceinline__ long long synth<long long>(uint64_t x) { return (long long)x; }
+
+template <class T>
+__global__ void fill_kernel(T* dst, uint64_t base, unsigned long long first_item, unsigned long long count,
+                            unsigned long long d, int soa, unsigned long long stride) {
+    const unsigned long long n = count * d;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        unsigned long long gi, loc;
+        if (!soa) { gi = first_item * d + i; loc = i; }
+        else { unsigned long long e = i / count, b = i - e * count; gi = (first_item + b) * d + e; loc = e * stride + b; }
+        dst[loc] = synth<T>(splitmix64(base + gi));
+    }
+}
+
+int fill_synthetic(const Shard& s, int dtype, size_t d, uint64_t seed, uint64_t op_id, void* dst) {
+    if (s.count == 0) return T5I_OK;
+    const uint64_t base = seed ^ (op_id << 56);
+    int g = flat_grid(s.count * d, 256);
+    const int soa = s.layout == T5L_SOA;
+    switch (dtype) {
+        case T5D_F64: fill_kernel<double><<<g, 256, 0, s.stream>>>((double*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
+        case T5D_F32: fill_kernel<float><<<g, 256, 0, s.stream>>>((float*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
+        case T5D_I64: fill_kernel<long long><<<g, 256, 0, s.stream>>>((long long*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
+}
+
+template <class T>
+__global__ void plant_kernel(T* A, int n, unsigned long long first_item, unsigned long long count,
+                             unsigned long long swap_every, unsigned long long sing_every, int soa, unsigned long long stride) {
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long g = first_item + b;
+        const unsigned long long es = soa ? stride : 1;          // element stride
+        T* m = soa ? A + b : A + b * (unsigned long long)(n * n);
+        if (swap_every && g % swap_every == 0) m[0] = T(0);
+        if (sing_every && g % sing_every == 0 && n >= 2)
+            for (int j = 0; j < n; ++j) m[(unsigned long long)(n + j) * es] = m[(unsigned long long)j * es];
+    }
+}
+
+int plant_specials(const Shard& s, int dtype, int n, uint64_t swap_every, uint64_t sing_every, void* A) {
+    if (s.count == 0) return T5I_OK;
+    int g = flat_grid(s.count, 256);
+    const int soa = s.layout == T5L_SOA;
+    if (dtype == T5D_F64) plant_kernel<double><<<g, 256, 0, s.stream>>>((double*)A, n, s.first, s.count, swap_every, sing_every, soa, s.soa_stride);
+    else if (dtype == T5D_F32) plant_kernel<float><<<g, 256, 0, s.stream>>>((float*)A, n, s.first, s.count, swap_every, sing_every, soa, s.soa_stride);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+// =====================================================================================
+// AoS [count][d]  <->  SoA [d][stride]: a 32x32 shared-memory tiled transpose.
+// =====================================================================================
+template <class T>
+__global__ void __launch_bounds__(256)
+relayout_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long long count, unsigned d,
+                unsigned long long stride, int to_soa) {
+    __shared__ T tile[32][33];
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const unsigned long long n_bt = (count + 31) / 32;
+    const unsigned n_dt = (d + 31) / 32;
+    for (unsigned long long t = blockIdx.x; t < n_bt * n_dt; t += gridDim.x) {
+        const unsigned long long b0 = (t / n_dt) * 32;
+        const unsigned e0 = (unsigned)(t % n_dt) * 32;
+        __syncthreads();
+        if (to_soa) {
+            // read AoS rows: item b0+r, elements e0+tx (contiguous in e)
+            for (unsigned r = ty; r < 32; r += 8)
+                if (b0 + r < count && e0 + tx < d) tile[r][tx] = src[(b0 + r) * d + e0 + tx];
+            __syncthreads();
+            for (unsigned r = ty; r < 32; r += 8)
+                if (e0 + r < d && b0 + tx < count) dst[(unsigned long long)(e0 + r) * stride + b0 + tx] = tile[tx][r];
+        } else {
+            for (unsigned r = ty; r < 32; r += 8)
+                if (e0 + r < d && b0 + tx < count) tile[r][tx] = src[(unsigned long long)(e0 + r) * stride + b0 + tx];
+            __syncthreads();
+            for (unsigned r = ty; r < 32; r += 8)
+                if (b0 + r < count && e0 + tx < d) dst[(b0 + r) * d + e0 + tx] = tile[tx][r];
+        }
+    }
+}
+
+int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
+    if (count == 0 || d == 0) return T5I_OK;
+    size_t tiles = ((count + 31) / 32) * ((d + 31) / 32);
+    size_t cap = (size_t)sm_count() * 8;
+    int grid = (int)(tiles < cap ? tiles : cap);
+    if (elem_bytes == 8) relayout_kernel<unsigned long long><<<grid, 256, 0, st>>>((const unsigned long long*)src, (unsigned long long*)dst, count, (unsigned)d, soa_stride, to_soa);
+    else if (elem_bytes == 4) relayout_kernel<unsigned><<<grid, 256, 0, st>>>((const unsigned*)src, (unsigned*)dst, count, (unsigned)d, soa_stride, to_soa);
+    else if (elem_bytes == 1) relayout_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)src, (unsigned char*)dst, count, (unsigned)d, soa_stride, to_soa);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+}  // namespace t5

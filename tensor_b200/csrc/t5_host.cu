@@ -1,0 +1,774 @@
+// C-ABI host layer (include/t5b200.h): contexts, sharded device buffers, the batch
+// partitioner, per-operation validation + dispatch to the kernel TUs, the
+// host-buffer (end-to-end) pipeline, the NCCL dot-sum exchange and the timing
+// helpers.  No kernel lives here; no CPU arithmetic path exists: when no kernel
+// covers a request the entry returns T5_ERR_UNSUPPORTED.
+#include "../../include/t5b200.h"
+#include "t5_internal.h"
+
+#include <dlfcn.h>
+#include <nccl.h>  // types/enums only; the functions are resolved with dlsym at run time
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace t5;
+
+// -------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that the library has no link-time dependency on it.
+// -------------------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(handle, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        GroupStart = (decltype(GroupStart))dlsym(handle, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(handle, "ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd;
+    }
+};
+
+struct HostSlot {  // staging of the host-buffer pipeline
+    cudaStream_t stream = nullptr;
+    void* d[3] = {nullptr, nullptr, nullptr};
+    size_t cap[3] = {0, 0, 0};
+};
+
+struct t5_ctx {
+    std::mutex mu;
+    int ndev = 0;
+    int dev[T5_MAX_DEVICES];
+    cudaStream_t stream[T5_MAX_DEVICES];
+    cudaEvent_t ev0[T5_MAX_DEVICES], ev1[T5_MAX_DEVICES];
+    void* scratch[T5_MAX_DEVICES];   // dot-sum block partials + the device partial (at the end)
+    void* flush[T5_MAX_DEVICES];     // L2 flush target (lazy)
+    std::map<std::vector<uint64_t>, std::vector<uint32_t*>> perm_cache;  // dims -> per-device table
+    HostSlot slots[T5_MAX_DEVICES][3];
+    std::string last_error;
+    std::atomic<uint64_t> launches{0};
+    std::atomic<int> live_bufs{0};
+    NcclApi nccl;
+    ncclComm_t comms[T5_MAX_DEVICES];
+    bool nccl_ready = false, nccl_failed = false, used_nccl = false;
+};
+
+struct t5_buf {
+    t5_ctx* ctx;
+    int dtype, layout;
+    size_t elems, batch;
+    void* ptr[T5_MAX_DEVICES];
+    size_t first[T5_MAX_DEVICES], count[T5_MAX_DEVICES], cap[T5_MAX_DEVICES], bytes[T5_MAX_DEVICES];
+};
+
+static constexpr size_t SCRATCH_BYTES = 148 * 8 * 8 + 64;
+static constexpr size_t FLUSH_BYTES = 256ull << 20;
+
+static int cuda_fail(t5_ctx* c, cudaError_t e, const char* where) {
+    if (c) c->last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? T5_ERR_OOM : T5_ERR_CUDA;
+}
+#define CU(c, call)                                                     \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return cuda_fail((c), e__, #call);      \
+    } while (0)
+
+static int map_internal(t5_ctx* c, int r, const char* what) {
+    switch (r) {
+        case T5I_OK: return T5_OK;
+        case T5I_CUDA: {
+            cudaError_t e = cudaGetLastError();
+            c->last_error = std::string(what) + ": launch failed: " + cudaGetErrorString(e);
+            return T5_ERR_CUDA;
+        }
+        default: return T5_ERR_UNSUPPORTED;
+    }
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* t5_strerror(int code) {
+    switch (code) {
+        case T5_OK: return "ok";
+        case T5_ERR_SHAPE: return "shape or length mismatch (WrongListLength)";
+        case T5_ERR_UNSUPPORTED: return "no device kernel for this dtype/shape/layout (there is no CPU fallback)";
+        case T5_ERR_CUDA: return "CUDA error";
+        case T5_ERR_NCCL: return "NCCL error";
+        case T5_ERR_OOM: return "out of device memory";
+        case T5_ERR_INVALID: return "invalid argument";
+    }
+    return "unknown error code";
+}
+
+const char* t5_version(void) { return "t5b200 sm_100a r1"; }
+
+const char* t5_last_error(t5_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int t5_partition(size_t batch, int ndev, int g, size_t* first, size_t* count) {
+    if (ndev < 1 || g < 0 || g >= ndev || !first || !count) return T5_ERR_INVALID;
+    size_t per = (batch + (size_t)ndev - 1) / (size_t)ndev;
+    per = (per + 255) / 256 * 256;
+    size_t f = per * (size_t)g;
+    if (f > batch) f = batch;
+    size_t l = per * (size_t)(g + 1);
+    if (l > batch) l = batch;
+    *first = f;
+    *count = l - f;
+    return T5_OK;
+}
+
+int t5_init(const int* devices, int ndev, t5_ctx** out) {
+    if (!out) return T5_ERR_INVALID;
+    *out = nullptr;
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible < 1) return T5_ERR_CUDA;
+    std::vector<int> devs;
+    if (!devices || ndev <= 0) {
+        for (int i = 0; i < visible; ++i) devs.push_back(i);
+    } else {
+        for (int i = 0; i < ndev; ++i) {
+            if (devices[i] < 0 || devices[i] >= visible) return T5_ERR_INVALID;
+            devs.push_back(devices[i]);
+        }
+    }
+    if ((int)devs.size() > T5_MAX_DEVICES) return T5_ERR_INVALID;
+    t5_ctx* c = new (std::nothrow) t5_ctx();
+    if (!c) return T5_ERR_OOM;
+    c->ndev = (int)devs.size();
+    for (int g = 0; g < c->ndev; ++g) {
+        c->dev[g] = devs[g];
+        c->stream[g] = nullptr; c->ev0[g] = c->ev1[g] = nullptr; c->scratch[g] = c->flush[g] = nullptr;
+    }
+    for (int g = 0; g < c->ndev; ++g) {
+        if ((e = cudaSetDevice(c->dev[g])) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&c->stream[g], cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&c->ev0[g])) != cudaSuccess || (e = cudaEventCreate(&c->ev1[g])) != cudaSuccess ||
+            (e = cudaMalloc(&c->scratch[g], SCRATCH_BYTES)) != cudaSuccess) {
+            int rc = cuda_fail(nullptr, e, "t5_init");
+            t5_shutdown(c);
+            return rc;
+        }
+    }
+    *out = c;
+    return T5_OK;
+}
+
+int t5_shutdown(t5_ctx* c) {
+    if (!c) return T5_ERR_INVALID;
+    for (int g = 0; g < c->ndev; ++g) {
+        cudaSetDevice(c->dev[g]);
+        if (c->stream[g]) cudaStreamSynchronize(c->stream[g]);
+        for (auto& s : c->slots[g]) {
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            for (auto p : s.d) if (p) cudaFree(p);
+        }
+        if (c->nccl_ready && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comms[g]);
+        if (c->scratch[g]) cudaFree(c->scratch[g]);
+        if (c->flush[g]) cudaFree(c->flush[g]);
+        if (c->ev0[g]) cudaEventDestroy(c->ev0[g]);
+        if (c->ev1[g]) cudaEventDestroy(c->ev1[g]);
+        if (c->stream[g]) cudaStreamDestroy(c->stream[g]);
+    }
+    for (auto& kv : c->perm_cache)
+        for (int g = 0; g < c->ndev; ++g)
+            if (kv.second[g]) { cudaSetDevice(c->dev[g]); cudaFree(kv.second[g]); }
+    delete c;
+    return T5_OK;
+}
+
+int t5_ndev(t5_ctx* c) { return c ? c->ndev : 0; }
+
+int t5_sync(t5_ctx* c) {
+    if (!c) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        CU(c, cudaStreamSynchronize(c->stream[g]));
+    }
+    return T5_OK;
+}
+
+uint64_t t5_launch_count(t5_ctx* c) { return c ? c->launches.load() : 0; }
+
+// ---- buffers --------------------------------------------------------------------------
+int t5_alloc(t5_ctx* c, int dtype, size_t elems, size_t batch, int layout, t5_buf** out) {
+    if (!c || !out) return T5_ERR_INVALID;
+    *out = nullptr;
+    const int es = dtype_size(dtype);
+    if (es == 0 || (layout != T5_AOS && layout != T5_SOA)) return T5_ERR_INVALID;
+    if (elems == 0) return T5_ERR_SHAPE;
+    t5_buf* b = new (std::nothrow) t5_buf();
+    if (!b) return T5_ERR_OOM;
+    b->ctx = c; b->dtype = dtype; b->layout = layout; b->elems = elems; b->batch = batch;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) { b->ptr[g] = nullptr; b->first[g] = b->count[g] = b->cap[g] = b->bytes[g] = 0; }
+    for (int g = 0; g < c->ndev; ++g) {
+        t5_partition(batch, c->ndev, g, &b->first[g], &b->count[g]);
+        b->cap[g] = (b->count[g] + 31) / 32 * 32;
+        size_t items = layout == T5_SOA ? b->cap[g] : b->count[g];
+        size_t bytes = (items * elems * (size_t)es + 255) / 256 * 256;
+        if (bytes == 0) bytes = 256;
+        b->bytes[g] = bytes;
+        cudaError_t e = cudaSetDevice(c->dev[g]);
+        if (e == cudaSuccess) e = cudaMalloc(&b->ptr[g], bytes);
+        if (e == cudaSuccess && layout == T5_SOA) e = cudaMemsetAsync(b->ptr[g], 0, bytes, c->stream[g]);
+        if (e != cudaSuccess) {
+            int rc = cuda_fail(c, e, "t5_alloc");
+            for (int h = 0; h <= g; ++h)
+                if (b->ptr[h]) { cudaSetDevice(c->dev[h]); cudaFree(b->ptr[h]); }
+            delete b;
+            return rc;
+        }
+    }
+    c->live_bufs++;
+    *out = b;
+    return T5_OK;
+}
+
+int t5_free(t5_buf* b) {
+    if (!b) return T5_ERR_INVALID;
+    t5_ctx* c = b->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!b->ptr[g]) continue;
+        // work reading/writing the buffer may still be in flight: stream-ordered release
+        cudaSetDevice(c->dev[g]);
+        cudaStreamSynchronize(c->stream[g]);
+        cudaFree(b->ptr[g]);
+    }
+    c->live_bufs--;
+    delete b;
+    return T5_OK;
+}
+
+size_t t5_buf_batch(const t5_buf* b) { return b ? b->batch : 0; }
+size_t t5_buf_elems(const t5_buf* b) { return b ? b->elems : 0; }
+int t5_buf_dtype(const t5_buf* b) { return b ? b->dtype : -1; }
+int t5_buf_layout(const t5_buf* b) { return b ? b->layout : -1; }
+
+void* t5_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+void t5_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int xfer(t5_buf* b, void* host, size_t bytes, bool up) {
+    if (!b) return T5_ERR_INVALID;
+    t5_ctx* c = b->ctx;
+    const size_t es = dtype_size(b->dtype);
+    const size_t item = b->elems * es;
+    if (bytes != b->batch * item) return T5_ERR_SHAPE;
+    if (b->batch && !host) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::vector<void*> tmp(c->ndev, nullptr);
+    int rc = T5_OK;
+    for (int g = 0; g < c->ndev && rc == T5_OK; ++g) {
+        if (!b->count[g]) continue;
+        cudaError_t e = cudaSetDevice(c->dev[g]);
+        char* h = (char*)host + b->first[g] * item;
+        const size_t n = b->count[g] * item;
+        if (e == cudaSuccess && b->layout == T5_AOS) {
+            e = up ? cudaMemcpyAsync(b->ptr[g], h, n, cudaMemcpyHostToDevice, c->stream[g])
+                   : cudaMemcpyAsync(h, b->ptr[g], n, cudaMemcpyDeviceToHost, c->stream[g]);
+        } else if (e == cudaSuccess) {
+            e = cudaMalloc(&tmp[g], n);
+            if (e == cudaSuccess && up) {
+                e = cudaMemcpyAsync(tmp[g], h, n, cudaMemcpyHostToDevice, c->stream[g]);
+                if (e == cudaSuccess && relayout(c->stream[g], (int)es, b->elems, b->count[g], b->cap[g], true, tmp[g], b->ptr[g]) != T5I_OK) e = cudaGetLastError();
+                c->launches++;
+            } else if (e == cudaSuccess) {
+                if (relayout(c->stream[g], (int)es, b->elems, b->count[g], b->cap[g], false, b->ptr[g], tmp[g]) != T5I_OK) e = cudaGetLastError();
+                c->launches++;
+                if (e == cudaSuccess) e = cudaMemcpyAsync(h, tmp[g], n, cudaMemcpyDeviceToHost, c->stream[g]);
+            }
+        }
+        if (e != cudaSuccess) rc = cuda_fail(c, e, up ? "t5_upload" : "t5_download");
+    }
+    for (int g = 0; g < c->ndev; ++g) {
+        cudaSetDevice(c->dev[g]);
+        cudaError_t e = cudaStreamSynchronize(c->stream[g]);
+        if (e != cudaSuccess && rc == T5_OK) rc = cuda_fail(c, e, "sync after transfer");
+        if (tmp[g]) cudaFree(tmp[g]);
+    }
+    return rc;
+}
+
+int t5_upload(t5_buf* b, const void* host, size_t bytes) { return xfer(b, const_cast<void*>(host), bytes, true); }
+int t5_download(t5_buf* b, void* host, size_t bytes) { return xfer(b, host, bytes, false); }
+
+int t5_relayout(t5_buf* dst, const t5_buf* src) {
+    if (!dst || !src || dst->ctx != src->ctx || dst == src) return T5_ERR_INVALID;
+    if (dst->dtype != src->dtype || dst->elems != src->elems || dst->batch != src->batch) return T5_ERR_SHAPE;
+    t5_ctx* c = dst->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const int es = dtype_size(dst->dtype);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!dst->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        if (dst->layout == src->layout) {
+            CU(c, cudaMemcpyAsync(dst->ptr[g], src->ptr[g], src->bytes[g], cudaMemcpyDeviceToDevice, c->stream[g]));
+        } else {
+            const bool to_soa = dst->layout == T5_SOA;
+            int r = relayout(c->stream[g], es, dst->elems, dst->count[g], to_soa ? dst->cap[g] : src->cap[g], to_soa, src->ptr[g], dst->ptr[g]);
+            c->launches++;
+            if (r != T5I_OK) return map_internal(c, r, "t5_relayout");
+        }
+    }
+    return T5_OK;
+}
+
+// ---- operand validation ------------------------------------------------------------------
+static int check(const t5_ctx* c, const t5_buf* b, int dtype, size_t elems, const t5_buf* like) {
+    if (!b || b->ctx != c) return T5_ERR_INVALID;
+    if (b->dtype != dtype) return T5_ERR_INVALID;
+    if (b->elems != elems) return T5_ERR_SHAPE;
+    if (like && (b->batch != like->batch)) return T5_ERR_SHAPE;
+    if (like && (b->layout != like->layout)) return T5_ERR_INVALID;
+    return T5_OK;
+}
+#define CHECK(expr) do { int rc__ = (expr); if (rc__ != T5_OK) return rc__; } while (0)
+
+static Shard shard_of(const t5_ctx* c, const t5_buf* b, int g) {
+    Shard s;
+    s.stream = c->stream[g]; s.layout = b->layout; s.count = b->count[g]; s.soa_stride = b->cap[g]; s.first = b->first[g];
+    return s;
+}
+
+// one shard of a (P x K).(K x Q) product; shared by t5_matmul / t5_dot / t5_prod and
+// the host-buffer pipeline
+static int product_shard(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
+    int r = T5I_NOT_SPECIALISED;
+    if (nc != 0) r = small_matmul(s, dtype, P, K, Q, A, B, C);
+    if (r == T5I_NOT_SPECIALISED && s.layout == T5L_AOS && dtype == T5D_F64 && nc != 0) r = dmma_matmul(s, P, K, Q, A, B, C);
+    if (r == T5I_NOT_SPECIALISED) r = generic_prod(s, dtype, P, K, Q, nc, A, B, C);
+    return r;
+}
+
+static int product_all(t5_ctx* c, int dtype, int P, int K, int Q, int nc, const t5_buf* A, const t5_buf* B, t5_buf* C, const char* what) {
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (P < 1 || K < 1 || Q < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)P * K, nullptr));
+    CHECK(check(c, B, dtype, (size_t)K * Q, A));
+    CHECK(check(c, C, dtype, (size_t)P * Q, A));
+    if (C == A || C == B) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        int r = product_shard(shard_of(c, A, g), dtype, P, K, Q, nc, A->ptr[g], B->ptr[g], C->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, what);
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_matmul(t5_ctx* c, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C) {
+    if (!c) return T5_ERR_INVALID;
+    return product_all(c, dtype, m, k, n, 1, A, B, C, "t5_matmul");
+}
+
+int t5_dot(t5_ctx* c, int dtype, int n, const t5_buf* X, const t5_buf* Y, t5_buf* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    return product_all(c, dtype, 1, n, 1, 1, X, Y, OUT, "t5_dot");
+}
+
+int t5_prod(t5_ctx* c, int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc,
+            const t5_buf* A, const t5_buf* B, t5_buf* C) {
+    if (!c || rankA < 0 || rankB < 0 || rankA > 16 || rankB > 16 || (rankA && !dimsA) || (rankB && !dimsB)) return T5_ERR_INVALID;
+    if (nc < 0 || nc > rankA || nc > rankB) return T5_ERR_SHAPE;
+    uint64_t P = 1, K = 1, Q = 1;
+    for (int a = 0; a < rankA - nc; ++a) P *= dimsA[a];
+    for (int a = 0; a < nc; ++a) {
+        if (dimsA[rankA - nc + a] != dimsB[a]) return T5_ERR_SHAPE;
+        K *= dimsB[a];
+    }
+    for (int a = nc; a < rankB; ++a) Q *= dimsB[a];
+    if (P == 0 || K == 0 || Q == 0 || P > (1u << 28) || K > (1u << 28) || Q > (1u << 28)) return T5_ERR_SHAPE;
+    return product_all(c, dtype, (int)P, (int)K, (int)Q, nc, A, B, C, "t5_prod");
+}
+
+// ---- dot_sum: the one entry with a cross-device exchange ---------------------------------
+static bool ensure_nccl(t5_ctx* c) {
+    if (c->nccl_ready) return true;
+    if (c->nccl_failed) return false;
+    if (!c->nccl.load() || c->nccl.CommInitAll(c->comms, c->ndev, c->dev) != ncclSuccess) {
+        c->nccl_failed = true;
+        return false;
+    }
+    c->nccl_ready = true;
+    return true;
+}
+
+int t5_dot_sum_used_nccl(t5_ctx* c) { return c && c->used_nccl ? 1 : 0; }
+
+int t5_dot_sum(t5_ctx* c, int dtype, int n, const t5_buf* X, const t5_buf* Y, void* host_scalar) {
+    if (!c || !host_scalar) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, X, dtype, (size_t)n, nullptr));
+    CHECK(check(c, Y, dtype, (size_t)n, X));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t part_off = SCRATCH_BYTES - 64;
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, X, g);
+        const size_t elems = (X->layout == T5_SOA ? X->cap[g] : X->count[g]) * (size_t)n;
+        int r = dot_sum_partial(s, dtype, elems, X->ptr[g], Y->ptr[g], c->scratch[g], (char*)c->scratch[g] + part_off);
+        if (r != T5I_OK) return map_internal(c, r, "t5_dot_sum");
+        c->launches += 2;
+    }
+    c->used_nccl = false;
+    double dsum = 0.0;
+    uint64_t isum = 0;
+    if (c->ndev > 1 && ensure_nccl(c)) {
+        // 1-element all-reduce over NVLink; every device ends with the total, device 0's copy is returned
+        ncclDataType_t ty = dtype == T5_I64 ? ncclUint64 : ncclFloat64;
+        if (c->nccl.GroupStart() != ncclSuccess) return T5_ERR_NCCL;
+        for (int g = 0; g < c->ndev; ++g) {
+            void* p = (char*)c->scratch[g] + part_off;
+            ncclResult_t nr = c->nccl.AllReduce(p, p, 1, ty, ncclSum, c->comms[g], c->stream[g]);
+            if (nr != ncclSuccess) {
+                c->last_error = std::string("ncclAllReduce: ") + (c->nccl.GetErrorString ? c->nccl.GetErrorString(nr) : "?");
+                c->nccl.GroupEnd();
+                return T5_ERR_NCCL;
+            }
+        }
+        if (c->nccl.GroupEnd() != ncclSuccess) return T5_ERR_NCCL;
+        for (int g = 0; g < c->ndev; ++g) {
+            CU(c, cudaSetDevice(c->dev[g]));
+            CU(c, cudaStreamSynchronize(c->stream[g]));
+        }
+        CU(c, cudaSetDevice(c->dev[0]));
+        if (dtype == T5_I64) CU(c, cudaMemcpy(&isum, (char*)c->scratch[0] + part_off, 8, cudaMemcpyDeviceToHost));
+        else CU(c, cudaMemcpy(&dsum, (char*)c->scratch[0] + part_off, 8, cudaMemcpyDeviceToHost));
+        c->used_nccl = true;
+    } else {
+        // single device, or NCCL not loadable: partials added on the host in device order
+        for (int g = 0; g < c->ndev; ++g) {
+            CU(c, cudaSetDevice(c->dev[g]));
+            CU(c, cudaStreamSynchronize(c->stream[g]));
+            if (dtype == T5_I64) { uint64_t v; CU(c, cudaMemcpy(&v, (char*)c->scratch[g] + part_off, 8, cudaMemcpyDeviceToHost)); isum += v; }
+            else { double v; CU(c, cudaMemcpy(&v, (char*)c->scratch[g] + part_off, 8, cudaMemcpyDeviceToHost)); dsum += v; }
+        }
+    }
+    if (dtype == T5_F64) *(double*)host_scalar = dsum;
+    else if (dtype == T5_F32) *(float*)host_scalar = (float)dsum;
+    else *(int64_t*)host_scalar = (int64_t)isum;
+    return T5_OK;
+}
+
+// ---- transpose -----------------------------------------------------------------------------
+// transposeV ds = linearize ds . reverse . unlinearize (reverse ds)   (Vector.hs:306-307),
+// written with 0-based indices: out linear index i over the REVERSED shape maps to the
+// input offset of the reversed multi-index.
+static void build_perm(const std::vector<uint64_t>& dims, std::vector<uint32_t>& perm) {
+    const int r = (int)dims.size();
+    size_t d = 1;
+    for (auto x : dims) d *= x;
+    perm.resize(d);
+    std::vector<uint64_t> in_stride(r, 1);
+    for (int a = r - 2; a >= 0; --a) in_stride[a] = in_stride[a + 1] * dims[a + 1];
+    for (size_t i = 0; i < d; ++i) {
+        // unlinearize i over reversed dims (dims[r-1], ..., dims[0]); last (fastest) out axis is in-axis 0
+        size_t rem = i, off = 0;
+        for (int a = 0; a < r; ++a) {           // a = input axis, which is output axis r-1-a (fastest first)
+            size_t idx = rem % dims[a];
+            rem /= dims[a];
+            off += idx * in_stride[a];
+        }
+        perm[i] = (uint32_t)off;
+    }
+}
+
+int t5_transpose(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const t5_buf* A, t5_buf* OUT) {
+    if (!c || rank < 0 || rank > 16 || (rank && !dims)) return T5_ERR_INVALID;
+    const int es = dtype_size(dtype);
+    if (es != 4 && es != 8) return T5_ERR_UNSUPPORTED;
+    std::vector<uint64_t> dv(dims, dims + rank);
+    size_t d = 1;
+    for (auto x : dv) { if (x == 0 || x > (1u << 28)) return T5_ERR_SHAPE; d *= x; if (d > (1u << 28)) return T5_ERR_SHAPE; }
+    CHECK(check(c, A, dtype, d, nullptr));
+    CHECK(check(c, OUT, dtype, d, A));
+    if (OUT == A) return T5_ERR_INVALID;
+    // squeeze axes of extent 1: they do not move data
+    std::vector<uint64_t> sq;
+    for (auto x : dv) if (x != 1) sq.push_back(x);
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        if (sq.size() <= 1) {  // rank 0/1 (after squeezing): the identity
+            CU(c, cudaMemcpyAsync(OUT->ptr[g], A->ptr[g], A->bytes[g], cudaMemcpyDeviceToDevice, c->stream[g]));
+            continue;
+        }
+        int r = T5I_NOT_SPECIALISED;
+        if (sq.size() == 2) r = small_transpose(s, es, (int)sq[0], (int)sq[1], A->ptr[g], OUT->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) {
+            if (A->layout != T5_AOS) return T5_ERR_UNSUPPORTED;
+            auto it = c->perm_cache.find(sq);
+            if (it == c->perm_cache.end()) it = c->perm_cache.emplace(sq, std::vector<uint32_t*>(T5_MAX_DEVICES, nullptr)).first;
+            if (!it->second[g]) {
+                std::vector<uint32_t> perm;
+                build_perm(sq, perm);
+                uint32_t* p = nullptr;
+                CU(c, cudaMalloc(&p, perm.size() * 4));
+                CU(c, cudaMemcpy(p, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+                it->second[g] = p;
+            }
+            r = generic_permute(s, es, d, it->second[g], A->ptr[g], OUT->ptr[g]);
+        }
+        if (r != T5I_OK) return map_internal(c, r, "t5_transpose");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+// ---- det / inverse / solve -----------------------------------------------------------------
+int t5_det(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, OUT, dtype, 1, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        int r = small_det(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_det(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_det");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_inverse(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* STATUS) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, OUT, dtype, (size_t)n * n, A));
+    CHECK(check(c, STATUS, T5_U8, 1, A));
+    if (OUT == A) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        int r = small_inverse(s, dtype, n, A->ptr[g], OUT->ptr[g], STATUS->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_solve(s, dtype, n, n, true, A->ptr[g], nullptr, OUT->ptr[g], STATUS->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_inverse");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_solve(t5_ctx* c, int dtype, int n, int nrhs, const t5_buf* A, const t5_buf* B, t5_buf* X, t5_buf* STATUS) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1 || nrhs < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, B, dtype, (size_t)n * nrhs, A));
+    CHECK(check(c, X, dtype, (size_t)n * nrhs, A));
+    CHECK(check(c, STATUS, T5_U8, 1, A));
+    if (X == A || X == B) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        int r = small_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_solve(s, dtype, n, nrhs, false, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_solve");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+// ---- element-wise --------------------------------------------------------------------------
+int t5_zip(t5_ctx* c, int dtype, int op, const t5_buf* A, const t5_buf* B, t5_buf* C) {
+    if (!c || !A) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (op < 0 || op > 2) return T5_ERR_INVALID;
+    CHECK(check(c, A, dtype, A->elems, nullptr));
+    CHECK(check(c, B, dtype, A->elems, A));
+    CHECK(check(c, C, dtype, A->elems, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        const size_t elems = (A->layout == T5_SOA ? A->cap[g] : A->count[g]) * A->elems;
+        int r = generic_zip(shard_of(c, A, g), dtype, op, elems, A->ptr[g], B->ptr[g], C->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_zip");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_scale(t5_ctx* c, int dtype, const void* scalar, const t5_buf* A, t5_buf* C) {
+    if (!c || !A || !scalar) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    CHECK(check(c, A, dtype, A->elems, nullptr));
+    CHECK(check(c, C, dtype, A->elems, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        const size_t elems = (A->layout == T5_SOA ? A->cap[g] : A->count[g]) * A->elems;
+        int r = generic_scale(shard_of(c, A, g), dtype, scalar, elems, A->ptr[g], C->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_scale");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+// ---- host-buffer pipeline --------------------------------------------------------------------
+// The batch is cut into chunks; chunk j of device g runs on slot j % 3 (own stream, own
+// staging buffers): H2D(A), H2D(B), kernel, D2H(C).  With three slots the two PCIe
+// directions and the SMs work on different chunks at the same time.
+static int slot_reserve(t5_ctx* c, HostSlot& s, int i, size_t bytes) {
+    if (!s.stream) CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (s.cap[i] >= bytes) return T5_OK;
+    if (s.d[i]) { CU(c, cudaStreamSynchronize(s.stream)); CU(c, cudaFree(s.d[i])); s.d[i] = nullptr; s.cap[i] = 0; }
+    CU(c, cudaMalloc(&s.d[i], bytes));
+    s.cap[i] = bytes;
+    return T5_OK;
+}
+
+int t5_matmul_host(t5_ctx* c, int dtype, int m, int k, int n, size_t batch, const void* A, const void* B, void* C) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (m < 1 || k < 1 || n < 1) return T5_ERR_SHAPE;
+    if (batch && (!A || !B || !C)) return T5_ERR_INVALID;
+    const size_t es = dtype_size(dtype);
+    const size_t ia = (size_t)m * k * es, ib = (size_t)k * n * es, ic = (size_t)m * n * es;
+    // ~32 MiB of operands per chunk, a multiple of 256 items
+    size_t chunk = (32ull << 20) / (ia + ib + ic);
+    chunk = chunk < 256 ? 256 : chunk / 256 * 256;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        size_t first, count;
+        t5_partition(batch, c->ndev, g, &first, &count);
+        if (!count) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        size_t j = 0;
+        for (size_t off = 0; off < count; off += chunk, ++j) {
+            const size_t cnt = count - off < chunk ? count - off : chunk;
+            HostSlot& s = c->slots[g][j % 3];
+            CHECK(slot_reserve(c, s, 0, chunk * ia));
+            CHECK(slot_reserve(c, s, 1, chunk * ib));
+            CHECK(slot_reserve(c, s, 2, chunk * ic));
+            const size_t it = first + off;
+            CU(c, cudaMemcpyAsync(s.d[0], (const char*)A + it * ia, cnt * ia, cudaMemcpyHostToDevice, s.stream));
+            CU(c, cudaMemcpyAsync(s.d[1], (const char*)B + it * ib, cnt * ib, cudaMemcpyHostToDevice, s.stream));
+            Shard sh; sh.stream = s.stream; sh.layout = T5L_AOS; sh.count = cnt; sh.soa_stride = 0; sh.first = it;
+            int r = product_shard(sh, dtype, m, k, n, 1, s.d[0], s.d[1], s.d[2]);
+            if (r != T5I_OK) return map_internal(c, r, "t5_matmul_host");
+            c->launches++;
+            CU(c, cudaMemcpyAsync((char*)C + it * ic, s.d[2], cnt * ic, cudaMemcpyDeviceToHost, s.stream));
+        }
+    }
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        for (auto& s : c->slots[g]) if (s.stream) CU(c, cudaStreamSynchronize(s.stream));
+    }
+    return T5_OK;
+}
+
+// ---- measurement helpers -----------------------------------------------------------------------
+int t5_timer_begin(t5_ctx* c) {
+    if (!c) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        CU(c, cudaEventRecord(c->ev0[g], c->stream[g]));
+    }
+    return T5_OK;
+}
+
+int t5_timer_end(t5_ctx* c, float* ms_max) {
+    if (!c || !ms_max) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        CU(c, cudaEventRecord(c->ev1[g], c->stream[g]));
+    }
+    float mx = 0.f;
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        CU(c, cudaEventSynchronize(c->ev1[g]));
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->ev0[g], c->ev1[g]));
+        if (ms > mx) mx = ms;
+    }
+    *ms_max = mx;
+    return T5_OK;
+}
+
+int t5_flush_l2(t5_ctx* c) {
+    if (!c) return T5_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        if (!c->flush[g]) CU(c, cudaMalloc(&c->flush[g], FLUSH_BYTES));
+        CU(c, cudaMemsetAsync(c->flush[g], 0x5a, FLUSH_BYTES, c->stream[g]));
+    }
+    return T5_OK;
+}
+
+int t5_fill_synthetic(t5_buf* b, uint64_t seed, uint64_t op_id) {
+    if (!b) return T5_ERR_INVALID;
+    t5_ctx* c = b->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!b->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        int r = fill_synthetic(shard_of(c, b, g), b->dtype, b->elems, seed, op_id, b->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_fill_synthetic");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_plant_specials(t5_buf* b, int n, uint64_t swap_every, uint64_t sing_every) {
+    if (!b) return T5_ERR_INVALID;
+    if (n < 1 || b->elems != (size_t)n * n) return T5_ERR_SHAPE;
+    t5_ctx* c = b->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!b->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        int r = plant_specials(shard_of(c, b, g), b->dtype, n, swap_every, sing_every, b->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_plant_specials");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,62 @@
+// Internal interface between the C-ABI host layer (t5_host.cu) and the kernel
+// translation units.  Not installed; the public boundary is include/t5b200.h.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define T5_MAX_DEVICES 16
+
+namespace t5 {
+
+enum { T5D_F64 = 0, T5D_F32 = 1, T5D_I64 = 2, T5D_U8 = 3 };
+enum { T5L_AOS = 0, T5L_SOA = 1 };
+// internal launcher results
+enum { T5I_OK = 0, T5I_NOT_SPECIALISED = -1, T5I_CUDA = -2, T5I_UNSUPPORTED = -3 };
+
+inline int dtype_size(int dtype) {
+    switch (dtype) {
+        case T5D_F64: case T5D_I64: return 8;
+        case T5D_F32: return 4;
+        case T5D_U8: return 1;
+    }
+    return 0;
+}
+
+// One device's slice of a batched call.
+struct Shard {
+    cudaStream_t stream;
+    int layout;         // T5L_AOS / T5L_SOA
+    size_t count;       // items in this shard
+    size_t soa_stride;  // SoA element stride (shard capacity, items)
+    size_t first;       // global index of the shard's first item
+};
+
+// ---- t5_small_ops.cu: register-resident thread-per-item kernels -----------------
+int small_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
+int small_transpose(const Shard& s, int elem_bytes, int r, int c, const void* A, void* O);
+int small_det(const Shard& s, int dtype, int n, const void* A, void* O);
+int small_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
+int small_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
+
+// ---- t5_generic.cu: any-shape kernels (AoS only) ---------------------------------
+// C[P x Q] = A[P x K] . B[K x Q] per item; ncontract == 0 -> single multiply.
+int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int ncontract, const void* A, const void* B, void* C);
+// out[b][i] = in[b][perm[i]], perm resident on the device (d entries)
+int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O);
+int generic_det(const Shard& s, int dtype, int n, const void* A, void* O);
+int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs, const void* A, const void* B, void* X, void* status);
+int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, const void* B, void* C);
+int generic_scale(const Shard& s, int dtype, const void* scalar_host, size_t elems, const void* A, void* C);
+// per-device partial of sum_b dot(x_b, y_b): *partial_dev is double (F64/F32) or int64
+int dot_sum_partial(const Shard& s, int dtype, size_t elems, const void* X, const void* Y, void* scratch_dev, void* partial_dev);
+int fill_synthetic(const Shard& s, int dtype, size_t elems_per_item, uint64_t seed, uint64_t op_id, void* dst);
+int plant_specials(const Shard& s, int dtype, int n, uint64_t swap_every, uint64_t sing_every, void* A);
+// AoS [count][d] <-> SoA [d][stride]
+int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst);
+
+// ---- t5_dgemm.cu: FP64 tensor-core (DMMA) batched product for large squares -------
+// returns T5I_NOT_SPECIALISED unless (m,k,n) is a supported multiple-of-tile shape
+int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
+
+}  // namespace t5

@@ -1,0 +1,88 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol that
+include/t5b200.h declares, its pure host functions behave, and without a GPU it
+fails with an error code (never a silent fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import tensor_b200 as tb
+from tensor_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "t5b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(t5_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 35
+    L = ctypes.CDLL(_lib.SO_PATH)
+    for n in names:
+        assert hasattr(L, n), f"libt5b200.so does not export {n}"
+    # and the binding table covers the header exactly
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_strerror():
+    L = _lib.lib()
+    assert b"sm_100a" in L.t5_version()
+    assert L.t5_strerror(0) == b"ok"
+    assert b"WrongListLength" in L.t5_strerror(_lib.ERR_SHAPE)
+    assert b"no CPU fallback" in L.t5_strerror(_lib.ERR_UNSUPPORTED)
+
+
+@pytest.mark.parametrize("batch", [0, 1, 255, 256, 257, 1000, 1 << 20, (1 << 24) + 3])
+@pytest.mark.parametrize("ndev", [1, 2, 3, 4, 8])
+def test_partition_covers_batch_contiguously(batch, ndev):
+    nxt = 0
+    for g in range(ndev):
+        first, count = tb.partition(batch, ndev, g)
+        assert first == min(nxt, batch)
+        nxt = first + count
+        if count and g < ndev - 1 and first + count < batch:
+            assert count % 256 == 0          # shard boundaries fall on tile multiples
+    assert nxt == batch
+    sizes = [tb.partition(batch, ndev, g)[1] for g in range(ndev)]
+    assert max(sizes) - min(s for s in sizes) <= max(sizes)  # contiguous, front-loaded
+    assert max(sizes) <= (batch + ndev - 1) // ndev + 255
+
+
+def test_partition_rejects_bad_arguments():
+    with pytest.raises(ValueError):
+        tb.partition(10, 0, 0)
+    with pytest.raises(ValueError):
+        tb.partition(10, 2, 2)
+
+
+def test_null_handles_are_errors_not_crashes():
+    L = _lib.lib()
+    assert L.t5_shutdown(None) == _lib.ERR_INVALID
+    assert L.t5_sync(None) == _lib.ERR_INVALID
+    assert L.t5_free(None) == _lib.ERR_INVALID
+    assert L.t5_matmul(None, 0, 3, 3, 3, None, None, None) == _lib.ERR_INVALID
+    assert L.t5_ndev(None) == 0
+
+
+def test_no_gpu_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(tb.DeviceError):
+        tb.Context([0])
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "tensor_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    s = f.read()
+                assert "import oracle" not in s and "from oracle" not in s and "t5oracle" not in s, fn

@@ -1,0 +1,377 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes) into the CUDA kernels and
+is compared with the CPU oracle on the same seeded inputs.  Integer work and every
+thread-per-item floating-point kernel are compared BIT-EXACTLY (the kernels keep the
+oracle's operation order and never fuse multiply-add); the DMMA 128x128 product uses
+the stated tolerance (1e-12 relative to sum |a||b|)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import tensor_b200 as tb
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NPD = {oracle.F64: np.float64, oracle.F32: np.float32, oracle.I64: np.int64}
+ALL = [oracle.F64, oracle.F32, oracle.I64]
+FRAC = [oracle.F64, oracle.F32]
+RAGGED = [0, 1, 31, 127, 128, 129, 255, 257, 1000, 4099]
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({8: np.uint64, 4: np.uint32, 1: np.uint8}[a.dtype.itemsize])
+
+
+def assert_bits_equal(got, want, what=""):
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    if not np.array_equal(bits(got), bits(want)):
+        bad = np.argwhere(bits(got).ravel() != bits(want).ravel()).ravel()
+        raise AssertionError(f"{what}: {bad.size} mismatching elements, first at {bad[:5]}: "
+                             f"got {got.ravel()[bad[:5]]} want {want.ravel()[bad[:5]]}")
+
+
+def inputs(dc, op_id, batch, da, db=None):
+    a = oracle.fill(dc, oracle.SEED_A, op_id, batch * da)
+    b = oracle.fill(dc, oracle.SEED_B, op_id, batch * db) if db else None
+    return a, b
+
+
+# ---- matmul (.*.) ----------------------------------------------------------------
+@pytest.mark.parametrize("dc", ALL)
+@pytest.mark.parametrize("mkn", [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (2, 5, 3), (7, 2, 6), (1, 9, 1), (8, 8, 8)])
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_matmul_bit_exact(ctx, dc, mkn, layout):
+    m, k, n = mkn
+    specialised = mkn in [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4)]
+    for batch in (1, 257, 4099):
+        a, b = inputs(dc, 1, batch, m * k, k * n)
+        A = ctx.from_numpy(a, (m, k), layout)
+        B = ctx.from_numpy(b, (k, n), layout)
+        if layout == tb.SOA and not specialised:
+            with pytest.raises(tb.Unsupported):
+                tb.matmul(A, B)
+            return
+        C = tb.matmul(A, B)
+        assert C.shape == (m, n)
+        assert_bits_equal(C.to_numpy(), oracle.matmul(a, b, m, k, n), f"matmul {mkn} dt{dc} batch{batch}")
+
+
+@pytest.mark.parametrize("batch", RAGGED)
+def test_matmul_ragged_batches(ctx, batch):
+    for dc, (m, k, n) in ((oracle.F64, (3, 3, 3)), (oracle.F32, (4, 4, 4)), (oracle.I64, (3, 3, 3))):
+        a, b = inputs(dc, 2, batch, m * k, k * n)
+        C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n)))
+        assert_bits_equal(C.to_numpy(), oracle.matmul(a, b, m, k, n), f"ragged {batch}")
+
+
+def test_matmul_signed_zero_and_specials(ctx):
+    # 0 + (-0) = +0: the fold starts from +0 exactly like the oracle
+    a = np.array([[-0.0, 0.0, 0.0, 0.0, np.inf, 1.0, np.nan, 0.0, 1e308]] * 3, dtype=np.float64)
+    b = np.array([[1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 10.0]] * 3, dtype=np.float64)
+    C = tb.matmul(ctx.from_numpy(a, (3, 3)), ctx.from_numpy(b, (3, 3))).to_numpy()
+    assert_bits_equal(C, oracle.matmul(a, b, 3, 3, 3), "specials")
+
+
+def test_int64_wraparound(ctx):
+    a = np.array([2 ** 62, 2, 0, 1], dtype=np.int64)
+    b = np.array([4, 0, 0, 2 ** 63 - 1], dtype=np.int64)
+    C = tb.matmul(ctx.from_numpy(a, (2, 2)), ctx.from_numpy(b, (2, 2))).to_numpy()
+    assert C.ravel().tolist() == [0, -2, 0, 2 ** 63 - 1]
+
+
+# ---- dot / dot_sum ---------------------------------------------------------------
+@pytest.mark.parametrize("dc", ALL)
+@pytest.mark.parametrize("n", [2, 3, 4, 7])
+def test_dot_bit_exact(ctx, dc, n):
+    for batch in (1, 1000, 4099):
+        x, y = inputs(dc, 3, batch, n, n)
+        D = tb.dot(ctx.from_numpy(x, (n,)), ctx.from_numpy(y, (n,)))
+        assert D.shape == ()
+        assert_bits_equal(D.to_numpy(), oracle.dot(x, y, n), f"dot n={n}")
+
+
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_dot_sum(ctx, layout):
+    batch, n = 100003, 4
+    xi, yi = inputs(oracle.I64, 4, batch, n, n)
+    assert tb.dot_sum(ctx.from_numpy(xi, (n,), layout), ctx.from_numpy(yi, (n,), layout)) == oracle.dot_sum(xi, yi, n)
+    x, y = inputs(oracle.F64, 4, batch, n, n)
+    got = tb.dot_sum(ctx.from_numpy(x, (n,), layout), ctx.from_numpy(y, (n,), layout))
+    # tolerance: 1e-12 relative to sum |x||y|
+    assert abs(got - oracle.dot_sum(x, y, n)) <= 1e-12 * np.sum(np.abs(x) * np.abs(y))
+    xf, yf = inputs(oracle.F32, 4, batch, n, n)
+    gotf = tb.dot_sum(ctx.from_numpy(xf, (n,), layout), ctx.from_numpy(yf, (n,), layout))
+    assert abs(float(gotf) - float(oracle.dot_sum(xf, yf, n))) <= 1e-5 * np.sum(np.abs(xf) * np.abs(yf))
+
+
+# ---- prod n / tensor product -----------------------------------------------------
+@pytest.mark.parametrize("dc", ALL)
+def test_prod_and_tensor_product(ctx, dc):
+    batch = 300
+    a, b = inputs(dc, 5, batch, 64, 64)
+    A, B = ctx.from_numpy(a, (8, 8)), ctx.from_numpy(b, (8, 8))
+    T = tb.tensor_product(A, B)
+    assert T.shape == (8, 8, 8, 8)
+    assert_bits_equal(T.to_numpy(), oracle.prod(a, [8, 8], b, [8, 8], 0), "8x8 (x) 8x8")
+    assert_bits_equal(tb.prod(A, B, 1).to_numpy(), oracle.prod(a, [8, 8], b, [8, 8], 1), "prod 1")
+    assert_bits_equal(tb.prod(A, B, 2).to_numpy(), oracle.prod(a, [8, 8], b, [8, 8], 2), "prod 2")
+    a3, b3 = inputs(dc, 6, batch, 2 * 3 * 4, 4 * 5)
+    P = tb.prod(ctx.from_numpy(a3, (2, 3, 4)), ctx.from_numpy(b3, (4, 5)), 1)
+    assert P.shape == (2, 3, 5)
+    assert_bits_equal(P.to_numpy(), oracle.prod(a3, [2, 3, 4], b3, [4, 5], 1), "rank3.rank2")
+    # odd Q exercises the scalar (non-vectorised) path
+    a4, b4 = inputs(dc, 7, batch, 3, 5)
+    assert_bits_equal(tb.tensor_product(ctx.from_numpy(a4, (3,)), ctx.from_numpy(b4, (5,))).to_numpy(),
+                      oracle.prod(a4, [3], b4, [5], 0), "3 (x) 5")
+
+
+def test_prod_shape_mismatch_is_wrong_list_length(ctx):
+    A = ctx.empty((3, 4), np.float64, 4)
+    B = ctx.empty((5, 2), np.float64, 4)
+    with pytest.raises(tb.WrongListLength):
+        tb.prod(A, B, 1)
+    with pytest.raises(tb.WrongListLength):
+        tb.matmul(A, B)
+
+
+# ---- transpose ---------------------------------------------------------------------
+def test_transpose_golden(ctx):
+    with open(os.path.join(GOLD, "transpose_known.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        for dt in (np.int64, np.float64, np.float32):
+            a = np.asarray(c["in"], dtype=dt)
+            T = tb.transpose(ctx.from_numpy(a, c["dims"]))
+            assert list(T.shape) == list(reversed(c["dims"]))
+            assert T.to_numpy().ravel().tolist() == np.asarray(c["out"], dtype=dt).tolist(), c["source"]
+
+
+@pytest.mark.parametrize("dc", ALL)
+@pytest.mark.parametrize("dims", [(4, 4), (3, 3), (2, 3), (4, 1), (5,), (2, 3, 4), (8, 8), (3, 1, 2, 2), (16, 16)])
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_transpose_bit_exact_and_involution(ctx, dc, dims, layout):
+    d = int(np.prod(dims))
+    small = len([x for x in dims if x != 1]) <= 1 or (len(dims) == 2 and max(dims) <= 4)
+    for batch in (1, 513, 4099):
+        a, _ = inputs(dc, 8, batch, d)
+        A = ctx.from_numpy(a, dims, layout)
+        if layout == tb.SOA and not small:
+            with pytest.raises(tb.Unsupported):
+                tb.transpose(A)
+            return
+        T = tb.transpose(A)
+        assert_bits_equal(T.to_numpy(), oracle.transpose(a, dims), f"transpose {dims}")
+        assert_bits_equal(tb.transpose(T).to_numpy().reshape(batch, *dims), a.reshape(batch, *dims), "involution")
+
+
+def test_int64_product_transpose_identity(ctx):
+    batch, n = 5000, 4
+    a, b = inputs(oracle.I64, 9, batch, n * n, n * n)
+    A, B = ctx.from_numpy(a, (n, n)), ctx.from_numpy(b, (n, n))
+    lhs = tb.transpose(A @ B).to_numpy()
+    rhs = (tb.transpose(B) @ tb.transpose(A)).to_numpy()
+    assert np.array_equal(lhs, rhs)
+
+
+# ---- det / inverse / solve ---------------------------------------------------------
+def elim_inputs(dc, n, batch, nrhs=1):
+    a = oracle.fill(dc, oracle.SEED_A, 10, batch * n * n).reshape(batch, n, n).copy()
+    oracle.plant_specials(a, n, 0, swap_every=16, sing_every=128)
+    b = oracle.fill(dc, oracle.SEED_B, 10, batch * n * nrhs)
+    return a, b
+
+
+@pytest.mark.parametrize("dc", FRAC)
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_det_inverse_solve_bit_exact(ctx, dc, n, layout):
+    if layout == tb.SOA and n > 4:
+        A = ctx.empty((n, n), NPD[dc], 8, layout)
+        with pytest.raises(tb.Unsupported):
+            tb.det(A)
+        return
+    for batch in (1, 300, 4099):
+        a, b = elim_inputs(dc, n, batch)
+        A = ctx.from_numpy(a, (n, n), layout)
+        assert_bits_equal(tb.det(A).to_numpy(), oracle.det(a, n), f"det{n}")
+        inv, st = tb.inverse(A)
+        oinv, ost = oracle.inverse(a, n)
+        assert np.array_equal(st.to_numpy(), ost)
+        assert_bits_equal(inv.to_numpy(), oinv, f"inverse{n}")
+        X, st = tb.solve(A, ctx.from_numpy(b, (n,), layout))
+        ox, ost = oracle.solve(a, b, n, 1)
+        assert np.array_equal(st.to_numpy(), ost)
+        assert_bits_equal(X.to_numpy(), ox.reshape(batch, n), f"solve{n}")
+        if batch >= 300:
+            assert ost.sum() == (batch + 127) // 128          # every 128th matrix is singular
+            assert np.all(oracle.det(a, n)[::128] == 0)
+
+
+@pytest.mark.parametrize("dc", FRAC)
+def test_solve_matrix_rhs_equals_inverse(ctx, dc):
+    batch, n = 777, 4
+    a, _ = elim_inputs(dc, n, batch)
+    eye = np.broadcast_to(np.eye(n, dtype=a.dtype), (batch, n, n)).copy()
+    A = ctx.from_numpy(a, (n, n))
+    X, st = tb.solve(A, ctx.from_numpy(eye, (n, n)))
+    inv, st2 = tb.inverse(A)
+    assert_bits_equal(X.to_numpy(), inv.to_numpy(), "solve(A, I) == inverse(A)")
+    assert np.array_equal(st.to_numpy(), st2.to_numpy())
+
+
+def test_det_rejects_int64_and_nonsquare(ctx):
+    with pytest.raises(tb.Unsupported):
+        tb.det(ctx.empty((3, 3), np.int64, 4))
+    with pytest.raises(tb.WrongListLength):
+        tb.det(ctx.empty((3, 4), np.float64, 4))
+
+
+def test_elimination_residuals(ctx):
+    batch, n = 20000, 4
+    a = oracle.fill(oracle.F64, oracle.SEED_A, 11, batch * n * n).reshape(batch, n, n)
+    b = oracle.fill(oracle.F64, oracle.SEED_B, 11, batch * n).reshape(batch, n)
+    A = ctx.from_numpy(a, (n, n))
+    X, st = tb.solve(A, ctx.from_numpy(b, (n,)))
+    x = X.to_numpy()
+    assert st.to_numpy().sum() == 0
+    r = np.abs(np.einsum("bij,bj->bi", a, x) - b).max(axis=1)
+    scale = np.abs(a).sum(axis=(1, 2)) * np.abs(x).max(axis=1) + np.abs(b).max(axis=1)
+    cond = np.linalg.cond(a)
+    assert np.all(r <= 1e-12 * scale * np.maximum(cond, 1.0))
+
+
+# ---- regression fixtures through the device ----------------------------------------
+def test_la_regression_fixtures_on_device(ctx):
+    with open(os.path.join(GOLD, "la_regression.json")) as f:
+        cases = json.load(f)
+    npd = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
+    for c in cases:
+        dt = npd[c["dtype"]]
+        ins = [np.asarray(x, dtype=dt) for x in c["in"]]
+        p = c["params"]
+        if c["op"] == "matmul":
+            A = ctx.from_numpy(ins[0], (p["m"], p["k"]))
+            B = ctx.from_numpy(ins[1], (p["k"], p["n"]))
+            outs = [tb.matmul(A, B).to_numpy()]
+        elif c["op"] == "dot":
+            outs = [tb.dot(ctx.from_numpy(ins[0], (p["n"],)), ctx.from_numpy(ins[1], (p["n"],))).to_numpy()]
+        elif c["op"] == "prod":
+            outs = [tb.prod(ctx.from_numpy(ins[0], p["dims_a"]), ctx.from_numpy(ins[1], p["dims_b"]), p["n"]).to_numpy()]
+        elif c["op"] == "det":
+            outs = [tb.det(ctx.from_numpy(ins[0], (p["n"], p["n"]))).to_numpy()]
+        elif c["op"] == "inverse":
+            o, s = tb.inverse(ctx.from_numpy(ins[0], (p["n"], p["n"])))
+            outs = [o.to_numpy(), s.to_numpy()]
+        else:
+            o, s = tb.solve(ctx.from_numpy(ins[0], (p["n"], p["n"])), ctx.from_numpy(ins[1], (p["n"],)))
+            outs = [o.to_numpy(), s.to_numpy()]
+        for got, want in zip(outs, c["out"]):
+            want = np.asarray(want, dtype=got.dtype)
+            assert np.array_equal(bits(got).ravel(), bits(want).ravel()), (c["op"], c["dtype"], p)
+
+
+# ---- marshalling, layouts, element-wise, errors ------------------------------------
+def test_from_list_length_check(ctx):
+    with pytest.raises(tb.WrongListLength):
+        ctx.from_list([1.0] * 17, (3, 3), np.float64, 2)
+    b = ctx.from_list(list(range(18)), (3, 3), np.int64, 2)
+    assert b.to_list() == list(range(18))
+    with pytest.raises(tb.WrongListLength):
+        b.upload(np.zeros(17, dtype=np.int64))
+
+
+@pytest.mark.parametrize("dc", ALL)
+def test_relayout_roundtrip(ctx, dc):
+    for batch, shape in ((1, (3, 3)), (1000, (4, 4)), (4099, (3,)), (77, (8, 8, 2))):
+        a, _ = inputs(dc, 12, batch, int(np.prod(shape)))
+        A = ctx.from_numpy(a, shape)
+        S = A.relayout(tb.SOA)
+        assert_bits_equal(S.to_numpy().ravel(), a, "soa download")
+        assert_bits_equal(S.relayout(tb.AOS).to_numpy().ravel(), a, "aos roundtrip")
+
+
+@pytest.mark.parametrize("dc", ALL)
+def test_elementwise(ctx, dc):
+    batch = 3001
+    a, b = inputs(dc, 13, batch, 9, 9)
+    A, B = ctx.from_numpy(a, (3, 3)), ctx.from_numpy(b, (3, 3))
+    with np.errstate(over="ignore"):
+        assert_bits_equal((A + B).to_numpy().ravel(), a + b, "+")
+        assert_bits_equal((A - B).to_numpy().ravel(), a - b, "-")
+        assert_bits_equal(tb.zip_with("*", A, B).to_numpy().ravel(), a * b, "*")
+        k = a[3]
+        assert_bits_equal(tb.scale(k, A).to_numpy().ravel(), k * a, "scale")
+
+
+def test_device_synthetic_matches_oracle(ctx):
+    for dc in ALL:
+        for layout in (tb.AOS, tb.SOA):
+            batch = 4099
+            A = ctx.synthetic((3, 3), NPD[dc], batch, oracle.SEED_A, 7, layout)
+            assert_bits_equal(A.to_numpy().ravel(), oracle.fill(dc, oracle.SEED_A, 7, batch * 9), "fill")
+    A = ctx.synthetic((4, 4), np.float64, 70000, oracle.SEED_A, 3).plant_specials()
+    ref = oracle.fill(oracle.F64, oracle.SEED_A, 3, 70000 * 16).reshape(70000, 4, 4).copy()
+    oracle.plant_specials(ref, 4)
+    assert_bits_equal(A.to_numpy(), ref, "plant")
+
+
+def test_host_entry_matches_device_entry(ctx):
+    batch = 300001
+    a, b = inputs(oracle.F32, 14, batch, 16, 16)
+    out = np.empty(batch * 16, dtype=np.float32)
+    tb.matmul_host(ctx, a, b, 4, 4, 4, out)
+    assert_bits_equal(out.reshape(batch, 4, 4), oracle.matmul(a, b, 4, 4, 4, threads=8), "host pipeline")
+
+
+def test_launch_counter_counts_kernels(ctx):
+    A = ctx.synthetic((3, 3), np.float64, 1000, 1, 1)
+    B = ctx.synthetic((3, 3), np.float64, 1000, 2, 1)
+    n0 = ctx.launch_count()
+    for _ in range(5):
+        tb.matmul(A, B)
+    assert ctx.launch_count() - n0 == 5
+
+
+# ---- full BASELINE sizes: size-independent properties --------------------------------
+def test_full_size_config1_properties(ctx):
+    batch = 1 << 20
+    A = ctx.synthetic((3, 3), np.int64, batch, oracle.SEED_A, 1)
+    B = ctx.synthetic((3, 3), np.int64, batch, oracle.SEED_B, 1)
+    lhs = tb.transpose(A @ B).to_numpy()
+    rhs = (tb.transpose(B) @ tb.transpose(A)).to_numpy()
+    assert np.array_equal(lhs, rhs)
+    # spot parity on a slice of the full batch, including the ragged tail region
+    a = oracle.fill(oracle.I64, oracle.SEED_A, 1, batch * 9).reshape(batch, 3, 3)
+    b = oracle.fill(oracle.I64, oracle.SEED_B, 1, batch * 9).reshape(batch, 3, 3)
+    sl = slice(batch - 5000, batch)
+    assert np.array_equal(lhs[sl], oracle.transpose(oracle.matmul(a[sl], b[sl], 3, 3, 3), [3, 3]))
+    Ad = ctx.synthetic((3, 3), np.float64, batch, oracle.SEED_A, 2)
+    eye = ctx.from_numpy(np.broadcast_to(np.eye(3), (batch, 3, 3)).copy(), (3, 3))
+    assert_bits_equal((Ad @ eye).to_numpy(), Ad.to_numpy(), "A.I == A")
+
+
+def test_full_size_config3_properties(ctx):
+    batch = 1 << 22
+    A = ctx.synthetic((4, 4), np.float64, batch, oracle.SEED_A, 3).plant_specials()
+    inv, st = tb.inverse(A)
+    s = st.to_numpy()
+    assert s.sum() == batch // 65536 and np.all(s[::65536] == 1)
+    d = tb.det(A).to_numpy()
+    assert np.all(d[::65536] == 0) and np.count_nonzero(d == 0) == batch // 65536
+    # A . A^-1 ~ I on the non-singular items (residual scaled by the condition number)
+    prod = (A @ inv).to_numpy()
+    ok = s == 0
+    res = np.abs(prod[ok] - np.eye(4)).max(axis=(1, 2))
+    a = A.to_numpy()[ok][:200000]
+    cond = np.linalg.cond(a)
+    assert np.all(res[:200000] <= 1e-12 * 100 * cond)
+    # parity with the oracle on a slice that contains swaps and a singular item
+    sl = slice(65536 - 2048, 65536 + 2048)
+    ao = A.to_numpy()[sl]
+    oinv, ost = oracle.inverse(ao, 4)
+    assert_bits_equal(inv.to_numpy()[sl], oinv, "inverse slice")
+    assert np.array_equal(s[sl], ost)
