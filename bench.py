@@ -68,10 +68,16 @@ def load_peaks():
     try:
         with open(p) as f:
             j = json.load(f)
-        return {"hbm_gbs": float(j["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)",
-                "fp64_tflops": j.get("fp64_tflops")}
+        out = {"hbm_gbs": float(j["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
     except Exception:
-        return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)", "fp64_tflops": None}
+        out = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    out["fp64_tflops"] = None
+    try:  # cuBLAS DGEMM 8192^3 measured by tools/measure_fp64_peak.py on this pool's B200
+        with open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")) as f:
+            out["fp64_tflops"] = float(json.load(f)["fp64_tflops"])
+    except Exception:
+        pass
+    return out
 
 
 def load_traffic(name):
@@ -223,7 +229,7 @@ def roofline(w, ms_per_launch, peaks):
                 "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"]}
     ach = w["flops"] * w["batch"] / (ms_per_launch * 1e-3) / 1e12
     peak = peaks.get("fp64_tflops") or 37.0
-    src = "measured cuBLAS DGEMM" if peaks.get("fp64_tflops") else "nominal FP64 37 TFLOP/s (no measured DGEMM peak yet)"
+    src = "measured cuBLAS DGEMM 8192^3 (profiles/r01_fp64_peak.json)" if peaks.get("fp64_tflops") else "nominal FP64 37 TFLOP/s (no measured DGEMM peak yet)"
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src}
 
 

@@ -80,7 +80,9 @@ struct t5_buf {
     size_t first[T5_MAX_DEVICES], count[T5_MAX_DEVICES], cap[T5_MAX_DEVICES], bytes[T5_MAX_DEVICES];
 };
 
-static constexpr size_t SCRATCH_BYTES = 148 * 8 * 8 + 64;
+static constexpr size_t PART_OFF = 148 * 8 * 8;          // dot-sum device partial
+static constexpr size_t SCHED_OFF = PART_OFF + 64;        // 4 x {next tile, finished CTAs}: main stream + 3 pipeline slots
+static constexpr size_t SCRATCH_BYTES = SCHED_OFF + 4 * 16;
 static constexpr size_t FLUSH_BYTES = 256ull << 20;
 
 static int cuda_fail(t5_ctx* c, cudaError_t e, const char* where) {
@@ -165,7 +167,8 @@ int t5_init(const int* devices, int ndev, t5_ctx** out) {
         if ((e = cudaSetDevice(c->dev[g])) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&c->stream[g], cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate(&c->ev0[g])) != cudaSuccess || (e = cudaEventCreate(&c->ev1[g])) != cudaSuccess ||
-            (e = cudaMalloc(&c->scratch[g], SCRATCH_BYTES)) != cudaSuccess) {
+            (e = cudaMalloc(&c->scratch[g], SCRATCH_BYTES)) != cudaSuccess ||
+            (e = cudaMemset(c->scratch[g], 0, SCRATCH_BYTES)) != cudaSuccess) {
             int rc = cuda_fail(nullptr, e, "t5_init");
             t5_shutdown(c);
             return rc;
@@ -354,6 +357,7 @@ static int check(const t5_ctx* c, const t5_buf* b, int dtype, size_t elems, cons
 static Shard shard_of(const t5_ctx* c, const t5_buf* b, int g) {
     Shard s;
     s.stream = c->stream[g]; s.layout = b->layout; s.count = b->count[g]; s.soa_stride = b->cap[g]; s.first = b->first[g];
+    s.sched = (unsigned long long*)((char*)c->scratch[g] + SCHED_OFF);
     return s;
 }
 
@@ -431,7 +435,7 @@ int t5_dot_sum(t5_ctx* c, int dtype, int n, const t5_buf* X, const t5_buf* Y, vo
     CHECK(check(c, X, dtype, (size_t)n, nullptr));
     CHECK(check(c, Y, dtype, (size_t)n, X));
     std::lock_guard<std::mutex> lk(c->mu);
-    const size_t part_off = SCRATCH_BYTES - 64;
+    const size_t part_off = PART_OFF;
     for (int g = 0; g < c->ndev; ++g) {
         CU(c, cudaSetDevice(c->dev[g]));
         Shard s = shard_of(c, X, g);
@@ -687,6 +691,7 @@ int t5_matmul_host(t5_ctx* c, int dtype, int m, int k, int n, size_t batch, cons
             CU(c, cudaMemcpyAsync(s.d[0], (const char*)A + it * ia, cnt * ia, cudaMemcpyHostToDevice, s.stream));
             CU(c, cudaMemcpyAsync(s.d[1], (const char*)B + it * ib, cnt * ib, cudaMemcpyHostToDevice, s.stream));
             Shard sh; sh.stream = s.stream; sh.layout = T5L_AOS; sh.count = cnt; sh.soa_stride = 0; sh.first = it;
+            sh.sched = (unsigned long long*)((char*)c->scratch[g] + SCHED_OFF) + 2 * (1 + j % 3);
             int r = product_shard(sh, dtype, m, k, n, 1, s.d[0], s.d[1], s.d[2]);
             if (r != T5I_OK) return map_internal(c, r, "t5_matmul_host");
             c->launches++;

@@ -30,6 +30,7 @@ struct Shard {
     size_t count;       // items in this shard
     size_t soa_stride;  // SoA element stride (shard capacity, items)
     size_t first;       // global index of the shard's first item
+    unsigned long long* sched;  // this stream's tile-scheduler words {next tile, finished CTAs}
 };
 
 // ---- t5_small_ops.cu: register-resident thread-per-item kernels -----------------

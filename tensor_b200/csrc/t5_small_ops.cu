@@ -6,158 +6,18 @@
 // This translation unit MUST be compiled with -fmad=false: the specification is
 // multiply-round-add-round in index order, which makes Double/Float results
 // bit-identical to the CPU oracle, not merely within tolerance.
-#include "t5_tile.cuh"
+#include "t5_small_ops.cuh"
 #include "t5_internal.h"
+#include <type_traits>
 
 namespace t5 {
 
-// ---- .*. : C[i,c] = fold_{j asc} (acc + A[i,j]*B[j,c]), acc0 = 0  (§8a a6) -------
-template <class T, int M, int K, int N>
-struct MatmulOp {
-    using In0 = Rec<T, M * K>; using In1 = Rec<T, K * N>;
-    using Out0 = Rec<T, M * N>; using Out1 = NoRec;
-    __device__ __forceinline__ static void run(const T* a, const T* b, T* c, unsigned char*) {
-        using R = Arith<T>;
-        #pragma unroll
-        for (int i = 0; i < M; ++i)
-            #pragma unroll
-            for (int col = 0; col < N; ++col) {
-                T acc = R::zero();
-                #pragma unroll
-                for (int j = 0; j < K; ++j) acc = R::add(acc, R::mul(a[i * K + j], b[j * N + col]));
-                c[i * N + col] = acc;
-            }
-    }
-};
-
-// ---- transpose of an R x C matrix: pure register renaming (§8a a4) -----------------
-template <class T, int R_, int C_>
-struct TransposeOp {
-    using In0 = Rec<T, R_ * C_>; using In1 = NoRec;
-    using Out0 = Rec<T, R_ * C_>; using Out1 = NoRec;
-    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* o, unsigned char*) {
-        #pragma unroll
-        for (int i = 0; i < R_; ++i)
-            #pragma unroll
-            for (int j = 0; j < C_; ++j) o[j * R_ + i] = a[i * C_ + j];
-    }
-};
-
-// ---- Gaussian elimination, first-non-zero pivot (§8a pivot rule) --------------------
-// w is N x W in registers; every index is a compile-time constant after unrolling,
-// the pivot search is a chain of predicated row swaps (no divergence, no local mem).
-template <class T, int N, int W>
-__device__ __forceinline__ bool eliminate(T (&w)[N][W], int& swaps) {
-    bool singular = false;
-    swaps = 0;
-    #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        #pragma unroll
-        for (int r = k + 1; r < N; ++r) {
-            const bool sw = (w[k][k] == T(0)) && (w[r][k] != T(0));
-            // columns < k of rows >= k are exact zeros already: swapping them is a no-op
-            #pragma unroll
-            for (int j = k; j < W; ++j) {
-                T x = w[k][j], y = w[r][j];
-                w[k][j] = sw ? y : x;
-                w[r][j] = sw ? x : y;
-            }
-            swaps += sw ? 1 : 0;
-        }
-        singular = singular || (w[k][k] == T(0));
-        #pragma unroll
-        for (int i = k + 1; i < N; ++i) {
-            const T f = w[i][k] / w[k][k];
-            #pragma unroll
-            for (int j = k + 1; j < W; ++j) w[i][j] = w[i][j] - f * w[k][j];
-            w[i][k] = T(0);
-        }
-    }
-    return !singular;
-}
-
-template <class T, int N>
-struct DetOp {
-    using In0 = Rec<T, N * N>; using In1 = NoRec;
-    using Out0 = Rec<T, 1>; using Out1 = NoRec;
-    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* o, unsigned char*) {
-        T w[N][N];
-        #pragma unroll
-        for (int i = 0; i < N; ++i)
-            #pragma unroll
-            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
-        int swaps;
-        const bool ok = eliminate<T, N, N>(w, swaps);
-        T acc = T(1);
-        #pragma unroll
-        for (int k = 0; k < N; ++k) acc = acc * w[k][k];
-        acc = (swaps & 1) ? -acc : acc;
-        o[0] = ok ? acc : T(0);
-    }
-};
-
-// solve A X = B, B is N x NRHS; also the body of inverse (B = I).
-template <class T, int N, int NRHS>
-__device__ __forceinline__ void solve_regs(T (&w)[N][N + NRHS], T* x, unsigned char* status) {
-    int swaps;
-    const bool ok = eliminate<T, N, N + NRHS>(w, swaps);
-    T xs[N][NRHS];
-    #pragma unroll
-    for (int k = N - 1; k >= 0; --k)
-        #pragma unroll
-        for (int c = 0; c < NRHS; ++c) {
-            T s = T(0);
-            #pragma unroll
-            for (int j = k + 1; j < N; ++j) s = s + w[k][j] * xs[j][c];
-            xs[k][c] = (w[k][N + c] - s) / w[k][k];
-        }
-    #pragma unroll
-    for (int k = 0; k < N; ++k)
-        #pragma unroll
-        for (int c = 0; c < NRHS; ++c) x[k * NRHS + c] = ok ? xs[k][c] : T(0);
-    status[0] = ok ? 0 : 1;
-}
-
-template <class T, int N, int NRHS>
-struct SolveOp {
-    using In0 = Rec<T, N * N>; using In1 = Rec<T, N * NRHS>;
-    using Out0 = Rec<T, N * NRHS>; using Out1 = Rec<unsigned char, 1>;
-    __device__ __forceinline__ static void run(const T* a, const T* b, T* x, unsigned char* status) {
-        T w[N][N + NRHS];
-        #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            #pragma unroll
-            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
-            #pragma unroll
-            for (int c = 0; c < NRHS; ++c) w[i][N + c] = b[i * NRHS + c];
-        }
-        solve_regs<T, N, NRHS>(w, x, status);
-    }
-};
-
-template <class T, int N>
-struct InverseOp {
-    using In0 = Rec<T, N * N>; using In1 = NoRec;
-    using Out0 = Rec<T, N * N>; using Out1 = Rec<unsigned char, 1>;
-    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* x, unsigned char* status) {
-        T w[N][2 * N];
-        #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            #pragma unroll
-            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
-            #pragma unroll
-            for (int c = 0; c < N; ++c) w[i][N + c] = (i == c) ? T(1) : T(0);
-        }
-        solve_regs<T, N, N>(w, x, status);
-    }
-};
-
 // ---- launchers ---------------------------------------------------------------------
-template <class Op, int THREADS, int IPT, int STAGES>
-static int launch_tile(cudaStream_t st, const void* in0, const void* in1, void* out0, void* out1, size_t n) {
+template <class Op, int THREADS, int IPT, int STAGES, int MIN_BLOCKS>
+static int launch_tile(const Shard& s, const void* in0, const void* in1, void* out0, void* out1) {
     using C = TileCfg<Op, THREADS, IPT, STAGES>;
     static_assert(C::SMEM <= 227 * 1024, "tile does not fit in shared memory");
-    auto kern = tile_kernel<Op, THREADS, IPT, STAGES>;
+    auto kern = tile_kernel<Op, THREADS, IPT, STAGES, MIN_BLOCKS>;
     static int grid_cap[T5_MAX_DEVICES] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
@@ -171,11 +31,12 @@ static int launch_tile(cudaStream_t st, const void* in0, const void* in1, void* 
         if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
         grid_cap[dev] = occ * sms;
     }
-    if (n == 0) return T5I_OK;
-    size_t tiles = (n + C::TILE - 1) / C::TILE;
+    if (s.count == 0) return T5I_OK;
+    if (!s.sched) return T5I_CUDA;
+    size_t tiles = (s.count + C::TILE - 1) / C::TILE;
     int grid = (int)(tiles < (size_t)grid_cap[dev] ? tiles : (size_t)grid_cap[dev]);
-    TileArgs a{in0, in1, out0, out1, (unsigned long long)n};
-    kern<<<grid, THREADS, C::SMEM, st>>>(a);
+    TileArgs a{in0, in1, out0, out1, (unsigned long long)s.count, s.sched};
+    kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
 
@@ -195,15 +56,31 @@ static int launch_soa(cudaStream_t st, const void* in0, const void* in1, void* o
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
 
-// Tile geometry: 128 threads, 1 record per thread; ring depth chosen so a CTA
-// stays near 48-64 KB and 3+ CTAs share an SM.
+// Tile geometry {THREADS, records per thread, ring depth}, picked per op from the sweep
+// tools/tune_tile.cu -> profiles/r01_tune_tile.csv (fractions of the measured HBM copy
+// peak in DESIGN.md).  Streaming ops want >= 16-64 KB of input per tile; the
+// elimination ops are latency-bound on FP64 division chains and want more, smaller CTAs.
+template <int T, int I, int S> struct G { static constexpr int threads = T, ipt = I, stages = S; };
+template <class Op> struct Geo {
+    static constexpr int in_bytes = Op::In0::bytes + Op::In1::bytes;
+    using type = std::conditional_t<(in_bytes <= 32), G<256, 2, 3>,
+                 std::conditional_t<(in_bytes <= 64), G<256, 1, 2>,
+                 std::conditional_t<(in_bytes <= 160), G<256, 2, 2>, G<128, 2, 2>>>>;
+};
+template <class T> struct Geo<DetOp<T, 3>> { using type = G<256, 1, 2>; };
+template <class T> struct Geo<DetOp<T, 4>> { using type = G<128, 2, 2>; };
+template <class T> struct Geo<InverseOp<T, 2>> { using type = G<128, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 3>> { using type = G<128, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 4>> { using type = G<64, 1, 2>; };
+template <class T, int N, int R> struct Geo<SolveOp<T, N, R>> {
+    using type = std::conditional_t<(R == 1), G<256, 1, 2>, std::conditional_t<(N <= 3), G<128, 1, 2>, G<64, 1, 2>>>;
+};
+
 template <class Op>
 static int launch_op(const Shard& s, const void* in0, const void* in1, void* out0, void* out1) {
     if (s.layout == T5L_SOA) return launch_soa<Op>(s.stream, in0, in1, out0, out1, s.count, s.soa_stride);
-    constexpr int in_bytes = Op::In0::stride + Op::In1::stride;
-    if constexpr (in_bytes <= 48) return launch_tile<Op, 256, 2, 4>(s.stream, in0, in1, out0, out1, s.count);
-    else if constexpr (in_bytes <= 160) return launch_tile<Op, 128, 1, 4>(s.stream, in0, in1, out0, out1, s.count);
-    else return launch_tile<Op, 128, 1, 3>(s.stream, in0, in1, out0, out1, s.count);
+    using g = typename Geo<Op>::type;
+    return launch_tile<Op, g::threads, g::ipt, g::stages, 1>(s, in0, in1, out0, out1);
 }
 
 template <class T>

@@ -1,0 +1,151 @@
+// Register-level arithmetic of the tiny fixed shapes.
+// Each Op is a pure function on register arrays; t5_tile.cuh supplies the data
+// movement (AoS tile pipeline or SoA skeleton).  Every TU that includes this must be
+// compiled with -fmad=false (multiply-round-add-round, bit-identical to the oracle).
+#pragma once
+#include "t5_tile.cuh"
+
+namespace t5 {
+
+// ---- .*. : C[i,c] = fold_{j asc} (acc + A[i,j]*B[j,c]), acc0 = 0  (§8a a6) -------
+template <class T, int M, int K, int N>
+struct MatmulOp {
+    using In0 = Rec<T, M * K>; using In1 = Rec<T, K * N>;
+    using Out0 = Rec<T, M * N>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const T* b, T* c, unsigned char*) {
+        using R = Arith<T>;
+        #pragma unroll
+        for (int i = 0; i < M; ++i)
+            #pragma unroll
+            for (int col = 0; col < N; ++col) {
+                T acc = R::zero();
+                #pragma unroll
+                for (int j = 0; j < K; ++j) acc = R::add(acc, R::mul(a[i * K + j], b[j * N + col]));
+                c[i * N + col] = acc;
+            }
+    }
+};
+
+// ---- transpose of an R x C matrix: pure register renaming (§8a a4) -----------------
+template <class T, int R_, int C_>
+struct TransposeOp {
+    using In0 = Rec<T, R_ * C_>; using In1 = NoRec;
+    using Out0 = Rec<T, R_ * C_>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* o, unsigned char*) {
+        #pragma unroll
+        for (int i = 0; i < R_; ++i)
+            #pragma unroll
+            for (int j = 0; j < C_; ++j) o[j * R_ + i] = a[i * C_ + j];
+    }
+};
+
+// ---- Gaussian elimination, first-non-zero pivot (§8a pivot rule) --------------------
+// w is N x W in registers; every index is a compile-time constant after unrolling,
+// the pivot search is a chain of predicated row swaps (no divergence, no local mem).
+template <class T, int N, int W>
+__device__ __forceinline__ bool eliminate(T (&w)[N][W], int& swaps) {
+    bool singular = false;
+    swaps = 0;
+    #pragma unroll
+    for (int k = 0; k < N; ++k) {
+        #pragma unroll
+        for (int r = k + 1; r < N; ++r) {
+            const bool sw = (w[k][k] == T(0)) && (w[r][k] != T(0));
+            // columns < k of rows >= k are exact zeros already: swapping them is a no-op
+            #pragma unroll
+            for (int j = k; j < W; ++j) {
+                T x = w[k][j], y = w[r][j];
+                w[k][j] = sw ? y : x;
+                w[r][j] = sw ? x : y;
+            }
+            swaps += sw ? 1 : 0;
+        }
+        singular = singular || (w[k][k] == T(0));
+        #pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const T f = w[i][k] / w[k][k];
+            #pragma unroll
+            for (int j = k + 1; j < W; ++j) w[i][j] = w[i][j] - f * w[k][j];
+            w[i][k] = T(0);
+        }
+    }
+    return !singular;
+}
+
+template <class T, int N>
+struct DetOp {
+    using In0 = Rec<T, N * N>; using In1 = NoRec;
+    using Out0 = Rec<T, 1>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* o, unsigned char*) {
+        T w[N][N];
+        #pragma unroll
+        for (int i = 0; i < N; ++i)
+            #pragma unroll
+            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+        int swaps;
+        const bool ok = eliminate<T, N, N>(w, swaps);
+        T acc = T(1);
+        #pragma unroll
+        for (int k = 0; k < N; ++k) acc = acc * w[k][k];
+        acc = (swaps & 1) ? -acc : acc;
+        o[0] = ok ? acc : T(0);
+    }
+};
+
+// solve A X = B, B is N x NRHS; also the body of inverse (B = I).
+template <class T, int N, int NRHS>
+__device__ __forceinline__ void solve_regs(T (&w)[N][N + NRHS], T* x, unsigned char* status) {
+    int swaps;
+    const bool ok = eliminate<T, N, N + NRHS>(w, swaps);
+    T xs[N][NRHS];
+    #pragma unroll
+    for (int k = N - 1; k >= 0; --k)
+        #pragma unroll
+        for (int c = 0; c < NRHS; ++c) {
+            T s = T(0);
+            #pragma unroll
+            for (int j = k + 1; j < N; ++j) s = s + w[k][j] * xs[j][c];
+            xs[k][c] = (w[k][N + c] - s) / w[k][k];
+        }
+    #pragma unroll
+    for (int k = 0; k < N; ++k)
+        #pragma unroll
+        for (int c = 0; c < NRHS; ++c) x[k * NRHS + c] = ok ? xs[k][c] : T(0);
+    status[0] = ok ? 0 : 1;
+}
+
+template <class T, int N, int NRHS>
+struct SolveOp {
+    using In0 = Rec<T, N * N>; using In1 = Rec<T, N * NRHS>;
+    using Out0 = Rec<T, N * NRHS>; using Out1 = Rec<unsigned char, 1>;
+    __device__ __forceinline__ static void run(const T* a, const T* b, T* x, unsigned char* status) {
+        T w[N][N + NRHS];
+        #pragma unroll
+        for (int i = 0; i < N; ++i) {
+            #pragma unroll
+            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+            #pragma unroll
+            for (int c = 0; c < NRHS; ++c) w[i][N + c] = b[i * NRHS + c];
+        }
+        solve_regs<T, N, NRHS>(w, x, status);
+    }
+};
+
+template <class T, int N>
+struct InverseOp {
+    using In0 = Rec<T, N * N>; using In1 = NoRec;
+    using Out0 = Rec<T, N * N>; using Out1 = Rec<unsigned char, 1>;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* x, unsigned char* status) {
+        T w[N][2 * N];
+        #pragma unroll
+        for (int i = 0; i < N; ++i) {
+            #pragma unroll
+            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+            #pragma unroll
+            for (int c = 0; c < N; ++c) w[i][N + c] = (i == c) ? T(1) : T(0);
+        }
+        solve_regs<T, N, N>(w, x, status);
+    }
+};
+
+}  // namespace t5

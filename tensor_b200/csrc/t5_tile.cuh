@@ -1,36 +1,74 @@
 // AoS tile pipeline: the skeleton every thread-per-item kernel runs in.
 //
 // A batch is `n_items` records per stream, records concatenated (the reference's
-// wire order, src/Data/Tensor/Vector.hs:360-367).  Records are 12..128 bytes, so
-// a thread reading "its" record straight from HBM would issue 32 scattered
+// wire order, src/Data/Tensor/Vector.hs:360-367).  Records are 4..128 bytes, so
+// a thread reading "its" record straight from HBM would touch 32 scattered
 // sectors per warp instruction.  Instead a persistent CTA walks tiles of
 // TILE = THREADS*IPT records:
 //
-//   global --cp.async 16 B (LDGSTS, coalesced, STAGES-deep ring)--> shared
-//   shared --LDS (record-per-thread, conflict-free by construction)--> registers
+//   global --cp.async 16 B (LDGSTS, coalesced, STAGES-deep ring)--> shared slots
+//   slot   --LDS (record-per-thread, conflict-free by construction)--> registers
 //   registers: Op::run  (pure register arithmetic, shared with the SoA skeleton)
-//   registers --STS--> shared out-stage --LDS.128 + STG.128 (coalesced, streaming)--> global
+//   result <= 16 B : STG straight from registers (consecutive threads, consecutive
+//                    addresses: already coalesced)
+//   result  > 16 B : written IN PLACE over the thread's own input slot, then
+//                    LDS.128 + STG.128 (coalesced, streaming) by the whole CTA
 //
-// Conflict-free record access: a record of B bytes is stored with stride
-// B (+16 when B/16 is even).  Then B/16 odd -> LDS.128 hits 8 distinct 16-B bank
-// groups per quarter-warp; B = 8*odd -> LDS.64 hits 16 distinct bank pairs per
-// half-warp; B = 4*odd -> LDS.32 hits 32 distinct banks.
+// Conflict-free slots.  A record of B bytes occupies a slot of `stride` bytes:
+//   B in {32, 64, 128}      : stride B, 16-B chunks XOR-swizzled inside each 128-B row
+//                             (chunk w of record i lives at w ^ ((i >> (3-log2 c)) & (c-1)),
+//                             c = B/16) - the same pattern TMA's 32/64/128B swizzle uses;
+//   B = 16*even (not 2^k)   : stride B+16 (odd number of chunks);
+//   B = 16*odd, 8*odd, 4*odd: stride B (LDS.128 / LDS.64 / LDS.32 hit distinct banks).
 //
-// Two __syncthreads per tile; the ring keeps (STAGES-1) tiles of loads in flight
-// per CTA, and several CTAs are resident per SM, which is what covers the HBM
-// latency (bytes in flight per SM = CTAs/SM * (STAGES-1) * tile bytes).
+// Tiles are handed out by a global atomic counter (dynamic scheduling): with a static
+// round-robin the slowest SM (far-die L2, busier DRAM partition) finished ~17% after
+// the average one (ncu, profiles/r01_*), which capped DRAM utilisation.
 #pragma once
 #include "t5_device.cuh"
 
 namespace t5 {
+
+constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
 
 template <class T, int N>
 struct Rec {
     using type = T;
     static constexpr int n = N;
     static constexpr int bytes = N * (int)sizeof(T);
-    static constexpr int pad = (bytes > 0 && bytes % 16 == 0 && ((bytes / 16) % 2 == 0)) ? 16 : 0;
+    static constexpr int cpi = bytes / 16;                                   // 16-B chunks per record (if bytes % 16 == 0)
+    static constexpr bool vec16 = bytes > 0 && bytes % 16 == 0;
+    static constexpr bool swz = vec16 && (cpi == 2 || cpi == 4 || cpi == 8); // power-of-two records: XOR swizzle
+    static constexpr int pad = (vec16 && !swz && (cpi % 2 == 0)) ? 16 : 0;
     static constexpr int stride = bytes + pad;
+    static constexpr int swz_shift = swz ? 3 - ilog2(cpi) : 0;
+
+    // byte offset of 16-B chunk w of record `item` inside a stage
+    __device__ __forceinline__ static int chunk_off(int item, int w) {
+        if constexpr (swz) return item * bytes + ((w ^ ((item >> swz_shift) & (cpi - 1))) << 4);
+        else return item * stride + (w << 4);
+    }
+    // byte offset of the ch-th 16-B chunk of the tile's contiguous global image
+    __device__ __forceinline__ static int tile_chunk_off(int ch) {
+        if constexpr (vec16 && (swz || pad)) return chunk_off(ch / cpi, ch % cpi);
+        else return ch << 4;
+    }
+    __device__ __forceinline__ static void load(const unsigned char* stage, int item, void* regs) {
+        if constexpr (vec16) {
+            #pragma unroll
+            for (int w = 0; w < cpi; ++w) reinterpret_cast<uint4*>(regs)[w] = *reinterpret_cast<const uint4*>(stage + chunk_off(item, w));
+        } else {
+            lds_item<bytes>(stage + item * stride, regs);
+        }
+    }
+    __device__ __forceinline__ static void store(unsigned char* stage, int item, const void* regs) {
+        if constexpr (vec16) {
+            #pragma unroll
+            for (int w = 0; w < cpi; ++w) *reinterpret_cast<uint4*>(stage + chunk_off(item, w)) = reinterpret_cast<const uint4*>(regs)[w];
+        } else {
+            sts_item<bytes>(stage + item * stride, regs);
+        }
+    }
 };
 using NoRec = Rec<unsigned char, 0>;
 
@@ -45,6 +83,7 @@ struct TileArgs {
     void* out0;
     void* out1;
     unsigned long long n_items;
+    unsigned long long* sched;  // [0] next tile, [1] finished CTAs; both zero between launches
 };
 
 // ---- cooperative tile movement ------------------------------------------------
@@ -52,25 +91,18 @@ template <class R, int TILE, int THREADS>
 __device__ __forceinline__ void tile_load_async(unsigned char* stage, const unsigned char* gsrc, int n_valid, int tid) {
     if constexpr (R::bytes > 0) {
         constexpr int NCH = TILE * R::bytes / 16;  // TILE % 32 == 0 makes this exact
-        constexpr int CPI = R::bytes / 16;         // only used when padded (bytes % 16 == 0)
         if (n_valid == TILE) {
             #pragma unroll
             for (int i = 0; i < (NCH + THREADS - 1) / THREADS; ++i) {
                 int ch = tid + i * THREADS;
-                if ((NCH % THREADS == 0) || ch < NCH) {
-                    unsigned char* d = R::pad ? stage + (ch / (CPI > 0 ? CPI : 1)) * R::stride + (ch % (CPI > 0 ? CPI : 1)) * 16
-                                              : stage + ch * 16;
-                    cp_async16(d, gsrc + (size_t)ch * 16);
-                }
+                if ((NCH % THREADS == 0) || ch < NCH) cp_async16(stage + R::tile_chunk_off(ch), gsrc + (size_t)ch * 16);
             }
         } else {
             const int vbytes = n_valid * R::bytes;
             const int nch = (vbytes + 15) / 16;
             for (int ch = tid; ch < nch; ch += THREADS) {
-                unsigned char* d = R::pad ? stage + (ch / (CPI > 0 ? CPI : 1)) * R::stride + (ch % (CPI > 0 ? CPI : 1)) * 16
-                                          : stage + ch * 16;
                 int rem = vbytes - ch * 16;
-                cp_async16(d, gsrc + (size_t)ch * 16, rem < 16 ? rem : 16);
+                cp_async16(stage + R::tile_chunk_off(ch), gsrc + (size_t)ch * 16, rem < 16 ? rem : 16);
             }
         }
     }
@@ -80,28 +112,37 @@ template <class R, int TILE, int THREADS>
 __device__ __forceinline__ void tile_store(const unsigned char* stage, unsigned char* gdst, int n_valid, int tid) {
     if constexpr (R::bytes > 0) {
         constexpr int NCH = TILE * R::bytes / 16;
-        constexpr int CPI = R::bytes / 16;
         if (n_valid == TILE) {
             #pragma unroll
             for (int i = 0; i < (NCH + THREADS - 1) / THREADS; ++i) {
                 int ch = tid + i * THREADS;
-                if ((NCH % THREADS == 0) || ch < NCH) {
-                    const unsigned char* s = R::pad ? stage + (ch / (CPI > 0 ? CPI : 1)) * R::stride + (ch % (CPI > 0 ? CPI : 1)) * 16
-                                                    : stage + ch * 16;
-                    st_global_stream16(gdst + (size_t)ch * 16, *reinterpret_cast<const uint4*>(s));
-                }
+                if ((NCH % THREADS == 0) || ch < NCH)
+                    st_global_stream16(gdst + (size_t)ch * 16, *reinterpret_cast<const uint4*>(stage + R::tile_chunk_off(ch)));
             }
         } else {
             const int vbytes = n_valid * R::bytes;
             const int nfull = vbytes / 16;
-            for (int ch = tid; ch < nfull; ch += THREADS) {
-                const unsigned char* s = R::pad ? stage + (ch / (CPI > 0 ? CPI : 1)) * R::stride + (ch % (CPI > 0 ? CPI : 1)) * 16
-                                                : stage + ch * 16;
-                st_global_stream16(gdst + (size_t)ch * 16, *reinterpret_cast<const uint4*>(s));
-            }
-            // ragged last chunk (only possible when the record size is not a multiple of 16)
+            for (int ch = tid; ch < nfull; ch += THREADS)
+                st_global_stream16(gdst + (size_t)ch * 16, *reinterpret_cast<const uint4*>(stage + R::tile_chunk_off(ch)));
+            // ragged last chunk (only possible when the record size is not a multiple of 16: linear slots)
             for (int b = nfull * 16 + tid; b < vbytes; b += THREADS) gdst[b] = stage[b];
         }
+    }
+}
+
+// result records of <= 16 B (and the status byte) go straight from registers to HBM
+template <int BYTES>
+__device__ __forceinline__ void stg_direct(unsigned char* g, const void* regs) {
+    if constexpr (BYTES == 16) *reinterpret_cast<uint4*>(g) = *reinterpret_cast<const uint4*>(regs);
+    else if constexpr (BYTES % 8 == 0) {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 8; ++i) reinterpret_cast<uint2*>(g)[i] = reinterpret_cast<const uint2*>(regs)[i];
+    } else if constexpr (BYTES % 4 == 0) {
+        #pragma unroll
+        for (int i = 0; i < BYTES / 4; ++i) reinterpret_cast<unsigned*>(g)[i] = reinterpret_cast<const unsigned*>(regs)[i];
+    } else {
+        #pragma unroll
+        for (int i = 0; i < BYTES; ++i) g[i] = reinterpret_cast<const unsigned char*>(regs)[i];
     }
 }
 
@@ -111,21 +152,26 @@ __device__ __forceinline__ void tile_store(const unsigned char* stage, unsigned 
 // operating on register arrays.
 template <class Op, int THREADS, int IPT, int STAGES>
 struct TileCfg {
+    using I0 = typename Op::In0; using I1 = typename Op::In1;
+    using O0 = typename Op::Out0; using O1 = typename Op::Out1;
     static constexpr int TILE = THREADS * IPT;
-    static constexpr int IN_STAGE = TILE * (Op::In0::stride + Op::In1::stride);
-    static constexpr int OUT_STAGE = TILE * (Op::Out0::stride + Op::Out1::stride);
+    // where Out0 goes: -1 direct from registers, 0 / 1 in place over In0 / In1, 2 its own stage
+    static constexpr int OUT0 = O0::bytes <= 16 ? -1 : (O0::bytes == I0::bytes ? 0 : (O0::bytes == I1::bytes ? 1 : 2));
+    static_assert(O1::bytes <= 16, "second output must be a small record (status byte)");
+    static constexpr int IN_STAGE = TILE * (I0::stride + I1::stride);
+    static constexpr int OUT_STAGE = OUT0 == 2 ? TILE * O0::stride : 0;
     static constexpr int SMEM = STAGES * IN_STAGE + OUT_STAGE;
 };
 
-template <class Op, int THREADS, int IPT, int STAGES>
-__global__ void __launch_bounds__(THREADS) tile_kernel(TileArgs a) {
+template <class Op, int THREADS, int IPT, int STAGES, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
     using C = TileCfg<Op, THREADS, IPT, STAGES>;
-    using I0 = typename Op::In0; using I1 = typename Op::In1;
-    using O0 = typename Op::Out0; using O1 = typename Op::Out1;
+    using I0 = typename C::I0; using I1 = typename C::I1;
+    using O0 = typename C::O0; using O1 = typename C::O1;
     constexpr int TILE = C::TILE;
+    static_assert(STAGES >= 2, "need a ring");
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* out_stage0 = smem + STAGES * C::IN_STAGE;
-    unsigned char* out_stage1 = out_stage0 + TILE * O0::stride;
+    __shared__ unsigned long long tile_q[STAGES];
 
     const int tid = threadIdx.x;
     const unsigned long long n_tiles = (a.n_items + TILE - 1) / TILE;
@@ -146,40 +192,69 @@ __global__ void __launch_bounds__(THREADS) tile_kernel(TileArgs a) {
         cp_async_commit();  // always commit: keeps the group count uniform
     };
 
-    unsigned long long tile = blockIdx.x;
+    // prologue: claim and start the first STAGES-1 tiles; keep one more claim in flight
+    unsigned long long next_claim = 0;
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = atomicAdd(a.sched, 1ull);
+        next_claim = atomicAdd(a.sched, 1ull);
+    }
+    __syncthreads();
     #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(tile + (unsigned long long)s * gridDim.x, s);
+    for (int s = 0; s < STAGES - 1; ++s) issue(tile_q[s], s);
 
     int stage = 0;
-    for (; tile < n_tiles; tile += gridDim.x) {
+    while (true) {
+        const unsigned long long tile = tile_q[stage];
+        if (tile >= n_tiles) break;  // claims are monotonic per CTA: nothing later is valid either
         int pf = stage + STAGES - 1; if (pf >= STAGES) pf -= STAGES;
-        issue(tile + (unsigned long long)(STAGES - 1) * gridDim.x, pf);
-        cp_async_wait<STAGES - 1>();
-        __syncthreads();  // (A) tile landed for every thread; previous copy-out finished
+        if (tid == 0) tile_q[pf] = next_claim;   // slot pf was consumed one iteration ago
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();  // (A) this tile has landed for every thread; stage pf is free; tile_q[pf] visible
+        issue(tile_q[pf], pf);
+        if (tid == 0) next_claim = atomicAdd(a.sched, 1ull);  // consumed next iteration: latency hidden
 
-        unsigned long long first = tile * TILE;
-        unsigned long long left = a.n_items - first;
+        const unsigned long long first = tile * TILE;
+        const unsigned long long left = a.n_items - first;
         const int nv = left < (unsigned long long)TILE ? (int)left : TILE;
-        const unsigned char* s0 = smem + stage * C::IN_STAGE;
-        const unsigned char* s1 = s0 + TILE * I0::stride;
+        unsigned char* s0 = smem + stage * C::IN_STAGE;
+        unsigned char* s1 = s0 + TILE * I0::stride;
+        unsigned char* so = C::OUT0 == 0 ? s0 : (C::OUT0 == 1 ? s1 : smem + STAGES * C::IN_STAGE);
         #pragma unroll
         for (int j = 0; j < IPT; ++j) {
             const int it = tid + j * THREADS;
             if (it < nv) {
                 RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
-                if constexpr (I0::bytes > 0) lds_item<I0::bytes>(s0 + it * I0::stride, r0.v);
-                if constexpr (I1::bytes > 0) lds_item<I1::bytes>(s1 + it * I1::stride, r1.v);
+                if constexpr (I0::bytes > 0) I0::load(s0, it, r0.v);
+                if constexpr (I1::bytes > 0) I1::load(s1, it, r1.v);
                 Op::run(r0.v, r1.v, w0.v, w1.v);
-                if constexpr (O0::bytes > 0) sts_item<O0::bytes>(out_stage0 + it * O0::stride, w0.v);
-                if constexpr (O1::bytes > 0) sts_item<O1::bytes>(out_stage1 + it * O1::stride, w1.v);
+                if constexpr (O0::bytes > 0) {
+                    if constexpr (C::OUT0 == -1) stg_direct<O0::bytes>(g_out0 + (first + it) * O0::bytes, w0.v);
+                    else if constexpr (C::OUT0 == 0) I0::store(so, it, w0.v);   // in place: same thread, same slot
+                    else if constexpr (C::OUT0 == 1) I1::store(so, it, w0.v);
+                    else O0::store(so, it, w0.v);
+                }
+                if constexpr (O1::bytes > 0) stg_direct<O1::bytes>(g_out1 + (first + it) * O1::bytes, w1.v);
             }
         }
-        __syncthreads();  // (B) out-stage complete; in-stage free for the next prefetch
-        tile_store<O0, TILE, THREADS>(out_stage0, g_out0 + first * O0::bytes, nv, tid);
-        tile_store<O1, TILE, THREADS>(out_stage1, g_out1 + first * O1::bytes, nv, tid);
+        if constexpr (C::OUT0 >= 0) {
+            __syncthreads();  // (B) every result record of the tile is in shared memory
+            if constexpr (C::OUT0 == 0) tile_store<I0, TILE, THREADS>(so, g_out0 + first * O0::bytes, nv, tid);
+            else if constexpr (C::OUT0 == 1) tile_store<I1, TILE, THREADS>(so, g_out0 + first * O0::bytes, nv, tid);
+            else tile_store<O0, TILE, THREADS>(so, g_out0 + first * O0::bytes, nv, tid);
+        }
         if (++stage == STAGES) stage = 0;
     }
     cp_async_wait<0>();
+    // the last CTA to leave re-arms the scheduler for the next launch on this stream
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.sched + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // ---- SoA skeleton: element e of item b at base[e * stride + b]; perfectly
