@@ -85,9 +85,71 @@ static int prod_launch(const Shard& s, int P, int K, int Q, int nc, const void* 
     return ok();
 }
 
+// ---- outer product (prod 0, the rank-r (x) rank-s tensor product of BASELINE configs[3]) ----
+// Write-bound: 2 x 512 B in, 32 KiB out per 8x8 (x) 8x8 item.  A CTA walks items; thread
+// (tp, tq) keeps its B vector in registers and streams rows p = tp, tp+R, ... of the
+// P x Q result: one broadcast load of A[p], VEC multiplies, one 16-B streaming store.  No
+// index division in the loop; every warp store instruction covers 512 contiguous bytes.
+template <class T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+outer_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int Q, unsigned long long count) {
+    using R = Arith<T>;
+    using V = typename VecT<T, VEC>::type;
+    const int Qv = Q / VEC;
+    const int rows = THREADS / Qv;          // host guarantees THREADS % Qv == 0
+    const int tq = threadIdx.x % Qv, tp = threadIdx.x / Qv;
+    for (unsigned long long item = blockIdx.x; item < count; item += gridDim.x) {
+        const V bv = __ldg(reinterpret_cast<const V*>(B + item * (size_t)Q) + tq);
+        const T* a = A + item * (size_t)P;
+        T* c = C + item * (size_t)P * Q + (size_t)tq * VEC;
+        int p = tp;
+        for (; p + 3 * rows < P; p += 4 * rows) {
+            T av[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) av[u] = __ldg(a + p + u * rows);
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint4 o;
+                #pragma unroll
+                for (int j = 0; j < VEC; ++j) reinterpret_cast<T*>(&o)[j] = R::mul(av[u], reinterpret_cast<const T*>(&bv)[j]);
+                st_global_stream16(c + (size_t)(p + u * rows) * Q, o);
+            }
+        }
+        for (; p < P; p += rows) {
+            const T av = __ldg(a + p);
+            uint4 o;
+            #pragma unroll
+            for (int j = 0; j < VEC; ++j) reinterpret_cast<T*>(&o)[j] = R::mul(av, reinterpret_cast<const T*>(&bv)[j]);
+            st_global_stream16(c + (size_t)p * Q, o);
+        }
+    }
+}
+
+template <class T, int VEC>
+static int outer_launch(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
+    constexpr int THREADS = 256;
+    if (s.count == 0) return T5I_OK;
+    size_t cap = (size_t)sm_count() * 8;
+    int grid = (int)(s.count < cap ? s.count : cap);
+    outer_kernel<T, VEC, THREADS><<<grid, THREADS, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, Q, (unsigned long long)s.count);
+    return ok();
+}
+
+// the streaming outer-product kernel applies when a CTA's threads tile whole rows of the result
+static bool outer_ok(int P, int Q, int vec) {
+    if (Q % vec) return false;
+    const int Qv = Q / vec;
+    return Qv <= 256 && 256 % Qv == 0 && (long long)P * Qv >= 256;
+}
+
 int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
     if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
     if ((long long)P * Q > (1 << 28) || (long long)P * K > (1 << 28) || (long long)K * Q > (1 << 28)) return T5I_UNSUPPORTED;
+    if (nc == 0) {
+        if (dtype == T5D_F64 && outer_ok(P, Q, 2)) return outer_launch<double, 2>(s, P, Q, A, B, C);
+        if (dtype == T5D_I64 && outer_ok(P, Q, 2)) return outer_launch<long long, 2>(s, P, Q, A, B, C);
+        if (dtype == T5D_F32 && outer_ok(P, Q, 4)) return outer_launch<float, 4>(s, P, Q, A, B, C);
+    }
     switch (dtype) {
         case T5D_F64: return (Q % 2 == 0) ? prod_launch<double, 2>(s, P, K, Q, nc, A, B, C) : prod_launch<double, 1>(s, P, K, Q, nc, A, B, C);
         case T5D_I64: return (Q % 2 == 0) ? prod_launch<long long, 2>(s, P, K, Q, nc, A, B, C) : prod_launch<long long, 1>(s, P, K, Q, nc, A, B, C);

@@ -1,0 +1,173 @@
+{-# LANGUAGE DataKinds              #-}
+{-# LANGUAGE FlexibleContexts       #-}
+{-# LANGUAGE FlexibleInstances      #-}
+{-# LANGUAGE FunctionalDependencies #-}
+{-# LANGUAGE KindSignatures         #-}
+{-# LANGUAGE MultiParamTypeClasses  #-}
+{-# LANGUAGE ScopedTypeVariables    #-}
+{-# LANGUAGE TypeOperators          #-}
+
+--------------------------------------------------------------------------------
+-- |
+-- Module      :  Data.Tensor.LinearAlgebra
+--
+-- The linear-algebra classes the reference dropped in 0.2.0 (CHANGELOG.md:24-29:
+-- @MatrixProduct@, @TensorProduct@; @SquareMatrix@ named at :28), re-introduced
+-- with the semantics fixed in SURVEY.md §8a, and their instances for device
+-- batches ("Data.Tensor.Device").  Each method is ONE @ccall@ into libt5b200.so;
+-- shapes come from the type-level index list exactly as Data.Tensor.Vector takes
+-- them (@fromShape sing@, src/Data/Tensor/Vector.hs:189, :231, :363).
+--
+-- Results are in 'IO' because they allocate device buffers; a pure facade can wrap
+-- them with 'unsafePerformIO' since inputs are immutable (SURVEY.md §8b Ownership).
+--
+-- NOT TYPE-CHECKED here (no GHC in the image, SURVEY.md §0 F2).
+--------------------------------------------------------------------------------
+
+module Data.Tensor.LinearAlgebra
+    ( MatrixProduct(..), DotProduct(..), TensorProduct(..), Transpose(..)
+    , SquareMatrix(..), LinearSystem(..)
+    , dotSum
+    ) where
+
+import           Data.Proxy
+import           Data.Singletons
+import           Data.Word
+import           Foreign.C.Types       (CInt)
+import           Foreign.Marshal.Alloc (alloca)
+import           Foreign.Marshal.Array (withArrayLen)
+import           Foreign.Ptr
+import           Foreign.Storable
+
+import           Data.MultiIndex       (PI (..))
+import           Data.Tensor.Device
+import           Data.Tensor.Device.FFI
+
+infixl 7 .*.
+infixl 7 ⊗
+
+-- | @a .*. b@ contracts the last index of @a@ with the first of @b@.
+class MatrixProduct a b c | a b -> c where
+    (.*.) :: a -> b -> IO c
+
+-- | One scalar per pair: @fold_{i ascending} (acc + x_i * y_i)@, @acc0 = 0@.
+class DotProduct a s | a -> s where
+    dot :: a -> a -> IO s
+
+-- | @a ⊗ b@: the rank-(r+s) outer product, one multiply per component.
+class TensorProduct a b c | a b -> c where
+    (⊗) :: a -> b -> IO c
+
+-- | Full index reversal — @transpose = unRev . t0@ (src/Data/Indexable.hs:101-102).
+class Transpose a b | a -> b where
+    transpose :: a -> IO b
+
+-- | @det@; @inverse@ returns the per-item 'Maybe' as a status batch (0 = Just, 1 = Nothing).
+class SquareMatrix m s st | m -> s st where
+    det     :: m -> IO s
+    inverse :: m -> IO (m, st)
+
+-- | @solve a b@: unique-solution square systems (first-non-zero pivoting, SURVEY §8a).
+class LinearSystem m v st | m v -> st where
+    solve :: m -> v -> IO (v, st)
+
+dims :: [Int] -> [Word64]
+dims = map fromIntegral
+
+code :: forall e. DeviceElt e => Proxy e -> CInt
+code = dtypeCode
+
+-- matrix . matrix --------------------------------------------------------------
+instance (SingI i, SingI j, SingI k, DeviceElt e) =>
+         MatrixProduct (Batch '[i, j] e) (Batch '[j, k] e) (Batch '[i, k] e) where
+    a .*. b = do
+        let [m, kk] = batchShape a; [_, n] = batchShape b
+            Context h = batchCtx a
+        c <- newBatch (batchCtx a) (batchCount a)
+        unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
+            c_matmul h (code (Proxy :: Proxy e)) (fromIntegral m) (fromIntegral kk) (fromIntegral n) pa pb pc
+                >>= checkRC (batchCtx a) "t5_matmul"
+        return c
+
+-- matrix . vector --------------------------------------------------------------
+instance (SingI i, SingI j, DeviceElt e) =>
+         MatrixProduct (Batch '[i, j] e) (Batch '[j] e) (Batch '[i] e) where
+    a .*. x = do
+        let [m, kk] = batchShape a
+            Context h = batchCtx a
+        y <- newBatch (batchCtx a) (batchCount a)
+        unsafeWithBatch a $ \pa -> unsafeWithBatch x $ \px -> unsafeWithBatch y $ \py ->
+            c_matmul h (code (Proxy :: Proxy e)) (fromIntegral m) (fromIntegral kk) 1 pa px py
+                >>= checkRC (batchCtx a) "t5_matmul"
+        return y
+
+instance (SingI i, DeviceElt e) => DotProduct (Batch '[i] e) (Batch '[] e) where
+    dot x y = do
+        let [n] = batchShape x
+            Context h = batchCtx x
+        s <- newBatch (batchCtx x) (batchCount x)
+        unsafeWithBatch x $ \px -> unsafeWithBatch y $ \py -> unsafeWithBatch s $ \ps ->
+            c_dot h (code (Proxy :: Proxy e)) (fromIntegral n) px py ps >>= checkRC (batchCtx x) "t5_dot"
+        return s
+
+-- | Sum over the batch of 'dot' — the only operation with a cross-GPU exchange
+-- (1-element ncclAllReduce, SURVEY.md §8e).
+dotSum :: forall i e. (SingI i, DeviceElt e) => Batch '[i] e -> Batch '[i] e -> IO e
+dotSum x y = alloca $ \out -> do
+    let [n] = batchShape x
+        Context h = batchCtx x
+    unsafeWithBatch x $ \px -> unsafeWithBatch y $ \py ->
+        c_dot_sum h (code (Proxy :: Proxy e)) (fromIntegral n) px py (castPtr out)
+            >>= checkRC (batchCtx x) "t5_dot_sum"
+    peek out
+
+instance (SingI is, SingI js, SingI ks, DeviceElt e {- ks ~ is ++ js -}) =>
+         TensorProduct (Batch is e) (Batch js e) (Batch ks e) where
+    a ⊗ b = do
+        let da = batchShape a; db = batchShape b
+            Context h = batchCtx a
+        c <- newBatch (batchCtx a) (batchCount a)
+        withArrayLen (dims da) $ \ra pda -> withArrayLen (dims db) $ \rb pdb ->
+          unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
+            c_prod h (code (Proxy :: Proxy e)) (fromIntegral ra) pda (fromIntegral rb) pdb 0 pa pb pc
+                >>= checkRC (batchCtx a) "t5_prod"
+        return c
+
+instance (SingI is, SingI js, DeviceElt e {- js ~ Reverse is -}) =>
+         Transpose (Batch is e) (Batch js e) where
+    transpose a = do
+        let da = batchShape a
+            Context h = batchCtx a
+        t <- newBatch (batchCtx a) (batchCount a)
+        withArrayLen (dims da) $ \r pd -> unsafeWithBatch a $ \pa -> unsafeWithBatch t $ \pt ->
+            c_transpose h (code (Proxy :: Proxy e)) (fromIntegral r) pd pa pt >>= checkRC (batchCtx a) "t5_transpose"
+        return t
+
+instance (SingI i, DeviceElt e, Fractional e) =>
+         SquareMatrix (Batch '[i, i] e) (Batch '[] e) (Batch '[] Word8) where
+    det a = do
+        let [n, _] = batchShape a
+            Context h = batchCtx a
+        d <- newBatch (batchCtx a) (batchCount a)
+        unsafeWithBatch a $ \pa -> unsafeWithBatch d $ \pd ->
+            c_det h (code (Proxy :: Proxy e)) (fromIntegral n) pa pd >>= checkRC (batchCtx a) "t5_det"
+        return d
+    inverse a = do
+        let [n, _] = batchShape a
+            Context h = batchCtx a
+        x  <- newBatch (batchCtx a) (batchCount a)
+        st <- newStatusBatch (batchCtx a) (batchCount a)
+        unsafeWithBatch a $ \pa -> unsafeWithBatch x $ \px -> unsafeWithBatch st $ \ps ->
+            c_inverse h (code (Proxy :: Proxy e)) (fromIntegral n) pa px ps >>= checkRC (batchCtx a) "t5_inverse"
+        return (x, st)
+
+instance (SingI i, DeviceElt e, Fractional e) =>
+         LinearSystem (Batch '[i, i] e) (Batch '[i] e) (Batch '[] Word8) where
+    solve a b = do
+        let [n, _] = batchShape a
+            Context h = batchCtx a
+        x  <- newBatch (batchCtx a) (batchCount a)
+        st <- newStatusBatch (batchCtx a) (batchCount a)
+        unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch x $ \px -> unsafeWithBatch st $ \ps ->
+            c_solve h (code (Proxy :: Proxy e)) (fromIntegral n) 1 pa pb px ps >>= checkRC (batchCtx a) "t5_solve"
+        return (x, st)

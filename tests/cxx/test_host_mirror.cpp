@@ -1,0 +1,113 @@
+// C++ host-mirror test: drives tensor_b200/cxx/tensor_b200.hpp (type-indexed Batch API over
+// the C ABI) on a GPU and checks every result bit-for-bit against the CPU oracle
+// (oracle/libt5oracle.so).  Reads like the reference's own property tests
+// (tests/Tensor.hs): build values, apply the class methods, compare.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../tensor_b200/cxx/tensor_b200.hpp"
+
+extern "C" {
+int t5o_fill(int dtype, uint64_t seed, uint64_t op_id, uint64_t first_elem, size_t count, void* out);
+int t5o_matmul(int dtype, int m, int k, int n, size_t batch, const void* A, const void* B, void* C, int threads);
+int t5o_dot(int dtype, int n, size_t batch, const void* X, const void* Y, void* OUT, int threads);
+int t5o_transpose(int elem_bytes, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT);
+int t5o_prod(int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc, size_t batch,
+             const void* A, const void* B, void* C, int threads);
+int t5o_det(int dtype, int n, size_t batch, const void* A, void* OUT, int threads);
+int t5o_inverse(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* status, int threads);
+int t5o_solve(int dtype, int n, int nrhs, size_t batch, const void* A, const void* B, void* X, uint8_t* status, int threads);
+}
+
+static int failures = 0;
+template <class T>
+static void expect_bits(const char* what, const std::vector<T>& got, const std::vector<T>& want) {
+    bool ok = got.size() == want.size() && (got.empty() || !std::memcmp(got.data(), want.data(), got.size() * sizeof(T)));
+    std::printf("%-40s %s\n", what, ok ? "ok" : "MISMATCH");
+    if (!ok) ++failures;
+}
+template <class T> static std::vector<T> synth(int dt, uint64_t seed, uint64_t op, size_t n) {
+    std::vector<T> v(n);
+    t5o_fill(dt, seed, op, 0, n, v.data());
+    return v;
+}
+
+int main() {
+    using namespace t5;
+    const uint64_t SA = 0x5EED000000000001ull, SB = 0x5EED000000000002ull;
+    Context ctx({0});
+    const size_t n = 4099;
+
+    {   // (.*.) on 3x3 Double and Int64, matrix . vector on 4x4 Float
+        auto a = synth<double>(0, SA, 1, n * 9), b = synth<double>(0, SB, 1, n * 9);
+        auto A = Batch<double, 3, 3>::from_list(ctx, n, a), B = Batch<double, 3, 3>::from_list(ctx, n, b);
+        std::vector<double> want(n * 9);
+        t5o_matmul(0, 3, 3, 3, n, a.data(), b.data(), want.data(), 1);
+        expect_bits("Matrix 3 3 Double .*.", (A * B).to_list(), want);
+
+        auto ai = synth<int64_t>(2, SA, 1, n * 9), bi = synth<int64_t>(2, SB, 1, n * 9);
+        std::vector<int64_t> wi(n * 9);
+        t5o_matmul(2, 3, 3, 3, n, ai.data(), bi.data(), wi.data(), 1);
+        expect_bits("Matrix 3 3 Int64 .*. (wrap-around)",
+                    (Batch<int64_t, 3, 3>::from_list(ctx, n, ai) * Batch<int64_t, 3, 3>::from_list(ctx, n, bi)).to_list(), wi);
+
+        auto m = synth<float>(1, SA, 2, n * 16), x = synth<float>(1, SB, 2, n * 4);
+        std::vector<float> wy(n * 4), wd(n);
+        t5o_matmul(1, 4, 4, 1, n, m.data(), x.data(), wy.data(), 1);
+        auto M = Batch<float, 4, 4>::from_list(ctx, n, m);
+        auto X = Batch<float, 4>::from_list(ctx, n, x);
+        Batch<float, 4> Y = M * X;
+        expect_bits("Matrix 4 4 Float .*. Vector 4", Y.to_list(), wy);
+        t5o_dot(1, 4, n, x.data(), wy.data(), wd.data(), 1);
+        expect_bits("dot (Vector 4 Float)", dot(X, Y).to_list(), wd);
+    }
+    {   // transpose: shape reversed at the type level, (A^T)^T == A
+        auto a = synth<double>(0, SA, 3, n * 24);
+        auto A = Batch<double, 2, 3, 4>::from_list(ctx, n, a);
+        Batch<double, 4, 3, 2> T = transpose(A);
+        std::vector<double> want(n * 24);
+        const uint64_t d[3] = {2, 3, 4};
+        t5o_transpose(8, 3, d, n, a.data(), want.data());
+        expect_bits("transpose (Tensor [2,3,4])", T.to_list(), want);
+        expect_bits("transpose . transpose == id", transpose(T).to_list(), a);
+    }
+    {   // tensor product
+        auto a = synth<double>(0, SA, 4, n * 6), b = synth<double>(0, SB, 4, n * 4);
+        Batch<double, 2, 3, 2, 2> T = tensor_product(Batch<double, 2, 3>::from_list(ctx, n, a), Batch<double, 2, 2>::from_list(ctx, n, b));
+        std::vector<double> want(n * 24);
+        const uint64_t da[2] = {2, 3}, db[2] = {2, 2};
+        t5o_prod(0, 2, da, 2, db, 0, n, a.data(), b.data(), want.data(), 1);
+        expect_bits("tensor product [2,3] (x) [2,2]", T.to_list(), want);
+    }
+    {   // det / inverse / solve with planted swaps and singular items
+        auto a = synth<double>(0, SA, 5, n * 16), b = synth<double>(0, SB, 5, n * 4);
+        for (size_t i = 0; i < n; i += 16) a[i * 16] = 0.0;
+        for (size_t i = 0; i < n; i += 128) std::memcpy(&a[i * 16 + 4], &a[i * 16], 4 * sizeof(double));
+        auto A = Batch<double, 4, 4>::from_list(ctx, n, a);
+        std::vector<double> wd(n), wi(n * 16), wx(n * 4);
+        std::vector<uint8_t> ws(n), ws2(n);
+        t5o_det(0, 4, n, a.data(), wd.data(), 1);
+        expect_bits("det (Matrix 4 4 Double)", det(A).to_list(), wd);
+        t5o_inverse(0, 4, n, a.data(), wi.data(), ws.data(), 1);
+        auto [inv, st] = inverse(A);
+        expect_bits("inverse", inv.to_list(), wi);
+        expect_bits("inverse status (Maybe)", st.to_list(), ws);
+        t5o_solve(0, 4, 1, n, a.data(), b.data(), wx.data(), ws2.data(), 1);
+        auto [x, st2] = solve(A, Batch<double, 4>::from_list(ctx, n, b));
+        expect_bits("solve", x.to_list(), wx);
+        expect_bits("solve status", st2.to_list(), ws2);
+    }
+    {   // fromList length check
+        bool threw = false;
+        try { Batch<double, 3, 3>::from_list(ctx, 2, std::vector<double>(17)); } catch (const WrongListLength&) { threw = true; }
+        std::printf("%-40s %s\n", "fromList wrong length -> WrongListLength", threw ? "ok" : "MISSING");
+        if (!threw) ++failures;
+        bool unsup = false;
+        try { det(Batch<int64_t, 3, 3>(ctx, 4)); } catch (const Unsupported&) { unsup = true; }
+        std::printf("%-40s %s\n", "det on Int64 -> Unsupported", unsup ? "ok" : "MISSING");
+        if (!unsup) ++failures;
+    }
+    std::printf(failures ? "FAILED (%d)\n" : "ALL OK\n", failures);
+    return failures ? 1 : 0;
+}

@@ -1,0 +1,75 @@
+"""Multi-GPU tests of the single-process, multi-device context (the way one Haskell
+process drives 8 GPUs): the batch axis is sharded, no collective on the product /
+elimination paths, and the dot-sum partials meet in a 1-element NCCL all-reduce.
+Skipped when fewer than 2 GPUs are visible (run with `gpurun --gpus 2`)."""
+import numpy as np
+import pytest
+
+import oracle
+import tensor_b200 as tb
+from tensor_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.fixture(scope="module")
+def mctx():
+    n = ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    c = tb.Context(list(range(min(n, 8))))
+    yield c
+    c.close()
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view({8: np.uint64, 4: np.uint32, 1: np.uint8}[a.dtype.itemsize])
+
+
+@pytest.mark.parametrize("batch", [1, 255, 100003, 1 << 20])
+def test_sharded_ops_match_oracle(mctx, batch):
+    assert mctx.ndev >= 2
+    a = oracle.fill(oracle.F64, oracle.SEED_A, 1, batch * 9)
+    b = oracle.fill(oracle.F64, oracle.SEED_B, 1, batch * 9)
+    A, B = mctx.from_numpy(a, (3, 3)), mctx.from_numpy(b, (3, 3))
+    assert np.array_equal(bits(tb.matmul(A, B).to_numpy()), bits(oracle.matmul(a, b, 3, 3, 3, threads=8)))
+    assert np.array_equal(bits(tb.transpose(A).to_numpy()), bits(oracle.transpose(a, [3, 3])))
+    am = a.reshape(batch, 3, 3).copy()
+    oracle.plant_specials(am, 3, 0, swap_every=16, sing_every=128)
+    inv, st = tb.inverse(mctx.from_numpy(am, (3, 3)))
+    oinv, ost = oracle.inverse(am, 3, threads=8)
+    assert np.array_equal(st.to_numpy(), ost) and np.array_equal(bits(inv.to_numpy()), bits(oinv))
+
+
+def test_device_synthetic_stream_is_global(mctx):
+    batch = 300001
+    A = mctx.synthetic((4, 4), np.float32, batch, oracle.SEED_A, 3)
+    assert np.array_equal(bits(A.to_numpy().ravel()), bits(oracle.fill(oracle.F32, oracle.SEED_A, 3, batch * 16)))
+
+
+def test_dot_sum_allreduce(mctx):
+    batch, n = 1 << 20, 4
+    xi = oracle.fill(oracle.I64, oracle.SEED_A, 4, batch * n)
+    yi = oracle.fill(oracle.I64, oracle.SEED_B, 4, batch * n)
+    got = tb.dot_sum(mctx.from_numpy(xi, (n,)), mctx.from_numpy(yi, (n,)))
+    assert got == oracle.dot_sum(xi, yi, n)               # Int64: order-independent, bit-exact
+    assert _lib.lib().t5_dot_sum_used_nccl(mctx._h) == 1, "multi-device dot_sum must go through NCCL"
+    x = oracle.fill(oracle.F64, oracle.SEED_A, 4, batch * n)
+    y = oracle.fill(oracle.F64, oracle.SEED_B, 4, batch * n)
+    got = tb.dot_sum(mctx.from_numpy(x, (n,)), mctx.from_numpy(y, (n,)))
+    assert abs(got - oracle.dot_sum(x, y, n)) <= 1e-12 * np.sum(np.abs(x * y))
+
+
+def test_host_entry_multi_device(mctx):
+    batch = 500001
+    a = oracle.fill(oracle.F32, oracle.SEED_A, 14, batch * 16)
+    b = oracle.fill(oracle.F32, oracle.SEED_B, 14, batch * 16)
+    out = np.empty(batch * 16, dtype=np.float32)
+    tb.matmul_host(mctx, a, b, 4, 4, 4, out)
+    assert np.array_equal(bits(out), bits(oracle.matmul(a, b, 4, 4, 4, threads=8).ravel()))
