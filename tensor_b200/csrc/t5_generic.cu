@@ -92,13 +92,16 @@ static int prod_launch(const Shard& s, int P, int K, int Q, int nc, const void* 
 // index division in the loop; every warp store instruction covers 512 contiguous bytes.
 template <class T, int VEC, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-outer_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int Q, unsigned long long count) {
+outer_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int Q, unsigned long long count,
+             int items_per_cta) {
     using R = Arith<T>;
     using V = typename VecT<T, VEC>::type;
     const int Qv = Q / VEC;
     const int rows = THREADS / Qv;          // host guarantees THREADS % Qv == 0
     const int tq = threadIdx.x % Qv, tp = threadIdx.x / Qv;
-    for (unsigned long long item = blockIdx.x; item < count; item += gridDim.x) {
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * items_per_cta;
+    const unsigned long long i1 = i0 + items_per_cta < count ? i0 + items_per_cta : count;
+    for (unsigned long long item = i0; item < i1; ++item) {
         const V bv = __ldg(reinterpret_cast<const V*>(B + item * (size_t)Q) + tq);
         const T* a = A + item * (size_t)P;
         T* c = C + item * (size_t)P * Q + (size_t)tq * VEC;
@@ -129,9 +132,15 @@ template <class T, int VEC>
 static int outer_launch(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
     constexpr int THREADS = 256;
     if (s.count == 0) return T5I_OK;
-    size_t cap = (size_t)sm_count() * 8;
-    int grid = (int)(s.count < cap ? s.count : cap);
-    outer_kernel<T, VEC, THREADS><<<grid, THREADS, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, Q, (unsigned long long)s.count);
+    // a CTA streams ~512 KiB of results: long enough to amortise its launch, short enough that
+    // the hardware block scheduler evens out the SMs
+    long long per = (512ll << 10) / ((long long)P * Q * (long long)sizeof(T));
+    if (per < 1) per = 1;
+    if (per > 64) per = 64;
+    size_t blocks = (s.count + per - 1) / per;
+    if (blocks > 0x7fffffffull) return T5I_UNSUPPORTED;
+    outer_kernel<T, VEC, THREADS><<<(int)blocks, THREADS, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, Q,
+                                                                        (unsigned long long)s.count, (int)per);
     return ok();
 }
 

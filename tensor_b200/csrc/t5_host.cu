@@ -366,6 +366,7 @@ static Shard shard_of(const t5_ctx* c, const t5_buf* b, int g) {
 static int product_shard(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
     int r = T5I_NOT_SPECIALISED;
     if (nc != 0) r = small_matmul(s, dtype, P, K, Q, A, B, C);
+    if (r == T5I_NOT_SPECIALISED && nc != 0) r = mid_matmul(s, dtype, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && s.layout == T5L_AOS && dtype == T5D_F64 && nc != 0) r = dmma_matmul(s, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED) r = generic_prod(s, dtype, P, K, Q, nc, A, B, C);
     return r;

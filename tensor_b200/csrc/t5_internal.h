@@ -40,6 +40,9 @@ int small_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
 int small_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
 
+// ---- t5_mid_ops.cu: row-per-thread contractions for 0.25-4 KiB records (8x8, 16x16, ...) -----
+int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
+
 // ---- t5_generic.cu: any-shape kernels (AoS only) ---------------------------------
 // C[P x Q] = A[P x K] . B[K x Q] per item; ncontract == 0 -> single multiply.
 int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int ncontract, const void* A, const void* B, void* C);

@@ -1,0 +1,185 @@
+// Mid-size contractions (records of 0.25-4 KiB, e.g. the 8x8 . 8x8 `prod 1` of BASELINE
+// configs[3]): too big for one thread per item, far too small for tensor-core tiles.
+//
+// One thread per ROW of the result: P threads share an item.  A tile of G = THREADS/P items
+// is staged with the same cp.async ring + dynamic tile scheduler as t5_tile.cuh; a thread
+// keeps its A row and its C row in registers and reads B row by row from shared memory
+// (all P threads of an item read the same address: a broadcast, one wavefront per
+// quarter-warp).  A rows are padded to an odd number of 16-B chunks and B items likewise,
+// so neither the per-row nor the per-item accesses collide.  Results leave straight from
+// registers (a C row is >= 16 contiguous bytes per thread).
+//
+// Arithmetic: acc = 0; for k ascending: acc = acc + a[k]*b[k][q] - the oracle's order;
+// this TU is compiled with -fmad=false, so results are bit-identical to the oracle.
+#include "t5_device.cuh"
+#include "t5_internal.h"
+
+namespace t5 {
+namespace mid {
+
+struct Args {
+    const void* A;
+    const void* B;
+    void* C;
+    unsigned long long n_items;
+    unsigned long long* sched;
+};
+
+template <class T, int P, int K, int Q, int THREADS, int STAGES>
+struct Cfg {
+    static constexpr int G = THREADS / P;                       // items per tile
+    static constexpr int A_ROW = K * (int)sizeof(T);
+    static constexpr int A_CPR = A_ROW / 16;                    // chunks per A row
+    static constexpr int A_RS = A_ROW + ((A_CPR % 2 == 0) ? 16 : 0);
+    static constexpr int A_STAGE = G * P * A_RS;
+    static constexpr int B_ROW = Q * (int)sizeof(T);
+    static constexpr int B_BYTES = K * B_ROW;
+    static constexpr int B_CPI = B_BYTES / 16;
+    static constexpr int B_ITEM = B_BYTES + ((B_CPI % 2 == 0) ? 16 : 0);
+    static constexpr int B_STAGE = G * B_ITEM;
+    static constexpr int STAGE = A_STAGE + B_STAGE;
+    static constexpr int SMEM = STAGES * STAGE;
+    static_assert(A_ROW % 16 == 0 && B_ROW % 16 == 0, "rows must be multiples of 16 bytes");
+    static_assert(THREADS % P == 0 && THREADS % 32 == 0, "bad thread count");
+};
+
+template <class T, int P, int K, int Q, int THREADS, int STAGES>
+__global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
+    using C = Cfg<T, P, K, Q, THREADS, STAGES>;
+    using R = Arith<T>;
+    constexpr int G = C::G;
+    constexpr int VPR = 16 / (int)sizeof(T);   // elements per 16-B chunk
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long tile_q[STAGES];
+
+    const int tid = threadIdx.x;
+    const unsigned long long n_tiles = (a.n_items + G - 1) / G;
+    const unsigned char* gA = (const unsigned char*)a.A;
+    const unsigned char* gB = (const unsigned char*)a.B;
+    T* gC = (T*)a.C;
+
+    auto issue = [&](unsigned long long tile, int stage) {
+        if (tile < n_tiles) {
+            const unsigned long long first = tile * G;
+            const unsigned long long left = a.n_items - first;
+            const int nv = left < (unsigned long long)G ? (int)left : G;
+            unsigned char* sA = smem + stage * C::STAGE;
+            unsigned char* sB = sA + C::A_STAGE;
+            const unsigned char* srcA = gA + first * (size_t)(P * C::A_ROW);
+            const unsigned char* srcB = gB + first * (size_t)C::B_BYTES;
+            const int nchA = nv * P * C::A_CPR, nchB = nv * C::B_CPI;
+            for (int ch = tid; ch < nchA; ch += THREADS)
+                cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
+            for (int ch = tid; ch < nchB; ch += THREADS)
+                cp_async16(sB + (ch / C::B_CPI) * C::B_ITEM + (ch % C::B_CPI) * 16, srcB + (size_t)ch * 16);
+        }
+        cp_async_commit();
+    };
+
+    unsigned long long next_claim = 0;
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = atomicAdd(a.sched, 1ull);
+        next_claim = atomicAdd(a.sched, 1ull);
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(tile_q[s], s);
+
+    const int il = tid / P, r = tid % P;
+    int stage = 0;
+    while (true) {
+        const unsigned long long tile = tile_q[stage];
+        if (tile >= n_tiles) break;
+        int pf = stage + STAGES - 1; if (pf >= STAGES) pf -= STAGES;
+        if (tid == 0) tile_q[pf] = next_claim;
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(tile_q[pf], pf);
+        if (tid == 0) next_claim = atomicAdd(a.sched, 1ull);
+
+        const unsigned long long first = tile * G;
+        const unsigned long long left = a.n_items - first;
+        const int nv = left < (unsigned long long)G ? (int)left : G;
+        if (il < nv) {
+            const unsigned char* sA = smem + stage * C::STAGE + (il * P + r) * C::A_RS;
+            const unsigned char* sB = smem + stage * C::STAGE + C::A_STAGE + il * C::B_ITEM;
+            alignas(16) T av[K];
+            #pragma unroll
+            for (int c = 0; c < C::A_CPR; ++c) reinterpret_cast<uint4*>(av)[c] = reinterpret_cast<const uint4*>(sA)[c];
+            alignas(16) T acc[Q];
+            #pragma unroll
+            for (int q = 0; q < Q; ++q) acc[q] = R::zero();
+            #pragma unroll
+            for (int k = 0; k < K; ++k) {
+                alignas(16) T bv[Q];
+                #pragma unroll
+                for (int c = 0; c < Q / VPR; ++c) reinterpret_cast<uint4*>(bv)[c] = reinterpret_cast<const uint4*>(sB + k * C::B_ROW)[c];
+                #pragma unroll
+                for (int q = 0; q < Q; ++q) acc[q] = R::add(acc[q], R::mul(av[k], bv[q]));
+            }
+            T* dst = gC + ((first + il) * P + r) * (size_t)Q;
+            #pragma unroll
+            for (int c = 0; c < Q / VPR; ++c) st_global_stream16(dst + c * VPR, reinterpret_cast<const uint4*>(acc)[c]);
+        }
+        if (++stage == STAGES) stage = 0;
+    }
+    cp_async_wait<0>();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.sched + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+template <class T, int P, int K, int Q, int THREADS, int STAGES>
+static int launch(const Shard& s, const void* A, const void* B, void* Cc) {
+    using C = Cfg<T, P, K, Q, THREADS, STAGES>;
+    static_assert(C::SMEM <= 227 * 1024, "ring does not fit");
+    auto kern = rowprod_kernel<T, P, K, Q, THREADS, STAGES>;
+    static int grid_cap[T5_MAX_DEVICES] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
+    if (!grid_cap[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return T5I_CUDA;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int occ = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, C::SMEM) != cudaSuccess) return T5I_CUDA;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        grid_cap[dev] = (occ < 1 ? 1 : occ) * (sms < 1 ? T5_SM_COUNT_FALLBACK : sms);
+    }
+    if (s.count == 0) return T5I_OK;
+    if (!s.sched) return T5I_CUDA;
+    size_t tiles = (s.count + C::G - 1) / C::G;
+    int grid = (int)(tiles < (size_t)grid_cap[dev] ? tiles : (size_t)grid_cap[dev]);
+    Args a{A, B, Cc, (unsigned long long)s.count, s.sched};
+    kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
+}
+
+template <class T>
+static int dispatch(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
+    if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 256, 3>(s, A, B, C);
+    if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 256, 2>(s, A, B, C);
+    if constexpr (sizeof(T) == 8) {
+        if (m == 6 && k == 6 && n == 6) return launch<T, 6, 6, 6, 192, 3>(s, A, B, C);
+    }
+    return T5I_NOT_SPECIALISED;
+}
+
+}  // namespace mid
+
+int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C) {
+    if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
+    switch (dtype) {
+        case T5D_F64: return mid::dispatch<double>(s, m, k, n, A, B, C);
+        case T5D_F32: return mid::dispatch<float>(s, m, k, n, A, B, C);
+        case T5D_I64: return mid::dispatch<long long>(s, m, k, n, A, B, C);
+    }
+    return T5I_NOT_SPECIALISED;
+}
+
+}  // namespace t5

@@ -411,3 +411,12 @@ def test_dmma_identity_and_linearity(ctx):
     assert_bits_equal((A @ ctx.from_numpy(eye, (n, n))).to_numpy().ravel(), a, "A.I == A (exact: one non-zero term per sum)")
     two = ctx.from_numpy(2.0 * eye, (n, n))
     assert_bits_equal((A @ two).to_numpy().ravel(), 2.0 * a, "A.(2I) == 2A")
+
+
+@pytest.mark.parametrize("dc", ALL)
+@pytest.mark.parametrize("n", [6, 8, 16])
+def test_row_per_thread_contraction_bit_exact(ctx, dc, n):
+    for batch in (1, 31, 33, 1000, 4099):
+        a, b = inputs(dc, 18, batch, n * n, n * n)
+        C = tb.matmul(ctx.from_numpy(a, (n, n)), ctx.from_numpy(b, (n, n))).to_numpy()
+        assert_bits_equal(C, oracle.matmul(a, b, n, n, n), f"{n}x{n} batch {batch}")
