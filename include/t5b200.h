@@ -144,6 +144,43 @@ int t5_solve(t5_ctx* ctx, int dtype, int n, int nrhs, const t5_buf* A, const t5_
 int t5_zip(t5_ctx* ctx, int dtype, int op, const t5_buf* A, const t5_buf* B, t5_buf* C);
 int t5_scale(t5_ctx* ctx, int dtype, const void* scalar, const t5_buf* A, t5_buf* C);
 
+
+/* ---- structural operations ---------------------------------------------------
+ * The reshuffles of the IsTensor / MultiIndexable / Sliceable instances
+ * (src/Data/Tensor/Vector.hs:260-354, :400-463) as device gathers.  Each one is a
+ * pure index map, bit-exact for every dtype.  Indices and axes are 1-based like the
+ * reference's MultiIndex (src/Data/Tensor/Vector.hs:150-168). */
+
+/* append n x y (Vector.hs:322-335): concatenate along axis `axis`; dimsA and dimsB agree
+ * everywhere else. */
+int t5_append(t5_ctx* ctx, int dtype, int axis, int rank, const uint64_t* dimsA, const uint64_t* dimsB,
+              const t5_buf* A, const t5_buf* B, t5_buf* OUT);
+/* split n t (Vector.hs:336-354): the inverse of append; OUT1 gets the first `first_extent`
+ * entries of axis `axis`, OUT2 the rest. */
+int t5_split(t5_ctx* ctx, int dtype, int axis, int rank, const uint64_t* dims, uint64_t first_extent,
+             const t5_buf* IN, t5_buf* OUT1, t5_buf* OUT2);
+/* t `at` ix (Vector.hs:277-283): fix every index but the first (index has rank-1 entries):
+ * the column extractor.  OUT has dims[0] elements per item. */
+int t5_at(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, const uint64_t* index, const t5_buf* A, t5_buf* OUT);
+/* [i] `ta` t: fix the first index: the row extractor.  Follows the tested GADT semantics
+ * (src/Data/Tensor.hs:245-247); Vector.hs:284-288 is off by one. */
+int t5_ta(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, uint64_t index, const t5_buf* A, t5_buf* OUT);
+/* slice t sl (Vector.hs:400-429, :461-463): slicer[a] == 0 keeps axis a (Nothing),
+ * slicer[a] == k > 0 fixes it to k (Just k). */
+int t5_slice(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, const uint64_t* slicer, const t5_buf* A, t5_buf* OUT);
+/* General axis permutation: output axis a is input axis perm[a] (0-based).  concat,
+ * unConcat, rev and unRev of nested tensors (Vector.hs:260-301) are axis permutations of
+ * the flat [outer][inner] layout; transpose is the full reversal. */
+int t5_permute_axes(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, const int* perm, const t5_buf* A, t5_buf* OUT);
+/* Pure host function (no device): the gather table of a structural operation, i.e. for
+ * every output element offset the input element offset it copies.  op: 0 append (params =
+ * axis, dimsB[rank]; entries >= prod(dims) refer to B), 1 / 2 split first / second half
+ * (params = axis, first_extent), 3 at (params = index[rank-1]), 4 ta (params = i),
+ * 5 slice (params = slicer[rank]), 6 permute_axes (params = perm[rank]).
+ * Writes at most table_cap entries; *d_out receives the table length. */
+int t5_structural_table(int op, int rank, const uint64_t* dims, const uint64_t* params, int nparams,
+                        uint32_t* table_out, size_t table_cap, size_t* d_out);
+
 /* ---- host-buffer (end-to-end) entries --------------------------------------
  * Same operations on HOST AoS arrays: the call uploads chunks, runs the kernel
  * and downloads results, overlapping the three on separate streams.  This is

@@ -137,3 +137,67 @@ def shape(t):
         s.append(len(t))
         t = t[0]
     return s
+
+
+# ---- indexing, at / ta (Tensor.hs:203-206, :243-247) ---------------------------------
+def index(t, ix):
+    """t ! ix with a 1-based multi-index (list)."""
+    for i in ix:
+        t = t[i - 1]
+    return unT0(t)
+
+
+def at(t, ix):
+    # T1 t `at` is = T1 $ T0 (t ! is) ; (t :| ts) `at` is = T0 (t ! is) :| (ts `at` is)
+    return [T0(index(s, ix)) for s in t]
+
+
+def ta(i, t):
+    # OneCons _ `ta` (t :| _) = t ; HeadSucc is `ta` (_ :| ts) = is `ta` ts   (1-based i)
+    return t[i - 1]
+
+
+# ---- append / split (Tensor.hs:267-288) -----------------------------------------------
+def append(n, x, y):
+    if n == 1:          # A1 / A1S: walk down x's first axis, then cons onto y
+        return list(x) + list(y)
+    assert len(x) == len(y)
+    return [append(n - 1, a, b) for a, b in zip(x, y)]   # An: zip along the first axis
+
+
+def split(n, first_extent, t):
+    if n == 1:
+        return list(t[:first_extent]), list(t[first_extent:])
+    parts = [split(n - 1, first_extent, s) for s in t]
+    return [p[0] for p in parts], [p[1] for p in parts]
+
+
+# ---- slice (Tensor.hs:372-379) -----------------------------------------------------------
+def slice_(t, sl):
+    """sl: list with None (AllCons) or a 1-based index (OneConsSl / HeadSuccSl chain)."""
+    if not sl:
+        assert isinstance(t, T0)
+        return t
+    if sl[0] is None:
+        return [slice_(s, sl[1:]) for s in t]
+    return slice_(t[sl[0] - 1], sl[1:])
+
+
+def from_nested(outer_dims, inner_dims, flat):
+    """Row-major flat data -> outer tensor whose elements are inner tensors."""
+    di = 1
+    for d in inner_dims:
+        di *= d
+    n = 1
+    for d in outer_dims:
+        n *= d
+    inners = [from_list(inner_dims, flat[i * di:(i + 1) * di]) for i in range(n)]
+    return from_list(outer_dims, inners)
+
+
+def nested_to_list(t):
+    """Flatten a tensor of tensors (or of scalars) row-major."""
+    out = []
+    for e in to_list(t):
+        out.extend(to_list(e) if isinstance(e, (list, T0)) else [e])
+    return out

@@ -9,4 +9,5 @@ from .device import (Batch, Context, DeviceError, PinnedArray, TensorException, 
                      Unsupported, WrongListLength)
 from .linear_algebra import (det, dot, dot_sum, inverse, matmul, matmul_host, prod, scale,  # noqa: F401
                              solve, tensor_product, transpose, zip_with)
-from . import synthetic  # noqa: F401
+from . import structure, synthetic  # noqa: F401
+from .structure import Nested  # noqa: F401

@@ -54,6 +54,13 @@ SIGNATURES = {
     "t5_solve": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "t5_zip": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_scale": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "t5_append": (_i, [_vp, _i, _i, _i, _u64p, _u64p, _vp, _vp, _vp]),
+    "t5_split": (_i, [_vp, _i, _i, _i, _u64p, _u64, _vp, _vp, _vp]),
+    "t5_at": (_i, [_vp, _i, _i, _u64p, _u64p, _vp, _vp]),
+    "t5_ta": (_i, [_vp, _i, _i, _u64p, _u64, _vp, _vp]),
+    "t5_slice": (_i, [_vp, _i, _i, _u64p, _u64p, _vp, _vp]),
+    "t5_permute_axes": (_i, [_vp, _i, _i, _u64p, ctypes.POINTER(ctypes.c_int), _vp, _vp]),
+    "t5_structural_table": (_i, [_i, _i, _u64p, _u64p, _i, ctypes.POINTER(ctypes.c_uint32), _sz, _szp]),
     "t5_matmul_host": (_i, [_vp, _i, _i, _i, _i, _sz, _vp, _vp, _vp]),
     "t5_timer_begin": (_i, [_vp]),
     "t5_timer_end": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -100,3 +107,20 @@ def partition(batch: int, ndev: int, g: int):
     if rc != OK:
         raise ValueError(lib().t5_strerror(rc).decode())
     return f.value, c.value
+
+
+ST_APPEND, ST_SPLIT_FIRST, ST_SPLIT_SECOND, ST_AT, ST_TA, ST_SLICE, ST_PERMUTE = range(7)
+
+
+def structural_table(op: int, dims, params):
+    """Pure host function of the library: the gather table of a structural operation."""
+    n = ctypes.c_size_t()
+    L = lib()
+    rc = L.t5_structural_table(op, len(dims), u64_array(dims), u64_array(params), len(params), None, 0, ctypes.byref(n))
+    if rc != OK:
+        raise ValueError(L.t5_strerror(rc).decode())
+    buf = (ctypes.c_uint32 * max(1, n.value))()
+    rc = L.t5_structural_table(op, len(dims), u64_array(dims), u64_array(params), len(params), buf, n.value, ctypes.byref(n))
+    if rc != OK:
+        raise ValueError(L.t5_strerror(rc).decode())
+    return [int(buf[i]) for i in range(n.value)]

@@ -173,38 +173,82 @@ int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const v
 // =====================================================================================
 template <class T, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-permute_kernel(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ perm, unsigned d,
-               unsigned long long count, int G) {
+gather_kernel(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ table, unsigned d_in,
+              unsigned d_out, unsigned long long count, int G) {
     for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
         const unsigned long long left = count - g0;
         const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
-        const unsigned total = gc * d;
+        const unsigned total = gc * d_out;
         for (unsigned l = threadIdx.x; l < total; l += THREADS) {
-            const unsigned il = l / d;
-            const unsigned i = l - il * d;
-            const size_t base = (size_t)(g0 + il) * d;
-            out[base + i] = __ldg(in + base + __ldg(perm + i));
+            const unsigned il = l / d_out;
+            const unsigned i = l - il * d_out;
+            out[(size_t)(g0 + il) * d_out + i] = __ldg(in + (size_t)(g0 + il) * d_in + __ldg(table + i));
         }
     }
 }
 
-int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O) {
+// two-source gather (append): table value v < dA reads A[v], else B[v - dA]
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+gather2_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, const uint32_t* __restrict__ table,
+               unsigned dA, unsigned dB, unsigned d_out, unsigned long long count, int G) {
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
+        const unsigned total = gc * d_out;
+        for (unsigned l = threadIdx.x; l < total; l += THREADS) {
+            const unsigned il = l / d_out;
+            const unsigned i = l - il * d_out;
+            const unsigned v = __ldg(table + i);
+            out[(size_t)(g0 + il) * d_out + i] = v < dA ? __ldg(A + (size_t)(g0 + il) * dA + v) : __ldg(B + (size_t)(g0 + il) * dB + (v - dA));
+        }
+    }
+}
+
+static int gather_geometry(size_t count, size_t d_out, int threads, int* G) {
+    int g = (int)((threads * 16 + d_out - 1) / d_out);
+    if (g < 1) g = 1;
+    *G = g;
+    size_t units = (count + g - 1) / g;
+    size_t cap = (size_t)sm_count() * 8;
+    return (int)(units < cap ? units : cap);
+}
+
+int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, const uint32_t* table_dev, const void* A, void* O) {
     constexpr int THREADS = 256;
     if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
-    if (s.count == 0) return T5I_OK;
-    if (d > (1u << 28)) return T5I_UNSUPPORTED;
-    int G = (int)((THREADS * 16 + d - 1) / d);
-    if (G < 1) G = 1;
-    size_t units = (s.count + G - 1) / G;
-    size_t cap = (size_t)sm_count() * 8;
-    int grid = (int)(units < cap ? units : cap);
+    if (s.count == 0 || d_out == 0) return T5I_OK;
+    if (d_in > (1u << 28) || d_out > (1u << 28)) return T5I_UNSUPPORTED;
+    int G;
+    const int grid = gather_geometry(s.count, d_out, THREADS, &G);
     if (elem_bytes == 8)
-        permute_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (unsigned long long*)O, perm_dev, (unsigned)d, s.count, G);
+        gather_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (unsigned long long*)O, table_dev, (unsigned)d_in, (unsigned)d_out, s.count, G);
     else if (elem_bytes == 4)
-        permute_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)A, (unsigned*)O, perm_dev, (unsigned)d, s.count, G);
+        gather_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)A, (unsigned*)O, table_dev, (unsigned)d_in, (unsigned)d_out, s.count, G);
     else
         return T5I_UNSUPPORTED;
     return ok();
+}
+
+int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d_out, const uint32_t* table_dev,
+                    const void* A, const void* B, void* O) {
+    constexpr int THREADS = 256;
+    if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
+    if (s.count == 0 || d_out == 0) return T5I_OK;
+    if (dA + dB > (1u << 28) || d_out > (1u << 28)) return T5I_UNSUPPORTED;
+    int G;
+    const int grid = gather_geometry(s.count, d_out, THREADS, &G);
+    if (elem_bytes == 8)
+        gather2_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (const unsigned long long*)B, (unsigned long long*)O, table_dev, (unsigned)dA, (unsigned)dB, (unsigned)d_out, s.count, G);
+    else if (elem_bytes == 4)
+        gather2_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)A, (const unsigned*)B, (unsigned*)O, table_dev, (unsigned)dA, (unsigned)dB, (unsigned)d_out, s.count, G);
+    else
+        return T5I_UNSUPPORTED;
+    return ok();
+}
+
+int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O) {
+    return generic_gather(s, elem_bytes, d, d, perm_dev, A, O);
 }
 
 // =====================================================================================

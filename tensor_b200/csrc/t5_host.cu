@@ -778,3 +778,237 @@ int t5_plant_specials(t5_buf* b, int n, uint64_t swap_every, uint64_t sing_every
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+// ---- structural operations: affine gather tables + dispatch -----------------------------------
+// Every structural op of the flat-vector backend (Vector.hs:260-354, :400-429) maps an output
+// multi-index to an input offset affinely: in = base + sum_a oidx[a] * stride[a].
+namespace {
+struct View { std::vector<uint64_t> dims, stride; uint64_t base = 0; };
+
+std::vector<uint64_t> row_major_strides(const std::vector<uint64_t>& d) {
+    std::vector<uint64_t> s(d.size(), 1);
+    for (int a = (int)d.size() - 2; a >= 0; --a) s[a] = s[a + 1] * d[a + 1];
+    return s;
+}
+uint64_t prod_of(const std::vector<uint64_t>& d) { uint64_t p = 1; for (auto x : d) p *= x; return p; }
+
+void view_table(const View& v, uint64_t add, std::vector<uint32_t>& out) {
+    const int r = (int)v.dims.size();
+    const uint64_t n = prod_of(v.dims);
+    std::vector<uint64_t> idx(r, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t off = v.base;
+        for (int a = 0; a < r; ++a) off += idx[a] * v.stride[a];
+        out.push_back((uint32_t)(off + add));
+        for (int a = r - 1; a >= 0; --a) { if (++idx[a] < v.dims[a]) break; idx[a] = 0; }
+    }
+}
+
+// returns T5_OK and fills table (+ out dims) or an error code
+int build_structural(int op, const std::vector<uint64_t>& dims, const std::vector<uint64_t>& prm,
+                     std::vector<uint32_t>& table, std::vector<uint64_t>& out_dims) {
+    const int r = (int)dims.size();
+    for (auto x : dims) if (x == 0 || x > (1u << 28)) return T5_ERR_SHAPE;
+    if (prod_of(dims) > (1u << 28)) return T5_ERR_SHAPE;
+    const auto st = row_major_strides(dims);
+    table.clear();
+    switch (op) {
+        case 0: {  // append: params = axis, dimsB...
+            if ((int)prm.size() != 1 + r || r < 1) return T5_ERR_SHAPE;
+            const int ax = (int)prm[0] - 1;
+            if (ax < 0 || ax >= r) return T5_ERR_SHAPE;
+            std::vector<uint64_t> db(prm.begin() + 1, prm.end());
+            for (int a = 0; a < r; ++a) if (a != ax && db[a] != dims[a]) return T5_ERR_SHAPE;
+            if (db[ax] == 0 || prod_of(db) + prod_of(dims) > (1u << 28)) return T5_ERR_SHAPE;
+            const auto sb = row_major_strides(db);
+            out_dims = dims; out_dims[ax] = dims[ax] + db[ax];
+            const uint64_t dA = prod_of(dims), n = prod_of(out_dims);
+            std::vector<uint64_t> idx(r, 0);
+            for (uint64_t i = 0; i < n; ++i) {
+                uint64_t off = 0;
+                if (idx[ax] < dims[ax]) { for (int a = 0; a < r; ++a) off += idx[a] * st[a]; }
+                else { for (int a = 0; a < r; ++a) off += (a == ax ? idx[a] - dims[ax] : idx[a]) * sb[a]; off += dA; }
+                table.push_back((uint32_t)off);
+                for (int a = r - 1; a >= 0; --a) { if (++idx[a] < out_dims[a]) break; idx[a] = 0; }
+            }
+            return T5_OK;
+        }
+        case 1: case 2: {  // split halves: params = axis, first_extent
+            if (prm.size() != 2 || r < 1) return T5_ERR_SHAPE;
+            const int ax = (int)prm[0] - 1;
+            if (ax < 0 || ax >= r || prm[1] == 0 || prm[1] >= dims[ax]) return T5_ERR_SHAPE;
+            View v; v.dims = dims; v.stride = st;
+            if (op == 1) v.dims[ax] = prm[1];
+            else { v.dims[ax] = dims[ax] - prm[1]; v.base = prm[1] * st[ax]; }
+            out_dims = v.dims;
+            view_table(v, 0, table);
+            return T5_OK;
+        }
+        case 3: {  // at: params = index over the tail axes
+            if (r < 1 || (int)prm.size() != r - 1) return T5_ERR_SHAPE;
+            View v; v.dims = {dims[0]}; v.stride = {st[0]};
+            for (int a = 1; a < r; ++a) { if (prm[a - 1] < 1 || prm[a - 1] > dims[a]) return T5_ERR_SHAPE; v.base += (prm[a - 1] - 1) * st[a]; }
+            out_dims = v.dims;
+            view_table(v, 0, table);
+            return T5_OK;
+        }
+        case 4: {  // ta: params = i
+            if (r < 1 || prm.size() != 1 || prm[0] < 1 || prm[0] > dims[0]) return T5_ERR_SHAPE;
+            View v; v.dims.assign(dims.begin() + 1, dims.end()); v.stride.assign(st.begin() + 1, st.end());
+            v.base = (prm[0] - 1) * st[0];
+            out_dims = v.dims;
+            view_table(v, 0, table);
+            return T5_OK;
+        }
+        case 5: {  // slice: params = slicer
+            if ((int)prm.size() != r) return T5_ERR_SHAPE;
+            View v;
+            for (int a = 0; a < r; ++a) {
+                if (prm[a] == 0) { v.dims.push_back(dims[a]); v.stride.push_back(st[a]); }
+                else { if (prm[a] > dims[a]) return T5_ERR_SHAPE; v.base += (prm[a] - 1) * st[a]; }
+            }
+            out_dims = v.dims;
+            view_table(v, 0, table);
+            return T5_OK;
+        }
+        case 6: {  // permute_axes: params = perm
+            if ((int)prm.size() != r) return T5_ERR_SHAPE;
+            std::vector<int> seen(r, 0);
+            View v;
+            for (int a = 0; a < r; ++a) {
+                if (prm[a] >= (uint64_t)r || seen[prm[a]]++) return T5_ERR_SHAPE;
+                v.dims.push_back(dims[prm[a]]); v.stride.push_back(st[prm[a]]);
+            }
+            out_dims = v.dims;
+            view_table(v, 0, table);
+            return T5_OK;
+        }
+    }
+    return T5_ERR_INVALID;
+}
+}  // namespace
+
+// table cached per (op, dims, params) and per device
+static int structural_table_dev(t5_ctx* c, int g, int op, const std::vector<uint64_t>& dims, const std::vector<uint64_t>& prm,
+                                uint32_t** dev_table, size_t* d_out, std::vector<uint64_t>* out_dims) {
+    std::vector<uint64_t> key{0xFFFFFFFFull, (uint64_t)op, (uint64_t)dims.size()};
+    key.insert(key.end(), dims.begin(), dims.end());
+    key.insert(key.end(), prm.begin(), prm.end());
+    std::vector<uint32_t> table;
+    std::vector<uint64_t> od;
+    int rc = build_structural(op, dims, prm, table, od);     // cheap relative to a launch; also validates
+    if (rc != T5_OK) return rc;
+    auto it = c->perm_cache.find(key);
+    if (it == c->perm_cache.end()) it = c->perm_cache.emplace(key, std::vector<uint32_t*>(T5_MAX_DEVICES, nullptr)).first;
+    if (!it->second[g]) {
+        uint32_t* p = nullptr;
+        CU(c, cudaMalloc(&p, (table.size() ? table.size() : 1) * 4));
+        CU(c, cudaMemcpy(p, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+        it->second[g] = p;
+    }
+    *dev_table = it->second[g];
+    *d_out = table.size();
+    if (out_dims) *out_dims = od;
+    return T5_OK;
+}
+
+static int structural_unary(t5_ctx* c, int dtype, int op, int rank, const uint64_t* dims, const std::vector<uint64_t>& prm,
+                            const t5_buf* A, t5_buf* OUT, const char* what) {
+    if (!c || rank < 0 || rank > 16 || (rank && !dims)) return T5_ERR_INVALID;
+    const int es = dtype_size(dtype);
+    if (es != 4 && es != 8) return T5_ERR_UNSUPPORTED;
+    std::vector<uint64_t> dv(dims, dims + rank);
+    std::vector<uint32_t> t0; std::vector<uint64_t> od;
+    CHECK(build_structural(op, dv, prm, t0, od));
+    const size_t d_in = prod_of(dv), d_out = t0.size();
+    CHECK(check(c, A, dtype, d_in, nullptr));
+    CHECK(check(c, OUT, dtype, d_out, A));
+    if (OUT == A) return T5_ERR_INVALID;
+    if (A->layout != T5_AOS) return T5_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        uint32_t* tab; size_t n;
+        CHECK(structural_table_dev(c, g, op, dv, prm, &tab, &n, nullptr));
+        int r = generic_gather(shard_of(c, A, g), es, d_in, d_out, tab, A->ptr[g], OUT->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, what);
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int t5_structural_table(int op, int rank, const uint64_t* dims, const uint64_t* params, int nparams,
+                        uint32_t* table_out, size_t table_cap, size_t* d_out) {
+    if (rank < 0 || rank > 16 || (rank && !dims) || nparams < 0 || (nparams && !params) || !d_out) return T5_ERR_INVALID;
+    std::vector<uint64_t> dv(dims, dims + rank), pv(params, params + nparams);
+    std::vector<uint32_t> table; std::vector<uint64_t> od;
+    int rc = build_structural(op, dv, pv, table, od);
+    if (rc != T5_OK) return rc;
+    *d_out = table.size();
+    if (table_out) for (size_t i = 0; i < table.size() && i < table_cap; ++i) table_out[i] = table[i];
+    return T5_OK;
+}
+
+int t5_append(t5_ctx* c, int dtype, int axis, int rank, const uint64_t* dimsA, const uint64_t* dimsB,
+              const t5_buf* A, const t5_buf* B, t5_buf* OUT) {
+    if (!c || rank < 1 || rank > 16 || !dimsA || !dimsB) return T5_ERR_INVALID;
+    const int es = dtype_size(dtype);
+    if (es != 4 && es != 8) return T5_ERR_UNSUPPORTED;
+    std::vector<uint64_t> da(dimsA, dimsA + rank), prm{(uint64_t)axis};
+    prm.insert(prm.end(), dimsB, dimsB + rank);
+    std::vector<uint32_t> t0; std::vector<uint64_t> od;
+    CHECK(build_structural(0, da, prm, t0, od));
+    const size_t dA = prod_of(da), dB = prod_of(std::vector<uint64_t>(dimsB, dimsB + rank));
+    CHECK(check(c, A, dtype, dA, nullptr));
+    CHECK(check(c, B, dtype, dB, A));
+    CHECK(check(c, OUT, dtype, dA + dB, A));
+    if (OUT == A || OUT == B) return T5_ERR_INVALID;
+    if (A->layout != T5_AOS) return T5_ERR_UNSUPPORTED;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        uint32_t* tab; size_t n;
+        CHECK(structural_table_dev(c, g, 0, da, prm, &tab, &n, nullptr));
+        int r = generic_gather2(shard_of(c, A, g), es, dA, dB, dA + dB, tab, A->ptr[g], B->ptr[g], OUT->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_append");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_split(t5_ctx* c, int dtype, int axis, int rank, const uint64_t* dims, uint64_t first_extent,
+             const t5_buf* IN, t5_buf* OUT1, t5_buf* OUT2) {
+    if (OUT1 == OUT2) return T5_ERR_INVALID;
+    std::vector<uint64_t> prm{(uint64_t)axis, first_extent};
+    CHECK(structural_unary(c, dtype, 1, rank, dims, prm, IN, OUT1, "t5_split"));
+    return structural_unary(c, dtype, 2, rank, dims, prm, IN, OUT2, "t5_split");
+}
+
+int t5_at(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const uint64_t* index, const t5_buf* A, t5_buf* OUT) {
+    if (rank < 1 || (rank > 1 && !index)) return T5_ERR_INVALID;
+    return structural_unary(c, dtype, 3, rank, dims, std::vector<uint64_t>(index, index + (rank - 1)), A, OUT, "t5_at");
+}
+
+int t5_ta(t5_ctx* c, int dtype, int rank, const uint64_t* dims, uint64_t index, const t5_buf* A, t5_buf* OUT) {
+    return structural_unary(c, dtype, 4, rank, dims, std::vector<uint64_t>{index}, A, OUT, "t5_ta");
+}
+
+int t5_slice(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const uint64_t* slicer, const t5_buf* A, t5_buf* OUT) {
+    if (rank < 0 || (rank && !slicer)) return T5_ERR_INVALID;
+    return structural_unary(c, dtype, 5, rank, dims, std::vector<uint64_t>(slicer, slicer + rank), A, OUT, "t5_slice");
+}
+
+int t5_permute_axes(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const int* perm, const t5_buf* A, t5_buf* OUT) {
+    if (rank < 0 || (rank && !perm)) return T5_ERR_INVALID;
+    std::vector<uint64_t> p;
+    for (int a = 0; a < rank; ++a) { if (perm[a] < 0) return T5_ERR_SHAPE; p.push_back((uint64_t)perm[a]); }
+    return structural_unary(c, dtype, 6, rank, dims, p, A, OUT, "t5_permute_axes");
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -48,6 +48,9 @@ int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, co
 int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int ncontract, const void* A, const void* B, void* C);
 // out[b][i] = in[b][perm[i]], perm resident on the device (d entries)
 int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O);
+// out[b][i] = in[b][table[i]] with d_in != d_out allowed (structural gathers); gather2: two sources (append)
+int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, const uint32_t* table_dev, const void* A, void* O);
+int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d_out, const uint32_t* table_dev, const void* A, const void* B, void* O);
 int generic_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs, const void* A, const void* B, void* X, void* status);
 int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, const void* B, void* C);
