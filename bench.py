@@ -53,13 +53,22 @@ WORKLOADS = {
                                  desc="1Mi 8x8 (x) 8x8 -> 8^4 Double tensor products (configs[3])"),
     "prod1_8x8_f64_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=1, batch=1 << 20, bytes=1536, bound="hbm",
                              desc="1Mi 8x8 . 8x8 Double contractions (configs[3], n=1)"),
+    "matmul4x4_f32_soa_16M": dict(op="matmul", dtype="f32", m=4, k=4, n=4, batch=1 << 24, bytes=192, bound="hbm", layout="soa",
+                                  desc="16Mi pairs of 4x4 Float matrices, .*., SoA device layout"),
+    "inverse4_f64_soa_4M": dict(op="inverse", dtype="f64", n=4, batch=1 << 22, bytes=257, bound="hbm", layout="soa",
+                                desc="4Mi 4x4 Double inverse, SoA device layout"),
+    "append_3x3_3x1_f64_4M": dict(op="append", dtype="f64", dims_a=(3, 3), dims_b=(3, 1), axis=2, batch=1 << 22, bytes=192, bound="hbm",
+                                  desc="4Mi augmented matrices [A | b] via append (structural gather)"),
+    "transpose8x8x8_f64_1M": dict(op="transpose", dtype="f64", dims=(8, 8, 8), batch=1 << 20, bytes=8192, bound="hbm",
+                                  desc="1Mi rank-3 8x8x8 Double transposes (any-rank gather)"),
     "matmul128_f64_64K": dict(op="matmul", dtype="f64", m=128, k=128, n=128, batch=1 << 16, bytes=393216, flops=4194304, bound="tensor",
                               desc="64Ki 128x128 Double .*. on FP64 tensor cores (configs[4])"),
 }
 HEADLINE = "matmul4x4_f32_16M"
 EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpose4x4_f32_16M", "matvec4_f32_16M",
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
-          "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M"]
+          "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
+          "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 
@@ -151,43 +160,51 @@ class Step:
         dt = NPD[w["dtype"]]
         B = w["batch"]
         op = w["op"]
-        syn = lambda shape, seed, opid: ctx.synthetic(shape, dt, B, seed, opid)  # noqa: E731
+        lay = tb.SOA if w.get("layout") == "soa" else tb.AOS
+        syn = lambda shape, seed, opid: ctx.synthetic(shape, dt, B, seed, opid, lay)  # noqa: E731
+        empty = lambda shape, d=dt: ctx.empty(shape, d, B, lay)  # noqa: E731
         h = ctx._h
         code = tb.device.DTYPE_OF[np.dtype(dt)]
         if op == "matmul":
             m, k, n = w["m"], w["k"], w["n"]
             self.a, self.b = syn((m, k), SEED_A, 1), syn((k, n), SEED_B, 1)
-            self.c = ctx.empty((m, n), dt, B)
+            self.c = empty((m, n))
             self.run = lambda: L.t5_matmul(h, code, m, k, n, self.a._h, self.b._h, self.c._h)
         elif op == "dot":
             n = w["n"]
             self.a, self.b = syn((n,), SEED_A, 2), syn((n,), SEED_B, 2)
-            self.c = ctx.empty((), dt, B)
+            self.c = empty(())
             self.run = lambda: L.t5_dot(h, code, n, self.a._h, self.b._h, self.c._h)
         elif op == "transpose":
             dims = w["dims"]
             self.a = syn(dims, SEED_A, 3)
-            self.c = ctx.empty(tuple(reversed(dims)), dt, B)
+            self.c = empty(tuple(reversed(dims)))
             da = tb._lib.u64_array(dims)
             self.run = lambda: L.t5_transpose(h, code, len(dims), da, self.a._h, self.c._h)
         elif op == "prod":
             da, db, nc = w["dims_a"], w["dims_b"], w["nc"]
             self.a, self.b = syn(da, SEED_A, 4), syn(db, SEED_B, 4)
-            self.c = ctx.empty(tuple(da[: len(da) - nc]) + tuple(db[nc:]), dt, B)
+            self.c = empty(tuple(da[: len(da) - nc]) + tuple(db[nc:]))
             ua, ub = tb._lib.u64_array(da), tb._lib.u64_array(db)
             self.run = lambda: L.t5_prod(h, code, len(da), ua, len(db), ub, nc, self.a._h, self.b._h, self.c._h)
+        elif op == "append":
+            da, db, ax = w["dims_a"], w["dims_b"], w["axis"]
+            self.a, self.b = syn(da, SEED_A, 6), syn(db, SEED_B, 6)
+            self.c = empty(tuple(x + y if k == ax - 1 else x for k, (x, y) in enumerate(zip(da, db))))
+            ua, ub = tb._lib.u64_array(da), tb._lib.u64_array(db)
+            self.run = lambda: L.t5_append(h, code, ax, len(da), ua, ub, self.a._h, self.b._h, self.c._h)
         elif op in ("det", "inverse", "solve"):
             n = w["n"]
             self.a = syn((n, n), SEED_A, 5).plant_specials(1024, 65536)
             if op == "det":
-                self.c = ctx.empty((), dt, B)
+                self.c = empty(())
                 self.run = lambda: L.t5_det(h, code, n, self.a._h, self.c._h)
             elif op == "inverse":
-                self.c, self.s = ctx.empty((n, n), dt, B), ctx.empty((), np.uint8, B)
+                self.c, self.s = empty((n, n)), empty((), np.uint8)
                 self.run = lambda: L.t5_inverse(h, code, n, self.a._h, self.c._h, self.s._h)
             else:
                 self.b = syn((n,), SEED_B, 5)
-                self.c, self.s = ctx.empty((n,), dt, B), ctx.empty((), np.uint8, B)
+                self.c, self.s = empty((n,)), empty((), np.uint8)
                 self.run = lambda: L.t5_solve(h, code, n, 1, self.a._h, self.b._h, self.c._h, self.s._h)
         else:
             raise ValueError(op)
@@ -385,7 +402,7 @@ def ours(args):
             ww = WORKLOADS[name]
             try:
                 st = StepRing(ctx, tb, ww)
-                t = time_steps(ctx, tb, st, 20, 3) / 20
+                t = time_steps(ctx, tb, st, 30, 5) / 30
                 r = roofline(ww, t, peaks)
                 others[name] = {"matrices_per_s": ww["batch"] / (t * 1e-3), "ms": t, "achieved": r["achieved"],
                                 "unit": r["unit"], "frac": r["frac"], "operand_sets": len(st.sets)}

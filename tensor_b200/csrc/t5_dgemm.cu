@@ -64,28 +64,41 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(Args p) {
     }
     __syncthreads();
 
-    // producer cursor: (sequence number of the tile inside this CTA, K chunk)
+    // producer cursor: (sequence number of the tile inside this CTA, K chunk) and the global
+    // addresses of that chunk; the tile -> (item, tm, tn) division runs once per tile only
     unsigned pf_n = 0; int pf_kc = 0;
-    auto issue = [&](int stage) {
+    bool pf_valid = false;
+    const double* pf_A = nullptr;
+    const double* pf_B = nullptr;
+    auto pf_locate = [&]() {
         const unsigned long long tile = tile_q[pf_n & 3];
-        if (tile < n_tiles) {
+        pf_valid = tile < n_tiles;
+        if (pf_valid) {
             const unsigned long long item = tile / tiles_per_item;
             const int rem = (int)(tile - item * tiles_per_item);
             const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
-            const double* Ag = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM) * p.K + pf_kc * BK;
-            const double* Bg = p.B + item * (size_t)p.K * p.N + (size_t)(pf_kc * BK) * p.N + tn * BN;
+            // this thread's first 16-B chunk of the A block (row = tid/16, col chunk = tid%16) and of the B block
+            pf_A = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + (tid >> 4)) * p.K + (tid & 15) * 2;
+            pf_B = p.B + item * (size_t)p.K * p.N + (size_t)(tid >> 6) * p.N + tn * BN + (tid & 63) * 2;
+        }
+    };
+    const unsigned a_dst = (tid >> 4) * (A_LD * 8) + (tid & 15) * 16;
+    const unsigned b_dst = (tid >> 6) * (B_LD * 8) + (tid & 63) * 16;
+    const size_t a_step = (size_t)(THREADS / 16) * p.K;     // 16 rows further down per pass
+    const size_t b_step = (size_t)(THREADS / 64) * p.N;     // 4 rows further down per pass
+    auto issue = [&](int stage) {
+        if (pf_kc == 0) pf_locate();
+        if (pf_valid) {
             unsigned char* As = smem + stage * STAGE;
             unsigned char* Bs = As + A_STAGE;
             #pragma unroll
-            for (int i = 0; i < (BM * BK / 2) / THREADS; ++i) {       // 16-B chunks of the A block: 128 rows x 16
-                const int ch = tid + i * THREADS, row = ch >> 4, c16 = ch & 15;
-                cp_async16(As + row * (A_LD * 8) + c16 * 16, Ag + (size_t)row * p.K + c16 * 2);
-            }
+            for (int i = 0; i < (BM * BK / 2) / THREADS; ++i)       // A block: 128 rows x 16 chunks, 16 rows per pass
+                cp_async16(As + a_dst + i * (THREADS / 16) * (A_LD * 8), pf_A + i * a_step);
             #pragma unroll
-            for (int i = 0; i < (BK * BN / 2) / THREADS; ++i) {       // B block: 32 rows x 64 chunks
-                const int ch = tid + i * THREADS, row = ch >> 6, c16 = ch & 63;
-                cp_async16(Bs + row * (B_LD * 8) + c16 * 16, Bg + (size_t)row * p.N + c16 * 2);
-            }
+            for (int i = 0; i < (BK * BN / 2) / THREADS; ++i)       // B block: 32 rows x 64 chunks, 4 rows per pass
+                cp_async16(Bs + b_dst + i * (THREADS / 64) * (B_LD * 8), pf_B + i * b_step);
+            pf_A += BK;                      // next K chunk: 32 columns right in A,
+            pf_B += (size_t)BK * p.N;        // 32 rows down in B
         }
         cp_async_commit();
         if (++pf_kc == kch) { pf_kc = 0; ++pf_n; }

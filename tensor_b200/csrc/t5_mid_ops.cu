@@ -11,7 +11,7 @@
 //
 // Arithmetic: acc = 0; for k ascending: acc = acc + a[k]*b[k][q] - the oracle's order;
 // this TU is compiled with -fmad=false, so results are bit-identical to the oracle.
-#include "t5_device.cuh"
+#include "t5_tile.cuh"
 #include "t5_internal.h"
 
 namespace t5 {
@@ -23,6 +23,7 @@ struct Args {
     void* C;
     unsigned long long n_items;
     unsigned long long* sched;
+    unsigned claim;
 };
 
 template <class T, int P, int K, int Q, int THREADS, int STAGES>
@@ -77,10 +78,11 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
     };
 
     unsigned long long next_claim = 0;
+    TileClaimer claimer;
     if (tid == 0) {
         #pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = atomicAdd(a.sched, 1ull);
-        next_claim = atomicAdd(a.sched, 1ull);
+        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = claimer.next(a.sched, a.claim);
+        next_claim = claimer.next(a.sched, a.claim);
     }
     __syncthreads();
     #pragma unroll
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         issue(tile_q[pf], pf);
-        if (tid == 0) next_claim = atomicAdd(a.sched, 1ull);
+        if (tid == 0) next_claim = claimer.next(a.sched, a.claim);
 
         const unsigned long long first = tile * G;
         const unsigned long long left = a.n_items - first;
@@ -155,7 +157,9 @@ static int launch(const Shard& s, const void* A, const void* B, void* Cc) {
     if (!s.sched) return T5I_CUDA;
     size_t tiles = (s.count + C::G - 1) / C::G;
     int grid = (int)(tiles < (size_t)grid_cap[dev] ? tiles : (size_t)grid_cap[dev]);
-    Args a{A, B, Cc, (unsigned long long)s.count, s.sched};
+    size_t claim = tiles / ((size_t)grid * 16);
+    claim = claim < 1 ? 1 : (claim > 8 ? 8 : claim);
+    Args a{A, B, Cc, (unsigned long long)s.count, s.sched, (unsigned)claim};
     kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }

@@ -35,7 +35,10 @@ static int launch_tile(const Shard& s, const void* in0, const void* in1, void* o
     if (!s.sched) return T5I_CUDA;
     size_t tiles = (s.count + C::TILE - 1) / C::TILE;
     int grid = (int)(tiles < (size_t)grid_cap[dev] ? tiles : (size_t)grid_cap[dev]);
-    TileArgs a{in0, in1, out0, out1, (unsigned long long)s.count, s.sched};
+    // several tiles per scheduler atomic once every CTA has plenty of tiles (keeps the tail short)
+    size_t claim = tiles / ((size_t)grid * 16);
+    claim = claim < 1 ? 1 : (claim > 8 ? 8 : claim);
+    TileArgs a{in0, in1, out0, out1, (unsigned long long)s.count, s.sched, (unsigned)claim};
     kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }

@@ -84,6 +84,20 @@ struct TileArgs {
     void* out1;
     unsigned long long n_items;
     unsigned long long* sched;  // [0] next tile, [1] finished CTAs; both zero between launches
+    unsigned claim;             // tiles claimed per atomic (>= 1)
+};
+
+// Tile claims: one atomicAdd on the scheduler word hands out `claim` consecutive tiles.  A
+// single L2 address sustains only ~300 M atomics/s chip-wide (measured: the 16Mi-record dot
+// kernel was capped at exactly that tile rate), so large batches claim several tiles at once.
+struct TileClaimer {
+    unsigned long long base = 0;
+    unsigned left = 0;
+    __device__ __forceinline__ unsigned long long next(unsigned long long* sched, unsigned claim) {
+        if (left == 0) { base = atomicAdd(sched, (unsigned long long)claim); left = claim; }
+        --left;
+        return base++;
+    }
 };
 
 // ---- cooperative tile movement ------------------------------------------------
@@ -194,10 +208,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
 
     // prologue: claim and start the first STAGES-1 tiles; keep one more claim in flight
     unsigned long long next_claim = 0;
+    TileClaimer claimer;
     if (tid == 0) {
         #pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = atomicAdd(a.sched, 1ull);
-        next_claim = atomicAdd(a.sched, 1ull);
+        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = claimer.next(a.sched, a.claim);
+        next_claim = claimer.next(a.sched, a.claim);
     }
     __syncthreads();
     #pragma unroll
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();  // (A) this tile has landed for every thread; stage pf is free; tile_q[pf] visible
         issue(tile_q[pf], pf);
-        if (tid == 0) next_claim = atomicAdd(a.sched, 1ull);  // consumed next iteration: latency hidden
+        if (tid == 0) next_claim = claimer.next(a.sched, a.claim);  // consumed next iteration: latency hidden
 
         const unsigned long long first = tile * TILE;
         const unsigned long long left = a.n_items - first;

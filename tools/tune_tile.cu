@@ -33,7 +33,10 @@ void run(const char* name, size_t n, int alg_bytes, bool flush) {
     if (occ < 1) return;
     size_t tiles = (n + C::TILE - 1) / C::TILE;
     int grid = (int)std::min<size_t>(tiles, (size_t)occ * 148);
-    TileArgs a{g_in0, g_in1, g_out0, g_out1, n, g_sched};
+    size_t claim = tiles / ((size_t)grid * 16);
+    claim = claim < 1 ? 1 : (claim > 8 ? 8 : claim);
+    if (getenv("T5_CLAIM")) claim = atoi(getenv("T5_CLAIM"));
+    TileArgs a{g_in0, g_in1, g_out0, g_out1, n, g_sched, (unsigned)claim};
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int i = 0; i < 3; ++i) kern<<<grid, THREADS, C::SMEM>>>(a);
@@ -66,7 +69,7 @@ void sweep(const char* name, size_t n, int alg_bytes, bool flush) {
 #define CFG(T, I, S) run<Op, T, I, S, 1>(name, n, alg_bytes, flush);
     CFG(64, 1, 2) CFG(64, 1, 3) CFG(64, 1, 4) CFG(64, 2, 3)
     CFG(128, 1, 2) CFG(128, 1, 3) CFG(128, 1, 4) CFG(128, 2, 2) CFG(128, 2, 3)
-    CFG(256, 1, 2) CFG(256, 1, 3) CFG(256, 1, 4) CFG(256, 2, 2) CFG(256, 2, 3)
+    CFG(256, 1, 2) CFG(256, 1, 3) CFG(256, 1, 4) CFG(256, 2, 2) CFG(256, 2, 3) CFG(256, 4, 2) CFG(256, 4, 3)
 #undef CFG
 }
 
