@@ -63,7 +63,7 @@ static int launch_soa(cudaStream_t st, const void* in0, const void* in1, void* o
 // tools/tune_tile.cu -> profiles/r01_tune_tile.csv (fractions of the measured HBM copy
 // peak in DESIGN.md).  Streaming ops want >= 16-64 KB of input per tile; the
 // elimination ops are latency-bound on FP64 division chains and want more, smaller CTAs.
-template <int T, int I, int S> struct G { static constexpr int threads = T, ipt = I, stages = S; };
+template <int T, int I, int S, int B = 1> struct G { static constexpr int threads = T, ipt = I, stages = S, min_blocks = B; };
 template <class Op> struct Geo {
     static constexpr int in_bytes = Op::In0::bytes + Op::In1::bytes;
     using type = std::conditional_t<(in_bytes <= 32), G<256, 2, 3>,
@@ -73,17 +73,17 @@ template <class Op> struct Geo {
 template <class T> struct Geo<DetOp<T, 3>> { using type = G<256, 1, 2>; };
 template <class T> struct Geo<DetOp<T, 4>> { using type = G<128, 2, 2>; };
 template <class T> struct Geo<InverseOp<T, 2>> { using type = G<128, 1, 2>; };
-template <class T> struct Geo<InverseOp<T, 3>> { using type = G<128, 1, 2>; };
-template <class T> struct Geo<InverseOp<T, 4>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 3>> { using type = G<128, 1, 2, 6>; };   // register cap 80: 6 CTAs/SM
+template <class T> struct Geo<InverseOp<T, 4>> { using type = G<64, 1, 2, 8>; };    // register cap 128: 8 CTAs/SM (r01_tune_elim_v3.csv)
 template <class T, int N, int R> struct Geo<SolveOp<T, N, R>> {
-    using type = std::conditional_t<(R == 1), G<256, 1, 2>, std::conditional_t<(N <= 3), G<128, 1, 2>, G<64, 1, 2>>>;
+    using type = std::conditional_t<(R == 1), G<256, 1, 2>, std::conditional_t<(N <= 3), G<128, 1, 2, 6>, G<64, 1, 2, 8>>>;
 };
 
 template <class Op>
 static int launch_op(const Shard& s, const void* in0, const void* in1, void* out0, void* out1) {
     if (s.layout == T5L_SOA) return launch_soa<Op>(s.stream, in0, in1, out0, out1, s.count, s.soa_stride);
     using g = typename Geo<Op>::type;
-    return launch_tile<Op, g::threads, g::ipt, g::stages, 1>(s, in0, in1, out0, out1);
+    return launch_tile<Op, g::threads, g::ipt, g::stages, g::min_blocks>(s, in0, in1, out0, out1);
 }
 
 template <class T>

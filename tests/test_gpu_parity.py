@@ -244,6 +244,52 @@ def test_elimination_residuals(ctx):
     assert np.all(r <= 1e-12 * scale * np.maximum(cond, 1.0))
 
 
+def _canon_nan(x):
+    """NaN sign / payload is not part of the contract (x86 and the GPU generate different
+    default NaNs); everything else is compared bit for bit."""
+    x = np.array(x, copy=True)
+    x[np.isnan(x)] = np.nan
+    return x
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_elimination_extreme_operands_bit_exact(ctx, n, layout):
+    """The Double elimination kernels divide through a shared reciprocal with the compiler's
+    own fast-path test; operands outside the fast path (denormal, huge, zero, Inf, NaN
+    quotients, numerators or pivots) must take the full division and still match the
+    oracle's IEEE `/` exactly."""
+    rng = np.random.default_rng(1234 + n)
+    batch = 6000
+    a = rng.uniform(-1, 1, size=(batch, n, n))
+    b = rng.uniform(-1, 1, size=(batch, n))
+    # per-matrix and per-entry power-of-two scalings over the whole exponent range
+    e_item = rng.integers(-1060, 1020, size=(batch, 1, 1))
+    a = np.ldexp(a, np.where(rng.random((batch, 1, 1)) < 0.6, e_item, 0))
+    e_ent = rng.integers(-1074, 1023, size=(batch, n, n))
+    a = np.where(rng.random((batch, n, n)) < 0.15, np.ldexp(a, e_ent), a)
+    b = np.ldexp(b, np.where(rng.random((batch, 1)) < 0.5, rng.integers(-1070, 1020, size=(batch, 1)), 0))
+    specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308,
+                         1.7976931348623157e308, -1.7976931348623157e308])
+    hit = rng.random((batch, n, n)) < 0.04
+    a = np.where(hit, rng.choice(specials, size=(batch, n, n)), a)
+    hitb = rng.random((batch, n)) < 0.04
+    b = np.where(hitb, rng.choice(specials, size=(batch, n)), b)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        A = ctx.from_numpy(a, (n, n), layout)
+        assert_bits_equal(_canon_nan(tb.det(A).to_numpy()), _canon_nan(oracle.det(a, n)), f"det{n} extremes")
+        inv, st = tb.inverse(A)
+        oinv, ost = oracle.inverse(a, n)
+        assert np.array_equal(st.to_numpy(), ost)
+        assert_bits_equal(_canon_nan(inv.to_numpy()), _canon_nan(oinv), f"inverse{n} extremes")
+        X, st = tb.solve(A, ctx.from_numpy(b, (n,), layout))
+        ox, ost = oracle.solve(a, b, n, 1)
+        assert np.array_equal(st.to_numpy(), ost)
+        assert_bits_equal(_canon_nan(X.to_numpy()), _canon_nan(ox.reshape(batch, n)), f"solve{n} extremes")
+
+
 # ---- regression fixtures through the device ----------------------------------------
 def test_la_regression_fixtures_on_device(ctx):
     with open(os.path.join(GOLD, "la_regression.json")) as f:

@@ -59,7 +59,7 @@ void run(const char* name, size_t n, int alg_bytes, bool flush) {
     }
     CK(cudaGetLastError());
     double us = total / iters * 1e3;
-    printf("%s,%zu,%d,%d,%d,%d,%d,%.2f,%.1f\n", name, n, THREADS, IPT, STAGES, occ, C::SMEM, us, alg_bytes * (double)n / us / 1e3);
+    printf("%s,%zu,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", name, n, THREADS, IPT, STAGES, MINB, occ, C::SMEM, us, alg_bytes * (double)n / us / 1e3);
     fflush(stdout);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
@@ -73,6 +73,19 @@ void sweep(const char* name, size_t n, int alg_bytes, bool flush) {
 #undef CFG
 }
 
+// register-capped variants (__launch_bounds__ min blocks) for the latency-bound elimination ops
+template <class Op>
+void sweep_minb(const char* name, size_t n, int alg_bytes, bool flush) {
+    run<Op, 64, 1, 2, 8>(name, n, alg_bytes, flush);
+    run<Op, 64, 1, 2, 10>(name, n, alg_bytes, flush);
+    run<Op, 64, 1, 3, 8>(name, n, alg_bytes, flush);
+    run<Op, 128, 1, 2, 4>(name, n, alg_bytes, flush);
+    run<Op, 128, 1, 2, 5>(name, n, alg_bytes, flush);
+    run<Op, 128, 1, 2, 6>(name, n, alg_bytes, flush);
+    run<Op, 256, 1, 2, 2>(name, n, alg_bytes, flush);
+    run<Op, 256, 1, 2, 3>(name, n, alg_bytes, flush);
+}
+
 int main(int argc, char** argv) {
     const size_t NMAX = 1ull << 24;
     const size_t BYTES = NMAX * 128;  // biggest stream: 16Mi x 128 B
@@ -80,7 +93,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&g_flush, FLUSH)); CK(cudaMalloc(&g_sched, 16)); CK(cudaMemset(g_sched, 0, 16));
     const char* which = argc > 1 ? argv[1] : "all";
     auto want = [&](const char* s) { return !strcmp(which, "all") || strstr(s, which); };
-    printf("op,n,threads,ipt,stages,ctas_per_sm,smem,us,GBps\n");
+    printf("op,n,threads,ipt,stages,minb,ctas_per_sm,smem,us,GBps\n");
     // float-typed inputs
     fill<<<2048, 256>>>((double*)g_in0, BYTES / 8, 1); fill<<<2048, 256>>>((double*)g_in1, BYTES / 8, 1); CK(cudaDeviceSynchronize());
     if (want("matmul4x4_f32")) sweep<MatmulOp<float, 4, 4, 4>>("matmul4x4_f32", 1 << 24, 192, false);
@@ -92,11 +105,11 @@ int main(int argc, char** argv) {
     if (want("matmul3x3_f64_1M")) sweep<MatmulOp<double, 3, 3, 3>>("matmul3x3_f64_1M", 1 << 20, 216, true);
     if (want("matmul3x3_f64_16M")) sweep<MatmulOp<double, 3, 3, 3>>("matmul3x3_f64_16M", 1 << 24, 216, false);
     if (want("matmul3x3_i64")) sweep<MatmulOp<long long, 3, 3, 3>>("matmul3x3_i64_16M", 1 << 24, 216, false);
-    if (want("det3_f64")) sweep<DetOp<double, 3>>("det3_f64_4M", 1 << 22, 80, true);
-    if (want("det4_f64")) sweep<DetOp<double, 4>>("det4_f64_4M", 1 << 22, 136, true);
-    if (want("inverse3_f64")) sweep<InverseOp<double, 3>>("inverse3_f64_4M", 1 << 22, 145, true);
-    if (want("inverse4_f64")) sweep<InverseOp<double, 4>>("inverse4_f64_4M", 1 << 22, 257, false);
-    if (want("solve3_f64")) sweep<SolveOp<double, 3, 1>>("solve3_f64_4M", 1 << 22, 121, true);
-    if (want("solve4_f64")) sweep<SolveOp<double, 4, 1>>("solve4_f64_4M", 1 << 22, 193, false);
+    if (want("det3_f64")) { sweep<DetOp<double, 3>>("det3_f64_4M", 1 << 22, 80, true); sweep_minb<DetOp<double, 3>>("det3_f64_4M", 1 << 22, 80, true); }
+    if (want("det4_f64")) { sweep<DetOp<double, 4>>("det4_f64_4M", 1 << 22, 136, true); sweep_minb<DetOp<double, 4>>("det4_f64_4M", 1 << 22, 136, true); }
+    if (want("inverse3_f64")) { sweep<InverseOp<double, 3>>("inverse3_f64_4M", 1 << 22, 145, true); sweep_minb<InverseOp<double, 3>>("inverse3_f64_4M", 1 << 22, 145, true); }
+    if (want("inverse4_f64")) { sweep<InverseOp<double, 4>>("inverse4_f64_4M", 1 << 22, 257, false); sweep_minb<InverseOp<double, 4>>("inverse4_f64_4M", 1 << 22, 257, false); }
+    if (want("solve3_f64")) { sweep<SolveOp<double, 3, 1>>("solve3_f64_4M", 1 << 22, 121, true); sweep_minb<SolveOp<double, 3, 1>>("solve3_f64_4M", 1 << 22, 121, true); }
+    if (want("solve4_f64")) { sweep<SolveOp<double, 4, 1>>("solve4_f64_4M", 1 << 22, 193, false); sweep_minb<SolveOp<double, 4, 1>>("solve4_f64_4M", 1 << 22, 193, false); }
     return 0;
 }
