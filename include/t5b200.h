@@ -138,6 +138,23 @@ int t5_det(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
 int t5_inverse(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* STATUS);
 int t5_solve(t5_ctx* ctx, int dtype, int n, int nrhs, const t5_buf* A, const t5_buf* B, t5_buf* X, t5_buf* STATUS);
 
+/* The rest of the old SquareMatrix class (CHANGELOG.md:28-29 names polyEval and minPoly;
+ * tr / charPoly per SURVEY.md §8f-4).  No reference code exists for them: the arithmetic is
+ * specified in oracle/t5_oracle.cpp (parity unpinned).
+ *   t5_trace     OUT[b] = fold_{i asc} (acc + A[b,i,i]) from 0.  All element types.
+ *   t5_poly_eval OUT_b = c0 I + c1 A_b + .. + cd A_b^d by Horner (R = cd I; R = R.A + cj I);
+ *                `coeffs` is a HOST array of ncoef elements of dtype, low order first, shared
+ *                by the whole batch; ncoef == 0 gives the zero matrix.  All element types.
+ *   t5_char_poly OUT has n+1 elements per item: the coefficients of det(xI - A), low order
+ *                first, OUT[n] = 1 (Faddeev-LeVerrier).  Double / Float.
+ *   t5_min_poly  OUT as for t5_char_poly, zero above the degree; DEGREE (T5_U8) receives the
+ *                degree: the first exact linear dependency among I, A, A^2, ..; degree n
+ *                returns the characteristic polynomial.  Double / Float, n <= 6, AoS. */
+int t5_trace(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
+int t5_poly_eval(t5_ctx* ctx, int dtype, int n, const void* coeffs, int ncoef, const t5_buf* A, t5_buf* OUT);
+int t5_char_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
+int t5_min_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* DEGREE);
+
 /* Element-wise vector-space operations (Functor/Applicative instances,
  * src/Data/Tensor/Vector.hs:180-190, :250-251: liftA2 (+), liftA2 (-), scalar *).
  * op: 0 = a + b, 1 = a - b, 2 = a * b (Hadamard); t5_scale multiplies by *scalar. */

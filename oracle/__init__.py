@@ -57,6 +57,10 @@ def lib() -> ctypes.CDLL:
         L.t5o_det.argtypes = [i32, i32, sz, vp, vp, i32]
         L.t5o_inverse.argtypes = [i32, i32, sz, vp, vp, vp, i32]
         L.t5o_solve.argtypes = [i32, i32, i32, sz, vp, vp, vp, vp, i32]
+        L.t5o_trace.argtypes = [i32, i32, sz, vp, vp, i32]
+        L.t5o_poly_eval.argtypes = [i32, i32, vp, i32, sz, vp, vp, i32]
+        L.t5o_char_poly.argtypes = [i32, i32, sz, vp, vp, i32]
+        L.t5o_min_poly.argtypes = [i32, i32, sz, vp, vp, vp, i32]
         L.t5o_fill.argtypes = [i32, u64, u64, u64, sz, vp]
         L.t5o_plant_specials.argtypes = [i32, i32, u64, sz, vp, u64, u64]
         _lib = L
@@ -167,6 +171,44 @@ def solve(a: np.ndarray, b: np.ndarray, n: int, nrhs: int, threads: int = 1):
     status = np.empty((batch,), dtype=np.uint8)
     _chk(lib().t5o_solve(DTYPE_OF[a.dtype], n, nrhs, batch, _ptr(a), _ptr(b), _ptr(out), _ptr(status), threads))
     return out, status
+
+
+# ---- tr / polyEval / charPoly / minPoly (parity unpinned) ------
+def trace(a: np.ndarray, n: int, threads: int = 1) -> np.ndarray:
+    a = _c(a)
+    batch = a.size // (n * n)
+    out = np.empty((batch,), dtype=a.dtype)
+    _chk(lib().t5o_trace(DTYPE_OF[a.dtype], n, batch, _ptr(a), _ptr(out), threads))
+    return out
+
+
+def poly_eval(a: np.ndarray, coeffs, n: int, threads: int = 1) -> np.ndarray:
+    """coeffs are low order first: c0 I + c1 A + ..."""
+    a = _c(a)
+    c = np.ascontiguousarray(coeffs, dtype=a.dtype)
+    batch = a.size // (n * n)
+    out = np.empty((batch, n, n), dtype=a.dtype)
+    _chk(lib().t5o_poly_eval(DTYPE_OF[a.dtype], n, _ptr(c), int(c.size), batch, _ptr(a), _ptr(out), threads))
+    return out
+
+
+def char_poly(a: np.ndarray, n: int, threads: int = 1) -> np.ndarray:
+    """[batch, n+1] coefficients of det(xI - A), low order first, last one = 1."""
+    a = _c(a)
+    batch = a.size // (n * n)
+    out = np.empty((batch, n + 1), dtype=a.dtype)
+    _chk(lib().t5o_char_poly(DTYPE_OF[a.dtype], n, batch, _ptr(a), _ptr(out), threads))
+    return out
+
+
+def min_poly(a: np.ndarray, n: int, threads: int = 1):
+    """([batch, n+1] coefficients low order first, zero above the degree; [batch] degrees)."""
+    a = _c(a)
+    batch = a.size // (n * n)
+    out = np.empty((batch, n + 1), dtype=a.dtype)
+    deg = np.empty((batch,), dtype=np.uint8)
+    _chk(lib().t5o_min_poly(DTYPE_OF[a.dtype], n, batch, _ptr(a), _ptr(out), _ptr(deg), threads))
+    return out, deg
 
 
 # ---- synthetic inputs (SURVEY §8d) ------------------------------------------

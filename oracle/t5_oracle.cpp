@@ -190,6 +190,107 @@ static uint8_t inverse_item(const T* A, T* X, int n) {
     return solve_item(A, I, X, n, n);
 }
 
+// ---------------------------------------------------------------------------
+// The rest of the old SquareMatrix surface (CHANGELOG.md:28-29 names `polyEval`
+// and `minPoly`; `tr` / `charPoly` per SURVEY.md §8f-4).  No reference code exists
+// for any of them: the definitions below ARE the specification
+// — **PARITY UNPINNED**.
+// ---------------------------------------------------------------------------
+
+// tr: fold_{i ascending} (acc + A[i,i]), acc0 = 0.
+template <class T>
+static T trace_item(const T* A, int n) {
+    using R = Arith<T>;
+    T acc = R::zero();
+    for (int i = 0; i < n; ++i) acc = R::add(acc, A[i * n + i]);
+    return acc;
+}
+
+// polyEval A [c0, c1, .., cd] = c0 I + c1 A + .. + cd A^d by Horner's rule:
+// R = cd I; for j = d-1 .. 0: R = (R .*. A) with cj added to the diagonal.
+// The product is the .*. fold of a6.  No coefficients -> the zero matrix.
+template <class T>
+static void poly_eval_item(const T* A, const T* c, int ncoef, T* OUT, int n) {
+    using R = Arith<T>;
+    T Rm[16 * 16], Tm[16 * 16];
+    for (int i = 0; i < n * n; ++i) Rm[i] = R::zero();
+    if (ncoef > 0)
+        for (int i = 0; i < n; ++i) Rm[i * n + i] = c[ncoef - 1];
+    for (int j = ncoef - 2; j >= 0; --j) {
+        matmul_item(Rm, A, Tm, n, n, n);
+        for (int i = 0; i < n; ++i) Tm[i * n + i] = R::add(Tm[i * n + i], c[j]);
+        std::memcpy(Rm, Tm, sizeof(T) * n * n);
+    }
+    std::memcpy(OUT, Rm, sizeof(T) * n * n);
+}
+
+// charPoly: coefficients c[0..n] (low order first, c[n] = 1) of det(x I - A) by
+// Faddeev-LeVerrier: M = I; for k = 1..n: AM = A .*. M; c[n-k] = negate (tr AM / k);
+// M = AM with c[n-k] added to the diagonal.  Fractional element types only.
+template <class T>
+static void char_poly_item(const T* A, T* c, int n) {
+    T M[16 * 16], AM[16 * 16];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) M[i * n + j] = (i == j) ? T(1) : T(0);
+    c[n] = T(1);
+    for (int k = 1; k <= n; ++k) {
+        matmul_item(A, M, AM, n, n, n);
+        const T ck = -(trace_item(AM, n) / T(k));
+        c[n - k] = ck;
+        for (int i = 0; i < n; ++i) AM[i * n + i] = AM[i * n + i] + ck;
+        std::memcpy(M, AM, sizeof(T) * n * n);
+    }
+}
+
+// minPoly: the monic polynomial of least degree m with p(A) = 0, found as the first
+// EXACT linear dependency among vec(I), vec(A), vec(A^2), .. (powers by P_m = P_{m-1} .*. A).
+// Candidate m is reduced against the echelon basis built from the lower powers, in
+// insertion order: f = v[p_i] / b_i[p_i]; v -= f b_i (every position, then v[p_i] := 0);
+// the combination g (g = e_m initially) follows: g -= f g_i.  If v is exactly zero the
+// answer is g[0..m] (g[m] = 1).  Otherwise v joins the basis with pivot = its first
+// non-zero position (the first-non-zero rule of a9-a11).  If I .. A^(n-1) are independent
+// the degree is n and the coefficients are charPoly's.  c has n+1 entries, zero above the
+// degree; returns the degree.
+template <class T>
+static uint8_t min_poly_item(const T* A, T* c, int n) {
+    const int L = n * n;
+    T P[16 * 16], Pn[16 * 16];
+    std::vector<T> basis((size_t)n * L), coef((size_t)n * (n + 1));
+    int pivot[16];
+    int nb = 0;
+    for (int m = 0; m < n; ++m) {
+        T v[16 * 16], g[17];
+        if (m == 0) {
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) P[i * n + j] = (i == j) ? T(1) : T(0);
+        } else {
+            matmul_item(P, A, Pn, n, n, n);
+            std::memcpy(P, Pn, sizeof(T) * L);
+        }
+        std::memcpy(v, P, sizeof(T) * L);
+        for (int j = 0; j <= n; ++j) g[j] = (j == m) ? T(1) : T(0);
+        for (int i = 0; i < nb; ++i) {
+            const T* b = &basis[(size_t)i * L];
+            const T* gi = &coef[(size_t)i * (n + 1)];
+            const T f = v[pivot[i]] / b[pivot[i]];
+            for (int t = 0; t < L; ++t) v[t] = v[t] - f * b[t];
+            v[pivot[i]] = T(0);
+            for (int j = 0; j <= n; ++j) g[j] = g[j] - f * gi[j];
+        }
+        int p = 0;
+        while (p < L && v[p] == T(0)) ++p;
+        if (p == L) {
+            for (int j = 0; j <= n; ++j) c[j] = (j <= m) ? g[j] : T(0);
+            return (uint8_t)m;
+        }
+        std::memcpy(&basis[(size_t)nb * L], v, sizeof(T) * L);
+        std::memcpy(&coef[(size_t)nb * (n + 1)], g, sizeof(T) * (n + 1));
+        pivot[nb++] = p;
+    }
+    char_poly_item(A, c, n);
+    return (uint8_t)n;
+}
+
 // Run f(b0, b1) over contiguous chunks of [0, batch) on `threads` std::threads.
 template <class F>
 static void par_chunks(size_t batch, int threads, F f) {
@@ -356,6 +457,40 @@ int t5o_solve(int dtype, int n, int nrhs, size_t batch, const void* A, const voi
         par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = solve_item<float>(a + b * n * n, bb + b * n * nrhs, x + b * n * nrhs, n, nrhs); });
         return 0;
     }
+    return 2;
+}
+
+// ---- tr / polyEval / charPoly / minPoly (§8f-4; parity unpinned) ---------------
+int t5o_trace(int dtype, int n, size_t batch, const void* A, void* OUT, int threads) {
+    if (n < 1 || n > 16) return 1;
+#define T5O_TR(T) { const T* a = (const T*)A; T* o = (T*)OUT; \
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) o[b] = trace_item<T>(a + b * n * n, n); }); return 0; }
+    switch (dtype) { case 0: T5O_TR(double) case 1: T5O_TR(float) case 2: T5O_TR(int64_t) }
+#undef T5O_TR
+    return 2;
+}
+int t5o_poly_eval(int dtype, int n, const void* coeffs, int ncoef, size_t batch, const void* A, void* OUT, int threads) {
+    if (n < 1 || n > 16 || ncoef < 0) return 1;
+#define T5O_PE(T) { const T* a = (const T*)A; T* o = (T*)OUT; const T* c = (const T*)coeffs; \
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) poly_eval_item<T>(a + b * n * n, c, ncoef, o + b * n * n, n); }); return 0; }
+    switch (dtype) { case 0: T5O_PE(double) case 1: T5O_PE(float) case 2: T5O_PE(int64_t) }
+#undef T5O_PE
+    return 2;
+}
+int t5o_char_poly(int dtype, int n, size_t batch, const void* A, void* OUT, int threads) {
+    if (n < 1 || n > 16) return 1;
+#define T5O_CP(T) { const T* a = (const T*)A; T* o = (T*)OUT; \
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) char_poly_item<T>(a + b * n * n, o + b * (n + 1), n); }); return 0; }
+    switch (dtype) { case 0: T5O_CP(double) case 1: T5O_CP(float) }
+#undef T5O_CP
+    return 2;
+}
+int t5o_min_poly(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* degree, int threads) {
+    if (n < 1 || n > 16) return 1;
+#define T5O_MP(T) { const T* a = (const T*)A; T* o = (T*)OUT; \
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) degree[b] = min_poly_item<T>(a + b * n * n, o + b * (n + 1), n); }); return 0; }
+    switch (dtype) { case 0: T5O_MP(double) case 1: T5O_MP(float) }
+#undef T5O_MP
     return 2;
 }
 

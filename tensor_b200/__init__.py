@@ -7,7 +7,7 @@ what the tests and bench drive.  There is no CPU implementation in this package.
 from ._lib import AOS, SOA, F64, F32, I64, U8, LibraryMissing, partition  # noqa: F401
 from .device import (Batch, Context, DeviceError, PinnedArray, TensorException,  # noqa: F401
                      Unsupported, WrongListLength)
-from .linear_algebra import (det, dot, dot_sum, inverse, matmul, matmul_host, prod, scale,  # noqa: F401
-                             solve, tensor_product, transpose, zip_with)
+from .linear_algebra import (char_poly, det, dot, dot_sum, inverse, matmul, matmul_host, min_poly,  # noqa: F401
+                             poly_eval, prod, scale, solve, tensor_product, tr, transpose, zip_with)
 from . import structure, synthetic  # noqa: F401
 from .structure import Nested  # noqa: F401

@@ -52,6 +52,10 @@ SIGNATURES = {
     "t5_det": (_i, [_vp, _i, _i, _vp, _vp]),
     "t5_inverse": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_solve": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "t5_trace": (_i, [_vp, _i, _i, _vp, _vp]),
+    "t5_poly_eval": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "t5_char_poly": (_i, [_vp, _i, _i, _vp, _vp]),
+    "t5_min_poly": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_zip": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_scale": (_i, [_vp, _i, _vp, _vp, _vp]),
     "t5_append": (_i, [_vp, _i, _i, _i, _u64p, _u64p, _vp, _vp, _vp]),

@@ -356,6 +356,183 @@ int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs,
 }
 
 // =====================================================================================
+// The rest of the SquareMatrix surface for any n <= 8 (tr, polyEval, charPoly) and
+// minPoly (n <= 6): thread per item, working matrices in local memory, the oracle's
+// operation order (see oracle/t5_oracle.cpp for the specification).
+// =====================================================================================
+template <class T>
+__device__ __forceinline__ void gen_matmul_nn(const T* a, const T* b, T* c, int n) {
+    using R = Arith<T>;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            T acc = R::zero();
+            for (int k = 0; k < n; ++k) acc = R::add(acc, R::mul(a[i * n + k], b[k * n + j]));
+            c[i * n + j] = acc;
+        }
+}
+
+template <class T>
+__global__ void gen_trace_kernel(const T* __restrict__ A, T* __restrict__ out, int n, unsigned long long count) {
+    using R = Arith<T>;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const T* a = A + b * (size_t)(n * n);
+        T acc = R::zero();
+        for (int i = 0; i < n; ++i) acc = R::add(acc, a[i * n + i]);
+        out[b] = acc;
+    }
+}
+
+template <class T>
+__global__ void gen_poly_eval_kernel(const T* __restrict__ A, const T* __restrict__ coef, int ncoef, T* __restrict__ out,
+                                     int n, unsigned long long count) {
+    using R = Arith<T>;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        T a[GEN_MAXN * GEN_MAXN], r[GEN_MAXN * GEN_MAXN], t[GEN_MAXN * GEN_MAXN];
+        const int nn = n * n;
+        for (int i = 0; i < nn; ++i) { a[i] = A[b * (size_t)nn + i]; r[i] = R::zero(); }
+        if (ncoef > 0)
+            for (int i = 0; i < n; ++i) r[i * n + i] = coef[ncoef - 1];
+        for (int j = ncoef - 2; j >= 0; --j) {
+            gen_matmul_nn(r, a, t, n);
+            const T cj = coef[j];
+            for (int i = 0; i < n; ++i) t[i * n + i] = R::add(t[i * n + i], cj);
+            for (int i = 0; i < nn; ++i) r[i] = t[i];
+        }
+        for (int i = 0; i < nn; ++i) out[b * (size_t)nn + i] = r[i];
+    }
+}
+
+template <class T>
+__device__ void gen_char_poly(const T* a, T* c, int n) {
+    T m[GEN_MAXN * GEN_MAXN], am[GEN_MAXN * GEN_MAXN];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) m[i * n + j] = (i == j) ? T(1) : T(0);
+    c[n] = T(1);
+    for (int k = 1; k <= n; ++k) {
+        gen_matmul_nn(a, m, am, n);
+        T tr = T(0);
+        for (int i = 0; i < n; ++i) tr = tr + am[i * n + i];
+        const T ck = -(tr / T(k));
+        c[n - k] = ck;
+        for (int i = 0; i < n; ++i) am[i * n + i] = am[i * n + i] + ck;
+        for (int i = 0; i < n * n; ++i) m[i] = am[i];
+    }
+}
+
+template <class T>
+__global__ void gen_char_poly_kernel(const T* __restrict__ A, T* __restrict__ out, int n, unsigned long long count) {
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        T a[GEN_MAXN * GEN_MAXN], c[GEN_MAXN + 1];
+        for (int i = 0; i < n * n; ++i) a[i] = A[b * (size_t)(n * n) + i];
+        gen_char_poly(a, c, n);
+        for (int j = 0; j <= n; ++j) out[b * (size_t)(n + 1) + j] = c[j];
+    }
+}
+
+constexpr int MINPOLY_MAXN = 6;
+
+template <class T>
+__global__ void gen_min_poly_kernel(const T* __restrict__ A, T* __restrict__ out, unsigned char* __restrict__ degree, int n,
+                                    unsigned long long count) {
+    constexpr int ML = MINPOLY_MAXN * MINPOLY_MAXN;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        T a[GEN_MAXN * GEN_MAXN], P[ML], Pn[ML], v[ML], g[MINPOLY_MAXN + 1];
+        T basis[MINPOLY_MAXN * ML], coef[MINPOLY_MAXN * (MINPOLY_MAXN + 1)];
+        int pivot[MINPOLY_MAXN];
+        const int L = n * n;
+        for (int i = 0; i < L; ++i) a[i] = A[b * (size_t)L + i];
+        T* c = out + b * (size_t)(n + 1);
+        int nb = 0, deg = -1;
+        for (int m = 0; m < n && deg < 0; ++m) {
+            if (m == 0) {
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < n; ++j) P[i * n + j] = (i == j) ? T(1) : T(0);
+            } else {
+                gen_matmul_nn(P, a, Pn, n);
+                for (int i = 0; i < L; ++i) P[i] = Pn[i];
+            }
+            for (int i = 0; i < L; ++i) v[i] = P[i];
+            for (int j = 0; j <= n; ++j) g[j] = (j == m) ? T(1) : T(0);
+            for (int i = 0; i < nb; ++i) {
+                const T* bi = basis + i * L;
+                const T* gi = coef + i * (n + 1);
+                const T f = v[pivot[i]] / bi[pivot[i]];
+                for (int t = 0; t < L; ++t) v[t] = v[t] - f * bi[t];
+                v[pivot[i]] = T(0);
+                for (int j = 0; j <= n; ++j) g[j] = g[j] - f * gi[j];
+            }
+            int p = 0;
+            while (p < L && v[p] == T(0)) ++p;
+            if (p == L) {
+                for (int j = 0; j <= n; ++j) c[j] = (j <= m) ? g[j] : T(0);
+                deg = m;
+            } else {
+                for (int t = 0; t < L; ++t) basis[nb * L + t] = v[t];
+                for (int j = 0; j <= n; ++j) coef[nb * (n + 1) + j] = g[j];
+                pivot[nb++] = p;
+            }
+        }
+        if (deg < 0) {
+            T cc[GEN_MAXN + 1];
+            gen_char_poly(a, cc, n);
+            for (int j = 0; j <= n; ++j) c[j] = cc[j];
+            deg = n;
+        }
+        degree[b] = (unsigned char)deg;
+    }
+}
+
+int generic_trace(const Shard& s, int dtype, int n, const void* A, void* O) {
+    if (s.layout != T5L_AOS || n < 1 || n > (1 << 14)) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    const int g = flat_grid(s.count, 256);
+    switch (dtype) {
+        case T5D_F64: gen_trace_kernel<double><<<g, 256, 0, s.stream>>>((const double*)A, (double*)O, n, s.count); break;
+        case T5D_F32: gen_trace_kernel<float><<<g, 256, 0, s.stream>>>((const float*)A, (float*)O, n, s.count); break;
+        case T5D_I64: gen_trace_kernel<long long><<<g, 256, 0, s.stream>>>((const long long*)A, (long long*)O, n, s.count); break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
+}
+
+int generic_poly_eval(const Shard& s, int dtype, int n, const void* coef, int ncoef, const void* A, void* O) {
+    if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN || ncoef < 0) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    const int g = flat_grid(s.count, 128);
+    switch (dtype) {
+        case T5D_F64: gen_poly_eval_kernel<double><<<g, 128, 0, s.stream>>>((const double*)A, (const double*)coef, ncoef, (double*)O, n, s.count); break;
+        case T5D_F32: gen_poly_eval_kernel<float><<<g, 128, 0, s.stream>>>((const float*)A, (const float*)coef, ncoef, (float*)O, n, s.count); break;
+        case T5D_I64: gen_poly_eval_kernel<long long><<<g, 128, 0, s.stream>>>((const long long*)A, (const long long*)coef, ncoef, (long long*)O, n, s.count); break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
+}
+
+int generic_char_poly(const Shard& s, int dtype, int n, const void* A, void* O) {
+    if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    const int g = flat_grid(s.count, 128);
+    if (dtype == T5D_F64) gen_char_poly_kernel<double><<<g, 128, 0, s.stream>>>((const double*)A, (double*)O, n, s.count);
+    else if (dtype == T5D_F32) gen_char_poly_kernel<float><<<g, 128, 0, s.stream>>>((const float*)A, (float*)O, n, s.count);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree) {
+    if (s.layout != T5L_AOS || n < 1 || n > MINPOLY_MAXN) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    const int g = flat_grid(s.count, 64);
+    if (dtype == T5D_F64) gen_min_poly_kernel<double><<<g, 64, 0, s.stream>>>((const double*)A, (double*)O, (unsigned char*)degree, n, s.count);
+    else if (dtype == T5D_F32) gen_min_poly_kernel<float><<<g, 64, 0, s.stream>>>((const float*)A, (float*)O, (unsigned char*)degree, n, s.count);
+    else return T5I_UNSUPPORTED;
+    return ok();
+}
+
+// =====================================================================================
 // Element-wise vector-space operations (Functor/Applicative, Vector.hs:180-190,
 // :250-251).  Layout-agnostic: they act on the flat element array of a shard.
 // =====================================================================================

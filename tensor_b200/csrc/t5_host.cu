@@ -62,6 +62,8 @@ struct t5_ctx {
     cudaEvent_t ev0[T5_MAX_DEVICES], ev1[T5_MAX_DEVICES];
     void* scratch[T5_MAX_DEVICES];   // dot-sum block partials + the device partial (at the end)
     void* flush[T5_MAX_DEVICES];     // L2 flush target (lazy)
+    void* coef[T5_MAX_DEVICES];      // polyEval coefficients for the any-shape kernel (lazy, grow-only)
+    size_t coef_cap[T5_MAX_DEVICES];
     std::map<std::vector<uint64_t>, std::vector<uint32_t*>> perm_cache;  // dims -> per-device table
     HostSlot slots[T5_MAX_DEVICES][3];
     std::string last_error;
@@ -161,7 +163,7 @@ int t5_init(const int* devices, int ndev, t5_ctx** out) {
     c->ndev = (int)devs.size();
     for (int g = 0; g < c->ndev; ++g) {
         c->dev[g] = devs[g];
-        c->stream[g] = nullptr; c->ev0[g] = c->ev1[g] = nullptr; c->scratch[g] = c->flush[g] = nullptr;
+        c->stream[g] = nullptr; c->ev0[g] = c->ev1[g] = nullptr; c->scratch[g] = c->flush[g] = c->coef[g] = nullptr; c->coef_cap[g] = 0;
     }
     for (int g = 0; g < c->ndev; ++g) {
         if ((e = cudaSetDevice(c->dev[g])) != cudaSuccess ||
@@ -190,6 +192,7 @@ int t5_shutdown(t5_ctx* c) {
         if (c->nccl_ready && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comms[g]);
         if (c->scratch[g]) cudaFree(c->scratch[g]);
         if (c->flush[g]) cudaFree(c->flush[g]);
+        if (c->coef[g]) cudaFree(c->coef[g]);
         if (c->ev0[g]) cudaEventDestroy(c->ev0[g]);
         if (c->ev1[g]) cudaEventDestroy(c->ev1[g]);
         if (c->stream[g]) cudaStreamDestroy(c->stream[g]);
@@ -610,6 +613,95 @@ int t5_solve(t5_ctx* c, int dtype, int n, int nrhs, const t5_buf* A, const t5_bu
         int r = small_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(s, dtype, n, nrhs, false, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_solve");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+// ---- tr / polyEval / charPoly / minPoly (the rest of SquareMatrix) -------------
+int t5_trace(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, OUT, dtype, 1, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        int r = small_trace(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_trace(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_trace");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_poly_eval(t5_ctx* c, int dtype, int n, const void* coeffs, int ncoef, const t5_buf* A, t5_buf* OUT) {
+    if (!c || ncoef < 0 || (ncoef > 0 && !coeffs)) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, OUT, dtype, (size_t)n * n, A));
+    if (OUT == A) return T5_ERR_INVALID;
+    const size_t cbytes = (size_t)ncoef * dtype_size(dtype);
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        int r = small_poly_eval(s, dtype, n, coeffs, ncoef, A->ptr[g], OUT->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) {
+            // any n <= 8 / any degree: the coefficients go to the device (stream-ordered, so a
+            // previous launch still reading the old ones is not disturbed)
+            if (c->coef_cap[g] < cbytes) {
+                if (c->coef[g]) { CU(c, cudaStreamSynchronize(c->stream[g])); CU(c, cudaFree(c->coef[g])); c->coef[g] = nullptr; c->coef_cap[g] = 0; }
+                const size_t cap = cbytes < 4096 ? 4096 : cbytes;
+                CU(c, cudaMalloc(&c->coef[g], cap));
+                c->coef_cap[g] = cap;
+            }
+            if (cbytes) CU(c, cudaMemcpyAsync(c->coef[g], coeffs, cbytes, cudaMemcpyHostToDevice, c->stream[g]));
+            r = generic_poly_eval(s, dtype, n, c->coef[g], ncoef, A->ptr[g], OUT->ptr[g]);
+        }
+        if (r != T5I_OK) return map_internal(c, r, "t5_poly_eval");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_char_poly(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, OUT, dtype, (size_t)n + 1, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        Shard s = shard_of(c, A, g);
+        int r = small_char_poly(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_char_poly(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_char_poly");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_min_poly(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* DEGREE) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)n * n, nullptr));
+    CHECK(check(c, OUT, dtype, (size_t)n + 1, A));
+    CHECK(check(c, DEGREE, T5_U8, 1, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        int r = generic_min_poly(shard_of(c, A, g), dtype, n, A->ptr[g], OUT->ptr[g], DEGREE->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_min_poly");
         c->launches++;
     }
     return T5_OK;

@@ -40,6 +40,10 @@ int small_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
 int small_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
 
+int small_trace(const Shard& s, int dtype, int n, const void* A, void* O);
+int small_poly_eval(const Shard& s, int dtype, int n, const void* coeffs_host, int ncoef, const void* A, void* O);
+int small_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
+
 // ---- t5_mid_ops.cu: row-per-thread contractions for 0.25-4 KiB records (8x8, 16x16, ...) -----
 int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
 
@@ -53,6 +57,11 @@ int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, co
 int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d_out, const uint32_t* table_dev, const void* A, const void* B, void* O);
 int generic_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs, const void* A, const void* B, void* X, void* status);
+// SquareMatrix extras for any n <= 8 (min_poly: n <= 6); coeffs_dev holds ncoef elements of dtype on the device
+int generic_trace(const Shard& s, int dtype, int n, const void* A, void* O);
+int generic_poly_eval(const Shard& s, int dtype, int n, const void* coeffs_dev, int ncoef, const void* A, void* O);
+int generic_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
+int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree);
 int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, const void* B, void* C);
 int generic_scale(const Shard& s, int dtype, const void* scalar_host, size_t elems, const void* A, void* C);
 // per-device partial of sum_b dot(x_b, y_b): *partial_dev is double (F64/F32) or int64

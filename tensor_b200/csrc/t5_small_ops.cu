@@ -8,13 +8,14 @@
 // bit-identical to the CPU oracle, not merely within tolerance.
 #include "t5_small_ops.cuh"
 #include "t5_internal.h"
+#include <cstring>
 #include <type_traits>
 
 namespace t5 {
 
 // ---- launchers ---------------------------------------------------------------------
 template <class Op, int THREADS, int IPT, int STAGES, int MIN_BLOCKS>
-static int launch_tile(const Shard& s, const void* in0, const void* in1, void* out0, void* out1) {
+static int launch_tile(const Shard& s, const void* in0, const void* in1, void* out0, void* out1, const OpParams& prm) {
     using C = TileCfg<Op, THREADS, IPT, STAGES>;
     static_assert(C::SMEM <= 227 * 1024, "tile does not fit in shared memory");
     auto kern = tile_kernel<Op, THREADS, IPT, STAGES, MIN_BLOCKS>;
@@ -38,13 +39,13 @@ static int launch_tile(const Shard& s, const void* in0, const void* in1, void* o
     // several tiles per scheduler atomic once every CTA has plenty of tiles (keeps the tail short)
     size_t claim = tiles / ((size_t)grid * 16);
     claim = claim < 1 ? 1 : (claim > 8 ? 8 : claim);
-    TileArgs a{in0, in1, out0, out1, (unsigned long long)s.count, s.sched, (unsigned)claim};
+    TileArgs a{in0, in1, out0, out1, (unsigned long long)s.count, s.sched, (unsigned)claim, prm};
     kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
 
 template <class Op>
-static int launch_soa(cudaStream_t st, const void* in0, const void* in1, void* out0, void* out1, size_t n, size_t stride) {
+static int launch_soa(cudaStream_t st, const void* in0, const void* in1, void* out0, void* out1, size_t n, size_t stride, const OpParams& prm) {
     constexpr int THREADS = 256;
     if (n == 0) return T5I_OK;
     size_t blocks = (n + THREADS - 1) / THREADS;
@@ -54,7 +55,7 @@ static int launch_soa(cudaStream_t st, const void* in0, const void* in1, void* o
     if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
     size_t cap = (size_t)sms * 8 * 4;  // 4 waves of full occupancy, grid-stride beyond
     int grid = (int)(blocks < cap ? blocks : cap);
-    SoaArgs a{in0, in1, out0, out1, (unsigned long long)n, (unsigned long long)stride};
+    SoaArgs a{in0, in1, out0, out1, (unsigned long long)n, (unsigned long long)stride, prm};
     soa_kernel<Op, THREADS><<<grid, THREADS, 0, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
@@ -80,10 +81,10 @@ template <class T, int N, int R> struct Geo<SolveOp<T, N, R>> {
 };
 
 template <class Op>
-static int launch_op(const Shard& s, const void* in0, const void* in1, void* out0, void* out1) {
-    if (s.layout == T5L_SOA) return launch_soa<Op>(s.stream, in0, in1, out0, out1, s.count, s.soa_stride);
+static int launch_op(const Shard& s, const void* in0, const void* in1, void* out0, void* out1, const OpParams& prm = OpParams{}) {
+    if (s.layout == T5L_SOA) return launch_soa<Op>(s.stream, in0, in1, out0, out1, s.count, s.soa_stride, prm);
     using g = typename Geo<Op>::type;
-    return launch_tile<Op, g::threads, g::ipt, g::stages, g::min_blocks>(s, in0, in1, out0, out1);
+    return launch_tile<Op, g::threads, g::ipt, g::stages, g::min_blocks>(s, in0, in1, out0, out1, prm);
 }
 
 template <class T>
@@ -159,6 +160,58 @@ static int solve_t(const Shard& s, int n, int nrhs, const void* A, const void* B
 int small_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
     if (dtype == T5D_F64) return solve_t<double>(s, n, nrhs, A, B, X, status);
     if (dtype == T5D_F32) return solve_t<float>(s, n, nrhs, A, B, X, status);
+    return T5I_NOT_SPECIALISED;
+}
+
+// ---- tr / polyEval / charPoly ------------------------------------------------
+template <class T>
+static int trace_t(const Shard& s, int n, const void* A, void* O) {
+    if (n == 2) return launch_op<TraceOp<T, 2>>(s, A, nullptr, O, nullptr);
+    if (n == 3) return launch_op<TraceOp<T, 3>>(s, A, nullptr, O, nullptr);
+    if (n == 4) return launch_op<TraceOp<T, 4>>(s, A, nullptr, O, nullptr);
+    return T5I_NOT_SPECIALISED;
+}
+int small_trace(const Shard& s, int dtype, int n, const void* A, void* O) {
+    switch (dtype) {
+        case T5D_F64: return trace_t<double>(s, n, A, O);
+        case T5D_F32: return trace_t<float>(s, n, A, O);
+        case T5D_I64: return trace_t<long long>(s, n, A, O);
+    }
+    return T5I_NOT_SPECIALISED;
+}
+
+template <class T>
+static int poly_eval_t(const Shard& s, int n, const OpParams& prm, const void* A, void* O) {
+    if (n == 2) return launch_op<PolyEvalOp<T, 2>>(s, A, nullptr, O, nullptr, prm);
+    if (n == 3) return launch_op<PolyEvalOp<T, 3>>(s, A, nullptr, O, nullptr, prm);
+    if (n == 4) return launch_op<PolyEvalOp<T, 4>>(s, A, nullptr, O, nullptr, prm);
+    return T5I_NOT_SPECIALISED;
+}
+// coeffs_host: ncoef elements of dtype, low order first; at most 16 ride in the parameter block
+int small_poly_eval(const Shard& s, int dtype, int n, const void* coeffs_host, int ncoef, const void* A, void* O) {
+    if (ncoef < 0 || ncoef > 16) return T5I_NOT_SPECIALISED;
+    OpParams prm{};
+    prm.n = ncoef;
+    const int es = dtype_size(dtype);
+    for (int j = 0; j < ncoef; ++j) memcpy(&prm.v[j], (const char*)coeffs_host + (size_t)j * es, es);
+    switch (dtype) {
+        case T5D_F64: return poly_eval_t<double>(s, n, prm, A, O);
+        case T5D_F32: return poly_eval_t<float>(s, n, prm, A, O);
+        case T5D_I64: return poly_eval_t<long long>(s, n, prm, A, O);
+    }
+    return T5I_NOT_SPECIALISED;
+}
+
+template <class T>
+static int char_poly_t(const Shard& s, int n, const void* A, void* O) {
+    if (n == 2) return launch_op<CharPolyOp<T, 2>>(s, A, nullptr, O, nullptr);
+    if (n == 3) return launch_op<CharPolyOp<T, 3>>(s, A, nullptr, O, nullptr);
+    if (n == 4) return launch_op<CharPolyOp<T, 4>>(s, A, nullptr, O, nullptr);
+    return T5I_NOT_SPECIALISED;
+}
+int small_char_poly(const Shard& s, int dtype, int n, const void* A, void* O) {
+    if (dtype == T5D_F64) return char_poly_t<double>(s, n, A, O);
+    if (dtype == T5D_F32) return char_poly_t<float>(s, n, A, O);
     return T5I_NOT_SPECIALISED;
 }
 

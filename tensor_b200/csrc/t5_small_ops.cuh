@@ -185,6 +185,97 @@ struct SolveOp {
     }
 };
 
+// ---- the rest of the SquareMatrix surface: tr, polyEval, charPoly ----------
+// tr: fold_{i asc} (acc + A[i,i]) from 0.
+template <class T, int N>
+struct TraceOp {
+    using In0 = Rec<T, N * N>; using In1 = NoRec;
+    using Out0 = Rec<T, 1>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* o, unsigned char*) {
+        using R = Arith<T>;
+        T acc = R::zero();
+        #pragma unroll
+        for (int i = 0; i < N; ++i) acc = R::add(acc, a[i * N + i]);
+        o[0] = acc;
+    }
+};
+
+// polyEval A [c0..cd] by Horner: R = cd I; for j = d-1..0: R = (R .*. A) + cj I.
+template <class T, int N>
+struct PolyEvalOp {
+    static constexpr bool uses_params = true;
+    using In0 = Rec<T, N * N>; using In1 = NoRec;
+    using Out0 = Rec<T, N * N>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* o, unsigned char*, const OpParams& prm) {
+        using R = Arith<T>;
+        T r[N][N];
+        const T lead = prm.n > 0 ? param_as<T>(prm.v[prm.n - 1]) : R::zero();
+        #pragma unroll
+        for (int i = 0; i < N; ++i)
+            #pragma unroll
+            for (int j = 0; j < N; ++j) r[i][j] = (i == j) ? lead : R::zero();
+        for (int c = prm.n - 2; c >= 0; --c) {
+            const T cj = param_as<T>(prm.v[c]);
+            T t[N][N];
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    T acc = R::zero();
+                    #pragma unroll
+                    for (int k = 0; k < N; ++k) acc = R::add(acc, R::mul(r[i][k], a[k * N + j]));
+                    t[i][j] = (i == j) ? R::add(acc, cj) : acc;
+                }
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int j = 0; j < N; ++j) r[i][j] = t[i][j];
+        }
+        #pragma unroll
+        for (int i = 0; i < N; ++i)
+            #pragma unroll
+            for (int j = 0; j < N; ++j) o[i * N + j] = r[i][j];
+    }
+};
+
+// charPoly by Faddeev-LeVerrier: M = I; for k = 1..N: AM = A .*. M; c[N-k] = -(tr AM / k);
+// M = AM + c[N-k] I.  Output c[0..N], c[N] = 1.
+template <class T, int N>
+struct CharPolyOp {
+    using In0 = Rec<T, N * N>; using In1 = NoRec;
+    using Out0 = Rec<T, N + 1>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* c, unsigned char*) {
+        T m[N][N];
+        #pragma unroll
+        for (int i = 0; i < N; ++i)
+            #pragma unroll
+            for (int j = 0; j < N; ++j) m[i][j] = (i == j) ? T(1) : T(0);
+        c[N] = T(1);
+        #pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            T am[N][N];
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    T acc = T(0);
+                    #pragma unroll
+                    for (int l = 0; l < N; ++l) acc = acc + a[i * N + l] * m[l][j];
+                    am[i][j] = acc;
+                }
+            T tr = T(0);
+            #pragma unroll
+            for (int i = 0; i < N; ++i) tr = tr + am[i][i];
+            const T ck = -(tr / T(k));
+            c[N - k] = ck;
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int j = 0; j < N; ++j) m[i][j] = (i == j) ? am[i][j] + ck : am[i][j];
+        }
+    }
+};
+
 template <class T, int N>
 struct InverseOp {
     using In0 = Rec<T, N * N>; using In1 = NoRec;

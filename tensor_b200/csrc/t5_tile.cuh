@@ -26,8 +26,27 @@
 // the average one (ncu, profiles/r01_*), which capped DRAM utilisation.
 #pragma once
 #include "t5_device.cuh"
+#include <type_traits>
 
 namespace t5 {
+
+// Per-launch scalars of an Op (today: the coefficients of polyEval).  Travels inside the
+// kernel parameter block, i.e. the constant bank: reading v[j] is an LDC, not a global load.
+struct OpParams {
+    int n;                       // number of valid entries of v
+    unsigned long long v[16];    // bit patterns of the element type, low-order bytes first
+};
+template <class T> __device__ __forceinline__ T param_as(unsigned long long raw) {
+    if constexpr (sizeof(T) == 8) { T x; memcpy(&x, &raw, 8); return x; }
+    else { unsigned lo = (unsigned)raw; T x; memcpy(&x, &lo, 4); return x; }
+}
+template <class Op, class = void> struct UsesParams : std::false_type {};
+template <class Op> struct UsesParams<Op, std::void_t<decltype(Op::uses_params)>> : std::true_type {};
+template <class Op, class A0, class A1, class B0, class B1>
+__device__ __forceinline__ void run_op(const A0* r0, const A1* r1, B0* w0, B1* w1, const OpParams& prm) {
+    if constexpr (UsesParams<Op>::value) Op::run(r0, r1, w0, w1, prm);
+    else Op::run(r0, r1, w0, w1);
+}
 
 constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
 
@@ -85,6 +104,7 @@ struct TileArgs {
     unsigned long long n_items;
     unsigned long long* sched;  // [0] next tile, [1] finished CTAs; both zero between launches
     unsigned claim;             // tiles claimed per atomic (>= 1)
+    OpParams prm;
 };
 
 // Tile claims: one atomicAdd on the scheduler word hands out `claim` consecutive tiles.  A
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
                 RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
                 if constexpr (I0::bytes > 0) I0::load(s0, it, r0.v);
                 if constexpr (I1::bytes > 0) I1::load(s1, it, r1.v);
-                Op::run(r0.v, r1.v, w0.v, w1.v);
+                run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
                 if constexpr (O0::bytes > 0) {
                     if constexpr (C::OUT0 == -1) stg_direct<O0::bytes>(g_out0 + (first + it) * O0::bytes, w0.v);
                     else if constexpr (C::OUT0 == 0) I0::store(so, it, w0.v);   // in place: same thread, same slot
@@ -281,6 +301,7 @@ struct SoaArgs {
     void* out1;
     unsigned long long n_items;
     unsigned long long stride;  // shard capacity in items
+    OpParams prm;
 };
 
 template <class Op, int THREADS>
@@ -298,7 +319,7 @@ __global__ void __launch_bounds__(THREADS) soa_kernel(SoaArgs a) {
         for (int e = 0; e < I0::n; ++e) r0.v[e] = __ldg(in0 + (size_t)e * a.stride + b);
         #pragma unroll
         for (int e = 0; e < I1::n; ++e) r1.v[e] = __ldg(in1 + (size_t)e * a.stride + b);
-        Op::run(r0.v, r1.v, w0.v, w1.v);
+        run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
         #pragma unroll
         for (int e = 0; e < O0::n; ++e) out0[(size_t)e * a.stride + b] = w0.v[e];
         #pragma unroll

@@ -165,6 +165,32 @@ std::pair<Batch<T, N>, Batch<uint8_t>> solve(const Batch<T, N, N>& a, const Batc
     a.ctx().check(t5_solve(a.ctx().handle(), dtype_of<T>::value, (int)N, 1, a.buf(), b.buf(), x.buf(), st.buf()), "t5_solve");
     return {x, st};
 }
+// the rest of SquareMatrix (CHANGELOG.md:28-29)
+template <class T, size_t N>
+Batch<T> tr(const Batch<T, N, N>& a) {
+    Batch<T> t(a.ctx(), a.count());
+    a.ctx().check(t5_trace(a.ctx().handle(), dtype_of<T>::value, (int)N, a.buf(), t.buf()), "t5_trace");
+    return t;
+}
+template <class T, size_t N>
+Batch<T, N, N> poly_eval(const Batch<T, N, N>& a, const std::vector<T>& coeffs) {  // c0 I + c1 a + ..
+    Batch<T, N, N> r(a.ctx(), a.count());
+    a.ctx().check(t5_poly_eval(a.ctx().handle(), dtype_of<T>::value, (int)N, coeffs.data(), (int)coeffs.size(), a.buf(), r.buf()), "t5_poly_eval");
+    return r;
+}
+template <class T, size_t N>
+Batch<T, N + 1> char_poly(const Batch<T, N, N>& a) {                               // low order first, leading 1
+    Batch<T, N + 1> c(a.ctx(), a.count());
+    a.ctx().check(t5_char_poly(a.ctx().handle(), dtype_of<T>::value, (int)N, a.buf(), c.buf()), "t5_char_poly");
+    return c;
+}
+template <class T, size_t N>
+std::pair<Batch<T, N + 1>, Batch<uint8_t>> min_poly(const Batch<T, N, N>& a) {      // (coefficients, degree)
+    Batch<T, N + 1> c(a.ctx(), a.count());
+    Batch<uint8_t> deg(a.ctx(), a.count());
+    a.ctx().check(t5_min_poly(a.ctx().handle(), dtype_of<T>::value, (int)N, a.buf(), c.buf(), deg.buf()), "t5_min_poly");
+    return {c, deg};
+}
 template <class T, size_t... Is>
 Batch<T, Is...> operator+(const Batch<T, Is...>& a, const Batch<T, Is...>& b) {   // liftA2 (+)
     Batch<T, Is...> c(a.ctx(), a.count());

@@ -134,6 +134,41 @@ def solve(a: Batch, b: Batch) -> Tuple[Batch, Batch]:
     return out, status
 
 
+def tr(a: Batch) -> Batch:
+    """``tr``: the trace, ``fold (+) 0`` of the diagonal in index order."""
+    n = _square(a, "tr")
+    out = Batch(a.ctx, (), a.dtype, a.batch, a.layout)
+    check(_lib.lib().t5_trace(a.ctx._h, a.dtype, n, a._h, out._h), a.ctx)
+    return out
+
+
+def poly_eval(a: Batch, coeffs) -> Batch:
+    """``polyEval a [c0, c1, ..]`` = c0 I + c1 a + c2 a^2 + .. by Horner's rule (CHANGELOG.md:28-29
+    names the method; semantics SURVEY §8f-4).  One coefficient list for the whole batch."""
+    n = _square(a, "polyEval")
+    c = np.ascontiguousarray(coeffs, dtype=NP_OF[a.dtype]).reshape(-1)
+    out = Batch(a.ctx, a.shape, a.dtype, a.batch, a.layout)
+    check(_lib.lib().t5_poly_eval(a.ctx._h, a.dtype, n, c.ctypes.data_as(ctypes.c_void_p), int(c.size), a._h, out._h), a.ctx)
+    return out
+
+
+def char_poly(a: Batch) -> Batch:
+    """``charPoly``: the n+1 coefficients of det(xI - a), low order first, leading 1 (Faddeev-LeVerrier)."""
+    n = _square(a, "charPoly")
+    out = Batch(a.ctx, (n + 1,), a.dtype, a.batch, a.layout)
+    check(_lib.lib().t5_char_poly(a.ctx._h, a.dtype, n, a._h, out._h), a.ctx)
+    return out
+
+
+def min_poly(a: Batch) -> Tuple[Batch, Batch]:
+    """``minPoly``: (coefficients low order first, zero above the degree; degree per item)."""
+    n = _square(a, "minPoly")
+    out = Batch(a.ctx, (n + 1,), a.dtype, a.batch, a.layout)
+    deg = Batch(a.ctx, (), U8, a.batch, a.layout)
+    check(_lib.lib().t5_min_poly(a.ctx._h, a.dtype, n, a._h, out._h, deg._h), a.ctx)
+    return out, deg
+
+
 _ZIP = {"+": 0, "-": 1, "*": 2}
 
 

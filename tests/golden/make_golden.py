@@ -78,6 +78,36 @@ def main():
         json.dump(reg, f)
     print("wrote", len(known), "transpose cases and", len(reg), "regression cases")
 
+    # the rest of SquareMatrix (tr / polyEval / charPoly / minPoly): oracle-generated
+    # regression net + hand-checkable structured matrices whose minimal polynomial is known exactly
+    reg = []
+    structured = {
+        2: [np.eye(2) * 3, [[0, 1], [0, 0]], [[2, 0], [0, 5]], np.zeros((2, 2)), [[1, 1], [0, 1]]],
+        3: [np.eye(3) * 2, np.diag([2.0, 2, 3]), [[0, 1, 0], [0, 0, 1], [0, 0, 0]], [[0, 1, 0], [0, 0, 0], [0, 0, 0]],
+            np.zeros((3, 3)), [[1, 0, 0], [0, 0, 0], [0, 0, 0]], [[4, 1, 0], [0, 4, 0], [0, 0, 4]]],
+        4: [np.eye(4), np.diag([1.0, 1, 2, 2]), np.diag([1.0, 2, 3, 4]), np.eye(4)[::-1].copy(), np.zeros((4, 4)),
+            [[0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [0, 0, 0, 0]]],
+    }
+    for dname, dc in (("f64", oracle.F64), ("f32", oracle.F32)):
+        npd = oracle.NP_DTYPE[dc]
+        for n in (2, 3, 4, 5):
+            rnd = oracle.fill(dc, oracle.SEED_A, 7, batch * n * n).reshape(batch, n, n)
+            mats = [rnd[i] for i in range(batch)] + [np.asarray(m, dtype=npd) for m in structured.get(n, [])]
+            a = np.ascontiguousarray(np.stack(mats), dtype=npd)
+            coeffs = [0.5, -1.25, 2.0, 0.75, -0.5][: n + 1]
+            rec("trace", dname, {"n": n}, [a], [oracle.trace(a, n)])
+            rec("poly_eval", dname, {"n": n, "coeffs": coeffs}, [a], [oracle.poly_eval(a, coeffs, n)])
+            rec("char_poly", dname, {"n": n}, [a], [oracle.char_poly(a, n)])
+            mp, deg = oracle.min_poly(a, n)
+            rec("min_poly", dname, {"n": n}, [a], [mp, deg])
+    for n in (2, 3, 4):
+        a = oracle.fill(oracle.I64, oracle.SEED_A, 7, batch * n * n).reshape(batch, n, n)
+        rec("trace", "i64", {"n": n}, [a], [oracle.trace(a, n)])
+        rec("poly_eval", "i64", {"n": n, "coeffs": [3, -7, 11, 2 ** 40]}, [a], [oracle.poly_eval(a, [3, -7, 11, 2 ** 40], n)])
+    with open(os.path.join(HERE, "sqmat_regression.json"), "w") as f:
+        json.dump(reg, f)
+    print("wrote", len(reg), "SquareMatrix-extras regression cases")
+
 
 if __name__ == "__main__":
     main()
