@@ -154,11 +154,11 @@ class ClockSampler:
 class Step:
     """Allocates the operands of a workload in HBM and exposes run() = one kernel launch."""
 
-    def __init__(self, ctx, tb, w, first_item=0):
+    def __init__(self, ctx, tb, w, batch=None):
         self.ctx, self.tb, self.w = ctx, tb, w
         L = tb._lib.lib()
         dt = NPD[w["dtype"]]
-        B = w["batch"]
+        B = self.batch = w["batch"] if batch is None else batch
         op = w["op"]
         lay = tb.SOA if w.get("layout") == "soa" else tb.AOS
         syn = lambda shape, seed, opid: ctx.synthetic(shape, dt, B, seed, opid, lay)  # noqa: E731
@@ -267,24 +267,134 @@ def roofline(w, ms_per_launch, peaks):
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src}
 
 
+# ---- end to end through the host-buffer C-ABI entries ---------------------------------------------
+E2E_MAX_BYTES = 3300 << 20     # host operands + results per call (pinned); larger workloads use a prefix of the batch
+
+
+class HostCall:
+    """The workload through the reference-facing call: HOST (pinned) arrays in, HOST arrays out, one
+    t5_*_host C-ABI call per step — host->device and device->host copies are inside the call."""
+
+    def __init__(self, ctx, tb, w):
+        self.ctx, self.tb, self.w = ctx, tb, w
+        if w.get("layout") == "soa" or w["op"] == "append":
+            raise NotImplementedError("no host-array entry for this workload")
+        self.batch = B = max(256, min(w["batch"], E2E_MAX_BYTES // w["bytes"]))
+        dev = Step(ctx, tb, w, batch=B)                      # the same synthetic stream, generated on the device ...
+        check_rc(dev.run(), ctx, tb)
+        self.pins = []
+
+        def pinned_copy(buf):                                # ... and copied out once, untimed
+            p = tb.PinnedArray((buf.batch * buf.elems,), tb.device.NP_OF[buf.dtype])
+            check_rc(tb._lib.lib().t5_download(buf._h, p.array.ctypes.data_as(ctypes.c_void_p), p.nbytes), ctx, tb)
+            self.pins.append(p)
+            return p
+
+        def pinned_out(buf):
+            p = tb.PinnedArray((buf.batch * buf.elems,), tb.device.NP_OF[buf.dtype])
+            self.pins.append(p)
+            return p
+
+        H = tb.host
+        op = w["op"]
+        a = pinned_copy(dev.a)
+        b = pinned_copy(dev.b) if hasattr(dev, "b") else None
+        c = pinned_out(dev.c)
+        st = pinned_out(dev.s) if hasattr(dev, "s") else None
+        self.h2d = a.nbytes + (b.nbytes if b else 0)
+        self.d2h = c.nbytes + (st.nbytes if st else 0)
+        self.out = c
+        if op == "matmul":
+            self.call = lambda: H.matmul(ctx, a.array, b.array, w["m"], w["k"], w["n"], out=c.array)
+            self.api = "t5_matmul_host"
+        elif op == "dot":
+            self.call = lambda: H.dot(ctx, a.array, b.array, w["n"], out=c.array)
+            self.api = "t5_dot_host"
+        elif op == "transpose":
+            self.call = lambda: H.transpose(ctx, a.array, w["dims"], out=c.array)
+            self.api = "t5_transpose_host"
+        elif op == "prod":
+            self.call = lambda: H.prod(ctx, a.array, w["dims_a"], b.array, w["dims_b"], w["nc"], out=c.array)
+            self.api = "t5_prod_host"
+        elif op == "det":
+            self.call = lambda: H.det(ctx, a.array, w["n"], out=c.array)
+            self.api = "t5_det_host"
+        elif op == "inverse":
+            self.call = lambda: H.inverse(ctx, a.array, w["n"], out=c.array, status=st.array)
+            self.api = "t5_inverse_host"
+        elif op == "solve":
+            self.call = lambda: H.solve(ctx, a.array, b.array, w["n"], 1, out=c.array, status=st.array)
+            self.api = "t5_solve_host"
+        else:
+            raise NotImplementedError(op)
+        # the device-entry result on the same inputs, for the spot check
+        n = min(dev.c.batch * dev.c.elems, 1 << 16)
+        self.want = dev.c.to_numpy().reshape(-1)[:n].copy()
+        dev.free()
+
+    def check(self):
+        got = self.out.array[: self.want.size]
+        view = {8: np.uint64, 4: np.uint32}[got.dtype.itemsize]
+        if not np.array_equal(got.view(view), self.want.view(view)):
+            raise SystemExit(f"{self.api}: host-entry result differs from the device-entry result")
+
+    def free(self):
+        for p in self.pins:
+            p.free()
+
+
+def time_e2e(hc, steps, barrier=lambda: None):
+    """Wall-clock seconds of `steps` host calls (each returns after its results are in host memory)."""
+    for _ in range(2):
+        hc.call()
+    hc.check()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hc.call()
+    el = time.perf_counter() - t0
+    barrier()
+    return el
+
+
 # ---- CPU arm: the oracle port on the host cores -------------------------------------------------
 class CpuWork:
-    """The oracle port on one bounded sample of the workload (inputs generated once, untimed)."""
+    """The oracle port (C++ restatement of the reference semantics) on one bounded sample of the
+    workload, all host threads; inputs generated once, untimed."""
 
-    def __init__(self, w):
+    def __init__(self, w, max_items=1 << 24, max_bytes=4 << 30):
         import oracle
-        self.oracle = oracle
-        dt = {"f64": oracle.F64, "f32": oracle.F32, "i64": oracle.I64}[w["dtype"]]
-        assert w["op"] == "matmul"
-        self.m, self.k, self.n = w["m"], w["k"], w["n"]
-        self.B = min(w["batch"], 1 << 24)
-        self.a = oracle.fill(dt, oracle.SEED_A, 1, self.B * self.m * self.k)
-        self.b = oracle.fill(dt, oracle.SEED_B, 1, self.B * self.k * self.n)
-        self.threads = os.cpu_count() or 1
+        self.oracle = o = oracle
+        dt = {"f64": o.F64, "f32": o.F32, "i64": o.I64}[w["dtype"]]
+        self.B = B = max(1, min(w["batch"], max_items, max_bytes // w["bytes"]))
+        self.threads = T = os.cpu_count() or 1
+        op = w["op"]
+        if op == "matmul":
+            m, k, n = w["m"], w["k"], w["n"]
+            a, b = o.fill(dt, o.SEED_A, 1, B * m * k), o.fill(dt, o.SEED_B, 1, B * k * n)
+            self.one_pass = lambda: o.matmul(a, b, m, k, n, threads=T)
+        elif op == "dot":
+            n = w["n"]
+            a, b = o.fill(dt, o.SEED_A, 2, B * n), o.fill(dt, o.SEED_B, 2, B * n)
+            self.one_pass = lambda: o.dot(a, b, n, threads=T)
+        elif op == "transpose":
+            dims = list(w["dims"])
+            a = o.fill(dt, o.SEED_A, 3, B * int(np.prod(dims)))
+            self.one_pass = lambda: o.transpose(a, dims, threads=T)
+        elif op == "prod":
+            da, db, nc = list(w["dims_a"]), list(w["dims_b"]), w["nc"]
+            a, b = o.fill(dt, o.SEED_A, 4, B * int(np.prod(da))), o.fill(dt, o.SEED_B, 4, B * int(np.prod(db)))
+            self.one_pass = lambda: o.prod(a, da, b, db, nc, threads=T)
+        elif op in ("det", "inverse", "solve"):
+            n = w["n"]
+            a = o.fill(dt, o.SEED_A, 5, B * n * n).reshape(B, n, n)
+            o.plant_specials(a, n, 0, 1024, 65536)
+            b = o.fill(dt, o.SEED_B, 5, B * n)
+            self.one_pass = {"det": lambda: o.det(a, n, threads=T), "inverse": lambda: o.inverse(a, n, threads=T),
+                             "solve": lambda: o.solve(a, b, n, 1, threads=T)}[op]
+        else:
+            raise NotImplementedError(op)
         self.one_pass()  # warm (page-in, thread start)
-
-    def one_pass(self):
-        self.oracle.matmul(self.a, self.b, self.m, self.k, self.n, threads=self.threads)
 
     def run_for(self, min_seconds, max_reps=200):
         reps, t0 = 0, time.perf_counter()
@@ -365,34 +475,15 @@ def ours(args):
 
     # ---- end to end through the host-buffer C-ABI entry (`e2e`) ----------------------------------
     e2e = None
-    if w["op"] == "matmul" and not args.no_e2e:
-        m, k, n = w["m"], w["k"], w["n"]
-        dt = NPD[w["dtype"]]
-        B = w["batch"]
-        ha, hb, hc = tb.PinnedArray((B * m * k,), dt), tb.PinnedArray((B * k * n,), dt), tb.PinnedArray((B * m * n,), dt)
-        # the host operands are the same synthetic stream (generated on the device, copied out once, untimed)
-        L = tb._lib.lib()
-        check_rc(L.t5_download(step.a._h, ha.array.ctypes.data_as(ctypes.c_void_p), ha.nbytes), ctx, tb)
-        check_rc(L.t5_download(step.b._h, hb.array.ctypes.data_as(ctypes.c_void_p), hb.nbytes), ctx, tb)
+    if not args.no_e2e:
+        hc = HostCall(ctx, tb, w)
         e_steps = max(2, min(steps, 8))
-        for _ in range(2):
-            tb.matmul_host(ctx, ha.array, hb.array, m, k, n, hc.array)
-        D.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            tb.matmul_host(ctx, ha.array, hb.array, m, k, n, hc.array)   # returns after the D2H of C completed
-        el = time.perf_counter() - t0
-        D.barrier()
-        el = D.max_over_ranks(el, dev)
-        # spot-check the host result against the device-resident result
-        ref = step.c.to_numpy().reshape(-1)
-        if not np.array_equal(ref[: 1 << 16].view(np.uint32 if dt == np.float32 else np.uint64),
-                              hc.array[: 1 << 16].view(np.uint32 if dt == np.float32 else np.uint64)):
-            raise SystemExit("host-entry result differs from device-entry result")
-        e2e = {"value": B * world * e_steps / el, "unit": "matrices/s", "h2d_bytes_per_step": int(ha.nbytes + hb.nbytes),
-               "d2h_bytes_per_step": int(hc.nbytes), "steps": e_steps, "api": "t5_matmul_host (pinned host buffers, 3-slot H2D/kernel/D2H pipeline)"}
-        for p in (ha, hb, hc):
-            p.free()
+        el = D.max_over_ranks(time_e2e(hc, e_steps, D.barrier), dev)
+        hc.check()
+        e2e = {"value": hc.batch * world * e_steps / el, "unit": "matrices/s", "h2d_bytes_per_step": int(hc.h2d),
+               "d2h_bytes_per_step": int(hc.d2h), "steps": e_steps, "batch_per_gpu": hc.batch,
+               "api": hc.api + " (pinned host buffers, 3-slot H2D/kernel/D2H pipeline, wall clock around the calls)"}
+        hc.free()
     ring.free()
 
     # ---- the other BASELINE configs (explanatory; not the headline) ----------------------------------
@@ -407,12 +498,30 @@ def ours(args):
                 others[name] = {"matrices_per_s": ww["batch"] / (t * 1e-3), "ms": t, "achieved": r["achieved"],
                                 "unit": r["unit"], "frac": r["frac"], "operand_sets": len(st.sets)}
                 st.free()
+                if not args.no_e2e:
+                    try:
+                        hc = HostCall(ctx, tb, ww)
+                        k_e = 3
+                        el = time_e2e(hc, k_e)
+                        others[name]["e2e"] = {"value": hc.batch * k_e / el, "unit": "matrices/s", "batch": hc.batch,
+                                               "h2d_bytes_per_step": int(hc.h2d), "d2h_bytes_per_step": int(hc.d2h), "api": hc.api}
+                        hc.free()
+                    except NotImplementedError:
+                        pass
+                if not args.no_cpu:
+                    try:
+                        cw = CpuWork(ww, max_items=1 << 22, max_bytes=256 << 20)
+                        v, reps, el = cw.run_for(1.0)
+                        others[name]["cpu"] = {"value": v, "unit": "matrices/s", "cores": cw.threads, "kind": "port",
+                                               "sample": f"{reps} passes over {cw.B} items ({el:.1f} s)"}
+                    except NotImplementedError:
+                        pass
             except Exception as e:  # report, never hide
                 others[name] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and w["op"] == "matmul":
+    if rank == 0 and world == 1 and not args.no_cpu:
         cw = CpuWork(w)
         v, reps, el = cw.run_for(10.0)
         cpu = {"value": v, "unit": "matrices/s", "cores": cw.threads, "kind": "port",

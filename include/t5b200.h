@@ -199,12 +199,23 @@ int t5_structural_table(int op, int rank, const uint64_t* dims, const uint64_t* 
                         uint32_t* table_out, size_t table_cap, size_t* d_out);
 
 /* ---- host-buffer (end-to-end) entries --------------------------------------
- * Same operations on HOST AoS arrays: the call uploads chunks, runs the kernel
- * and downloads results, overlapping the three on separate streams.  This is
- * what a Haskell instance method on an ordinary (host) tensor batch calls.
- * Pinned host memory (t5_pinned_alloc) gives full PCIe speed. */
+ * The same operations on HOST AoS arrays (`batch` items each): the call uploads chunks,
+ * runs the kernel and downloads results, overlapping the three on separate streams, and
+ * returns when the results are in host memory.  This is what a Haskell instance method
+ * on an ordinary (host) tensor batch calls; semantics, element types and error codes are
+ * those of the device-buffer entry of the same name.  Pinned host memory
+ * (t5_pinned_alloc) gives full PCIe speed; pageable memory works but is staged by the
+ * driver.  `status` arrays hold one byte per item. */
 int t5_matmul_host(t5_ctx* ctx, int dtype, int m, int k, int n, size_t batch,
                    const void* A, const void* B, void* C);
+int t5_dot_host(t5_ctx* ctx, int dtype, int n, size_t batch, const void* X, const void* Y, void* OUT);
+int t5_prod_host(t5_ctx* ctx, int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB,
+                 int ncontract, size_t batch, const void* A, const void* B, void* C);
+int t5_transpose_host(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT);
+int t5_det_host(t5_ctx* ctx, int dtype, int n, size_t batch, const void* A, void* OUT);
+int t5_inverse_host(t5_ctx* ctx, int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* status);
+int t5_solve_host(t5_ctx* ctx, int dtype, int n, int nrhs, size_t batch, const void* A, const void* B, void* X,
+                  uint8_t* status);
 
 /* ---- measurement helpers ---------------------------------------------------
  * CUDA events on the context's own streams (the streams the kernels run on);

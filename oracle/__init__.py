@@ -49,7 +49,7 @@ def lib() -> ctypes.CDLL:
         L.t5o_unlinearize.argtypes = [u64p, i32, u64, u64p]
         L.t5o_transposeV.restype = u64
         L.t5o_transposeV.argtypes = [u64p, i32, u64]
-        L.t5o_transpose.argtypes = [i32, i32, u64p, sz, vp, vp]
+        L.t5o_transpose.argtypes = [i32, i32, u64p, sz, vp, vp, i32]
         L.t5o_matmul.argtypes = [i32, i32, i32, i32, sz, vp, vp, vp, i32]
         L.t5o_dot.argtypes = [i32, i32, sz, vp, vp, vp, i32]
         L.t5o_dot_sum.argtypes = [i32, i32, sz, vp, vp, vp]
@@ -102,12 +102,12 @@ def transposeV(ds, i) -> int:
 
 
 # ---- operations; every array is [batch, *dims] C-contiguous -----------------
-def transpose(a: np.ndarray, dims) -> np.ndarray:
+def transpose(a: np.ndarray, dims, threads: int = 1) -> np.ndarray:
     dims = list(dims)
     a = _c(a)
     batch = a.size // max(1, int(np.prod(dims, dtype=np.int64)))
     out = np.empty((batch, *dims[::-1]), dtype=a.dtype)
-    _chk(lib().t5o_transpose(a.dtype.itemsize, len(dims), _u64(dims), batch, _ptr(a), _ptr(out)))
+    _chk(lib().t5o_transpose(a.dtype.itemsize, len(dims), _u64(dims), batch, _ptr(a), _ptr(out), threads))
     return out
 
 

@@ -340,16 +340,19 @@ uint64_t t5o_transposeV(const uint64_t* ds, int r, uint64_t i) { return transpos
 // ---- transpose = unRev . t0  (Indexable.hs:101-102, Vector.hs:295-301) ------
 // unRev with sh = [] : zh = reverse rh; out[i] = content ! transposeV rh i.
 // Pure permutation: elem_bytes in {4, 8}.
-int t5o_transpose(int elem_bytes, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT) {
+int t5o_transpose(int elem_bytes, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT, int threads) {
     if (rank < 0 || rank > 16) return 1;
     uint64_t d = 1;
     for (int a = 0; a < rank; ++a) d *= dims[a];
     std::vector<uint64_t> perm(d);
     for (uint64_t i = 0; i < d; ++i) perm[i] = transposeV(dims, rank, i);
     const char* in = (const char*)A; char* out = (char*)OUT;
-    for (size_t b = 0; b < batch; ++b)
-        for (uint64_t i = 0; i < d; ++i)
-            std::memcpy(out + (b * d + i) * elem_bytes, in + (b * d + perm[i]) * elem_bytes, elem_bytes);
+    const uint64_t* pm = perm.data();
+    par_chunks(batch, threads, [=](size_t b0, size_t b1) {
+        for (size_t b = b0; b < b1; ++b)
+            for (uint64_t i = 0; i < d; ++i)
+                std::memcpy(out + (b * d + i) * elem_bytes, in + (b * d + pm[i]) * elem_bytes, elem_bytes);
+    });
     return 0;
 }
 

@@ -9,5 +9,5 @@ from .device import (Batch, Context, DeviceError, PinnedArray, TensorException, 
                      Unsupported, WrongListLength)
 from .linear_algebra import (char_poly, det, dot, dot_sum, inverse, matmul, matmul_host, min_poly,  # noqa: F401
                              poly_eval, prod, scale, solve, tensor_product, tr, transpose, zip_with)
-from . import structure, synthetic  # noqa: F401
+from . import host, structure, synthetic  # noqa: F401
 from .structure import Nested  # noqa: F401

@@ -66,6 +66,12 @@ SIGNATURES = {
     "t5_permute_axes": (_i, [_vp, _i, _i, _u64p, ctypes.POINTER(ctypes.c_int), _vp, _vp]),
     "t5_structural_table": (_i, [_i, _i, _u64p, _u64p, _i, ctypes.POINTER(ctypes.c_uint32), _sz, _szp]),
     "t5_matmul_host": (_i, [_vp, _i, _i, _i, _i, _sz, _vp, _vp, _vp]),
+    "t5_dot_host": (_i, [_vp, _i, _i, _sz, _vp, _vp, _vp]),
+    "t5_prod_host": (_i, [_vp, _i, _i, _u64p, _i, _u64p, _i, _sz, _vp, _vp, _vp]),
+    "t5_transpose_host": (_i, [_vp, _i, _i, _u64p, _sz, _vp, _vp]),
+    "t5_det_host": (_i, [_vp, _i, _i, _sz, _vp, _vp]),
+    "t5_inverse_host": (_i, [_vp, _i, _i, _sz, _vp, _vp, _vp]),
+    "t5_solve_host": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp, _vp]),
     "t5_timer_begin": (_i, [_vp]),
     "t5_timer_end": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "t5_flush_l2": (_i, [_vp]),

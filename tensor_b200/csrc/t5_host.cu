@@ -50,8 +50,8 @@ struct NcclApi {
 
 struct HostSlot {  // staging of the host-buffer pipeline
     cudaStream_t stream = nullptr;
-    void* d[3] = {nullptr, nullptr, nullptr};
-    size_t cap[3] = {0, 0, 0};
+    void* d[4] = {nullptr, nullptr, nullptr, nullptr};   // <= 2 inputs + <= 2 outputs
+    size_t cap[4] = {0, 0, 0, 0};
 };
 
 struct t5_ctx {
@@ -403,19 +403,29 @@ int t5_dot(t5_ctx* c, int dtype, int n, const t5_buf* X, const t5_buf* Y, t5_buf
     return product_all(c, dtype, 1, n, 1, 1, X, Y, OUT, "t5_dot");
 }
 
-int t5_prod(t5_ctx* c, int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc,
-            const t5_buf* A, const t5_buf* B, t5_buf* C) {
-    if (!c || rankA < 0 || rankB < 0 || rankA > 16 || rankB > 16 || (rankA && !dimsA) || (rankB && !dimsB)) return T5_ERR_INVALID;
+// (rankA, dimsA) x (rankB, dimsB) contracted over nc indices -> the P x K . K x Q view
+static int prod_dims(int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc, int* Pp, int* Kp, int* Qp) {
+    if (rankA < 0 || rankB < 0 || rankA > 16 || rankB > 16 || (rankA && !dimsA) || (rankB && !dimsB)) return T5_ERR_INVALID;
     if (nc < 0 || nc > rankA || nc > rankB) return T5_ERR_SHAPE;
     uint64_t P = 1, K = 1, Q = 1;
-    for (int a = 0; a < rankA - nc; ++a) P *= dimsA[a];
+    for (int a = 0; a < rankA - nc; ++a) { P *= dimsA[a]; if (P > (1u << 28)) return T5_ERR_SHAPE; }
     for (int a = 0; a < nc; ++a) {
         if (dimsA[rankA - nc + a] != dimsB[a]) return T5_ERR_SHAPE;
         K *= dimsB[a];
+        if (K > (1u << 28)) return T5_ERR_SHAPE;
     }
-    for (int a = nc; a < rankB; ++a) Q *= dimsB[a];
-    if (P == 0 || K == 0 || Q == 0 || P > (1u << 28) || K > (1u << 28) || Q > (1u << 28)) return T5_ERR_SHAPE;
-    return product_all(c, dtype, (int)P, (int)K, (int)Q, nc, A, B, C, "t5_prod");
+    for (int a = nc; a < rankB; ++a) { Q *= dimsB[a]; if (Q > (1u << 28)) return T5_ERR_SHAPE; }
+    if (P == 0 || K == 0 || Q == 0) return T5_ERR_SHAPE;
+    *Pp = (int)P; *Kp = (int)K; *Qp = (int)Q;
+    return T5_OK;
+}
+
+int t5_prod(t5_ctx* c, int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc,
+            const t5_buf* A, const t5_buf* B, t5_buf* C) {
+    if (!c) return T5_ERR_INVALID;
+    int P, K, Q;
+    CHECK(prod_dims(rankA, dimsA, rankB, dimsB, nc, &P, &K, &Q));
+    return product_all(c, dtype, P, K, Q, nc, A, B, C, "t5_prod");
 }
 
 // ---- dot_sum: the one entry with a cross-device exchange ---------------------------------
@@ -511,46 +521,65 @@ static void build_perm(const std::vector<uint64_t>& dims, std::vector<uint32_t>&
     }
 }
 
-int t5_transpose(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const t5_buf* A, t5_buf* OUT) {
-    if (!c || rank < 0 || rank > 16 || (rank && !dims)) return T5_ERR_INVALID;
+// One shard of a transpose.  sq = dims with the extent-1 axes squeezed out, d = elements per item.
+// Caller holds the context lock and has set the device.
+static int transpose_shard(t5_ctx* c, int g, const Shard& s, int es, const std::vector<uint64_t>& sq, size_t d,
+                           const void* in, void* out, size_t bytes) {
+    if (sq.size() <= 1) {  // rank 0/1 (after squeezing): the identity
+        CU(c, cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s.stream));
+        return T5_OK;
+    }
+    int r = T5I_NOT_SPECIALISED;
+    if (sq.size() == 2) r = small_transpose(s, es, (int)sq[0], (int)sq[1], in, out);
+    if (r == T5I_NOT_SPECIALISED) {
+        if (s.layout != T5L_AOS) return T5_ERR_UNSUPPORTED;
+        auto it = c->perm_cache.find(sq);
+        if (it == c->perm_cache.end()) it = c->perm_cache.emplace(sq, std::vector<uint32_t*>(T5_MAX_DEVICES, nullptr)).first;
+        if (!it->second[g]) {
+            std::vector<uint32_t> perm;
+            build_perm(sq, perm);
+            uint32_t* p = nullptr;
+            CU(c, cudaMalloc(&p, perm.size() * 4));
+            CU(c, cudaMemcpy(p, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+            it->second[g] = p;
+        }
+        r = generic_permute(s, es, d, it->second[g], in, out);
+    }
+    if (r != T5I_OK) return map_internal(c, r, "t5_transpose");
+    c->launches++;
+    return T5_OK;
+}
+
+static int transpose_args(int dtype, int rank, const uint64_t* dims, std::vector<uint64_t>& sq, size_t& d) {
+    if (rank < 0 || rank > 16 || (rank && !dims)) return T5_ERR_INVALID;
     const int es = dtype_size(dtype);
     if (es != 4 && es != 8) return T5_ERR_UNSUPPORTED;
-    std::vector<uint64_t> dv(dims, dims + rank);
+    d = 1;
+    sq.clear();
+    for (int a = 0; a < rank; ++a) {
+        const uint64_t x = dims[a];
+        if (x == 0 || x > (1u << 28)) return T5_ERR_SHAPE;
+        d *= x;
+        if (d > (1u << 28)) return T5_ERR_SHAPE;
+        if (x != 1) sq.push_back(x);   // axes of extent 1 do not move data
+    }
+    return T5_OK;
+}
+
+int t5_transpose(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const t5_buf* A, t5_buf* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    std::vector<uint64_t> sq;
     size_t d = 1;
-    for (auto x : dv) { if (x == 0 || x > (1u << 28)) return T5_ERR_SHAPE; d *= x; if (d > (1u << 28)) return T5_ERR_SHAPE; }
+    CHECK(transpose_args(dtype, rank, dims, sq, d));
+    const int es = dtype_size(dtype);
     CHECK(check(c, A, dtype, d, nullptr));
     CHECK(check(c, OUT, dtype, d, A));
     if (OUT == A) return T5_ERR_INVALID;
-    // squeeze axes of extent 1: they do not move data
-    std::vector<uint64_t> sq;
-    for (auto x : dv) if (x != 1) sq.push_back(x);
     std::lock_guard<std::mutex> lk(c->mu);
     for (int g = 0; g < c->ndev; ++g) {
         if (!A->count[g]) continue;
         CU(c, cudaSetDevice(c->dev[g]));
-        Shard s = shard_of(c, A, g);
-        if (sq.size() <= 1) {  // rank 0/1 (after squeezing): the identity
-            CU(c, cudaMemcpyAsync(OUT->ptr[g], A->ptr[g], A->bytes[g], cudaMemcpyDeviceToDevice, c->stream[g]));
-            continue;
-        }
-        int r = T5I_NOT_SPECIALISED;
-        if (sq.size() == 2) r = small_transpose(s, es, (int)sq[0], (int)sq[1], A->ptr[g], OUT->ptr[g]);
-        if (r == T5I_NOT_SPECIALISED) {
-            if (A->layout != T5_AOS) return T5_ERR_UNSUPPORTED;
-            auto it = c->perm_cache.find(sq);
-            if (it == c->perm_cache.end()) it = c->perm_cache.emplace(sq, std::vector<uint32_t*>(T5_MAX_DEVICES, nullptr)).first;
-            if (!it->second[g]) {
-                std::vector<uint32_t> perm;
-                build_perm(sq, perm);
-                uint32_t* p = nullptr;
-                CU(c, cudaMalloc(&p, perm.size() * 4));
-                CU(c, cudaMemcpy(p, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
-                it->second[g] = p;
-            }
-            r = generic_permute(s, es, d, it->second[g], A->ptr[g], OUT->ptr[g]);
-        }
-        if (r != T5I_OK) return map_internal(c, r, "t5_transpose");
-        c->launches++;
+        CHECK(transpose_shard(c, g, shard_of(c, A, g), es, sq, d, A->ptr[g], OUT->ptr[g], A->bytes[g]));
     }
     return T5_OK;
 }
@@ -745,9 +774,12 @@ int t5_scale(t5_ctx* c, int dtype, const void* scalar, const t5_buf* A, t5_buf* 
 }
 
 // ---- host-buffer pipeline --------------------------------------------------------------------
-// The batch is cut into chunks; chunk j of device g runs on slot j % 3 (own stream, own
-// staging buffers): H2D(A), H2D(B), kernel, D2H(C).  With three slots the two PCIe
-// directions and the SMs work on different chunks at the same time.
+// The end-to-end form of every hot-path operation: operands and results are HOST AoS arrays
+// (what a Haskell instance method on ordinary tensors holds).  The batch is cut into chunks;
+// chunk j of device g runs on slot j % 3 (own stream, own staging buffers): H2D of the
+// inputs, the kernel, D2H of the results.  With three slots the two PCIe directions and the
+// SMs work on different chunks at the same time.  Pinned host memory (t5_pinned_alloc) gives
+// full PCIe speed; pageable memory is correct but staged by the driver.
 static int slot_reserve(t5_ctx* c, HostSlot& s, int i, size_t bytes) {
     if (!s.stream) CU(c, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     if (s.cap[i] >= bytes) return T5_OK;
@@ -757,45 +789,153 @@ static int slot_reserve(t5_ctx* c, HostSlot& s, int i, size_t bytes) {
     return T5_OK;
 }
 
-int t5_matmul_host(t5_ctx* c, int dtype, int m, int k, int n, size_t batch, const void* A, const void* B, void* C) {
-    if (!c) return T5_ERR_INVALID;
-    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
-    if (m < 1 || k < 1 || n < 1) return T5_ERR_SHAPE;
-    if (batch && (!A || !B || !C)) return T5_ERR_INVALID;
-    const size_t es = dtype_size(dtype);
-    const size_t ia = (size_t)m * k * es, ib = (size_t)k * n * es, ic = (size_t)m * n * es;
+struct HostOperand { const void* in; void* out; size_t item_bytes; };   // exactly one of in / out is set
+
+// launch(g, shard, dev_ptrs[]) -> T5_* code; dev_ptrs follow the order of `ops`.
+extern "C++" {
+template <class Launch>
+static int host_pipeline(t5_ctx* c, size_t batch, const HostOperand* ops, int nops, Launch launch) {
+    if (nops < 1 || nops > 4) return T5_ERR_INVALID;
+    size_t per_item = 0;
+    for (int i = 0; i < nops; ++i) {
+        if (batch && !ops[i].in && !ops[i].out) return T5_ERR_INVALID;
+        per_item += ops[i].item_bytes;
+    }
     // ~32 MiB of operands per chunk, a multiple of 256 items
-    size_t chunk = (32ull << 20) / (ia + ib + ic);
+    size_t chunk = (32ull << 20) / (per_item ? per_item : 1);
     chunk = chunk < 256 ? 256 : chunk / 256 * 256;
     std::lock_guard<std::mutex> lk(c->mu);
-    for (int g = 0; g < c->ndev; ++g) {
+    int rc = T5_OK;
+    for (int g = 0; g < c->ndev && rc == T5_OK; ++g) {
         size_t first, count;
         t5_partition(batch, c->ndev, g, &first, &count);
         if (!count) continue;
         CU(c, cudaSetDevice(c->dev[g]));
         size_t j = 0;
-        for (size_t off = 0; off < count; off += chunk, ++j) {
+        for (size_t off = 0; off < count && rc == T5_OK; off += chunk, ++j) {
             const size_t cnt = count - off < chunk ? count - off : chunk;
             HostSlot& s = c->slots[g][j % 3];
-            CHECK(slot_reserve(c, s, 0, chunk * ia));
-            CHECK(slot_reserve(c, s, 1, chunk * ib));
-            CHECK(slot_reserve(c, s, 2, chunk * ic));
+            void* dev[4] = {nullptr, nullptr, nullptr, nullptr};
+            for (int i = 0; i < nops; ++i) {
+                CHECK(slot_reserve(c, s, i, chunk * ops[i].item_bytes));
+                dev[i] = s.d[i];
+            }
             const size_t it = first + off;
-            CU(c, cudaMemcpyAsync(s.d[0], (const char*)A + it * ia, cnt * ia, cudaMemcpyHostToDevice, s.stream));
-            CU(c, cudaMemcpyAsync(s.d[1], (const char*)B + it * ib, cnt * ib, cudaMemcpyHostToDevice, s.stream));
+            for (int i = 0; i < nops; ++i)
+                if (ops[i].in)
+                    CU(c, cudaMemcpyAsync(dev[i], (const char*)ops[i].in + it * ops[i].item_bytes, cnt * ops[i].item_bytes,
+                                          cudaMemcpyHostToDevice, s.stream));
             Shard sh; sh.stream = s.stream; sh.layout = T5L_AOS; sh.count = cnt; sh.soa_stride = 0; sh.first = it;
             sh.sched = (unsigned long long*)((char*)c->scratch[g] + SCHED_OFF) + 2 * (1 + j % 3);
-            int r = product_shard(sh, dtype, m, k, n, 1, s.d[0], s.d[1], s.d[2]);
-            if (r != T5I_OK) return map_internal(c, r, "t5_matmul_host");
-            c->launches++;
-            CU(c, cudaMemcpyAsync((char*)C + it * ic, s.d[2], cnt * ic, cudaMemcpyDeviceToHost, s.stream));
+            rc = launch(g, sh, dev);
+            if (rc != T5_OK) break;
+            for (int i = 0; i < nops; ++i)
+                if (ops[i].out)
+                    CU(c, cudaMemcpyAsync((char*)ops[i].out + it * ops[i].item_bytes, dev[i], cnt * ops[i].item_bytes,
+                                          cudaMemcpyDeviceToHost, s.stream));
         }
     }
+    // drain every slot even after an error: the caller's host buffers must not be in flight on return
     for (int g = 0; g < c->ndev; ++g) {
-        CU(c, cudaSetDevice(c->dev[g]));
-        for (auto& s : c->slots[g]) if (s.stream) CU(c, cudaStreamSynchronize(s.stream));
+        cudaSetDevice(c->dev[g]);
+        for (auto& s : c->slots[g])
+            if (s.stream) {
+                cudaError_t e = cudaStreamSynchronize(s.stream);
+                if (e != cudaSuccess && rc == T5_OK) rc = cuda_fail(c, e, "host pipeline sync");
+            }
     }
-    return T5_OK;
+    return rc;
+}
+}  // extern "C++"
+
+static int product_host(t5_ctx* c, int dtype, int P, int K, int Q, int nc, size_t batch, const void* A, const void* B, void* C,
+                        const char* what) {
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (P < 1 || K < 1 || Q < 1) return T5_ERR_SHAPE;
+    const size_t es = dtype_size(dtype);
+    const HostOperand ops[3] = {{A, nullptr, (size_t)P * K * es}, {B, nullptr, (size_t)K * Q * es}, {nullptr, C, (size_t)P * Q * es}};
+    return host_pipeline(c, batch, ops, 3, [&](int, const Shard& sh, void* const* d) {
+        int r = product_shard(sh, dtype, P, K, Q, nc, d[0], d[1], d[2]);
+        if (r != T5I_OK) return map_internal(c, r, what);
+        c->launches++;
+        return (int)T5_OK;
+    });
+}
+
+int t5_matmul_host(t5_ctx* c, int dtype, int m, int k, int n, size_t batch, const void* A, const void* B, void* C) {
+    if (!c) return T5_ERR_INVALID;
+    return product_host(c, dtype, m, k, n, 1, batch, A, B, C, "t5_matmul_host");
+}
+
+int t5_dot_host(t5_ctx* c, int dtype, int n, size_t batch, const void* X, const void* Y, void* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    return product_host(c, dtype, 1, n, 1, 1, batch, X, Y, OUT, "t5_dot_host");
+}
+
+int t5_prod_host(t5_ctx* c, int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc,
+                 size_t batch, const void* A, const void* B, void* C) {
+    if (!c) return T5_ERR_INVALID;
+    int P, K, Q;
+    CHECK(prod_dims(rankA, dimsA, rankB, dimsB, nc, &P, &K, &Q));
+    return product_host(c, dtype, P, K, Q, nc, batch, A, B, C, "t5_prod_host");
+}
+
+int t5_transpose_host(t5_ctx* c, int dtype, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    std::vector<uint64_t> sq;
+    size_t d = 1;
+    CHECK(transpose_args(dtype, rank, dims, sq, d));
+    const int es = dtype_size(dtype);
+    const HostOperand ops[2] = {{A, nullptr, d * es}, {nullptr, OUT, d * es}};
+    return host_pipeline(c, batch, ops, 2, [&](int g, const Shard& sh, void* const* dv) {
+        return transpose_shard(c, g, sh, es, sq, d, dv[0], dv[1], sh.count * d * es);
+    });
+}
+
+int t5_det_host(t5_ctx* c, int dtype, int n, size_t batch, const void* A, void* OUT) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    const size_t es = dtype_size(dtype);
+    const HostOperand ops[2] = {{A, nullptr, (size_t)n * n * es}, {nullptr, OUT, es}};
+    return host_pipeline(c, batch, ops, 2, [&](int, const Shard& sh, void* const* d) {
+        int r = small_det(sh, dtype, n, d[0], d[1]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_det(sh, dtype, n, d[0], d[1]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_det_host");
+        c->launches++;
+        return (int)T5_OK;
+    });
+}
+
+int t5_inverse_host(t5_ctx* c, int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* status) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1) return T5_ERR_SHAPE;
+    const size_t es = dtype_size(dtype);
+    const HostOperand ops[3] = {{A, nullptr, (size_t)n * n * es}, {nullptr, OUT, (size_t)n * n * es}, {nullptr, status, 1}};
+    return host_pipeline(c, batch, ops, 3, [&](int, const Shard& sh, void* const* d) {
+        int r = small_inverse(sh, dtype, n, d[0], d[1], d[2]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_solve(sh, dtype, n, n, true, d[0], nullptr, d[1], d[2]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_inverse_host");
+        c->launches++;
+        return (int)T5_OK;
+    });
+}
+
+int t5_solve_host(t5_ctx* c, int dtype, int n, int nrhs, size_t batch, const void* A, const void* B, void* X, uint8_t* status) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (n < 1 || nrhs < 1) return T5_ERR_SHAPE;
+    const size_t es = dtype_size(dtype);
+    const HostOperand ops[4] = {{A, nullptr, (size_t)n * n * es}, {B, nullptr, (size_t)n * nrhs * es},
+                                {nullptr, X, (size_t)n * nrhs * es}, {nullptr, status, 1}};
+    return host_pipeline(c, batch, ops, 4, [&](int, const Shard& sh, void* const* d) {
+        int r = small_solve(sh, dtype, n, nrhs, d[0], d[1], d[2], d[3]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_solve(sh, dtype, n, nrhs, false, d[0], d[1], d[2], d[3]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_solve_host");
+        c->launches++;
+        return (int)T5_OK;
+    });
 }
 
 // ---- measurement helpers -----------------------------------------------------------------------

@@ -12,12 +12,16 @@ extern "C" {
 int t5o_fill(int dtype, uint64_t seed, uint64_t op_id, uint64_t first_elem, size_t count, void* out);
 int t5o_matmul(int dtype, int m, int k, int n, size_t batch, const void* A, const void* B, void* C, int threads);
 int t5o_dot(int dtype, int n, size_t batch, const void* X, const void* Y, void* OUT, int threads);
-int t5o_transpose(int elem_bytes, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT);
+int t5o_transpose(int elem_bytes, int rank, const uint64_t* dims, size_t batch, const void* A, void* OUT, int threads);
 int t5o_prod(int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint64_t* dimsB, int nc, size_t batch,
              const void* A, const void* B, void* C, int threads);
 int t5o_det(int dtype, int n, size_t batch, const void* A, void* OUT, int threads);
 int t5o_inverse(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* status, int threads);
 int t5o_solve(int dtype, int n, int nrhs, size_t batch, const void* A, const void* B, void* X, uint8_t* status, int threads);
+int t5o_trace(int dtype, int n, size_t batch, const void* A, void* OUT, int threads);
+int t5o_poly_eval(int dtype, int n, const void* coeffs, int ncoef, size_t batch, const void* A, void* OUT, int threads);
+int t5o_char_poly(int dtype, int n, size_t batch, const void* A, void* OUT, int threads);
+int t5o_min_poly(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* degree, int threads);
 }
 
 static int failures = 0;
@@ -68,7 +72,7 @@ int main() {
         Batch<double, 4, 3, 2> T = transpose(A);
         std::vector<double> want(n * 24);
         const uint64_t d[3] = {2, 3, 4};
-        t5o_transpose(8, 3, d, n, a.data(), want.data());
+        t5o_transpose(8, 3, d, n, a.data(), want.data(), 1);
         expect_bits("transpose (Tensor [2,3,4])", T.to_list(), want);
         expect_bits("transpose . transpose == id", transpose(T).to_list(), a);
     }
@@ -97,6 +101,27 @@ int main() {
         auto [x, st2] = solve(A, Batch<double, 4>::from_list(ctx, n, b));
         expect_bits("solve", x.to_list(), wx);
         expect_bits("solve status", st2.to_list(), ws2);
+    }
+    {   // the rest of SquareMatrix: tr, polyEval, charPoly, minPoly
+        auto a = synth<double>(0, SA, 7, n * 9);
+        for (size_t i = 0; i < n; i += 7) {              // exact structure: 2 I has minimal polynomial x - 2
+            for (int e = 0; e < 9; ++e) a[i * 9 + e] = (e % 4 == 0) ? 2.0 : 0.0;
+        }
+        auto A = Batch<double, 3, 3>::from_list(ctx, n, a);
+        std::vector<double> wt(n), wp(n * 9), wc(n * 4), wm(n * 4);
+        std::vector<uint8_t> wdeg(n);
+        const std::vector<double> coeffs = {0.5, -1.25, 2.0, 0.75};
+        t5o_trace(0, 3, n, a.data(), wt.data(), 1);
+        expect_bits("tr (Matrix 3 3 Double)", tr(A).to_list(), wt);
+        t5o_poly_eval(0, 3, coeffs.data(), 4, n, a.data(), wp.data(), 1);
+        expect_bits("polyEval", poly_eval(A, coeffs).to_list(), wp);
+        t5o_char_poly(0, 3, n, a.data(), wc.data(), 1);
+        Batch<double, 4> cp = char_poly(A);
+        expect_bits("charPoly", cp.to_list(), wc);
+        t5o_min_poly(0, 3, n, a.data(), wm.data(), wdeg.data(), 1);
+        auto [mp, deg] = min_poly(A);
+        expect_bits("minPoly", mp.to_list(), wm);
+        expect_bits("minPoly degree", deg.to_list(), wdeg);
     }
     {   // fromList length check
         bool threw = false;
