@@ -17,6 +17,9 @@
 // drains between items.  Rounding differs from the sequential fold of the oracle (the
 // tensor pipe fuses and re-associates inside a k4 step): tests hold this kernel to
 // |delta| <= 1e-12 * sum_j |a_ij||b_jk|, the tolerance north_star states for Double.
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
 #include "t5_device.cuh"
 #include "t5_internal.h"
 
@@ -167,26 +170,246 @@ __global__ void __launch_bounds__(THREADS, 1) dmma_gemm_kernel(Args p) {
 }
 }  // namespace dg
 
+// ---------------------------------------------------------------------------------------
+// TMA + mbarrier variant (default).  Same warp tiling and DMMA fragments as above, but the
+// operand ring is filled by ONE producer lane with cp.async.bulk.tensor (3-D tensor maps,
+// SWIZZLE_128B) and handed over through full/empty mbarriers, so the eight DMMA warps never
+// meet at a CTA barrier: they drift apart, one warp of a scheduler's pair stores its
+// accumulators while the other keeps the FP64 tensor pipe busy, and no DMMA-warp issue slot
+// or register goes to address generation for the copies.
+//
+//   A map: dims {16, count*M, K/16}, box {16, 128, 2}  -> shared [2][128 rows][16 doubles]
+//   B map: dims {16, count*K, N/16}, box {16, 32, 8}   -> shared [8][32 k-rows][16 doubles]
+//   (128-byte rows, 16-B chunks XOR-ed with row & 7 by the TMA unit; stage bases 1024-B aligned)
+//
+// The four k of a DMMA step are free to be any four k of the chunk as long as A and B agree.
+// Lane (g, t) of step s uses k = (t>>1) + 2(s&1) + 4(t&1) + 8((s>>1)&1) + 16(s>>2): with the
+// 128-B swizzle this makes every fragment LDS.64 of a warp hit 16 distinct bank pairs twice
+// (2 wavefronts for 256 B, the minimum) for both operands without any padding.
+namespace dt {
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+// 8 DMMA warps (two warpgroups) + one producer warpgroup of which a single lane works.  Registers
+// are a per-scheduler pool (3 warps x 168 at launch); setmaxnreg moves the producer group's share
+// to the DMMA warps (2 x 232 + 40 <= 512 per scheduler lane), which need 64 accumulators + fragments.
+constexpr int CONSUMER_WARPS = 8, THREADS = (CONSUMER_WARPS + 4) * 32;
+constexpr int A_STAGE = BM * BK * 8, B_STAGE = BK * BN * 8, STAGE = A_STAGE + B_STAGE;
+constexpr int SMEM = STAGES * STAGE + 1024;     // + slack to align the ring to 1024 B
+static_assert(SMEM <= 227 * 1024, "ring does not fit");
+
+struct Args {
+    double* C;
+    int M, N, K;
+    unsigned long long count;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spins on try_wait; a ring that never fills (bad tensor map) traps instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES];       // full[0..S), empty[S..2S)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const unsigned bar0 = smem_u32(bars);
+    const int tiles_m = p.M / BM, tiles_n = p.N / BN, kch = p.K / BK;
+    const unsigned long long tiles_per_item = (unsigned long long)tiles_m * tiles_n;
+    const unsigned long long n_tiles = p.count * tiles_per_item;
+
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);                                 // full: the producer's expect_tx arrive
+            mbar_init(bar0 + 8 * (STAGES + s), CONSUMER_WARPS);         // empty: one arrive per DMMA warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= CONSUMER_WARPS) {
+        // ---- producer: one lane walks (tile, K chunk) in the consumers' order ----
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (warp != CONSUMER_WARPS || lane != 0) return;
+        unsigned it = 0;
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const unsigned long long item = tile / tiles_per_item;
+            const int rem = (int)(tile - item * tiles_per_item);
+            const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+            const int a_row = (int)(item * p.M) + tm * BM;
+            const int b_row = (int)(item * p.K);
+            for (int kc = 0; kc < kch; ++kc, ++it) {
+                const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(bar0 + 8 * (STAGES + s), ph ^ 1);              // stage released by all 8 warps
+                const unsigned full = bar0 + 8 * s;
+                mbar_expect_tx(full, STAGE);
+                tma_load_3d(ring + s * STAGE, &mapA, full, 0, a_row, kc * (BK / 16));
+                tma_load_3d(ring + s * STAGE + A_STAGE, &mapB, full, 0, b_row + kc * BK, tn * (BN / 16));
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: 8 DMMA warps, 2 x 4 over the tile ----
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    const int g = lane >> 2, t = lane & 3, t0 = t & 1, t1 = t >> 1;
+    const int wm = warp >> 2, wn = warp & 3;
+    // runtime parts of the swizzled fragment addresses (see the header comment)
+    const unsigned a_thr = (unsigned)(wm * 64 + g) * 128u + (unsigned)t1 * 8u;
+    const unsigned a_x = (unsigned)(g ^ (2 * t0));                               // chunk = (cs | 2 t0) ^ g = cs ^ a_x
+    const unsigned b_thr = (unsigned)(wn * 2) * 4096u + (unsigned)(t1 + 4 * t0) * 128u + (unsigned)(g & 1) * 8u;
+    const unsigned b_x = (unsigned)((g >> 1) ^ t1 ^ (4 * t0));                   // chunk ^ (k & 7) = cx ^ b_x
+
+    double acc[8][4][2];
+    unsigned it = 0;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        #pragma unroll
+        for (int i = 0; i < 8; ++i)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kc = 0; kc < kch; ++kc, ++it) {
+            const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(bar0 + 8 * s, ph);                                 // TMA bytes have landed
+            const unsigned As = ring + s * STAGE + a_thr, Bs = ring + s * STAGE + A_STAGE + b_thr;
+            #pragma unroll
+            for (int st = 0; st < BK / 4; ++st) {
+                const unsigned cs = (unsigned)((st & 1) + 4 * ((st >> 1) & 1));
+                const unsigned a_off = (unsigned)(st >> 2) * 16384u + ((cs ^ a_x) << 4);
+                const unsigned k_imm = (unsigned)(2 * (st & 1) + 8 * ((st >> 1) & 1) + 16 * (st >> 2)) * 128u;
+                double a[8], b[4];
+                #pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = lds_f64(As + a_off + (unsigned)i * 1024u);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned cx = (unsigned)(4 * (j & 1)) ^ (unsigned)(2 * (st & 1));
+                    b[j] = lds_f64(Bs + k_imm + (unsigned)(j >> 1) * 4096u + ((cx ^ b_x) << 4));
+                }
+                #pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) dg::dmma(acc[i][j], a[i], b[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + s));         // this warp is done with the stage
+        }
+
+        const unsigned long long item = tile / tiles_per_item;
+        const int rem = (int)(tile - item * tiles_per_item);
+        const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+        double* Cg = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + wm * 64 + g) * p.N + tn * BN + wn * 32 + 2 * t;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i)
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 v;
+                reinterpret_cast<double*>(&v)[0] = acc[i][j][0];
+                reinterpret_cast<double*>(&v)[1] = acc[i][j][1];
+                st_global_stream16(Cg + (size_t)(i * 8) * p.N + j * 8, v);
+            }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+// rows x cols doubles, row-major, viewed as {16, rows, cols/16}; box {16, box_rows, box_grp}
+static bool make_map(CUtensorMap* map, const void* base, unsigned long long rows, int cols, int box_rows, int box_grp) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {16, rows, (cuuint64_t)(cols / 16)};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 8, 128};
+    const cuuint32_t box[3] = {16, (cuuint32_t)box_rows, (cuuint32_t)box_grp};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int launch(const Shard& s, int m, int k, int n, const double* A, const double* B, double* C, int sms) {
+    // TMA coordinates are int32: walk the shard in pieces whose row counts fit
+    const size_t per = (size_t)0x7fffffff / (size_t)(m > k ? m : k);
+    for (size_t off = 0; off < s.count; off += per) {
+        const size_t cnt = s.count - off < per ? s.count - off : per;
+        CUtensorMap ma, mb;
+        if (!make_map(&ma, A + off * (size_t)m * k, (unsigned long long)cnt * m, k, BM, BK / 16)) return T5I_CUDA;
+        if (!make_map(&mb, B + off * (size_t)k * n, (unsigned long long)cnt * k, n, BK, BN / 16)) return T5I_CUDA;
+        const unsigned long long tiles = (unsigned long long)cnt * (m / BM) * (n / BN);
+        const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
+        Args a{C + off * (size_t)m * n, m, n, k, (unsigned long long)cnt};
+        dmma_tma_kernel<<<grid, THREADS, SMEM, s.stream>>>(ma, mb, a);
+        if (cudaGetLastError() != cudaSuccess) return T5I_CUDA;
+    }
+    return T5I_OK;
+}
+}  // namespace dt
+
+
 int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
-    using namespace dg;
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    if (m % BM || n % BN || k % BK || k < BK) return T5I_NOT_SPECIALISED;
+    if (m % dg::BM || n % dg::BN || k % dg::BK || k < dg::BK) return T5I_NOT_SPECIALISED;
+    // T5_DMMA=cpasync selects the cp.async-ring kernel (kept for A/B measurements); default is the TMA kernel
+    static const bool use_tma = [] { const char* e = getenv("T5_DMMA"); return !(e && !strcmp(e, "cpasync")); }();
     static bool configured[T5_MAX_DEVICES] = {false};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
     if (!configured[dev]) {
-        if (cudaFuncSetAttribute(dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return T5I_CUDA;
+        if (cudaFuncSetAttribute(dg::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM) != cudaSuccess) return T5I_CUDA;
+        if (cudaFuncSetAttribute(dt::dmma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dt::SMEM) != cudaSuccess) return T5I_CUDA;
         configured[dev] = true;
     }
     if (s.count == 0) return T5I_OK;
-    if (!s.sched) return T5I_CUDA;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
-    const unsigned long long tiles = (unsigned long long)s.count * (m / BM) * (n / BN);
+    if (use_tma) return dt::launch(s, m, k, n, (const double*)A, (const double*)B, (double*)C, sms);
+    if (!s.sched) return T5I_CUDA;
+    const unsigned long long tiles = (unsigned long long)s.count * (m / dg::BM) * (n / dg::BN);
     const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
-    Args a{(const double*)A, (const double*)B, (double*)C, m, n, k, (unsigned long long)s.count, s.sched};
-    dmma_gemm_kernel<<<grid, THREADS, SMEM, s.stream>>>(a);
+    dg::Args a{(const double*)A, (const double*)B, (double*)C, m, n, k, (unsigned long long)s.count, s.sched};
+    dg::dmma_gemm_kernel<<<grid, dg::THREADS, dg::SMEM, s.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
 
