@@ -63,6 +63,8 @@ WORKLOADS = {
                                   desc="1Mi rank-3 8x8x8 Double transposes (any-rank gather)"),
     "matmul128_f64_64K": dict(op="matmul", dtype="f64", m=128, k=128, n=128, batch=1 << 16, bytes=393216, flops=4194304, bound="tensor",
                               desc="64Ki 128x128 Double .*. on FP64 tensor cores (configs[4])"),
+    "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
+                              desc="256Ki 64x64 Double .*. on FP64 tensor cores (smallest DMMA shape; 5.3 flop/B, HBM floor ~= tensor floor)"),
 }
 HEADLINE = "matmul4x4_f32_16M"
 EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpose4x4_f32_16M", "matvec4_f32_16M",
@@ -70,6 +72,20 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
+
+
+def pcie_roofline(h2d, d2h, seconds_per_step):
+    """e2e is bound by the PCIe Gen5 x16 link, not HBM: floor = the slower direction at its measured
+    one-direction pinned-copy rate (tools/pcie_peak.cu -> profiles/r01_pcie_peak.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_pcie_peak.json")) as f:
+            pk = json.load(f)
+    except OSError:
+        return None
+    floor = max(h2d / (pk["h2d_32MiB"] * 1e9), d2h / (pk["d2h_32MiB"] * 1e9))
+    return {"bound": "pcie", "h2d_peak": pk["h2d_32MiB"], "d2h_peak": pk["d2h_32MiB"], "unit": "GB/s",
+            "achieved_h2d": h2d / seconds_per_step / 1e9, "achieved_d2h": d2h / seconds_per_step / 1e9,
+            "frac": floor / seconds_per_step, "peak_source": "profiles/r01_pcie_peak.json (pinned cudaMemcpyAsync, this pool's B200 box)"}
 
 
 def load_peaks():
@@ -482,14 +498,15 @@ def ours(args):
         hc.check()
         e2e = {"value": hc.batch * world * e_steps / el, "unit": "matrices/s", "h2d_bytes_per_step": int(hc.h2d),
                "d2h_bytes_per_step": int(hc.d2h), "steps": e_steps, "batch_per_gpu": hc.batch,
-               "api": hc.api + " (pinned host buffers, 3-slot H2D/kernel/D2H pipeline, wall clock around the calls)"}
+               "api": hc.api + " (pinned host buffers, 3-slot H2D/kernel/D2H pipeline, wall clock around the calls)",
+               "roofline": pcie_roofline(hc.h2d, hc.d2h, el / e_steps)}
         hc.free()
     ring.free()
 
     # ---- the other BASELINE configs (explanatory; not the headline) ----------------------------------
     others = {}
     if args.all and world == 1:
-        for name in EXTRAS + (["matmul128_f64_64K"] if args.big else []):
+        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K"] if args.big else []):
             ww = WORKLOADS[name]
             try:
                 st = StepRing(ctx, tb, ww)
@@ -555,7 +572,8 @@ def main():
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--all", action="store_true", default=True, help="also time the other BASELINE configs (N=1)")
     ap.add_argument("--headline-only", dest="all", action="store_false")
-    ap.add_argument("--big", action="store_true", help="include the 25.8 GB 128x128 Double config in --all")
+    ap.add_argument("--big", action="store_true", default=True, help="include the 25.8 GB 128x128 / 64x64 Double tensor-core configs in --all (default)")
+    ap.add_argument("--no-big", dest="big", action="store_false")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

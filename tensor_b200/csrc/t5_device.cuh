@@ -22,6 +22,31 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------
+// The persistent kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (pdl_launch, below): `pdl_trigger` lets the NEXT kernel of the stream be rasterised onto SMs as
+// this grid's CTAs retire, `pdl_wait` blocks it until this grid has finished and its writes (results
+// and the re-armed tile-scheduler words) are visible.  That hides the ~2-3 us launch/ramp gap that
+// dominates the 1Mi-item configs (a 226 MB stream is 35 us of HBM time).  Both are no-ops for a
+// plain <<<>>> launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+template <class Kern, class Args>
+static inline cudaError_t pdl_launch(Kern kern, int grid, int threads, size_t smem, cudaStream_t stream, const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args);
+}
+
 // ---- streaming 16-byte global store / load (no L1 allocation) -----------------
 __device__ __forceinline__ void st_global_stream16(void* gdst, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"l"(gdst), "r"(v.x), "r"(v.y),

@@ -4,6 +4,8 @@
 // Compiled with -fmad=false (bit-exact against the oracle's multiply-round-add).
 #include "t5_device.cuh"
 #include "t5_internal.h"
+#include <mutex>
+#include <unordered_map>
 
 namespace t5 {
 
@@ -14,6 +16,28 @@ static inline int sm_count() {
     return sms > 0 ? sms : T5_SM_COUNT_FALLBACK;
 }
 static inline int ok() { return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA; }
+
+// Persistent grid-stride kernels are launched with exactly as many CTAs as can be RESIDENT
+// (occupancy x SMs).  A fixed "8 per SM" put 1184 CTAs on 888 slots for the 40-register gather
+// kernel: a second, one-third-full wave that cost 30% (ncu, profiles/r01c).
+static int resident_blocks(const void* kern, int threads) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(kern);
+    if (it != cache.end()) return it->second;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 2048 / threads / 2;
+    }
+    cache[kern] = occ;
+    return occ;
+}
+static inline int resident_grid(const void* kern, int threads, size_t units) {
+    const size_t cap = (size_t)sm_count() * resident_blocks(kern, threads);
+    return (int)(units < cap ? (units ? units : 1) : cap);
+}
 
 // =====================================================================================
 // prod n: per item C[P x Q] = A[P x K] . B[K x Q]; consecutive threads
@@ -77,9 +101,7 @@ static int prod_launch(const Shard& s, int P, int K, int Q, int nc, const void* 
     int G = (int)((THREADS * 8 + PQv - 1) / PQv);
     if (G < 1) G = 1;
     if ((long long)G * PQv > 0x3fffffff) return T5I_UNSUPPORTED;
-    size_t units = (s.count + G - 1) / G;
-    size_t cap = (size_t)sm_count() * 8;
-    int grid = (int)(units < cap ? units : cap);
+    const int grid = resident_grid((const void*)prod_kernel<T, VEC, THREADS>, THREADS, (s.count + G - 1) / G);
     prod_kernel<T, VEC, THREADS><<<grid, THREADS, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, K, Q, nc,
                                                                  (unsigned long long)s.count, G);
     return ok();
@@ -175,14 +197,20 @@ template <class T, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 gather_kernel(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ table, unsigned d_in,
               unsigned d_out, unsigned long long count, int G) {
+    const unsigned step_q = THREADS / d_out, step_r = THREADS - step_q * d_out;
     for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
         const unsigned long long left = count - g0;
         const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
         const unsigned total = gc * d_out;
+        // (item, element) of this thread's l-th output advance by constant steps: no division in the loop
+        unsigned il = threadIdx.x / d_out, i = threadIdx.x - il * d_out;
+        const T* src = in + (size_t)g0 * d_in;
+        T* dst = out + (size_t)g0 * d_out;
+        #pragma unroll 4
         for (unsigned l = threadIdx.x; l < total; l += THREADS) {
-            const unsigned il = l / d_out;
-            const unsigned i = l - il * d_out;
-            out[(size_t)(g0 + il) * d_out + i] = __ldg(in + (size_t)(g0 + il) * d_in + __ldg(table + i));
+            dst[l] = __ldg(src + (size_t)il * d_in + __ldg(table + i));
+            il += step_q; i += step_r;
+            if (i >= d_out) { i -= d_out; ++il; }
         }
     }
 }
@@ -192,26 +220,30 @@ template <class T, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 gather2_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ out, const uint32_t* __restrict__ table,
                unsigned dA, unsigned dB, unsigned d_out, unsigned long long count, int G) {
+    const unsigned step_q = THREADS / d_out, step_r = THREADS - step_q * d_out;
     for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
         const unsigned long long left = count - g0;
         const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
         const unsigned total = gc * d_out;
+        unsigned il = threadIdx.x / d_out, i = threadIdx.x - il * d_out;
+        const T* srcA = A + (size_t)g0 * dA;
+        const T* srcB = B + (size_t)g0 * dB;
+        T* dst = out + (size_t)g0 * d_out;
+        #pragma unroll 4
         for (unsigned l = threadIdx.x; l < total; l += THREADS) {
-            const unsigned il = l / d_out;
-            const unsigned i = l - il * d_out;
             const unsigned v = __ldg(table + i);
-            out[(size_t)(g0 + il) * d_out + i] = v < dA ? __ldg(A + (size_t)(g0 + il) * dA + v) : __ldg(B + (size_t)(g0 + il) * dB + (v - dA));
+            dst[l] = v < dA ? __ldg(srcA + (size_t)il * dA + v) : __ldg(srcB + (size_t)il * dB + (v - dA));
+            il += step_q; i += step_r;
+            if (i >= d_out) { i -= d_out; ++il; }
         }
     }
 }
 
-static int gather_geometry(size_t count, size_t d_out, int threads, int* G) {
+static int gather_geometry(const void* kern, size_t count, size_t d_out, int threads, int* G) {
     int g = (int)((threads * 16 + d_out - 1) / d_out);
     if (g < 1) g = 1;
     *G = g;
-    size_t units = (count + g - 1) / g;
-    size_t cap = (size_t)sm_count() * 8;
-    return (int)(units < cap ? units : cap);
+    return resident_grid(kern, threads, (count + g - 1) / g);
 }
 
 int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, const uint32_t* table_dev, const void* A, void* O) {
@@ -220,7 +252,8 @@ int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, co
     if (s.count == 0 || d_out == 0) return T5I_OK;
     if (d_in > (1u << 28) || d_out > (1u << 28)) return T5I_UNSUPPORTED;
     int G;
-    const int grid = gather_geometry(s.count, d_out, THREADS, &G);
+    const int grid = gather_geometry(elem_bytes == 8 ? (const void*)gather_kernel<unsigned long long, THREADS>
+                                                     : (const void*)gather_kernel<unsigned, THREADS>, s.count, d_out, THREADS, &G);
     if (elem_bytes == 8)
         gather_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (unsigned long long*)O, table_dev, (unsigned)d_in, (unsigned)d_out, s.count, G);
     else if (elem_bytes == 4)
@@ -237,7 +270,8 @@ int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t
     if (s.count == 0 || d_out == 0) return T5I_OK;
     if (dA + dB > (1u << 28) || d_out > (1u << 28)) return T5I_UNSUPPORTED;
     int G;
-    const int grid = gather_geometry(s.count, d_out, THREADS, &G);
+    const int grid = gather_geometry(elem_bytes == 8 ? (const void*)gather2_kernel<unsigned long long, THREADS>
+                                                     : (const void*)gather2_kernel<unsigned, THREADS>, s.count, d_out, THREADS, &G);
     if (elem_bytes == 8)
         gather2_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (const unsigned long long*)B, (unsigned long long*)O, table_dev, (unsigned)dA, (unsigned)dB, (unsigned)d_out, s.count, G);
     else if (elem_bytes == 4)
@@ -329,17 +363,18 @@ __global__ void gen_solve_kernel(const T* __restrict__ A, const T* __restrict__ 
     }
 }
 
-static inline int flat_grid(size_t n, int threads) {
-    size_t blocks = (n + threads - 1) / threads;
-    size_t cap = (size_t)sm_count() * 16;
-    return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
+// one thread per work unit, grid-stride beyond the resident capacity
+template <class... KArgs, class... Args>
+static inline void launch_flat(void (*kern)(KArgs...), size_t n, int threads, cudaStream_t st, Args... args) {
+    const int grid = resident_grid((const void*)kern, threads, (n + threads - 1) / threads);
+    kern<<<grid, threads, 0, st>>>(args...);
 }
 
 int generic_det(const Shard& s, int dtype, int n, const void* A, void* O) {
     if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
-    if (dtype == T5D_F64) gen_det_kernel<double><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const double*)A, (double*)O, n, s.count);
-    else if (dtype == T5D_F32) gen_det_kernel<float><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const float*)A, (float*)O, n, s.count);
+    if (dtype == T5D_F64) launch_flat(gen_det_kernel<double>, s.count, 128, s.stream, (const double*)A, (double*)O, n, s.count);
+    else if (dtype == T5D_F32) launch_flat(gen_det_kernel<float>, s.count, 128, s.stream, (const float*)A, (float*)O, n, s.count);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -348,9 +383,9 @@ int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs,
     if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN || nrhs < 1 || nrhs > GEN_MAXN) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
     if (dtype == T5D_F64)
-        gen_solve_kernel<double><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const double*)A, (const double*)B, (double*)X, (unsigned char*)status, n, nrhs, identity_rhs, s.count);
+        launch_flat(gen_solve_kernel<double>, s.count, 128, s.stream, (const double*)A, (const double*)B, (double*)X, (unsigned char*)status, n, nrhs, identity_rhs, s.count);
     else if (dtype == T5D_F32)
-        gen_solve_kernel<float><<<flat_grid(s.count, 128), 128, 0, s.stream>>>((const float*)A, (const float*)B, (float*)X, (unsigned char*)status, n, nrhs, identity_rhs, s.count);
+        launch_flat(gen_solve_kernel<float>, s.count, 128, s.stream, (const float*)A, (const float*)B, (float*)X, (unsigned char*)status, n, nrhs, identity_rhs, s.count);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -489,11 +524,10 @@ __global__ void gen_min_poly_kernel(const T* __restrict__ A, T* __restrict__ out
 int generic_trace(const Shard& s, int dtype, int n, const void* A, void* O) {
     if (s.layout != T5L_AOS || n < 1 || n > (1 << 14)) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
-    const int g = flat_grid(s.count, 256);
     switch (dtype) {
-        case T5D_F64: gen_trace_kernel<double><<<g, 256, 0, s.stream>>>((const double*)A, (double*)O, n, s.count); break;
-        case T5D_F32: gen_trace_kernel<float><<<g, 256, 0, s.stream>>>((const float*)A, (float*)O, n, s.count); break;
-        case T5D_I64: gen_trace_kernel<long long><<<g, 256, 0, s.stream>>>((const long long*)A, (long long*)O, n, s.count); break;
+        case T5D_F64: launch_flat(gen_trace_kernel<double>, s.count, 256, s.stream, (const double*)A, (double*)O, n, s.count); break;
+        case T5D_F32: launch_flat(gen_trace_kernel<float>, s.count, 256, s.stream, (const float*)A, (float*)O, n, s.count); break;
+        case T5D_I64: launch_flat(gen_trace_kernel<long long>, s.count, 256, s.stream, (const long long*)A, (long long*)O, n, s.count); break;
         default: return T5I_UNSUPPORTED;
     }
     return ok();
@@ -502,11 +536,10 @@ int generic_trace(const Shard& s, int dtype, int n, const void* A, void* O) {
 int generic_poly_eval(const Shard& s, int dtype, int n, const void* coef, int ncoef, const void* A, void* O) {
     if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN || ncoef < 0) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
-    const int g = flat_grid(s.count, 128);
     switch (dtype) {
-        case T5D_F64: gen_poly_eval_kernel<double><<<g, 128, 0, s.stream>>>((const double*)A, (const double*)coef, ncoef, (double*)O, n, s.count); break;
-        case T5D_F32: gen_poly_eval_kernel<float><<<g, 128, 0, s.stream>>>((const float*)A, (const float*)coef, ncoef, (float*)O, n, s.count); break;
-        case T5D_I64: gen_poly_eval_kernel<long long><<<g, 128, 0, s.stream>>>((const long long*)A, (const long long*)coef, ncoef, (long long*)O, n, s.count); break;
+        case T5D_F64: launch_flat(gen_poly_eval_kernel<double>, s.count, 128, s.stream, (const double*)A, (const double*)coef, ncoef, (double*)O, n, s.count); break;
+        case T5D_F32: launch_flat(gen_poly_eval_kernel<float>, s.count, 128, s.stream, (const float*)A, (const float*)coef, ncoef, (float*)O, n, s.count); break;
+        case T5D_I64: launch_flat(gen_poly_eval_kernel<long long>, s.count, 128, s.stream, (const long long*)A, (const long long*)coef, ncoef, (long long*)O, n, s.count); break;
         default: return T5I_UNSUPPORTED;
     }
     return ok();
@@ -515,9 +548,8 @@ int generic_poly_eval(const Shard& s, int dtype, int n, const void* coef, int nc
 int generic_char_poly(const Shard& s, int dtype, int n, const void* A, void* O) {
     if (s.layout != T5L_AOS || n < 1 || n > GEN_MAXN) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
-    const int g = flat_grid(s.count, 128);
-    if (dtype == T5D_F64) gen_char_poly_kernel<double><<<g, 128, 0, s.stream>>>((const double*)A, (double*)O, n, s.count);
-    else if (dtype == T5D_F32) gen_char_poly_kernel<float><<<g, 128, 0, s.stream>>>((const float*)A, (float*)O, n, s.count);
+    if (dtype == T5D_F64) launch_flat(gen_char_poly_kernel<double>, s.count, 128, s.stream, (const double*)A, (double*)O, n, s.count);
+    else if (dtype == T5D_F32) launch_flat(gen_char_poly_kernel<float>, s.count, 128, s.stream, (const float*)A, (float*)O, n, s.count);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -525,9 +557,8 @@ int generic_char_poly(const Shard& s, int dtype, int n, const void* A, void* O) 
 int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree) {
     if (s.layout != T5L_AOS || n < 1 || n > MINPOLY_MAXN) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
-    const int g = flat_grid(s.count, 64);
-    if (dtype == T5D_F64) gen_min_poly_kernel<double><<<g, 64, 0, s.stream>>>((const double*)A, (double*)O, (unsigned char*)degree, n, s.count);
-    else if (dtype == T5D_F32) gen_min_poly_kernel<float><<<g, 64, 0, s.stream>>>((const float*)A, (float*)O, (unsigned char*)degree, n, s.count);
+    if (dtype == T5D_F64) launch_flat(gen_min_poly_kernel<double>, s.count, 64, s.stream, (const double*)A, (double*)O, (unsigned char*)degree, n, s.count);
+    else if (dtype == T5D_F32) launch_flat(gen_min_poly_kernel<float>, s.count, 64, s.stream, (const float*)A, (float*)O, (unsigned char*)degree, n, s.count);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -555,10 +586,9 @@ __global__ void scale_kernel(const T* __restrict__ a, T* __restrict__ c, T k, un
 
 template <class T>
 static int zip_t(const Shard& s, int op, size_t n, const void* A, const void* B, void* C) {
-    int g = flat_grid(n, 256);
-    if (op == 0) zip_kernel<T, 0><<<g, 256, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, n);
-    else if (op == 1) zip_kernel<T, 1><<<g, 256, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, n);
-    else if (op == 2) zip_kernel<T, 2><<<g, 256, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, n);
+    if (op == 0) launch_flat(zip_kernel<T, 0>, n, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
+    else if (op == 1) launch_flat(zip_kernel<T, 1>, n, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
+    else if (op == 2) launch_flat(zip_kernel<T, 2>, n, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -576,11 +606,10 @@ int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, 
 
 int generic_scale(const Shard& s, int dtype, const void* k, size_t elems, const void* A, void* C) {
     if (elems == 0) return T5I_OK;
-    int g = flat_grid(elems, 256);
     switch (dtype) {
-        case T5D_F64: scale_kernel<double><<<g, 256, 0, s.stream>>>((const double*)A, (double*)C, *(const double*)k, elems); break;
-        case T5D_F32: scale_kernel<float><<<g, 256, 0, s.stream>>>((const float*)A, (float*)C, *(const float*)k, elems); break;
-        case T5D_I64: scale_kernel<long long><<<g, 256, 0, s.stream>>>((const long long*)A, (long long*)C, *(const long long*)k, elems); break;
+        case T5D_F64: launch_flat(scale_kernel<double>, elems, 256, s.stream, (const double*)A, (double*)C, *(const double*)k, elems); break;
+        case T5D_F32: launch_flat(scale_kernel<float>, elems, 256, s.stream, (const float*)A, (float*)C, *(const float*)k, elems); break;
+        case T5D_I64: launch_flat(scale_kernel<long long>, elems, 256, s.stream, (const long long*)A, (long long*)C, *(const long long*)k, elems); break;
         default: return T5I_UNSUPPORTED;
     }
     return ok();
@@ -680,12 +709,11 @@ __global__ void fill_kernel(T* dst, uint64_t base, unsigned long long first_item
 int fill_synthetic(const Shard& s, int dtype, size_t d, uint64_t seed, uint64_t op_id, void* dst) {
     if (s.count == 0) return T5I_OK;
     const uint64_t base = seed ^ (op_id << 56);
-    int g = flat_grid(s.count * d, 256);
     const int soa = s.layout == T5L_SOA;
     switch (dtype) {
-        case T5D_F64: fill_kernel<double><<<g, 256, 0, s.stream>>>((double*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
-        case T5D_F32: fill_kernel<float><<<g, 256, 0, s.stream>>>((float*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
-        case T5D_I64: fill_kernel<long long><<<g, 256, 0, s.stream>>>((long long*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
+        case T5D_F64: launch_flat(fill_kernel<double>, s.count * d, 256, s.stream, (double*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
+        case T5D_F32: launch_flat(fill_kernel<float>, s.count * d, 256, s.stream, (float*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
+        case T5D_I64: launch_flat(fill_kernel<long long>, s.count * d, 256, s.stream, (long long*)dst, base, s.first, s.count, d, soa, s.soa_stride); break;
         default: return T5I_UNSUPPORTED;
     }
     return ok();
@@ -707,10 +735,9 @@ __global__ void plant_kernel(T* A, int n, unsigned long long first_item, unsigne
 
 int plant_specials(const Shard& s, int dtype, int n, uint64_t swap_every, uint64_t sing_every, void* A) {
     if (s.count == 0) return T5I_OK;
-    int g = flat_grid(s.count, 256);
     const int soa = s.layout == T5L_SOA;
-    if (dtype == T5D_F64) plant_kernel<double><<<g, 256, 0, s.stream>>>((double*)A, n, s.first, s.count, swap_every, sing_every, soa, s.soa_stride);
-    else if (dtype == T5D_F32) plant_kernel<float><<<g, 256, 0, s.stream>>>((float*)A, n, s.first, s.count, swap_every, sing_every, soa, s.soa_stride);
+    if (dtype == T5D_F64) launch_flat(plant_kernel<double>, s.count, 256, s.stream, (double*)A, n, s.first, s.count, swap_every, sing_every, soa, s.soa_stride);
+    else if (dtype == T5D_F32) launch_flat(plant_kernel<float>, s.count, 256, s.stream, (float*)A, n, s.first, s.count, swap_every, sing_every, soa, s.soa_stride);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -749,9 +776,10 @@ relayout_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long lo
 
 int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
     if (count == 0 || d == 0) return T5I_OK;
-    size_t tiles = ((count + 31) / 32) * ((d + 31) / 32);
-    size_t cap = (size_t)sm_count() * 8;
-    int grid = (int)(tiles < cap ? tiles : cap);
+    const size_t tiles = ((count + 31) / 32) * ((d + 31) / 32);
+    const void* kern = elem_bytes == 8 ? (const void*)relayout_kernel<unsigned long long>
+                     : elem_bytes == 4 ? (const void*)relayout_kernel<unsigned> : (const void*)relayout_kernel<unsigned char>;
+    const int grid = resident_grid(kern, 256, tiles);
     if (elem_bytes == 8) relayout_kernel<unsigned long long><<<grid, 256, 0, st>>>((const unsigned long long*)src, (unsigned long long*)dst, count, (unsigned)d, soa_stride, to_soa);
     else if (elem_bytes == 4) relayout_kernel<unsigned><<<grid, 256, 0, st>>>((const unsigned*)src, (unsigned*)dst, count, (unsigned)d, soa_stride, to_soa);
     else if (elem_bytes == 1) relayout_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)src, (unsigned char*)dst, count, (unsigned)d, soa_stride, to_soa);

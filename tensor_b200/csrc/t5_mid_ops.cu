@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
         cp_async_commit();
     };
 
+    pdl_trigger();
+    pdl_wait();
     unsigned long long next_claim = 0;
     TileClaimer claimer;
     if (tid == 0) {
@@ -160,14 +162,15 @@ static int launch(const Shard& s, const void* A, const void* B, void* Cc) {
     size_t claim = tiles / ((size_t)grid * 16);
     claim = claim < 1 ? 1 : (claim > 8 ? 8 : claim);
     Args a{A, B, Cc, (unsigned long long)s.count, s.sched, (unsigned)claim};
-    kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
-    return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
+    if (pdl_launch(kern, grid, THREADS, C::SMEM, s.stream, a) != cudaSuccess) { cudaGetLastError(); return T5I_CUDA; }
+    return T5I_OK;
 }
 
 template <class T>
 static int dispatch(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
-    if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 256, 3>(s, A, B, C);
-    if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 256, 2>(s, A, B, C);
+    // geometry from tools/tune_mid.cu (profiles/r01_tune_mid.csv): small CTAs, many per SM
+    if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 64, 4>(s, A, B, C);
+    if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 128, 2>(s, A, B, C);
     if constexpr (sizeof(T) == 8) {
         if (m == 6 && k == 6 && n == 6) return launch<T, 6, 6, 6, 192, 3>(s, A, B, C);
     }

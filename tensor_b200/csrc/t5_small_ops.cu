@@ -40,8 +40,8 @@ static int launch_tile(const Shard& s, const void* in0, const void* in1, void* o
     size_t claim = tiles / ((size_t)grid * 16);
     claim = claim < 1 ? 1 : (claim > 8 ? 8 : claim);
     TileArgs a{in0, in1, out0, out1, (unsigned long long)s.count, s.sched, (unsigned)claim, prm};
-    kern<<<grid, THREADS, C::SMEM, s.stream>>>(a);
-    return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
+    if (pdl_launch(kern, grid, THREADS, C::SMEM, s.stream, a) != cudaSuccess) { cudaGetLastError(); return T5I_CUDA; }
+    return T5I_OK;
 }
 
 template <class Op>

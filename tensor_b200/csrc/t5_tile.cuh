@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
         cp_async_commit();  // always commit: keeps the group count uniform
     };
 
+    pdl_trigger();
+    pdl_wait();   // nothing of the previous launch (operands it produced, scheduler words) is touched before this
     // prologue: claim and start the first STAGES-1 tiles; keep one more claim in flight
     unsigned long long next_claim = 0;
     TileClaimer claimer;
