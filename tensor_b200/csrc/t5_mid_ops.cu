@@ -169,7 +169,9 @@ static int launch(const Shard& s, const void* A, const void* B, void* Cc) {
 template <class T>
 static int dispatch(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
     // geometry from tools/tune_mid.cu (profiles/r01_tune_mid.csv): small CTAs, many per SM
-    if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 64, 4>(s, A, B, C);
+    // 8x8: 256 threads x 2 stages = 3 CTAs (768 threads) per SM.  64 x 4 is as fast in isolation but, with
+    // only 8 warps per SM on the FP64 chains, lost 25% inside a long bench run (clock-sensitive).
+    if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 256, 2>(s, A, B, C);
     if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 128, 2>(s, A, B, C);
     if constexpr (sizeof(T) == 8) {
         if (m == 6 && k == 6 && n == 6) return launch<T, 6, 6, 6, 192, 3>(s, A, B, C);

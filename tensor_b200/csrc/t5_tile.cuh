@@ -294,38 +294,129 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
     }
 }
 
-// ---- SoA skeleton: element e of item b at base[e * stride + b]; perfectly
-// coalesced thread-per-item access, no staging needed. -----------------------------
+// ---- SoA skeleton: element e of item b at base[e * stride + b] ----------------------------
+// Thread-per-item access is already coalesced in this layout (a warp reads 128/256 contiguous
+// bytes per element), but a thread that loads its 9..32 elements, runs a division chain and
+// stores leaves HBM idle while it computes.  So SoA batches go through the same machinery as AoS:
+// a STAGES-deep cp.async ring fills shared [element][item-in-tile] rows (one contiguous
+// TILE*sizeof(T) segment per element: conflict-free for stride-1 LDS with no swizzle at all), the
+// dynamic tile scheduler hands out tiles, and results go straight from registers to their rows.
 struct SoaArgs {
     const void* in0;
     const void* in1;
     void* out0;
     void* out1;
     unsigned long long n_items;
-    unsigned long long stride;  // shard capacity in items
+    unsigned long long stride;  // shard capacity in items (multiple of 32)
+    unsigned long long* sched;  // tile scheduler words, as TileArgs
+    unsigned claim;
     OpParams prm;
 };
 
-template <class Op, int THREADS>
-__global__ void __launch_bounds__(THREADS) soa_kernel(SoaArgs a) {
+template <class R, int TILE, int THREADS>
+__device__ __forceinline__ void soa_rows_load_async(unsigned char* sdst, const unsigned char* grow0, unsigned long long stride,
+                                                    int n_valid, int tid) {
+    if constexpr (R::n > 0 && R::bytes > 0) {
+        using T = typename R::type;
+        constexpr int ROWB = TILE * (int)sizeof(T), CPR = ROWB / 16, NCH = R::n * CPR, IPC = 16 / (int)sizeof(T);
+        #pragma unroll
+        for (int i = 0; i < (NCH + THREADS - 1) / THREADS; ++i) {
+            const int ch = tid + i * THREADS;
+            if ((NCH % THREADS == 0) || ch < NCH) {
+                const int e = ch / CPR, c = ch - e * CPR;
+                // rows are padded to 32 items, so a chunk that starts on a valid item is readable in full
+                if (c * IPC < n_valid) cp_async16(sdst + e * ROWB + c * 16, grow0 + ((size_t)e * stride) * sizeof(T) + (size_t)c * 16);
+            }
+        }
+    }
+}
+
+template <class Op, int THREADS, int IPT, int STAGES, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) soa_tile_kernel(SoaArgs a) {
     using I0 = typename Op::In0; using I1 = typename Op::In1;
     using O0 = typename Op::Out0; using O1 = typename Op::Out1;
-    const typename I0::type* in0 = (const typename I0::type*)a.in0;
-    const typename I1::type* in1 = (const typename I1::type*)a.in1;
+    using T0 = typename I0::type; using T1 = typename I1::type;
+    constexpr int TILE = THREADS * IPT;
+    constexpr int IN_STAGE = TILE * (I0::bytes + I1::bytes);
+    static_assert(STAGES >= 2, "need a ring");
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long tile_q[STAGES];
+
+    const int tid = threadIdx.x;
+    const unsigned long long n_tiles = (a.n_items + TILE - 1) / TILE;
+    const unsigned char* g_in0 = (const unsigned char*)a.in0;
+    const unsigned char* g_in1 = (const unsigned char*)a.in1;
     typename O0::type* out0 = (typename O0::type*)a.out0;
     typename O1::type* out1 = (typename O1::type*)a.out1;
-    for (unsigned long long b = (unsigned long long)blockIdx.x * THREADS + threadIdx.x; b < a.n_items;
-         b += (unsigned long long)gridDim.x * THREADS) {
-        RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
+
+    auto issue = [&](unsigned long long tile, int stage) {
+        if (tile < n_tiles) {
+            const unsigned long long first = tile * TILE;
+            const unsigned long long left = a.n_items - first;
+            const int nv = left < (unsigned long long)TILE ? (int)left : TILE;
+            unsigned char* s0 = smem + stage * IN_STAGE;
+            soa_rows_load_async<I0, TILE, THREADS>(s0, g_in0 + first * sizeof(T0), a.stride, nv, tid);
+            soa_rows_load_async<I1, TILE, THREADS>(s0 + TILE * I0::bytes, g_in1 + first * sizeof(T1), a.stride, nv, tid);
+        }
+        cp_async_commit();
+    };
+
+    pdl_trigger();
+    pdl_wait();
+    unsigned long long next_claim = 0;
+    TileClaimer claimer;
+    if (tid == 0) {
         #pragma unroll
-        for (int e = 0; e < I0::n; ++e) r0.v[e] = __ldg(in0 + (size_t)e * a.stride + b);
+        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = claimer.next(a.sched, a.claim);
+        next_claim = claimer.next(a.sched, a.claim);
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(tile_q[s], s);
+
+    int stage = 0;
+    while (true) {
+        const unsigned long long tile = tile_q[stage];
+        if (tile >= n_tiles) break;
+        int pf = stage + STAGES - 1; if (pf >= STAGES) pf -= STAGES;
+        if (tid == 0) tile_q[pf] = next_claim;
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(tile_q[pf], pf);
+        if (tid == 0) next_claim = claimer.next(a.sched, a.claim);
+
+        const unsigned long long first = tile * TILE;
+        const unsigned long long left = a.n_items - first;
+        const int nv = left < (unsigned long long)TILE ? (int)left : TILE;
+        const T0* s0 = reinterpret_cast<const T0*>(smem + stage * IN_STAGE);
+        const T1* s1 = reinterpret_cast<const T1*>(smem + stage * IN_STAGE + TILE * I0::bytes);
         #pragma unroll
-        for (int e = 0; e < I1::n; ++e) r1.v[e] = __ldg(in1 + (size_t)e * a.stride + b);
-        run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
-        #pragma unroll
-        for (int e = 0; e < O0::n; ++e) out0[(size_t)e * a.stride + b] = w0.v[e];
-        #pragma unroll
-        for (int e = 0; e < O1::n; ++e) out1[(size_t)e * a.stride + b] = w1.v[e];
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * THREADS;
+            if (it < nv) {
+                RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
+                #pragma unroll
+                for (int e = 0; e < I0::n; ++e) r0.v[e] = s0[e * TILE + it];
+                #pragma unroll
+                for (int e = 0; e < I1::n; ++e) r1.v[e] = s1[e * TILE + it];
+                run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
+                const unsigned long long b = first + it;
+                #pragma unroll
+                for (int e = 0; e < O0::n; ++e) out0[(size_t)e * a.stride + b] = w0.v[e];
+                #pragma unroll
+                for (int e = 0; e < O1::n; ++e) out1[(size_t)e * a.stride + b] = w1.v[e];
+            }
+        }
+        if (++stage == STAGES) stage = 0;
+    }
+    cp_async_wait<0>();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.sched + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 

@@ -39,24 +39,27 @@ void run(const char* name, size_t n, int alg_bytes, bool flush) {
     TileArgs a{g_in0, g_in1, g_out0, g_out1, n, g_sched, (unsigned)claim};
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) kern<<<grid, THREADS, C::SMEM>>>(a);
+    // `flush` now means: rotate over operand sets (> L2 in total) instead of re-reading one set; launches are
+    // back to back with the PDL attribute, exactly as the library issues them
+    constexpr size_t REC = C::I0::bytes > C::I1::bytes ? (C::I0::bytes > C::O0::bytes ? C::I0::bytes : C::O0::bytes)
+                                                        : (C::I1::bytes > C::O0::bytes ? C::I1::bytes : C::O0::bytes);
+    size_t fit = ((size_t)1 << 31) / (n * REC);
+    const int sets = flush ? (int)(fit < 1 ? 1 : (fit > 8 ? 8 : fit)) : 1;
+    auto launch = [&](int i) {
+        TileArgs b = a;
+        const size_t k = (size_t)(i % sets) * n;
+        b.in0 = (const char*)g_in0 + k * C::I0::bytes; b.in1 = (const char*)g_in1 + k * C::I1::bytes;
+        b.out0 = (char*)g_out0 + k * C::O0::bytes; b.out1 = (char*)g_out1 + k * C::O1::bytes;
+        CK(pdl_launch(kern, grid, THREADS, C::SMEM, 0, b));
+    };
+    for (int i = 0; i < 3; ++i) launch(i);
     CK(cudaDeviceSynchronize());
-    const int iters = flush ? 10 : 20;
+    const int iters = 40;
     float total = 0;
-    if (!flush) {
-        CK(cudaEventRecord(e0));
-        for (int i = 0; i < iters; ++i) kern<<<grid, THREADS, C::SMEM>>>(a);
-        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-        CK(cudaEventElapsedTime(&total, e0, e1));
-    } else {
-        for (int i = 0; i < iters; ++i) {
-            CK(cudaMemsetAsync(g_flush, i, FLUSH));
-            CK(cudaEventRecord(e0));
-            kern<<<grid, THREADS, C::SMEM>>>(a);
-            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-            float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); total += ms;
-        }
-    }
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) launch(i);
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&total, e0, e1));
     CK(cudaGetLastError());
     double us = total / iters * 1e3;
     printf("%s,%zu,%d,%d,%d,%d,%d,%d,%.2f,%.1f\n", name, n, THREADS, IPT, STAGES, MINB, occ, C::SMEM, us, alg_bytes * (double)n / us / 1e3);
@@ -89,7 +92,7 @@ void sweep_minb(const char* name, size_t n, int alg_bytes, bool flush) {
 int main(int argc, char** argv) {
     const size_t NMAX = 1ull << 24;
     const size_t BYTES = NMAX * 128;  // biggest stream: 16Mi x 128 B
-    CK(cudaMalloc(&g_in0, BYTES)); CK(cudaMalloc(&g_in1, BYTES)); CK(cudaMalloc(&g_out0, BYTES)); CK(cudaMalloc(&g_out1, NMAX));
+    CK(cudaMalloc(&g_in0, BYTES)); CK(cudaMalloc(&g_in1, BYTES)); CK(cudaMalloc(&g_out0, BYTES)); CK(cudaMalloc(&g_out1, NMAX * 8));
     CK(cudaMalloc(&g_flush, FLUSH)); CK(cudaMalloc(&g_sched, 16)); CK(cudaMemset(g_sched, 0, 16));
     const char* which = argc > 1 ? argv[1] : "all";
     auto want = [&](const char* s) { return !strcmp(which, "all") || strstr(s, which); };
