@@ -81,8 +81,49 @@ foreign import ccall safe "t5_zip"
   c_zip :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
 foreign import ccall safe "t5_scale"
   c_scale :: Ptr Ctx -> CInt -> Ptr () -> Ptr Buf -> Ptr Buf -> IO CInt
+
+-- the rest of the old SquareMatrix class (CHANGELOG.md:28-29; SURVEY.md §8f-4)
+foreign import ccall safe "t5_trace"
+  c_trace :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_poly_eval"
+  c_poly_eval :: Ptr Ctx -> CInt -> CInt -> Ptr () -> CInt -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_char_poly"
+  c_char_poly :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_min_poly"
+  c_min_poly :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
+
+-- structural operations (src/Data/Tensor/Vector.hs:260-354, :400-463) as device gathers
+foreign import ccall safe "t5_append"
+  c_append :: Ptr Ctx -> CInt -> CInt -> CInt -> Ptr Word64 -> Ptr Word64 -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_split"
+  c_split :: Ptr Ctx -> CInt -> CInt -> CInt -> Ptr Word64 -> Word64 -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_at"
+  c_at :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> Ptr Word64 -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_ta"
+  c_ta :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> Word64 -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_slice"
+  c_slice :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> Ptr Word64 -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_permute_axes"
+  c_permute_axes :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> Ptr CInt -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_structural_table"
+  c_structural_table :: CInt -> CInt -> Ptr Word64 -> Ptr Word64 -> CInt -> Ptr Word32 -> CSize -> Ptr CSize -> IO CInt
+
+-- host-buffer (end-to-end) entries: operands and results are ordinary (ideally pinned) host arrays
 foreign import ccall safe "t5_matmul_host"
   c_matmul_host :: Ptr Ctx -> CInt -> CInt -> CInt -> CInt -> CSize -> Ptr () -> Ptr () -> Ptr () -> IO CInt
+foreign import ccall safe "t5_dot_host"
+  c_dot_host :: Ptr Ctx -> CInt -> CInt -> CSize -> Ptr () -> Ptr () -> Ptr () -> IO CInt
+foreign import ccall safe "t5_prod_host"
+  c_prod_host :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> CInt -> Ptr Word64 -> CInt -> CSize
+              -> Ptr () -> Ptr () -> Ptr () -> IO CInt
+foreign import ccall safe "t5_transpose_host"
+  c_transpose_host :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> CSize -> Ptr () -> Ptr () -> IO CInt
+foreign import ccall safe "t5_det_host"
+  c_det_host :: Ptr Ctx -> CInt -> CInt -> CSize -> Ptr () -> Ptr () -> IO CInt
+foreign import ccall safe "t5_inverse_host"
+  c_inverse_host :: Ptr Ctx -> CInt -> CInt -> CSize -> Ptr () -> Ptr () -> Ptr Word8 -> IO CInt
+foreign import ccall safe "t5_solve_host"
+  c_solve_host :: Ptr Ctx -> CInt -> CInt -> CInt -> CSize -> Ptr () -> Ptr () -> Ptr () -> Ptr Word8 -> IO CInt
 
 foreign import ccall safe "t5_timer_begin" c_timer_begin :: Ptr Ctx -> IO CInt
 foreign import ccall safe "t5_timer_end"   c_timer_end   :: Ptr Ctx -> Ptr CFloat -> IO CInt

@@ -27,7 +27,8 @@
 module Data.Tensor.LinearAlgebra
     ( MatrixProduct(..), DotProduct(..), TensorProduct(..), Transpose(..)
     , SquareMatrix(..), LinearSystem(..)
-    , dotSum
+    , dotSum, prodN, tr, polyEval, charPoly, minPoly
+    , addB, subB, hadamardB, scaleB
     ) where
 
 import           Data.Proxy
@@ -35,7 +36,9 @@ import           Data.Singletons
 import           Data.Word
 import           Foreign.C.Types       (CInt)
 import           Foreign.Marshal.Alloc (alloca)
+import           Foreign.Marshal.Utils (with)
 import           Foreign.Marshal.Array (withArrayLen)
+import qualified Data.Vector.Storable  as S
 import           Foreign.Ptr
 import           Foreign.Storable
 
@@ -171,3 +174,80 @@ instance (SingI i, DeviceElt e, Fractional e) =>
         unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch x $ \px -> unsafeWithBatch st $ \ps ->
             c_solve h (code (Proxy :: Proxy e)) (fromIntegral n) 1 pa pb px ps >>= checkRC (batchCtx a) "t5_solve"
         return (x, st)
+
+-- | @prodN n a b@ (@prod n@): contract the last @n@ indices of @a@ with the first @n@ of @b@.
+prodN :: forall is js ks e. (SingI is, SingI js, SingI ks, DeviceElt e)
+      => Int -> Batch is e -> Batch js e -> IO (Batch ks e)
+prodN n a b = do
+    let Context h = batchCtx a
+    c <- newBatch (batchCtx a) (batchCount a)
+    withArrayLen (dims (batchShape a)) $ \ra pda -> withArrayLen (dims (batchShape b)) $ \rb pdb ->
+      unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
+        c_prod h (code (Proxy :: Proxy e)) (fromIntegral ra) pda (fromIntegral rb) pdb (fromIntegral n) pa pb pc
+            >>= checkRC (batchCtx a) "t5_prod"
+    return c
+
+-- The rest of the old SquareMatrix class (CHANGELOG.md:28-29; SURVEY.md §8f-4) ------------
+
+-- | Trace: @fold_{i ascending} (acc + a_ii)@ from 0.
+tr :: forall i e. (SingI i, DeviceElt e) => Batch '[i, i] e -> IO (Batch '[] e)
+tr a = do
+    let [n, _] = batchShape a; Context h = batchCtx a
+    o <- newBatch (batchCtx a) (batchCount a)
+    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po ->
+        c_trace h (code (Proxy :: Proxy e)) (fromIntegral n) pa po >>= checkRC (batchCtx a) "t5_trace"
+    return o
+
+-- | @polyEval cs a = c0 I + c1 a + .. + cd a^d@ (Horner), coefficients low order first.
+polyEval :: forall i e. (SingI i, DeviceElt e) => [e] -> Batch '[i, i] e -> IO (Batch '[i, i] e)
+polyEval cs a = do
+    let [n, _] = batchShape a; Context h = batchCtx a
+    o <- newBatch (batchCtx a) (batchCount a)
+    S.unsafeWith (S.fromList cs) $ \pc -> unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po ->
+        c_poly_eval h (code (Proxy :: Proxy e)) (fromIntegral n) (castPtr pc) (fromIntegral (length cs)) pa po
+            >>= checkRC (batchCtx a) "t5_poly_eval"
+    return o
+
+-- | Coefficients of @det (xI - a)@, low order first (@n + 1@ per item; the result shape
+-- @'[j]@ must be @i + 1@).
+charPoly :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e) => Batch '[i, i] e -> IO (Batch '[j] e)
+charPoly a = do
+    let [n, _] = batchShape a; Context h = batchCtx a
+    o <- newBatch (batchCtx a) (batchCount a)
+    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po ->
+        c_char_poly h (code (Proxy :: Proxy e)) (fromIntegral n) pa po >>= checkRC (batchCtx a) "t5_char_poly"
+    return o
+
+-- | Minimal polynomial (zero-padded above its degree) and the degree per item.
+minPoly :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e)
+        => Batch '[i, i] e -> IO (Batch '[j] e, Batch '[] Word8)
+minPoly a = do
+    let [n, _] = batchShape a; Context h = batchCtx a
+    o <- newBatch (batchCtx a) (batchCount a)
+    d <- newStatusBatch (batchCtx a) (batchCount a)
+    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po -> unsafeWithBatch d $ \pd ->
+        c_min_poly h (code (Proxy :: Proxy e)) (fromIntegral n) pa po pd >>= checkRC (batchCtx a) "t5_min_poly"
+    return (o, d)
+
+-- Vector-space operations: what @liftA2 (+)@, @liftA2 (-)@, @liftA2 (*)@ and @fmap (k *)@ of the
+-- Functor / Applicative instances (src/Data/Tensor/Vector.hs:180-190, :250-251) are on batches.
+zipB :: forall is e. (SingI is, DeviceElt e) => CInt -> Batch is e -> Batch is e -> IO (Batch is e)
+zipB op a b = do
+    let Context h = batchCtx a
+    c <- newBatch (batchCtx a) (batchCount a)
+    unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
+        c_zip h (code (Proxy :: Proxy e)) op pa pb pc >>= checkRC (batchCtx a) "t5_zip"
+    return c
+
+addB, subB, hadamardB :: (SingI is, DeviceElt e) => Batch is e -> Batch is e -> IO (Batch is e)
+addB = zipB 0
+subB = zipB 1
+hadamardB = zipB 2
+
+scaleB :: forall is e. (SingI is, DeviceElt e) => e -> Batch is e -> IO (Batch is e)
+scaleB k a = do
+    let Context h = batchCtx a
+    c <- newBatch (batchCtx a) (batchCount a)
+    with k $ \pk -> unsafeWithBatch a $ \pa -> unsafeWithBatch c $ \pc ->
+        c_scale h (code (Proxy :: Proxy e)) (castPtr pk) pa pc >>= checkRC (batchCtx a) "t5_scale"
+    return c

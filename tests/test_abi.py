@@ -86,3 +86,28 @@ def test_product_package_never_imports_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     s = f.read()
                 assert "import oracle" not in s and "from oracle" not in s and "t5oracle" not in s, fn
+
+
+def test_haskell_ffi_module_binds_every_declared_symbol():
+    """The reference-side binding (tensor_b200/hs, uncompilable here: no GHC) must at least name every
+    entry point of the header, so that the boundary a maintainer would add is complete."""
+    with open(os.path.join(ROOT, "tensor_b200", "hs", "Data", "Tensor", "Device", "FFI.hs")) as f:
+        hs = f.read()
+    bound = set(re.findall(r'foreign import ccall safe "&?(t5_[a-z0-9_]+)"', hs))
+    missing = [n for n in declared_symbols() if n not in bound]
+    assert not missing, f"FFI.hs has no foreign import for {missing}"
+    # and every C entry is used by some Haskell module above the raw bindings or is a measurement helper
+    used = ""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tensor_b200", "hs")):
+        for fn in files:
+            if fn.endswith(".hs") and fn != "FFI.hs":
+                with open(os.path.join(dirpath, fn)) as f:
+                    used += f.read()
+    helpers = {"t5_timer_begin", "t5_timer_end", "t5_flush_l2", "t5_fill_synthetic", "t5_plant_specials",
+               "t5_launch_count", "t5_version", "t5_strerror", "t5_sync", "t5_free", "t5_partition", "t5_relayout",
+               "t5_pinned_alloc", "t5_pinned_free", "t5_buf_batch", "t5_buf_elems", "t5_buf_dtype", "t5_buf_layout",
+               "t5_dot_sum_used_nccl", "t5_structural_table"}
+    for n in declared_symbols():
+        if n in helpers:
+            continue
+        assert "c_" + n[3:] in used, f"no Haskell caller for {n}"
