@@ -63,6 +63,12 @@ WORKLOADS = {
                                   desc="1Mi rank-3 8x8x8 Double transposes (any-rank gather)"),
     "matmul128_f64_64K": dict(op="matmul", dtype="f64", m=128, k=128, n=128, batch=1 << 16, bytes=393216, flops=4194304, bound="tensor",
                               desc="64Ki 128x128 Double .*. on FP64 tensor cores (configs[4])"),
+    "dotsum4_f32_16M": dict(op="dot_sum", dtype="f32", n=4, batch=1 << 24, bytes=32, bound="hbm",
+                            desc="sum over 16Mi pairs of 4-vector Float dot products (the one reduction; returns a host scalar per call)"),
+    "dotsum4_f32_soa_16M": dict(op="dot_sum", dtype="f32", n=4, batch=1 << 24, bytes=32, bound="hbm", layout="soa",
+                                desc="the same reduction on SoA device buffers"),
+    "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="fp32",
+                              desc="64Ki 128x128 Float .*. (exact blocked SIMT product: no TF32, unfused multiply+add)"),
     "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
                               desc="256Ki 64x64 Double .*. on FP64 tensor cores (smallest DMMA shape; 5.3 flop/B, HBM floor ~= tensor floor)"),
 }
@@ -70,7 +76,7 @@ HEADLINE = "matmul4x4_f32_16M"
 EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpose4x4_f32_16M", "matvec4_f32_16M",
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
-          "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M"]
+          "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 
@@ -191,6 +197,12 @@ class Step:
             self.a, self.b = syn((n,), SEED_A, 2), syn((n,), SEED_B, 2)
             self.c = empty(())
             self.run = lambda: L.t5_dot(h, code, n, self.a._h, self.b._h, self.c._h)
+        elif op == "dot_sum":
+            n = w["n"]
+            self.a, self.b = syn((n,), SEED_A, 2), syn((n,), SEED_B, 2)
+            self.out = np.zeros((1,), dtype=dt)
+            po = self.out.ctypes.data_as(ctypes.c_void_p)
+            self.run = lambda: L.t5_dot_sum(h, code, n, self.a._h, self.b._h, po)   # returns the scalar: synchronises
         elif op == "transpose":
             dims = w["dims"]
             self.a = syn(dims, SEED_A, 3)
@@ -278,6 +290,12 @@ def roofline(w, ms_per_launch, peaks):
         return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "peak_source": peaks["source"]}
     ach = w["flops"] * w["batch"] / (ms_per_launch * 1e-3) / 1e12
+    if w["bound"] == "fp32":
+        # exact (unfused) Float product: one FMUL + one FADD per multiply-add, so the ceiling is the FP32
+        # ISSUE rate, 128 lanes x SMs x max clock instructions/s = that many flop/s (half the FMA peak)
+        peak = 128 * 148 * 1.965e9 / 1e12
+        return {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": "nominal: 128 FP32 lanes x 148 SMs x 1965 MHz, unfused mul+add (no FMA, no TF32)"}
     peak = peaks.get("fp64_tflops") or 37.0
     src = "measured cuBLAS DGEMM 8192^3 (profiles/r01_fp64_peak.json)" if peaks.get("fp64_tflops") else "nominal FP64 37 TFLOP/s (no measured DGEMM peak yet)"
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src}
@@ -443,7 +461,7 @@ def reference_arm(args):
                        "(no ghc), so the C++ restatement (oracle port, unboxed: faster than boxed Data.Vector) is timed"},
             "cpu_baseline": {"value": value, "unit": "matrices/s", "cores": cw.threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "matrices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -506,7 +524,7 @@ def ours(args):
     # ---- the other BASELINE configs (explanatory; not the headline) ----------------------------------
     others = {}
     if args.all and world == 1:
-        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K"] if args.big else []):
+        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K", "matmul128_f32_64K"] if args.big else []):
             ww = WORKLOADS[name]
             try:
                 st = StepRing(ctx, tb, ww)
@@ -555,7 +573,7 @@ def ours(args):
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if others:
             line["workloads"] = others
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         import torch.distributed as dist
@@ -577,9 +595,27 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that print banners on fd 1 (NCCL's
+    # "NCCL version ..." under torchrun) are sent to stderr for the duration of the run
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 if __name__ == "__main__":

@@ -630,13 +630,35 @@ constexpr int DS_THREADS = 256;
 constexpr int DS_MAX_BLOCKS = 148 * 8;
 
 template <class T, class Acc>
+__device__ __forceinline__ void dot_accumulate(Acc& acc, const uint4& a, const uint4& b) {
+    using R = Arith<T>;
+    constexpr int V = 16 / (int)sizeof(T);
+    #pragma unroll
+    for (int j = 0; j < V; ++j) acc += (Acc)R::mul(reinterpret_cast<const T*>(&a)[j], reinterpret_cast<const T*>(&b)[j]);
+}
+
+// 16-byte streaming loads, two vectors of each operand in flight per thread (the shard buffers
+// are 256-B aligned); the assignment of elements to threads is fixed, so the result is reproducible.
+template <class T, class Acc>
 __global__ void __launch_bounds__(DS_THREADS)
 dot_sum_stage1(const T* __restrict__ x, const T* __restrict__ y, Acc* __restrict__ partials, unsigned long long n) {
     using R = Arith<T>;
+    constexpr int V = 16 / (int)sizeof(T);
+    const unsigned long long nv = n / V;
+    const unsigned long long stride = (unsigned long long)gridDim.x * DS_THREADS;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* yv = reinterpret_cast<const uint4*>(y);
     Acc acc = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * DS_THREADS + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * DS_THREADS)
-        acc += (Acc)R::mul(x[i], y[i]);
+    unsigned long long i = (unsigned long long)blockIdx.x * DS_THREADS + threadIdx.x;
+    for (; i + stride < nv; i += 2 * stride) {
+        const uint4 a0 = ld_global_stream16(xv + i), b0 = ld_global_stream16(yv + i);
+        const uint4 a1 = ld_global_stream16(xv + i + stride), b1 = ld_global_stream16(yv + i + stride);
+        dot_accumulate<T, Acc>(acc, a0, b0);
+        dot_accumulate<T, Acc>(acc, a1, b1);
+    }
+    for (; i < nv; i += stride) dot_accumulate<T, Acc>(acc, ld_global_stream16(xv + i), ld_global_stream16(yv + i));
+    for (unsigned long long j = nv * V + (unsigned long long)blockIdx.x * DS_THREADS + threadIdx.x; j < n; j += stride)
+        acc += (Acc)R::mul(x[j], y[j]);
     __shared__ Acc sm[DS_THREADS / 32];
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
@@ -665,7 +687,7 @@ __global__ void __launch_bounds__(DS_THREADS) dot_sum_stage2(const Acc* __restri
 // scratch_dev: >= DS_MAX_BLOCKS * 8 bytes.  SoA shards pass elems = stride*d with
 // zero padding (allocation is zero-initialised), so the flat form is layout-agnostic.
 int dot_sum_partial(const Shard& s, int dtype, size_t elems, const void* X, const void* Y, void* scratch, void* partial) {
-    size_t blocks = (elems + DS_THREADS - 1) / DS_THREADS;
+    size_t blocks = (elems / (16 / dtype_size(dtype)) + DS_THREADS - 1) / DS_THREADS;   // one 16-B vector per thread and pass
     int grid = (int)(blocks < (size_t)DS_MAX_BLOCKS ? (blocks ? blocks : 1) : DS_MAX_BLOCKS);
     switch (dtype) {
         case T5D_F64:

@@ -75,4 +75,8 @@ int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa
 // returns T5I_NOT_SPECIALISED unless (m,k,n) is a supported multiple-of-tile shape
 int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
 
+// ---- t5_xgemm.cu: exact (oracle-order, bit-identical) register-tiled product for shapes without a
+// faster specialisation: large Float / Int64 matrices, Double shapes off the DMMA tile grid
+int exact_blocked_matmul(const Shard& s, int dtype, int P, int K, int Q, const void* A, const void* B, void* C);
+
 }  // namespace t5

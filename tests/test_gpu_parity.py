@@ -450,6 +450,42 @@ def test_mid_size_matmul_generic_is_bit_exact(ctx):
             assert_bits_equal(C, oracle.matmul(a, b, m, k, n), f"generic {m}x{k}x{n}")
 
 
+# ---- exact blocked product (t5_xgemm.cu): oracle order, so bit-exact for every dtype and shape ----
+@pytest.mark.parametrize("dc", ALL)
+@pytest.mark.parametrize("mkn", [(128, 128, 128), (64, 64, 64), (65, 17, 63), (32, 8, 32), (33, 100, 20), (100, 20, 36),
+                                 (16, 16, 17), (200, 9, 40), (24, 31, 130), (48, 48, 48), (1, 64, 300), (300, 64, 1)])
+def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
+    m, k, n = mkn
+    if dc == oracle.F64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
+        pytest.skip("Double 64-multiples take the tensor-core path")
+    for batch in (1, 5, 37):
+        a, b = inputs(dc, 21, batch, m * k, k * n)
+        C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
+        assert_bits_equal(C, oracle.matmul(a, b, m, k, n), f"blocked {m}x{k}x{n} batch {batch}")
+
+
+def test_exact_blocked_matmul_specials_and_k_tail(ctx):
+    """inf / nan / signed zeros in the operands and a K that is not a multiple of the chunk: the K
+    tail must be a loop bound, not zero padding (0 * inf would poison sums the oracle never forms)."""
+    m, k, n, batch = 40, 19, 24, 3
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(batch * m * k)
+    b = rng.standard_normal(batch * k * n)
+    a[5] = np.inf; a[m * k + 7] = -0.0; a[2 * m * k + 11] = np.nan
+    b[3] = -np.inf; b[k * n + 9] = 0.0; b[2 * k * n + 100] = 1e308
+
+    def same(got, want, what):      # bit-equal, except that a NaN only has to be a NaN (generated NaNs differ in sign/payload between x86 and the GPU)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan), what
+        assert_bits_equal(np.where(nan, 0, got), np.where(nan, 0, want), what)
+
+    C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
+    same(C.ravel(), oracle.matmul(a, b, m, k, n).ravel(), "specials f64")
+    af, bf = a.astype(np.float32), b.astype(np.float32)
+    Cf = tb.matmul(ctx.from_numpy(af, (m, k)), ctx.from_numpy(bf, (k, n))).to_numpy()
+    same(Cf.ravel(), oracle.matmul(af, bf, m, k, n).ravel(), "specials f32")
+
+
 def test_dmma_identity_and_linearity(ctx):
     batch, n = 20, 128
     a, _ = inputs(oracle.F64, 17, batch, n * n)
