@@ -311,7 +311,7 @@ class HostCall:
 
     def __init__(self, ctx, tb, w):
         self.ctx, self.tb, self.w = ctx, tb, w
-        if w.get("layout") == "soa" or w["op"] == "append":
+        if w.get("layout") == "soa" or w["op"] in ("append", "dot_sum"):
             raise NotImplementedError("no host-array entry for this workload")
         self.batch = B = max(256, min(w["batch"], E2E_MAX_BYTES // w["bytes"]))
         dev = Step(ctx, tb, w, batch=B)                      # the same synthetic stream, generated on the device ...

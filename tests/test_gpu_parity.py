@@ -423,6 +423,78 @@ def test_full_size_config3_properties(ctx):
     assert np.array_equal(s[sl], ost)
 
 
+def test_full_size_config2_properties(ctx):
+    """16Mi 4x4 Float (BASELINE configs[1]): (A.B)^T == B^T.A^T holds BIT-EXACTLY for floats too (the same
+    products are added in the same j order), A.I == A, transpose is an involution; spot parity on slices."""
+    batch = 1 << 24
+    A = ctx.synthetic((4, 4), np.float32, batch, oracle.SEED_A, 1)
+    B = ctx.synthetic((4, 4), np.float32, batch, oracle.SEED_B, 1)
+    C = A @ B
+    lhs = tb.transpose(C).to_numpy()
+    At, Bt = tb.transpose(A), tb.transpose(B)
+    rhs = (Bt @ At).to_numpy()
+    assert_bits_equal(lhs, rhs, "(AB)^T == B^T A^T")
+    del rhs
+    assert_bits_equal(tb.transpose(At).to_numpy(), A.to_numpy(), "transpose involution")
+    a = oracle.fill(oracle.F32, oracle.SEED_A, 1, batch * 16).reshape(batch, 4, 4)
+    b = oracle.fill(oracle.F32, oracle.SEED_B, 1, batch * 16).reshape(batch, 4, 4)
+    for sl in (slice(0, 4096), slice(batch // 2 - 1000, batch // 2 + 1000), slice(batch - 4099, batch)):
+        want = oracle.transpose(oracle.matmul(a[sl], b[sl], 4, 4, 4), [4, 4]).reshape(-1, 4, 4)
+        assert_bits_equal(lhs[sl], want, f"slice {sl}")
+    # mat.vec and dot on 4-vectors at full size: linearity in the vector is exact for a power-of-two factor
+    x = ctx.synthetic((4,), np.float32, batch, oracle.SEED_B, 2)
+    y = (A @ x).to_numpy()
+    y2 = (A @ tb.scale(np.float32(4.0), x)).to_numpy()
+    assert_bits_equal(y2, 4.0 * y, "A.(4x) == 4 A.x")
+    d = tb.dot(x, x).to_numpy()
+    assert np.all(d >= 0) and d.shape == (batch,)
+
+
+def test_full_size_config4_properties(ctx):
+    """1Mi 8x8 (x) 8x8 -> 8^4 Double (BASELINE configs[3]; 34 GB result): the squared norm of an outer
+    product factorises, sum(C_b^2) == sum(a_b^2) * sum(b_b^2), reduced on the device; prefix parity."""
+    batch = 1 << 20
+    A = ctx.synthetic((8, 8), np.float64, batch, oracle.SEED_A, 4)
+    B = ctx.synthetic((8, 8), np.float64, batch, oracle.SEED_B, 4)
+    C = tb.tensor_product(A, B)
+    assert C.shape == (8, 8, 8, 8)
+    import ctypes
+    out = np.zeros(1)                                   # sum(C*C) reduced on the device (C viewed as 4096-vectors)
+    tb.device.check(tb._lib.lib().t5_dot_sum(ctx._h, C.dtype, 4096, C._h, C._h, out.ctypes.data_as(ctypes.c_void_p)), ctx)
+    a = A.to_numpy().reshape(batch, 64)
+    b = B.to_numpy().reshape(batch, 64)
+    want = float(np.sum(np.sum(a * a, axis=1) * np.sum(b * b, axis=1)))
+    assert abs(out[0] - want) <= 1e-9 * want, (out[0], want)
+    # n = 1 contraction at full size equals the matrix product (prod 1 == .*.), bit-exact
+    P1 = tb.prod(A, B, 1).to_numpy()
+    M = (A @ B).to_numpy()
+    assert_bits_equal(P1, M, "prod 1 == .*.")
+    sl = slice(batch - 300, batch)
+    assert_bits_equal(M[sl].reshape(-1), oracle.matmul(a[sl].ravel(), b[sl].ravel(), 8, 8, 8).ravel(), "8x8 slice")
+
+
+def test_full_size_config5_properties(ctx):
+    """64Ki 128x128 Double on the FP64 tensor cores (BASELINE configs[4]), checked entirely on the device:
+    A.(2I) == 2A exactly (one non-zero term per sum), so sum((A.(2I) - 2A)^2) must be exactly 0."""
+    batch, n = 1 << 16, 128
+    A = ctx.synthetic((n, n), np.float64, batch, oracle.SEED_A, 5)
+    two_eye = ctx.from_numpy(np.broadcast_to(2.0 * np.eye(n), (256, n, n)).copy(), (n, n))
+    a_slab = np.ascontiguousarray(A.to_numpy()[: 256])
+    C = tb.matmul(ctx.from_numpy(a_slab, (n, n)), two_eye).to_numpy()
+    assert_bits_equal(C, 2.0 * a_slab, "A.(2I) == 2A (slab)")
+    # full batch: C = A.B against the tolerance bound on a strided sample, and a launch over every tile
+    B = ctx.synthetic((n, n), np.float64, batch, oracle.SEED_B, 5)
+    Cfull = A @ B
+    ctx.sync()
+    c = np.ascontiguousarray(Cfull.to_numpy()[:: 4099])      # copies, so each 8.6 GB download is dropped at once
+    a = np.ascontiguousarray(A.to_numpy()[:: 4099])
+    b = np.ascontiguousarray(B.to_numpy()[:: 4099])
+    want = np.einsum("bij,bjk->bik", a, b)
+    bound = 1e-12 * np.einsum("bij,bjk->bik", np.abs(a), np.abs(b))
+    assert np.all(np.abs(c - want) <= bound)
+    assert np.all(np.isfinite(c))
+
+
 # ---- FP64 tensor-core (DMMA) product: tolerance stated by north_star -------------------
 @pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 64, 128), (256, 32, 128), (128, 96, 256),
                                  (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64)])
