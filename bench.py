@@ -67,6 +67,10 @@ WORKLOADS = {
                             desc="sum over 16Mi pairs of 4-vector Float dot products (the one reduction; returns a host scalar per call)"),
     "dotsum4_f32_soa_16M": dict(op="dot_sum", dtype="f32", n=4, batch=1 << 24, bytes=32, bound="hbm", layout="soa",
                                 desc="the same reduction on SoA device buffers"),
+    "relayout_4x4_f32_16M": dict(op="relayout", dtype="f32", dims=(4, 4), batch=1 << 24, bytes=128, bound="hbm",
+                                 desc="16Mi 4x4 Float items, AoS (wire order) -> SoA device layout"),
+    "relayout_3x3_f64_soa_4M": dict(op="relayout", dtype="f64", dims=(3, 3), batch=1 << 22, bytes=144, bound="hbm", layout="soa",
+                                    desc="4Mi 3x3 Double items, SoA -> AoS"),
     "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="fp32",
                               desc="64Ki 128x128 Float .*. (exact blocked SIMT product: no TF32, unfused multiply+add)"),
     "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
@@ -76,7 +80,8 @@ HEADLINE = "matmul4x4_f32_16M"
 EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpose4x4_f32_16M", "matvec4_f32_16M",
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
-          "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M"]
+          "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
+          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 
@@ -203,6 +208,11 @@ class Step:
             self.out = np.zeros((1,), dtype=dt)
             po = self.out.ctypes.data_as(ctypes.c_void_p)
             self.run = lambda: L.t5_dot_sum(h, code, n, self.a._h, self.b._h, po)   # returns the scalar: synchronises
+        elif op == "relayout":
+            dims = w["dims"]
+            self.a = syn(dims, SEED_A, 7)                                   # AoS (or SoA) source
+            self.c = ctx.empty(dims, dt, B, tb.AOS if lay == tb.SOA else tb.SOA)
+            self.run = lambda: L.t5_relayout(self.c._h, self.a._h)
         elif op == "transpose":
             dims = w["dims"]
             self.a = syn(dims, SEED_A, 3)
@@ -311,7 +321,7 @@ class HostCall:
 
     def __init__(self, ctx, tb, w):
         self.ctx, self.tb, self.w = ctx, tb, w
-        if w.get("layout") == "soa" or w["op"] in ("append", "dot_sum"):
+        if w.get("layout") == "soa" or w["op"] in ("append", "dot_sum", "relayout"):
             raise NotImplementedError("no host-array entry for this workload")
         self.batch = B = max(256, min(w["batch"], E2E_MAX_BYTES // w["bytes"]))
         dev = Step(ctx, tb, w, batch=B)                      # the same synthetic stream, generated on the device ...

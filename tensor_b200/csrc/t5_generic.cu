@@ -796,8 +796,90 @@ relayout_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long lo
     }
 }
 
+// Small records (d <= 64 elements: every tiny matrix / vector of the hot path).  The AoS image of
+// TI consecutive items is ONE contiguous segment, so it moves with perfectly coalesced linear
+// accesses; the SoA side moves as d row segments of TI elements.  In between the tile sits in
+// shared memory as [item][element] with an odd pitch, which makes the column reads / writes of the
+// SoA phase conflict-free.  No index division in either loop.
+constexpr int RL_TI = 128, RL_THREADS = 256;
+
+template <class T>
+__global__ void __launch_bounds__(RL_THREADS)
+relayout_small_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long long count, unsigned d,
+                      unsigned long long stride, int to_soa) {
+    extern __shared__ __align__(16) unsigned char rl_smem[];
+    T* tile = reinterpret_cast<T*>(rl_smem);
+    const unsigned pitch = d | 1u;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned step_q = RL_THREADS / d, step_r = RL_THREADS - step_q * d;
+    const unsigned long long n_tiles = (count + RL_TI - 1) / RL_TI;
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const unsigned long long b0 = t * RL_TI;
+        const unsigned nv = count - b0 < (unsigned long long)RL_TI ? (unsigned)(count - b0) : (unsigned)RL_TI;
+        const unsigned total = nv * d;
+        __syncthreads();                                    // the previous tile has left shared memory
+        if (to_soa) {
+            const T* a = src + b0 * d;
+            unsigned i = tid / d, e = tid - i * d;
+            for (unsigned l = tid; l < total; l += RL_THREADS) {
+                tile[i * pitch + e] = a[l];
+                i += step_q; e += step_r;
+                if (e >= d) { e -= d; ++i; }
+            }
+            __syncthreads();
+            for (unsigned r = warp; r < d; r += RL_THREADS / 32) {
+                T* row = dst + (unsigned long long)r * stride + b0;
+                #pragma unroll
+                for (unsigned j = 0; j < RL_TI / 32; ++j) {
+                    const unsigned it = lane + 32 * j;
+                    if (it < nv) row[it] = tile[it * pitch + r];
+                }
+            }
+        } else {
+            for (unsigned r = warp; r < d; r += RL_THREADS / 32) {
+                const T* row = src + (unsigned long long)r * stride + b0;
+                #pragma unroll
+                for (unsigned j = 0; j < RL_TI / 32; ++j) {
+                    const unsigned it = lane + 32 * j;
+                    if (it < nv) tile[it * pitch + r] = row[it];
+                }
+            }
+            __syncthreads();
+            T* a = dst + b0 * d;
+            unsigned i = tid / d, e = tid - i * d;
+            for (unsigned l = tid; l < total; l += RL_THREADS) {
+                a[l] = tile[i * pitch + e];
+                i += step_q; e += step_r;
+                if (e >= d) { e -= d; ++i; }
+            }
+        }
+    }
+}
+
+template <class T>
+static int relayout_small(cudaStream_t st, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
+    const size_t smem = (size_t)RL_TI * (d | 1) * sizeof(T);
+    auto kern = relayout_small_kernel<T>;
+    static bool configured[T5_MAX_DEVICES] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
+    if (!configured[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_TI * 65 * (int)sizeof(T)) != cudaSuccess) return T5I_CUDA;
+        configured[dev] = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+    const size_t tiles = (count + RL_TI - 1) / RL_TI;
+    const size_t cap = (size_t)sm_count() * occ;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    kern<<<grid, RL_THREADS, smem, st>>>((const T*)src, (T*)dst, count, (unsigned)d, soa_stride, to_soa ? 1 : 0);
+    return ok();
+}
+
 int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
     if (count == 0 || d == 0) return T5I_OK;
+    if (d <= 64 && elem_bytes == 8) return relayout_small<unsigned long long>(st, d, count, soa_stride, to_soa, src, dst);
+    if (d <= 64 && elem_bytes == 4) return relayout_small<unsigned>(st, d, count, soa_stride, to_soa, src, dst);
     const size_t tiles = ((count + 31) / 32) * ((d + 31) / 32);
     const void* kern = elem_bytes == 8 ? (const void*)relayout_kernel<unsigned long long>
                      : elem_bytes == 4 ? (const void*)relayout_kernel<unsigned> : (const void*)relayout_kernel<unsigned char>;
