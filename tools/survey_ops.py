@@ -1,0 +1,84 @@
+"""Developer survey: time every remaining public operation once (device-resident, CUDA events on the
+library's stream) and print achieved GB/s against algorithmic bytes, to find untuned paths.
+Each call allocates its result, so the figures include cudaMalloc/cudaFree of the output; read them as
+lower bounds.  Usage (GPU box): python tools/survey_ops.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tensor_b200 as tb  # noqa: E402
+from tensor_b200 import structure as st  # noqa: E402
+
+SEED = 0x5EED000000000001
+
+
+def timed(ctx, fn, reps=5):
+    outs = [fn() for _ in range(2)]
+    for o in outs:
+        free(o)
+    ctx.sync()
+    ctx.timer_begin()
+    outs = [fn() for _ in range(reps)]
+    ms = ctx.timer_end() / reps
+    for o in outs:
+        free(o)
+    return ms
+
+
+def free(o):
+    if isinstance(o, tuple):
+        for x in o:
+            free(x)
+    elif hasattr(o, "free"):
+        o.free()
+
+
+def main():
+    with tb.Context([0]) as ctx:
+        rows = []
+
+        def add(name, nbytes, fn):
+            ms = timed(ctx, fn)
+            rows.append((name, ms, nbytes / ms / 1e6))
+            print("%-44s %8.3f ms %8.0f GB/s" % rows[-1], flush=True)
+
+        B = 1 << 22
+        for dt, es in ((np.float64, 8), (np.float32, 4)):
+            tag = "f64" if es == 8 else "f32"
+            A3 = ctx.synthetic((3, 3), dt, B, SEED, 1)
+            A4 = ctx.synthetic((4, 4), dt, B, SEED, 2)
+            B4 = ctx.synthetic((4, 4), dt, B, SEED + 1, 2)
+            v3 = ctx.synthetic((3, 1), dt, B, SEED, 3)
+            A6 = ctx.synthetic((6, 6), dt, B // 4, SEED, 4)
+            b6 = ctx.synthetic((6,), dt, B // 4, SEED + 1, 4)
+            A8 = ctx.synthetic((8, 8), dt, B // 4, SEED, 5)
+            T234 = ctx.synthetic((2, 3, 4), dt, B, SEED, 6)
+            add(f"zip + 4x4 {tag}", B * 16 * es * 3, lambda: tb.zip_with("+", A4, B4))
+            add(f"scale 4x4 {tag}", B * 16 * es * 2, lambda: tb.scale(dt(3.0), A4))
+            add(f"tr 4x4 {tag}", B * (16 + 1) * es, lambda: tb.tr(A4))
+            add(f"polyEval deg3 4x4 {tag}", B * 32 * es, lambda: tb.poly_eval(A4, [1.0, 2.0, 0.5, 0.25]))
+            add(f"charPoly 4x4 {tag}", B * (16 + 5) * es, lambda: tb.char_poly(A4))
+            add(f"minPoly 4x4 {tag}", B * (16 + 5) * es + B, lambda: tb.min_poly(A4))
+            add(f"append 3x3|3 {tag}", B * 24 * es, lambda: st.append(2, A3, v3))
+            add(f"split 4x4 -> 4x3,4x1 {tag}", B * 32 * es, lambda: st.split(2, 3, A4))
+            add(f"at 4x4 column {tag}", B * (16 + 4) * es, lambda: st.at(A4, [2]))
+            add(f"ta 4x4 row {tag}", B * (16 + 4) * es, lambda: st.ta(2, A4))
+            add(f"slice 2x3x4 [_,2,_] {tag}", B * (24 + 8) * es, lambda: st.slice_(T234, [None, 2, None]))
+            add(f"permute_axes 2x3x4 (2,0,1) {tag}", B * 48 * es, lambda: st.permute_axes(T234, [2, 0, 1]))
+            add(f"transpose 2x3x4 {tag}", B * 48 * es, lambda: tb.transpose(T234))
+            add(f"det 6x6 {tag}", (B // 4) * 37 * es, lambda: tb.det(A6))
+            add(f"inverse 6x6 {tag}", (B // 4) * 72 * es, lambda: tb.inverse(A6))
+            add(f"solve 6x6 {tag}", (B // 4) * 48 * es, lambda: tb.solve(A6, b6))
+            add(f"det 8x8 {tag}", (B // 4) * 65 * es, lambda: tb.det(A8))
+            add(f"inverse 8x8 {tag}", (B // 4) * 128 * es, lambda: tb.inverse(A8))
+            add(f"matmul 5x5 {tag}", B * 75 * es, lambda: tb.matmul(ctx.synthetic((5, 5), dt, B, SEED, 7), ctx.synthetic((5, 5), dt, B, SEED, 8)))
+            add(f"matmul 4x4 (Double/Float) {tag}", B * 48 * es, lambda: tb.matmul(A4, B4))
+            add(f"matmul 32x32 {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(ctx.synthetic((32, 32), dt, B // 64, SEED, 9), ctx.synthetic((32, 32), dt, B // 64, SEED, 10)))
+            for x in (A3, A4, B4, v3, A6, b6, A8, T234):
+                x.free()
+
+
+if __name__ == "__main__":
+    main()
