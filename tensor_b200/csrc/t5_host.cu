@@ -618,6 +618,7 @@ int t5_det(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT) {
         CU(c, cudaSetDevice(c->dev[g]));
         Shard s = shard_of(c, A, g);
         int r = small_det(s, dtype, n, A->ptr[g], OUT->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = rowlane_det(s, dtype, n, A->ptr[g], OUT->ptr[g]);
         if (r == T5I_NOT_SPECIALISED) r = generic_det(s, dtype, n, A->ptr[g], OUT->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_det");
         c->launches++;
@@ -639,6 +640,7 @@ int t5_inverse(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf
         CU(c, cudaSetDevice(c->dev[g]));
         Shard s = shard_of(c, A, g);
         int r = small_inverse(s, dtype, n, A->ptr[g], OUT->ptr[g], STATUS->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = rowlane_inverse(s, dtype, n, A->ptr[g], OUT->ptr[g], STATUS->ptr[g]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(s, dtype, n, n, true, A->ptr[g], nullptr, OUT->ptr[g], STATUS->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_inverse");
         c->launches++;
@@ -661,6 +663,7 @@ int t5_solve(t5_ctx* c, int dtype, int n, int nrhs, const t5_buf* A, const t5_bu
         CU(c, cudaSetDevice(c->dev[g]));
         Shard s = shard_of(c, A, g);
         int r = small_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = rowlane_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(s, dtype, n, nrhs, false, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_solve");
         c->launches++;
@@ -921,6 +924,7 @@ int t5_det_host(t5_ctx* c, int dtype, int n, size_t batch, const void* A, void* 
     const HostOperand ops[2] = {{A, nullptr, (size_t)n * n * es}, {nullptr, OUT, es}};
     return host_pipeline(c, batch, ops, 2, [&](int, const Shard& sh, void* const* d) {
         int r = small_det(sh, dtype, n, d[0], d[1]);
+        if (r == T5I_NOT_SPECIALISED) r = rowlane_det(sh, dtype, n, d[0], d[1]);
         if (r == T5I_NOT_SPECIALISED) r = generic_det(sh, dtype, n, d[0], d[1]);
         if (r != T5I_OK) return map_internal(c, r, "t5_det_host");
         c->launches++;
@@ -936,6 +940,7 @@ int t5_inverse_host(t5_ctx* c, int dtype, int n, size_t batch, const void* A, vo
     const HostOperand ops[3] = {{A, nullptr, (size_t)n * n * es}, {nullptr, OUT, (size_t)n * n * es}, {nullptr, status, 1}};
     return host_pipeline(c, batch, ops, 3, [&](int, const Shard& sh, void* const* d) {
         int r = small_inverse(sh, dtype, n, d[0], d[1], d[2]);
+        if (r == T5I_NOT_SPECIALISED) r = rowlane_inverse(sh, dtype, n, d[0], d[1], d[2]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(sh, dtype, n, n, true, d[0], nullptr, d[1], d[2]);
         if (r != T5I_OK) return map_internal(c, r, "t5_inverse_host");
         c->launches++;
@@ -952,6 +957,7 @@ int t5_solve_host(t5_ctx* c, int dtype, int n, int nrhs, size_t batch, const voi
                                 {nullptr, X, (size_t)n * nrhs * es}, {nullptr, status, 1}};
     return host_pipeline(c, batch, ops, 4, [&](int, const Shard& sh, void* const* d) {
         int r = small_solve(sh, dtype, n, nrhs, d[0], d[1], d[2], d[3]);
+        if (r == T5I_NOT_SPECIALISED) r = rowlane_solve(sh, dtype, n, nrhs, d[0], d[1], d[2], d[3]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(sh, dtype, n, nrhs, false, d[0], d[1], d[2], d[3]);
         if (r != T5I_OK) return map_internal(c, r, "t5_solve_host");
         c->launches++;

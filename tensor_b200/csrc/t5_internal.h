@@ -75,6 +75,11 @@ int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa
 // returns T5I_NOT_SPECIALISED unless (m,k,n) is a supported multiple-of-tile shape
 int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
 
+// ---- t5_rowelim.cu: row-per-lane (8 lanes per matrix, warp shuffles) elimination for 5 <= n <= 8 -----
+int rowlane_det(const Shard& s, int dtype, int n, const void* A, void* O);
+int rowlane_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
+int rowlane_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
+
 // ---- t5_xgemm.cu: exact (oracle-order, bit-identical) register-tiled product for shapes without a
 // faster specialisation: large Float / Int64 matrices, Double shapes off the DMMA tile grid
 int exact_blocked_matmul(const Shard& s, int dtype, int P, int K, int Q, const void* A, const void* B, void* C);

@@ -186,7 +186,7 @@ def elim_inputs(dc, n, batch, nrhs=1):
 
 
 @pytest.mark.parametrize("dc", FRAC)
-@pytest.mark.parametrize("n", [2, 3, 4, 5, 8])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_det_inverse_solve_bit_exact(ctx, dc, n, layout):
     if layout == tb.SOA and n > 4:
@@ -212,8 +212,9 @@ def test_det_inverse_solve_bit_exact(ctx, dc, n, layout):
 
 
 @pytest.mark.parametrize("dc", FRAC)
-def test_solve_matrix_rhs_equals_inverse(ctx, dc):
-    batch, n = 777, 4
+@pytest.mark.parametrize("n", [4, 6, 8])
+def test_solve_matrix_rhs_equals_inverse(ctx, dc, n):
+    batch = 777
     a, _ = elim_inputs(dc, n, batch)
     eye = np.broadcast_to(np.eye(n, dtype=a.dtype), (batch, n, n)).copy()
     A = ctx.from_numpy(a, (n, n))
@@ -221,6 +222,38 @@ def test_solve_matrix_rhs_equals_inverse(ctx, dc):
     inv, st2 = tb.inverse(A)
     assert_bits_equal(X.to_numpy(), inv.to_numpy(), "solve(A, I) == inverse(A)")
     assert np.array_equal(st.to_numpy(), st2.to_numpy())
+
+
+@pytest.mark.parametrize("n", [5, 8])
+def test_row_per_lane_elimination_pivot_positions(ctx, n):
+    """Row-per-lane kernels (5 <= n <= 8): a zero pivot in EVERY column position with the first non-zero
+    entry at every possible row below it, several swaps in one matrix, and singular columns at each k."""
+    rng = np.random.default_rng(n)
+    mats = []
+    for k in range(n):
+        for r in range(k + 1, n):                 # column k is zero in rows k..r-1: pivot must come from row r
+            u = np.triu(rng.standard_normal((n, n))) + np.eye(n)   # start from an upper-triangular matrix: elimination
+            u[k:r, k] = 0.0                                        # leaves its diagonal alone, so the zeros stay zero
+            u[r, k] = 1.5
+            mats.append(u)
+        s = np.triu(rng.standard_normal((n, n))) + np.eye(n)
+        s[k:, k] = 0.0                                             # no pivot in column k at all: singular
+        mats.append(s)
+    p = np.eye(n)[::-1].copy()                                     # anti-diagonal: n // 2 swaps
+    mats.append(p)
+    a = np.stack(mats).astype(np.float64)
+    batch = a.shape[0]
+    b = rng.standard_normal((batch, n))
+    A = ctx.from_numpy(a, (n, n))
+    assert_bits_equal(tb.det(A).to_numpy(), oracle.det(a, n), "det")
+    inv, st = tb.inverse(A)
+    oinv, ost = oracle.inverse(a, n)
+    assert ost.sum() == n and np.array_equal(st.to_numpy(), ost)
+    assert_bits_equal(inv.to_numpy(), oinv, "inverse")
+    X, st = tb.solve(A, ctx.from_numpy(b, (n,)))
+    ox, ost = oracle.solve(a, b, n, 1)
+    assert np.array_equal(st.to_numpy(), ost)
+    assert_bits_equal(X.to_numpy(), ox.reshape(batch, n), "solve")
 
 
 def test_det_rejects_int64_and_nonsquare(ctx):
