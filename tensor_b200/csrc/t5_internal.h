@@ -75,6 +75,10 @@ int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa
 // returns T5I_NOT_SPECIALISED unless (m,k,n) is a supported multiple-of-tile shape
 int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
 
+// ---- t5_tf32x3.cu: Float products on tcgen05 tensor cores (3xTF32 split, TMEM accumulators) for shapes
+// on the 128 x 128 x 32 tile grid; within north_star's 1e-5 Float tolerance, not bit-exact
+int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
+
 // ---- t5_rowelim.cu: row-per-lane (8 lanes per matrix, warp shuffles) elimination for 5 <= n <= 8 -----
 int rowlane_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int rowlane_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);

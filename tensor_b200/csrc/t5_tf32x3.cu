@@ -1,0 +1,359 @@
+// Batched Float `.*.` for large matrices on the 5th-generation tensor cores: tcgen05.mma kind::tf32
+// with the operand split a = a_hi + a_lo ("3xTF32"), accumulators in TMEM.
+//
+// A single TF32 pass keeps 10 mantissa bits (~1e-3): not acceptable.  With
+//      A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi        (a_hi = a truncated to TF32, a_lo = a - a_hi, exact)
+// the dropped term is ~2^-20 |a||b|, well inside the |delta| <= 1e-5 * sum_j |a_ij||b_jk| bar that
+// north_star states for Float (tests hold this kernel to it; shapes off the 128/32 tile grid, and
+// Int64, stay on the bit-exact SIMT product of t5_xgemm.cu).  128x128x128 items are then HBM-bound
+// (21 flop/B) instead of FP32-issue-bound.
+//
+//   warp 0 (1 lane)   TMA producer: A chunk 128 x 32 (K-major, SWIZZLE_128B), B chunk 32 x 128
+//                     (MN-major: [4 n-blocks][32 k-rows][32 floats], SWIZZLE_128B_ATOM_32B - the
+//                     only layout tcgen05 accepts for MN-major 32-bit operands)      --full[s]-->
+//   warps 4-7         split: x_lo = x - trunc_tf32(x) for both chunks into twin tiles of the same
+//                     (swizzled) layout; fence.proxy.async                            --conv[s]-->
+//   warp 1 (1 lane)   tcgen05.mma cta_group::1 kind::tf32, M=128 N=128 K=8: per K step
+//                     (A_lo,B) (A,B_lo) (A,B) into one of two 128-column TMEM accumulators;
+//                     tcgen05.commit frees the stage (--empty[s]-->) and, after the last
+//                     chunk, hands the accumulator over                               --tmem_full[a]-->
+//   warps 8-11        epilogue: tcgen05.ld 32 lanes x 32 columns, rows straight to HBM --tmem_empty[a]-->
+//   warp 2            TMEM allocation (256 columns) and release
+//
+// The hardware reads the FP32 bit patterns of the "hi" tiles and ignores the 13 low mantissa bits,
+// so the raw operands serve as a_hi / b_hi and only the lo tiles are computed.
+#include <cuda.h>
+#include "t5_device.cuh"
+#include "t5_internal.h"
+
+namespace t5 {
+namespace tf {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int THREADS = 384;
+constexpr int TILE_A = BM * BK * 4, TILE_B = BK * BN * 4;            // 16 KB each
+constexpr int STAGE = 2 * (TILE_A + TILE_B);                        // hi + lo tiles: 64 KB
+constexpr int SMEM = STAGES * STAGE + 1024;
+constexpr int TMEM_COLS = 256;                                      // two 128-column FP32 accumulators
+static_assert(SMEM <= 227 * 1024, "ring does not fit");
+
+constexpr float FLT_MAX_F = 3.4028234664e38f;
+
+struct Args {
+    const float* A;
+    const float* B;
+    float* C;
+    int M, N, K;
+    unsigned long long count;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 24)) __trap();       // a ring that never fills traps instead of hanging the device
+    }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void tc_mma_tf32(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b,
+                                            unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor (SM100 UMMA): start address, leading / stride byte offsets in
+// 16-byte units, version 1, SWIZZLE_128B.
+// layout: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only layout the
+// hardware accepts for MN-major 32-bit operands).
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsigned lbo16, unsigned sbo16, unsigned layout) {
+    return (unsigned long long)((smem_addr >> 4) & 0x3fffu) | ((unsigned long long)(lbo16 & 0x3fffu) << 16) |
+           ((unsigned long long)(sbo16 & 0x3fffu) << 32) | (1ull << 46) | ((unsigned long long)layout << 61);
+}
+// Instruction descriptor: D = F32, A = B = TF32, A K-major, B MN-major, N = 128, M = 128.
+constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((unsigned)(BN >> 3) << 17) |
+                           ((unsigned)(BM >> 4) << 24);
+
+__device__ __forceinline__ float lo_part(float x) {
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const float lo = x - hi;                                   // exact
+    return (fabsf(x) <= 3.4028234664e38f) ? lo : 0.0f;         // inf / nan: such tiles are recomputed exactly (see special_tile)
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[3 * STAGES + 4];   // full, conv, empty, tmem_full[2], tmem_empty[2]
+    __shared__ unsigned tmem_base_smem;
+    // Non-finite operands: inf * (lo part) would turn the reference's inf into NaN.  The split warps
+    // record the sequence number of any tile that contains one; its epilogue recomputes that tile
+    // with the sequential exact fold instead of reading TMEM (rare path, same results as the oracle).
+    __shared__ unsigned special_tile[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const unsigned bar0 = smem_u32(bars);
+    auto full_bar = [&](unsigned s) { return bar0 + 8 * s; };
+    auto conv_bar = [&](unsigned s) { return bar0 + 8 * (STAGES + s); };
+    auto empty_bar = [&](unsigned s) { return bar0 + 8 * (2 * STAGES + s); };
+    auto tfull_bar = [&](unsigned a) { return bar0 + 8 * (3 * STAGES + a); };
+    auto tempty_bar = [&](unsigned a) { return bar0 + 8 * (3 * STAGES + 2 + a); };
+
+    const int tiles_m = p.M / BM, tiles_n = p.N / BN, kch = p.K / BK;
+    const unsigned long long tiles_per_item = (unsigned long long)tiles_m * tiles_n;
+    const unsigned long long n_tiles = p.count * tiles_per_item;
+
+    if (tid < 8) special_tile[tid] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(conv_bar(s), 4);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     ::"r"(smem_u32(&tmem_base_smem)), "r"((unsigned)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ---- TMA producer ----
+        if (lane == 0) {
+            unsigned it = 0;
+            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const unsigned long long item = tile / tiles_per_item;
+                const int rem = (int)(tile - item * tiles_per_item);
+                const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+                const int a_row = (int)(item * p.M) + tm * BM;
+                const int b_row = (int)(item * p.K);
+                for (int kc = 0; kc < kch; ++kc, ++it) {
+                    const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), TILE_A + TILE_B);
+                    tma_load_2d(ring + s * STAGE, &mapA, full_bar(s), kc * BK, a_row);
+                    tma_load_3d(ring + s * STAGE + TILE_A, &mapB, full_bar(s), 0, b_row + kc * BK, tn * (BN / 32));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            unsigned it = 0, tl = 0;
+            for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+                const unsigned acc = tl & 1;
+                mbar_wait(tempty_bar(acc), ((tl >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
+                tc_fence_after();
+                const unsigned tmem_d = tmem_base + acc * BN;
+                for (int kc = 0; kc < kch; ++kc, ++it) {
+                    const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(conv_bar(s), ph);                             // operands and their lo parts are in place
+                    tc_fence_after();
+                    const unsigned a_hi = ring + s * STAGE, b_hi = a_hi + TILE_A;
+                    const unsigned a_lo = b_hi + TILE_B, b_lo = a_lo + TILE_A;
+                    #pragma unroll
+                    for (int k8 = 0; k8 < BK / 8; ++k8) {
+                        // A (K-major): 32 bytes further along the 128-byte swizzled rows; 8-row groups 1024 B apart
+                        const unsigned long long da_hi = umma_desc(a_hi + k8 * 32, 1, 64, 2);
+                        const unsigned long long da_lo = umma_desc(a_lo + k8 * 32, 1, 64, 2);
+                        // B (MN-major, 32-byte swizzle atoms of 4 k-rows x 128 B): 8 k-rows = 1024 B further per step,
+                        // 4-row atoms 512 B apart (SBO), 32-column blocks 4096 B apart (LBO)
+                        const unsigned long long db_hi = umma_desc(b_hi + k8 * 1024, 256, 32, 1);
+                        const unsigned long long db_lo = umma_desc(b_lo + k8 * 1024, 256, 32, 1);
+                        tc_mma_tf32(tmem_d, da_lo, db_hi, IDESC, (kc | k8) ? 1u : 0u);   // small terms first
+                        tc_mma_tf32(tmem_d, da_hi, db_lo, IDESC, 1u);
+                        tc_mma_tf32(tmem_d, da_hi, db_hi, IDESC, 1u);
+                    }
+                    tc_commit(empty_bar(s));                                // stage free once these MMAs have read it
+                }
+                tc_commit(tfull_bar(acc));                                  // accumulator complete
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ---- split warps: lo tiles ----
+        const int t = tid - 128;
+        unsigned it = 0, tl = 0;
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            for (int kc = 0; kc < kch; ++kc, ++it) {
+                const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                const unsigned hi = ring + s * STAGE, lo = hi + TILE_A + TILE_B;
+                bool special = false;
+                #pragma unroll 4
+                for (int c = 0; c < (TILE_A + TILE_B) / 16 / 128; ++c) {
+                    const unsigned off = (unsigned)(t + c * 128) * 16u;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(hi + off));
+                    special = special || !(fabsf(v.x) <= FLT_MAX_F && fabsf(v.y) <= FLT_MAX_F && fabsf(v.z) <= FLT_MAX_F && fabsf(v.w) <= FLT_MAX_F);
+                    v.x = lo_part(v.x); v.y = lo_part(v.y); v.z = lo_part(v.z); v.w = lo_part(v.w);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(lo + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                }
+                if (special) *(volatile unsigned*)&special_tile[tl & 7] = tl + 1;
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(conv_bar(s));
+            }
+        }
+    } else if (warp >= 8) {
+        // ---- epilogue: TMEM -> registers -> HBM; warp q owns TMEM lanes 32q .. 32q+31 = rows of the tile ----
+        const int q = warp & 3;
+        unsigned tl = 0;
+        for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+            const unsigned acc = tl & 1;
+            const unsigned long long item = tile / tiles_per_item;
+            const int rem = (int)(tile - item * tiles_per_item);
+            const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+            mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
+            tc_fence_after();
+            float* crow = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * 32 + lane) * p.N + tn * BN;
+            if (*(volatile unsigned*)&special_tile[tl & 7] == tl + 1) {
+                // exact sequential fold for this thread's row (multiply, round, add, round; k ascending)
+                const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + q * 32 + lane) * p.K;
+                const float* bcol = p.B + item * (size_t)p.K * p.N + tn * BN;
+                for (int j = 0; j < BN; ++j) {
+                    float acc_x = 0.0f;
+                    for (int kk = 0; kk < p.K; ++kk) acc_x = __fadd_rn(acc_x, __fmul_rn(__ldg(arow + kk), __ldg(bcol + (size_t)kk * p.N + j)));
+                    crow[j] = acc_x;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                continue;
+            }
+            #pragma unroll
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                unsigned r[32];
+                const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + cc * 32;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 v{r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]};
+                    st_global_stream16(crow + cc * 32 + j * 4, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((unsigned)TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return (EncodeTiledFn)f;
+    }();
+    return fn;
+}
+
+static int launch(const Shard& s, int m, int k, int n, const float* A, const float* B, float* C, int sms) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return T5I_CUDA;
+    const size_t per = (size_t)0x7fffffff / (size_t)(m > k ? m : k);      // TMA coordinates are int32
+    for (size_t off = 0; off < s.count; off += per) {
+        const size_t cnt = s.count - off < per ? s.count - off : per;
+        CUtensorMap ma, mb;
+        {   // A: [cnt*m rows][k] floats, box 32 floats x 128 rows, K-major
+            const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)cnt * m};
+            const cuuint64_t strides[1] = {(cuuint64_t)k * 4};
+            const cuuint32_t box[2] = {BK, BM}, estr[2] = {1, 1};
+            if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A + off * (size_t)m * k), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
+        }
+        {   // B: [cnt*k rows][n] floats viewed as {32, rows, n/32}; box {32, 32 k-rows, 4 column blocks}
+            const cuuint64_t dims[3] = {32, (cuuint64_t)cnt * k, (cuuint64_t)(n / 32)};
+            const cuuint64_t strides[2] = {(cuuint64_t)n * 4, 128};
+            const cuuint32_t box[3] = {32, BK, BN / 32}, estr[3] = {1, 1, 1};
+            if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(B + off * (size_t)k * n), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
+        }
+        const unsigned long long tiles = (unsigned long long)cnt * (m / BM) * (n / BN);
+        const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
+        Args a{A + off * (size_t)m * k, B + off * (size_t)k * n, C + off * (size_t)m * n, m, n, k, (unsigned long long)cnt};
+        tf32x3_kernel<<<grid, THREADS, SMEM, s.stream>>>(ma, mb, a);
+        if (cudaGetLastError() != cudaSuccess) return T5I_CUDA;
+    }
+    return T5I_OK;
+}
+
+}  // namespace tf
+
+int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
+    if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
+    if (m % tf::BM || n % tf::BN || k % tf::BK || k < tf::BK) return T5I_NOT_SPECIALISED;
+    static bool configured[T5_MAX_DEVICES] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
+    if (!configured[dev]) {
+        if (cudaFuncSetAttribute(tf::tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM) != cudaSuccess) return T5I_CUDA;
+        configured[dev] = true;
+    }
+    if (s.count == 0) return T5I_OK;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
+    return tf::launch(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
+}
+
+}  // namespace t5

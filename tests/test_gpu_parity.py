@@ -563,10 +563,52 @@ def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
     m, k, n = mkn
     if dc == oracle.F64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
         pytest.skip("Double 64-multiples take the tensor-core path")
+    if dc == oracle.F32 and m % 128 == 0 and n % 128 == 0 and k % 32 == 0:
+        pytest.skip("Float 128-multiples take the tcgen05 3xTF32 path (tolerance test below)")
     for batch in (1, 5, 37):
         a, b = inputs(dc, 21, batch, m * k, k * n)
         C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
         assert_bits_equal(C, oracle.matmul(a, b, m, k, n), f"blocked {m}x{k}x{n} batch {batch}")
+
+
+# ---- Float on tcgen05 (3xTF32, TMEM accumulators): tolerance stated by north_star for Float ----
+@pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 32, 128), (256, 64, 128), (128, 96, 256), (256, 160, 256)])
+def test_tf32x3_matmul_within_tolerance(ctx, mkn):
+    m, k, n = mkn
+    for batch in (1, 7, 150, 301):          # > 148 tiles: every CTA works, some take several tiles (both TMEM accumulators)
+        a, b = inputs(oracle.F32, 22, batch, m * k, k * n)
+        C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
+        a3 = a.reshape(batch, m, k).astype(np.float64)
+        b3 = b.reshape(batch, k, n).astype(np.float64)
+        want = np.einsum("bij,bjk->bik", a3, b3)
+        bound = 1e-5 * np.einsum("bij,bjk->bik", np.abs(a3), np.abs(b3))      # |delta| <= 1e-5 * sum_j |a_ij||b_jk|
+        err = np.abs(C.astype(np.float64) - want)
+        assert np.all(err <= bound), f"max excess {np.max(err / bound)} at {np.unravel_index(np.argmax(err / bound), err.shape)}"
+        # and far better than a single TF32 pass would be (~1e-3): the split terms are really there
+        assert np.max(err / bound) < 0.5
+
+
+def test_tf32x3_identity_and_specials(ctx):
+    batch, n = 5, 128
+    a, _ = inputs(oracle.F32, 23, batch, n * n)
+    eye = np.broadcast_to(np.eye(n, dtype=np.float32), (batch, n, n)).copy()
+    A = ctx.from_numpy(a, (n, n))
+    C = (A @ ctx.from_numpy(eye, (n, n))).to_numpy().ravel()
+    assert np.allclose(C, a, rtol=2e-6, atol=0)                 # hi + lo recombine the operand to ~2^-21
+    # non-finite operands: the tiles that contain them are recomputed with the exact sequential fold, so they
+    # match the oracle bit for bit (inf stays inf where the reference has inf, NaN where it has NaN)
+    a2 = a.copy(); a2[7] = np.inf; a2[n * n + 3] = np.nan; a2[3 * n * n + 130] = -np.inf
+    b2, _ = inputs(oracle.F32, 24, batch, n * n)
+    b2 = b2.copy(); b2[2 * n * n + 77] = np.inf
+    C2 = (ctx.from_numpy(a2, (n, n)) @ ctx.from_numpy(b2, (n, n))).to_numpy().reshape(batch, n, n)
+    want = oracle.matmul(a2, b2, n, n, n).reshape(batch, n, n)
+    for item in (0, 1, 2, 3):
+        nan = np.isnan(want[item])
+        assert np.array_equal(np.isnan(C2[item]), nan), item
+        assert_bits_equal(np.where(nan, 0, C2[item]), np.where(nan, 0, want[item]), f"special item {item}")
+    assert np.isinf(want[0]).any() and np.isinf(C2[0]).any()
+    err = np.abs(C2[4].astype(np.float64) - want[4])                      # the untouched item stays on the tensor cores
+    assert np.all(err <= 1e-5 * (np.abs(a2.reshape(batch, n, n)[4]).astype(np.float64) @ np.abs(b2.reshape(batch, n, n)[4]).astype(np.float64)))
 
 
 def test_exact_blocked_matmul_specials_and_k_tail(ctx):
