@@ -10,7 +10,7 @@
 // Rounding differs from the sequential fold of the oracle (the tensor pipe fuses and
 // re-associates inside a k4 step): tests hold this kernel to
 // |delta| <= 1e-12 * sum_j |a_ij||b_jk|, the tolerance north_star states for Double.
-// History (numbers in DESIGN.md §5.8): a cp.async ring issued by the DMMA warps with a CTA barrier
+// History (numbers in DESIGN.md §5.9): a cp.async ring issued by the DMMA warps with a CTA barrier
 // per K chunk kept the DMMA pipe 74 % busy (9.49 ms for 64Ki x 128^3); this kernel 96 % (7.73 ms).
 #include <cuda.h>
 #include "t5_device.cuh"

@@ -33,7 +33,9 @@ constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int THREADS = 384;
 constexpr int TILE_A = BM * BK * 4, TILE_B = BK * BN * 4;            // 16 KB each
 constexpr int STAGE = 2 * (TILE_A + TILE_B);                        // hi + lo tiles: 64 KB
-constexpr int SMEM = STAGES * STAGE + 1024;
+constexpr int EPI_PITCH = 36 * 4;                                   // staging row pitch: 32 floats + 16 B (conflict-free v4 access)
+constexpr int EPI_WARP = 32 * EPI_PITCH;                            // one 32 x 32 block per epilogue warp
+constexpr int SMEM = STAGES * STAGE + 1024 + 4 * EPI_WARP;
 constexpr int TMEM_COLS = 256;                                      // two 128-column FP32 accumulators
 static_assert(SMEM <= 227 * 1024, "ring does not fit");
 
@@ -234,6 +236,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     } else if (warp >= 8) {
         // ---- epilogue: TMEM -> registers -> HBM; warp q owns TMEM lanes 32q .. 32q+31 = rows of the tile ----
         const int q = warp & 3;
+        const unsigned stage_w = ring + STAGES * STAGE + q * EPI_WARP;
         unsigned tl = 0;
         for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             const unsigned acc = tl & 1;
@@ -242,7 +245,8 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
             mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
             tc_fence_after();
-            float* crow = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * 32 + lane) * p.N + tn * BN;
+            float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * 32) * p.N + tn * BN;   // this warp's 32 rows
+            float* crow = cblk + (size_t)lane * p.N;
             if (*(volatile unsigned*)&special_tile[tl & 7] == tl + 1) {
                 // exact sequential fold for this thread's row (multiply, round, add, round; k ascending)
                 const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + q * 32 + lane) * p.K;
@@ -270,10 +274,21 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                              : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                // a thread holds 32 columns of ONE row: transpose the warp's 32 x 32 block through shared memory so
+                // that every store instruction writes four full 128-byte row segments instead of 32 half sectors
+                __syncwarp();
                 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint4 v{r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]};
-                    st_global_stream16(crow + cc * 32 + j * 4, v);
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(stage_w + lane * EPI_PITCH + j * 16),
+                                 "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+                __syncwarp();
+                #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3), c4 = lane & 7;
+                    uint4 v;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                 : "r"(stage_w + rr * EPI_PITCH + c4 * 16));
+                    st_global_stream16(cblk + (size_t)rr * p.N + cc * 32 + c4 * 4, v);
                 }
             }
             tc_fence_before();
