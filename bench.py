@@ -71,6 +71,10 @@ WORKLOADS = {
                                  desc="16Mi 4x4 Float items, AoS (wire order) -> SoA device layout"),
     "relayout_3x3_f64_soa_4M": dict(op="relayout", dtype="f64", dims=(3, 3), batch=1 << 22, bytes=144, bound="hbm", layout="soa",
                                     desc="4Mi 3x3 Double items, SoA -> AoS"),
+    "matmul5x5_f64_4M": dict(op="matmul", dtype="f64", m=5, k=5, n=5, batch=1 << 22, bytes=600, bound="hbm",
+                             desc="4Mi 5x5 Double .*. (odd tiny shape, tile pipeline)"),
+    "matmul5x5_f32_4M": dict(op="matmul", dtype="f32", m=5, k=5, n=5, batch=1 << 22, bytes=300, bound="hbm",
+                             desc="4Mi 5x5 Float .*. (odd tiny shape, tile pipeline)"),
     "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="hbm",
                               desc="64Ki 128x128 Float .*. on tcgen05 tensor cores (3xTF32 split, TMEM accumulators; 21 flop/B: HBM-bound)"),
     "matmul96_f32_64K": dict(op="matmul", dtype="f32", m=96, k=96, n=96, batch=1 << 16, bytes=110592, flops=1769472, bound="fp32",

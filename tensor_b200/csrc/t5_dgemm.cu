@@ -12,7 +12,7 @@
 // |delta| <= 1e-12 * sum_j |a_ij||b_jk|, the tolerance north_star states for Double.
 // History (numbers in DESIGN.md §5.9): a cp.async ring issued by the DMMA warps with a CTA barrier
 // per K chunk kept the DMMA pipe 74 % busy (9.49 ms for 64Ki x 128^3); this kernel 96 % (7.73 ms).
-#include <cuda.h>
+#include "t5_async.cuh"
 #include "t5_device.cuh"
 #include "t5_internal.h"
 
@@ -68,31 +68,6 @@ struct Args {
     unsigned long long count;
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Spins on try_wait; a ring that never fills (bad tensor map) traps instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done = 0;
-    for (unsigned spins = 0; !done; ++spins) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.b32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spins > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 __device__ __forceinline__ double lds_f64(unsigned addr) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
@@ -120,8 +95,7 @@ dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             mbar_init(bar0 + 8 * s, 1);                                 // full: the producer's expect_tx arrive
             mbar_init(bar0 + 8 * (STAGES + s), CONSUMER_WARPS);         // empty: one arrive per DMMA warp
         }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
 
@@ -204,25 +178,9 @@ dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            f = nullptr;
-        return (EncodeTiledFn)f;
-    }();
-    return fn;
-}
-
 // rows x cols doubles, row-major, viewed as {8, rows, cols/8}; box {8, box_rows, box_grp}
 static bool make_map(CUtensorMap* map, const void* base, unsigned long long rows, int cols, int box_rows, int box_grp) {
-    EncodeTiledFn enc = encode_fn();
+    TensorMapEncodeFn enc = tensor_map_encoder();
     if (!enc) return false;
     const cuuint64_t dims[3] = {8, rows, (cuuint64_t)(cols / 8)};
     const cuuint64_t strides[2] = {(cuuint64_t)cols * 8, 64};

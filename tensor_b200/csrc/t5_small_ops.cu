@@ -84,6 +84,9 @@ template <class Op> struct Geo {
                  std::conditional_t<(in_bytes <= 64), G<256, 1, 2>,
                  std::conditional_t<(in_bytes <= 160), G<128, 2, 2>, G<128, 2, 2>>>>;
 };
+template <class T> struct Geo<MatmulOp<T, 5, 5, 5>> { using type = G<128, 1, 2>; };
+template <class T> struct Geo<MatmulOp<T, 6, 6, 6>> { using type = G<128, 1, 2>; };
+template <class T> struct Geo<MatmulOp<T, 7, 7, 7>> { using type = G<128, 1, 2>; };
 template <class T> struct Geo<DetOp<T, 3>> { using type = G<256, 1, 2>; };
 template <class T> struct Geo<DetOp<T, 4>> { using type = G<128, 1, 2, 6>; };
 template <class T> struct Geo<InverseOp<T, 2>> { using type = G<128, 1, 2>; };
@@ -109,6 +112,8 @@ static int matmul_t(const Shard& s, int m, int k, int n, const void* A, const vo
     T5_MM(2, 2, 1) T5_MM(3, 3, 1) T5_MM(4, 4, 1)
     T5_MM(1, 2, 2) T5_MM(1, 3, 3) T5_MM(1, 4, 4)
     T5_MM(1, 2, 1) T5_MM(1, 3, 1) T5_MM(1, 4, 1)
+    T5_MM(5, 5, 5)                                             // 75 elements in registers: fine for every type
+    if constexpr (sizeof(T) == 4) { T5_MM(6, 6, 6) T5_MM(7, 7, 7) }   // 8-byte 6x6 is the row-per-thread kernel's
 #undef T5_MM
     return T5I_NOT_SPECIALISED;
 }

@@ -22,7 +22,7 @@
 //
 // The hardware reads the FP32 bit patterns of the "hi" tiles and ignores the 13 low mantissa bits,
 // so the raw operands serve as a_hi / b_hi and only the lo tiles are computed.
-#include <cuda.h>
+#include "t5_async.cuh"
 #include "t5_device.cuh"
 #include "t5_internal.h"
 
@@ -49,34 +49,6 @@ struct Args {
     unsigned long long count;
 };
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done = 0;
-    for (unsigned spins = 0; !done; ++spins) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.b32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spins > (1u << 24)) __trap();       // a ring that never fills traps instead of hanging the device
-    }
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(unsigned bar) {
@@ -143,8 +115,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 4);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_init_fence();
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
@@ -304,24 +275,8 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = [] {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            f = nullptr;
-        return (EncodeTiledFn)f;
-    }();
-    return fn;
-}
-
 static int launch(const Shard& s, int m, int k, int n, const float* A, const float* B, float* C, int sms) {
-    EncodeTiledFn enc = encode_fn();
+    TensorMapEncodeFn enc = tensor_map_encoder();
     if (!enc) return T5I_CUDA;
     const size_t per = (size_t)0x7fffffff / (size_t)(m > k ? m : k);      // TMA coordinates are int32
     for (size_t off = 0; off < s.count; off += per) {

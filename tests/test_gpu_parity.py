@@ -42,11 +42,13 @@ def inputs(dc, op_id, batch, da, db=None):
 
 # ---- matmul (.*.) ----------------------------------------------------------------
 @pytest.mark.parametrize("dc", ALL)
-@pytest.mark.parametrize("mkn", [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (2, 5, 3), (7, 2, 6), (1, 9, 1), (8, 8, 8)])
+@pytest.mark.parametrize("mkn", [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (2, 5, 3), (7, 2, 6), (1, 9, 1), (8, 8, 8),
+                                 (5, 5, 5), (6, 6, 6), (7, 7, 7)])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_matmul_bit_exact(ctx, dc, mkn, layout):
     m, k, n = mkn
-    specialised = mkn in [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4)]
+    specialised = mkn in [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (5, 5, 5)] or \
+        (dc == oracle.F32 and mkn in [(6, 6, 6), (7, 7, 7)])
     for batch in (1, 257, 4099):
         a, b = inputs(dc, 1, batch, m * k, k * n)
         A = ctx.from_numpy(a, (m, k), layout)

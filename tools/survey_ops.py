@@ -73,10 +73,12 @@ def main():
             add(f"solve 6x6 {tag}", (B // 4) * 48 * es, lambda: tb.solve(A6, b6))
             add(f"det 8x8 {tag}", (B // 4) * 65 * es, lambda: tb.det(A8))
             add(f"inverse 8x8 {tag}", (B // 4) * 128 * es, lambda: tb.inverse(A8))
-            add(f"matmul 5x5 {tag}", B * 75 * es, lambda: tb.matmul(ctx.synthetic((5, 5), dt, B, SEED, 7), ctx.synthetic((5, 5), dt, B, SEED, 8)))
+            A5, B5 = ctx.synthetic((5, 5), dt, B, SEED, 7), ctx.synthetic((5, 5), dt, B, SEED, 8)
+            add(f"matmul 5x5 {tag}", B * 75 * es, lambda: tb.matmul(A5, B5))
             add(f"matmul 4x4 (Double/Float) {tag}", B * 48 * es, lambda: tb.matmul(A4, B4))
-            add(f"matmul 32x32 {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(ctx.synthetic((32, 32), dt, B // 64, SEED, 9), ctx.synthetic((32, 32), dt, B // 64, SEED, 10)))
-            for x in (A3, A4, B4, v3, A6, b6, A8, T234):
+            A32, B32 = ctx.synthetic((32, 32), dt, B // 64, SEED, 9), ctx.synthetic((32, 32), dt, B // 64, SEED, 10)
+            add(f"matmul 32x32 {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(A32, B32))
+            for x in (A3, A4, B4, v3, A6, b6, A8, T234, A5, B5, A32, B32):
                 x.free()
 
 
