@@ -103,7 +103,13 @@ int t5_buf_layout(const t5_buf* buf);
 /* MatrixProduct (.*.): C[i,c] = fold_{j ascending} (acc + A[i,j]*B[j,c]), acc0 = 0,
  * multiply then add, never fused.  A is m x k, B is k x n, C is m x n.  n == 1 is
  * matrix . vector, m == 1 vector . matrix.  Int64 wraps.  (Absent from the
- * reference checkout — CHANGELOG.md:24-25; specified in SURVEY.md §8a a6.) */
+ * reference checkout — CHANGELOG.md:24-25; specified in SURVEY.md §8a a6.)
+ * Results are bit-identical to that fold for every element type and shape, with two
+ * exceptions that run on the tensor cores and meet the stated tolerance instead
+ * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|): Double with m, n multiples of 64 and k a
+ * multiple of 32 (FP64 DMMA, tol 1e-12), Float with m, n multiples of 128 and k a
+ * multiple of 32 (tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with
+ * the exact fold).  AoS only; the same shapes in SoA are T5_ERR_UNSUPPORTED. */
 int t5_matmul(t5_ctx* ctx, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C);
 
 /* DotProduct (dot): OUT[b] = fold_{i ascending} (acc + X[b,i]*Y[b,i]).  §8a a7. */
