@@ -75,6 +75,8 @@ WORKLOADS = {
                              desc="4Mi 5x5 Double .*. (odd tiny shape, tile pipeline)"),
     "matmul5x5_f32_4M": dict(op="matmul", dtype="f32", m=5, k=5, n=5, batch=1 << 22, bytes=300, bound="hbm",
                              desc="4Mi 5x5 Float .*. (odd tiny shape, tile pipeline)"),
+    "inverse8_f64_1M": dict(op="inverse", dtype="f64", n=8, batch=1 << 20, bytes=1025, bound="hbm",
+                            desc="1Mi 8x8 Double inverse (row-per-lane elimination, warp shuffles)"),
     "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="hbm",
                               desc="64Ki 128x128 Float .*. on tcgen05 tensor cores (3xTF32 split, TMEM accumulators; 21 flop/B: HBM-bound)"),
     "matmul96_f32_64K": dict(op="matmul", dtype="f32", m=96, k=96, n=96, batch=1 << 16, bytes=110592, flops=1769472, bound="fp32",
