@@ -1,0 +1,152 @@
+"""Property tests in the style of the reference's QuickCheck suites (tests/Tensor.hs:25-80,
+tests/MultiIndex.hs), restated with hypothesis over RANDOM shapes:
+
+* CPU: the library's own host-side index-map builder (t5_structural_table, a pure C function of
+  libt5b200.so) against the GADT-backend restatement for append/split, at/ta, slice, rev/unRev -
+  the same equalities the reference checks, but on shapes hypothesis chooses;
+* GPU (marked): the same round trips and the linear-algebra metamorphic identities through the C ABI
+  on random small shapes, every result compared with the oracle bit for bit."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import oracle
+from oracle import gadt_model as G
+from oracle import structural as S
+from tensor_b200 import _lib
+
+dims_st = st.lists(st.integers(1, 4), min_size=1, max_size=4)
+CPU = settings(max_examples=60, deadline=None)
+GPU = settings(max_examples=20, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+def flat(dims, start=0):
+    return list(range(start, start + S.product(dims)))
+
+
+# ---- CPU: product host logic vs the GADT model --------------------------------------------------
+@CPU
+@given(dims_st, st.data())
+def test_split_of_append_is_identity_on_library_tables(dims, data):
+    """split sh (append sh x y) == (x, y)   (tests/Tensor.hs:25-29), any rank, any axis."""
+    axis = data.draw(st.integers(1, len(dims)))
+    other = data.draw(st.integers(1, 4))
+    e = list(dims)
+    e[axis - 1] = other
+    x, y = flat(dims), flat(e, 10_000)
+    table = _lib.structural_table(_lib.ST_APPEND, dims, [axis] + e)
+    dA = len(x)
+    joined = [x[t] if t < dA else y[t - dA] for t in table]
+    want = G.append(axis, G.from_list(dims, x), G.from_list(e, y))
+    assert G.to_list(want) == joined
+    out_dims = list(dims)
+    out_dims[axis - 1] += other
+    t1 = _lib.structural_table(_lib.ST_SPLIT_FIRST, out_dims, [axis, dims[axis - 1]])
+    t2 = _lib.structural_table(_lib.ST_SPLIT_SECOND, out_dims, [axis, dims[axis - 1]])
+    assert [joined[i] for i in t1] == x and [joined[i] for i in t2] == y
+
+
+@CPU
+@given(dims_st, st.data())
+def test_slice_at_ta_on_library_tables(dims, data):
+    x = flat(dims)
+    t = G.from_list(dims, x)
+    sl = [data.draw(st.one_of(st.none(), st.integers(1, d))) for d in dims]
+    table = _lib.structural_table(_lib.ST_SLICE, dims, [0 if s is None else s for s in sl])
+    assert [x[j] for j in table] == G.to_list(G.slice_(t, sl))
+    # slice x (allCons .. nilS) == x   (tests/Tensor.hs:36-40)
+    assert _lib.structural_table(_lib.ST_SLICE, dims, [0] * len(dims)) == list(range(len(x)))
+    i = data.draw(st.integers(1, dims[0]))
+    assert [x[j] for j in _lib.structural_table(_lib.ST_TA, dims, [i])] == G.to_list(G.ta(i, t))
+    if len(dims) > 1:
+        ix = [data.draw(st.integers(1, d)) for d in dims[1:]]
+        assert [x[j] for j in _lib.structural_table(_lib.ST_AT, dims, ix)] == G.to_list(G.at(t, ix))
+
+
+@CPU
+@given(st.lists(st.integers(1, 3), min_size=0, max_size=3), st.lists(st.integers(1, 3), min_size=0, max_size=3))
+def test_rev_unrev_are_axis_permutations(outer, inner):
+    """rev / unRev of nested tensors (tests/Tensor.hs:42-80) as permutations of the flat [outer][inner] layout,
+    and unRev . rev == id."""
+    dims = list(outer) + list(inner)
+    if not dims:
+        return
+    r, n = len(outer), len(dims)
+    rev_perm = list(reversed(range(r))) + list(range(r, n))
+    assert _lib.structural_table(_lib.ST_PERMUTE, dims, rev_perm) == S.rev_table(outer, inner)[1]
+    rev_dims = [dims[p] for p in rev_perm]
+    back = _lib.structural_table(_lib.ST_PERMUTE, rev_dims, rev_perm)       # reversing the outer axes twice
+    fwd = _lib.structural_table(_lib.ST_PERMUTE, dims, rev_perm)
+    assert [fwd[j] for j in back] == list(range(S.product(dims)))
+    # transpose == full reversal == transposeV (Vector.hs:306-307), and it is an involution
+    tr = _lib.structural_table(_lib.ST_PERMUTE, dims, list(reversed(range(n))))
+    assert tr == [S.transposeV(dims, i) for i in range(S.product(dims))]
+    tr_back = _lib.structural_table(_lib.ST_PERMUTE, list(reversed(dims)), list(reversed(range(n))))
+    assert [tr[j] for j in tr_back] == list(range(S.product(dims)))
+
+
+@CPU
+@given(st.integers(1, 6), st.integers(1, 6), st.integers(1, 6), st.integers(0, 2 ** 32 - 1))
+def test_oracle_product_identities(m, k, n, seed):
+    """(A.B)^T == B^T.A^T exactly for Int64 (wrapping) AND for Double (same products, same order); A.I == A."""
+    rng = np.random.default_rng(seed)
+    for dc, mk in ((oracle.I64, lambda s: rng.integers(-2 ** 62, 2 ** 62, s, dtype=np.int64)),
+                   (oracle.F64, lambda s: rng.standard_normal(s))):
+        a, b = mk(3 * m * k), mk(3 * k * n)
+        ab_t = oracle.transpose(oracle.matmul(a, b, m, k, n), [m, n])
+        bt_at = oracle.matmul(oracle.transpose(b, [k, n]), oracle.transpose(a, [m, k]), n, k, m)
+        assert np.array_equal(ab_t.ravel().view(np.uint64), bt_at.ravel().view(np.uint64))
+        eye = np.broadcast_to(np.eye(k, dtype=a.dtype), (3, k, k)).copy()
+        assert np.array_equal(oracle.matmul(a, eye, m, k, k).ravel().view(np.uint64), np.asarray(a).view(np.uint64))
+
+
+# ---- GPU: the same properties through the C ABI ---------------------------------------------------
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    import tensor_b200 as tb
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    c = tb.Context([0])
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@GPU
+@given(st.integers(1, 9), st.integers(1, 9), st.integers(1, 9), st.sampled_from([oracle.F64, oracle.F32, oracle.I64]),
+       st.integers(1, 700), st.integers(0, 2 ** 16))
+def test_gpu_matmul_random_shapes_bit_exact(ctx, m, k, n, dc, batch, op_id):
+    import tensor_b200 as tb
+    a = oracle.fill(dc, oracle.SEED_A, op_id, batch * m * k)
+    b = oracle.fill(dc, oracle.SEED_B, op_id, batch * k * n)
+    A, B = ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))
+    C = tb.matmul(A, B).to_numpy()
+    want = oracle.matmul(a, b, m, k, n)
+    assert np.array_equal(np.ascontiguousarray(C).view(np.uint8), np.ascontiguousarray(want).view(np.uint8))
+    # (A.B)^T == B^T.A^T, computed entirely on the device, bit for bit
+    lhs = tb.transpose(tb.matmul(A, B)).to_numpy()
+    rhs = tb.matmul(tb.transpose(B), tb.transpose(A)).to_numpy()
+    assert np.array_equal(lhs.view(np.uint8), rhs.view(np.uint8))
+
+
+@pytest.mark.gpu
+@GPU
+@given(dims_st, st.data())
+def test_gpu_split_of_append_and_transpose_involution(ctx, dims, data):
+    import tensor_b200 as tb
+    from tensor_b200 import structure as T
+    axis = data.draw(st.integers(1, len(dims)))
+    e = list(dims)
+    e[axis - 1] = data.draw(st.integers(1, 4))
+    batch = data.draw(st.integers(1, 300))
+    x = oracle.fill(oracle.I64, oracle.SEED_A, 31, batch * S.product(dims))
+    y = oracle.fill(oracle.I64, oracle.SEED_B, 31, batch * S.product(e))
+    X, Y = ctx.from_numpy(x, tuple(dims)), ctx.from_numpy(y, tuple(e))
+    Z = T.append(axis, X, Y)
+    X2, Y2 = T.split(axis, dims[axis - 1], Z)
+    assert np.array_equal(X2.to_numpy().ravel(), x) and np.array_equal(Y2.to_numpy().ravel(), y)
+    assert np.array_equal(tb.transpose(tb.transpose(Z)).to_numpy(), Z.to_numpy())
+    assert np.array_equal(tb.transpose(X).to_numpy().reshape(batch, -1),
+                          oracle.transpose(x, list(dims)).reshape(batch, -1))
