@@ -107,3 +107,16 @@ def test_host_entry_large_items_dmma(ctx):
     want = np.einsum("bij,bjk->bik", A, B)
     bound = np.einsum("bij,bjk->bik", np.abs(A), np.abs(B))
     assert np.all(np.abs(got - want) <= 1e-12 * bound)
+
+
+def test_host_entry_large_items_tcgen05(ctx):
+    # 128x128 Float through the host pipeline: the tcgen05 3xTF32 kernel per chunk, a fresh pair of TMA
+    # tensor maps per launch; 700 items = several chunks over the three slots
+    batch = 700
+    a = oracle.fill(oracle.F32, oracle.SEED_A, 26, batch * 128 * 128)
+    b = oracle.fill(oracle.F32, oracle.SEED_B, 26, batch * 128 * 128)
+    got = host.matmul(ctx, a, b, 128, 128, 128).astype(np.float64)
+    A, B = a.reshape(batch, 128, 128).astype(np.float64), b.reshape(batch, 128, 128).astype(np.float64)
+    want = np.einsum("bij,bjk->bik", A, B)
+    bound = np.einsum("bij,bjk->bik", np.abs(A), np.abs(B))
+    assert np.all(np.abs(got.reshape(want.shape) - want) <= 1e-5 * bound)
