@@ -79,6 +79,8 @@ WORKLOADS = {
                             desc="1Mi 8x8 Double inverse (row-per-lane elimination, warp shuffles)"),
     "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="hbm",
                               desc="64Ki 128x128 Float .*. on tcgen05 tensor cores (3xTF32 split, TMEM accumulators; 21 flop/B: HBM-bound)"),
+    "matmul64_f32_256K": dict(op="matmul", dtype="f32", m=64, k=64, n=64, batch=1 << 18, bytes=49152, flops=524288, bound="hbm",
+                              desc="256Ki 64x64 Float .*. on tcgen05 tensor cores (3xTF32, UMMA M = N = 64; 10.7 flop/B: HBM-bound)"),
     "matmul96_f32_64K": dict(op="matmul", dtype="f32", m=96, k=96, n=96, batch=1 << 16, bytes=110592, flops=1769472, bound="fp32",
                              desc="64Ki 96x96 Float .*. (off the tensor-core tile grid: exact blocked SIMT product, unfused multiply+add)"),
     "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
@@ -542,7 +544,7 @@ def ours(args):
     # ---- the other BASELINE configs (explanatory; not the headline) ----------------------------------
     others = {}
     if args.all and world == 1:
-        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K", "matmul128_f32_64K", "matmul96_f32_64K"] if args.big else []):
+        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K", "matmul128_f32_64K", "matmul64_f32_256K", "matmul96_f32_64K"] if args.big else []):
             ww = WORKLOADS[name]
             try:
                 st = StepRing(ctx, tb, ww)

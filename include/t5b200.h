@@ -107,7 +107,7 @@ int t5_buf_layout(const t5_buf* buf);
  * Results are bit-identical to that fold for every element type and shape, with two
  * exceptions that run on the tensor cores and meet the stated tolerance instead
  * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|): Double with m, n multiples of 64 and k a
- * multiple of 32 (FP64 DMMA, tol 1e-12), Float with m, n multiples of 128 and k a
+ * multiple of 32 (FP64 DMMA, tol 1e-12), Float with m, n multiples of 64 and k a
  * multiple of 32 (tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with
  * the exact fold).  AoS only; the same shapes in SoA are T5_ERR_UNSUPPORTED. */
 int t5_matmul(t5_ctx* ctx, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C);

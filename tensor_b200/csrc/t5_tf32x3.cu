@@ -29,15 +29,27 @@
 namespace t5 {
 namespace tf {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int BK = 32;
 constexpr int THREADS = 384;
-constexpr int TILE_A = BM * BK * 4, TILE_B = BK * BN * 4;            // 16 KB each
-constexpr int STAGE = 2 * (TILE_A + TILE_B);                        // hi + lo tiles: 64 KB
 constexpr int EPI_PITCH = 36 * 4;                                   // staging row pitch: 32 floats + 16 B (conflict-free v4 access)
-constexpr int EPI_WARP = 32 * EPI_PITCH;                            // one 32 x 32 block per epilogue warp
-constexpr int SMEM = STAGES * STAGE + 1024 + 4 * EPI_WARP;
-constexpr int TMEM_COLS = 256;                                      // two 128-column FP32 accumulators
-static_assert(SMEM <= 227 * 1024, "ring does not fit");
+constexpr int EPI_WARP = 32 * EPI_PITCH;                            // one (<= 32) x 32 block per epilogue warp
+
+// Square tiles of 128 (3 stages of 64 KB) or 64 (6 stages of 16 KB) - the UMMA shapes M = N = 128 / 64.
+template <int TILE_, int STAGES_>
+struct Geo {
+    static constexpr int BM = TILE_, BN = TILE_, STAGES = STAGES_;
+    static constexpr int TILE_A = BM * BK * 4, TILE_B = BK * BN * 4;
+    static constexpr int STAGE = 2 * (TILE_A + TILE_B);             // hi + lo tiles
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 4 * EPI_WARP;
+    static constexpr int TMEM_COLS = 2 * BN;                        // two FP32 accumulators (power of two >= 32)
+    static constexpr int ROWS_PER_WARP = BM / 4;                    // M = 64 keeps 16 rows in lanes 0-15 of every 32-lane quarter
+    // Instruction descriptor: D = F32, A = B = TF32, A K-major, B MN-major, N, M.
+    static constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+                                      ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+    static_assert(SMEM <= 227 * 1024, "ring does not fit");
+};
+using Geo128 = Geo<128, 3>;
+using Geo64 = Geo<64, 6>;
 
 constexpr float FLT_MAX_F = 3.4028234664e38f;
 
@@ -71,9 +83,6 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsi
     return (unsigned long long)((smem_addr >> 4) & 0x3fffu) | ((unsigned long long)(lbo16 & 0x3fffu) << 16) |
            ((unsigned long long)(sbo16 & 0x3fffu) << 32) | (1ull << 46) | ((unsigned long long)layout << 61);
 }
-// Instruction descriptor: D = F32, A = B = TF32, A K-major, B MN-major, N = 128, M = 128.
-constexpr unsigned IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((unsigned)(BN >> 3) << 17) |
-                           ((unsigned)(BM >> 4) << 24);
 
 __device__ __forceinline__ float lo_part(float x) {
     const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
@@ -81,8 +90,12 @@ __device__ __forceinline__ float lo_part(float x) {
     return (fabsf(x) <= 3.4028234664e38f) ? lo : 0.0f;         // inf / nan: such tiles are recomputed exactly (see special_tile)
 }
 
+template <class G>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args p) {
+    constexpr int BM = G::BM, BN = G::BN, STAGES = G::STAGES, TILE_A = G::TILE_A, TILE_B = G::TILE_B, STAGE = G::STAGE;
+    constexpr int TMEM_COLS = G::TMEM_COLS, RPW = G::ROWS_PER_WARP;
+    constexpr unsigned IDESC = G::IDESC;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * STAGES + 4];   // full, conv, empty, tmem_full[2], tmem_empty[2]
     __shared__ unsigned tmem_base_smem;
@@ -216,13 +229,13 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
             mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
             tc_fence_after();
-            float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * 32) * p.N + tn * BN;   // this warp's 32 rows
+            float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * RPW) * p.N + tn * BN;   // this warp's rows
             float* crow = cblk + (size_t)lane * p.N;
             if (*(volatile unsigned*)&special_tile[tl & 7] == tl + 1) {
                 // exact sequential fold for this thread's row (multiply, round, add, round; k ascending)
-                const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + q * 32 + lane) * p.K;
+                const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + q * RPW + lane) * p.K;
                 const float* bcol = p.B + item * (size_t)p.K * p.N + tn * BN;
-                for (int j = 0; j < BN; ++j) {
+                for (int j = 0; j < BN && lane < RPW; ++j) {
                     float acc_x = 0.0f;
                     for (int kk = 0; kk < p.K; ++kk) acc_x = __fadd_rn(acc_x, __fmul_rn(__ldg(arow + kk), __ldg(bcol + (size_t)kk * p.N + j)));
                     crow[j] = acc_x;
@@ -254,7 +267,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                                  "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
                 __syncwarp();
                 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < RPW / 4; ++i) {
                     const int rr = i * 4 + (lane >> 3), c4 = lane & 7;
                     uint4 v;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
@@ -275,7 +288,9 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
 }
 
+template <class G>
 static int launch(const Shard& s, int m, int k, int n, const float* A, const float* B, float* C, int sms) {
+    constexpr int BM = G::BM, BN = G::BN;
     TensorMapEncodeFn enc = tensor_map_encoder();
     if (!enc) return T5I_CUDA;
     const size_t per = (size_t)0x7fffffff / (size_t)(m > k ? m : k);      // TMA coordinates are int32
@@ -301,7 +316,7 @@ static int launch(const Shard& s, int m, int k, int n, const float* A, const flo
         const unsigned long long tiles = (unsigned long long)cnt * (m / BM) * (n / BN);
         const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
         Args a{A + off * (size_t)m * k, B + off * (size_t)k * n, C + off * (size_t)m * n, m, n, k, (unsigned long long)cnt};
-        tf32x3_kernel<<<grid, THREADS, SMEM, s.stream>>>(ma, mb, a);
+        tf32x3_kernel<G><<<grid, THREADS, G::SMEM, s.stream>>>(ma, mb, a);
         if (cudaGetLastError() != cudaSuccess) return T5I_CUDA;
     }
     return T5I_OK;
@@ -311,19 +326,22 @@ static int launch(const Shard& s, int m, int k, int n, const float* A, const flo
 
 int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    if (m % tf::BM || n % tf::BN || k % tf::BK || k < tf::BK) return T5I_NOT_SPECIALISED;
+    if (m % 64 || n % 64 || k % tf::BK || k < tf::BK) return T5I_NOT_SPECIALISED;
+    const bool big = m % 128 == 0 && n % 128 == 0;
     static bool configured[T5_MAX_DEVICES] = {false};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
     if (!configured[dev]) {
-        if (cudaFuncSetAttribute(tf::tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::SMEM) != cudaSuccess) return T5I_CUDA;
+        if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo128::SMEM) != cudaSuccess) return T5I_CUDA;
+        if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo64::SMEM) != cudaSuccess) return T5I_CUDA;
         configured[dev] = true;
     }
     if (s.count == 0) return T5I_OK;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
-    return tf::launch(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
+    return big ? tf::launch<tf::Geo128>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms)
+               : tf::launch<tf::Geo64>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
 }
 
 }  // namespace t5

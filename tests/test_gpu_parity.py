@@ -552,8 +552,8 @@ def test_mid_size_matmul_generic_is_bit_exact(ctx):
             batch = 9
             a, b = inputs(dc, 16, batch, m * k, k * n)
             C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
-            if dc == oracle.F64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
-                continue        # Double 64-multiples take the tensor-core path (tolerance test above)
+            if dc != oracle.I64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
+                continue        # Double / Float 64-multiples take the tensor-core paths (tolerance tests)
             assert_bits_equal(C, oracle.matmul(a, b, m, k, n), f"generic {m}x{k}x{n}")
 
 
@@ -565,8 +565,8 @@ def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
     m, k, n = mkn
     if dc == oracle.F64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
         pytest.skip("Double 64-multiples take the tensor-core path")
-    if dc == oracle.F32 and m % 128 == 0 and n % 128 == 0 and k % 32 == 0:
-        pytest.skip("Float 128-multiples take the tcgen05 3xTF32 path (tolerance test below)")
+    if dc == oracle.F32 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
+        pytest.skip("Float 64-multiples take the tcgen05 3xTF32 path (tolerance test below)")
     for batch in (1, 5, 37):
         a, b = inputs(dc, 21, batch, m * k, k * n)
         C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
@@ -574,7 +574,8 @@ def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
 
 
 # ---- Float on tcgen05 (3xTF32, TMEM accumulators): tolerance stated by north_star for Float ----
-@pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 32, 128), (256, 64, 128), (128, 96, 256), (256, 160, 256)])
+@pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 32, 128), (256, 64, 128), (128, 96, 256), (256, 160, 256),
+                                 (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64)])
 def test_tf32x3_matmul_within_tolerance(ctx, mkn):
     m, k, n = mkn
     for batch in (1, 7, 150, 301):          # > 148 tiles: every CTA works, some take several tiles (both TMEM accumulators)
@@ -590,8 +591,9 @@ def test_tf32x3_matmul_within_tolerance(ctx, mkn):
         assert np.max(err / bound) < 0.5
 
 
-def test_tf32x3_identity_and_specials(ctx):
-    batch, n = 5, 128
+@pytest.mark.parametrize("n", [128, 64])
+def test_tf32x3_identity_and_specials(ctx, n):
+    batch = 5
     a, _ = inputs(oracle.F32, 23, batch, n * n)
     eye = np.broadcast_to(np.eye(n, dtype=np.float32), (batch, n, n)).copy()
     A = ctx.from_numpy(a, (n, n))
