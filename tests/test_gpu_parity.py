@@ -530,6 +530,27 @@ def test_full_size_config5_properties(ctx):
     assert np.all(np.isfinite(c))
 
 
+def test_full_size_float128_tcgen05_properties(ctx):
+    """64Ki 128x128 Float on the tcgen05 tensor cores at the size of BASELINE configs[4] (443 tiles per CTA, both
+    TMEM accumulators and every ring phase many times over): a strided sample against float64."""
+    batch, n = 1 << 16, 128
+    A = ctx.synthetic((n, n), np.float32, batch, oracle.SEED_A, 6)
+    B = ctx.synthetic((n, n), np.float32, batch, oracle.SEED_B, 6)
+    C = A @ B
+    ctx.sync()
+    c = np.ascontiguousarray(C.to_numpy()[:: 1021]).astype(np.float64)
+    a = np.ascontiguousarray(A.to_numpy()[:: 1021]).astype(np.float64)
+    b = np.ascontiguousarray(B.to_numpy()[:: 1021]).astype(np.float64)
+    want = np.einsum("bij,bjk->bik", a, b)
+    bound = 1e-5 * np.einsum("bij,bjk->bik", np.abs(a), np.abs(b))
+    assert np.all(np.abs(c - want) <= bound)
+    # the very last items too (tail of the persistent loop)
+    tail = slice(batch - 3, batch)
+    ct = C.to_numpy()[tail].astype(np.float64)
+    at, bt = A.to_numpy()[tail].astype(np.float64), B.to_numpy()[tail].astype(np.float64)
+    assert np.all(np.abs(ct - np.einsum("bij,bjk->bik", at, bt)) <= 1e-5 * np.einsum("bij,bjk->bik", np.abs(at), np.abs(bt)))
+
+
 # ---- FP64 tensor-core (DMMA) product: tolerance stated by north_star -------------------
 @pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 64, 128), (256, 32, 128), (128, 96, 256),
                                  (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64)])
