@@ -10,6 +10,9 @@
 //   auto t  = tensor_product(a, b);     // (⊗)    : Batch<T,Is...> ⊗ Batch<T,Js...> -> Batch<T,Is...,Js...>
 //   auto at = transpose(a);             // transpose = unRev . t0 (Indexable.hs:101-102)
 //   auto d  = det(a);  auto [inv, st] = inverse(a);  auto [x, st] = solve(a, b);
+//   auto p  = prod<1>(a, b);            // prod n : contract the last n indices of a with the first n of b
+//   auto z  = append<2>(a, col);        // append / split / at / ta / slice (Vector.hs:277-354, :400-463)
+//   matmul_host<double, 3, 3, 3>(ctx, n, pa, pb, pc);   // ordinary host arrays in and out, one call
 //
 // A shape error is a COMPILE error, as in Haskell; a wrong list length throws
 // WrongListLength (src/Data/Tensor.hs:96-100); an unsupported request throws Unsupported
@@ -19,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -196,6 +200,142 @@ Batch<T, Is...> operator+(const Batch<T, Is...>& a, const Batch<T, Is...>& b) { 
     Batch<T, Is...> c(a.ctx(), a.count());
     a.ctx().check(t5_zip(a.ctx().handle(), dtype_of<T>::value, 0, a.buf(), b.buf(), c.buf()), "t5_zip");
     return c;
+}
+
+template <class T, size_t... Is>
+Batch<T, Is...> operator-(const Batch<T, Is...>& a, const Batch<T, Is...>& b) {   // liftA2 (-)
+    Batch<T, Is...> c(a.ctx(), a.count());
+    a.ctx().check(t5_zip(a.ctx().handle(), dtype_of<T>::value, 1, a.buf(), b.buf(), c.buf()), "t5_zip");
+    return c;
+}
+template <class T, size_t... Is>
+Batch<T, Is...> hadamard(const Batch<T, Is...>& a, const Batch<T, Is...>& b) {    // liftA2 (*)
+    Batch<T, Is...> c(a.ctx(), a.count());
+    a.ctx().check(t5_zip(a.ctx().handle(), dtype_of<T>::value, 2, a.buf(), b.buf(), c.buf()), "t5_zip");
+    return c;
+}
+template <class T, size_t... Is>
+Batch<T, Is...> operator*(T k, const Batch<T, Is...>& a) {                        // fmap (k *)
+    Batch<T, Is...> c(a.ctx(), a.count());
+    a.ctx().check(t5_scale(a.ctx().handle(), dtype_of<T>::value, &k, a.buf(), c.buf()), "t5_scale");
+    return c;
+}
+
+// ---- type-level shape arithmetic for prod n / append / split / at / ta ----------------------
+namespace detail {
+template <class T, class S> struct batch_of;
+template <class T, size_t... Is> struct batch_of<T, Shape<Is...>> { using type = Batch<T, Is...>; };
+template <class A, class B> struct cat;
+template <size_t... Is, size_t... Js> struct cat<Shape<Is...>, Shape<Js...>> { using type = Shape<Is..., Js...>; };
+template <size_t N, class S> struct drop { using type = S; };
+template <size_t N, size_t I, size_t... Is> struct drop<N, Shape<I, Is...>> {
+    using type = std::conditional_t<N == 0, Shape<I, Is...>, typename drop<(N ? N - 1 : 0), Shape<Is...>>::type>;
+};
+template <size_t N, class S> struct take { using type = Shape<>; };
+template <size_t N, size_t I, size_t... Is> struct take<N, Shape<I, Is...>> {
+    using type = std::conditional_t<N == 0, Shape<>, typename cat<Shape<I>, typename take<(N ? N - 1 : 0), Shape<Is...>>::type>::type>;
+};
+template <size_t N, class S> struct nth;
+template <size_t N, size_t I, size_t... Is> struct nth<N, Shape<I, Is...>> {
+    static constexpr size_t value = N == 0 ? I : nth<(N ? N - 1 : 0), Shape<Is..., 0>>::value;   // padded: never read past the end
+};
+template <size_t N> struct nth<N, Shape<>> { static constexpr size_t value = 0; };
+// replace entry AX (0-based) of a shape
+template <size_t AX, size_t V, class S> struct set_axis {
+    using type = typename cat<typename cat<typename take<AX, S>::type, Shape<V>>::type, typename drop<AX + 1, S>::type>::type;
+};
+template <class A, class B> constexpr bool same_shape = std::is_same<A, B>::value;
+}  // namespace detail
+
+// prod n: contract the last NC indices of a with the first NC of b; a mismatch is a compile error
+template <size_t NC, class T, size_t... Is, size_t... Js>
+auto prod(const Batch<T, Is...>& a, const Batch<T, Js...>& b) {
+    using SA = Shape<Is...>; using SB = Shape<Js...>;
+    static_assert(NC <= SA::rank && NC <= SB::rank, "prod n: n exceeds a rank");
+    static_assert(detail::same_shape<typename detail::drop<SA::rank - NC, SA>::type, typename detail::take<NC, SB>::type>,
+                  "prod n: the contracted dimensions differ");
+    using SC = typename detail::cat<typename detail::take<SA::rank - NC, SA>::type, typename detail::drop<NC, SB>::type>::type;
+    typename detail::batch_of<T, SC>::type c(a.ctx(), a.count());
+    auto da = SA::dims(); auto db = SB::dims();
+    a.ctx().check(t5_prod(a.ctx().handle(), dtype_of<T>::value, (int)da.size(), da.data(), (int)db.size(), db.data(), (int)NC,
+                          a.buf(), b.buf(), c.buf()), "t5_prod");
+    return c;
+}
+
+// append n x y / split n t (Vector.hs:322-354); AXIS is 1-based like the reference's SOne, SSucc ..
+template <size_t AXIS, class T, size_t... Is, size_t... Js>
+auto append(const Batch<T, Is...>& x, const Batch<T, Js...>& y) {
+    using SX = Shape<Is...>; using SY = Shape<Js...>;
+    static_assert(SX::rank == SY::rank && AXIS >= 1 && AXIS <= SX::rank, "append: ranks differ or bad axis");
+    constexpr size_t EX = detail::nth<AXIS - 1, SX>::value, EY = detail::nth<AXIS - 1, SY>::value;
+    static_assert(detail::same_shape<typename detail::set_axis<AXIS - 1, 0, SX>::type, typename detail::set_axis<AXIS - 1, 0, SY>::type>,
+                  "append: the other dimensions differ");
+    using SZ = typename detail::set_axis<AXIS - 1, EX + EY, SX>::type;
+    typename detail::batch_of<T, SZ>::type z(x.ctx(), x.count());
+    auto dx = SX::dims(); auto dy = SY::dims();
+    x.ctx().check(t5_append(x.ctx().handle(), dtype_of<T>::value, (int)AXIS, (int)dx.size(), dx.data(), dy.data(), x.buf(), y.buf(), z.buf()), "t5_append");
+    return z;
+}
+template <size_t AXIS, size_t FIRST, class T, size_t... Is>
+auto split(const Batch<T, Is...>& t) {
+    using S = Shape<Is...>;
+    static_assert(AXIS >= 1 && AXIS <= S::rank, "split: bad axis");
+    constexpr size_t E = detail::nth<AXIS - 1, S>::value;
+    static_assert(FIRST >= 1 && FIRST < E, "split: both parts must be non-empty");
+    typename detail::batch_of<T, typename detail::set_axis<AXIS - 1, FIRST, S>::type>::type a(t.ctx(), t.count());
+    typename detail::batch_of<T, typename detail::set_axis<AXIS - 1, E - FIRST, S>::type>::type b(t.ctx(), t.count());
+    auto d = S::dims();
+    t.ctx().check(t5_split(t.ctx().handle(), dtype_of<T>::value, (int)AXIS, (int)d.size(), d.data(), FIRST, t.buf(), a.buf(), b.buf()), "t5_split");
+    return std::make_pair(a, b);
+}
+// [i] `ta` t: fix the first index (1-based); t `at` ix: fix every index but the first
+template <class T, size_t I, size_t... Is>
+Batch<T, Is...> ta(size_t i, const Batch<T, I, Is...>& t) {
+    Batch<T, Is...> o(t.ctx(), t.count());
+    auto d = Shape<I, Is...>::dims();
+    t.ctx().check(t5_ta(t.ctx().handle(), dtype_of<T>::value, (int)d.size(), d.data(), i, t.buf(), o.buf()), "t5_ta");
+    return o;
+}
+template <class T, size_t I, size_t... Is>
+Batch<T, I> at(const Batch<T, I, Is...>& t, const std::vector<uint64_t>& ix) {
+    if (ix.size() != sizeof...(Is)) throw WrongListLength();
+    Batch<T, I> o(t.ctx(), t.count());
+    auto d = Shape<I, Is...>::dims();
+    t.ctx().check(t5_at(t.ctx().handle(), dtype_of<T>::value, (int)d.size(), d.data(), ix.data(), t.buf(), o.buf()), "t5_at");
+    return o;
+}
+// slice t sl: slicer entry 0 keeps an axis (Nothing), k > 0 fixes it (Just k); the result shape is given explicitly
+// and checked by the library (WrongListLength on a mismatch)
+template <size_t... Os, class T, size_t... Is>
+Batch<T, Os...> slice(const Batch<T, Is...>& t, const std::vector<uint64_t>& slicer) {
+    if (slicer.size() != sizeof...(Is)) throw WrongListLength();
+    Batch<T, Os...> o(t.ctx(), t.count());
+    auto d = Shape<Is...>::dims();
+    t.ctx().check(t5_slice(t.ctx().handle(), dtype_of<T>::value, (int)d.size(), d.data(), slicer.data(), t.buf(), o.buf()), "t5_slice");
+    return o;
+}
+
+// ---- ordinary host arrays in and out: one call per operation (the end-to-end entries) -------------
+template <class T, size_t I, size_t J, size_t K>
+void matmul_host(const Context& ctx, size_t count, const T* a, const T* b, T* c) {
+    ctx.check(t5_matmul_host(ctx.handle(), dtype_of<T>::value, (int)I, (int)J, (int)K, count, a, b, c), "t5_matmul_host");
+}
+template <class T, size_t N>
+void det_host(const Context& ctx, size_t count, const T* a, T* out) {
+    ctx.check(t5_det_host(ctx.handle(), dtype_of<T>::value, (int)N, count, a, out), "t5_det_host");
+}
+template <class T, size_t N>
+void inverse_host(const Context& ctx, size_t count, const T* a, T* out, uint8_t* status) {
+    ctx.check(t5_inverse_host(ctx.handle(), dtype_of<T>::value, (int)N, count, a, out, status), "t5_inverse_host");
+}
+template <class T, size_t N>
+void solve_host(const Context& ctx, size_t count, const T* a, const T* b, T* x, uint8_t* status) {
+    ctx.check(t5_solve_host(ctx.handle(), dtype_of<T>::value, (int)N, 1, count, a, b, x, status), "t5_solve_host");
+}
+template <class T, size_t... Is>
+void transpose_host(const Context& ctx, size_t count, const T* a, T* out) {
+    auto d = Shape<Is...>::dims();
+    ctx.check(t5_transpose_host(ctx.handle(), dtype_of<T>::value, (int)d.size(), d.data(), count, a, out), "t5_transpose_host");
 }
 
 }  // namespace t5

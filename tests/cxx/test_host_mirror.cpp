@@ -123,6 +123,65 @@ int main() {
         expect_bits("minPoly", mp.to_list(), wm);
         expect_bits("minPoly degree", deg.to_list(), wdeg);
     }
+    {   // prod n, vector-space ops, structural ops, host-array entries
+        auto a = synth<double>(0, SA, 8, n * 6), b = synth<double>(0, SB, 8, n * 12);
+        auto A = Batch<double, 2, 3>::from_list(ctx, n, a);
+        auto B = Batch<double, 3, 4>::from_list(ctx, n, b);
+        Batch<double, 2, 4> P = prod<1>(A, B);                      // [2,3] x [3,4] contracted over 1 index
+        std::vector<double> wp(n * 8);
+        t5o_matmul(0, 2, 3, 4, n, a.data(), b.data(), wp.data(), 1);
+        expect_bits("prod 1 == .*. ([2,3] x [3,4])", P.to_list(), wp);
+        expect_bits("prod 1 == operator*", (A * B).to_list(), wp);
+        Batch<double, 2, 3, 3, 4> O = prod<0>(A, B);
+        std::vector<double> wo(n * 72);
+        const uint64_t da[2] = {2, 3}, db[2] = {3, 4};
+        t5o_prod(0, 2, da, 2, db, 0, n, a.data(), b.data(), wo.data(), 1);
+        expect_bits("prod 0 == tensor product", O.to_list(), wo);
+
+        auto c = synth<double>(0, SB, 9, n * 6);
+        auto C = Batch<double, 2, 3>::from_list(ctx, n, c);
+        std::vector<double> ws(n * 6), wd(n * 6), wh(n * 6), wk(n * 6);
+        for (size_t i = 0; i < n * 6; ++i) { ws[i] = a[i] + c[i]; wd[i] = a[i] - c[i]; wh[i] = a[i] * c[i]; wk[i] = 3.0 * a[i]; }
+        expect_bits("liftA2 (+)", (A + C).to_list(), ws);
+        expect_bits("liftA2 (-)", (A - C).to_list(), wd);
+        expect_bits("liftA2 (*)", hadamard(A, C).to_list(), wh);
+        expect_bits("fmap (3 *)", (3.0 * A).to_list(), wk);
+
+        // [A | col]: append along axis 2, then split it back (tests/Tensor.hs:25-29)
+        auto col = synth<double>(0, SB, 10, n * 2);
+        auto Col = Batch<double, 2, 1>::from_list(ctx, n, col);
+        Batch<double, 2, 4> Aug = append<2>(A, Col);
+        std::vector<double> wa(n * 8);
+        for (size_t i = 0; i < n; ++i)
+            for (int r = 0; r < 2; ++r) {
+                for (int j = 0; j < 3; ++j) wa[i * 8 + r * 4 + j] = a[i * 6 + r * 3 + j];
+                wa[i * 8 + r * 4 + 3] = col[i * 2 + r];
+            }
+        expect_bits("append 2 [2,3] [2,1]", Aug.to_list(), wa);
+        auto [L, R] = split<2, 3>(Aug);
+        expect_bits("split . append == id (left)", L.to_list(), a);
+        expect_bits("split . append == id (right)", R.to_list(), col);
+        Batch<double, 3> row2 = ta(2, A);
+        Batch<double, 2> col3 = at(A, {3});
+        std::vector<double> wr(n * 3), wc(n * 2);
+        for (size_t i = 0; i < n; ++i) {
+            for (int j = 0; j < 3; ++j) wr[i * 3 + j] = a[i * 6 + 3 + j];
+            for (int r = 0; r < 2; ++r) wc[i * 2 + r] = a[i * 6 + r * 3 + 2];
+        }
+        expect_bits("[2] `ta` t (row 2)", row2.to_list(), wr);
+        expect_bits("t `at` [3] (column 3)", col3.to_list(), wc);
+        expect_bits("slice [Nothing, Just 3] == at [3]", slice<2>(A, {0, 3}).to_list(), wc);
+
+        std::vector<double> hc(n * 8), hinv(n * 16), hi_want(n * 16);
+        matmul_host<double, 2, 3, 4>(ctx, n, a.data(), b.data(), hc.data());
+        expect_bits("matmul_host (host arrays, one call)", hc, wp);
+        auto m4 = synth<double>(0, SA, 11, n * 16);
+        std::vector<uint8_t> hst(n), wst(n);
+        inverse_host<double, 4>(ctx, n, m4.data(), hinv.data(), hst.data());
+        t5o_inverse(0, 4, n, m4.data(), hi_want.data(), wst.data(), 1);
+        expect_bits("inverse_host", hinv, hi_want);
+        expect_bits("inverse_host status", hst, wst);
+    }
     {   // fromList length check
         bool threw = false;
         try { Batch<double, 3, 3>::from_list(ctx, 2, std::vector<double>(17)); } catch (const WrongListLength&) { threw = true; }
