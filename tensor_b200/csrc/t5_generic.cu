@@ -567,28 +567,68 @@ int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, v
 // Element-wise vector-space operations (Functor/Applicative, Vector.hs:180-190,
 // :250-251).  Layout-agnostic: they act on the flat element array of a shard.
 // =====================================================================================
+// 16-byte streaming accesses, two vectors per operand in flight per thread; `n` elements, buffers
+// 256-byte aligned (shards), scalar tail for n % (16 / sizeof(T)).
 template <class T, int OP>
-__global__ void zip_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ c, unsigned long long n) {
+__device__ __forceinline__ T zip_op(T x, T y) {
     using R = Arith<T>;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        T x = a[i], y = b[i];
-        c[i] = OP == 0 ? R::add(x, y) : (OP == 1 ? R::sub(x, y) : R::mul(x, y));
+    return OP == 0 ? R::add(x, y) : (OP == 1 ? R::sub(x, y) : R::mul(x, y));
+}
+template <class T, int OP>
+__global__ void __launch_bounds__(256) zip_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ c, unsigned long long n) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const unsigned long long nv = n / V, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint4* av = reinterpret_cast<const uint4*>(a);
+    const uint4* bv = reinterpret_cast<const uint4*>(b);
+    uint4* cv = reinterpret_cast<uint4*>(c);
+    auto apply = [](const uint4& x, const uint4& y) {
+        uint4 r;
+        #pragma unroll
+        for (int j = 0; j < V; ++j)
+            reinterpret_cast<T*>(&r)[j] = zip_op<T, OP>(reinterpret_cast<const T*>(&x)[j], reinterpret_cast<const T*>(&y)[j]);
+        return r;
+    };
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nv; i += 2 * stride) {
+        const uint4 x0 = ld_global_stream16(av + i), y0 = ld_global_stream16(bv + i);
+        const uint4 x1 = ld_global_stream16(av + i + stride), y1 = ld_global_stream16(bv + i + stride);
+        st_global_stream16(cv + i, apply(x0, y0));
+        st_global_stream16(cv + i + stride, apply(x1, y1));
     }
+    for (; i < nv; i += stride) st_global_stream16(cv + i, apply(ld_global_stream16(av + i), ld_global_stream16(bv + i)));
+    for (unsigned long long t = nv * V + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+        c[t] = zip_op<T, OP>(a[t], b[t]);
 }
 template <class T>
-__global__ void scale_kernel(const T* __restrict__ a, T* __restrict__ c, T k, unsigned long long n) {
+__global__ void __launch_bounds__(256) scale_kernel(const T* __restrict__ a, T* __restrict__ c, T k, unsigned long long n) {
     using R = Arith<T>;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x)
-        c[i] = R::mul(k, a[i]);
+    constexpr int V = 16 / (int)sizeof(T);
+    const unsigned long long nv = n / V, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint4* av = reinterpret_cast<const uint4*>(a);
+    uint4* cv = reinterpret_cast<uint4*>(c);
+    auto apply = [k](const uint4& x) {
+        uint4 r;
+        #pragma unroll
+        for (int j = 0; j < V; ++j) reinterpret_cast<T*>(&r)[j] = R::mul(k, reinterpret_cast<const T*>(&x)[j]);
+        return r;
+    };
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nv; i += 2 * stride) {
+        const uint4 x0 = ld_global_stream16(av + i), x1 = ld_global_stream16(av + i + stride);
+        st_global_stream16(cv + i, apply(x0));
+        st_global_stream16(cv + i + stride, apply(x1));
+    }
+    for (; i < nv; i += stride) st_global_stream16(cv + i, apply(ld_global_stream16(av + i)));
+    for (unsigned long long t = nv * V + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+        c[t] = R::mul(k, a[t]);
 }
 
 template <class T>
 static int zip_t(const Shard& s, int op, size_t n, const void* A, const void* B, void* C) {
-    if (op == 0) launch_flat(zip_kernel<T, 0>, n, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
-    else if (op == 1) launch_flat(zip_kernel<T, 1>, n, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
-    else if (op == 2) launch_flat(zip_kernel<T, 2>, n, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
+    const size_t units = n / (16 / sizeof(T)) / 2 + 1;     // one thread per two 16-byte vectors
+    if (op == 0) launch_flat(zip_kernel<T, 0>, units, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
+    else if (op == 1) launch_flat(zip_kernel<T, 1>, units, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
+    else if (op == 2) launch_flat(zip_kernel<T, 2>, units, 256, s.stream, (const T*)A, (const T*)B, (T*)C, n);
     else return T5I_UNSUPPORTED;
     return ok();
 }
@@ -607,9 +647,9 @@ int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, 
 int generic_scale(const Shard& s, int dtype, const void* k, size_t elems, const void* A, void* C) {
     if (elems == 0) return T5I_OK;
     switch (dtype) {
-        case T5D_F64: launch_flat(scale_kernel<double>, elems, 256, s.stream, (const double*)A, (double*)C, *(const double*)k, elems); break;
-        case T5D_F32: launch_flat(scale_kernel<float>, elems, 256, s.stream, (const float*)A, (float*)C, *(const float*)k, elems); break;
-        case T5D_I64: launch_flat(scale_kernel<long long>, elems, 256, s.stream, (const long long*)A, (long long*)C, *(const long long*)k, elems); break;
+        case T5D_F64: launch_flat(scale_kernel<double>, elems / 4 + 1, 256, s.stream, (const double*)A, (double*)C, *(const double*)k, elems); break;
+        case T5D_F32: launch_flat(scale_kernel<float>, elems / 8 + 1, 256, s.stream, (const float*)A, (float*)C, *(const float*)k, elems); break;
+        case T5D_I64: launch_flat(scale_kernel<long long>, elems / 4 + 1, 256, s.stream, (const long long*)A, (long long*)C, *(const long long*)k, elems); break;
         default: return T5I_UNSUPPORTED;
     }
     return ok();

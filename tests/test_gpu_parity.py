@@ -377,15 +377,18 @@ def test_relayout_roundtrip(ctx, dc):
 
 @pytest.mark.parametrize("dc", ALL)
 def test_elementwise(ctx, dc):
-    batch = 3001
-    a, b = inputs(dc, 13, batch, 9, 9)
-    A, B = ctx.from_numpy(a, (3, 3)), ctx.from_numpy(b, (3, 3))
-    with np.errstate(over="ignore"):
-        assert_bits_equal((A + B).to_numpy().ravel(), a + b, "+")
-        assert_bits_equal((A - B).to_numpy().ravel(), a - b, "-")
-        assert_bits_equal(tb.zip_with("*", A, B).to_numpy().ravel(), a * b, "*")
-        k = a[3]
-        assert_bits_equal(tb.scale(k, A).to_numpy().ravel(), k * a, "scale")
+    # 3001 x 9, 1 x 3, 5 x 3, 700001 x 1: element counts that end inside a 16-byte vector and inside the
+    # unrolled-by-two main loop of the vectorised kernels
+    for batch, d in ((3001, 9), (1, 3), (5, 3), (700001, 1), (2, 2)):
+        a, b = inputs(dc, 13, batch, d, d)
+        shape = (3, 3) if d == 9 else ((d,) if d > 1 else ())
+        A, B = ctx.from_numpy(a, shape), ctx.from_numpy(b, shape)
+        with np.errstate(over="ignore"):
+            assert_bits_equal((A + B).to_numpy().ravel(), a + b, "+")
+            assert_bits_equal((A - B).to_numpy().ravel(), a - b, "-")
+            assert_bits_equal(tb.zip_with("*", A, B).to_numpy().ravel(), a * b, "*")
+            k = a[min(3, a.size - 1)]
+            assert_bits_equal(tb.scale(k, A).to_numpy().ravel(), k * a, "scale")
 
 
 def test_device_synthetic_matches_oracle(ctx):

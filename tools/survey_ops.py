@@ -55,6 +55,7 @@ def main():
             b6 = ctx.synthetic((6,), dt, B // 4, SEED + 1, 4)
             A8 = ctx.synthetic((8, 8), dt, B // 4, SEED, 5)
             T234 = ctx.synthetic((2, 3, 4), dt, B, SEED, 6)
+            timed(ctx, lambda: tb.zip_with("+", A4, B4))        # grows the allocator pool once, untimed
             add(f"zip + 4x4 {tag}", B * 16 * es * 3, lambda: tb.zip_with("+", A4, B4))
             add(f"scale 4x4 {tag}", B * 16 * es * 2, lambda: tb.scale(dt(3.0), A4))
             add(f"tr 4x4 {tag}", B * (16 + 1) * es, lambda: tb.tr(A4))
