@@ -1,7 +1,7 @@
 """Developer survey: time every remaining public operation once (device-resident, CUDA events on the
 library's stream) and print achieved GB/s against algorithmic bytes, to find untuned paths.
-Each call allocates its result, so the figures include cudaMalloc/cudaFree of the output; read them as
-lower bounds.  Usage (GPU box): python tools/survey_ops.py"""
+Each call allocates its result from the context's stream-ordered pool (warmed to steady size first), so the
+figures are what a chained caller sees per operation.  Usage (GPU box): python tools/survey_ops.py"""
 import os
 import sys
 
@@ -15,7 +15,7 @@ SEED = 0x5EED000000000001
 
 
 def timed(ctx, fn, reps=5):
-    outs = [fn() for _ in range(2)]
+    outs = [fn() for _ in range(reps)]      # as many live outputs as the timed loop: the pool reaches its steady size
     for o in outs:
         free(o)
     ctx.sync()
