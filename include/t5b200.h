@@ -161,6 +161,17 @@ int t5_poly_eval(t5_ctx* ctx, int dtype, int n, const void* coeffs, int ncoef, c
 int t5_char_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
 int t5_min_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* DEGREE);
 
+/* rowEchelonForm / triangularSolve of the old Data.Tensor.LinearAlgebra (removed with it,
+ * CHANGELOG.md:24-29; SURVEY.md §8f-4 "rowEchelonForm-style outputs"; parity unpinned, the
+ * arithmetic is specified in oracle/t5_oracle.cpp row_echelon_item).  OUT receives the REDUCED
+ * row echelon form of each rows x cols item of A: Gauss-Jordan with the first-non-zero pivot
+ * rule and the quotient multipliers of det/inverse/solve (rank == n iff t5_inverse succeeds),
+ * the pivot column cleared in every other row, then the pivot row divided by its pivot.  Pivots are searched in the first pivot_cols columns only: pivot_cols = cols
+ * is rowEchelonForm; on an augmented [A | B] item with pivot_cols = cols(A) it is
+ * triangularSolve (A reduced, B carried along).  RANK (T5_U8) receives the number of pivots.
+ * Double / Float, rows <= 8, cols <= 16, AoS. */
+int t5_row_echelon(t5_ctx* ctx, int dtype, int rows, int cols, int pivot_cols, const t5_buf* A, t5_buf* OUT, t5_buf* RANK);
+
 /* Element-wise vector-space operations (Functor/Applicative instances,
  * src/Data/Tensor/Vector.hs:180-190, :250-251: liftA2 (+), liftA2 (-), scalar *).
  * op: 0 = a + b, 1 = a - b, 2 = a * b (Hadamard); t5_scale multiplies by *scalar. */

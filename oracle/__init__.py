@@ -61,6 +61,7 @@ def lib() -> ctypes.CDLL:
         L.t5o_poly_eval.argtypes = [i32, i32, vp, i32, sz, vp, vp, i32]
         L.t5o_char_poly.argtypes = [i32, i32, sz, vp, vp, i32]
         L.t5o_min_poly.argtypes = [i32, i32, sz, vp, vp, vp, i32]
+        L.t5o_row_echelon.argtypes = [i32, i32, i32, i32, sz, vp, vp, vp, i32]
         L.t5o_fill.argtypes = [i32, u64, u64, u64, sz, vp]
         L.t5o_plant_specials.argtypes = [i32, i32, u64, sz, vp, u64, u64]
         _lib = L
@@ -209,6 +210,18 @@ def min_poly(a: np.ndarray, n: int, threads: int = 1):
     deg = np.empty((batch,), dtype=np.uint8)
     _chk(lib().t5o_min_poly(DTYPE_OF[a.dtype], n, batch, _ptr(a), _ptr(out), _ptr(deg), threads))
     return out, deg
+
+
+def row_echelon(a: np.ndarray, m: int, n: int, pivot_cols: int | None = None, threads: int = 1):
+    """([batch, m, n] reduced row echelon forms, [batch] ranks); pivots are searched in the first
+    pivot_cols columns only (default: all n)."""
+    a = _c(a)
+    batch = a.size // (m * n)
+    out = np.empty((batch, m, n), dtype=a.dtype)
+    rank = np.empty((batch,), dtype=np.uint8)
+    pc = n if pivot_cols is None else int(pivot_cols)
+    _chk(lib().t5o_row_echelon(DTYPE_OF[a.dtype], m, n, pc, batch, _ptr(a), _ptr(out), _ptr(rank), threads))
+    return out, rank
 
 
 # ---- synthetic inputs (SURVEY §8d) ------------------------------------------

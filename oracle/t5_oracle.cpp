@@ -291,6 +291,46 @@ static uint8_t min_poly_item(const T* A, T* c, int n) {
     return (uint8_t)n;
 }
 
+// rowEchelonForm (SURVEY §8f-4 "rowEchelonForm-style outputs"; the class method itself left the
+// library with Data.Tensor.LinearAlgebra, CHANGELOG.md:24-29 - **PARITY UNPINNED**, this IS the
+// specification).  Reduced row echelon form of an m x n matrix by Gauss-Jordan with the
+// first-non-zero pivot rule and the quotient multipliers of a9-a11 (so that below the pivots the
+// matrix evolves exactly as in det / inverse / solve: an exactly repeated row is an exact zero
+// row here too, and rank == n iff inverse succeeds), pivot rows normalised afterwards:
+//   rank = 0; for c = 0 .. pivot_cols-1 while rank < m:
+//     p = first row >= rank with W[p,c] /= 0 (exact compare); none -> next column
+//     swap rows p and rank
+//     every other row i (ascending): f = W[i,c] / W[rank,c];
+//                                    W[i,j] = W[i,j] - f*W[rank,j] (j > c);  W[i,c] = 0
+//     d = W[rank,c];  W[rank,j] = W[rank,j] / d  (j > c);  W[rank,c] = 1
+//     rank += 1
+// Only the first pivot_cols columns are searched for pivots: pivot_cols = n is rowEchelonForm,
+// pivot_cols = cols(A) on [A | B] is the old triangularSolve (A reduced, B carried along).
+// Returns the rank (number of pivots).
+template <class T>
+static uint8_t row_echelon_item(const T* A, T* W, int m, int n, int pivot_cols) {
+    std::memcpy(W, A, sizeof(T) * m * n);
+    int rank = 0;
+    for (int c = 0; c < pivot_cols && rank < m; ++c) {
+        int p = rank;
+        while (p < m && W[p * n + c] == T(0)) ++p;
+        if (p == m) continue;
+        if (p != rank)
+            for (int j = 0; j < n; ++j) std::swap(W[p * n + j], W[rank * n + j]);
+        const T d = W[rank * n + c];
+        for (int i = 0; i < m; ++i) {
+            if (i == rank) continue;
+            const T f = W[i * n + c] / d;
+            for (int j = c + 1; j < n; ++j) W[i * n + j] = W[i * n + j] - f * W[rank * n + j];
+            W[i * n + c] = T(0);
+        }
+        for (int j = c + 1; j < n; ++j) W[rank * n + j] = W[rank * n + j] / d;
+        W[rank * n + c] = T(1);
+        ++rank;
+    }
+    return (uint8_t)rank;
+}
+
 // Run f(b0, b1) over contiguous chunks of [0, batch) on `threads` std::threads.
 template <class F>
 static void par_chunks(size_t batch, int threads, F f) {
@@ -494,6 +534,15 @@ int t5o_min_poly(int dtype, int n, size_t batch, const void* A, void* OUT, uint8
         par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) degree[b] = min_poly_item<T>(a + b * n * n, o + b * (n + 1), n); }); return 0; }
     switch (dtype) { case 0: T5O_MP(double) case 1: T5O_MP(float) }
 #undef T5O_MP
+    return 2;
+}
+
+int t5o_row_echelon(int dtype, int m, int n, int pivot_cols, size_t batch, const void* A, void* OUT, uint8_t* rank, int threads) {
+    if (m < 1 || n < 1 || m > 16 || n > 32 || pivot_cols < 0 || pivot_cols > n) return 1;
+#define T5O_RE(T) { const T* a = (const T*)A; T* o = (T*)OUT; \
+        par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) rank[b] = row_echelon_item<T>(a + b * m * n, o + b * m * n, m, n, pivot_cols); }); return 0; }
+    switch (dtype) { case 0: T5O_RE(double) case 1: T5O_RE(float) }
+#undef T5O_RE
     return 2;
 }
 

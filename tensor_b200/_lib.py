@@ -56,6 +56,7 @@ SIGNATURES = {
     "t5_poly_eval": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "t5_char_poly": (_i, [_vp, _i, _i, _vp, _vp]),
     "t5_min_poly": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "t5_row_echelon": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "t5_zip": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_scale": (_i, [_vp, _i, _vp, _vp, _vp]),
     "t5_append": (_i, [_vp, _i, _i, _i, _u64p, _u64p, _vp, _vp, _vp]),

@@ -564,6 +564,110 @@ int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, v
 }
 
 // =====================================================================================
+// rowEchelonForm / triangularSolve (specification: oracle/t5_oracle.cpp
+// row_echelon_item): reduced row echelon form of any rows x cols matrix, rows <= 8, cols <= 16.
+// The pivot ROW is a run-time quantity here (a column without a pivot does not advance it), so a
+// register-resident working matrix is not possible; local memory (3 MB per SM of L1/L2 traffic)
+// is what made the first any-n elimination kernels slow.  Instead a CTA stages TPB consecutive
+// records into shared memory TRANSPOSED - element e of the CTA's item t at w[e * (TPB+1) + t] -
+// with coalesced global reads, every thread reduces its own column of that array in place
+// (stride-1 across the warp: conflict-free LDS/STS for any run-time index), and the CTA writes the
+// tile back coalesced.  Same operations in the same order as the oracle: bit-identical.
+// =====================================================================================
+constexpr int ECH_MAX_ROWS = 8, ECH_MAX_COLS = 16;
+
+template <class T, int TPB>
+__global__ void __launch_bounds__(TPB)
+row_echelon_kernel(const T* __restrict__ A, T* __restrict__ OUT, unsigned char* __restrict__ RANK, int m, int n, int pivot_cols,
+                   unsigned long long count) {
+    extern __shared__ __align__(16) unsigned char ech_smem[];
+    T* w = reinterpret_cast<T*>(ech_smem);
+    constexpr int P = TPB + 1;
+    const int L = m * n;
+    const int tid = threadIdx.x;
+    const unsigned long long n_tiles = (count + TPB - 1) / TPB;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * TPB;
+        const int nv = (count - first < (unsigned long long)TPB) ? (int)(count - first) : TPB;
+        const int total = nv * L;
+        const T* g = A + first * (size_t)L;
+        {
+            int item = tid / L, e = tid - item * L;
+            #pragma unroll 4
+            for (int idx = tid; idx < total; idx += TPB) {
+                w[e * P + item] = g[idx];
+                e += TPB;
+                while (e >= L) { e -= L; ++item; }
+            }
+        }
+        __syncthreads();
+        if (tid < nv) {
+            T* x = w + tid;                                     // element (i, j) of this item: x[(i * n + j) * P]
+            int rank = 0;
+            for (int c = 0; c < pivot_cols && rank < m; ++c) {
+                int p = rank;
+                while (p < m && x[(p * n + c) * P] == T(0)) ++p;
+                if (p == m) continue;
+                if (p != rank)
+                    for (int j = 0; j < n; ++j) {
+                        const T t = x[(p * n + j) * P];
+                        x[(p * n + j) * P] = x[(rank * n + j) * P];
+                        x[(rank * n + j) * P] = t;
+                    }
+                T* pr = x + (rank * n) * P;
+                const T d = pr[c * P];
+                for (int i = 0; i < m; ++i) {
+                    if (i == rank) continue;
+                    T* ri = x + (i * n) * P;
+                    const T f = ri[c * P] / d;
+                    for (int j = c + 1; j < n; ++j) ri[j * P] = ri[j * P] - f * pr[j * P];
+                    ri[c * P] = T(0);
+                }
+                for (int j = c + 1; j < n; ++j) pr[j * P] = pr[j * P] / d;
+                pr[c * P] = T(1);
+                ++rank;
+            }
+            RANK[first + tid] = (unsigned char)rank;
+        }
+        __syncthreads();
+        {
+            T* o = OUT + first * (size_t)L;
+            int item = tid / L, e = tid - item * L;
+            #pragma unroll 4
+            for (int idx = tid; idx < total; idx += TPB) {
+                o[idx] = w[e * P + item];
+                e += TPB;
+                while (e >= L) { e -= L; ++item; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T, int TPB>
+static int launch_row_echelon(const Shard& s, int m, int n, int pivot_cols, const void* A, void* O, void* rank) {
+    auto kern = row_echelon_kernel<T, TPB>;
+    const int smem = m * n * (TPB + 1) * (int)sizeof(T);
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return T5I_CUDA;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const size_t tiles = (s.count + TPB - 1) / TPB, cap = (size_t)occ * sm_count();
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    kern<<<grid, TPB, smem, s.stream>>>((const T*)A, (T*)O, (unsigned char*)rank, m, n, pivot_cols, (unsigned long long)s.count);
+    return ok();
+}
+
+int generic_row_echelon(const Shard& s, int dtype, int m, int n, int pivot_cols, const void* A, void* O, void* rank) {
+    if (s.layout != T5L_AOS || m < 1 || n < 1 || m > ECH_MAX_ROWS || n > ECH_MAX_COLS || pivot_cols < 0 || pivot_cols > n) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    // small records: 128 items per CTA (more bytes in flight per CTA); large ones: 64, so that several CTAs fit an SM
+    const bool small = (size_t)m * n * (dtype == T5D_F64 ? 8 : 4) <= 192;
+    if (dtype == T5D_F64) return small ? launch_row_echelon<double, 128>(s, m, n, pivot_cols, A, O, rank) : launch_row_echelon<double, 64>(s, m, n, pivot_cols, A, O, rank);
+    if (dtype == T5D_F32) return small ? launch_row_echelon<float, 128>(s, m, n, pivot_cols, A, O, rank) : launch_row_echelon<float, 64>(s, m, n, pivot_cols, A, O, rank);
+    return T5I_UNSUPPORTED;
+}
+
+// =====================================================================================
 // Element-wise vector-space operations (Functor/Applicative, Vector.hs:180-190,
 // :250-251).  Layout-agnostic: they act on the flat element array of a shard.
 // =====================================================================================

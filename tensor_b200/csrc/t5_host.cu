@@ -756,8 +756,28 @@ int t5_min_poly(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_bu
     for (int g = 0; g < c->ndev; ++g) {
         if (!A->count[g]) continue;
         CU(c, cudaSetDevice(c->dev[g]));
-        int r = generic_min_poly(shard_of(c, A, g), dtype, n, A->ptr[g], OUT->ptr[g], DEGREE->ptr[g]);
+        Shard s = shard_of(c, A, g);
+        int r = small_min_poly(s, dtype, n, A->ptr[g], OUT->ptr[g], DEGREE->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_min_poly(s, dtype, n, A->ptr[g], OUT->ptr[g], DEGREE->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_min_poly");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
+int t5_row_echelon(t5_ctx* c, int dtype, int rows, int cols, int pivot_cols, const t5_buf* A, t5_buf* OUT, t5_buf* RANK) {
+    if (!c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;
+    if (rows < 1 || cols < 1 || pivot_cols < 0 || pivot_cols > cols) return T5_ERR_SHAPE;
+    CHECK(check(c, A, dtype, (size_t)rows * cols, nullptr));
+    CHECK(check(c, OUT, dtype, (size_t)rows * cols, A));
+    CHECK(check(c, RANK, T5_U8, 1, A));
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!A->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        int r = generic_row_echelon(shard_of(c, A, g), dtype, rows, cols, pivot_cols, A->ptr[g], OUT->ptr[g], RANK->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_row_echelon");
         c->launches++;
     }
     return T5_OK;

@@ -43,6 +43,7 @@ int small_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const
 int small_trace(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_poly_eval(const Shard& s, int dtype, int n, const void* coeffs_host, int ncoef, const void* A, void* O);
 int small_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
+int small_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree);
 
 // ---- t5_mid_ops.cu: row-per-thread contractions for 0.25-4 KiB records (8x8, 16x16, ...) -----
 int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
@@ -62,6 +63,7 @@ int generic_trace(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_poly_eval(const Shard& s, int dtype, int n, const void* coeffs_dev, int ncoef, const void* A, void* O);
 int generic_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree);
+int generic_row_echelon(const Shard& s, int dtype, int rows, int cols, int pivot_cols, const void* A, void* O, void* rank);
 int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, const void* B, void* C);
 int generic_scale(const Shard& s, int dtype, const void* scalar_host, size_t elems, const void* A, void* C);
 // per-device partial of sum_b dot(x_b, y_b): *partial_dev is double (F64/F32) or int64

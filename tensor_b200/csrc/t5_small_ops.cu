@@ -92,6 +92,20 @@ template <class T> struct Geo<DetOp<T, 4>> { using type = G<128, 1, 2, 6>; };
 template <class T> struct Geo<InverseOp<T, 2>> { using type = G<128, 1, 2>; };
 template <class T> struct Geo<InverseOp<T, 3>> { using type = G<128, 1, 2, 6>; };   // register cap 80: 6 CTAs/SM
 template <class T> struct Geo<InverseOp<T, 4>> { using type = G<64, 1, 2, 8>; };    // register cap 128: 8 CTAs/SM (r01_tune_elim_v3.csv)
+// 5x5 / 6x6 elimination: one record per thread, small CTAs
+template <class T> struct Geo<DetOp<T, 5>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<DetOp<T, 6>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 5>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 6>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<SolveOp<T, 5, 1>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<SolveOp<T, 6, 1>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<DetOp<T, 7>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<DetOp<T, 8>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 7>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<InverseOp<T, 8>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<SolveOp<T, 7, 1>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<SolveOp<T, 8, 1>> { using type = G<64, 1, 2>; };
+template <class T, int N> struct Geo<MinPolyOp<T, N>> { using type = G<64, 1, 2>; };              // up to 248 registers (4x4 Double)
 template <class T, int N, int R> struct Geo<SolveOp<T, N, R>> {
     using type = std::conditional_t<(R == 1), std::conditional_t<(N <= 3), G<256, 1, 3>, G<128, 1, 2, 5>>,
                                     std::conditional_t<(N <= 3), G<128, 1, 2, 6>, G<64, 1, 2, 8>>>;
@@ -147,6 +161,10 @@ static int det_t(const Shard& s, int n, const void* A, void* O) {
     if (n == 2) return launch_op<DetOp<T, 2>>(s, A, nullptr, O, nullptr);
     if (n == 3) return launch_op<DetOp<T, 3>>(s, A, nullptr, O, nullptr);
     if (n == 4) return launch_op<DetOp<T, 4>>(s, A, nullptr, O, nullptr);
+    if (n == 5) return launch_op<DetOp<T, 5>>(s, A, nullptr, O, nullptr);
+    if (n == 6) return launch_op<DetOp<T, 6>>(s, A, nullptr, O, nullptr);
+    if (n == 7) return launch_op<DetOp<T, 7>>(s, A, nullptr, O, nullptr);
+    if (n == 8) return launch_op<DetOp<T, 8>>(s, A, nullptr, O, nullptr);
     return T5I_NOT_SPECIALISED;
 }
 int small_det(const Shard& s, int dtype, int n, const void* A, void* O) {
@@ -160,6 +178,10 @@ static int inverse_t(const Shard& s, int n, const void* A, void* O, void* status
     if (n == 2) return launch_op<InverseOp<T, 2>>(s, A, nullptr, O, status);
     if (n == 3) return launch_op<InverseOp<T, 3>>(s, A, nullptr, O, status);
     if (n == 4) return launch_op<InverseOp<T, 4>>(s, A, nullptr, O, status);
+    if (n == 5) return launch_op<InverseOp<T, 5>>(s, A, nullptr, O, status);
+    if (n == 6) return launch_op<InverseOp<T, 6>>(s, A, nullptr, O, status);
+    if (n == 7) return launch_op<InverseOp<T, 7>>(s, A, nullptr, O, status);
+    if (n == 8) return launch_op<InverseOp<T, 8>>(s, A, nullptr, O, status);
     return T5I_NOT_SPECIALISED;
 }
 int small_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status) {
@@ -172,7 +194,7 @@ template <class T>
 static int solve_t(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
 #define T5_SV(N_, R_) \
     if (n == N_ && nrhs == R_) return launch_op<SolveOp<T, N_, R_>>(s, A, B, X, status);
-    T5_SV(2, 1) T5_SV(3, 1) T5_SV(4, 1) T5_SV(2, 2) T5_SV(3, 3) T5_SV(4, 4)
+    T5_SV(2, 1) T5_SV(3, 1) T5_SV(4, 1) T5_SV(2, 2) T5_SV(3, 3) T5_SV(4, 4) T5_SV(5, 1) T5_SV(6, 1) T5_SV(7, 1) T5_SV(8, 1)
 #undef T5_SV
     return T5I_NOT_SPECIALISED;
 }
@@ -231,6 +253,19 @@ static int char_poly_t(const Shard& s, int n, const void* A, void* O) {
 int small_char_poly(const Shard& s, int dtype, int n, const void* A, void* O) {
     if (dtype == T5D_F64) return char_poly_t<double>(s, n, A, O);
     if (dtype == T5D_F32) return char_poly_t<float>(s, n, A, O);
+    return T5I_NOT_SPECIALISED;
+}
+
+template <class T>
+static int min_poly_t(const Shard& s, int n, const void* A, void* O, void* degree) {
+    if (n == 2) return launch_op<MinPolyOp<T, 2>>(s, A, nullptr, O, degree);
+    if (n == 3) return launch_op<MinPolyOp<T, 3>>(s, A, nullptr, O, degree);
+    if (n == 4) return launch_op<MinPolyOp<T, 4>>(s, A, nullptr, O, degree);
+    return T5I_NOT_SPECIALISED;
+}
+int small_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree) {
+    if (dtype == T5D_F64) return min_poly_t<double>(s, n, A, O, degree);
+    if (dtype == T5D_F32) return min_poly_t<float>(s, n, A, O, degree);
     return T5I_NOT_SPECIALISED;
 }
 

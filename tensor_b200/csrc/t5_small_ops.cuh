@@ -87,6 +87,14 @@ struct Recip<double> {
     }
 };
 
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
 // ---- Gaussian elimination, first-non-zero pivot (§8a pivot rule) --------------------
 // w is N x W in registers; every index is a compile-time constant after unrolling.  The
 // pivot search only runs when the diagonal entry is an exact zero (rare): inside, a chain
@@ -95,11 +103,14 @@ template <class T, int N, int W>
 __device__ __forceinline__ bool eliminate(T (&w)[N][W], int& swaps, Recip<T> (&rc)[N]) {
     bool singular = false;
     swaps = 0;
-    #pragma unroll
-    for (int k = 0; k < N; ++k) {
+    // static_for (template recursion), not `#pragma unroll`: for n >= 5 the unroller gives up on
+    // the pivot chain and on the row loop (the inlined division is large), and one runtime row
+    // index is enough to push the whole working matrix into local memory.
+    static_for<0, N>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
         if (k + 1 < N && w[k][k] == T(0)) {
-            #pragma unroll
-            for (int r = k + 1; r < N; ++r) {
+            static_for<k + 1, N>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
                 const bool sw = (w[k][k] == T(0)) && (w[r][k] != T(0));
                 // columns < k of rows >= k are exact zeros already: swapping them is a no-op
                 #pragma unroll
@@ -109,18 +120,18 @@ __device__ __forceinline__ bool eliminate(T (&w)[N][W], int& swaps, Recip<T> (&r
                     w[r][j] = sw ? x : y;
                 }
                 swaps += sw ? 1 : 0;
-            }
+            });
         }
         singular = singular || (w[k][k] == T(0));
         rc[k] = Recip<T>(w[k][k]);
-        #pragma unroll
-        for (int i = k + 1; i < N; ++i) {
+        static_for<k + 1, N>([&](auto i_) {
+            constexpr int i = decltype(i_)::value;
             const T f = rc[k].div(w[i][k]);
             #pragma unroll
             for (int j = k + 1; j < W; ++j) w[i][j] = w[i][j] - f * w[k][j];
             w[i][k] = T(0);
-        }
-    }
+        });
+    });
     return !singular;
 }
 
@@ -152,15 +163,16 @@ __device__ __forceinline__ void solve_regs(T (&w)[N][N + NRHS], T* x, unsigned c
     Recip<T> rc[N];
     const bool ok = eliminate<T, N, N + NRHS>(w, swaps, rc);
     T xs[N][NRHS];
-    #pragma unroll
-    for (int k = N - 1; k >= 0; --k)
-        #pragma unroll
-        for (int c = 0; c < NRHS; ++c) {
+    static_for<0, N>([&](auto kk_) {
+        constexpr int k = N - 1 - decltype(kk_)::value;
+        static_for<0, NRHS>([&](auto c_) {
+            constexpr int c = decltype(c_)::value;
             T s = T(0);
             #pragma unroll
             for (int j = k + 1; j < N; ++j) s = s + w[k][j] * xs[j][c];
             xs[k][c] = rc[k].div(w[k][N + c] - s);
-        }
+        });
+    });
     #pragma unroll
     for (int k = 0; k < N; ++k)
         #pragma unroll
@@ -276,6 +288,93 @@ struct CharPolyOp {
     }
 };
 
+// minPoly: first exact linear dependency among vec(I), vec(A), vec(A^2), ..; the
+// oracle's Krylov elimination (oracle/t5_oracle.cpp min_poly_item) with every loop unrolled at
+// compile time.  The only run-time indices are the pivot positions (first non-zero entry of a
+// reduced candidate): they are read and cleared through select chains, so the basis, the
+// combinations and the candidate all stay in registers (the any-n kernel keeps them in local
+// memory: 4Mi 4x4 Double 5.7 ms).  Operation order per element is the oracle's.
+template <class T, int LEN>
+__device__ __forceinline__ T pick(const T (&v)[LEN], int p) {
+    T r = v[0];
+    #pragma unroll
+    for (int t = 1; t < LEN; ++t) r = (t == p) ? v[t] : r;
+    return r;
+}
+
+template <class T, int N>
+struct MinPolyOp {
+    static constexpr int L = N * N;
+    using In0 = Rec<T, L>; using In1 = NoRec;
+    using Out0 = Rec<T, N + 1>; using Out1 = Rec<unsigned char, 1>;
+    __device__ __forceinline__ static void run(const T* a, const unsigned char*, T* c, unsigned char* degree) {
+        T basis[N][L], coef[N][N + 1], P[L];
+        int pivot[N] = {};
+        int deg = -1;
+        static_for<0, N>([&](auto m_) {
+            constexpr int m = decltype(m_)::value;
+            if (deg < 0) {   // every earlier candidate joined the basis: it has exactly m members
+                if constexpr (m == 0) {
+                    #pragma unroll
+                    for (int t = 0; t < L; ++t) P[t] = (t / N == t % N) ? T(1) : T(0);
+                } else {
+                    T pn[L];
+                    #pragma unroll
+                    for (int i = 0; i < N; ++i)
+                        #pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            T acc = T(0);
+                            #pragma unroll
+                            for (int k = 0; k < N; ++k) acc = acc + P[i * N + k] * a[k * N + j];
+                            pn[i * N + j] = acc;
+                        }
+                    #pragma unroll
+                    for (int t = 0; t < L; ++t) P[t] = pn[t];
+                }
+                T v[L], g[N + 1];
+                #pragma unroll
+                for (int t = 0; t < L; ++t) v[t] = P[t];
+                #pragma unroll
+                for (int j = 0; j <= N; ++j) g[j] = (j == m) ? T(1) : T(0);
+                static_for<0, m>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    const int p = pivot[i];
+                    const T f = pick(v, p) / pick(basis[i], p);
+                    #pragma unroll
+                    for (int t = 0; t < L; ++t) {
+                        const T d = v[t] - f * basis[i][t];
+                        v[t] = (t == p) ? T(0) : d;
+                    }
+                    #pragma unroll
+                    for (int j = 0; j <= N; ++j) g[j] = g[j] - f * coef[i][j];
+                });
+                int p = L;
+                #pragma unroll
+                for (int t = L - 1; t >= 0; --t) p = (v[t] != T(0)) ? t : p;
+                if (p == L) {
+                    #pragma unroll
+                    for (int j = 0; j <= N; ++j) c[j] = (j <= m) ? g[j] : T(0);
+                    deg = m;
+                } else {
+                    #pragma unroll
+                    for (int t = 0; t < L; ++t) basis[m][t] = v[t];
+                    #pragma unroll
+                    for (int j = 0; j <= N; ++j) coef[m][j] = g[j];
+                    pivot[m] = p;
+                }
+            }
+        });
+        if (deg < 0) {   // I .. A^(N-1) independent: the characteristic polynomial
+            CharPolyOp<T, N>::run(a, nullptr, c, nullptr);
+            deg = N;
+        }
+        degree[0] = (unsigned char)deg;
+    }
+};
+
+// inverse(A) = solve(A, I).  (Eliminating [A | I] in two column blocks to shorten the working
+// matrix was tried for n >= 5: the input record and the finished block stay live across the
+// blocks, so the register peak does not drop and the extra pass made every size slower.)
 template <class T, int N>
 struct InverseOp {
     using In0 = Rec<T, N * N>; using In1 = NoRec;

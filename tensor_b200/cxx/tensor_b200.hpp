@@ -195,6 +195,14 @@ std::pair<Batch<T, N + 1>, Batch<uint8_t>> min_poly(const Batch<T, N, N>& a) {  
     a.ctx().check(t5_min_poly(a.ctx().handle(), dtype_of<T>::value, (int)N, a.buf(), c.buf(), deg.buf()), "t5_min_poly");
     return {c, deg};
 }
+// rowEchelonForm (reduced; pivots looked for in the first pivot_cols columns, default all): (form, rank)
+template <class T, size_t R, size_t C>
+std::pair<Batch<T, R, C>, Batch<uint8_t>> row_echelon_form(const Batch<T, R, C>& a, int pivot_cols = (int)C) {
+    Batch<T, R, C> e(a.ctx(), a.count());
+    Batch<uint8_t> rank(a.ctx(), a.count());
+    a.ctx().check(t5_row_echelon(a.ctx().handle(), dtype_of<T>::value, (int)R, (int)C, pivot_cols, a.buf(), e.buf(), rank.buf()), "t5_row_echelon");
+    return {e, rank};
+}
 template <class T, size_t... Is>
 Batch<T, Is...> operator+(const Batch<T, Is...>& a, const Batch<T, Is...>& b) {   // liftA2 (+)
     Batch<T, Is...> c(a.ctx(), a.count());

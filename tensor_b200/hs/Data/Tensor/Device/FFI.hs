@@ -91,6 +91,8 @@ foreign import ccall safe "t5_char_poly"
   c_char_poly :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> IO CInt
 foreign import ccall safe "t5_min_poly"
   c_min_poly :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_row_echelon"
+  c_row_echelon :: Ptr Ctx -> CInt -> CInt -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
 
 -- structural operations (src/Data/Tensor/Vector.hs:260-354, :400-463) as device gathers
 foreign import ccall safe "t5_append"

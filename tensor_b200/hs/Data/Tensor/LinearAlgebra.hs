@@ -27,7 +27,7 @@
 module Data.Tensor.LinearAlgebra
     ( MatrixProduct(..), DotProduct(..), TensorProduct(..), Transpose(..)
     , SquareMatrix(..), LinearSystem(..)
-    , dotSum, prodN, tr, polyEval, charPoly, minPoly
+    , dotSum, prodN, tr, polyEval, charPoly, minPoly, rowEchelonForm, echelonWith
     , addB, subB, hadamardB, scaleB
     ) where
 
@@ -227,6 +227,26 @@ minPoly a = do
     d <- newStatusBatch (batchCtx a) (batchCount a)
     unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po -> unsafeWithBatch d $ \pd ->
         c_min_poly h (code (Proxy :: Proxy e)) (fromIntegral n) pa po pd >>= checkRC (batchCtx a) "t5_min_poly"
+    return (o, d)
+
+-- | Reduced row echelon form of every item and its rank (the @rowEchelonForm@ of the old
+-- @Data.Tensor.LinearAlgebra@, CHANGELOG.md:24-29): Gauss-Jordan with the first-non-zero pivot rule.
+rowEchelonForm :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e)
+               => Batch '[i, j] e -> IO (Batch '[i, j] e, Batch '[] Word8)
+rowEchelonForm a = let [_, c] = batchShape a in echelonWith c a
+
+-- | @triangularSolve@ on an augmented batch @[a | b]@ whose first @k@ columns are @a@: row operations
+-- until @a@ is in reduced row echelon form, @b@ carried along; pivots are only looked for in @a@.
+-- (Build the augmented batch with 'append' and cut the result with 'split'.)
+echelonWith :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e)
+            => Int -> Batch '[i, j] e -> IO (Batch '[i, j] e, Batch '[] Word8)
+echelonWith k a = do
+    let [r, c] = batchShape a; Context h = batchCtx a
+    o <- newBatch (batchCtx a) (batchCount a)
+    d <- newStatusBatch (batchCtx a) (batchCount a)
+    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po -> unsafeWithBatch d $ \pd ->
+        c_row_echelon h (code (Proxy :: Proxy e)) (fromIntegral r) (fromIntegral c) (fromIntegral k) pa po pd
+            >>= checkRC (batchCtx a) "t5_row_echelon"
     return (o, d)
 
 -- Vector-space operations: what @liftA2 (+)@, @liftA2 (-)@, @liftA2 (*)@ and @fmap (k *)@ of the

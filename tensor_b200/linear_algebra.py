@@ -169,6 +169,42 @@ def min_poly(a: Batch) -> Tuple[Batch, Batch]:
     return out, deg
 
 
+def row_echelon_form(a: Batch, pivot_cols: int | None = None) -> Tuple[Batch, Batch]:
+    """``rowEchelonForm``: (reduced row echelon form of every rows x cols item, rank per item).  Pivots are
+    looked for in the first ``pivot_cols`` columns only (default: all of them)."""
+    if len(a.shape) != 2:
+        raise WrongListLength(f"rowEchelonForm needs a matrix, got shape {a.shape}")
+    rows, cols = a.shape
+    pc = cols if pivot_cols is None else int(pivot_cols)
+    out = Batch(a.ctx, a.shape, a.dtype, a.batch, a.layout)
+    rank = Batch(a.ctx, (), U8, a.batch, a.layout)
+    check(_lib.lib().t5_row_echelon(a.ctx._h, a.dtype, rows, cols, pc, a._h, out._h, rank._h), a.ctx)
+    return out, rank
+
+
+def triangular_solve(a: Batch, b: Batch) -> Tuple[Batch, Batch, Batch]:
+    """``triangularSolve a b``: row operations on the augmented [a | b] until a is in reduced row echelon form;
+    returns (reduced a, transformed b, rank of a).  b is a matrix with a's row count, or a vector of that length."""
+    from . import structure
+    if len(a.shape) != 2 or len(b.shape) not in (1, 2) or b.shape[0] != a.shape[0]:
+        raise WrongListLength(f"triangularSolve: shapes {a.shape} and {b.shape} do not form an augmented matrix")
+    vec = len(b.shape) == 1
+    saved = b.shape
+    try:
+        if vec:
+            b.shape = (saved[0], 1)      # an n-vector and an n x 1 matrix are the same record (Vector.hs:139-144)
+        aug = structure.append(2, a, b)
+    finally:
+        b.shape = saved
+    ech, rank = row_echelon_form(aug, a.shape[1])
+    ra, rb = structure.split(2, a.shape[1], ech)
+    aug.free()
+    ech.free()
+    if vec:
+        rb.shape = saved
+    return ra, rb, rank
+
+
 _ZIP = {"+": 0, "-": 1, "*": 2}
 
 

@@ -22,6 +22,7 @@ int t5o_trace(int dtype, int n, size_t batch, const void* A, void* OUT, int thre
 int t5o_poly_eval(int dtype, int n, const void* coeffs, int ncoef, size_t batch, const void* A, void* OUT, int threads);
 int t5o_char_poly(int dtype, int n, size_t batch, const void* A, void* OUT, int threads);
 int t5o_min_poly(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* degree, int threads);
+int t5o_row_echelon(int dtype, int m, int n, int pivot_cols, size_t batch, const void* A, void* OUT, uint8_t* rank, int threads);
 }
 
 static int failures = 0;
@@ -122,6 +123,22 @@ int main() {
         auto [mp, deg] = min_poly(A);
         expect_bits("minPoly", mp.to_list(), wm);
         expect_bits("minPoly degree", deg.to_list(), wdeg);
+    }
+    {   // rowEchelonForm on a 3 x 4 batch (every 5th item has an exactly repeated row), all columns / first 3 eligible
+        auto a = synth<double>(0, SA, 9, n * 12);
+        for (size_t i = 0; i < n; i += 5)
+            for (int j = 0; j < 4; ++j) a[i * 12 + 8 + j] = a[i * 12 + j];
+        auto A = Batch<double, 3, 4>::from_list(ctx, n, a);
+        std::vector<double> we(n * 12);
+        std::vector<uint8_t> wr(n);
+        t5o_row_echelon(0, 3, 4, 4, n, a.data(), we.data(), wr.data(), 1);
+        auto [e, rk] = row_echelon_form(A);
+        expect_bits("rowEchelonForm (Matrix 3 4 Double)", e.to_list(), we);
+        expect_bits("rowEchelonForm rank", rk.to_list(), wr);
+        t5o_row_echelon(0, 3, 4, 3, n, a.data(), we.data(), wr.data(), 1);
+        auto [e3, rk3] = row_echelon_form(A, 3);
+        expect_bits("triangularSolve ([A | b], 3 pivot columns)", e3.to_list(), we);
+        expect_bits("triangularSolve rank", rk3.to_list(), wr);
     }
     {   // prod n, vector-space ops, structural ops, host-array entries
         auto a = synth<double>(0, SA, 8, n * 6), b = synth<double>(0, SB, 8, n * 12);

@@ -191,11 +191,6 @@ def elim_inputs(dc, n, batch, nrhs=1):
 @pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_det_inverse_solve_bit_exact(ctx, dc, n, layout):
-    if layout == tb.SOA and n > 4:
-        A = ctx.empty((n, n), NPD[dc], 8, layout)
-        with pytest.raises(tb.Unsupported):
-            tb.det(A)
-        return
     for batch in (1, 300, 4099):
         a, b = elim_inputs(dc, n, batch)
         A = ctx.from_numpy(a, (n, n), layout)
@@ -228,7 +223,7 @@ def test_solve_matrix_rhs_equals_inverse(ctx, dc, n):
 
 @pytest.mark.parametrize("n", [5, 8])
 def test_row_per_lane_elimination_pivot_positions(ctx, n):
-    """Row-per-lane kernels (5 <= n <= 8): a zero pivot in EVERY column position with the first non-zero
+    """5 <= n <= 8 (record-per-thread and row-per-lane kernels): a zero pivot in EVERY column position with the first non-zero
     entry at every possible row below it, several swaps in one matrix, and singular columns at each k."""
     rng = np.random.default_rng(n)
     mats = []
@@ -256,6 +251,12 @@ def test_row_per_lane_elimination_pivot_positions(ctx, n):
     ox, ost = oracle.solve(a, b, n, 1)
     assert np.array_equal(st.to_numpy(), ost)
     assert_bits_equal(X.to_numpy(), ox.reshape(batch, n), "solve")
+    # matrix right-hand side: the row-per-lane kernel (det / inverse / vector solve above run record-per-thread)
+    bm = rng.standard_normal((batch, n, 3))
+    X, st = tb.solve(A, ctx.from_numpy(bm, (n, 3)))
+    ox, ost = oracle.solve(a, bm, n, 3)
+    assert np.array_equal(st.to_numpy(), ost)
+    assert_bits_equal(X.to_numpy(), ox.reshape(batch, n, 3), "solve, 3 right-hand sides")
 
 
 def test_det_rejects_int64_and_nonsquare(ctx):

@@ -69,11 +69,21 @@ def main():
             add(f"slice 2x3x4 [_,2,_] {tag}", B * (24 + 8) * es, lambda: st.slice_(T234, [None, 2, None]))
             add(f"permute_axes 2x3x4 (2,0,1) {tag}", B * 48 * es, lambda: st.permute_axes(T234, [2, 0, 1]))
             add(f"transpose 2x3x4 {tag}", B * 48 * es, lambda: tb.transpose(T234))
+            A5e = ctx.synthetic((5, 5), dt, B // 4, SEED, 14); b5e = ctx.synthetic((5,), dt, B // 4, SEED + 1, 14)
+            add(f"det 5x5 {tag}", (B // 4) * 26 * es, lambda: tb.det(A5e))
+            add(f"inverse 5x5 {tag}", (B // 4) * 50 * es, lambda: tb.inverse(A5e))
+            add(f"solve 5x5 {tag}", (B // 4) * 35 * es, lambda: tb.solve(A5e, b5e))
             add(f"det 6x6 {tag}", (B // 4) * 37 * es, lambda: tb.det(A6))
             add(f"inverse 6x6 {tag}", (B // 4) * 72 * es, lambda: tb.inverse(A6))
             add(f"solve 6x6 {tag}", (B // 4) * 48 * es, lambda: tb.solve(A6, b6))
             add(f"det 8x8 {tag}", (B // 4) * 65 * es, lambda: tb.det(A8))
+            b8 = ctx.synthetic((8,), dt, B // 4, SEED + 1, 15)
+            add(f"solve 8x8 {tag}", (B // 4) * 80 * es, lambda: tb.solve(A8, b8))
             add(f"inverse 8x8 {tag}", (B // 4) * 128 * es, lambda: tb.inverse(A8))
+            A45 = ctx.synthetic((4, 5), dt, B, SEED, 16)
+            add(f"rowEchelonForm 4x4 {tag}", B * (32 * es + 1), lambda: tb.row_echelon_form(A4))
+            add(f"rowEchelonForm 4x5 (triangularSolve) {tag}", B * (40 * es + 1), lambda: tb.row_echelon_form(A45, 4))
+            add(f"rowEchelonForm 8x8 {tag}", (B // 4) * (128 * es + 1), lambda: tb.row_echelon_form(A8))
             A5, B5 = ctx.synthetic((5, 5), dt, B, SEED, 7), ctx.synthetic((5, 5), dt, B, SEED, 8)
             add(f"matmul 5x5 {tag}", B * 75 * es, lambda: tb.matmul(A5, B5))
             add(f"matmul 4x4 (Double/Float) {tag}", B * 48 * es, lambda: tb.matmul(A4, B4))
