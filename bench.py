@@ -76,7 +76,21 @@ WORKLOADS = {
     "matmul5x5_f32_4M": dict(op="matmul", dtype="f32", m=5, k=5, n=5, batch=1 << 22, bytes=300, bound="hbm",
                              desc="4Mi 5x5 Float .*. (odd tiny shape, tile pipeline)"),
     "inverse8_f64_1M": dict(op="inverse", dtype="f64", n=8, batch=1 << 20, bytes=1025, bound="hbm",
-                            desc="1Mi 8x8 Double inverse (row-per-lane elimination, warp shuffles)"),
+                            desc="1Mi 8x8 Double inverse (record per thread; 128 doubles of working matrix: spills)"),
+    "det8_f64_1M": dict(op="det", dtype="f64", n=8, batch=1 << 20, bytes=520, bound="hbm",
+                        desc="1Mi 8x8 Double det (record per thread, compile-time unrolled elimination)"),
+    "solve8_f64_1M": dict(op="solve", dtype="f64", n=8, batch=1 << 20, bytes=641, bound="hbm",
+                          desc="1Mi 8x8 Double solve, one right-hand side (record per thread)"),
+    "inverse6_f64_1M": dict(op="inverse", dtype="f64", n=6, batch=1 << 20, bytes=577, bound="hbm",
+                            desc="1Mi 6x6 Double inverse (record per thread)"),
+    "minpoly4_f64_4M": dict(op="min_poly", dtype="f64", n=4, batch=1 << 22, bytes=169, bound="hbm",
+                            desc="4Mi 4x4 Double minPoly (Krylov elimination in registers, then charPoly)"),
+    "echelon4x4_f64_4M": dict(op="row_echelon", dtype="f64", rows=4, cols=4, batch=1 << 22, bytes=257, bound="hbm",
+                              desc="4Mi 4x4 Double rowEchelonForm (reduced; + rank byte)"),
+    "echelon4x5_f64_4M": dict(op="row_echelon", dtype="f64", rows=4, cols=5, pivot_cols=4, batch=1 << 22, bytes=321, bound="hbm",
+                              desc="4Mi 4x5 Double triangularSolve ([A | b], pivots in A)"),
+    "echelon6x7_f64_1M": dict(op="row_echelon", dtype="f64", rows=6, cols=7, batch=1 << 20, bytes=673, bound="hbm",
+                              desc="1Mi 6x7 Double rowEchelonForm (any-shape kernel: shared-memory resident)"),
     "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="hbm",
                               desc="64Ki 128x128 Float .*. on tcgen05 tensor cores (3xTF32 split, TMEM accumulators; 21 flop/B: HBM-bound)"),
     "matmul64_f32_256K": dict(op="matmul", dtype="f32", m=64, k=64, n=64, batch=1 << 18, bytes=49152, flops=524288, bound="hbm",
@@ -91,7 +105,8 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
-          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M"]
+          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
+          "inverse6_f64_1M", "inverse8_f64_1M", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 
@@ -254,6 +269,17 @@ class Step:
                 self.b = syn((n,), SEED_B, 5)
                 self.c, self.s = empty((n,)), empty((), np.uint8)
                 self.run = lambda: L.t5_solve(h, code, n, 1, self.a._h, self.b._h, self.c._h, self.s._h)
+        elif op == "min_poly":
+            n = w["n"]
+            self.a = syn((n, n), SEED_A, 7)
+            self.c, self.s = empty((n + 1,)), empty((), np.uint8)
+            self.run = lambda: L.t5_min_poly(h, code, n, self.a._h, self.c._h, self.s._h)
+        elif op == "row_echelon":
+            r, c = w["rows"], w["cols"]
+            pc = w.get("pivot_cols", c)
+            self.a = syn((r, c), SEED_A, 9)
+            self.c, self.s = empty((r, c)), empty((), np.uint8)
+            self.run = lambda: L.t5_row_echelon(h, code, r, c, pc, self.a._h, self.c._h, self.s._h)
         else:
             raise ValueError(op)
 
@@ -331,7 +357,7 @@ class HostCall:
 
     def __init__(self, ctx, tb, w):
         self.ctx, self.tb, self.w = ctx, tb, w
-        if w.get("layout") == "soa" or w["op"] in ("append", "dot_sum", "relayout"):
+        if w.get("layout") == "soa" or w["op"] in ("append", "dot_sum", "relayout", "min_poly", "row_echelon"):
             raise NotImplementedError("no host-array entry for this workload")
         self.batch = B = max(256, min(w["batch"], E2E_MAX_BYTES // w["bytes"]))
         dev = Step(ctx, tb, w, batch=B)                      # the same synthetic stream, generated on the device ...
@@ -446,6 +472,14 @@ class CpuWork:
             b = o.fill(dt, o.SEED_B, 5, B * n)
             self.one_pass = {"det": lambda: o.det(a, n, threads=T), "inverse": lambda: o.inverse(a, n, threads=T),
                              "solve": lambda: o.solve(a, b, n, 1, threads=T)}[op]
+        elif op == "min_poly":
+            n = w["n"]
+            a = o.fill(dt, o.SEED_A, 7, B * n * n)
+            self.one_pass = lambda: o.min_poly(a, n, threads=T)
+        elif op == "row_echelon":
+            r, c = w["rows"], w["cols"]
+            a = o.fill(dt, o.SEED_A, 9, B * r * c)
+            self.one_pass = lambda: o.row_echelon(a, r, c, w.get("pivot_cols", c), threads=T)
         else:
             raise NotImplementedError(op)
         self.one_pass()  # warm (page-in, thread start)

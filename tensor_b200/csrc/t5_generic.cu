@@ -281,6 +281,53 @@ int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t
     return ok();
 }
 
+// one-source, two-destination scatter (split): every input element belongs to exactly one of the two
+// results, so the input is read ONCE, coalesced (two gathers read it twice: 384 B of traffic for the
+// 256 algorithmic bytes of a 4x4 -> 4x3 | 4x1 Double split).  table[e] = offset in the first result, or
+// 0x80000000 | offset in the second.
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+scatter2_kernel(const T* __restrict__ in, T* __restrict__ out1, T* __restrict__ out2, const uint32_t* __restrict__ table,
+                unsigned d_in, unsigned d1, unsigned d2, unsigned long long count, int G) {
+    const unsigned step_q = THREADS / d_in, step_r = THREADS - step_q * d_in;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
+        const unsigned total = gc * d_in;
+        unsigned il = threadIdx.x / d_in, i = threadIdx.x - il * d_in;
+        const T* src = in + (size_t)g0 * d_in;
+        T* dst1 = out1 + (size_t)g0 * d1;
+        T* dst2 = out2 + (size_t)g0 * d2;
+        #pragma unroll 4
+        for (unsigned l = threadIdx.x; l < total; l += THREADS) {
+            const unsigned v = __ldg(table + i);
+            const T x = __ldg(src + l);
+            if (v & 0x80000000u) dst2[(size_t)il * d2 + (v & 0x7fffffffu)] = x;
+            else dst1[(size_t)il * d1 + v] = x;
+            il += step_q; i += step_r;
+            if (i >= d_in) { i -= d_in; ++il; }
+        }
+    }
+}
+
+int generic_scatter2(const Shard& s, int elem_bytes, size_t d_in, size_t d1, size_t d2, const uint32_t* table_dev,
+                     const void* A, void* O1, void* O2) {
+    constexpr int THREADS = 256;
+    if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
+    if (s.count == 0 || d_in == 0) return T5I_OK;
+    if (d_in > (1u << 28)) return T5I_UNSUPPORTED;
+    int G;
+    const int grid = gather_geometry(elem_bytes == 8 ? (const void*)scatter2_kernel<unsigned long long, THREADS>
+                                                     : (const void*)scatter2_kernel<unsigned, THREADS>, s.count, d_in, THREADS, &G);
+    if (elem_bytes == 8)
+        scatter2_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)A, (unsigned long long*)O1, (unsigned long long*)O2, table_dev, (unsigned)d_in, (unsigned)d1, (unsigned)d2, s.count, G);
+    else if (elem_bytes == 4)
+        scatter2_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)A, (unsigned*)O1, (unsigned*)O2, table_dev, (unsigned)d_in, (unsigned)d1, (unsigned)d2, s.count, G);
+    else
+        return T5I_UNSUPPORTED;
+    return ok();
+}
+
 int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O) {
     return generic_gather(s, elem_bytes, d, d, perm_dev, A, O);
 }

@@ -776,7 +776,9 @@ int t5_row_echelon(t5_ctx* c, int dtype, int rows, int cols, int pivot_cols, con
     for (int g = 0; g < c->ndev; ++g) {
         if (!A->count[g]) continue;
         CU(c, cudaSetDevice(c->dev[g]));
-        int r = generic_row_echelon(shard_of(c, A, g), dtype, rows, cols, pivot_cols, A->ptr[g], OUT->ptr[g], RANK->ptr[g]);
+        Shard s = shard_of(c, A, g);
+        int r = small_row_echelon(s, dtype, rows, cols, pivot_cols, A->ptr[g], OUT->ptr[g], RANK->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = generic_row_echelon(s, dtype, rows, cols, pivot_cols, A->ptr[g], OUT->ptr[g], RANK->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_row_echelon");
         c->launches++;
     }
@@ -1273,10 +1275,49 @@ int t5_append(t5_ctx* c, int dtype, int axis, int rank, const uint64_t* dimsA, c
 
 int t5_split(t5_ctx* c, int dtype, int axis, int rank, const uint64_t* dims, uint64_t first_extent,
              const t5_buf* IN, t5_buf* OUT1, t5_buf* OUT2) {
-    if (OUT1 == OUT2) return T5_ERR_INVALID;
-    std::vector<uint64_t> prm{(uint64_t)axis, first_extent};
-    CHECK(structural_unary(c, dtype, 1, rank, dims, prm, IN, OUT1, "t5_split"));
-    return structural_unary(c, dtype, 2, rank, dims, prm, IN, OUT2, "t5_split");
+    if (!c || rank < 0 || rank > 16 || (rank && !dims)) return T5_ERR_INVALID;
+    if (OUT1 == OUT2 || OUT1 == IN || OUT2 == IN) return T5_ERR_INVALID;
+    const int es = dtype_size(dtype);
+    if (es != 4 && es != 8) return T5_ERR_UNSUPPORTED;
+    std::vector<uint64_t> dv(dims, dims + rank), prm{(uint64_t)axis, first_extent};
+    std::vector<uint32_t> t1, t2; std::vector<uint64_t> od;
+    CHECK(build_structural(1, dv, prm, t1, od));
+    CHECK(build_structural(2, dv, prm, t2, od));
+    const size_t d_in = prod_of(dv);
+    CHECK(check(c, IN, dtype, d_in, nullptr));
+    CHECK(check(c, OUT1, dtype, t1.size(), IN));
+    CHECK(check(c, OUT2, dtype, t2.size(), IN));
+    if (IN->layout != T5_AOS) return T5_ERR_UNSUPPORTED;
+    if (es == 4) {
+        // 4-byte elements: the scatter's short store runs cost more than the second read saves
+        // (4Mi 4x4 -> 4x3 | 4x1: Float 0.145 ms as two gathers vs 0.160 ms; Double 0.278 vs 0.211 ms)
+        CHECK(structural_unary(c, dtype, 1, rank, dims, prm, IN, OUT1, "t5_split"));
+        return structural_unary(c, dtype, 2, rank, dims, prm, IN, OUT2, "t5_split");
+    }
+    // the two gather tables partition the input: invert them into one scatter table, read the input once
+    std::vector<uint32_t> sc(d_in, 0);
+    for (size_t o = 0; o < t1.size(); ++o) sc[t1[o]] = (uint32_t)o;
+    for (size_t o = 0; o < t2.size(); ++o) sc[t2[o]] = 0x80000000u | (uint32_t)o;
+    std::vector<uint64_t> key{0xFFFFFFFEull, (uint64_t)rank};
+    key.insert(key.end(), dv.begin(), dv.end());
+    key.insert(key.end(), prm.begin(), prm.end());
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!IN->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        auto it = c->perm_cache.find(key);
+        if (it == c->perm_cache.end()) it = c->perm_cache.emplace(key, std::vector<uint32_t*>(T5_MAX_DEVICES, nullptr)).first;
+        if (!it->second[g]) {
+            uint32_t* p = nullptr;
+            CU(c, cudaMalloc(&p, (sc.size() ? sc.size() : 1) * 4));
+            CU(c, cudaMemcpy(p, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
+            it->second[g] = p;
+        }
+        int r = generic_scatter2(shard_of(c, IN, g), es, d_in, t1.size(), t2.size(), it->second[g], IN->ptr[g], OUT1->ptr[g], OUT2->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_split");
+        c->launches++;
+    }
+    return T5_OK;
 }
 
 int t5_at(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const uint64_t* index, const t5_buf* A, t5_buf* OUT) {

@@ -44,6 +44,8 @@ int small_trace(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_poly_eval(const Shard& s, int dtype, int n, const void* coeffs_host, int ncoef, const void* A, void* O);
 int small_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree);
+// t5_echelon.cu: rowEchelonForm of the small fixed shapes (n x n, n x (n+1), n x 2n for n = 2..4), AoS and SoA
+int small_row_echelon(const Shard& s, int dtype, int rows, int cols, int pivot_cols, const void* A, void* O, void* rank);
 
 // ---- t5_mid_ops.cu: row-per-thread contractions for 0.25-4 KiB records (8x8, 16x16, ...) -----
 int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
@@ -56,6 +58,7 @@ int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* pe
 // out[b][i] = in[b][table[i]] with d_in != d_out allowed (structural gathers); gather2: two sources (append)
 int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, const uint32_t* table_dev, const void* A, void* O);
 int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d_out, const uint32_t* table_dev, const void* A, const void* B, void* O);
+int generic_scatter2(const Shard& s, int elem_bytes, size_t d_in, size_t d1, size_t d2, const uint32_t* table_dev, const void* A, void* O1, void* O2);
 int generic_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs, const void* A, const void* B, void* X, void* status);
 // SquareMatrix extras for any n <= 8 (min_poly: n <= 6); coeffs_dev holds ncoef elements of dtype on the device

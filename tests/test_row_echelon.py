@@ -137,6 +137,36 @@ def test_row_echelon_bit_exact(ctx, dname, m, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dname", ["f64", "f32"])
+@pytest.mark.parametrize("m,n", [(2, 2), (3, 3), (4, 4), (2, 3), (3, 4), (4, 5), (2, 4), (3, 6), (4, 8)])
+def test_row_echelon_register_shapes_soa_and_all_deficient(ctx, dname, m, n):
+    """The shapes with a register-resident kernel: SoA layout, and batches in which EVERY item is rank-deficient
+    (the run-time rank then selects the off-diagonal step instances for whole warps)."""
+    tb = _tb()
+    a = mats(dname, m, n, 1500, op_id=17)
+    got, rank = tb.row_echelon_form(ctx.from_numpy(a, (m, n), tb.SOA))
+    want, wrank = oracle.row_echelon(a, m, n)
+    assert got.layout == tb.SOA
+    assert np.array_equal(rank.to_numpy(), wrank)
+    assert np.array_equal(bits(got.to_numpy()), bits(want))
+    rng = np.random.default_rng(n)
+    for variant in range(4):
+        d = a.copy()
+        if variant == 0:
+            d[:, :, 0] = 0                                   # no pivot in the first column: the rank lags from the start
+        elif variant == 1:
+            d[:, :, min(1, n - 1)] = 0
+        elif variant == 2:
+            d[:, m - 1] = d[:, 0]                            # repeated row: an exact zero row at the end
+        else:
+            d[np.arange(1500), rng.integers(0, m, 1500)] = 0  # a zero row somewhere
+        got, rank = tb.row_echelon_form(ctx.from_numpy(d, (m, n)))
+        want, wrank = oracle.row_echelon(d, m, n)
+        assert np.array_equal(rank.to_numpy(), wrank), variant
+        assert np.array_equal(bits(got.to_numpy()), bits(want)), variant
+
+
+@pytest.mark.gpu
 def test_row_echelon_special_values(ctx):
     """Signed zeros, infinities, NaN and denormals go through the same operations as on the CPU."""
     tb = _tb()
@@ -192,7 +222,7 @@ def test_row_echelon_errors(ctx):
     with pytest.raises(tb.Unsupported):
         tb.row_echelon_form(ctx.empty((4, 17), np.float64, 4))                   # cols <= 16
     with pytest.raises(tb.Unsupported):
-        tb.row_echelon_form(ctx.empty((3, 3), np.float64, 4, tb.SOA))            # AoS only
+        tb.row_echelon_form(ctx.empty((5, 3), np.float64, 4, tb.SOA))            # SoA: the register-resident shapes only
     with pytest.raises(tb.WrongListLength):
         tb.row_echelon_form(ctx.empty((3, 3), np.float64, 4), 4)                 # more pivot columns than columns
     with pytest.raises(tb.WrongListLength):
