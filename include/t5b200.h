@@ -177,6 +177,11 @@ int t5_row_echelon(t5_ctx* ctx, int dtype, int rows, int cols, int pivot_cols, c
  * op: 0 = a + b, 1 = a - b, 2 = a * b (Hadamard); t5_scale multiplies by *scalar. */
 int t5_zip(t5_ctx* ctx, int dtype, int op, const t5_buf* A, const t5_buf* B, t5_buf* C);
 int t5_scale(t5_ctx* ctx, int dtype, const void* scalar, const t5_buf* A, t5_buf* C);
+/* `pure` of the Applicative instance (src/Data/Tensor/Vector.hs:185-188), generalised to a whole
+ * record: every item of OUT becomes a copy of `record`, a HOST array of OUT's per-item element
+ * count.  A record of equal elements is `pure a`; the identity matrix is the old SquareMatrix
+ * `unit`; zeros are the VectorSpace `zero`.  All element types, AoS and SoA. */
+int t5_replicate(t5_ctx* ctx, int dtype, const void* record, t5_buf* OUT);
 
 
 /* ---- structural operations ---------------------------------------------------

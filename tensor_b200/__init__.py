@@ -8,7 +8,7 @@ from ._lib import AOS, SOA, F64, F32, I64, U8, LibraryMissing, partition  # noqa
 from .device import (Batch, Context, DeviceError, PinnedArray, TensorException,  # noqa: F401
                      Unsupported, WrongListLength)
 from .linear_algebra import (char_poly, det, dot, dot_sum, inverse, matmul, matmul_host, min_poly,  # noqa: F401
-                             poly_eval, prod, row_echelon_form, scale, solve, tensor_product, tr, transpose,
-                             triangular_solve, zip_with)
+                             poly_eval, prod, pure, replicate, row_echelon_form, scale, solve, tensor_product, tr, transpose,
+                             triangular_solve, unit, zip_with)
 from . import host, structure, synthetic  # noqa: F401
 from .structure import Nested  # noqa: F401

@@ -59,6 +59,7 @@ SIGNATURES = {
     "t5_row_echelon": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "t5_zip": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_scale": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "t5_replicate": (_i, [_vp, _i, _vp, _vp]),
     "t5_append": (_i, [_vp, _i, _i, _i, _u64p, _u64p, _vp, _vp, _vp]),
     "t5_split": (_i, [_vp, _i, _i, _i, _u64p, _u64, _vp, _vp, _vp]),
     "t5_at": (_i, [_vp, _i, _i, _u64p, _u64p, _vp, _vp]),

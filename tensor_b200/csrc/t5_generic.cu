@@ -611,6 +611,60 @@ int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, v
 }
 
 // =====================================================================================
+// pure / replicate (Applicative `pure`, src/Data/Tensor/Vector.hs:185-188; also `zero`, `unit`,
+// basis vectors): every item of the batch becomes a copy of one d-element record.  Write-only
+// stream; the record is read through the read-only cache.  AoS: flat index -> element by constant
+// steps (no division in the loop); SoA: row e is the constant rec[e].
+// =====================================================================================
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+replicate_kernel(const T* __restrict__ rec, T* __restrict__ out, unsigned d, unsigned long long total) {
+    const unsigned long long step = (unsigned long long)gridDim.x * THREADS;
+    unsigned long long i = (unsigned long long)blockIdx.x * THREADS + threadIdx.x;
+    unsigned e = (unsigned)(i % d);
+    const unsigned se = (unsigned)(step % d);
+    #pragma unroll 4
+    for (; i < total; i += step) {
+        out[i] = __ldg(rec + e);
+        e += se;
+        if (e >= d) e -= d;
+    }
+}
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+replicate_soa_kernel(const T* __restrict__ rec, T* __restrict__ out, unsigned d, unsigned long long count, unsigned long long stride) {
+    for (unsigned e = blockIdx.y; e < d; e += gridDim.y) {
+        const T v = __ldg(rec + e);
+        T* row = out + (size_t)e * stride;
+        for (unsigned long long b = (unsigned long long)blockIdx.x * THREADS + threadIdx.x; b < count; b += (unsigned long long)gridDim.x * THREADS)
+            row[b] = v;
+    }
+}
+
+int generic_replicate(const Shard& s, int elem_bytes, size_t d, const void* rec_dev, void* O) {
+    constexpr int THREADS = 256;
+    if (s.count == 0 || d == 0) return T5I_OK;
+    if (d > (1u << 28)) return T5I_UNSUPPORTED;
+    if (elem_bytes != 4 && elem_bytes != 8) return T5I_UNSUPPORTED;
+    if (s.layout == T5L_SOA) {
+        const size_t bx = (s.count + THREADS - 1) / THREADS;
+        dim3 grid((unsigned)(bx < 4096 ? bx : 4096), (unsigned)(d < 64 ? d : 64));
+        if (elem_bytes == 8) replicate_soa_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)rec_dev, (unsigned long long*)O, (unsigned)d, s.count, s.soa_stride);
+        else replicate_soa_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)rec_dev, (unsigned*)O, (unsigned)d, s.count, s.soa_stride);
+        return ok();
+    }
+    const unsigned long long total = (unsigned long long)s.count * d;
+    if (elem_bytes == 8) {
+        const int grid = resident_grid((const void*)replicate_kernel<unsigned long long, THREADS>, THREADS, (total + THREADS - 1) / THREADS);
+        replicate_kernel<unsigned long long, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned long long*)rec_dev, (unsigned long long*)O, (unsigned)d, total);
+    } else {
+        const int grid = resident_grid((const void*)replicate_kernel<unsigned, THREADS>, THREADS, (total + THREADS - 1) / THREADS);
+        replicate_kernel<unsigned, THREADS><<<grid, THREADS, 0, s.stream>>>((const unsigned*)rec_dev, (unsigned*)O, (unsigned)d, total);
+    }
+    return ok();
+}
+
+// =====================================================================================
 // rowEchelonForm / triangularSolve (specification: oracle/t5_oracle.cpp
 // row_echelon_item): reduced row echelon form of any rows x cols matrix, rows <= 8, cols <= 16.
 // The pivot ROW is a run-time quantity here (a column without a pivot does not advance it), so a

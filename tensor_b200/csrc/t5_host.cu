@@ -765,6 +765,31 @@ int t5_min_poly(t5_ctx* c, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_bu
     return T5_OK;
 }
 
+int t5_replicate(t5_ctx* c, int dtype, const void* record, t5_buf* OUT) {
+    if (!c || !OUT || OUT->ctx != c) return T5_ERR_INVALID;
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return T5_ERR_UNSUPPORTED;
+    if (OUT->dtype != dtype) return T5_ERR_INVALID;
+    if (OUT->elems && !record) return T5_ERR_INVALID;
+    const size_t rbytes = OUT->elems * dtype_size(dtype);
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!OUT->count[g] || !rbytes) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        // the record rides in the per-device parameter buffer polyEval uses (stream-ordered copy)
+        if (c->coef_cap[g] < rbytes) {
+            if (c->coef[g]) { CU(c, cudaStreamSynchronize(c->stream[g])); CU(c, cudaFree(c->coef[g])); c->coef[g] = nullptr; c->coef_cap[g] = 0; }
+            const size_t cap = rbytes < 4096 ? 4096 : rbytes;
+            CU(c, cudaMalloc(&c->coef[g], cap));
+            c->coef_cap[g] = cap;
+        }
+        CU(c, cudaMemcpyAsync(c->coef[g], record, rbytes, cudaMemcpyHostToDevice, c->stream[g]));
+        int r = generic_replicate(shard_of(c, OUT, g), dtype_size(dtype), OUT->elems, c->coef[g], OUT->ptr[g]);
+        if (r != T5I_OK) return map_internal(c, r, "t5_replicate");
+        c->launches++;
+    }
+    return T5_OK;
+}
+
 int t5_row_echelon(t5_ctx* c, int dtype, int rows, int cols, int pivot_cols, const t5_buf* A, t5_buf* OUT, t5_buf* RANK) {
     if (!c) return T5_ERR_INVALID;
     if (dtype != T5_F64 && dtype != T5_F32) return T5_ERR_UNSUPPORTED;

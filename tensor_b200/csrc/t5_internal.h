@@ -68,6 +68,7 @@ int generic_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree);
 int generic_row_echelon(const Shard& s, int dtype, int rows, int cols, int pivot_cols, const void* A, void* O, void* rank);
 int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, const void* B, void* C);
+int generic_replicate(const Shard& s, int elem_bytes, size_t d, const void* rec_dev, void* O);
 int generic_scale(const Shard& s, int dtype, const void* scalar_host, size_t elems, const void* A, void* C);
 // per-device partial of sum_b dot(x_b, y_b): *partial_dev is double (F64/F32) or int64
 int dot_sum_partial(const Shard& s, int dtype, size_t elems, const void* X, const void* Y, void* scratch_dev, void* partial_dev);

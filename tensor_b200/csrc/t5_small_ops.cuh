@@ -372,10 +372,8 @@ struct MinPolyOp {
     }
 };
 
-// inverse(A) = solve(A, I).  (Eliminating [A | I] in two column blocks to shorten the working
-// matrix was tried for n >= 5: the input record and the finished block stay live across the
-// blocks, so the register peak does not drop and the extra pass made every size slower.)
-template <class T, int N>
+// inverse(A) = solve(A, I) for n <= 4: the whole [A | I] working matrix in registers.
+template <class T, int N, class = void>
 struct InverseOp {
     using In0 = Rec<T, N * N>; using In1 = NoRec;
     using Out0 = Rec<T, N * N>; using Out1 = Rec<unsigned char, 1>;
@@ -389,6 +387,97 @@ struct InverseOp {
             for (int c = 0; c < N; ++c) w[i][N + c] = (i == c) ? T(1) : T(0);
         }
         solve_regs<T, N, N>(w, x, status);
+    }
+};
+
+// n >= 5: [A | I] is N x 2N (128 doubles for 8x8) and the result another N x N, more than a thread
+// has registers for.  The columns of the right-hand side never interact, so the elimination is split
+// in time instead: (1) eliminate A alone, KEEPING each multiplier f(i,k) in the entry it zeroes (row
+// swaps move whole rows, multipliers included) and the pivot row chosen in column k; (2) replay those
+// row operations on a block of identity columns at a time: a row carries its right-hand side through every
+// swap, so the columns start as the PERMUTED identity (integer bookkeeping) and then see
+// x[i] -= f(i,k) x[k] for i > k, k ascending, with no swap left in the arithmetic; back-substitute, and
+// hand the finished entries to the writer before the next block starts.  Every element sees the
+// operations of the one-pass elimination in the same order (bit-identical to the oracle);
+// the live set is N x N + 2N + the reciprocals (8x8 Double: ~100 doubles instead of 192+).
+template <class T, int N>
+struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
+    static constexpr bool streams_out0 = true;
+    static constexpr int CB = 2;   // wider blocks (N/2, N) measured no faster for Double and slower for Float (registers)
+    using In0 = Rec<T, N * N>; using In1 = NoRec;
+    using Out0 = Rec<T, N * N>; using Out1 = Rec<unsigned char, 1>;
+    template <class W>
+    __device__ __forceinline__ static void run_stream(const T* a, const unsigned char*, const W& out, unsigned char* status) {
+        T w[N][N];
+        #pragma unroll
+        for (int i = 0; i < N; ++i)
+            #pragma unroll
+            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+        int piv[N];
+        Recip<T> rc[N];
+        bool singular = false;
+        static_for<0, N>([&](auto k_) {
+            constexpr int k = decltype(k_)::value;
+            piv[k] = k;
+            if (k + 1 < N && w[k][k] == T(0)) {
+                static_for<k + 1, N>([&](auto r_) {
+                    constexpr int r = decltype(r_)::value;
+                    const bool sw = (w[k][k] == T(0)) && (w[r][k] != T(0));
+                    #pragma unroll
+                    for (int j = 0; j < N; ++j) {      // whole rows: the multipliers of earlier steps travel with their row
+                        T x = w[k][j], y = w[r][j];
+                        w[k][j] = sw ? y : x;
+                        w[r][j] = sw ? x : y;
+                    }
+                    piv[k] = sw ? r : piv[k];
+                });
+            }
+            singular = singular || (w[k][k] == T(0));
+            rc[k] = Recip<T>(w[k][k]);
+            static_for<k + 1, N>([&](auto i_) {
+                constexpr int i = decltype(i_)::value;
+                const T f = rc[k].div(w[i][k]);
+                #pragma unroll
+                for (int j = k + 1; j < N; ++j) w[i][j] = w[i][j] - f * w[k][j];
+                w[i][k] = f;
+            });
+        });
+        const bool ok = !singular;
+        static_for<0, (N + CB - 1) / CB>([&](auto blk_) {
+            constexpr int c0 = decltype(blk_)::value * CB;
+            constexpr int cb = (N - c0 < CB) ? N - c0 : CB;
+            // row i of the permuted identity: a row keeps its right-hand side through every swap, so
+            // column c0+c starts as e_{src} with the 1 wherever original row c0+c ended up
+            T x[N][cb];
+            #pragma unroll
+            for (int c = 0; c < cb; ++c) {
+                int pos = c0 + c;
+                #pragma unroll
+                for (int k = 0; k < N; ++k) pos = (pos == k) ? piv[k] : ((pos == piv[k]) ? k : pos);
+                #pragma unroll
+                for (int i = 0; i < N; ++i) x[i][c] = (i == pos) ? T(1) : T(0);
+            }
+            static_for<0, N>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                static_for<k + 1, N>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    #pragma unroll
+                    for (int c = 0; c < cb; ++c) x[i][c] = x[i][c] - w[i][k] * x[k][c];
+                });
+            });
+            static_for<0, N>([&](auto kk_) {
+                constexpr int k = N - 1 - decltype(kk_)::value;
+                static_for<0, cb>([&](auto c_) {
+                    constexpr int c = decltype(c_)::value;
+                    T s = T(0);
+                    #pragma unroll
+                    for (int j = k + 1; j < N; ++j) s = s + w[k][j] * x[j][c];
+                    x[k][c] = rc[k].div(x[k][c] - s);
+                    out.template put<k * N + c0 + c>(ok ? x[k][c] : T(0));
+                });
+            });
+        });
+        status[0] = ok ? 0 : 1;
     }
 };
 

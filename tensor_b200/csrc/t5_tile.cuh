@@ -48,6 +48,14 @@ __device__ __forceinline__ void run_op(const A0* r0, const A1* r1, B0* w0, B1* w
     else Op::run(r0, r1, w0, w1);
 }
 
+// Ops whose result record does not fit in registers next to their working set (the 7x7 / 8x8 Double
+// inverse: 64 + 64 doubles) declare `streams_out0` and provide
+//   run_stream(const In0::type*, const In1::type*, Writer&, Out1::type*)
+// which hands each result element to the writer as soon as it is final: into the thread's own
+// (already consumed) input slot in the AoS pipeline, straight to its row in the SoA one.
+template <class Op, class = void> struct StreamsOut : std::false_type {};
+template <class Op> struct StreamsOut<Op, std::void_t<decltype(Op::streams_out0)>> : std::true_type {};
+
 constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
 
 template <class T, int N>
@@ -72,6 +80,12 @@ struct Rec {
         if constexpr (vec16 && (swz || pad)) return chunk_off(ch / cpi, ch % cpi);
         else return ch << 4;
     }
+    // byte offset of element e of record `item` (for ops that write results element by element)
+    __device__ __forceinline__ static int elem_off(int item, int e) {
+        constexpr int sz = (int)sizeof(T);
+        if constexpr (vec16) return chunk_off(item, (e * sz) >> 4) + ((e * sz) & 15);
+        else return item * stride + e * sz;
+    }
     __device__ __forceinline__ static void load(const unsigned char* stage, int item, void* regs) {
         if constexpr (vec16) {
             #pragma unroll
@@ -94,6 +108,23 @@ using NoRec = Rec<unsigned char, 0>;
 template <class R>
 struct RegArr {
     alignas(16) typename R::type v[R::n > 0 ? R::n : 1];
+};
+
+template <class R>
+struct SlotWriter {
+    unsigned char* stage;
+    int item;
+    template <int E>
+    __device__ __forceinline__ void put(typename R::type v) const {
+        *reinterpret_cast<typename R::type*>(stage + R::elem_off(item, E)) = v;
+    }
+};
+template <class T>
+struct SoaWriter {
+    T* base;                        // row 0 of this item
+    unsigned long long stride;
+    template <int E>
+    __device__ __forceinline__ void put(T v) const { base[(size_t)E * stride] = v; }
 };
 
 struct TileArgs {
@@ -264,8 +295,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
                 RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
                 if constexpr (I0::bytes > 0) I0::load(s0, it, r0.v);
                 if constexpr (I1::bytes > 0) I1::load(s1, it, r1.v);
-                run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
-                if constexpr (O0::bytes > 0) {
+                if constexpr (StreamsOut<Op>::value) {
+                    static_assert(C::OUT0 == 0, "streamed results go in place over the first input record");
+                    SlotWriter<I0> wr{so, it};
+                    Op::run_stream(r0.v, r1.v, wr, w1.v);
+                } else {
+                    run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
+                }
+                if constexpr (O0::bytes > 0 && !StreamsOut<Op>::value) {
                     if constexpr (C::OUT0 == -1) stg_direct<O0::bytes>(g_out0 + (first + it) * O0::bytes, w0.v);
                     else if constexpr (C::OUT0 == 0) I0::store(so, it, w0.v);   // in place: same thread, same slot
                     else if constexpr (C::OUT0 == 1) I1::store(so, it, w0.v);
@@ -399,10 +436,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) soa_tile_kernel(SoaArgs a
                 for (int e = 0; e < I0::n; ++e) r0.v[e] = s0[e * TILE + it];
                 #pragma unroll
                 for (int e = 0; e < I1::n; ++e) r1.v[e] = s1[e * TILE + it];
-                run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
                 const unsigned long long b = first + it;
-                #pragma unroll
-                for (int e = 0; e < O0::n; ++e) out0[(size_t)e * a.stride + b] = w0.v[e];
+                if constexpr (StreamsOut<Op>::value) {
+                    SoaWriter<typename O0::type> wr{out0 + b, a.stride};
+                    Op::run_stream(r0.v, r1.v, wr, w1.v);
+                } else {
+                    run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
+                    #pragma unroll
+                    for (int e = 0; e < O0::n; ++e) out0[(size_t)e * a.stride + b] = w0.v[e];
+                }
                 #pragma unroll
                 for (int e = 0; e < O1::n; ++e) out1[(size_t)e * a.stride + b] = w1.v[e];
             }

@@ -86,6 +86,14 @@ class Batch {
         ctx.check(t5_upload(b.buf(), xs.data(), xs.size() * sizeof(T)), "t5_upload");
         return b;
     }
+    // every item a copy of one record; a record of equal elements is `pure a` (Vector.hs:185-188)
+    static Batch replicate(const Context& ctx, size_t count, const std::vector<T>& record) {
+        if (record.size() != shape::size) throw WrongListLength();
+        Batch b(ctx, count);
+        ctx.check(t5_replicate(ctx.handle(), dtype_of<T>::value, record.data(), b.buf()), "t5_replicate");
+        return b;
+    }
+    static Batch pure(const Context& ctx, size_t count, T a) { return replicate(ctx, count, std::vector<T>(shape::size, a)); }
     // toList (Vector.hs:367)
     std::vector<T> to_list() const {
         std::vector<T> out(count_ * shape::size);
@@ -194,6 +202,13 @@ std::pair<Batch<T, N + 1>, Batch<uint8_t>> min_poly(const Batch<T, N, N>& a) {  
     Batch<uint8_t> deg(a.ctx(), a.count());
     a.ctx().check(t5_min_poly(a.ctx().handle(), dtype_of<T>::value, (int)N, a.buf(), c.buf(), deg.buf()), "t5_min_poly");
     return {c, deg};
+}
+// unit: a batch of identity matrices (the old SquareMatrix method)
+template <class T, size_t N>
+Batch<T, N, N> unit(const Context& ctx, size_t count) {
+    std::vector<T> id(N * N, T(0));
+    for (size_t i = 0; i < N; ++i) id[i * N + i] = T(1);
+    return Batch<T, N, N>::replicate(ctx, count, id);
 }
 // rowEchelonForm (reduced; pivots looked for in the first pivot_cols columns, default all): (form, rank)
 template <class T, size_t R, size_t C>

@@ -81,6 +81,8 @@ foreign import ccall safe "t5_zip"
   c_zip :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt
 foreign import ccall safe "t5_scale"
   c_scale :: Ptr Ctx -> CInt -> Ptr () -> Ptr Buf -> Ptr Buf -> IO CInt
+foreign import ccall safe "t5_replicate"
+  c_replicate :: Ptr Ctx -> CInt -> Ptr () -> Ptr Buf -> IO CInt
 
 -- the rest of the old SquareMatrix class (CHANGELOG.md:28-29; SURVEY.md §8f-4)
 foreign import ccall safe "t5_trace"

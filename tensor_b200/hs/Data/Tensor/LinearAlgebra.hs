@@ -28,9 +28,10 @@ module Data.Tensor.LinearAlgebra
     ( MatrixProduct(..), DotProduct(..), TensorProduct(..), Transpose(..)
     , SquareMatrix(..), LinearSystem(..)
     , dotSum, prodN, tr, polyEval, charPoly, minPoly, rowEchelonForm, echelonWith
-    , addB, subB, hadamardB, scaleB
+    , addB, subB, hadamardB, scaleB, replicateB, pureB, unitB
     ) where
 
+import           Control.Exception     (throwIO)
 import           Data.Proxy
 import           Data.Singletons
 import           Data.Word
@@ -42,7 +43,8 @@ import qualified Data.Vector.Storable  as S
 import           Foreign.Ptr
 import           Foreign.Storable
 
-import           Data.MultiIndex       (PI (..))
+import           Data.MultiIndex       (PI (..), Shape, fromShape)
+import           Data.Tensor           (TensorException (WrongListLength))
 import           Data.Tensor.Device
 import           Data.Tensor.Device.FFI
 
@@ -263,6 +265,26 @@ addB, subB, hadamardB :: (SingI is, DeviceElt e) => Batch is e -> Batch is e -> 
 addB = zipB 0
 subB = zipB 1
 hadamardB = zipB 2
+
+-- | Every item a copy of one tensor given as its row-major element list (length checked against the
+-- shape like 'fromList', src/Data/Tensor/Vector.hs:362-366).
+replicateB :: forall is e. (SingI is, DeviceElt e) => Context -> Int -> [e] -> IO (Batch is e)
+replicateB ctx@(Context h) n xs = do
+    o <- newBatch ctx n
+    let d = fromIntegral (product (batchShape o)) :: Int
+    if length xs /= d then throwIO WrongListLength else
+        S.unsafeWith (S.fromList xs) $ \px -> unsafeWithBatch o $ \po ->
+            c_replicate h (code (Proxy :: Proxy e)) (castPtr px) po >>= checkRC ctx "t5_replicate"
+    return o
+
+-- | @pure a@ of the Applicative instance (src/Data/Tensor/Vector.hs:185-188) on a batch.
+pureB :: forall is e. (SingI is, DeviceElt e) => Context -> Int -> e -> IO (Batch is e)
+pureB ctx n a = replicateB ctx n (replicate (fromIntegral (product (fromShape (sing :: Shape is)))) a)
+
+-- | @unit@ of the old @SquareMatrix@ class: a batch of identity matrices.
+unitB :: forall i e. (SingI i, DeviceElt e, Num e) => Context -> Int -> IO (Batch '[i, i] e)
+unitB ctx n = let k = fromIntegral (head (fromShape (sing :: Shape '[i, i]))) :: Int
+              in replicateB ctx n [if r == c then 1 else 0 | r <- [1 .. k], c <- [1 .. k]]
 
 scaleB :: forall is e. (SingI is, DeviceElt e) => e -> Batch is e -> IO (Batch is e)
 scaleB k a = do

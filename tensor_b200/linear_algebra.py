@@ -16,7 +16,7 @@ from typing import Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import U8
+from ._lib import AOS, U8
 from .device import Batch, Context, NP_OF, WrongListLength, check
 
 
@@ -224,6 +224,29 @@ def scale(k, a: Batch) -> Batch:
     kk = np.asarray([k], dtype=NP_OF[a.dtype])
     check(_lib.lib().t5_scale(a.ctx._h, a.dtype, kk.ctypes.data_as(ctypes.c_void_p), a._h, out._h), a.ctx)
     return out
+
+
+def replicate(ctx: Context, record, shape, batch: int, dtype=None, layout: int = AOS) -> Batch:
+    """Every item a copy of ``record`` (one tensor of ``shape``, row-major): the record form of ``pure``."""
+    rec = np.ascontiguousarray(record, dtype=dtype)
+    shape = tuple(int(x) for x in shape)
+    out = ctx.empty(shape, rec.dtype, batch, layout)
+    if rec.size != out.elems:
+        out.free()
+        raise WrongListLength(f"replicate: record of {rec.size} elements for shape {shape}")
+    check(_lib.lib().t5_replicate(ctx._h, out.dtype, rec.ctypes.data_as(ctypes.c_void_p), out._h), ctx)
+    return out
+
+
+def pure(ctx: Context, value, shape, dtype, batch: int, layout: int = AOS) -> Batch:
+    """``pure a`` (Vector.hs:185-188): all components equal to ``value``."""
+    n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+    return replicate(ctx, np.full((n,), value, dtype=dtype), shape, batch, dtype, layout)
+
+
+def unit(ctx: Context, n: int, dtype, batch: int, layout: int = AOS) -> Batch:
+    """``unit``: a batch of n x n identity matrices (the old SquareMatrix method)."""
+    return replicate(ctx, np.eye(n, dtype=dtype), (n, n), batch, dtype, layout)
 
 
 def matmul_host(ctx: Context, a: np.ndarray, b: np.ndarray, m: int, k: int, n: int, out: np.ndarray) -> np.ndarray:

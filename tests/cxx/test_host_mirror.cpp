@@ -124,6 +124,17 @@ int main() {
         expect_bits("minPoly", mp.to_list(), wm);
         expect_bits("minPoly degree", deg.to_list(), wdeg);
     }
+    {   // pure / unit: A .*. unit == A .*. I bit for bit, pure a is constant
+        auto a = synth<double>(0, SA, 10, n * 9);
+        auto A = Batch<double, 3, 3>::from_list(ctx, n, a);
+        auto U = unit<double, 3>(ctx, n);
+        std::vector<double> eye(n * 9, 0.0), want(n * 9);
+        for (size_t i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) eye[i * 9 + d * 4] = 1.0;
+        expect_bits("unit", U.to_list(), eye);
+        t5o_matmul(0, 3, 3, 3, n, a.data(), eye.data(), want.data(), 1);
+        expect_bits("A .*. unit", (A * U).to_list(), want);
+        expect_bits("pure 2.5", Batch<double, 2, 2>::pure(ctx, n, 2.5).to_list(), std::vector<double>(n * 4, 2.5));
+    }
     {   // rowEchelonForm on a 3 x 4 batch (every 5th item has an exactly repeated row), all columns / first 3 eligible
         auto a = synth<double>(0, SA, 9, n * 12);
         for (size_t i = 0; i < n; i += 5)

@@ -392,6 +392,28 @@ def test_elementwise(ctx, dc):
             assert_bits_equal(tb.scale(k, A).to_numpy().ravel(), k * a, "scale")
 
 
+@pytest.mark.parametrize("dc", ALL)
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_pure_replicate_unit(ctx, dc, layout):
+    """pure (Vector.hs:185-188) / replicate / unit: every item equals the record, in either layout."""
+    dt = NPD[dc]
+    for batch, shape in ((1, (3, 3)), (4099, (2, 3, 4)), (70001, (5,)), (300, ()), (0, (4, 4))):
+        rec, _ = inputs(dc, 15, 1, int(np.prod(shape)) if shape else 1)
+        R = tb.replicate(ctx, rec, shape, batch, dt, layout)
+        assert R.shape == tuple(shape) and R.batch == batch and R.layout == layout
+        assert_bits_equal(R.to_numpy().reshape(batch, rec.size), np.broadcast_to(rec, (batch, rec.size)).copy(), "replicate")
+    P = tb.pure(ctx, dt(7), (2, 2), dt, 1000, layout)
+    assert np.array_equal(P.to_numpy(), np.full((1000, 2, 2), 7, dtype=dt))
+    U = tb.unit(ctx, 4, dt, 513, layout)
+    assert np.array_equal(U.to_numpy(), np.broadcast_to(np.eye(4, dtype=dt), (513, 4, 4)))
+    a, _ = inputs(dc, 16, 513, 16)
+    A = ctx.from_numpy(a, (4, 4), layout)
+    with np.errstate(over="ignore"):
+        assert_bits_equal((A @ U).to_numpy().ravel(), oracle.matmul(a, np.broadcast_to(np.eye(4, dtype=dt), (513, 4, 4)).copy().ravel(), 4, 4, 4).ravel(), "A .*. unit")
+    with pytest.raises(tb.WrongListLength):
+        tb.replicate(ctx, np.zeros(5, dtype=dt), (2, 3), 10, dt, layout)
+
+
 def test_device_synthetic_matches_oracle(ctx):
     for dc in ALL:
         for layout in (tb.AOS, tb.SOA):
