@@ -150,3 +150,46 @@ def test_gpu_split_of_append_and_transpose_involution(ctx, dims, data):
     assert np.array_equal(tb.transpose(tb.transpose(Z)).to_numpy(), Z.to_numpy())
     assert np.array_equal(tb.transpose(X).to_numpy().reshape(batch, -1),
                           oracle.transpose(x, list(dims)).reshape(batch, -1))
+
+
+@pytest.mark.gpu
+@GPU
+@given(st.integers(1, 8), st.integers(1, 16), st.data(), st.sampled_from([oracle.F64, oracle.F32]), st.integers(1, 500),
+       st.integers(0, 2 ** 16))
+def test_gpu_row_echelon_random_shapes_bit_exact(ctx, m, n, data, dc, batch, op_id):
+    """rowEchelonForm on random shapes / pivot-column counts with small-integer entries (so that exact rank
+    defects occur naturally): bit-identical to the oracle, idempotent, rank == rank of the leading block."""
+    import tensor_b200 as tb
+    pc = data.draw(st.integers(0, n))
+    raw = oracle.fill(oracle.I64, oracle.SEED_A, op_id, batch * m * n)
+    a = ((raw >> 7) % 5 - 2).astype(oracle.NP_DTYPE[dc]).reshape(batch, m, n)
+    got, rank = tb.row_echelon_form(ctx.from_numpy(a, (m, n)), pc)
+    want, wrank = oracle.row_echelon(a, m, n, pc)
+    g = got.to_numpy()
+    assert np.array_equal(rank.to_numpy(), wrank)
+    assert np.array_equal(g.view(np.uint8), want.view(np.uint8))
+    again, rank2 = tb.row_echelon_form(got, pc)
+    assert np.array_equal(again.to_numpy(), g) and np.array_equal(rank2.to_numpy(), wrank)
+    assert np.all(wrank <= min(m, pc))
+
+
+@pytest.mark.gpu
+@GPU
+@given(st.integers(2, 8), st.sampled_from([oracle.F64, oracle.F32]), st.integers(1, 300), st.integers(0, 2 ** 16))
+def test_gpu_inverse_solve_echelon_agree_on_rank(ctx, n, dc, batch, op_id):
+    """inverse status, det == 0 and rowEchelonForm rank < n single out the same items (they share the pivot rule and
+    the multipliers below the diagonal), and the three agree with the oracle bit for bit."""
+    import tensor_b200 as tb
+    raw = oracle.fill(oracle.I64, oracle.SEED_B, op_id, batch * n * n)
+    a = ((raw >> 9) % 3 - 1).astype(oracle.NP_DTYPE[dc]).reshape(batch, n, n)     # entries in {-1, 0, 1}: many singular items
+    A = ctx.from_numpy(a, (n, n))
+    inv, st_ = tb.inverse(A)
+    d = tb.det(A).to_numpy()
+    _, rank = tb.row_echelon_form(A)
+    singular = st_.to_numpy() == 1
+    assert np.array_equal(singular, rank.to_numpy() < n)
+    assert np.array_equal(singular, d == 0)
+    oinv, ost = oracle.inverse(a, n)
+    assert np.array_equal(st_.to_numpy(), ost)
+    assert np.array_equal(inv.to_numpy().view(np.uint8), oinv.view(np.uint8))
+    assert np.array_equal(d.view(np.uint8), oracle.det(a, n).view(np.uint8))
