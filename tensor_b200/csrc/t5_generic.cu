@@ -107,6 +107,67 @@ static int prod_launch(const Shard& s, int P, int K, int Q, int nc, const void* 
     return ok();
 }
 
+// ---- long dot products: `dot` of n-vectors and `prod n` down to a scalar (BASELINE configs[3] with
+// n = 2: 8x8 : 8x8 -> scalar), n > 4 ----
+// The fold `acc = acc + x_j*y_j`, j ascending, is one sequential chain per item (the specification
+// fixes the order, so lanes cannot share an item), but a thread that reads its own 2 x n elements
+// from HBM touches 32 scattered sectors per warp load (the any-shape kernel: 0.30 / 0.15 of the HBM
+// peak for 64-element Double / Float vectors).  A CTA therefore stages chunks of KC elements of TPB
+// consecutive items into shared memory TRANSPOSED (coalesced global reads in runs of KC elements;
+// element e of item t at s[e][t], pitch TPB+1: conflict-free both ways) and every thread folds its own
+// column.  Same operations, same order: bit-identical for all three element types.
+template <class T, int TPB, int KC>
+__global__ void __launch_bounds__(TPB)
+longdot_kernel(const T* __restrict__ X, const T* __restrict__ Y, T* __restrict__ out, int K, unsigned long long count) {
+    using R = Arith<T>;
+    __shared__ T sx[KC][TPB + 1];
+    __shared__ T sy[KC][TPB + 1];
+    const int tid = threadIdx.x;
+    const unsigned long long n_tiles = (count + TPB - 1) / TPB;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long first = tile * TPB;
+        const int nv = (count - first < (unsigned long long)TPB) ? (int)(count - first) : TPB;
+        const T* gx = X + first * (size_t)K;
+        const T* gy = Y + first * (size_t)K;
+        T acc = R::zero();
+        for (int k0 = 0; k0 < K; k0 += KC) {
+            const int kc = (K - k0 < KC) ? K - k0 : KC;
+            const int sq = TPB / kc, sr = TPB - sq * kc;
+            int item = tid / kc, e = tid - item * kc;
+            const int total = nv * kc;
+            __syncthreads();                                   // the previous chunk has been folded
+            #pragma unroll 8
+            for (int idx = tid; idx < total; idx += TPB) {
+                const size_t g = (size_t)item * K + k0 + e;
+                sx[e][item] = __ldg(gx + g);
+                sy[e][item] = __ldg(gy + g);
+                item += sq; e += sr;
+                if (e >= kc) { e -= kc; ++item; }
+            }
+            __syncthreads();
+            if (tid < nv) {
+                #pragma unroll 8
+                for (int k = 0; k < kc; ++k) acc = R::add(acc, R::mul(sx[k][tid], sy[k][tid]));
+            }
+        }
+        if (tid < nv) out[first + tid] = acc;
+    }
+}
+
+int generic_longdot(const Shard& s, int dtype, int K, const void* X, const void* Y, void* O) {
+    constexpr int TPB = 128, KC8 = 16, KC4 = 32;    // 128-byte runs per item and chunk; 33 KB of static shared memory
+    if (s.layout != T5L_AOS || K < 1) return T5I_NOT_SPECIALISED;
+    if (s.count == 0) return T5I_OK;
+    const size_t tiles = (s.count + TPB - 1) / TPB;
+    switch (dtype) {
+        case T5D_F64: longdot_kernel<double, TPB, KC8><<<resident_grid((const void*)longdot_kernel<double, TPB, KC8>, TPB, tiles), TPB, 0, s.stream>>>((const double*)X, (const double*)Y, (double*)O, K, s.count); break;
+        case T5D_F32: longdot_kernel<float, TPB, KC4><<<resident_grid((const void*)longdot_kernel<float, TPB, KC4>, TPB, tiles), TPB, 0, s.stream>>>((const float*)X, (const float*)Y, (float*)O, K, s.count); break;
+        case T5D_I64: longdot_kernel<long long, TPB, KC8><<<resident_grid((const void*)longdot_kernel<long long, TPB, KC8>, TPB, tiles), TPB, 0, s.stream>>>((const long long*)X, (const long long*)Y, (long long*)O, K, s.count); break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
+}
+
 // ---- outer product (prod 0, the rank-r (x) rank-s tensor product of BASELINE configs[3]) ----
 // Write-bound: 2 x 512 B in, 32 KiB out per 8x8 (x) 8x8 item.  A CTA walks items; thread
 // (tp, tq) keeps its B vector in registers and streams rows p = tp, tp+R, ... of the
@@ -166,6 +227,51 @@ static int outer_launch(const Shard& s, int P, int Q, const void* A, const void*
     return ok();
 }
 
+static int gather_geometry(const void* kern, size_t count, size_t d_out, int threads, int* G);
+
+// Small outer products (3 (x) 3, 4 (x) 4, 3x3 (x) 3x3 -> 3^4, ...): the results of G consecutive items form
+// one contiguous run, thread l of the run writes output l (coalesced for any P, Q, odd ones included) and
+// finds its (item, p, q) by constant steps and one multiply-high - the any-shape kernel spent two run-time
+// integer divisions per output (0.29 / 0.18 of the HBM peak for 4Mi 3x3 (x) 3x3 Double / Float).  The
+// operands are re-read through L1 (they are 1/P + 1/Q of the output bytes).
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+outer_small_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, unsigned P, unsigned Q, unsigned magicQ,
+                   unsigned long long count, int G) {
+    using R = Arith<T>;
+    const unsigned PQ = P * Q;
+    const unsigned step_q = THREADS / PQ, step_r = THREADS - step_q * PQ;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
+        const unsigned total = gc * PQ;
+        unsigned il = threadIdx.x / PQ, e = threadIdx.x - il * PQ;
+        const T* a = A + (size_t)g0 * P;
+        const T* b = B + (size_t)g0 * Q;
+        T* c = C + (size_t)g0 * PQ;
+        #pragma unroll 4
+        for (unsigned l = threadIdx.x; l < total; l += THREADS) {
+            const unsigned p = __umulhi(e, magicQ);            // e / Q, exact for e < 2^16 (host checks P*Q)
+            const unsigned q = e - p * Q;
+            c[l] = R::mul(__ldg(a + (size_t)il * P + p), __ldg(b + (size_t)il * Q + q));
+            il += step_q; e += step_r;
+            if (e >= PQ) { e -= PQ; ++il; }
+        }
+    }
+}
+
+template <class T>
+static int outer_small_launch(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
+    constexpr int THREADS = 256;
+    if (s.count == 0) return T5I_OK;
+    int G;
+    const int grid = gather_geometry((const void*)outer_small_kernel<T, THREADS>, s.count, (size_t)P * Q, THREADS, &G);
+    const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Q - 1) / (unsigned)Q);
+    outer_small_kernel<T, THREADS><<<grid, THREADS, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, (unsigned)P, (unsigned)Q, magic,
+                                                                   (unsigned long long)s.count, G);
+    return ok();
+}
+
 // the streaming outer-product kernel applies when a CTA's threads tile whole rows of the result
 static bool outer_ok(int P, int Q, int vec) {
     if (Q % vec) return false;
@@ -180,6 +286,11 @@ int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const v
         if (dtype == T5D_F64 && outer_ok(P, Q, 2)) return outer_launch<double, 2>(s, P, Q, A, B, C);
         if (dtype == T5D_I64 && outer_ok(P, Q, 2)) return outer_launch<long long, 2>(s, P, Q, A, B, C);
         if (dtype == T5D_F32 && outer_ok(P, Q, 4)) return outer_launch<float, 4>(s, P, Q, A, B, C);
+        if ((long long)P * Q < 65536 && Q > 1) {
+            if (dtype == T5D_F64) return outer_small_launch<double>(s, P, Q, A, B, C);
+            if (dtype == T5D_I64) return outer_small_launch<long long>(s, P, Q, A, B, C);
+            if (dtype == T5D_F32) return outer_small_launch<float>(s, P, Q, A, B, C);
+        }
     }
     switch (dtype) {
         case T5D_F64: return (Q % 2 == 0) ? prod_launch<double, 2>(s, P, K, Q, nc, A, B, C) : prod_launch<double, 1>(s, P, K, Q, nc, A, B, C);

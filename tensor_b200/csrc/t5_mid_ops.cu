@@ -173,8 +173,10 @@ static int dispatch(const Shard& s, int m, int k, int n, const void* A, const vo
     // only 8 warps per SM on the FP64 chains, lost 25% inside a long bench run (clock-sensitive).
     if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 256, 2>(s, A, B, C);
     if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 128, 2>(s, A, B, C);
-    if constexpr (sizeof(T) == 8) {
+    if (m == 12 && k == 12 && n == 12) return launch<T, 12, 12, 12, 192, 2>(s, A, B, C);
+    if constexpr (sizeof(T) == 8) {   // rows must be whole 16-byte chunks
         if (m == 6 && k == 6 && n == 6) return launch<T, 6, 6, 6, 192, 3>(s, A, B, C);
+        if (m == 10 && k == 10 && n == 10) return launch<T, 10, 10, 10, 160, 2>(s, A, B, C);
     }
     return T5I_NOT_SPECIALISED;
 }

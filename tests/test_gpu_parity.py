@@ -43,7 +43,7 @@ def inputs(dc, op_id, batch, da, db=None):
 # ---- matmul (.*.) ----------------------------------------------------------------
 @pytest.mark.parametrize("dc", ALL)
 @pytest.mark.parametrize("mkn", [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (2, 5, 3), (7, 2, 6), (1, 9, 1), (8, 8, 8),
-                                 (5, 5, 5), (6, 6, 6), (7, 7, 7)])
+                                 (5, 5, 5), (6, 6, 6), (7, 7, 7), (10, 10, 10), (12, 12, 12), (16, 16, 16)])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_matmul_bit_exact(ctx, dc, mkn, layout):
     m, k, n = mkn
@@ -87,7 +87,7 @@ def test_int64_wraparound(ctx):
 
 # ---- dot / dot_sum ---------------------------------------------------------------
 @pytest.mark.parametrize("dc", ALL)
-@pytest.mark.parametrize("n", [2, 3, 4, 7])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 16, 33, 64, 100])    # n > 4: the staged long-dot kernel (chunk tails at 33, 100)
 def test_dot_bit_exact(ctx, dc, n):
     for batch in (1, 1000, 4099):
         x, y = inputs(dc, 3, batch, n, n)
@@ -125,6 +125,13 @@ def test_prod_and_tensor_product(ctx, dc):
     P = tb.prod(ctx.from_numpy(a3, (2, 3, 4)), ctx.from_numpy(b3, (4, 5)), 1)
     assert P.shape == (2, 3, 5)
     assert_bits_equal(P.to_numpy(), oracle.prod(a3, [2, 3, 4], b3, [4, 5], 1), "rank3.rank2")
+    # small outer products: the coalesced-run kernel (odd and even extents, ragged batch)
+    for (da, db) in (((3, 3), (3, 3)), ((4,), (4,)), ((2, 2), (5,)), ((7,), (2, 3))):
+        for bt in (1, 4099):
+            ao, bo = inputs(dc, 8, bt, int(np.prod(da)), int(np.prod(db)))
+            To = tb.tensor_product(ctx.from_numpy(ao, da), ctx.from_numpy(bo, db))
+            assert To.shape == tuple(da) + tuple(db)
+            assert_bits_equal(To.to_numpy(), oracle.prod(ao, list(da), bo, list(db), 0), f"{da} (x) {db}")
     # odd Q exercises the scalar (non-vectorised) path
     a4, b4 = inputs(dc, 7, batch, 3, 5)
     assert_bits_equal(tb.tensor_product(ctx.from_numpy(a4, (3,)), ctx.from_numpy(b4, (5,))).to_numpy(),

@@ -89,6 +89,35 @@ def main():
             add(f"matmul 4x4 (Double/Float) {tag}", B * 48 * es, lambda: tb.matmul(A4, B4))
             A32, B32 = ctx.synthetic((32, 32), dt, B // 64, SEED, 9), ctx.synthetic((32, 32), dt, B // 64, SEED, 10)
             add(f"matmul 32x32 {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(A32, B32))
+            # second sweep: shapes around the benchmarked ones (finds untuned dispatch corners)
+            B8 = ctx.synthetic((8, 8), dt, B // 4, SEED + 1, 17)
+            v8 = ctx.synthetic((8,), dt, B // 4, SEED + 1, 18)
+            v64a, v64b = ctx.synthetic((64,), dt, B // 4, SEED, 19), ctx.synthetic((64,), dt, B // 4, SEED + 1, 19)
+            v4a, v4b = ctx.synthetic((4,), dt, B, SEED, 20), ctx.synthetic((4,), dt, B, SEED + 1, 20)
+            A2, B2 = ctx.synthetic((2, 2), dt, B, SEED, 21), ctx.synthetic((2, 2), dt, B, SEED + 1, 21)
+            A16, B16 = ctx.synthetic((16, 16), dt, B // 16, SEED, 22), ctx.synthetic((16, 16), dt, B // 16, SEED + 1, 22)
+            A12, B12 = ctx.synthetic((12, 12), dt, B // 16, SEED, 23), ctx.synthetic((12, 12), dt, B // 16, SEED + 1, 23)
+            I8 = ctx.synthetic((8, 8), dt, B // 4, SEED + 2, 24)
+            B44 = ctx.synthetic((4, 4), dt, B, SEED + 2, 25)
+            add(f"prod 2: 8x8 : 8x8 -> scalar {tag}", (B // 4) * 129 * es, lambda: tb.prod(A8, B8, 2))
+            add(f"dot 64 {tag}", (B // 4) * 129 * es, lambda: tb.dot(v64a, v64b))
+            add(f"matvec 8x8 . 8 {tag}", (B // 4) * 80 * es, lambda: tb.matmul(A8, v8))
+            add(f"matmul 8x8 {tag}", (B // 4) * 192 * es, lambda: tb.matmul(A8, B8))
+            add(f"matmul 2x2 {tag}", B * 12 * es, lambda: tb.matmul(A2, B2))
+            add(f"matmul 12x12 {tag}", (B // 16) * 432 * es, lambda: tb.matmul(A12, B12))
+            add(f"matmul 16x16 {tag}", (B // 16) * 768 * es, lambda: tb.matmul(A16, B16))
+            add(f"outer 4 (x) 4 {tag}", B * 24 * es, lambda: tb.prod(v4a, v4b, 0))
+            add(f"outer 3x3 (x) 3x3 {tag}", B * 99 * es, lambda: tb.prod(A3, A3, 0))
+            add(f"transpose 3x3 {tag}", B * 18 * es, lambda: tb.transpose(A3))
+            add(f"transpose 8x8 {tag}", (B // 4) * 128 * es, lambda: tb.transpose(A8))
+            add(f"transpose 16x16 {tag}", (B // 16) * 512 * es, lambda: tb.transpose(A16))
+            add(f"det 2x2 {tag}", B * 5 * es, lambda: tb.det(A2))
+            add(f"inverse 2x2 {tag}", B * (8 * es) + B, lambda: tb.inverse(A2))
+            add(f"solve 4x4, 4 rhs {tag}", B * (48 * es) + B, lambda: tb.solve(A4, B44))
+            add(f"solve 8x8, 8 rhs {tag}", (B // 4) * (192 * es) + B // 4, lambda: tb.solve(A8, I8))
+            add(f"pure 4x4 {tag}", B * 16 * es, lambda: tb.pure(ctx, 1.5, (4, 4), dt, B))
+            for x in (B8, v8, v64a, v64b, v4a, v4b, A2, B2, A16, B16, A12, B12, I8, B44):
+                x.free()
             for x in (A3, A4, B4, v3, A6, b6, A8, T234, A5, B5, A32, B32):
                 x.free()
 
