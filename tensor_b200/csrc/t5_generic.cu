@@ -439,6 +439,129 @@ int generic_scatter2(const Shard& s, int elem_bytes, size_t d_in, size_t d1, siz
     return ok();
 }
 
+// ---- matrix transpose for extents >= 16 (a4: rank-2 index reversal) -------------------------------
+// The table-driven gather reads a column of the source per output row: for 16x16 Double records that is
+// 128-byte strides (0.59 of the HBM peak), for 128x128 ones 1-KB strides.  Large matrices: a CTA moves
+// 32 x 32 sub-blocks through a padded shared tile, row segments contiguous on both sides.
+template <class T, int TILE, int ROWS>
+__global__ void __launch_bounds__(TILE * ROWS)
+transpose2d_kernel(const T* __restrict__ in, T* __restrict__ out, int R, int C, int tr, int tc, unsigned long long total_tiles) {
+    __shared__ T tile[TILE][TILE + 1];
+    const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;
+    const unsigned per_item = (unsigned)(tr * tc);
+    const size_t d = (size_t)R * C;
+    for (unsigned long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const unsigned long long item = t / per_item;
+        const unsigned rem = (unsigned)(t - item * per_item);
+        const int ti = rem / tc, tj = rem - ti * tc;
+        const T* src = in + item * d;
+        T* dst = out + item * d;
+        {
+            const int x = tj * TILE + tx, y0 = ti * TILE;
+            #pragma unroll
+            for (int j = ty; j < TILE; j += ROWS)
+                if (x < C && y0 + j < R) tile[j][tx] = __ldg(src + (size_t)(y0 + j) * C + x);
+        }
+        __syncthreads();
+        {
+            const int x = ti * TILE + tx, y0 = tj * TILE;
+            #pragma unroll
+            for (int j = ty; j < TILE; j += ROWS)
+                if (x < R && y0 + j < C) dst[(size_t)(y0 + j) * R + x] = tile[tx][j];
+        }
+        __syncthreads();
+    }
+}
+
+template <class T, int TILE, int ROWS>
+static int transpose2d_launch(const Shard& s, int R, int C, const void* A, void* O) {
+    const int tr = (R + TILE - 1) / TILE, tc = (C + TILE - 1) / TILE;
+    const unsigned long long total = (unsigned long long)s.count * tr * tc;
+    const int grid = resident_grid((const void*)transpose2d_kernel<T, TILE, ROWS>, TILE * ROWS, total);
+    transpose2d_kernel<T, TILE, ROWS><<<grid, TILE * ROWS, 0, s.stream>>>((const T*)A, (T*)O, R, C, tr, tc, total);
+    return ok();
+}
+
+// Matrices of a few KB (16x16 .. ~45x45 Double): whole items are staged instead - G consecutive items
+// arrive as one contiguous run (coalesced), rows at an odd pitch; the result leaves as one contiguous
+// run too, each thread reading down a source column (stride = the odd pitch: conflict-free).  Index
+// arithmetic: constant steps + one multiply-high per element, no division.
+// VEC = 2 (4-byte elements, R and C even): global accesses are 8-byte pairs - a pair never straddles a row on
+// either side - so a warp instruction still moves 256 contiguous bytes.
+template <class T, int VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+transpose_staged_kernel(const T* __restrict__ in, T* __restrict__ out, unsigned R, unsigned C, unsigned pitch, unsigned magicC,
+                        unsigned magicR, unsigned long long count, int G) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    T* sm = reinterpret_cast<T*>(tsm);
+    struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+    const unsigned d = R * C, item_pitch = R * pitch;
+    const unsigned dv = d / VEC;                                   // vectors per item
+    const unsigned step_q = THREADS / dv, step_r = THREADS - step_q * dv;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
+        const unsigned total = gc * dv;
+        const Pack* src = reinterpret_cast<const Pack*>(in + (size_t)g0 * d);
+        Pack* dst = reinterpret_cast<Pack*>(out + (size_t)g0 * d);
+        unsigned il = threadIdx.x / dv, ev = threadIdx.x - il * dv;
+        #pragma unroll 4
+        for (unsigned l = threadIdx.x; l < total; l += THREADS) {
+            const unsigned e = ev * VEC;
+            const unsigned i = __umulhi(e, magicC), j = e - i * C;          // e = i*C + j
+            const Pack p = src[l];
+            #pragma unroll
+            for (int u = 0; u < VEC; ++u) sm[il * item_pitch + i * pitch + j + u] = p.v[u];
+            il += step_q; ev += step_r;
+            if (ev >= dv) { ev -= dv; ++il; }
+        }
+        __syncthreads();
+        il = threadIdx.x / dv; ev = threadIdx.x - il * dv;
+        #pragma unroll 4
+        for (unsigned l = threadIdx.x; l < total; l += THREADS) {
+            const unsigned e = ev * VEC;
+            const unsigned j = __umulhi(e, magicR), i = e - j * R;          // output e = j*R + i
+            Pack p;
+            #pragma unroll
+            for (int u = 0; u < VEC; ++u) p.v[u] = sm[il * item_pitch + (i + u) * pitch + j];
+            dst[l] = p;
+            il += step_q; ev += step_r;
+            if (ev >= dv) { ev -= dv; ++il; }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T, int VEC>
+static int transpose_staged_launch(const Shard& s, int R, int C, const void* A, void* O) {
+    constexpr int THREADS = 256;
+    auto kern = transpose_staged_kernel<T, VEC, THREADS>;
+    const unsigned pitch = (unsigned)C | 1u;
+    const size_t item_bytes = (size_t)R * pitch * sizeof(T);
+    int G = (int)((32 * 1024) / item_bytes);
+    if (G < 1) G = 1;
+    const int smem = (int)(G * item_bytes);
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return T5I_CUDA;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const size_t groups = (s.count + G - 1) / G, cap = (size_t)occ * sm_count();
+    const int grid = (int)(groups < cap ? groups : cap);
+    const unsigned mC = (unsigned)((0x100000000ull + (unsigned)C - 1) / (unsigned)C), mR = (unsigned)((0x100000000ull + (unsigned)R - 1) / (unsigned)R);
+    kern<<<grid, THREADS, smem, s.stream>>>((const T*)A, (T*)O, (unsigned)R, (unsigned)C, pitch, mC, mR, (unsigned long long)s.count, G);
+    return ok();
+}
+
+int generic_transpose2d(const Shard& s, int elem_bytes, int R, int C, const void* A, void* O) {
+    if (s.layout != T5L_AOS || (R < 16 && C < 16)) return T5I_NOT_SPECIALISED;   // smaller: the table gather is at 0.95+
+    if (elem_bytes != 4 && elem_bytes != 8) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    if ((size_t)R * ((unsigned)C | 1u) * elem_bytes <= 16 * 1024 && (size_t)R * C < 65536)
+        return elem_bytes == 8 ? transpose_staged_launch<unsigned long long, 1>(s, R, C, A, O)
+             : (R % 2 == 0 && C % 2 == 0) ? transpose_staged_launch<unsigned, 2>(s, R, C, A, O) : transpose_staged_launch<unsigned, 1>(s, R, C, A, O);
+    if (R < 16 || C < 16) return T5I_NOT_SPECIALISED;
+    return elem_bytes == 8 ? transpose2d_launch<unsigned long long, 32, 8>(s, R, C, A, O) : transpose2d_launch<unsigned, 32, 8>(s, R, C, A, O);
+}
+
 int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O) {
     return generic_gather(s, elem_bytes, d, d, perm_dev, A, O);
 }

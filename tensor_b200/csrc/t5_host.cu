@@ -556,6 +556,7 @@ static int transpose_shard(t5_ctx* c, int g, const Shard& s, int es, const std::
     }
     int r = T5I_NOT_SPECIALISED;
     if (sq.size() == 2) r = small_transpose(s, es, (int)sq[0], (int)sq[1], in, out);
+    if (r == T5I_NOT_SPECIALISED && sq.size() == 2) r = generic_transpose2d(s, es, (int)sq[0], (int)sq[1], in, out);
     if (r == T5I_NOT_SPECIALISED) {
         if (s.layout != T5L_AOS) return T5_ERR_UNSUPPORTED;
         auto it = c->perm_cache.find(sq);

@@ -160,12 +160,13 @@ def test_transpose_golden(ctx):
 
 
 @pytest.mark.parametrize("dc", ALL)
-@pytest.mark.parametrize("dims", [(4, 4), (3, 3), (2, 3), (4, 1), (5,), (2, 3, 4), (8, 8), (3, 1, 2, 2), (16, 16)])
+@pytest.mark.parametrize("dims", [(4, 4), (3, 3), (2, 3), (4, 1), (5,), (2, 3, 4), (8, 8), (3, 1, 2, 2), (16, 16),
+                                  (17, 33), (32, 32), (20, 40), (64, 16), (16, 1, 31), (15, 40), (128, 128), (100, 130)])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_transpose_bit_exact_and_involution(ctx, dc, dims, layout):
     d = int(np.prod(dims))
     small = len([x for x in dims if x != 1]) <= 1 or (len(dims) == 2 and max(dims) <= 4)
-    for batch in (1, 513, 4099):
+    for batch in ((1, 513, 4099) if d <= 1024 else (1, 37)):   # extents >= 16: the tiled matrix transpose (ragged tiles at 17, 33, 100, 130)
         a, _ = inputs(dc, 8, batch, d)
         A = ctx.from_numpy(a, dims, layout)
         if layout == tb.SOA and not small:

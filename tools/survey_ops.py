@@ -111,6 +111,11 @@ def main():
             add(f"transpose 3x3 {tag}", B * 18 * es, lambda: tb.transpose(A3))
             add(f"transpose 8x8 {tag}", (B // 4) * 128 * es, lambda: tb.transpose(A8))
             add(f"transpose 16x16 {tag}", (B // 16) * 512 * es, lambda: tb.transpose(A16))
+            A128 = ctx.synthetic((128, 128), dt, B // 1024, SEED, 26)
+            A2040 = ctx.synthetic((20, 40), dt, B // 64, SEED, 27)
+            add(f"transpose 128x128 {tag}", (B // 1024) * 32768 * es, lambda: tb.transpose(A128))
+            add(f"transpose 20x40 {tag}", (B // 64) * 1600 * es, lambda: tb.transpose(A2040))
+            A128.free(); A2040.free()
             add(f"det 2x2 {tag}", B * 5 * es, lambda: tb.det(A2))
             add(f"inverse 2x2 {tag}", B * (8 * es) + B, lambda: tb.inverse(A2))
             add(f"solve 4x4, 4 rhs {tag}", B * (48 * es) + B, lambda: tb.solve(A4, B44))
