@@ -668,6 +668,7 @@ int t5_solve(t5_ctx* c, int dtype, int n, int nrhs, const t5_buf* A, const t5_bu
         CU(c, cudaSetDevice(c->dev[g]));
         Shard s = shard_of(c, A, g);
         int r = small_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) r = many_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r == T5I_NOT_SPECIALISED) r = rowlane_solve(s, dtype, n, nrhs, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(s, dtype, n, nrhs, false, A->ptr[g], B->ptr[g], X->ptr[g], STATUS->ptr[g]);
         if (r != T5I_OK) return map_internal(c, r, "t5_solve");
@@ -1017,6 +1018,7 @@ int t5_solve_host(t5_ctx* c, int dtype, int n, int nrhs, size_t batch, const voi
                                 {nullptr, X, (size_t)n * nrhs * es}, {nullptr, status, 1}};
     return host_pipeline(c, batch, ops, 4, [&](int, const Shard& sh, void* const* d) {
         int r = small_solve(sh, dtype, n, nrhs, d[0], d[1], d[2], d[3]);
+        if (r == T5I_NOT_SPECIALISED) r = many_solve(sh, dtype, n, nrhs, d[0], d[1], d[2], d[3]);
         if (r == T5I_NOT_SPECIALISED) r = rowlane_solve(sh, dtype, n, nrhs, d[0], d[1], d[2], d[3]);
         if (r == T5I_NOT_SPECIALISED) r = generic_solve(sh, dtype, n, nrhs, false, d[0], d[1], d[2], d[3]);
         if (r != T5I_OK) return map_internal(c, r, "t5_solve_host");

@@ -12,6 +12,11 @@
 
 namespace t5 {
 
+#define T5_MATVEC_GEO(N_) \
+    template <class T> struct Geo<MatmulOp<T, N_, N_, 1>> { using type = G<64, 1, 2>; }; \
+    template <class T> struct Geo<MatmulOp<T, 1, N_, N_>> { using type = G<64, 1, 2>; };
+T5_MATVEC_GEO(5) T5_MATVEC_GEO(6) T5_MATVEC_GEO(7) T5_MATVEC_GEO(8)
+#undef T5_MATVEC_GEO
 template <class T> struct Geo<MatmulOp<T, 5, 5, 5>> { using type = G<128, 1, 2>; };
 template <class T> struct Geo<MatmulOp<T, 6, 6, 6>> { using type = G<128, 1, 2>; };
 template <class T> struct Geo<MatmulOp<T, 7, 7, 7>> { using type = G<128, 1, 2>; };
@@ -48,6 +53,8 @@ static int matmul_t(const Shard& s, int m, int k, int n, const void* A, const vo
     T5_MM(1, 2, 2) T5_MM(1, 3, 3) T5_MM(1, 4, 4)
     T5_MM(1, 2, 1) T5_MM(1, 3, 1) T5_MM(1, 4, 1)
     T5_MM(5, 5, 5)                                             // 75 elements in registers: fine for every type
+    T5_MM(5, 5, 1) T5_MM(6, 6, 1) T5_MM(7, 7, 1) T5_MM(8, 8, 1)  // matrix . vector: the matrix record in registers (<= 64 elements)
+    T5_MM(1, 5, 5) T5_MM(1, 6, 6) T5_MM(1, 7, 7) T5_MM(1, 8, 8)  // vector . matrix
     if constexpr (sizeof(T) == 4) { T5_MM(6, 6, 6) T5_MM(7, 7, 7) }   // 8-byte 6x6 is the row-per-thread kernel's
 #undef T5_MM
     return T5I_NOT_SPECIALISED;

@@ -87,6 +87,8 @@ struct Recip<double> {
     }
 };
 
+template <int K> using k_of = std::integral_constant<int, K>;
+
 template <int B, int E, class F>
 __device__ __forceinline__ void static_for(F&& f) {
     if constexpr (B < E) {
@@ -400,6 +402,65 @@ struct InverseOp {
 // hand the finished entries to the writer before the next block starts.  Every element sees the
 // operations of the one-pass elimination in the same order (bit-identical to the oracle);
 // the live set is N x N + 2N + the reciprocals (8x8 Double: ~100 doubles instead of 192+).
+// (1) of the split elimination: LU of A with the pivot rule and multipliers of `eliminate`, the
+// multiplier f(i,k) kept in w[i][k]; piv[k] = the row that was swapped into position k.
+template <class T, int N>
+__device__ __forceinline__ bool lu_factor(T (&w)[N][N], int (&piv)[N], Recip<T> (&rc)[N]) {
+    bool singular = false;
+    static_for<0, N>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        piv[k] = k;
+        if (k + 1 < N && w[k][k] == T(0)) {
+            static_for<k + 1, N>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const bool sw = (w[k][k] == T(0)) && (w[r][k] != T(0));
+                #pragma unroll
+                for (int j = 0; j < N; ++j) {      // whole rows: the multipliers of earlier steps travel with their row
+                    T x = w[k][j], y = w[r][j];
+                    w[k][j] = sw ? y : x;
+                    w[r][j] = sw ? x : y;
+                }
+                piv[k] = sw ? r : piv[k];
+            });
+        }
+        singular = singular || (w[k][k] == T(0));
+        rc[k] = Recip<T>(w[k][k]);
+        static_for<k + 1, N>([&](auto i_) {
+            constexpr int i = decltype(i_)::value;
+            const T f = rc[k].div(w[i][k]);
+            #pragma unroll
+            for (int j = k + 1; j < N; ++j) w[i][j] = w[i][j] - f * w[k][j];
+            w[i][k] = f;
+        });
+    });
+    return !singular;
+}
+
+// (2): the row operations replayed on CB right-hand-side columns that are ALREADY row-permuted
+// (x = P b), then the back-substitution; emit(k, c, value) receives each finished entry.
+template <class T, int N, int CB, class Emit>
+__device__ __forceinline__ void lu_solve_block(const T (&w)[N][N], const Recip<T> (&rc)[N], T (&x)[N][CB], Emit&& emit) {
+    static_for<0, N>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        static_for<k + 1, N>([&](auto i_) {
+            constexpr int i = decltype(i_)::value;
+            #pragma unroll
+            for (int c = 0; c < CB; ++c) x[i][c] = x[i][c] - w[i][k] * x[k][c];
+        });
+    });
+    static_for<0, N>([&](auto kk_) {
+        constexpr int k = N - 1 - decltype(kk_)::value;
+        static_for<0, CB>([&](auto c_) {
+            constexpr int c = decltype(c_)::value;
+            T s = T(0);
+            #pragma unroll
+            for (int j = k + 1; j < N; ++j) s = s + w[k][j] * x[j][c];
+            x[k][c] = rc[k].div(x[k][c] - s);
+            emit(k_of<k>{}, c_, x[k][c]);
+        });
+    });
+}
+
 template <class T, int N>
 struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
     static constexpr bool streams_out0 = true;
@@ -415,39 +476,12 @@ struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
             for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
         int piv[N];
         Recip<T> rc[N];
-        bool singular = false;
-        static_for<0, N>([&](auto k_) {
-            constexpr int k = decltype(k_)::value;
-            piv[k] = k;
-            if (k + 1 < N && w[k][k] == T(0)) {
-                static_for<k + 1, N>([&](auto r_) {
-                    constexpr int r = decltype(r_)::value;
-                    const bool sw = (w[k][k] == T(0)) && (w[r][k] != T(0));
-                    #pragma unroll
-                    for (int j = 0; j < N; ++j) {      // whole rows: the multipliers of earlier steps travel with their row
-                        T x = w[k][j], y = w[r][j];
-                        w[k][j] = sw ? y : x;
-                        w[r][j] = sw ? x : y;
-                    }
-                    piv[k] = sw ? r : piv[k];
-                });
-            }
-            singular = singular || (w[k][k] == T(0));
-            rc[k] = Recip<T>(w[k][k]);
-            static_for<k + 1, N>([&](auto i_) {
-                constexpr int i = decltype(i_)::value;
-                const T f = rc[k].div(w[i][k]);
-                #pragma unroll
-                for (int j = k + 1; j < N; ++j) w[i][j] = w[i][j] - f * w[k][j];
-                w[i][k] = f;
-            });
-        });
-        const bool ok = !singular;
+        const bool ok = lu_factor<T, N>(w, piv, rc);
         static_for<0, (N + CB - 1) / CB>([&](auto blk_) {
             constexpr int c0 = decltype(blk_)::value * CB;
             constexpr int cb = (N - c0 < CB) ? N - c0 : CB;
-            // row i of the permuted identity: a row keeps its right-hand side through every swap, so
-            // column c0+c starts as e_{src} with the 1 wherever original row c0+c ended up
+            // a row keeps its right-hand side through every swap, so column c0+c of the identity starts as
+            // e_pos with the 1 wherever original row c0+c ended up
             T x[N][cb];
             #pragma unroll
             for (int c = 0; c < cb; ++c) {
@@ -457,24 +491,58 @@ struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
                 #pragma unroll
                 for (int i = 0; i < N; ++i) x[i][c] = (i == pos) ? T(1) : T(0);
             }
-            static_for<0, N>([&](auto k_) {
-                constexpr int k = decltype(k_)::value;
-                static_for<k + 1, N>([&](auto i_) {
-                    constexpr int i = decltype(i_)::value;
-                    #pragma unroll
-                    for (int c = 0; c < cb; ++c) x[i][c] = x[i][c] - w[i][k] * x[k][c];
-                });
+            lu_solve_block<T, N, cb>(w, rc, x, [&](auto k_, auto c_, T v) {
+                out.template put<decltype(k_)::value * N + c0 + decltype(c_)::value>(ok ? v : T(0));
             });
-            static_for<0, N>([&](auto kk_) {
-                constexpr int k = N - 1 - decltype(kk_)::value;
-                static_for<0, cb>([&](auto c_) {
-                    constexpr int c = decltype(c_)::value;
-                    T s = T(0);
-                    #pragma unroll
-                    for (int j = k + 1; j < N; ++j) s = s + w[k][j] * x[j][c];
-                    x[k][c] = rc[k].div(x[k][c] - s);
-                    out.template put<k * N + c0 + c>(ok ? x[k][c] : T(0));
-                });
+        });
+        status[0] = ok ? 0 : 1;
+    }
+};
+
+// solve A X = B with a MATRIX right-hand side for n >= 5: the same split.  B is not loaded into
+// registers: each block of two columns is read from the operand's shared-memory slot when its turn
+// comes (`lazy_in1`; the row permutation is a run-time index there, which shared memory does not mind),
+// and X is written over B's slot column block by column block (over A's when they are the same size).
+template <class T, int N, int NRHS>
+struct SolveManyOp {
+    static constexpr bool streams_out0 = true;
+    static constexpr bool lazy_in1 = true;
+    static constexpr int CB = 2;
+    using In0 = Rec<T, N * N>; using In1 = Rec<T, N * NRHS>;
+    using Out0 = Rec<T, N * NRHS>; using Out1 = Rec<unsigned char, 1>;
+    template <class Rd, class W>
+    __device__ __forceinline__ static void run_stream(const T* a, const Rd& b, const W& out, unsigned char* status) {
+        T w[N][N];
+        #pragma unroll
+        for (int i = 0; i < N; ++i)
+            #pragma unroll
+            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+        int piv[N];
+        Recip<T> rc[N];
+        const bool ok = lu_factor<T, N>(w, piv, rc);
+        int perm[N];                      // position i holds original row perm[i]
+        #pragma unroll
+        for (int i = 0; i < N; ++i) perm[i] = i;
+        static_for<0, N>([&](auto k_) {
+            constexpr int k = decltype(k_)::value;
+            static_for<k + 1, N>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const bool sw = piv[k] == r;
+                const int p = perm[k], q = perm[r];
+                perm[k] = sw ? q : p;
+                perm[r] = sw ? p : q;
+            });
+        });
+        static_for<0, (NRHS + CB - 1) / CB>([&](auto blk_) {
+            constexpr int c0 = decltype(blk_)::value * CB;
+            constexpr int cb = (NRHS - c0 < CB) ? NRHS - c0 : CB;
+            T x[N][cb];
+            #pragma unroll
+            for (int i = 0; i < N; ++i)
+                #pragma unroll
+                for (int c = 0; c < cb; ++c) x[i][c] = b.get(perm[i] * NRHS + c0 + c);
+            lu_solve_block<T, N, cb>(w, rc, x, [&](auto k_, auto c_, T v) {
+                out.template put<decltype(k_)::value * NRHS + c0 + decltype(c_)::value>(ok ? v : T(0));
             });
         });
         status[0] = ok ? 0 : 1;

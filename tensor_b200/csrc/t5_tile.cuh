@@ -110,6 +110,24 @@ struct RegArr {
     alignas(16) typename R::type v[R::n > 0 ? R::n : 1];
 };
 
+template <class Op, class = void> struct LazyIn1 : std::false_type {};
+template <class Op> struct LazyIn1<Op, std::void_t<decltype(Op::lazy_in1)>> : std::true_type {};
+
+template <class R>
+struct SlotReader {                 // second operand read on demand from the thread's slot (run-time element index)
+    const unsigned char* stage;
+    int item;
+    __device__ __forceinline__ typename R::type get(int e) const {
+        return *reinterpret_cast<const typename R::type*>(stage + R::elem_off(item, e));
+    }
+};
+template <class T>
+struct SoaReader {
+    const T* base;                  // row 0 of this item inside the staged tile
+    int pitch;                      // items per staged row
+    __device__ __forceinline__ T get(int e) const { return base[e * pitch]; }
+};
+
 template <class R>
 struct SlotWriter {
     unsigned char* stage;
@@ -294,11 +312,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
             if (it < nv) {
                 RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
                 if constexpr (I0::bytes > 0) I0::load(s0, it, r0.v);
-                if constexpr (I1::bytes > 0) I1::load(s1, it, r1.v);
+                if constexpr (I1::bytes > 0 && !LazyIn1<Op>::value) I1::load(s1, it, r1.v);
                 if constexpr (StreamsOut<Op>::value) {
-                    static_assert(C::OUT0 == 0, "streamed results go in place over the first input record");
-                    SlotWriter<I0> wr{so, it};
-                    Op::run_stream(r0.v, r1.v, wr, w1.v);
+                    static_assert(C::OUT0 == 0 || C::OUT0 == 1, "streamed results go in place over an input record");
+                    SlotWriter<std::conditional_t<C::OUT0 == 0, I0, I1>> wr{so, it};
+                    if constexpr (LazyIn1<Op>::value) {
+                        SlotReader<I1> rd{s1, it};
+                        Op::run_stream(r0.v, rd, wr, w1.v);
+                    } else {
+                        Op::run_stream(r0.v, r1.v, wr, w1.v);
+                    }
                 } else {
                     run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
                 }
@@ -434,12 +457,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) soa_tile_kernel(SoaArgs a
                 RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
                 #pragma unroll
                 for (int e = 0; e < I0::n; ++e) r0.v[e] = s0[e * TILE + it];
-                #pragma unroll
-                for (int e = 0; e < I1::n; ++e) r1.v[e] = s1[e * TILE + it];
+                if constexpr (!LazyIn1<Op>::value) {
+                    #pragma unroll
+                    for (int e = 0; e < I1::n; ++e) r1.v[e] = s1[e * TILE + it];
+                }
                 const unsigned long long b = first + it;
                 if constexpr (StreamsOut<Op>::value) {
                     SoaWriter<typename O0::type> wr{out0 + b, a.stride};
-                    Op::run_stream(r0.v, r1.v, wr, w1.v);
+                    if constexpr (LazyIn1<Op>::value) {
+                        SoaReader<T1> rd{s1 + it, TILE};
+                        Op::run_stream(r0.v, rd, wr, w1.v);
+                    } else {
+                        Op::run_stream(r0.v, r1.v, wr, w1.v);
+                    }
                 } else {
                     run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
                     #pragma unroll

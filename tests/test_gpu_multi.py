@@ -47,6 +47,33 @@ def test_sharded_ops_match_oracle(mctx, batch):
     assert np.array_equal(st.to_numpy(), ost) and np.array_equal(bits(inv.to_numpy()), bits(oinv))
 
 
+@pytest.mark.parametrize("batch", [3, 100003])
+def test_sharded_wider_surface_matches_oracle(mctx, batch):
+    """The ops either side of the hot path on a sharded batch: every device runs its own range, results meet in
+    one download - rowEchelonForm, 8x8 inverse (streamed-result kernel), long dot, staged transpose, split, pure."""
+    from tensor_b200 import structure as st
+    a4 = oracle.fill(oracle.F64, oracle.SEED_A, 31, batch * 20).reshape(batch, 4, 5).copy()
+    a4[::5, 2] = a4[::5, 0]                                             # exact rank defects
+    e, r = tb.row_echelon_form(mctx.from_numpy(a4, (4, 5)), 4)
+    oe, orank = oracle.row_echelon(a4, 4, 5, 4, threads=8)
+    assert np.array_equal(r.to_numpy(), orank) and np.array_equal(bits(e.to_numpy()), bits(oe))
+    a8 = oracle.fill(oracle.F64, oracle.SEED_A, 32, batch * 64).reshape(batch, 8, 8).copy()
+    oracle.plant_specials(a8, 8, 0, swap_every=16, sing_every=128)
+    A8 = mctx.from_numpy(a8, (8, 8))
+    inv, stt = tb.inverse(A8)
+    oinv, ost = oracle.inverse(a8, 8, threads=8)
+    assert np.array_equal(stt.to_numpy(), ost) and np.array_equal(bits(inv.to_numpy()), bits(oinv))
+    b8 = oracle.fill(oracle.F64, oracle.SEED_B, 32, batch * 64)
+    assert np.array_equal(bits(tb.prod(A8, mctx.from_numpy(b8, (8, 8)), 2).to_numpy()),
+                          bits(oracle.prod(a8.ravel(), [8, 8], b8, [8, 8], 2)))
+    a16 = oracle.fill(oracle.F32, oracle.SEED_A, 33, batch * 16 * 20)
+    assert np.array_equal(bits(tb.transpose(mctx.from_numpy(a16, (16, 20))).to_numpy()), bits(oracle.transpose(a16, [16, 20])))
+    l, rgt = st.split(2, 3, mctx.from_numpy(a4, (4, 5)))
+    assert np.array_equal(l.to_numpy(), a4[:, :, :3]) and np.array_equal(rgt.to_numpy(), a4[:, :, 3:])
+    u = tb.unit(mctx, 3, np.int64, batch)
+    assert np.array_equal(u.to_numpy(), np.broadcast_to(np.eye(3, dtype=np.int64), (batch, 3, 3)))
+
+
 def test_device_synthetic_stream_is_global(mctx):
     batch = 300001
     A = mctx.synthetic((4, 4), np.float32, batch, oracle.SEED_A, 3)

@@ -43,11 +43,13 @@ def inputs(dc, op_id, batch, da, db=None):
 # ---- matmul (.*.) ----------------------------------------------------------------
 @pytest.mark.parametrize("dc", ALL)
 @pytest.mark.parametrize("mkn", [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (2, 5, 3), (7, 2, 6), (1, 9, 1), (8, 8, 8),
-                                 (5, 5, 5), (6, 6, 6), (7, 7, 7), (10, 10, 10), (12, 12, 12), (16, 16, 16)])
+                                 (5, 5, 5), (6, 6, 6), (7, 7, 7), (10, 10, 10), (12, 12, 12), (16, 16, 16),
+                                 (5, 5, 1), (8, 8, 1), (1, 7, 7), (1, 8, 8), (6, 6, 1)])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_matmul_bit_exact(ctx, dc, mkn, layout):
     m, k, n = mkn
-    specialised = mkn in [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (5, 5, 5)] or \
+    specialised = mkn in [(3, 3, 3), (4, 4, 4), (2, 2, 2), (4, 4, 1), (3, 3, 1), (1, 4, 4), (5, 5, 5),
+                          (5, 5, 1), (8, 8, 1), (1, 7, 7), (1, 8, 8), (6, 6, 1)] or \
         (dc == oracle.F32 and mkn in [(6, 6, 6), (7, 7, 7)])
     for batch in (1, 257, 4099):
         a, b = inputs(dc, 1, batch, m * k, k * n)
@@ -214,6 +216,30 @@ def test_det_inverse_solve_bit_exact(ctx, dc, n, layout):
         if batch >= 300:
             assert ost.sum() == (batch + 127) // 128          # every 128th matrix is singular
             assert np.all(oracle.det(a, n)[::128] == 0)
+
+
+@pytest.mark.parametrize("dc", FRAC)
+@pytest.mark.parametrize("n", [5, 6, 7, 8])
+@pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
+def test_solve_matrix_rhs_bit_exact(ctx, dc, n, layout):
+    """Matrix right-hand sides for 5 <= n <= 8: 2, 3, 4 and n columns run record-per-thread (LU + lazily read
+    right-hand side, AoS and SoA), any other count on the row-per-lane kernel (AoS only)."""
+    for nrhs in (2, 3, 4, n, 5 if n != 5 else 6):
+        for batch in (1, 1500):
+            a, _ = elim_inputs(dc, n, batch)
+            b = oracle.fill(dc, oracle.SEED_B, 20 + nrhs, batch * n * nrhs)
+            A = ctx.from_numpy(a, (n, n), layout)
+            B = ctx.from_numpy(b, (n, nrhs), layout)
+            if layout == tb.SOA and nrhs not in (2, 3, 4, n):
+                with pytest.raises(tb.Unsupported):
+                    tb.solve(A, B)
+                continue
+            X, st = tb.solve(A, B)
+            ox, ost = oracle.solve(a, b, n, nrhs)
+            assert np.array_equal(st.to_numpy(), ost), (n, nrhs)
+            assert_bits_equal(X.to_numpy(), ox.reshape(batch, n, nrhs), f"solve n={n} nrhs={nrhs}")
+            if batch > 128:
+                assert ost.sum() == (batch + 127) // 128
 
 
 @pytest.mark.parametrize("dc", FRAC)
