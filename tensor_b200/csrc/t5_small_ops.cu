@@ -25,19 +25,20 @@ template <class T> struct Geo<DetOp<T, 4>> { using type = G<128, 1, 2, 6>; };
 template <class T> struct Geo<InverseOp<T, 2>> { using type = G<128, 1, 2>; };
 template <class T> struct Geo<InverseOp<T, 3>> { using type = G<128, 1, 2, 6>; };   // register cap 80: 6 CTAs/SM
 template <class T> struct Geo<InverseOp<T, 4>> { using type = G<64, 1, 2, 8>; };    // register cap 128: 8 CTAs/SM (r01_tune_elim_v3.csv)
-// 5x5 / 6x6 elimination: one record per thread, small CTAs
-template <class T> struct Geo<DetOp<T, 5>> { using type = G<64, 1, 2>; };
+// 5 <= n <= 8 elimination: one record per thread, 64-thread CTAs; the one-stage pipeline (t5_tile.cuh) wherever it
+// measured faster (profiles/r01f_op_survey.txt: every 7x7 / 8x8 op, the 5x5 / 6x6 det and solve except det 6x6)
+template <class T> struct Geo<DetOp<T, 5>> { using type = G<64, 1, 1>; };
 template <class T> struct Geo<DetOp<T, 6>> { using type = G<64, 1, 2>; };
 template <class T> struct Geo<InverseOp<T, 5>> { using type = G<64, 1, 2>; };
 template <class T> struct Geo<InverseOp<T, 6>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<SolveOp<T, 5, 1>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<SolveOp<T, 6, 1>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<DetOp<T, 7>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<DetOp<T, 8>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<InverseOp<T, 7>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<InverseOp<T, 8>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<SolveOp<T, 7, 1>> { using type = G<64, 1, 2>; };
-template <class T> struct Geo<SolveOp<T, 8, 1>> { using type = G<64, 1, 2>; };
+template <class T> struct Geo<SolveOp<T, 5, 1>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<SolveOp<T, 6, 1>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<DetOp<T, 7>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<DetOp<T, 8>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<InverseOp<T, 7>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<InverseOp<T, 8>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<SolveOp<T, 7, 1>> { using type = G<64, 1, 1>; };
+template <class T> struct Geo<SolveOp<T, 8, 1>> { using type = G<64, 1, 1>; };
 template <class T, int N> struct Geo<MinPolyOp<T, N>> { using type = G<64, 1, 2>; };              // up to 248 registers (4x4 Double)
 template <class T, int N, int R> struct Geo<SolveOp<T, N, R>> {
     using type = std::conditional_t<(R == 1), std::conditional_t<(N <= 3), G<256, 1, 3>, G<128, 1, 2, 5>>,

@@ -6,9 +6,10 @@
 
 namespace t5 {
 
-// 8x8 Double with 8 columns: 2 x (528 + 528) B of ring per record - one 64-thread CTA per SM; 32-thread CTAs fit three
+// Two operand records per item: from ~450 B on (6x6 Double with 4+ columns, 7x7, 8x8) a two-stage ring leaves one or two CTAs per SM;
+// the one-stage pipeline (t5_tile.cuh) doubles that.
 template <class T, int N, int R> struct Geo<SolveManyOp<T, N, R>> {
-    using type = std::conditional_t<(sizeof(T) * (N * N + N * R) >= 1024), G<32, 1, 2>, G<64, 1, 2>>;
+    using type = std::conditional_t<(sizeof(T) * (N * N + N * R) >= 448), G<64, 1, 1>, G<64, 1, 2>>;
 };
 
 template <class T, int N>

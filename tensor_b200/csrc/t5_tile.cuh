@@ -354,6 +354,95 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
     }
 }
 
+// ---- one-stage variant for the largest records -------------------------------------------------
+// An 8x8 Double record is 528 B of slot; a two-stage ring is 1 056 B per thread, three 64-thread CTAs per SM
+// = six warps, too few for the FP64 dependency chains of det / solve / inverse (ncu: FP64 pipe ~21 % busy,
+// `wait` the top stall).  With ONE stage per CTA the registers become the limit (four CTAs = eight warps)
+// and the copy/compute overlap comes from the other resident CTAs instead of from a prefetched tile.
+template <class Op, int THREADS, int IPT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel_1s(TileArgs a) {
+    using C = TileCfg<Op, THREADS, IPT, 1>;
+    using I0 = typename C::I0; using I1 = typename C::I1;
+    using O0 = typename C::O0; using O1 = typename C::O1;
+    constexpr int TILE = C::TILE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long tile_q[2];
+
+    const int tid = threadIdx.x;
+    const unsigned long long n_tiles = (a.n_items + TILE - 1) / TILE;
+    const unsigned char* g_in0 = (const unsigned char*)a.in0;
+    const unsigned char* g_in1 = (const unsigned char*)a.in1;
+    unsigned char* g_out0 = (unsigned char*)a.out0;
+    unsigned char* g_out1 = (unsigned char*)a.out1;
+
+    pdl_trigger();
+    pdl_wait();
+    TileClaimer claimer;
+    if (tid == 0) tile_q[0] = claimer.next(a.sched, a.claim);
+    __syncthreads();
+    int q = 0;
+    while (true) {
+        const unsigned long long tile = tile_q[q];
+        if (tile >= n_tiles) break;
+        const unsigned long long first = tile * TILE;
+        const unsigned long long left = a.n_items - first;
+        const int nv = left < (unsigned long long)TILE ? (int)left : TILE;
+        unsigned char* s0 = smem;
+        unsigned char* s1 = s0 + TILE * I0::stride;
+        unsigned char* so = C::OUT0 == 0 ? s0 : (C::OUT0 == 1 ? s1 : smem + C::IN_STAGE);
+        tile_load_async<I0, TILE, THREADS>(s0, g_in0 + first * I0::bytes, nv, tid);
+        tile_load_async<I1, TILE, THREADS>(s1, g_in1 + first * I1::bytes, nv, tid);
+        cp_async_commit();
+        if (tid == 0) tile_q[q ^ 1] = claimer.next(a.sched, a.claim);   // the next claim travels while this tile lands
+        cp_async_wait<0>();
+        __syncthreads();
+        #pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+            const int it = tid + j * THREADS;
+            if (it < nv) {
+                RegArr<I0> r0; RegArr<I1> r1; RegArr<O0> w0; RegArr<O1> w1;
+                if constexpr (I0::bytes > 0) I0::load(s0, it, r0.v);
+                if constexpr (I1::bytes > 0 && !LazyIn1<Op>::value) I1::load(s1, it, r1.v);
+                if constexpr (StreamsOut<Op>::value) {
+                    static_assert(C::OUT0 == 0 || C::OUT0 == 1, "streamed results go in place over an input record");
+                    SlotWriter<std::conditional_t<C::OUT0 == 0, I0, I1>> wr{so, it};
+                    if constexpr (LazyIn1<Op>::value) {
+                        SlotReader<I1> rd{s1, it};
+                        Op::run_stream(r0.v, rd, wr, w1.v);
+                    } else {
+                        Op::run_stream(r0.v, r1.v, wr, w1.v);
+                    }
+                } else {
+                    run_op<Op>(r0.v, r1.v, w0.v, w1.v, a.prm);
+                }
+                if constexpr (O0::bytes > 0 && !StreamsOut<Op>::value) {
+                    if constexpr (C::OUT0 == -1) stg_direct<O0::bytes>(g_out0 + (first + it) * O0::bytes, w0.v);
+                    else if constexpr (C::OUT0 == 0) I0::store(so, it, w0.v);
+                    else if constexpr (C::OUT0 == 1) I1::store(so, it, w0.v);
+                    else O0::store(so, it, w0.v);
+                }
+                if constexpr (O1::bytes > 0) stg_direct<O1::bytes>(g_out1 + (first + it) * O1::bytes, w1.v);
+            }
+        }
+        if constexpr (C::OUT0 >= 0) {
+            __syncthreads();
+            if constexpr (C::OUT0 == 0) tile_store<I0, TILE, THREADS>(so, g_out0 + first * O0::bytes, nv, tid);
+            else if constexpr (C::OUT0 == 1) tile_store<I1, TILE, THREADS>(so, g_out0 + first * O0::bytes, nv, tid);
+            else tile_store<O0, TILE, THREADS>(so, g_out0 + first * O0::bytes, nv, tid);
+        }
+        __syncthreads();      // the slot is free again; tile_q[q ^ 1] is visible
+        q ^= 1;
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.sched + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+            a.sched[0] = 0;
+            a.sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 // ---- SoA skeleton: element e of item b at base[e * stride + b] ----------------------------
 // Thread-per-item access is already coalesced in this layout (a warp reads 128/256 contiguous
 // bytes per element), but a thread that loads its 9..32 elements, runs a division chain and

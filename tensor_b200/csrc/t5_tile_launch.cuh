@@ -27,7 +27,9 @@ template <class Op, int THREADS, int IPT, int STAGES, int MIN_BLOCKS>
 static int launch_tile(const Shard& s, const void* in0, const void* in1, void* out0, void* out1, const OpParams& prm) {
     using C = TileCfg<Op, THREADS, IPT, STAGES>;
     static_assert(C::SMEM <= 227 * 1024, "tile does not fit in shared memory");
-    auto kern = tile_kernel<Op, THREADS, IPT, STAGES, MIN_BLOCKS>;
+    void (*kern)(TileArgs);
+    if constexpr (STAGES == 1) kern = tile_kernel_1s<Op, THREADS, IPT, MIN_BLOCKS>;
+    else kern = tile_kernel<Op, THREADS, IPT, STAGES, MIN_BLOCKS>;
     static int grid_cap[T5_MAX_DEVICES] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
@@ -93,7 +95,8 @@ template <class Op> struct Geo {
 template <class Op>
 static int launch_op(const Shard& s, const void* in0, const void* in1, void* out0, void* out1, const OpParams& prm = OpParams{}) {
     using g = typename Geo<Op>::type;
-    if (s.layout == T5L_SOA) return launch_soa<Op, g::threads, g::ipt, g::stages, g::min_blocks>(s, in0, in1, out0, out1, prm);
+    // (the one-stage geometry exists for the AoS pipeline only: SoA batches keep a two-stage ring)
+    if (s.layout == T5L_SOA) return launch_soa<Op, g::threads, g::ipt, (g::stages < 2 ? 2 : g::stages), g::min_blocks>(s, in0, in1, out0, out1, prm);
     return launch_tile<Op, g::threads, g::ipt, g::stages, g::min_blocks>(s, in0, in1, out0, out1, prm);
 }
 
