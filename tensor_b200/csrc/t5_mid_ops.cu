@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
     constexpr int G = C::G;
     constexpr int VPR = 16 / (int)sizeof(T);   // elements per 16-B chunk
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ unsigned long long tile_q[STAGES];
+    __shared__ unsigned long long tile_q[STAGES + 1];
 
     const int tid = threadIdx.x;
     const unsigned long long n_tiles = (a.n_items + G - 1) / G;
@@ -77,31 +77,8 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
         cp_async_commit();
     };
 
-    pdl_trigger();
-    pdl_wait();
-    unsigned long long next_claim = 0;
-    TileClaimer claimer;
-    if (tid == 0) {
-        #pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = claimer.next(a.sched, a.claim);
-        next_claim = claimer.next(a.sched, a.claim);
-    }
-    __syncthreads();
-    #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(tile_q[s], s);
-
     const int il = tid / P, r = tid % P;
-    int stage = 0;
-    while (true) {
-        const unsigned long long tile = tile_q[stage];
-        if (tile >= n_tiles) break;
-        int pf = stage + STAGES - 1; if (pf >= STAGES) pf -= STAGES;
-        if (tid == 0) tile_q[pf] = next_claim;
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        issue(tile_q[pf], pf);
-        if (tid == 0) next_claim = claimer.next(a.sched, a.claim);
-
+    auto compute = [&](unsigned long long tile, int stage) {
         const unsigned long long first = tile * G;
         const unsigned long long left = a.n_items - first;
         const int nv = left < (unsigned long long)G ? (int)left : G;
@@ -126,7 +103,52 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
             #pragma unroll
             for (int c = 0; c < Q / VPR; ++c) st_global_stream16(dst + c * VPR, reinterpret_cast<const uint4*>(acc)[c]);
         }
-        if (++stage == STAGES) stage = 0;
+    };
+
+    pdl_trigger();
+    pdl_wait();
+    TileClaimer claimer;
+    if constexpr (STAGES == 1) {
+        // one slot per CTA: residency is bounded by threads instead of by the ring (16x16 Double: 3 -> 6 CTAs per SM);
+        // the other resident CTAs cover this one's copy, the next claim travels while the tile lands
+        if (tid == 0) tile_q[0] = claimer.next(a.sched, a.claim);
+        __syncthreads();
+        int q = 0;
+        while (true) {
+            const unsigned long long tile = tile_q[q];
+            if (tile >= n_tiles) break;
+            issue(tile, 0);
+            if (tid == 0) tile_q[q ^ 1] = claimer.next(a.sched, a.claim);
+            cp_async_wait<0>();
+            __syncthreads();
+            compute(tile, 0);
+            __syncthreads();
+            q ^= 1;
+        }
+    } else {
+        unsigned long long next_claim = 0;
+        if (tid == 0) {
+            #pragma unroll
+            for (int s = 0; s < STAGES - 1; ++s) tile_q[s] = claimer.next(a.sched, a.claim);
+            next_claim = claimer.next(a.sched, a.claim);
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) issue(tile_q[s], s);
+
+        int stage = 0;
+        while (true) {
+            const unsigned long long tile = tile_q[stage];
+            if (tile >= n_tiles) break;
+            int pf = stage + STAGES - 1; if (pf >= STAGES) pf -= STAGES;
+            if (tid == 0) tile_q[pf] = next_claim;
+            cp_async_wait<(STAGES >= 2 ? STAGES - 2 : 0)>();
+            __syncthreads();
+            issue(tile_q[pf], pf);
+            if (tid == 0) next_claim = claimer.next(a.sched, a.claim);
+            compute(tile, stage);
+            if (++stage == STAGES) stage = 0;
+        }
     }
     cp_async_wait<0>();
     if (tid == 0) {
@@ -172,11 +194,11 @@ static int dispatch(const Shard& s, int m, int k, int n, const void* A, const vo
     // 8x8: 256 threads x 2 stages = 3 CTAs (768 threads) per SM.  64 x 4 is as fast in isolation but, with
     // only 8 warps per SM on the FP64 chains, lost 25% inside a long bench run (clock-sensitive).
     if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 256, 2>(s, A, B, C);
-    if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 128, 2>(s, A, B, C);
-    if (m == 12 && k == 12 && n == 12) return launch<T, 12, 12, 12, 192, 2>(s, A, B, C);
+    if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 128, 1>(s, A, B, C);
+    if (m == 12 && k == 12 && n == 12) return launch<T, 12, 12, 12, 192, 1>(s, A, B, C);
     if constexpr (sizeof(T) == 8) {   // rows must be whole 16-byte chunks
         if (m == 6 && k == 6 && n == 6) return launch<T, 6, 6, 6, 192, 3>(s, A, B, C);
-        if (m == 10 && k == 10 && n == 10) return launch<T, 10, 10, 10, 160, 2>(s, A, B, C);
+        if (m == 10 && k == 10 && n == 10) return launch<T, 10, 10, 10, 160, 1>(s, A, B, C);
     }
     return T5I_NOT_SPECIALISED;
 }
