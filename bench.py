@@ -90,7 +90,9 @@ WORKLOADS = {
     "echelon4x5_f64_4M": dict(op="row_echelon", dtype="f64", rows=4, cols=5, pivot_cols=4, batch=1 << 22, bytes=321, bound="hbm",
                               desc="4Mi 4x5 Double triangularSolve ([A | b], pivots in A)"),
     "echelon6x7_f64_1M": dict(op="row_echelon", dtype="f64", rows=6, cols=7, batch=1 << 20, bytes=673, bound="hbm",
-                              desc="1Mi 6x7 Double rowEchelonForm (any-shape kernel: shared-memory resident)"),
+                              desc="1Mi 6x7 Double rowEchelonForm (registers: 27 step instances)"),
+    "echelon7x9_f64_1M": dict(op="row_echelon", dtype="f64", rows=7, cols=9, batch=1 << 20, bytes=1009, bound="hbm",
+                              desc="1Mi 7x9 Double rowEchelonForm (any-shape kernel: shared-memory resident)"),
     "matmul128_f32_64K": dict(op="matmul", dtype="f32", m=128, k=128, n=128, batch=1 << 16, bytes=196608, flops=4194304, bound="hbm",
                               desc="64Ki 128x128 Float .*. on tcgen05 tensor cores (3xTF32 split, TMEM accumulators; 21 flop/B: HBM-bound)"),
     "matmul64_f32_256K": dict(op="matmul", dtype="f32", m=64, k=64, n=64, batch=1 << 18, bytes=49152, flops=524288, bound="hbm",
@@ -106,7 +108,7 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
           "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
-          "inverse6_f64_1M", "inverse8_f64_1M", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M"]
+          "inverse6_f64_1M", "inverse8_f64_1M", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M", "echelon7x9_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 

@@ -46,7 +46,7 @@ int small_char_poly(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_min_poly(const Shard& s, int dtype, int n, const void* A, void* O, void* degree);
 // t5_solve_many.cu: matrix right-hand sides (2, 3, 4 or n columns) for 5 <= n <= 8, AoS and SoA
 int many_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
-// t5_echelon.cu: rowEchelonForm of the small fixed shapes (n x n, n x (n+1), n x 2n for n = 2..4), AoS and SoA
+// t5_echelon.cu: rowEchelonForm in registers (n x n, n x (n+1) for n = 2..8, n x 2n for n = 2..4), AoS and SoA
 int small_row_echelon(const Shard& s, int dtype, int rows, int cols, int pivot_cols, const void* A, void* O, void* rank);
 
 // ---- t5_mid_ops.cu: row-per-thread contractions for 0.25-4 KiB records (8x8, 16x16, ...) -----

@@ -13,7 +13,7 @@ import oracle
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "row_echelon_regression.json")
 NPD = {"f64": np.float64, "f32": np.float32}
 CODE = {"f64": oracle.F64, "f32": oracle.F32}
-SHAPES = [(1, 1), (2, 2), (3, 3), (4, 4), (3, 4), (4, 5), (4, 8), (5, 3), (6, 7), (8, 8), (8, 16), (2, 16), (8, 1)]
+SHAPES = [(1, 1), (2, 2), (3, 3), (4, 4), (3, 4), (4, 5), (4, 8), (5, 3), (6, 7), (8, 8), (8, 16), (2, 16), (8, 1), (7, 7), (8, 9), (6, 5), (7, 9)]
 
 
 def bits(a):
@@ -138,7 +138,8 @@ def test_row_echelon_bit_exact(ctx, dname, m, n):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dname", ["f64", "f32"])
-@pytest.mark.parametrize("m,n", [(2, 2), (3, 3), (4, 4), (2, 3), (3, 4), (4, 5), (2, 4), (3, 6), (4, 8)])
+@pytest.mark.parametrize("m,n", [(2, 2), (3, 3), (4, 4), (2, 3), (3, 4), (4, 5), (2, 4), (3, 6), (4, 8),
+                                 (5, 5), (6, 6), (7, 7), (8, 8), (5, 6), (6, 7), (7, 8), (8, 9)])
 def test_row_echelon_register_shapes_soa_and_all_deficient(ctx, dname, m, n):
     """The shapes with a register-resident kernel: SoA layout, and batches in which EVERY item is rank-deficient
     (the run-time rank then selects the off-diagonal step instances for whole warps)."""

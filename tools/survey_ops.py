@@ -83,6 +83,11 @@ def main():
             A45 = ctx.synthetic((4, 5), dt, B, SEED, 16)
             add(f"rowEchelonForm 4x4 {tag}", B * (32 * es + 1), lambda: tb.row_echelon_form(A4))
             add(f"rowEchelonForm 4x5 (triangularSolve) {tag}", B * (40 * es + 1), lambda: tb.row_echelon_form(A45, 4))
+            A67 = ctx.synthetic((6, 7), dt, B // 4, SEED, 30)
+            A79 = ctx.synthetic((7, 9), dt, B // 4, SEED, 31)
+            add(f"rowEchelonForm 6x7 {tag}", (B // 4) * (84 * es + 1), lambda: tb.row_echelon_form(A67, 6))
+            add(f"rowEchelonForm 7x9 (any-shape kernel) {tag}", (B // 4) * (126 * es + 1), lambda: tb.row_echelon_form(A79))
+            A67.free(); A79.free()
             add(f"rowEchelonForm 8x8 {tag}", (B // 4) * (128 * es + 1), lambda: tb.row_echelon_form(A8))
             A5, B5 = ctx.synthetic((5, 5), dt, B, SEED, 7), ctx.synthetic((5, 5), dt, B, SEED, 8)
             add(f"matmul 5x5 {tag}", B * 75 * es, lambda: tb.matmul(A5, B5))
@@ -116,6 +121,12 @@ def main():
             add(f"transpose 128x128 {tag}", (B // 1024) * 32768 * es, lambda: tb.transpose(A128))
             add(f"transpose 20x40 {tag}", (B // 64) * 1600 * es, lambda: tb.transpose(A2040))
             A128.free(); A2040.free()
+            b3s, b4s = ctx.synthetic((3,), dt, B, SEED + 1, 28), ctx.synthetic((4,), dt, B, SEED + 1, 29)
+            for nn, AA, bb in ((3, A3, b3s), (4, A4, b4s)):
+                add(f"det {nn}x{nn} {tag}", B * (nn * nn + 1) * es, lambda: tb.det(AA))
+                add(f"inverse {nn}x{nn} {tag}", B * (2 * nn * nn * es + 1), lambda: tb.inverse(AA))
+                add(f"solve {nn}x{nn} {tag}", B * ((nn * nn + 2 * nn) * es + 1), lambda: tb.solve(AA, bb))
+            b3s.free(); b4s.free()
             add(f"det 2x2 {tag}", B * 5 * es, lambda: tb.det(A2))
             add(f"inverse 2x2 {tag}", B * (8 * es) + B, lambda: tb.inverse(A2))
             add(f"solve 4x4, 4 rhs {tag}", B * (48 * es) + B, lambda: tb.solve(A4, B44))
