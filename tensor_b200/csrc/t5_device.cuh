@@ -16,6 +16,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+template <int BYTES>   // 4- or 8-byte asynchronous copies (rows that are not whole 16-byte chunks)
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gsrc) {
+    static_assert(BYTES == 4 || BYTES == 8, "cp.async.ca moves 4, 8 or 16 bytes");
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -107,6 +107,101 @@ static int prod_launch(const Shard& s, int P, int K, int Q, int nc, const void* 
     return ok();
 }
 
+// ---- products of small records with ODD extents (7x7, 9x9 .. 19x19; any n for 4-byte elements) ----
+// Between the specialised kernels (n <= 8, and the row-per-thread kernel for 16-byte-multiple rows) the per-output
+// kernel above re-reads A and B through L1 with one thread per result element, unvectorised for odd n, and two
+// run-time integer divisions each (tools/sweep_matmul.py: 0.13-0.3 of the HBM peak for n = 9..19).  Here a CTA
+// copies G whole items of A and of B into shared memory as two contiguous, coalesced runs; a thread owns four
+// adjacent results of one row: per k one A element (a broadcast for its neighbours) and four B elements (stride-1
+// across the warp), accumulated in the oracle's order - k ascending, multiply then add - so results are
+// bit-identical for all three element types; (item, row, column block) come from two multiply-highs.  1.5-1.9x the
+// per-output kernel on those shapes (a 2 x 4 register block measured slower: the kernel is latency-, not
+// LDS-bound); even extents of 8-byte elements and rectangular shapes measured no better and stay where they were.
+template <class T, int JT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+stagedprod_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int m, int k, int n, int nb, unsigned magic_units,
+                  unsigned magic_nb, unsigned long long count, int G) {
+    using R = Arith<T>;
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    const unsigned dA = m * k, dB = k * n, dC = m * n, units = m * nb;
+    T* sA = reinterpret_cast<T*>(sp_smem);
+    T* sB = sA + (size_t)G * dA;
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : (unsigned)G;
+        const T* ga = A + (size_t)g0 * dA;
+        const T* gb = B + (size_t)g0 * dB;
+        #pragma unroll 4
+        for (unsigned l = threadIdx.x; l < gc * dA; l += THREADS) sA[l] = __ldg(ga + l);
+        #pragma unroll 4
+        for (unsigned l = threadIdx.x; l < gc * dB; l += THREADS) sB[l] = __ldg(gb + l);
+        __syncthreads();
+        for (unsigned u = threadIdx.x; u < gc * units; u += THREADS) {
+            const unsigned item = units == 1 ? u : __umulhi(u, magic_units), r = u - item * units;   // (a divisor of 1 has no 32-bit magic)
+            const unsigned i = nb == 1 ? r : __umulhi(r, magic_nb), j0 = (r - i * nb) * JT;
+            const T* a = sA + item * dA + i * k;
+            const T* b = sB + item * dB + j0;
+            T* c = C + (size_t)(g0 + item) * dC + (size_t)i * n + j0;
+            T acc[JT];
+            #pragma unroll
+            for (int t = 0; t < JT; ++t) acc[t] = R::zero();
+            if (j0 + JT <= (unsigned)n) {
+                for (int kk = 0; kk < k; ++kk) {
+                    const T av = a[kk];
+                    #pragma unroll
+                    for (int t = 0; t < JT; ++t) acc[t] = R::add(acc[t], R::mul(av, b[kk * n + t]));
+                }
+                #pragma unroll
+                for (int t = 0; t < JT; ++t) c[t] = acc[t];
+            } else {
+                const int jt = n - (int)j0;
+                for (int kk = 0; kk < k; ++kk) {
+                    const T av = a[kk];
+                    #pragma unroll
+                    for (int t = 0; t < JT; ++t)
+                        if (t < jt) acc[t] = R::add(acc[t], R::mul(av, b[kk * n + t]));
+                }
+                #pragma unroll
+                for (int t = 0; t < JT; ++t)
+                    if (t < jt) c[t] = acc[t];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T>
+static int stagedprod_launch(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
+    constexpr int THREADS = 256, JT = 4;
+    auto kern = stagedprod_kernel<T, JT, THREADS>;
+    const size_t item_bytes = ((size_t)m * k + (size_t)k * n) * sizeof(T);
+    const int nb = (n + JT - 1) / JT;
+    const unsigned units = (unsigned)m * nb;
+    long long G = (long long)((32 * 1024) / item_bytes);
+    if (G * units > 65535) G = 65535 / units;           // the multiply-high divisions are exact below 2^16
+    if (G < 2) return T5I_NOT_SPECIALISED;
+    const int smem = (int)(G * item_bytes);
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const size_t groups = (s.count + G - 1) / G, cap = (size_t)occ * sm_count();
+    const int grid = (int)(groups < cap ? groups : cap);
+    const unsigned mu = (unsigned)((0x100000000ull + units - 1) / units), mn = (unsigned)((0x100000000ull + (unsigned)nb - 1) / (unsigned)nb);
+    kern<<<grid, THREADS, smem, s.stream>>>((const T*)A, (const T*)B, (T*)C, m, k, n, nb, mu, mn, (unsigned long long)s.count, (int)G);
+    return ok();
+}
+
+int generic_stagedprod(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C) {
+    if (s.layout != T5L_AOS || m < 5 || k < 5 || n < 5 || m > 24 || k > 24 || n > 24) return T5I_NOT_SPECIALISED;
+    if (dtype != T5D_F32 && n % 2 == 0) return T5I_NOT_SPECIALISED;     // even rows of 8-byte elements: the vectorised per-output kernel ties
+    if (s.count == 0) return T5I_OK;
+    switch (dtype) {
+        case T5D_F64: return stagedprod_launch<double>(s, m, k, n, A, B, C);
+        case T5D_F32: return stagedprod_launch<float>(s, m, k, n, A, B, C);
+        case T5D_I64: return stagedprod_launch<long long>(s, m, k, n, A, B, C);
+    }
+    return T5I_UNSUPPORTED;
+}
+
 // ---- long dot products: `dot` of n-vectors and `prod n` down to a scalar (BASELINE configs[3] with
 // n = 2: 8x8 : 8x8 -> scalar), n > 4 ----
 // The fold `acc = acc + x_j*y_j`, j ascending, is one sequential chain per item (the specification

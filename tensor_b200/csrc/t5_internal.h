@@ -54,6 +54,7 @@ int mid_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, co
 
 // ---- t5_generic.cu: any-shape kernels (AoS only) ---------------------------------
 // C[P x Q] = A[P x K] . B[K x Q] per item; ncontract == 0 -> single multiply.
+int generic_stagedprod(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
 int generic_longdot(const Shard& s, int dtype, int K, const void* X, const void* Y, void* O);
 int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int ncontract, const void* A, const void* B, void* C);
 // out[b][i] = in[b][perm[i]], perm resident on the device (d entries)

@@ -26,22 +26,27 @@ struct Args {
     unsigned claim;
 };
 
+constexpr int up16(int x) { return (x + 15) / 16 * 16; }
+
 template <class T, int P, int K, int Q, int THREADS, int STAGES>
 struct Cfg {
     static constexpr int G = THREADS / P;                       // items per tile
     static constexpr int A_ROW = K * (int)sizeof(T);
-    static constexpr int A_CPR = A_ROW / 16;                    // chunks per A row
-    static constexpr int A_RS = A_ROW + ((A_CPR % 2 == 0) ? 16 : 0);
-    static constexpr int A_STAGE = G * P * A_RS;
     static constexpr int B_ROW = Q * (int)sizeof(T);
-    static constexpr int B_BYTES = K * B_ROW;
+    // rows that are whole 16-byte chunks are copied chunk-wise and B items stay packed; other extents (odd n for
+    // 8-byte elements, n % 4 != 0 for Float) are copied element-wise into rows padded to the next chunk
+    static constexpr bool ALIGNED = A_ROW % 16 == 0 && B_ROW % 16 == 0;
+    static constexpr int A_CPR = up16(A_ROW) / 16;              // chunks per (padded) A row
+    static constexpr int A_RS = up16(A_ROW) + ((A_CPR % 2 == 0) ? 16 : 0);
+    static constexpr int A_STAGE = G * P * A_RS;
+    static constexpr int B_RS = ALIGNED ? B_ROW : up16(B_ROW);  // B row pitch inside an item
+    static constexpr int B_BYTES = K * B_RS;
     static constexpr int B_CPI = B_BYTES / 16;
     static constexpr int B_ITEM = B_BYTES + ((B_CPI % 2 == 0) ? 16 : 0);
     static constexpr int B_STAGE = G * B_ITEM;
     static constexpr int STAGE = A_STAGE + B_STAGE;
     static constexpr int SMEM = STAGES * STAGE;
-    static_assert(A_ROW % 16 == 0 && B_ROW % 16 == 0, "rows must be multiples of 16 bytes");
-    static_assert(THREADS % P == 0 && THREADS % 32 == 0, "bad thread count");
+    static_assert(THREADS % 32 == 0 && G >= 1, "bad thread count");
 };
 
 template <class T, int P, int K, int Q, int THREADS, int STAGES>
@@ -67,12 +72,23 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
             unsigned char* sA = smem + stage * C::STAGE;
             unsigned char* sB = sA + C::A_STAGE;
             const unsigned char* srcA = gA + first * (size_t)(P * C::A_ROW);
-            const unsigned char* srcB = gB + first * (size_t)C::B_BYTES;
-            const int nchA = nv * P * C::A_CPR, nchB = nv * C::B_CPI;
-            for (int ch = tid; ch < nchA; ch += THREADS)
-                cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
-            for (int ch = tid; ch < nchB; ch += THREADS)
-                cp_async16(sB + (ch / C::B_CPI) * C::B_ITEM + (ch % C::B_CPI) * 16, srcB + (size_t)ch * 16);
+            const unsigned char* srcB = gB + first * (size_t)(K * C::B_ROW);
+            if constexpr (C::ALIGNED) {
+                const int nchA = nv * P * C::A_CPR, nchB = nv * C::B_CPI;
+                for (int ch = tid; ch < nchA; ch += THREADS)
+                    cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
+                for (int ch = tid; ch < nchB; ch += THREADS)
+                    cp_async16(sB + (ch / C::B_CPI) * C::B_ITEM + (ch % C::B_CPI) * 16, srcB + (size_t)ch * 16);
+            } else {
+                constexpr int ES = (int)sizeof(T);
+                const int neA = nv * P * K, neB = nv * K * Q;
+                for (int e = tid; e < neA; e += THREADS)
+                    cp_async_small<ES>(sA + (e / K) * C::A_RS + (e % K) * ES, srcA + (size_t)e * ES);
+                for (int e = tid; e < neB; e += THREADS) {
+                    const int item = e / (K * Q), rem = e - item * (K * Q);
+                    cp_async_small<ES>(sB + item * C::B_ITEM + (rem / Q) * C::B_RS + (rem % Q) * ES, srcB + (size_t)e * ES);
+                }
+            }
         }
         cp_async_commit();
     };
@@ -82,26 +98,32 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
         const unsigned long long first = tile * G;
         const unsigned long long left = a.n_items - first;
         const int nv = left < (unsigned long long)G ? (int)left : G;
-        if (il < nv) {
+        if (il < nv && il < G) {          // (threads beyond G * P idle when P does not divide the CTA)
             const unsigned char* sA = smem + stage * C::STAGE + (il * P + r) * C::A_RS;
             const unsigned char* sB = smem + stage * C::STAGE + C::A_STAGE + il * C::B_ITEM;
-            alignas(16) T av[K];
+            constexpr int KP = C::A_CPR * VPR, QC = (Q + VPR - 1) / VPR, QP = QC * VPR;   // extents rounded up to whole chunks
+            alignas(16) T av[KP];
             #pragma unroll
             for (int c = 0; c < C::A_CPR; ++c) reinterpret_cast<uint4*>(av)[c] = reinterpret_cast<const uint4*>(sA)[c];
-            alignas(16) T acc[Q];
+            alignas(16) T acc[QP];
             #pragma unroll
             for (int q = 0; q < Q; ++q) acc[q] = R::zero();
             #pragma unroll
             for (int k = 0; k < K; ++k) {
-                alignas(16) T bv[Q];
+                alignas(16) T bv[QP];            // (the padding lanes of a partial last chunk are never read)
                 #pragma unroll
-                for (int c = 0; c < Q / VPR; ++c) reinterpret_cast<uint4*>(bv)[c] = reinterpret_cast<const uint4*>(sB + k * C::B_ROW)[c];
+                for (int c = 0; c < QC; ++c) reinterpret_cast<uint4*>(bv)[c] = reinterpret_cast<const uint4*>(sB + k * C::B_RS)[c];
                 #pragma unroll
                 for (int q = 0; q < Q; ++q) acc[q] = R::add(acc[q], R::mul(av[k], bv[q]));
             }
             T* dst = gC + ((first + il) * P + r) * (size_t)Q;
-            #pragma unroll
-            for (int c = 0; c < Q / VPR; ++c) st_global_stream16(dst + c * VPR, reinterpret_cast<const uint4*>(acc)[c]);
+            if constexpr (C::ALIGNED) {
+                #pragma unroll
+                for (int c = 0; c < Q / VPR; ++c) st_global_stream16(dst + c * VPR, reinterpret_cast<const uint4*>(acc)[c]);
+            } else {
+                #pragma unroll
+                for (int q = 0; q < Q; ++q) dst[q] = acc[q];
+            }
         }
     };
 
@@ -196,7 +218,31 @@ static int dispatch(const Shard& s, int m, int k, int n, const void* A, const vo
     if (m == 8 && k == 8 && n == 8) return launch<T, 8, 8, 8, 256, 2>(s, A, B, C);
     if (m == 16 && k == 16 && n == 16) return launch<T, 16, 16, 16, 128, 1>(s, A, B, C);
     if (m == 12 && k == 12 && n == 12) return launch<T, 12, 12, 12, 192, 1>(s, A, B, C);
+    if (m == 20 && k == 20 && n == 20) return launch<T, 20, 20, 20, 160, 1>(s, A, B, C);
+    if (m == 24 && k == 24 && n == 24) return launch<T, 24, 24, 24, 192, 1>(s, A, B, C);
+    // odd extents (element-wise staging into padded rows): one-stage, CTAs of whole warps, a few idle threads
+    if constexpr (sizeof(T) == 8) {
+        if (m == 7 && k == 7 && n == 7) return launch<T, 7, 7, 7, 256, 1>(s, A, B, C);
+        if (m == 9 && k == 9 && n == 9) return launch<T, 9, 9, 9, 256, 1>(s, A, B, C);
+        if (m == 11 && k == 11 && n == 11) return launch<T, 11, 11, 11, 256, 1>(s, A, B, C);
+        if (m == 13 && k == 13 && n == 13) return launch<T, 13, 13, 13, 256, 1>(s, A, B, C);
+        if (m == 15 && k == 15 && n == 15) return launch<T, 15, 15, 15, 256, 1>(s, A, B, C);
+        if (m == 17 && k == 17 && n == 17) return launch<T, 17, 17, 17, 256, 1>(s, A, B, C);
+        if (m == 19 && k == 19 && n == 19) return launch<T, 19, 19, 19, 256, 1>(s, A, B, C);
+    } else {
+        if (m == 9 && k == 9 && n == 9) return launch<T, 9, 9, 9, 256, 1>(s, A, B, C);
+        if (m == 10 && k == 10 && n == 10) return launch<T, 10, 10, 10, 256, 1>(s, A, B, C);
+        if (m == 11 && k == 11 && n == 11) return launch<T, 11, 11, 11, 256, 1>(s, A, B, C);
+        if (m == 13 && k == 13 && n == 13) return launch<T, 13, 13, 13, 256, 1>(s, A, B, C);
+        if (m == 14 && k == 14 && n == 14) return launch<T, 14, 14, 14, 256, 1>(s, A, B, C);
+        if (m == 15 && k == 15 && n == 15) return launch<T, 15, 15, 15, 256, 1>(s, A, B, C);
+        if (m == 17 && k == 17 && n == 17) return launch<T, 17, 17, 17, 256, 1>(s, A, B, C);
+        if (m == 18 && k == 18 && n == 18) return launch<T, 18, 18, 18, 256, 1>(s, A, B, C);
+        if (m == 19 && k == 19 && n == 19) return launch<T, 19, 19, 19, 256, 1>(s, A, B, C);
+    }
     if constexpr (sizeof(T) == 8) {   // rows must be whole 16-byte chunks
+        if (m == 14 && k == 14 && n == 14) return launch<T, 14, 14, 14, 224, 1>(s, A, B, C);
+        if (m == 18 && k == 18 && n == 18) return launch<T, 18, 18, 18, 288, 1>(s, A, B, C);
         if (m == 6 && k == 6 && n == 6) return launch<T, 6, 6, 6, 192, 3>(s, A, B, C);
         if (m == 10 && k == 10 && n == 10) return launch<T, 10, 10, 10, 160, 1>(s, A, B, C);
     }
