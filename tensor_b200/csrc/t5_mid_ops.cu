@@ -220,6 +220,10 @@ static int dispatch(const Shard& s, int m, int k, int n, const void* A, const vo
     if (m == 12 && k == 12 && n == 12) return launch<T, 12, 12, 12, 192, 1>(s, A, B, C);
     if (m == 20 && k == 20 && n == 20) return launch<T, 20, 20, 20, 160, 1>(s, A, B, C);
     if (m == 24 && k == 24 && n == 24) return launch<T, 24, 24, 24, 192, 1>(s, A, B, C);
+    if constexpr (sizeof(T) == 4) {   // a warp per matrix; 8-byte 32x32 measured slower than the blocked product (FP64 / IMAD bound)
+        if (m == 32 && k == 32 && n == 32) return launch<T, 32, 32, 32, 128, 1>(s, A, B, C);
+    }
+    if (m == 48 && k == 48 && n == 48) return launch<T, 48, 48, 48, 96, 1>(s, A, B, C);
     // odd extents (element-wise staging into padded rows): one-stage, CTAs of whole warps, a few idle threads
     if constexpr (sizeof(T) == 8) {
         if (m == 7 && k == 7 && n == 7) return launch<T, 7, 7, 7, 256, 1>(s, A, B, C);
