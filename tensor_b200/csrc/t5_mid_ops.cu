@@ -224,6 +224,16 @@ static int dispatch(const Shard& s, int m, int k, int n, const void* A, const vo
         if (m == 32 && k == 32 && n == 32) return launch<T, 32, 32, 32, 128, 1>(s, A, B, C);
     }
     if (m == 48 && k == 48 && n == 48) return launch<T, 48, 48, 48, 96, 1>(s, A, B, C);
+    // matrix . vector beyond the tile pipeline's n <= 8: a thread per row, the vector broadcast from shared memory
+    if (n == 1 && m == k) {
+        if (m == 9) return launch<T, 9, 9, 1, 256, 1>(s, A, B, C);
+        if (m == 10) return launch<T, 10, 10, 1, 256, 1>(s, A, B, C);
+        if (m == 12) return launch<T, 12, 12, 1, 256, 1>(s, A, B, C);
+        if (m == 16) return launch<T, 16, 16, 1, 256, 1>(s, A, B, C);
+        if (m == 20) return launch<T, 20, 20, 1, 256, 1>(s, A, B, C);
+        if (m == 24) return launch<T, 24, 24, 1, 256, 1>(s, A, B, C);
+        if (m == 32) return launch<T, 32, 32, 1, 256, 1>(s, A, B, C);
+    }
     // odd extents (element-wise staging into padded rows): one-stage, CTAs of whole warps, a few idle threads
     if constexpr (sizeof(T) == 8) {
         if (m == 7 && k == 7 && n == 7) return launch<T, 7, 7, 7, 256, 1>(s, A, B, C);

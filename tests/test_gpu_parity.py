@@ -46,7 +46,8 @@ def inputs(dc, op_id, batch, da, db=None):
                                  (5, 5, 5), (6, 6, 6), (7, 7, 7), (10, 10, 10), (12, 12, 12), (16, 16, 16),
                                  (5, 5, 1), (8, 8, 1), (1, 7, 7), (1, 8, 8), (6, 6, 1),
                                  (9, 9, 9), (11, 11, 11), (13, 7, 19), (14, 14, 14), (17, 17, 17), (18, 18, 18), (19, 19, 19),
-                                 (20, 20, 20), (24, 24, 24), (5, 24, 9), (23, 5, 6), (32, 32, 32), (48, 48, 48)])
+                                 (20, 20, 20), (24, 24, 24), (5, 24, 9), (23, 5, 6), (32, 32, 32), (48, 48, 48),
+                                 (9, 9, 1), (16, 16, 1), (24, 24, 1), (32, 32, 1)])
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_matmul_bit_exact(ctx, dc, mkn, layout):
     m, k, n = mkn

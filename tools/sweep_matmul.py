@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tensor_b200 as tb
 from survey_ops import timed, SEED
 with tb.Context([0]) as ctx:
-    shapes = [(n, n, n) for n in list(range(2, 21)) + [24, 32, 48]] + [(3, 4, 1), (4, 3, 2), (2, 8, 2), (8, 4, 8), (16, 16, 1), (1, 16, 16), (4, 16, 4), (32, 32, 1)]
+    shapes = [(n, n, n) for n in list(range(2, 21)) + [24, 32, 48]] + [(3, 4, 1), (4, 3, 2), (2, 8, 2), (8, 4, 8), (16, 16, 1), (1, 16, 16), (4, 16, 4), (32, 32, 1), (9, 9, 1), (12, 12, 1), (24, 24, 1)]
     for dt, es in ((np.float64, 8), (np.float32, 4), (np.int64, 8)):
         for (m, k, n) in shapes:
             B = max(256, (256 << 20) // ((m * k + k * n + m * n) * es))
