@@ -94,18 +94,23 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
     };
 
     const int il = tid / P, r = tid % P;
+    // Rows that are not whole chunks would leave as 8- or 4-byte stores one row pitch apart (ncu: 8 of every 32 bytes
+    // of a sector used, half the L2 sectors excessive): those results are packed into the (consumed) A region of the
+    // slot first and the CTA writes the tile as one contiguous run.  One-stage kernels only (the slot is not a ring).
+    constexpr bool PACK_OUT = !C::ALIGNED && STAGES == 1 && Q <= K;
     auto compute = [&](unsigned long long tile, int stage) {
         const unsigned long long first = tile * G;
         const unsigned long long left = a.n_items - first;
         const int nv = left < (unsigned long long)G ? (int)left : G;
-        if (il < nv && il < G) {          // (threads beyond G * P idle when P does not divide the CTA)
+        constexpr int KP = C::A_CPR * VPR, QC = (Q + VPR - 1) / VPR, QP = QC * VPR;   // extents rounded up to whole chunks
+        alignas(16) T acc[QP];
+        const bool active = il < nv && il < G;          // (threads beyond G * P idle when P does not divide the CTA)
+        if (active) {
             const unsigned char* sA = smem + stage * C::STAGE + (il * P + r) * C::A_RS;
             const unsigned char* sB = smem + stage * C::STAGE + C::A_STAGE + il * C::B_ITEM;
-            constexpr int KP = C::A_CPR * VPR, QC = (Q + VPR - 1) / VPR, QP = QC * VPR;   // extents rounded up to whole chunks
             alignas(16) T av[KP];
             #pragma unroll
             for (int c = 0; c < C::A_CPR; ++c) reinterpret_cast<uint4*>(av)[c] = reinterpret_cast<const uint4*>(sA)[c];
-            alignas(16) T acc[QP];
             #pragma unroll
             for (int q = 0; q < Q; ++q) acc[q] = R::zero();
             #pragma unroll
@@ -116,14 +121,29 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
                 #pragma unroll
                 for (int q = 0; q < Q; ++q) acc[q] = R::add(acc[q], R::mul(av[k], bv[q]));
             }
-            T* dst = gC + ((first + il) * P + r) * (size_t)Q;
-            if constexpr (C::ALIGNED) {
-                #pragma unroll
-                for (int c = 0; c < Q / VPR; ++c) st_global_stream16(dst + c * VPR, reinterpret_cast<const uint4*>(acc)[c]);
-            } else {
-                #pragma unroll
-                for (int q = 0; q < Q; ++q) dst[q] = acc[q];
+            if constexpr (!PACK_OUT) {
+                T* dst = gC + ((first + il) * P + r) * (size_t)Q;
+                if constexpr (C::ALIGNED) {
+                    #pragma unroll
+                    for (int c = 0; c < Q / VPR; ++c) st_global_stream16(dst + c * VPR, reinterpret_cast<const uint4*>(acc)[c]);
+                } else {
+                    #pragma unroll
+                    for (int q = 0; q < Q; ++q) dst[q] = acc[q];
+                }
             }
+        }
+        if constexpr (PACK_OUT) {
+            T* sC = reinterpret_cast<T*>(smem + stage * C::STAGE);          // G * P * Q elements <= the A region (Q <= K)
+            __syncthreads();                                                 // every A row is in registers
+            if (active) {
+                #pragma unroll
+                for (int q = 0; q < Q; ++q) sC[(il * P + r) * Q + q] = acc[q];
+            }
+            __syncthreads();
+            T* dst = gC + first * (size_t)(P * Q);
+            const int total = nv * P * Q;
+            #pragma unroll 4
+            for (int e = tid; e < total; e += THREADS) dst[e] = sC[e];
         }
     };
 
