@@ -18,7 +18,7 @@ from tensor_b200 import _lib
 
 dims_st = st.lists(st.integers(1, 4), min_size=1, max_size=4)
 CPU = settings(max_examples=60, deadline=None)
-GPU = settings(max_examples=20, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+GPU = settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 
 
 def flat(dims, start=0):
@@ -115,7 +115,7 @@ def ctx():
 
 @pytest.mark.gpu
 @GPU
-@given(st.integers(1, 9), st.integers(1, 9), st.integers(1, 9), st.sampled_from([oracle.F64, oracle.F32, oracle.I64]),
+@given(st.integers(1, 24), st.integers(1, 24), st.integers(1, 24), st.sampled_from([oracle.F64, oracle.F32, oracle.I64]),
        st.integers(1, 700), st.integers(0, 2 ** 16))
 def test_gpu_matmul_random_shapes_bit_exact(ctx, m, k, n, dc, batch, op_id):
     import tensor_b200 as tb
@@ -193,3 +193,19 @@ def test_gpu_inverse_solve_echelon_agree_on_rank(ctx, n, dc, batch, op_id):
     assert np.array_equal(st_.to_numpy(), ost)
     assert np.array_equal(inv.to_numpy().view(np.uint8), oinv.view(np.uint8))
     assert np.array_equal(d.view(np.uint8), oracle.det(a, n).view(np.uint8))
+
+
+@pytest.mark.gpu
+@GPU
+@given(st.integers(5, 48), st.sampled_from(["square", "matvec", "vecmat"]), st.sampled_from([oracle.F64, oracle.F32, oracle.I64]),
+       st.integers(1, 400), st.integers(0, 2 ** 16))
+def test_gpu_square_and_matvec_sizes_bit_exact(ctx, n, kind, dc, batch, op_id):
+    """Every square size 5..48 and its matrix.vector / vector.matrix forms - the sizes served by the row-per-thread
+    kernel (aligned and padded-row variants, packed results), the staged kernel and the blocked product."""
+    import tensor_b200 as tb
+    m, k, q = {"square": (n, n, n), "matvec": (n, n, 1), "vecmat": (1, n, n)}[kind]
+    a = oracle.fill(dc, oracle.SEED_A, op_id, batch * m * k)
+    b = oracle.fill(dc, oracle.SEED_B, op_id, batch * k * q)
+    C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, q))).to_numpy()
+    want = oracle.matmul(a, b, m, k, q)
+    assert np.array_equal(np.ascontiguousarray(C).view(np.uint8), np.ascontiguousarray(want).view(np.uint8))
