@@ -1022,13 +1022,16 @@ row_echelon_kernel(const T* __restrict__ A, T* __restrict__ OUT, unsigned char* 
         const int total = nv * L;
         const T* g = A + first * (size_t)L;
         {
+            // asynchronous element copies: a CTA is only 2-4 warps, and with register-staged loads (4 in flight per
+            // thread) the kernel ran at the latency, not the bandwidth, of HBM (1.5 TB/s for Float and Double alike)
             int item = tid / L, e = tid - item * L;
-            #pragma unroll 4
             for (int idx = tid; idx < total; idx += TPB) {
-                w[e * P + item] = g[idx];
+                cp_async_small<(int)sizeof(T)>(w + e * P + item, g + idx);
                 e += TPB;
                 while (e >= L) { e -= L; ++item; }
             }
+            cp_async_commit();
+            cp_async_wait<0>();
         }
         __syncthreads();
         if (tid < nv) {
@@ -1046,14 +1049,28 @@ row_echelon_kernel(const T* __restrict__ A, T* __restrict__ OUT, unsigned char* 
                     }
                 T* pr = x + (rank * n) * P;
                 const T d = pr[c * P];
+                // the pivot row and each target row pass through registers (compile-time unrolled over the 16 possible
+                // columns, predicated): with both rows addressed through shared-memory pointers the compiler must keep
+                // every load behind the previous store, and the updates ran one shared-memory latency at a time
+                T prow[ECH_MAX_COLS];
+                #pragma unroll
+                for (int j = 0; j < ECH_MAX_COLS; ++j) prow[j] = (j > c && j < n) ? pr[j * P] : T(0);
                 for (int i = 0; i < m; ++i) {
                     if (i == rank) continue;
                     T* ri = x + (i * n) * P;
                     const T f = ri[c * P] / d;
-                    for (int j = c + 1; j < n; ++j) ri[j * P] = ri[j * P] - f * pr[j * P];
+                    T rrow[ECH_MAX_COLS];
+                    #pragma unroll
+                    for (int j = 0; j < ECH_MAX_COLS; ++j)
+                        if (j > c && j < n) rrow[j] = ri[j * P];
+                    #pragma unroll
+                    for (int j = 0; j < ECH_MAX_COLS; ++j)
+                        if (j > c && j < n) ri[j * P] = rrow[j] - f * prow[j];
                     ri[c * P] = T(0);
                 }
-                for (int j = c + 1; j < n; ++j) pr[j * P] = pr[j * P] / d;
+                #pragma unroll
+                for (int j = 0; j < ECH_MAX_COLS; ++j)
+                    if (j > c && j < n) pr[j * P] = prow[j] / d;
                 pr[c * P] = T(1);
                 ++rank;
             }
