@@ -76,7 +76,7 @@ WORKLOADS = {
     "matmul5x5_f32_4M": dict(op="matmul", dtype="f32", m=5, k=5, n=5, batch=1 << 22, bytes=300, bound="hbm",
                              desc="4Mi 5x5 Float .*. (odd tiny shape, tile pipeline)"),
     "inverse8_f64_1M": dict(op="inverse", dtype="f64", n=8, batch=1 << 20, bytes=1025, bound="hbm",
-                            desc="1Mi 8x8 Double inverse (record per thread; 128 doubles of working matrix: spills)"),
+                            desc="1Mi 8x8 Double inverse (record per thread: LU with kept multipliers, identity columns replayed two at a time, streamed results)"),
     "det8_f64_1M": dict(op="det", dtype="f64", n=8, batch=1 << 20, bytes=520, bound="hbm",
                         desc="1Mi 8x8 Double det (record per thread, compile-time unrolled elimination)"),
     "solve8_f64_1M": dict(op="solve", dtype="f64", n=8, batch=1 << 20, bytes=641, bound="hbm",
