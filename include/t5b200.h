@@ -109,7 +109,9 @@ int t5_buf_layout(const t5_buf* buf);
  * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|): Double with m, n multiples of 64 and k a
  * multiple of 32 (FP64 DMMA, tol 1e-12), Float with m, n multiples of 64 and k a
  * multiple of 32 (tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with
- * the exact fold).  AoS only; the same shapes in SoA are T5_ERR_UNSUPPORTED. */
+ * the exact fold).  The tensor-core kernels take AoS batches; in SoA those shapes run the
+ * thread-per-item contraction (exact fold, bit-identical), as does every other shape
+ * without an SoA tile kernel. */
 int t5_matmul(t5_ctx* ctx, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C);
 
 /* DotProduct (dot): OUT[b] = fold_{i ascending} (acc + X[b,i]*Y[b,i]).  §8a a7. */
@@ -155,7 +157,7 @@ int t5_solve(t5_ctx* ctx, int dtype, int n, int nrhs, const t5_buf* A, const t5_
  *                first, OUT[n] = 1 (Faddeev-LeVerrier).  Double / Float.
  *   t5_min_poly  OUT as for t5_char_poly, zero above the degree; DEGREE (T5_U8) receives the
  *                degree: the first exact linear dependency among I, A, A^2, ..; degree n
- *                returns the characteristic polynomial.  Double / Float, n <= 6, AoS. */
+ *                returns the characteristic polynomial.  Double / Float, n <= 6; SoA for n <= 4. */
 int t5_trace(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
 int t5_poly_eval(t5_ctx* ctx, int dtype, int n, const void* coeffs, int ncoef, const t5_buf* A, t5_buf* OUT);
 int t5_char_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
@@ -169,7 +171,8 @@ int t5_min_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_
  * the pivot column cleared in every other row, then the pivot row divided by its pivot.  Pivots are searched in the first pivot_cols columns only: pivot_cols = cols
  * is rowEchelonForm; on an augmented [A | B] item with pivot_cols = cols(A) it is
  * triangularSolve (A reduced, B carried along).  RANK (T5_U8) receives the number of pivots.
- * Double / Float, rows <= 8, cols <= 16, AoS. */
+ * Double / Float, rows <= 8, cols <= 16; SoA for n x n and n x (n+1) with n <= 8 and n x 2n with
+ * n <= 4 (the register-resident kernels). */
 int t5_row_echelon(t5_ctx* ctx, int dtype, int rows, int cols, int pivot_cols, const t5_buf* A, t5_buf* OUT, t5_buf* RANK);
 
 /* Element-wise vector-space operations (Functor/Applicative instances,
@@ -187,8 +190,9 @@ int t5_replicate(t5_ctx* ctx, int dtype, const void* record, t5_buf* OUT);
 /* ---- structural operations ---------------------------------------------------
  * The reshuffles of the IsTensor / MultiIndexable / Sliceable instances
  * (src/Data/Tensor/Vector.hs:260-354, :400-463) as device gathers.  Each one is a
- * pure index map, bit-exact for every dtype.  Indices and axes are 1-based like the
- * reference's MultiIndex (src/Data/Tensor/Vector.hs:150-168). */
+ * pure index map, bit-exact for every dtype, AoS (table-driven gather) and SoA (a copy of
+ * whole rows).  Indices and axes are 1-based like the reference's MultiIndex
+ * (src/Data/Tensor/Vector.hs:150-168). */
 
 /* append n x y (Vector.hs:322-335): concatenate along axis `axis`; dimsA and dimsB agree
  * everywhere else. */

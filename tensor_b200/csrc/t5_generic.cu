@@ -367,6 +367,8 @@ static int outer_small_launch(const Shard& s, int P, int Q, const void* A, const
     return ok();
 }
 
+int generic_soa_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C);
+
 // the streaming outer-product kernel applies when a CTA's threads tile whole rows of the result
 static bool outer_ok(int P, int Q, int vec) {
     if (Q % vec) return false;
@@ -375,6 +377,7 @@ static bool outer_ok(int P, int Q, int vec) {
 }
 
 int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
+    if (s.layout == T5L_SOA) return generic_soa_prod(s, dtype, P, K, Q, nc, A, B, C);
     if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
     if ((long long)P * Q > (1 << 28) || (long long)P * K > (1 << 28) || (long long)K * Q > (1 << 28)) return T5I_UNSUPPORTED;
     if (nc == 0) {
@@ -655,6 +658,75 @@ int generic_transpose2d(const Shard& s, int elem_bytes, int R, int C, const void
              : (R % 2 == 0 && C % 2 == 0) ? transpose_staged_launch<unsigned, 2>(s, R, C, A, O) : transpose_staged_launch<unsigned, 1>(s, R, C, A, O);
     if (R < 16 || C < 16) return T5I_NOT_SPECIALISED;
     return elem_bytes == 8 ? transpose2d_launch<unsigned long long, 32, 8>(s, R, C, A, O) : transpose2d_launch<unsigned, 32, 8>(s, R, C, A, O);
+}
+
+// ---- SoA forms of the any-shape operations ---------------------------------------------------------
+// In the SoA layout (element e of item b at [e * cap + b], cap a multiple of 32 items) every pure index map -
+// transpose of any rank, append / split / at / ta / slice / axis permutation - is a copy of whole ROWS: output
+// row e is input row table[e], contiguous on both sides, 16 bytes per thread.  And a thread-per-item contraction
+// reads and writes coalesced by construction.  These make every product shape and every structural operation
+// available on SoA batches (the specialised tile kernels still take the shapes they cover).
+__global__ void __launch_bounds__(256)
+soa_rows_kernel(const uint4* __restrict__ A, const uint4* __restrict__ B, uint4* __restrict__ out, const uint32_t* __restrict__ table,
+                unsigned dA, unsigned d_out, unsigned long long row_chunks) {
+    for (unsigned e = blockIdx.y; e < d_out; e += gridDim.y) {
+        const unsigned v = __ldg(table + e);
+        const uint4* src = (v < dA ? A + (size_t)v * row_chunks : B + (size_t)(v - dA) * row_chunks);
+        uint4* dst = out + (size_t)e * row_chunks;
+        for (unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x; c < row_chunks; c += (unsigned long long)gridDim.x * 256)
+            st_global_stream16(dst + c, ld_global_stream16(src + c));
+    }
+}
+
+// one- or two-source row gather on SoA shards of equal capacity (B may be null when every table entry is < dA)
+int generic_soa_gather(const Shard& s, int elem_bytes, size_t dA, size_t d_out, const uint32_t* table_dev, const void* A, const void* B, void* O) {
+    if (s.layout != T5L_SOA || (elem_bytes != 4 && elem_bytes != 8)) return T5I_UNSUPPORTED;
+    if (s.count == 0 || d_out == 0) return T5I_OK;
+    if (s.soa_stride % 32 || d_out > (1u << 28)) return T5I_UNSUPPORTED;
+    const unsigned long long row_chunks = s.soa_stride * elem_bytes / 16;       // rows are whole 16-byte chunks (cap % 32 == 0)
+    const size_t bx = (row_chunks + 255) / 256;
+    dim3 grid((unsigned)(bx < 1024 ? bx : 1024), (unsigned)(d_out < 256 ? d_out : 256));
+    soa_rows_kernel<<<grid, 256, 0, s.stream>>>((const uint4*)A, (const uint4*)B, (uint4*)O, table_dev, (unsigned)dA, (unsigned)d_out, row_chunks);
+    return ok();
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+soa_prod_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int K, int Q, int nc, unsigned long long count,
+                unsigned long long stride) {
+    using R = Arith<T>;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * 256 + threadIdx.x; b < count; b += (unsigned long long)gridDim.x * 256) {
+        const T* a = A + b;
+        const T* bb = B + b;
+        T* c = C + b;
+        if (nc == 0) {
+            for (int p = 0; p < P; ++p) {
+                const T av = a[(size_t)p * stride];
+                for (int q = 0; q < Q; ++q) c[((size_t)p * Q + q) * stride] = R::mul(av, __ldg(bb + (size_t)q * stride));
+            }
+        } else {
+            for (int i = 0; i < P; ++i)
+                for (int j = 0; j < Q; ++j) {
+                    T acc = R::zero();
+                    for (int k = 0; k < K; ++k)
+                        acc = R::add(acc, R::mul(__ldg(a + ((size_t)i * K + k) * stride), __ldg(bb + ((size_t)k * Q + j) * stride)));
+                    c[((size_t)i * Q + j) * stride] = acc;
+                }
+        }
+    }
+}
+
+int generic_soa_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
+    if (s.layout != T5L_SOA) return T5I_UNSUPPORTED;
+    if (s.count == 0) return T5I_OK;
+    const size_t bx = (s.count + 255) / 256;
+    switch (dtype) {
+        case T5D_F64: soa_prod_kernel<double><<<resident_grid((const void*)soa_prod_kernel<double>, 256, bx), 256, 0, s.stream>>>((const double*)A, (const double*)B, (double*)C, P, K, Q, nc, s.count, s.soa_stride); break;
+        case T5D_F32: soa_prod_kernel<float><<<resident_grid((const void*)soa_prod_kernel<float>, 256, bx), 256, 0, s.stream>>>((const float*)A, (const float*)B, (float*)C, P, K, Q, nc, s.count, s.soa_stride); break;
+        case T5D_I64: soa_prod_kernel<long long><<<resident_grid((const void*)soa_prod_kernel<long long>, 256, bx), 256, 0, s.stream>>>((const long long*)A, (const long long*)B, (long long*)C, P, K, Q, nc, s.count, s.soa_stride); break;
+        default: return T5I_UNSUPPORTED;
+    }
+    return ok();
 }
 
 int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O) {

@@ -59,6 +59,7 @@ int generic_longdot(const Shard& s, int dtype, int K, const void* X, const void*
 int generic_prod(const Shard& s, int dtype, int P, int K, int Q, int ncontract, const void* A, const void* B, void* C);
 // out[b][i] = in[b][perm[i]], perm resident on the device (d entries)
 int generic_transpose2d(const Shard& s, int elem_bytes, int R, int C, const void* A, void* O);
+int generic_soa_gather(const Shard& s, int elem_bytes, size_t dA, size_t d_out, const uint32_t* table_dev, const void* A, const void* B, void* O);
 int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* perm_dev, const void* A, void* O);
 // out[b][i] = in[b][table[i]] with d_in != d_out allowed (structural gathers); gather2: two sources (append)
 int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, const uint32_t* table_dev, const void* A, void* O);

@@ -103,6 +103,26 @@ def test_nested_reshuffles(ctx, outer, inner):
     assert np.array_equal(st.unrev(T0).to_numpy().ravel(), tb.transpose(N.flat).to_numpy().ravel())
 
 
+@pytest.mark.parametrize("dc", ALL)
+def test_structural_ops_on_soa_batches(ctx, dc):
+    """SoA batches: every structural operation is a copy of whole rows - the same results as on AoS, in SoA."""
+    for batch in (1, 1000, 4099):
+        d, e, dims = [3, 3], [3, 2], [2, 3, 4]
+        x, y, z = data(dc, d, batch), data(dc, e, batch, 24), data(dc, dims, batch, 25)
+        Xa, Ya, Za = ctx.from_numpy(x, d), ctx.from_numpy(y, e), ctx.from_numpy(z, dims)
+        Xs, Ys, Zs = ctx.from_numpy(x, d, tb.SOA), ctx.from_numpy(y, e, tb.SOA), ctx.from_numpy(z, dims, tb.SOA)
+        J = st.append(2, Xs, Ys)
+        assert J.layout == tb.SOA and np.array_equal(J.to_numpy(), st.append(2, Xa, Ya).to_numpy())
+        L, R = st.split(2, 3, J)
+        assert L.layout == tb.SOA and np.array_equal(L.to_numpy().ravel(), x) and np.array_equal(R.to_numpy().ravel(), y)
+        assert np.array_equal(st.ta(2, Zs).to_numpy(), st.ta(2, Za).to_numpy())
+        assert np.array_equal(st.at(Zs, [2, 3]).to_numpy(), st.at(Za, [2, 3]).to_numpy())
+        assert np.array_equal(st.slice_(Zs, [None, 2, None]).to_numpy(), st.slice_(Za, [None, 2, None]).to_numpy())
+        assert np.array_equal(st.permute_axes(Zs, [2, 0, 1]).to_numpy(), st.permute_axes(Za, [2, 0, 1]).to_numpy())
+        T = tb.transpose(Zs)
+        assert T.layout == tb.SOA and np.array_equal(T.to_numpy(), oracle.transpose(z, dims).reshape(batch, 4, 3, 2))
+
+
 def test_structural_errors(ctx):
     X = ctx.empty((2, 3), np.float64, 4)
     with pytest.raises(tb.WrongListLength):
