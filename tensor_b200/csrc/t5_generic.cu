@@ -673,8 +673,20 @@ soa_rows_kernel(const uint4* __restrict__ A, const uint4* __restrict__ B, uint4*
         const unsigned v = __ldg(table + e);
         const uint4* src = (v < dA ? A + (size_t)v * row_chunks : B + (size_t)(v - dA) * row_chunks);
         uint4* dst = out + (size_t)e * row_chunks;
-        for (unsigned long long c = (unsigned long long)blockIdx.x * 256 + threadIdx.x; c < row_chunks; c += (unsigned long long)gridDim.x * 256)
-            st_global_stream16(dst + c, ld_global_stream16(src + c));
+        // a CTA moves contiguous 16-KB spans (4 x 256 chunks, four loads in flight per thread)
+        for (unsigned long long c0 = (unsigned long long)blockIdx.x * 1024; c0 < row_chunks; c0 += (unsigned long long)gridDim.x * 1024) {
+            uint4 v4[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long c = c0 + u * 256 + threadIdx.x;
+                if (c < row_chunks) v4[u] = ld_global_stream16(src + c);
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long c = c0 + u * 256 + threadIdx.x;
+                if (c < row_chunks) st_global_stream16(dst + c, v4[u]);
+            }
+        }
     }
 }
 
@@ -684,8 +696,13 @@ int generic_soa_gather(const Shard& s, int elem_bytes, size_t dA, size_t d_out, 
     if (s.count == 0 || d_out == 0) return T5I_OK;
     if (s.soa_stride % 32 || d_out > (1u << 28)) return T5I_UNSUPPORTED;
     const unsigned long long row_chunks = s.soa_stride * elem_bytes / 16;       // rows are whole 16-byte chunks (cap % 32 == 0)
-    const size_t bx = (row_chunks + 255) / 256;
-    dim3 grid((unsigned)(bx < 1024 ? bx : 1024), (unsigned)(d_out < 256 ? d_out : 256));
+    const size_t bx = (row_chunks + 1023) / 1024;
+    // ~8 resident CTAs per SM in total, spread over rows first
+    const unsigned gy = (unsigned)(d_out < 256 ? d_out : 256);
+    unsigned gx = (unsigned)((8 * (size_t)sm_count() + gy - 1) / gy);
+    if (gx > bx) gx = (unsigned)bx;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, gy);
     soa_rows_kernel<<<grid, 256, 0, s.stream>>>((const uint4*)A, (const uint4*)B, (uint4*)O, table_dev, (unsigned)dA, (unsigned)d_out, row_chunks);
     return ok();
 }

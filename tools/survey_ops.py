@@ -121,6 +121,14 @@ def main():
             add(f"transpose 128x128 {tag}", (B // 1024) * 32768 * es, lambda: tb.transpose(A128))
             add(f"transpose 20x40 {tag}", (B // 64) * 1600 * es, lambda: tb.transpose(A2040))
             A128.free(); A2040.free()
+            T234s, A3s, v3s = T234.relayout(tb.SOA), A3.relayout(tb.SOA), v3.relayout(tb.SOA)
+            A8s, B8s = A8.relayout(tb.SOA), B8.relayout(tb.SOA)
+            add(f"SoA transpose 2x3x4 {tag}", B * 48 * es, lambda: tb.transpose(T234s))
+            add(f"SoA append 3x3|3 {tag}", B * 24 * es, lambda: st.append(2, A3s, v3s))
+            add(f"SoA slice 2x3x4 [_,2,_] {tag}", B * (24 + 8) * es, lambda: st.slice_(T234s, [None, 2, None]))
+            add(f"SoA matmul 8x8 (thread-per-item contraction) {tag}", (B // 4) * 192 * es, lambda: tb.matmul(A8s, B8s))
+            for x in (T234s, A3s, v3s, A8s, B8s):
+                x.free()
             b3s, b4s = ctx.synthetic((3,), dt, B, SEED + 1, 28), ctx.synthetic((4,), dt, B, SEED + 1, 29)
             for nn, AA, bb in ((3, A3, b3s), (4, A4, b4s)):
                 add(f"det {nn}x{nn} {tag}", B * (nn * nn + 1) * es, lambda: tb.det(AA))
