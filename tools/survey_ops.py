@@ -121,8 +121,10 @@ def main():
             add(f"transpose 128x128 {tag}", (B // 1024) * 32768 * es, lambda: tb.transpose(A128))
             add(f"transpose 20x40 {tag}", (B // 64) * 1600 * es, lambda: tb.transpose(A2040))
             A128.free(); A2040.free()
-            T234s, A3s, v3s = T234.relayout(tb.SOA), A3.relayout(tb.SOA), v3.relayout(tb.SOA)
-            A8s, B8s = A8.relayout(tb.SOA), B8.relayout(tb.SOA)
+            T234s, A3s, v3s = (ctx.synthetic((2, 3, 4), dt, B, SEED, 6, tb.SOA), ctx.synthetic((3, 3), dt, B, SEED, 1, tb.SOA),
+                               ctx.synthetic((3, 1), dt, B, SEED, 3, tb.SOA))
+            A8s, B8s = ctx.synthetic((8, 8), dt, B // 4, SEED, 5, tb.SOA), ctx.synthetic((8, 8), dt, B // 4, SEED + 1, 17, tb.SOA)
+            timed(ctx, lambda: st.append(2, A3s, v3s))          # (lets the allocator pool settle on the SoA result sizes)
             add(f"SoA transpose 2x3x4 {tag}", B * 48 * es, lambda: tb.transpose(T234s))
             add(f"SoA append 3x3|3 {tag}", B * 24 * es, lambda: st.append(2, A3s, v3s))
             add(f"SoA slice 2x3x4 [_,2,_] {tag}", B * (24 + 8) * es, lambda: st.slice_(T234s, [None, 2, None]))
