@@ -315,7 +315,7 @@ def _canon_nan(x):
     return x
 
 
-@pytest.mark.parametrize("n", [2, 3, 4])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])     # n >= 5: LU with kept multipliers, streamed results, one-stage pipeline
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_elimination_extreme_operands_bit_exact(ctx, n, layout):
     """The Double elimination kernels divide through a shared reciprocal with the compiler's
@@ -351,6 +351,17 @@ def test_elimination_extreme_operands_bit_exact(ctx, n, layout):
         ox, ost = oracle.solve(a, b, n, 1)
         assert np.array_equal(st.to_numpy(), ost)
         assert_bits_equal(_canon_nan(X.to_numpy()), _canon_nan(ox.reshape(batch, n)), f"solve{n} extremes")
+        # matrix right-hand side (n >= 5: the lazily read, streamed kernel) and the echelon form of the same items
+        if layout == tb.AOS or n == 2 or n >= 5:        # (SoA: two columns have a kernel for n = 2 and n >= 5)
+            b2 = np.ascontiguousarray(np.stack([b, b[::-1]], axis=2))
+            X2, st2 = tb.solve(A, ctx.from_numpy(b2, (n, 2), layout))
+            ox2, ost2 = oracle.solve(a, b2, n, 2)
+            assert np.array_equal(st2.to_numpy(), ost2)
+            assert_bits_equal(_canon_nan(X2.to_numpy()), _canon_nan(ox2.reshape(batch, n, 2)), f"solve{n} x 2 extremes")
+        E, rk = tb.row_echelon_form(A)
+        oe, ork = oracle.row_echelon(a, n, n)
+        assert np.array_equal(rk.to_numpy(), ork)
+        assert_bits_equal(_canon_nan(E.to_numpy()), _canon_nan(oe), f"rowEchelonForm{n} extremes")
 
 
 # ---- regression fixtures through the device ----------------------------------------
