@@ -733,9 +733,95 @@ soa_prod_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict_
     }
 }
 
+// Contractions whose B operand is a few hundred elements (8x8 . 8x8, the `prod 1` of BASELINE configs[3], in SoA):
+// the kernel above re-reads every B element P times through L1 and thrashes it (0.2 of the HBM peak for 8x8).
+// Here a CTA first copies its items' B rows into shared memory - [element][item], stride-1 across the warp, so both
+// the coalesced fill and the per-thread reads are conflict-free - and each thread then streams its A elements from
+// global memory once per four results: global traffic is the algorithmic traffic.  Same fold, k ascending.
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+soa_prod_staged_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int K, int Q, unsigned long long count,
+                       unsigned long long stride) {
+    using R = Arith<T>;
+    extern __shared__ __align__(16) unsigned char spb_smem[];
+    T* sB = reinterpret_cast<T*>(spb_smem);                  // [K * Q][THREADS]
+    const int KQ = K * Q;
+    const unsigned long long n_tiles = (count + THREADS - 1) / THREADS;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long b = tile * THREADS + threadIdx.x;
+        const bool live = b < count;
+        __syncthreads();                                         // the previous tile's B is no longer read
+        if (live)
+            for (int e = 0; e < KQ; ++e) cp_async_small<(int)sizeof(T)>(sB + e * THREADS + threadIdx.x, B + (size_t)e * stride + b);
+        cp_async_commit();
+        cp_async_wait<0>();                                      // (each thread reads only what it copied itself)
+        if (live) {
+            const T* a = A + b;
+            T* c = C + b;
+            const T* sb = sB + threadIdx.x;
+            constexpr int KMAX = 16;
+            for (int i = 0; i < P; ++i) {
+                // the A row in registers (compile-time unrolled, predicated): K independent loads in flight, each element read once
+                T arow[KMAX];
+                if (K <= KMAX) {
+                    #pragma unroll
+                    for (int k = 0; k < KMAX; ++k)
+                        if (k < K) arow[k] = __ldg(a + ((size_t)i * K + k) * stride);
+                }
+                for (int j0 = 0; j0 < Q; j0 += 4) {
+                    T acc[4];
+                    #pragma unroll
+                    for (int t = 0; t < 4; ++t) acc[t] = R::zero();
+                    const int jt = Q - j0 < 4 ? Q - j0 : 4;
+                    if (K <= KMAX) {
+                        #pragma unroll
+                        for (int k = 0; k < KMAX; ++k)
+                            if (k < K) {
+                                #pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    if (t < jt) acc[t] = R::add(acc[t], R::mul(arow[k], sb[(k * Q + j0 + t) * THREADS]));
+                            }
+                    } else {
+                        for (int k = 0; k < K; ++k) {
+                            const T av = __ldg(a + ((size_t)i * K + k) * stride);
+                            #pragma unroll
+                            for (int t = 0; t < 4; ++t)
+                                if (t < jt) acc[t] = R::add(acc[t], R::mul(av, sb[(k * Q + j0 + t) * THREADS]));
+                        }
+                    }
+                    #pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (t < jt) c[((size_t)i * Q + j0 + t) * stride] = acc[t];
+                }
+            }
+        }
+    }
+}
+
+template <class T>
+static int soa_prod_staged_launch(const Shard& s, int P, int K, int Q, const void* A, const void* B, void* C) {
+    constexpr int THREADS = 128;
+    auto kern = soa_prod_staged_kernel<T, THREADS>;
+    const int smem = K * Q * THREADS * (int)sizeof(T);
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return T5I_CUDA;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const size_t tiles = (s.count + THREADS - 1) / THREADS, cap = (size_t)occ * sm_count();
+    kern<<<(int)(tiles < cap ? tiles : cap), THREADS, smem, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, K, Q, (unsigned long long)s.count, s.soa_stride);
+    return ok();
+}
+
 int generic_soa_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
     if (s.layout != T5L_SOA) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
+    // B of 16..200 elements and more than one result row: stage B (<= 200 KB of shared memory per 128 items)
+    if (nc != 0 && P > 1 && (long long)K * Q >= 16 && (long long)K * Q * 128 * (dtype == T5D_F32 ? 4 : 8) <= 200 * 1024) {
+        switch (dtype) {
+            case T5D_F64: return soa_prod_staged_launch<double>(s, P, K, Q, A, B, C);
+            case T5D_F32: return soa_prod_staged_launch<float>(s, P, K, Q, A, B, C);
+            case T5D_I64: return soa_prod_staged_launch<long long>(s, P, K, Q, A, B, C);
+        }
+    }
     const size_t bx = (s.count + 255) / 256;
     switch (dtype) {
         case T5D_F64: soa_prod_kernel<double><<<resident_grid((const void*)soa_prod_kernel<double>, 256, bx), 256, 0, s.stream>>>((const double*)A, (const double*)B, (double*)C, P, K, Q, nc, s.count, s.soa_stride); break;
