@@ -798,6 +798,62 @@ soa_prod_staged_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __re
     }
 }
 
+// Outer products in SoA (the 8x8 (x) 8x8 -> 8^4 of BASELINE configs[3]: 4096 result rows per item).  One item per
+// thread writes 256 contiguous bytes per row and warp - every store instruction lands in a different DRAM page -
+// and re-reads B through a thrashing L1 (0.5 of the HBM peak).  Here a thread owns 16 bytes' worth of consecutive
+// items (2 Double / 4 Float: 512-byte row segments per warp), and the CTA's B vectors are staged once in shared
+// memory ([q][thread], stride-1).  One multiply per result, as specified.
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+soa_outer_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, int Q, unsigned long long count,
+                 unsigned long long stride) {
+    using R = Arith<T>;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    extern __shared__ __align__(16) unsigned char so_smem[];
+    uint4* sB = reinterpret_cast<uint4*>(so_smem);           // [Q][THREADS] vectors of VEC items
+    const unsigned long long n_vec = (count + VEC - 1) / VEC; // (rows are padded to 32 items: whole vectors are addressable)
+    const unsigned long long n_tiles = (n_vec + THREADS - 1) / THREADS;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long v = tile * THREADS + threadIdx.x;
+        const bool live = v < n_vec;
+        const size_t off = (size_t)v * VEC;
+        if (live)
+            for (int q = 0; q < Q; ++q) cp_async16(sB + q * THREADS + threadIdx.x, B + (size_t)q * stride + off);
+        cp_async_commit();
+        cp_async_wait<0>();                                      // (each thread reads only what it copied itself)
+        if (live) {
+            for (int p = 0; p < P; ++p) {
+                const uint4 araw = ld_global_stream16(A + (size_t)p * stride + off);
+                const T* av = reinterpret_cast<const T*>(&araw);
+                T* crow = C + (size_t)p * Q * stride + off;
+                #pragma unroll 4
+                for (int q = 0; q < Q; ++q) {
+                    const uint4 braw = sB[q * THREADS + threadIdx.x];
+                    const T* bv = reinterpret_cast<const T*>(&braw);
+                    uint4 o;
+                    #pragma unroll
+                    for (int t = 0; t < VEC; ++t) reinterpret_cast<T*>(&o)[t] = R::mul(av[t], bv[t]);
+                    st_global_stream16(crow + (size_t)q * stride, o);
+                }
+            }
+        }
+    }
+}
+
+template <class T>
+static int soa_outer_launch(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
+    constexpr int THREADS = 64;
+    auto kern = soa_outer_kernel<T, THREADS>;
+    const int smem = Q * THREADS * 16;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return T5I_CUDA;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const size_t tiles = ((s.count + VEC - 1) / VEC + THREADS - 1) / THREADS, cap = (size_t)occ * sm_count();
+    kern<<<(int)(tiles < cap ? tiles : cap), THREADS, smem, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, Q, (unsigned long long)s.count, s.soa_stride);
+    return ok();
+}
+
 template <class T>
 static int soa_prod_staged_launch(const Shard& s, int P, int K, int Q, const void* A, const void* B, void* C) {
     constexpr int THREADS = 128;
@@ -814,6 +870,13 @@ static int soa_prod_staged_launch(const Shard& s, int P, int K, int Q, const voi
 int generic_soa_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
     if (s.layout != T5L_SOA) return T5I_UNSUPPORTED;
     if (s.count == 0) return T5I_OK;
+    if (nc == 0 && (long long)Q * 64 * 16 <= 200 * 1024 && (long long)P * Q >= 16) {      // outer products with up to 200 B elements
+        switch (dtype) {
+            case T5D_F64: return soa_outer_launch<double>(s, P, Q, A, B, C);
+            case T5D_F32: return soa_outer_launch<float>(s, P, Q, A, B, C);
+            case T5D_I64: return soa_outer_launch<long long>(s, P, Q, A, B, C);
+        }
+    }
     // B of 16..200 elements and more than one result row: stage B (<= 200 KB of shared memory per 128 items)
     if (nc != 0 && P > 1 && (long long)K * Q >= 16 && (long long)K * Q * 128 * (dtype == T5D_F32 ? 4 : 8) <= 200 * 1024) {
         switch (dtype) {

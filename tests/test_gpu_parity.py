@@ -137,6 +137,25 @@ def test_prod_and_tensor_product(ctx, dc):
                       oracle.prod(a4, [3], b4, [5], 0), "3 (x) 5")
 
 
+@pytest.mark.parametrize("dc", ALL)
+def test_prod_and_tensor_product_soa(ctx, dc):
+    """The same contractions on SoA batches: the staged-B contraction, the vectorised outer product, the fallbacks."""
+    for batch in (1, 333, 4099):
+        a, b = inputs(dc, 5, batch, 64, 64)
+        A, B = ctx.from_numpy(a, (8, 8), tb.SOA), ctx.from_numpy(b, (8, 8), tb.SOA)
+        T = tb.tensor_product(A, B)
+        assert T.layout == tb.SOA and T.shape == (8, 8, 8, 8)
+        assert_bits_equal(T.to_numpy(), oracle.prod(a, [8, 8], b, [8, 8], 0), "SoA 8x8 (x) 8x8")
+        assert_bits_equal(tb.prod(A, B, 1).to_numpy(), oracle.prod(a, [8, 8], b, [8, 8], 1), "SoA prod 1")
+        assert_bits_equal(tb.prod(A, B, 2).to_numpy(), oracle.prod(a, [8, 8], b, [8, 8], 2), "SoA prod 2")
+        a4, b4 = inputs(dc, 7, batch, 3, 5)
+        assert_bits_equal(tb.tensor_product(ctx.from_numpy(a4, (3,), tb.SOA), ctx.from_numpy(b4, (5,), tb.SOA)).to_numpy(),
+                          oracle.prod(a4, [3], b4, [5], 0), "SoA 3 (x) 5")
+        a3, b3 = inputs(dc, 6, batch, 2 * 3 * 4, 4 * 5)
+        P = tb.prod(ctx.from_numpy(a3, (2, 3, 4), tb.SOA), ctx.from_numpy(b3, (4, 5), tb.SOA), 1)
+        assert_bits_equal(P.to_numpy(), oracle.prod(a3, [2, 3, 4], b3, [4, 5], 1), "SoA rank3.rank2")
+
+
 def test_prod_shape_mismatch_is_wrong_list_length(ctx):
     A = ctx.empty((3, 4), np.float64, 4)
     B = ctx.empty((5, 2), np.float64, 4)
