@@ -53,6 +53,10 @@ WORKLOADS = {
                                  desc="1Mi 8x8 (x) 8x8 -> 8^4 Double tensor products (configs[3])"),
     "prod1_8x8_f64_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=1, batch=1 << 20, bytes=1536, bound="hbm",
                              desc="1Mi 8x8 . 8x8 Double contractions (configs[3], n=1)"),
+    "tensorprod8x8_f64_soa_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=0, batch=1 << 20, bytes=33792, bound="hbm", layout="soa",
+                                     desc="1Mi 8x8 (x) 8x8 -> 8^4 Double on SoA buffers (16 bytes of consecutive items per thread, B staged in shared memory)"),
+    "prod1_8x8_f64_soa_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=1, batch=1 << 20, bytes=1536, bound="hbm", layout="soa",
+                                 desc="1Mi 8x8 . 8x8 Double (prod 1) on SoA buffers (B staged in shared memory, A row in registers)"),
     "matmul4x4_f32_soa_16M": dict(op="matmul", dtype="f32", m=4, k=4, n=4, batch=1 << 24, bytes=192, bound="hbm", layout="soa",
                                   desc="16Mi pairs of 4x4 Float matrices, .*., SoA device layout"),
     "inverse4_f64_soa_4M": dict(op="inverse", dtype="f64", n=4, batch=1 << 22, bytes=257, bound="hbm", layout="soa",
@@ -105,7 +109,7 @@ WORKLOADS = {
 HEADLINE = "matmul4x4_f32_16M"
 EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpose4x4_f32_16M", "matvec4_f32_16M",
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
-          "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M",
+          "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M", "tensorprod8x8_f64_soa_1M", "prod1_8x8_f64_soa_1M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
           "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
           "inverse6_f64_1M", "inverse8_f64_1M", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M", "echelon7x9_f64_1M"]
