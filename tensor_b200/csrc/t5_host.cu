@@ -68,6 +68,8 @@ struct t5_ctx {
     // cudaMalloc / sync + cudaFree that was ~0.3 ms per call, several times the kernels it served.
     cudaMemPool_t pool[T5_MAX_DEVICES];
     void* scratch[T5_MAX_DEVICES];   // dot-sum block partials + the device partial (at the end)
+    void* host_word[T5_MAX_DEVICES]; // 8 pinned bytes per device: the dot-sum partial comes back with an async copy on the
+                                     // launch stream, so the call blocks once (stream sync) instead of twice (sync + cudaMemcpy)
     void* flush[T5_MAX_DEVICES];     // L2 flush target (lazy)
     void* coef[T5_MAX_DEVICES];      // polyEval coefficients for the any-shape kernel (lazy, grow-only)
     size_t coef_cap[T5_MAX_DEVICES];
@@ -183,13 +185,14 @@ int t5_init(const int* devices, int ndev, t5_ctx** out) {
     for (int g = 0; g < c->ndev; ++g) {
         c->dev[g] = devs[g];
         c->pool[g] = nullptr;
-        c->stream[g] = nullptr; c->ev0[g] = c->ev1[g] = nullptr; c->scratch[g] = c->flush[g] = c->coef[g] = nullptr; c->coef_cap[g] = 0;
+        c->stream[g] = nullptr; c->ev0[g] = c->ev1[g] = nullptr; c->scratch[g] = c->flush[g] = c->coef[g] = nullptr; c->coef_cap[g] = 0; c->host_word[g] = nullptr;
     }
     for (int g = 0; g < c->ndev; ++g) {
         if ((e = cudaSetDevice(c->dev[g])) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&c->stream[g], cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate(&c->ev0[g])) != cudaSuccess || (e = cudaEventCreate(&c->ev1[g])) != cudaSuccess ||
             (e = cudaMalloc(&c->scratch[g], SCRATCH_BYTES)) != cudaSuccess ||
+            (e = cudaMallocHost(&c->host_word[g], 8)) != cudaSuccess ||
             (e = cudaMemset(c->scratch[g], 0, SCRATCH_BYTES)) != cudaSuccess ||
             (e = make_pool(c->dev[g], &c->pool[g])) != cudaSuccess) {
             int rc = cuda_fail(nullptr, e, "t5_init");
@@ -213,6 +216,7 @@ int t5_shutdown(t5_ctx* c) {
         if (c->nccl_ready && c->nccl.CommDestroy) c->nccl.CommDestroy(c->comms[g]);
         if (c->pool[g]) cudaMemPoolDestroy(c->pool[g]);     // returns every cached block to the device
         if (c->scratch[g]) cudaFree(c->scratch[g]);
+        if (c->host_word[g]) cudaFreeHost(c->host_word[g]);
         if (c->flush[g]) cudaFree(c->flush[g]);
         if (c->coef[g]) cudaFree(c->coef[g]);
         if (c->ev0[g]) cudaEventDestroy(c->ev0[g]);
@@ -518,9 +522,13 @@ int t5_dot_sum(t5_ctx* c, int dtype, int n, const t5_buf* X, const t5_buf* Y, vo
         // single device, or NCCL not loadable: partials added on the host in device order
         for (int g = 0; g < c->ndev; ++g) {
             CU(c, cudaSetDevice(c->dev[g]));
+            CU(c, cudaMemcpyAsync(c->host_word[g], (char*)c->scratch[g] + part_off, 8, cudaMemcpyDeviceToHost, c->stream[g]));
+        }
+        for (int g = 0; g < c->ndev; ++g) {
+            CU(c, cudaSetDevice(c->dev[g]));
             CU(c, cudaStreamSynchronize(c->stream[g]));
-            if (dtype == T5_I64) { uint64_t v; CU(c, cudaMemcpy(&v, (char*)c->scratch[g] + part_off, 8, cudaMemcpyDeviceToHost)); isum += v; }
-            else { double v; CU(c, cudaMemcpy(&v, (char*)c->scratch[g] + part_off, 8, cudaMemcpyDeviceToHost)); dsum += v; }
+            if (dtype == T5_I64) isum += *(const volatile uint64_t*)c->host_word[g];
+            else dsum += *(const volatile double*)c->host_word[g];
         }
     }
     if (dtype == T5_F64) *(double*)host_scalar = dsum;
