@@ -40,7 +40,7 @@ def main():
         rows = []
 
         def add(name, nbytes, fn):
-            ms = timed(ctx, fn)
+            ms = min(timed(ctx, fn), timed(ctx, fn))      # best of two: the first pass can include the pool growing to a new high-water mark
             rows.append((name, ms, nbytes / ms / 1e6))
             print("%-44s %8.3f ms %8.0f GB/s" % rows[-1], flush=True)
 
