@@ -60,13 +60,23 @@ enum {
 const char* t5_strerror(int code);
 /* Last CUDA / NCCL error text seen by this context (empty string when none). */
 const char* t5_last_error(t5_ctx* ctx);
-/* Library build tag, e.g. "t5b200 sm_100a r1". */
+/* Library build tag, e.g. "t5b200 sm_100a r2". */
 const char* t5_version(void);
 
 /* ---- context ------------------------------------------------------------- */
 /* devices == NULL && ndev == 0: every visible device.  One stream per device. */
 int t5_init(const int* devices, int ndev, t5_ctx** out);
+/* Synchronises, then releases every device resource of the context - the device memory of
+ * buffers that are still alive included.  Such buffers become ORPHANS: every operation on
+ * them returns T5_ERR_INVALID, and t5_free on an orphan is legal at any later time, from any
+ * thread, and only releases the handle (the last one also releases the context's host
+ * bookkeeping).  This is the order a Haskell program produces: `bracket t5_init t5_shutdown`
+ * ends before the garbage collector runs the ForeignPtr finalizers (&t5_free) of the
+ * batches it created (SURVEY.md §8b Ownership).  The ctx pointer itself must not be used
+ * after t5_shutdown; a second t5_shutdown while orphans exist returns T5_ERR_INVALID. */
 int t5_shutdown(t5_ctx* ctx);
+/* Buffers allocated from this context and not yet freed. */
+int t5_live_buffers(t5_ctx* ctx);
 int t5_ndev(t5_ctx* ctx);
 int t5_sync(t5_ctx* ctx);
 
@@ -81,6 +91,8 @@ int t5_partition(size_t batch, int ndev, int g, size_t* first, size_t* count);
  * sharded by t5_partition.  Haskell owns it through a ForeignPtr whose
  * finalizer is t5_free. */
 int t5_alloc(t5_ctx* ctx, int dtype, size_t elems_per_item, size_t batch, int layout, t5_buf** out);
+/* Stream-ordered and non-blocking: work that still reads or writes the buffer finishes
+ * first.  Thread-safe, sets its own device, legal after t5_shutdown (see there). */
 int t5_free(t5_buf* buf);
 /* host is AoS; bytes must equal batch * elems_per_item * sizeof(dtype), else
  * T5_ERR_SHAPE (fromList's length check, src/Data/Tensor/Vector.hs:362-366). */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "t5_version": (ctypes.c_char_p, []),
     "t5_init": (_i, [ctypes.POINTER(ctypes.c_int), _i, _vpp]),
     "t5_shutdown": (_i, [_vp]),
+    "t5_live_buffers": (_i, [_vp]),
     "t5_ndev": (_i, [_vp]),
     "t5_sync": (_i, [_vp]),
     "t5_partition": (_i, [_sz, _i, _i, _szp, _szp]),

@@ -1513,24 +1513,66 @@ __global__ void __launch_bounds__(DS_THREADS) dot_sum_stage2(const Acc* __restri
     }
 }
 
-// scratch_dev: >= DS_MAX_BLOCKS * 8 bytes.  SoA shards pass elems = stride*d with
-// zero padding (allocation is zero-initialised), so the flat form is layout-agnostic.
-int dot_sum_partial(const Shard& s, int dtype, size_t elems, const void* X, const void* Y, void* scratch, void* partial) {
-    size_t blocks = (elems / (16 / dtype_size(dtype)) + DS_THREADS - 1) / DS_THREADS;   // one 16-B vector per thread and pass
-    int grid = (int)(blocks < (size_t)DS_MAX_BLOCKS ? (blocks ? blocks : 1) : DS_MAX_BLOCKS);
+// SoA shards whose rows carry padding (row_stride > row_valid): only items [0, row_valid) of every row are summed, so
+// the result never depends on what an element-wise op left in the pad (0 * inf = NaN there would poison the sum).
+// Rows are whole 16-byte vectors (row_stride is a multiple of 32 items); a thread walks (row, vector-in-row) by
+// adding the grid stride as (rows, vectors) - one division at entry, none in the loop.
+template <class T, class Acc>
+__global__ void __launch_bounds__(DS_THREADS)
+dot_sum_stage1_rows(const T* __restrict__ x, const T* __restrict__ y, Acc* __restrict__ partials, unsigned long long rows,
+                    unsigned long long row_vecs, unsigned long long row_valid) {
+    using R = Arith<T>;
+    constexpr int V = 16 / (int)sizeof(T);
+    const unsigned long long stride = (unsigned long long)gridDim.x * DS_THREADS;
+    const unsigned long long srow = stride / row_vecs, svec = stride % row_vecs;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * DS_THREADS + threadIdx.x;
+    unsigned long long row = i0 / row_vecs, vec = i0 % row_vecs;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    const uint4* yv = reinterpret_cast<const uint4*>(y);
+    Acc acc = 0;
+    while (row < rows) {
+        const unsigned long long e0 = vec * V;
+        if (e0 < row_valid) {
+            const unsigned long long i = row * row_vecs + vec;
+            const uint4 a = ld_global_stream16(xv + i), b = ld_global_stream16(yv + i);
+            const unsigned long long left = row_valid - e0;
+            #pragma unroll
+            for (int j = 0; j < V; ++j)
+                if ((unsigned long long)j < left) acc += (Acc)R::mul(reinterpret_cast<const T*>(&a)[j], reinterpret_cast<const T*>(&b)[j]);
+        }
+        row += srow; vec += svec;
+        if (vec >= row_vecs) { vec -= row_vecs; ++row; }
+    }
+    __shared__ Acc sm[DS_THREADS / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Acc v = threadIdx.x < DS_THREADS / 32 ? sm[threadIdx.x] : Acc(0);
+        v = warp_sum(v);
+        if (threadIdx.x == 0) partials[blockIdx.x] = v;
+    }
+}
+
+template <class T, class Acc>
+static void dot_sum_launch(const Shard& s, size_t elems, size_t row_stride, size_t row_valid, const void* X, const void* Y, void* scratch, void* partial) {
+    constexpr size_t V = 16 / sizeof(T);
+    const size_t blocks = (elems / V + DS_THREADS - 1) / DS_THREADS;   // one 16-B vector per thread and pass
+    const int grid = (int)(blocks < (size_t)DS_MAX_BLOCKS ? (blocks ? blocks : 1) : DS_MAX_BLOCKS);
+    if (row_stride && row_valid < row_stride)
+        dot_sum_stage1_rows<T, Acc><<<grid, DS_THREADS, 0, s.stream>>>((const T*)X, (const T*)Y, (Acc*)scratch, elems / row_stride, row_stride / V, row_valid);
+    else
+        dot_sum_stage1<T, Acc><<<grid, DS_THREADS, 0, s.stream>>>((const T*)X, (const T*)Y, (Acc*)scratch, elems);
+    dot_sum_stage2<Acc><<<1, DS_THREADS, 0, s.stream>>>((const Acc*)scratch, grid, (Acc*)partial);
+}
+
+// scratch_dev: >= DS_MAX_BLOCKS * 8 bytes.  AoS: elems = count*d, row_stride = 0.  SoA: elems = stride*d, rows of
+// row_stride items of which the first row_valid are data (the rest is padding and is skipped).
+int dot_sum_partial(const Shard& s, int dtype, size_t elems, size_t row_stride, size_t row_valid, const void* X, const void* Y, void* scratch, void* partial) {
     switch (dtype) {
-        case T5D_F64:
-            dot_sum_stage1<double, double><<<grid, DS_THREADS, 0, s.stream>>>((const double*)X, (const double*)Y, (double*)scratch, elems);
-            dot_sum_stage2<double><<<1, DS_THREADS, 0, s.stream>>>((const double*)scratch, grid, (double*)partial);
-            break;
-        case T5D_F32:
-            dot_sum_stage1<float, double><<<grid, DS_THREADS, 0, s.stream>>>((const float*)X, (const float*)Y, (double*)scratch, elems);
-            dot_sum_stage2<double><<<1, DS_THREADS, 0, s.stream>>>((const double*)scratch, grid, (double*)partial);
-            break;
-        case T5D_I64:
-            dot_sum_stage1<long long, unsigned long long><<<grid, DS_THREADS, 0, s.stream>>>((const long long*)X, (const long long*)Y, (unsigned long long*)scratch, elems);
-            dot_sum_stage2<unsigned long long><<<1, DS_THREADS, 0, s.stream>>>((const unsigned long long*)scratch, grid, (unsigned long long*)partial);
-            break;
+        case T5D_F64: dot_sum_launch<double, double>(s, elems, row_stride, row_valid, X, Y, scratch, partial); break;
+        case T5D_F32: dot_sum_launch<float, double>(s, elems, row_stride, row_valid, X, Y, scratch, partial); break;
+        case T5D_I64: dot_sum_launch<long long, unsigned long long>(s, elems, row_stride, row_valid, X, Y, scratch, partial); break;
         default: return T5I_UNSUPPORTED;
     }
     return ok();

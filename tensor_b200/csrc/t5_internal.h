@@ -77,7 +77,8 @@ int generic_zip(const Shard& s, int dtype, int op, size_t elems, const void* A, 
 int generic_replicate(const Shard& s, int elem_bytes, size_t d, const void* rec_dev, void* O);
 int generic_scale(const Shard& s, int dtype, const void* scalar_host, size_t elems, const void* A, void* C);
 // per-device partial of sum_b dot(x_b, y_b): *partial_dev is double (F64/F32) or int64
-int dot_sum_partial(const Shard& s, int dtype, size_t elems, const void* X, const void* Y, void* scratch_dev, void* partial_dev);
+// (SoA: rows of row_stride items, the first row_valid are data; AoS: row_stride = 0)
+int dot_sum_partial(const Shard& s, int dtype, size_t elems, size_t row_stride, size_t row_valid, const void* X, const void* Y, void* scratch_dev, void* partial_dev);
 int fill_synthetic(const Shard& s, int dtype, size_t elems_per_item, uint64_t seed, uint64_t op_id, void* dst);
 int plant_specials(const Shard& s, int dtype, int n, uint64_t swap_every, uint64_t sing_every, void* A);
 // AoS [count][d] <-> SoA [d][stride]

@@ -25,7 +25,7 @@
 --------------------------------------------------------------------------------
 
 module Data.Tensor.Device
-    ( Context(..), withContext, contextDevices
+    ( Context(..), withContext, contextDevices, liveBuffers
     , DeviceElt(..)
     , Batch, batchCount, batchShape
     , fromTensors, toTensors, fromListB, toListB
@@ -68,6 +68,11 @@ instance Exception TensorDeviceException
 -- in it is sharded over them (t5_partition).
 newtype Context = Context (Ptr Ctx)
 
+-- | Run an action with a device context.  @t5_shutdown@ runs when the action ends - typically BEFORE the garbage
+-- collector has run the @t5_free@ finalizers of the batches the action created.  That order is legal by contract
+-- (include/t5b200.h, t5_shutdown): the library releases the device memory of the still-live buffers at shutdown
+-- and turns them into orphans, every later operation on one of them throws 'DeviceError' (T5_ERR_INVALID), and
+-- the finalizer of an orphan only releases its handle.  No 'touchForeignPtr' choreography is needed.
 withContext :: [Int] -> (Context -> IO a) -> IO a
 withContext devs act =
     withArrayLen (map fromIntegral devs) $ \n p ->
@@ -79,6 +84,10 @@ withContext devs act =
 
 contextDevices :: Context -> IO Int
 contextDevices (Context h) = fromIntegral <$> c_ndev h
+
+-- | Batches allocated in this context whose finalizer has not run yet.
+liveBuffers :: Context -> IO Int
+liveBuffers (Context h) = fromIntegral <$> c_live_buffers h
 
 -- | Element types that have device kernels.
 class (Storable e, NFData e) => DeviceElt e where

@@ -38,6 +38,7 @@ foreign import ccall safe "t5_version"    c_version    :: IO CString
 
 foreign import ccall safe "t5_init"     c_init     :: Ptr CInt -> CInt -> Ptr (Ptr Ctx) -> IO CInt
 foreign import ccall safe "t5_shutdown" c_shutdown :: Ptr Ctx -> IO CInt
+foreign import ccall safe "t5_live_buffers" c_live_buffers :: Ptr Ctx -> IO CInt
 foreign import ccall safe "t5_ndev"     c_ndev     :: Ptr Ctx -> IO CInt
 foreign import ccall safe "t5_sync"     c_sync     :: Ptr Ctx -> IO CInt
 foreign import ccall safe "t5_partition"

@@ -1,11 +1,13 @@
-{-# LANGUAGE DataKinds              #-}
-{-# LANGUAGE FlexibleContexts       #-}
-{-# LANGUAGE FlexibleInstances      #-}
-{-# LANGUAGE FunctionalDependencies #-}
-{-# LANGUAGE KindSignatures         #-}
-{-# LANGUAGE MultiParamTypeClasses  #-}
-{-# LANGUAGE ScopedTypeVariables    #-}
-{-# LANGUAGE TypeOperators          #-}
+{-# LANGUAGE DataKinds             #-}
+{-# LANGUAGE FlexibleContexts      #-}
+{-# LANGUAGE FlexibleInstances     #-}
+{-# LANGUAGE KindSignatures        #-}
+{-# LANGUAGE MultiParamTypeClasses #-}
+{-# LANGUAGE PolyKinds             #-}
+{-# LANGUAGE ScopedTypeVariables   #-}
+{-# LANGUAGE TypeFamilies          #-}
+{-# LANGUAGE TypeOperators         #-}
+{-# LANGUAGE UndecidableInstances  #-}
 
 --------------------------------------------------------------------------------
 -- |
@@ -14,282 +16,199 @@
 -- The linear-algebra classes the reference dropped in 0.2.0 (CHANGELOG.md:24-29:
 -- @MatrixProduct@, @TensorProduct@; @SquareMatrix@ named at :28), re-introduced
 -- with the semantics fixed in SURVEY.md §8a, and their instances for device
--- batches ("Data.Tensor.Device").  Each method is ONE @ccall@ into libt5b200.so;
--- shapes come from the type-level index list exactly as Data.Tensor.Vector takes
--- them (@fromShape sing@, src/Data/Tensor/Vector.hs:189, :231, :363).
+-- batches ("Data.Tensor.Device").
 --
--- Results are in 'IO' because they allocate device buffers; a pure facade can wrap
--- them with 'unsafePerformIO' since inputs are immutable (SURVEY.md §8b Ownership).
+-- The class methods are PURE, like every operation of the reference
+-- (@transpose@, src/Data/Indexable.hs:101-102; the Functor / Applicative
+-- instances, src/Data/Tensor/Vector.hs:180-190): a device batch is an immutable
+-- value, every operation returns a fresh buffer and never writes its operands
+-- (include/t5b200.h, "Inputs are never written"), so wrapping the one @ccall@ of
+-- "Data.Tensor.LinearAlgebra.Device" in 'unsafePerformIO' is referentially
+-- transparent.  Each wrapper is NOINLINE (one allocation per evaluation, no
+-- duplication by the simplifier) and uses 'unsafePerformIO', not
+-- 'unsafeDupablePerformIO': a duplicated evaluation would launch the kernel twice.
+-- Laziness is safe with respect to context lifetime: a thunk forced after
+-- 'withContext' has returned finds a closed context, the library answers
+-- T5_ERR_INVALID (never a crash - buffers outliving t5_shutdown are orphans,
+-- t5b200.h), and the wrapper throws 'DeviceError'.
+--
+-- Result SHAPES are computed at the type level - @is ++ js@ for the tensor
+-- product, the reference's own 'ReverseI' relation (src/Data/Indexable.hs:82-97)
+-- for 'transpose' - through associated type families, so that a shape error is a
+-- type error exactly as with "Data.Tensor.Vector".
 --
 -- NOT TYPE-CHECKED here (no GHC in the image, SURVEY.md §0 F2).
 --------------------------------------------------------------------------------
 
 module Data.Tensor.LinearAlgebra
-    ( MatrixProduct(..), DotProduct(..), TensorProduct(..), Transpose(..)
+    ( -- * Classes (pure)
+      MatrixProduct(..), DotProduct(..), TensorProduct(..), Product(..)
     , SquareMatrix(..), LinearSystem(..)
-    , dotSum, prodN, tr, polyEval, charPoly, minPoly, rowEchelonForm, echelonWith
-    , addB, subB, hadamardB, scaleB, replicateB, pureB, unitB
+    , transposeB'
+      -- * Type-level shape arithmetic
+    , type (++), Drop, Take
+      -- * Pure forms of the remaining operations
+    , dotSum', tr', polyEval', charPoly', minPoly', rowEchelonForm', triangularSolve'
+    , (.+.), (.-.), (.*), hadamard
+      -- * The IO layer, re-exported for callers that sequence device work themselves
+    , module Data.Tensor.LinearAlgebra.Device
     ) where
 
-import           Control.Exception     (throwIO)
 import           Data.Proxy
 import           Data.Singletons
-import           Data.Word
-import           Foreign.C.Types       (CInt)
-import           Foreign.Marshal.Alloc (alloca)
-import           Foreign.Marshal.Utils (with)
-import           Foreign.Marshal.Array (withArrayLen)
-import qualified Data.Vector.Storable  as S
-import           Foreign.Ptr
-import           Foreign.Storable
+import           Data.Word                        (Word8)
+import           System.IO.Unsafe                 (unsafePerformIO)
 
-import           Data.MultiIndex       (PI (..), Shape, fromShape)
-import           Data.Tensor           (TensorException (WrongListLength))
+import           Data.Indexable                   (ReverseI)
+import           Data.MultiIndex                  (PI (..), fromPI)
 import           Data.Tensor.Device
-import           Data.Tensor.Device.FFI
+import           Data.Tensor.LinearAlgebra.Device
 
 infixl 7 .*.
 infixl 7 ⊗
+infixl 6 .+., .-.
+infixl 7 .*
+
+-- | List concatenation on index lists: the shape of a tensor product.
+type family (is :: [PI]) ++ (js :: [PI]) :: [PI] where
+    '[]       ++ js = js
+    (i ': is) ++ js = i ': (is ++ js)
+
+-- | @Take n is@ / @Drop n is@ with a unary count: the shape arithmetic of @prod n@.
+type family Drop (n :: PI) (is :: [PI]) :: [PI] where
+    Drop 'One      (i ': is) = is
+    Drop ('S n)    (i ': is) = Drop n is
+type family Take (n :: PI) (is :: [PI]) :: [PI] where
+    Take 'One      (i ': is) = '[i]
+    Take ('S n)    (i ': is) = i ': Take n is
+-- | All but the last @n@ indices.
+type family DropLast (n :: PI) (is :: [PI]) :: [PI] where
+    DropLast n is = RevList (Drop n (RevList is))
+type family RevList (is :: [PI]) :: [PI] where
+    RevList is = RevOnto is '[]
+type family RevOnto (is :: [PI]) (acc :: [PI]) :: [PI] where
+    RevOnto '[]       acc = acc
+    RevOnto (i ': is) acc = RevOnto is (i ': acc)
 
 -- | @a .*. b@ contracts the last index of @a@ with the first of @b@.
-class MatrixProduct a b c | a b -> c where
-    (.*.) :: a -> b -> IO c
+class MatrixProduct a b where
+    type MatrixProductSpace a b
+    (.*.) :: a -> b -> MatrixProductSpace a b
 
 -- | One scalar per pair: @fold_{i ascending} (acc + x_i * y_i)@, @acc0 = 0@.
-class DotProduct a s | a -> s where
-    dot :: a -> a -> IO s
+class DotProduct a where
+    type DotSpace a
+    dot :: a -> a -> DotSpace a
 
 -- | @a ⊗ b@: the rank-(r+s) outer product, one multiply per component.
-class TensorProduct a b c | a b -> c where
-    (⊗) :: a -> b -> IO c
+class TensorProduct a b where
+    type a :⊗: b
+    (⊗) :: a -> b -> a :⊗: b
 
--- | Full index reversal — @transpose = unRev . t0@ (src/Data/Indexable.hs:101-102).
-class Transpose a b | a -> b where
-    transpose :: a -> IO b
+-- | @prod n a b@: contract the last @n@ indices of @a@ with the first @n@ of @b@ (the count is a
+-- type-level 'PI' passed by proxy, so the result shape is computed).
+class Product (n :: PI) a b where
+    type ProdSpace n a b
+    prod :: proxy n -> a -> b -> ProdSpace n a b
 
--- | @det@; @inverse@ returns the per-item 'Maybe' as a status batch (0 = Just, 1 = Nothing).
-class SquareMatrix m s st | m -> s st where
-    det     :: m -> IO s
-    inverse :: m -> IO (m, st)
+-- | @det@ and @inverse@; the per-item 'Maybe' of @inverse@ is the status batch (0 = Just, 1 = Nothing).
+class SquareMatrix m where
+    type Scalars m
+    type Statuses m
+    det     :: m -> Scalars m
+    inverse :: m -> (m, Statuses m)
 
 -- | @solve a b@: unique-solution square systems (first-non-zero pivoting, SURVEY §8a).
-class LinearSystem m v st | m v -> st where
-    solve :: m -> v -> IO (v, st)
+class LinearSystem m v where
+    type SolStatuses m v
+    solve :: m -> v -> (v, SolStatuses m v)
 
-dims :: [Int] -> [Word64]
-dims = map fromIntegral
+-- Instances for device batches ---------------------------------------------------------------
 
-code :: forall e. DeviceElt e => Proxy e -> CInt
-code = dtypeCode
+instance (SingI i, SingI j, SingI k, DeviceElt e) => MatrixProduct (Batch '[i, j] e) (Batch '[j, k] e) where
+    type MatrixProductSpace (Batch '[i, j] e) (Batch '[j, k] e) = Batch '[i, k] e
+    a .*. b = pure2 matmulB a b
 
--- matrix . matrix --------------------------------------------------------------
-instance (SingI i, SingI j, SingI k, DeviceElt e) =>
-         MatrixProduct (Batch '[i, j] e) (Batch '[j, k] e) (Batch '[i, k] e) where
-    a .*. b = do
-        let [m, kk] = batchShape a; [_, n] = batchShape b
-            Context h = batchCtx a
-        c <- newBatch (batchCtx a) (batchCount a)
-        unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
-            c_matmul h (code (Proxy :: Proxy e)) (fromIntegral m) (fromIntegral kk) (fromIntegral n) pa pb pc
-                >>= checkRC (batchCtx a) "t5_matmul"
-        return c
+instance (SingI i, SingI j, DeviceElt e) => MatrixProduct (Batch '[i, j] e) (Batch '[j] e) where
+    type MatrixProductSpace (Batch '[i, j] e) (Batch '[j] e) = Batch '[i] e
+    a .*. x = pure2 matvecB a x
 
--- matrix . vector --------------------------------------------------------------
-instance (SingI i, SingI j, DeviceElt e) =>
-         MatrixProduct (Batch '[i, j] e) (Batch '[j] e) (Batch '[i] e) where
-    a .*. x = do
-        let [m, kk] = batchShape a
-            Context h = batchCtx a
-        y <- newBatch (batchCtx a) (batchCount a)
-        unsafeWithBatch a $ \pa -> unsafeWithBatch x $ \px -> unsafeWithBatch y $ \py ->
-            c_matmul h (code (Proxy :: Proxy e)) (fromIntegral m) (fromIntegral kk) 1 pa px py
-                >>= checkRC (batchCtx a) "t5_matmul"
-        return y
+instance (SingI i, DeviceElt e) => DotProduct (Batch '[i] e) where
+    type DotSpace (Batch '[i] e) = Batch '[] e
+    dot x y = pure2 dotB x y
 
-instance (SingI i, DeviceElt e) => DotProduct (Batch '[i] e) (Batch '[] e) where
-    dot x y = do
-        let [n] = batchShape x
-            Context h = batchCtx x
-        s <- newBatch (batchCtx x) (batchCount x)
-        unsafeWithBatch x $ \px -> unsafeWithBatch y $ \py -> unsafeWithBatch s $ \ps ->
-            c_dot h (code (Proxy :: Proxy e)) (fromIntegral n) px py ps >>= checkRC (batchCtx x) "t5_dot"
-        return s
+instance (SingI is, SingI js, SingI (is ++ js), DeviceElt e) => TensorProduct (Batch is e) (Batch js e) where
+    type Batch is e :⊗: Batch js e = Batch (is ++ js) e
+    a ⊗ b = pure2 tensorProductB a b
 
--- | Sum over the batch of 'dot' — the only operation with a cross-GPU exchange
--- (1-element ncclAllReduce, SURVEY.md §8e).
-dotSum :: forall i e. (SingI i, DeviceElt e) => Batch '[i] e -> Batch '[i] e -> IO e
-dotSum x y = alloca $ \out -> do
-    let [n] = batchShape x
-        Context h = batchCtx x
-    unsafeWithBatch x $ \px -> unsafeWithBatch y $ \py ->
-        c_dot_sum h (code (Proxy :: Proxy e)) (fromIntegral n) px py (castPtr out)
-            >>= checkRC (batchCtx x) "t5_dot_sum"
-    peek out
+instance (SingI is, SingI js, SingI (DropLast n is ++ Drop n js), SingI n, DeviceElt e)
+      => Product n (Batch is e) (Batch js e) where
+    type ProdSpace n (Batch is e) (Batch js e) = Batch (DropLast n is ++ Drop n js) e
+    prod _ a b = pure2 (prodN (piToInt (sing :: Sing n))) a b
 
-instance (SingI is, SingI js, SingI ks, DeviceElt e {- ks ~ is ++ js -}) =>
-         TensorProduct (Batch is e) (Batch js e) (Batch ks e) where
-    a ⊗ b = do
-        let da = batchShape a; db = batchShape b
-            Context h = batchCtx a
-        c <- newBatch (batchCtx a) (batchCount a)
-        withArrayLen (dims da) $ \ra pda -> withArrayLen (dims db) $ \rb pdb ->
-          unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
-            c_prod h (code (Proxy :: Proxy e)) (fromIntegral ra) pda (fromIntegral rb) pdb 0 pa pb pc
-                >>= checkRC (batchCtx a) "t5_prod"
-        return c
+instance (SingI i, DeviceElt e, Fractional e) => SquareMatrix (Batch '[i, i] e) where
+    type Scalars  (Batch '[i, i] e) = Batch '[] e
+    type Statuses (Batch '[i, i] e) = Batch '[] Word8
+    det a     = pure1 detB a
+    inverse a = pure1 inverseB a
 
-instance (SingI is, SingI js, DeviceElt e {- js ~ Reverse is -}) =>
-         Transpose (Batch is e) (Batch js e) where
-    transpose a = do
-        let da = batchShape a
-            Context h = batchCtx a
-        t <- newBatch (batchCtx a) (batchCount a)
-        withArrayLen (dims da) $ \r pd -> unsafeWithBatch a $ \pa -> unsafeWithBatch t $ \pt ->
-            c_transpose h (code (Proxy :: Proxy e)) (fromIntegral r) pd pa pt >>= checkRC (batchCtx a) "t5_transpose"
-        return t
+instance (SingI i, DeviceElt e, Fractional e) => LinearSystem (Batch '[i, i] e) (Batch '[i] e) where
+    type SolStatuses (Batch '[i, i] e) (Batch '[i] e) = Batch '[] Word8
+    solve a b = pure2 solveB a b
 
-instance (SingI i, DeviceElt e, Fractional e) =>
-         SquareMatrix (Batch '[i, i] e) (Batch '[] e) (Batch '[] Word8) where
-    det a = do
-        let [n, _] = batchShape a
-            Context h = batchCtx a
-        d <- newBatch (batchCtx a) (batchCount a)
-        unsafeWithBatch a $ \pa -> unsafeWithBatch d $ \pd ->
-            c_det h (code (Proxy :: Proxy e)) (fromIntegral n) pa pd >>= checkRC (batchCtx a) "t5_det"
-        return d
-    inverse a = do
-        let [n, _] = batchShape a
-            Context h = batchCtx a
-        x  <- newBatch (batchCtx a) (batchCount a)
-        st <- newStatusBatch (batchCtx a) (batchCount a)
-        unsafeWithBatch a $ \pa -> unsafeWithBatch x $ \px -> unsafeWithBatch st $ \ps ->
-            c_inverse h (code (Proxy :: Proxy e)) (fromIntegral n) pa px ps >>= checkRC (batchCtx a) "t5_inverse"
-        return (x, st)
+-- | 'Data.Indexable.transpose' for device batches, with the reference's own constraint
+-- (@ReverseI is '[] js@, src/Data/Indexable.hs:101) computing the result shape.  It is a separate
+-- function rather than a 'MultiIndexable' instance because a batch has no per-element 'Indexable'
+-- access from Haskell (its elements live in HBM); on a batch it is one gather kernel.
+transposeB' :: forall is js e. (ReverseI is '[] js, SingI is, SingI js, DeviceElt e) => Batch is e -> Batch js e
+transposeB' a = pure1 transposeB a
 
-instance (SingI i, DeviceElt e, Fractional e) =>
-         LinearSystem (Batch '[i, i] e) (Batch '[i] e) (Batch '[] Word8) where
-    solve a b = do
-        let [n, _] = batchShape a
-            Context h = batchCtx a
-        x  <- newBatch (batchCtx a) (batchCount a)
-        st <- newStatusBatch (batchCtx a) (batchCount a)
-        unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch x $ \px -> unsafeWithBatch st $ \ps ->
-            c_solve h (code (Proxy :: Proxy e)) (fromIntegral n) 1 pa pb px ps >>= checkRC (batchCtx a) "t5_solve"
-        return (x, st)
+-- Pure forms of the remaining operations --------------------------------------------------------
 
--- | @prodN n a b@ (@prod n@): contract the last @n@ indices of @a@ with the first @n@ of @b@.
-prodN :: forall is js ks e. (SingI is, SingI js, SingI ks, DeviceElt e)
-      => Int -> Batch is e -> Batch js e -> IO (Batch ks e)
-prodN n a b = do
-    let Context h = batchCtx a
-    c <- newBatch (batchCtx a) (batchCount a)
-    withArrayLen (dims (batchShape a)) $ \ra pda -> withArrayLen (dims (batchShape b)) $ \rb pdb ->
-      unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
-        c_prod h (code (Proxy :: Proxy e)) (fromIntegral ra) pda (fromIntegral rb) pdb (fromIntegral n) pa pb pc
-            >>= checkRC (batchCtx a) "t5_prod"
-    return c
+-- | Sum over the batch of 'dot' - the only operation with a cross-GPU exchange (SURVEY.md §8e).
+dotSum' :: (SingI i, DeviceElt e) => Batch '[i] e -> Batch '[i] e -> e
+dotSum' x y = pure2 dotSum x y
 
--- The rest of the old SquareMatrix class (CHANGELOG.md:28-29; SURVEY.md §8f-4) ------------
+tr' :: (SingI i, DeviceElt e) => Batch '[i, i] e -> Batch '[] e
+tr' a = pure1 tr a
 
--- | Trace: @fold_{i ascending} (acc + a_ii)@ from 0.
-tr :: forall i e. (SingI i, DeviceElt e) => Batch '[i, i] e -> IO (Batch '[] e)
-tr a = do
-    let [n, _] = batchShape a; Context h = batchCtx a
-    o <- newBatch (batchCtx a) (batchCount a)
-    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po ->
-        c_trace h (code (Proxy :: Proxy e)) (fromIntegral n) pa po >>= checkRC (batchCtx a) "t5_trace"
-    return o
+polyEval' :: (SingI i, DeviceElt e) => [e] -> Batch '[i, i] e -> Batch '[i, i] e
+polyEval' cs a = pure1 (polyEval cs) a
 
--- | @polyEval cs a = c0 I + c1 a + .. + cd a^d@ (Horner), coefficients low order first.
-polyEval :: forall i e. (SingI i, DeviceElt e) => [e] -> Batch '[i, i] e -> IO (Batch '[i, i] e)
-polyEval cs a = do
-    let [n, _] = batchShape a; Context h = batchCtx a
-    o <- newBatch (batchCtx a) (batchCount a)
-    S.unsafeWith (S.fromList cs) $ \pc -> unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po ->
-        c_poly_eval h (code (Proxy :: Proxy e)) (fromIntegral n) (castPtr pc) (fromIntegral (length cs)) pa po
-            >>= checkRC (batchCtx a) "t5_poly_eval"
-    return o
+charPoly' :: (SingI i, DeviceElt e, Fractional e) => Batch '[i, i] e -> Batch '[ 'S i ] e
+charPoly' a = pure1 charPoly a
 
--- | Coefficients of @det (xI - a)@, low order first (@n + 1@ per item; the result shape
--- @'[j]@ must be @i + 1@).
-charPoly :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e) => Batch '[i, i] e -> IO (Batch '[j] e)
-charPoly a = do
-    let [n, _] = batchShape a; Context h = batchCtx a
-    o <- newBatch (batchCtx a) (batchCount a)
-    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po ->
-        c_char_poly h (code (Proxy :: Proxy e)) (fromIntegral n) pa po >>= checkRC (batchCtx a) "t5_char_poly"
-    return o
+minPoly' :: (SingI i, DeviceElt e, Fractional e) => Batch '[i, i] e -> (Batch '[ 'S i ] e, Batch '[] Word8)
+minPoly' a = pure1 minPoly a
 
--- | Minimal polynomial (zero-padded above its degree) and the degree per item.
-minPoly :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e)
-        => Batch '[i, i] e -> IO (Batch '[j] e, Batch '[] Word8)
-minPoly a = do
-    let [n, _] = batchShape a; Context h = batchCtx a
-    o <- newBatch (batchCtx a) (batchCount a)
-    d <- newStatusBatch (batchCtx a) (batchCount a)
-    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po -> unsafeWithBatch d $ \pd ->
-        c_min_poly h (code (Proxy :: Proxy e)) (fromIntegral n) pa po pd >>= checkRC (batchCtx a) "t5_min_poly"
-    return (o, d)
+rowEchelonForm' :: (SingI i, SingI j, DeviceElt e, Fractional e) => Batch '[i, j] e -> (Batch '[i, j] e, Batch '[] Word8)
+rowEchelonForm' a = pure1 rowEchelonForm a
 
--- | Reduced row echelon form of every item and its rank (the @rowEchelonForm@ of the old
--- @Data.Tensor.LinearAlgebra@, CHANGELOG.md:24-29): Gauss-Jordan with the first-non-zero pivot rule.
-rowEchelonForm :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e)
-               => Batch '[i, j] e -> IO (Batch '[i, j] e, Batch '[] Word8)
-rowEchelonForm a = let [_, c] = batchShape a in echelonWith c a
+-- | @triangularSolve' k ab@: reduce the first @k@ columns of the augmented batch @[a | b]@.
+triangularSolve' :: (SingI i, SingI j, DeviceElt e, Fractional e)
+                 => Int -> Batch '[i, j] e -> (Batch '[i, j] e, Batch '[] Word8)
+triangularSolve' k a = pure1 (echelonWith k) a
 
--- | @triangularSolve@ on an augmented batch @[a | b]@ whose first @k@ columns are @a@: row operations
--- until @a@ is in reduced row echelon form, @b@ carried along; pivots are only looked for in @a@.
--- (Build the augmented batch with 'append' and cut the result with 'split'.)
-echelonWith :: forall i j e. (SingI i, SingI j, DeviceElt e, Fractional e)
-            => Int -> Batch '[i, j] e -> IO (Batch '[i, j] e, Batch '[] Word8)
-echelonWith k a = do
-    let [r, c] = batchShape a; Context h = batchCtx a
-    o <- newBatch (batchCtx a) (batchCount a)
-    d <- newStatusBatch (batchCtx a) (batchCount a)
-    unsafeWithBatch a $ \pa -> unsafeWithBatch o $ \po -> unsafeWithBatch d $ \pd ->
-        c_row_echelon h (code (Proxy :: Proxy e)) (fromIntegral r) (fromIntegral c) (fromIntegral k) pa po pd
-            >>= checkRC (batchCtx a) "t5_row_echelon"
-    return (o, d)
+-- | The vector-space operations (@liftA2 (+)@, @liftA2 (-)@, @fmap (k *)@ of
+-- src/Data/Tensor/Vector.hs:180-190, :250-251) on batches.
+(.+.), (.-.), hadamard :: (SingI is, DeviceElt e) => Batch is e -> Batch is e -> Batch is e
+a .+. b = pure2 addB a b
+a .-. b = pure2 subB a b
+hadamard a b = pure2 hadamardB a b
 
--- Vector-space operations: what @liftA2 (+)@, @liftA2 (-)@, @liftA2 (*)@ and @fmap (k *)@ of the
--- Functor / Applicative instances (src/Data/Tensor/Vector.hs:180-190, :250-251) are on batches.
-zipB :: forall is e. (SingI is, DeviceElt e) => CInt -> Batch is e -> Batch is e -> IO (Batch is e)
-zipB op a b = do
-    let Context h = batchCtx a
-    c <- newBatch (batchCtx a) (batchCount a)
-    unsafeWithBatch a $ \pa -> unsafeWithBatch b $ \pb -> unsafeWithBatch c $ \pc ->
-        c_zip h (code (Proxy :: Proxy e)) op pa pb pc >>= checkRC (batchCtx a) "t5_zip"
-    return c
+(.*) :: (SingI is, DeviceElt e) => e -> Batch is e -> Batch is e
+k .* a = pure1 (scaleB k) a
 
-addB, subB, hadamardB :: (SingI is, DeviceElt e) => Batch is e -> Batch is e -> IO (Batch is e)
-addB = zipB 0
-subB = zipB 1
-hadamardB = zipB 2
+-- Purification ----------------------------------------------------------------------------------
 
--- | Every item a copy of one tensor given as its row-major element list (length checked against the
--- shape like 'fromList', src/Data/Tensor/Vector.hs:362-366).
-replicateB :: forall is e. (SingI is, DeviceElt e) => Context -> Int -> [e] -> IO (Batch is e)
-replicateB ctx@(Context h) n xs = do
-    o <- newBatch ctx n
-    let d = fromIntegral (product (batchShape o)) :: Int
-    if length xs /= d then throwIO WrongListLength else
-        S.unsafeWith (S.fromList xs) $ \px -> unsafeWithBatch o $ \po ->
-            c_replicate h (code (Proxy :: Proxy e)) (castPtr px) po >>= checkRC ctx "t5_replicate"
-    return o
+pure1 :: (a -> IO r) -> a -> r
+pure1 f a = unsafePerformIO (f a)
+{-# NOINLINE pure1 #-}
 
--- | @pure a@ of the Applicative instance (src/Data/Tensor/Vector.hs:185-188) on a batch.
-pureB :: forall is e. (SingI is, DeviceElt e) => Context -> Int -> e -> IO (Batch is e)
-pureB ctx n a = replicateB ctx n (replicate (fromIntegral (product (fromShape (sing :: Shape is)))) a)
+pure2 :: (a -> b -> IO r) -> a -> b -> r
+pure2 f a b = unsafePerformIO (f a b)
+{-# NOINLINE pure2 #-}
 
--- | @unit@ of the old @SquareMatrix@ class: a batch of identity matrices.
-unitB :: forall i e. (SingI i, DeviceElt e, Num e) => Context -> Int -> IO (Batch '[i, i] e)
-unitB ctx n = let k = fromIntegral (head (fromShape (sing :: Shape '[i, i]))) :: Int
-              in replicateB ctx n [if r == c then 1 else 0 | r <- [1 .. k], c <- [1 .. k]]
-
-scaleB :: forall is e. (SingI is, DeviceElt e) => e -> Batch is e -> IO (Batch is e)
-scaleB k a = do
-    let Context h = batchCtx a
-    c <- newBatch (batchCtx a) (batchCount a)
-    with k $ \pk -> unsafeWithBatch a $ \pa -> unsafeWithBatch c $ \pc ->
-        c_scale h (code (Proxy :: Proxy e)) (castPtr pk) pa pc >>= checkRC (batchCtx a) "t5_scale"
-    return c
+-- | The run-time value of a type-level positive integer ('fromPI', src/Data/MultiIndex.hs:64-66).
+piToInt :: Sing (n :: PI) -> Int
+piToInt = fromPI

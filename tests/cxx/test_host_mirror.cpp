@@ -210,6 +210,31 @@ int main() {
         expect_bits("inverse_host", hinv, hi_want);
         expect_bits("inverse_host status", hst, wst);
     }
+    {   // ownership: a finalizer may run t5_free AFTER t5_shutdown.  The buffers become orphans:
+        // operations on them are refused, a late free only releases the handle, nothing touches freed memory.
+        t5_ctx* h = nullptr;
+        const int dev0 = 0;
+        bool ok = t5_init(&dev0, 1, &h) == T5_OK;
+        t5_buf *a = nullptr, *b = nullptr;
+        ok = ok && t5_alloc(h, T5_F64, 9, 1000, T5_AOS, &a) == T5_OK && t5_alloc(h, T5_F64, 9, 1000, T5_SOA, &b) == T5_OK;
+        ok = ok && t5_live_buffers(h) == 2;
+        ok = ok && t5_free(b) == T5_OK && t5_live_buffers(h) == 1;
+        ok = ok && t5_shutdown(h) == T5_OK;                  // one buffer still alive
+        std::vector<double> host(9000);
+        ok = ok && t5_download(a, host.data(), host.size() * 8) == T5_ERR_INVALID;   // orphan: refused, no crash
+        ok = ok && t5_shutdown(h) == T5_ERR_INVALID;         // struct still alive because of the orphan: detected
+        ok = ok && t5_free(a) == T5_OK;                      // the last orphan takes the context with it
+        std::printf("%-40s %s\n", "t5_free after t5_shutdown (orphans)", ok ? "ok" : "FAILED");
+        if (!ok) ++failures;
+        // the same through the C++ mirror: a Batch (shared_ptr deleter = t5_free) that outlives its Context
+        std::unique_ptr<Batch<double, 3, 3>> late;
+        {
+            Context inner({0});
+            late.reset(new Batch<double, 3, 3>(Batch<double, 3, 3>::pure(inner, 100, 1.5)));
+        }
+        late.reset();
+        std::printf("%-40s ok\n", "Batch destroyed after its Context");
+    }
     {   // fromList length check
         bool threw = false;
         try { Batch<double, 3, 3>::from_list(ctx, 2, std::vector<double>(17)); } catch (const WrongListLength&) { threw = true; }
