@@ -37,6 +37,8 @@ WORKLOADS = {
                              desc="1Mi pairs of 3x3 Int64 matrices, .*. (configs[0], bit-exact variant)"),
     "matmul3x3_f64_64M": dict(op="matmul", dtype="f64", m=3, k=3, n=3, batch=1 << 26, bytes=216, bound="hbm",
                               desc="64Mi pairs of 3x3 Double matrices, .*. (launch-amortised size, SURVEY H6)"),
+    "inverse4_f64_64M": dict(op="inverse", dtype="f64", n=4, batch=1 << 26, bytes=257, bound="hbm",
+                             desc="64Mi 4x4 Double inverse (configs[2] at a launch-amortised size, SURVEY H6)"),
     "transpose4x4_f32_16M": dict(op="transpose", dtype="f32", dims=(4, 4), batch=1 << 24, bytes=128, bound="hbm",
                                  desc="16Mi 4x4 Float transposes (configs[1])"),
     "matvec4_f32_16M": dict(op="matmul", dtype="f32", m=4, k=4, n=1, batch=1 << 24, bytes=96, bound="hbm",
@@ -116,14 +118,33 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 
-def pcie_roofline(h2d, d2h, seconds_per_step):
-    """e2e is bound by the PCIe Gen5 x16 link, not HBM: floor = the slower direction at its measured
-    one-direction pinned-copy rate (tools/pcie_peak.cu -> profiles/r01_pcie_peak.json)."""
+def pcie_roofline(h2d, d2h, seconds_per_step, n_gpus=1):
+    """e2e is bound by the host<->device links, not HBM.  h2d / d2h are the bytes ALL GPUs move per step.  N = 1:
+    floor = the slower direction at its measured one-direction pinned-copy rate (tools/pcie_peak.cu ->
+    profiles/r01_pcie_peak.json).  N > 1: the ceiling is the measured N-way concurrent rate of this box class
+    (tools/pcie_peak_multi.cu -> profiles/r02_pcie_peak_multi.json: aggregate GB/s with N devices copying at once,
+    2:1 H2D:D2H mix) - N single-GPU links do not add up on a VM whose host memory is the shared resource."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_pcie_peak.json")) as f:
             pk = json.load(f)
     except OSError:
         return None
+    if n_gpus > 1:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_pcie_peak_multi.json")) as f:
+                mk = json.load(f).get(f"n{n_gpus}")
+        except OSError:
+            mk = None
+        if mk:
+            mix = mk["mix_2to1"] if d2h * 4 >= h2d else mk["h2d"]
+            floor = (h2d + d2h) / (mix * 1e9)
+            return {"bound": "pcie", "n_gpus": n_gpus, "aggregate_peak": mix, "unit": "GB/s",
+                    "achieved": (h2d + d2h) / seconds_per_step / 1e9, "frac": floor / seconds_per_step,
+                    "peak_source": f"profiles/r02_pcie_peak_multi.json n{n_gpus} (N devices copying concurrently, pinned, one host thread each)"}
+        floor = max(h2d / (n_gpus * pk["h2d_32MiB"] * 1e9), d2h / (n_gpus * pk["d2h_32MiB"] * 1e9))
+        return {"bound": "pcie", "n_gpus": n_gpus, "unit": "GB/s", "achieved": (h2d + d2h) / seconds_per_step / 1e9,
+                "frac": floor / seconds_per_step,
+                "peak_source": "N x the single-GPU one-direction ceiling (no N-way measurement on file: an upper bound, not a measured ceiling)"}
     floor = max(h2d / (pk["h2d_32MiB"] * 1e9), d2h / (pk["d2h_32MiB"] * 1e9))
     return {"bound": "pcie", "h2d_peak": pk["h2d_32MiB"], "d2h_peak": pk["d2h_32MiB"], "unit": "GB/s",
             "achieved_h2d": h2d / seconds_per_step / 1e9, "achieved_d2h": d2h / seconds_per_step / 1e9,
@@ -148,11 +169,15 @@ def load_peaks():
 
 
 def load_traffic(name):
+    """DRAM bytes per launch of the workload's kernel from the round's last `ncu --set full` pass
+    (dram__bytes_read.sum + dram__bytes_write.sum; tools/ncu_summary.py writes profiles/traffic.json and stamps the
+    capture's git SHA).  A profiler cannot run inside the timed run, so this is a recorded figure with provenance."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(name)
+            j = json.load(f)
+        return j.get(name), j.get("_source")
     except Exception:
-        return None
+        return None, None
 
 
 # ---- clocks sampled during the timed region (NVML from a thread) ----------------------------
@@ -525,6 +550,159 @@ def reference_arm(args):
     return 0
 
 
+# ---- a chained expression: PCIe paid once, four operations on device-resident batches ----------------
+CHAIN_DESC = ("4Mi 4x4 Double: upload A (pinned host) -> inverse -> inverse .*. A -> transpose -> det -> download det + status; "
+              "every intermediate stays in HBM")
+
+
+def chain_e2e(ctx, tb, batch=1 << 22, reps=3, with_cpu=True):
+    """The public device API on a chain (tensor_b200.inverse / matmul / transpose / det on Batch values), wall clock
+    from the first host byte leaving to the last result byte arriving, beside the CPU port running the same chain."""
+    import oracle
+    n = 4
+    L = tb._lib.lib()
+    src = ctx.synthetic((n, n), np.float64, batch, SEED_A, 5).plant_specials(1024, 65536)
+    pin_a = tb.PinnedArray((batch, n, n), np.float64)
+    check_rc(L.t5_download(src._h, pin_a.array.ctypes.data_as(ctypes.c_void_p), pin_a.nbytes), ctx, tb)
+    src.free()
+    pin_d, pin_s = tb.PinnedArray((batch,), np.float64), tb.PinnedArray((batch,), np.uint8)
+
+    def one():
+        A = ctx.from_numpy(pin_a.array, (n, n))                      # H2D, 128 B per item
+        inv, st = tb.inverse(A)
+        P = tb.matmul(inv, A)
+        T = tb.transpose(P)
+        d = tb.det(T)
+        check_rc(L.t5_download(d._h, pin_d.array.ctypes.data_as(ctypes.c_void_p), pin_d.nbytes), ctx, tb)   # D2H, 9 B per item
+        check_rc(L.t5_download(st._h, pin_s.array.ctypes.data_as(ctypes.c_void_p), pin_s.nbytes), ctx, tb)
+        for b in (A, inv, st, P, T, d):
+            b.free()
+
+    n0 = ctx.launch_count()
+    one()
+    launches = ctx.launch_count() - n0
+    one()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
+    el = (time.perf_counter() - t0) / reps
+    # the same four kernels alone, device-resident (CUDA events): where the time goes once PCIe is out of the way
+    A = ctx.from_numpy(pin_a.array, (n, n))
+    ctx.sync()
+    ctx.timer_begin()
+    for _ in range(reps):
+        inv, st = tb.inverse(A)
+        P = tb.matmul(inv, A)
+        T = tb.transpose(P)
+        d = tb.det(T)
+        for b in (inv, st, P, T, d):
+            b.free()
+    dev_ms = ctx.timer_end() / reps
+    A.free()
+    out = {"workload": CHAIN_DESC, "batch": batch, "value": batch / el, "unit": "chains/s", "ms": el * 1e3,
+           "h2d_bytes": int(pin_a.nbytes), "d2h_bytes": int(pin_d.nbytes + pin_s.nbytes), "gpu_launches": int(launches),
+           "device_only_ms": dev_ms, "device_only_value": batch / (dev_ms * 1e-3),
+           "api": "tensor_b200.Context.from_numpy / inverse / matmul / transpose / det / t5_download (device-buffer C ABI)"}
+    if with_cpu:
+        a = pin_a.array.copy()
+        T_ = os.cpu_count() or 1
+
+        def cpu_one():
+            inv, st = oracle.inverse(a, n, threads=T_)
+            p = oracle.matmul(inv.reshape(-1), a.reshape(-1), n, n, n, threads=T_)
+            t = oracle.transpose(p.reshape(-1), [n, n], threads=T_)
+            return oracle.det(t.reshape(batch, n, n), n, threads=T_), st
+
+        dc, sc = cpu_one()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpu_one()
+        cel = (time.perf_counter() - t0) / reps
+        one()
+        same = bool(np.array_equal(pin_d.array.view(np.uint64), np.asarray(dc).reshape(-1).view(np.uint64))
+                    and np.array_equal(pin_s.array, np.asarray(sc).reshape(-1)))
+        out["cpu"] = {"value": batch / cel, "unit": "chains/s", "ms": cel * 1e3, "cores": T_, "kind": "port",
+                      "sample": f"{reps} passes over {batch} items, C++ oracle port, four calls per pass"}
+        out["bit_identical_to_cpu_chain"] = same
+    for p_ in (pin_a, pin_d, pin_s):
+        p_.free()
+    return out
+
+
+# ---- one process, N devices: the way a Haskell caller drives a box (SURVEY §8e) ----------------------------
+SP_WORKLOADS = ["matmul128_f64_64K", "matmul4x4_f32_16M", "matmul3x3_f64_1M", "matmul3x3_f64_64M", "det4_f64_4M",
+                "inverse4_f64_4M", "solve4_f64_4M", "inverse4_f64_64M", "tensorprod8x8_f64_1M"]
+
+
+def single_process_section(tb, ndev, peaks, steps=20, warmup=3, with_e2e=True):
+    """ONE context over `ndev` devices (t5_init(devices...)): every buffer and launch is split by t5_partition,
+    one stream per device, no collective except the dot-sum scalar.  STRONG scaling: the batch sizes are the
+    BASELINE totals, each device gets 1/ndev.  Times are CUDA events per device stream; `ms` = max over devices."""
+    import oracle
+    L = tb._lib.lib()
+    out = {"devices": ndev, "scaling": "strong",
+           "api": f"tensor_b200.Context(range({ndev})) = t5_init({ndev} devices); t5_partition shards the batch axis; "
+                  "one launch stream per device, launches issued back to back from one host thread",
+           "workloads": {}}
+    with tb.Context(list(range(ndev))) as ctx:
+        for name in SP_WORKLOADS:
+            w = WORKLOADS[name]
+            try:
+                ring = StepRing(ctx, tb, w)
+                for _ in range(warmup):
+                    check_rc(ring.run(), ctx, tb)
+                ctx.sync()
+                ctx.timer_begin()
+                for _ in range(steps):
+                    check_rc(ring.run(), ctx, tb)
+                ms = ctx.timer_end() / steps
+                per_dev = [x / steps for x in ctx.timer_per_device()]
+                r = roofline(w, ms, peaks)
+                out["workloads"][name] = {"desc": w["desc"], "batch_total": w["batch"], "ms": ms, "ms_per_device": per_dev,
+                                          "matrices_per_s": w["batch"] / (ms * 1e-3), "achieved": r["achieved"], "unit": r["unit"],
+                                          "frac_of_one_gpu_peak": r["frac"], "frac_of_n_gpu_peak": r["frac"] / ndev,
+                                          "operand_sets": len(ring.sets)}
+                ring.free()
+            except Exception as e:  # report, never hide
+                out["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
+        # the one cross-device exchange: per-device partial -> 1-element ncclAllReduce over NVLink -> host scalar
+        try:
+            w = WORKLOADS["dotsum4_f32_16M"]
+            st = Step(ctx, tb, w)
+            for _ in range(warmup):
+                check_rc(st.run(), ctx, tb)
+            used = int(L.t5_dot_sum_used_nccl(ctx._h))
+            if ndev > 1 and used != 1:
+                raise RuntimeError("multi-device t5_dot_sum did not go through NCCL: " + L.t5_last_error(ctx._h).decode())
+            ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                check_rc(st.run(), ctx, tb)                       # each call returns the scalar: it synchronises
+            el = (time.perf_counter() - t0) / steps
+            # Int64 sum is order-independent: bit-exact against the oracle whatever the sharding
+            B = 1 << 20
+            xi, yi = oracle.fill(oracle.I64, oracle.SEED_A, 4, B * 4), oracle.fill(oracle.I64, oracle.SEED_B, 4, B * 4)
+            got = tb.dot_sum(ctx.from_numpy(xi, (4,)), ctx.from_numpy(yi, (4,)))
+            out["dot_sum"] = {"desc": w["desc"], "batch_total": w["batch"], "ms_per_call_wall": el * 1e3, "used_nccl": used,
+                              "matrices_per_s": w["batch"] / el, "achieved_GBps": w["bytes"] * w["batch"] / el / 1e9,
+                              "int64_bit_exact_vs_oracle": bool(int(got) == int(oracle.dot_sum(xi, yi, 4)))}
+            st.free()
+        except Exception as e:
+            out["dot_sum"] = {"error": f"{type(e).__name__}: {e}"}
+        if with_e2e:
+            try:
+                hc = HostCall(ctx, tb, WORKLOADS[HEADLINE])
+                k_e = 4
+                el = time_e2e(hc, k_e)
+                out["e2e"] = {"value": hc.batch * k_e / el, "unit": "matrices/s", "batch_total": hc.batch, "h2d_bytes_per_step": int(hc.h2d),
+                              "d2h_bytes_per_step": int(hc.d2h), "api": hc.api + f" on ONE context over {ndev} devices (one host thread per device inside the call)",
+                              "roofline": pcie_roofline(hc.h2d, hc.d2h, el / k_e, ndev)}
+                hc.free()
+            except Exception as e:
+                out["e2e"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 # ---- our arm ---------------------------------------------------------------------------------------
 def ours(args):
     import tensor_b200 as tb
@@ -540,7 +718,7 @@ def ours(args):
     ctx = tb.Context([local_rank])
     peaks = load_peaks()
     w = WORKLOADS[args.workload]
-    warmup = max(3, args.warmup)
+    warmup = max(3, args.warmup)           # the timing rules ask for >= 3; a smaller request is raised and reported
     steps = max(1, args.steps)
     sampler = ClockSampler(local_rank)
 
@@ -564,7 +742,7 @@ def ours(args):
     ms_per_step = ms_max / steps
     value = w["batch"] * world * steps / (ms_max * 1e-3)
     roof = roofline(w, ms / steps, peaks)
-    roof["traffic"] = load_traffic(args.workload)
+    roof["traffic"], roof["traffic_source"] = load_traffic(args.workload)
     clocks = sampler.summary()
 
     # ---- end to end through the host-buffer C-ABI entry (`e2e`) ----------------------------------
@@ -576,8 +754,8 @@ def ours(args):
         hc.check()
         e2e = {"value": hc.batch * world * e_steps / el, "unit": "matrices/s", "h2d_bytes_per_step": int(hc.h2d),
                "d2h_bytes_per_step": int(hc.d2h), "steps": e_steps, "batch_per_gpu": hc.batch,
-               "api": hc.api + " (pinned host buffers, 3-slot H2D/kernel/D2H pipeline, wall clock around the calls)",
-               "roofline": pcie_roofline(hc.h2d, hc.d2h, el / e_steps)}
+               "api": hc.api + " (pinned host buffers, 3-slot H2D/kernel/D2H pipeline, wall clock around the calls; one process and one context per GPU)",
+               "roofline": pcie_roofline(hc.h2d * world, hc.d2h * world, el / e_steps, world)}
         hc.free()
     ring.free()
 
@@ -614,13 +792,33 @@ def ours(args):
             except Exception as e:  # report, never hide
                 others[name] = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- CPU baseline beside it (rank 0, N == 1 only) ------------------------------------------------
+    # ---- a chain of device-resident operations: where the device-side speed goes once PCIe is paid once ----------
+    chain = None
+    if rank == 0 and not args.no_e2e and not args.no_chain:
+        try:
+            chain = chain_e2e(ctx, tb, with_cpu=not args.no_cpu)
+        except Exception as e:  # report, never hide
+            chain = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- CPU baseline beside it (rank 0; the other ranks wait on the host, their GPUs idle) --------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         cw = CpuWork(w)
-        v, reps, el = cw.run_for(10.0)
+        v, reps, el = cw.run_for(10.0 if world == 1 else 4.0)
         cpu = {"value": v, "unit": "matrices/s", "cores": cw.threads, "kind": "port",
                "sample": f"{reps} passes over {cw.B} items of the same workload ({el:.1f} s), C++ oracle port of the reference semantics"}
+
+    # ---- one process driving all N devices (strong scaling, NCCL dot-sum): rank 0 alone, after every rank has
+    # released its own context; the others wait in a HOST barrier so that no GPU runs a spinning collective
+    ctx.close()
+    D.barrier_cpu()
+    single = None
+    if rank == 0 and not args.no_single:
+        try:
+            single = single_process_section(tb, world, peaks, with_e2e=not args.no_e2e)
+        except Exception as e:
+            single = {"error": f"{type(e).__name__}: {e}"}
+    D.barrier_cpu()
 
     if rank == 0:
         line = {"metric": "batched matrices/sec", "value": value, "unit": "matrices/s", "n_gpus": world,
@@ -629,12 +827,13 @@ def ours(args):
                 "config": {"workload": w["desc"], "batch_per_gpu": w["batch"], "layout": "AoS (reference wire order)",
                            "l2": "%d operand set(s) x %.2f GB used round-robin: every launch streams from HBM (>> 126 MB L2), no flush"
                                  % (len(ring.sets), w["bytes"] * w["batch"] / 1e9),
-                           "parallelism": f"batch-sharded x{world}, no collective on the data path"},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                           "parallelism": f"batch-sharded x{world}, no collective on the data path",
+                           "warmup_requested": args.warmup},
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "chain": chain, "single_process": single}
         if others:
             line["workloads"] = others
         emit(line)
-    ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -654,6 +853,8 @@ def main():
     ap.add_argument("--no-big", dest="big", action="store_false")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="skip the chained device-resident e2e workload")
+    ap.add_argument("--no-single", action="store_true", help="skip the one-process-N-devices section (strong scaling, NCCL dot-sum)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: libraries that print banners on fd 1 (NCCL's
     # "NCCL version ..." under torchrun) are sent to stderr for the duration of the run

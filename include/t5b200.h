@@ -260,6 +260,9 @@ int t5_solve_host(t5_ctx* ctx, int dtype, int n, int nrhs, size_t batch, const v
  * t5_timer_end synchronises and returns the MAX over devices in milliseconds. */
 int t5_timer_begin(t5_ctx* ctx);
 int t5_timer_end(t5_ctx* ctx, float* ms_max);
+/* After t5_timer_end: the elapsed time of each device's own stream (ms[g], g < min(cap, ndev)) -
+ * the per-device view of a sharded call (strong scaling: every device should take 1/ndev). */
+int t5_timer_per_device(t5_ctx* ctx, float* ms, int cap);
 /* Overwrite a > L2-sized scratch buffer on every device (L2 flush between timed
  * iterations of small workloads). */
 int t5_flush_l2(t5_ctx* ctx);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "t5_solve_host": (_i, [_vp, _i, _i, _i, _sz, _vp, _vp, _vp, _vp]),
     "t5_timer_begin": (_i, [_vp]),
     "t5_timer_end": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "t5_timer_per_device": (_i, [_vp, ctypes.POINTER(ctypes.c_float), _i]),
     "t5_flush_l2": (_i, [_vp]),
     "t5_fill_synthetic": (_i, [_vp, _u64, _u64]),
     "t5_plant_specials": (_i, [_vp, _i, _u64, _u64]),

@@ -1302,6 +1302,17 @@ int t5_timer_end(t5_ctx* c, float* ms_max) {
     return T5_OK;
 }
 
+int t5_timer_per_device(t5_ctx* c, float* ms, int cap) {
+    if (!c || !ms || cap < 0) return T5_ERR_INVALID;
+    LOCKED(c);
+    for (int g = 0; g < c->ndev && g < cap; ++g) {
+        CU(c, cudaSetDevice(c->dev[g]));
+        CU(c, cudaEventSynchronize(c->ev1[g]));
+        CU(c, cudaEventElapsedTime(&ms[g], c->ev0[g], c->ev1[g]));
+    }
+    return T5_OK;
+}
+
 int t5_flush_l2(t5_ctx* c) {
     if (!c) return T5_ERR_INVALID;
     LOCKED(c);

@@ -96,6 +96,16 @@ class Context:
         check(_lib.lib().t5_timer_end(self._h, ctypes.byref(ms)), self)
         return float(ms.value)
 
+    def timer_per_device(self):
+        """After timer_end(): milliseconds each device's stream took (one entry per device)."""
+        n = self.ndev
+        ms = (ctypes.c_float * n)()
+        check(_lib.lib().t5_timer_per_device(self._h, ms, n), self)
+        return [float(x) for x in ms]
+
+    def live_buffers(self) -> int:
+        return int(_lib.lib().t5_live_buffers(self._h))
+
     def flush_l2(self):
         check(_lib.lib().t5_flush_l2(self._h), self)
 

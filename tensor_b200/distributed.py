@@ -21,9 +21,13 @@ def env_world() -> Tuple[int, int, int]:
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
+_CPU_GROUP = None
+
+
 def init_process_group(backend: str | None = None):
     import torch
     import torch.distributed as dist
+    global _CPU_GROUP
     rank, local_rank, world = env_world()
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -33,9 +37,19 @@ def init_process_group(backend: str | None = None):
             torch.cuda.set_device(local_rank)
             dist.init_process_group(backend=backend, rank=rank, world_size=world,
                                     device_id=torch.device("cuda", local_rank))
+            # a second, host-side group: a rank that waits in an NCCL barrier spins a kernel on its GPU, which
+            # would disturb a rank that is timing work on ALL devices (bench.py's single-process section)
+            _CPU_GROUP = dist.new_group(backend="gloo")
         else:
             dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local_rank, world
+
+
+def barrier_cpu():
+    """Barrier that keeps every GPU idle while ranks wait (gloo over TCP on the host)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=_CPU_GROUP) if _CPU_GROUP is not None else dist.barrier()
 
 
 def strong_shard(batch: int, world: int, rank: int) -> Tuple[int, int]:

@@ -132,6 +132,8 @@ foreign import ccall safe "t5_solve_host"
 
 foreign import ccall safe "t5_timer_begin" c_timer_begin :: Ptr Ctx -> IO CInt
 foreign import ccall safe "t5_timer_end"   c_timer_end   :: Ptr Ctx -> Ptr CFloat -> IO CInt
+foreign import ccall safe "t5_timer_per_device"
+  c_timer_per_device :: Ptr Ctx -> Ptr CFloat -> CInt -> IO CInt
 foreign import ccall safe "t5_flush_l2"    c_flush_l2    :: Ptr Ctx -> IO CInt
 foreign import ccall safe "t5_fill_synthetic" c_fill_synthetic :: Ptr Buf -> Word64 -> Word64 -> IO CInt
 foreign import ccall safe "t5_plant_specials" c_plant_specials :: Ptr Buf -> CInt -> Word64 -> Word64 -> IO CInt

@@ -103,7 +103,7 @@ def test_haskell_ffi_module_binds_every_declared_symbol():
             if fn.endswith(".hs") and fn != "FFI.hs":
                 with open(os.path.join(dirpath, fn)) as f:
                     used += f.read()
-    helpers = {"t5_timer_begin", "t5_timer_end", "t5_flush_l2", "t5_fill_synthetic", "t5_plant_specials",
+    helpers = {"t5_timer_begin", "t5_timer_end", "t5_timer_per_device", "t5_flush_l2", "t5_fill_synthetic", "t5_plant_specials",
                "t5_launch_count", "t5_version", "t5_strerror", "t5_sync", "t5_free", "t5_partition", "t5_relayout",
                "t5_pinned_alloc", "t5_pinned_free", "t5_buf_batch", "t5_buf_elems", "t5_buf_dtype", "t5_buf_layout",
                "t5_dot_sum_used_nccl", "t5_structural_table"}

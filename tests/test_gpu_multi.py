@@ -100,3 +100,66 @@ def test_host_entry_multi_device(mctx):
     out = np.empty(batch * 16, dtype=np.float32)
     tb.matmul_host(mctx, a, b, 4, 4, 4, out)
     assert np.array_equal(bits(out), bits(oracle.matmul(a, b, 4, 4, 4, threads=8).ravel()))
+
+
+def test_host_entries_one_thread_per_device(mctx):
+    """Host-array entries on a multi-device context: one host thread per device inside the call, every device's
+    slots drained before it returns; the rank-3 transpose also reaches the shared index-table cache from them."""
+    from tensor_b200 import host
+    batch = 300_001
+    a3 = oracle.fill(oracle.F64, oracle.SEED_A, 51, batch * 24)
+    assert np.array_equal(bits(host.transpose(mctx, a3, (2, 3, 4))), bits(oracle.transpose(a3, [2, 3, 4], threads=8)))
+    n = 4
+    a = oracle.fill(oracle.F64, oracle.SEED_A, 52, batch * n * n).reshape(batch, n, n).copy()
+    oracle.plant_specials(a, n, 0, swap_every=16, sing_every=128)
+    b = oracle.fill(oracle.F64, oracle.SEED_B, 52, batch * n)
+    x, s = host.solve(mctx, a, b, n)
+    ox, os_ = oracle.solve(a, b, n, 1, threads=8)
+    assert np.array_equal(s, os_) and np.array_equal(bits(x), bits(ox))
+    inv, s = host.inverse(mctx, a, n)
+    oinv, os_ = oracle.inverse(a, n, threads=8)
+    assert np.array_equal(s, os_) and np.array_equal(bits(inv), bits(oinv))
+
+
+def test_per_device_timer_and_partition(mctx):
+    batch = 1 << 20
+    A = mctx.synthetic((4, 4), np.float32, batch, oracle.SEED_A, 1)
+    B = mctx.synthetic((4, 4), np.float32, batch, oracle.SEED_B, 1)
+    mctx.sync()
+    mctx.timer_begin()
+    C = tb.matmul(A, B)
+    ms = mctx.timer_end()
+    per = mctx.timer_per_device()
+    assert len(per) == mctx.ndev and max(per) == pytest.approx(ms, rel=1e-6) and min(per) > 0
+    shares = [tb.partition(batch, mctx.ndev, g)[1] for g in range(mctx.ndev)]
+    assert sum(shares) == batch and max(shares) - min(shares) <= 256 * mctx.ndev
+    a, b = A.to_numpy().ravel(), B.to_numpy().ravel()
+    assert np.array_equal(bits(C.to_numpy()), bits(oracle.matmul(a, b, 4, 4, 4, threads=8)))
+
+
+def test_soa_dot_sum_and_detour_multi_device(mctx):
+    batch = 100_003                                                   # ragged: every device has row padding
+    x = oracle.fill(oracle.I64, oracle.SEED_A, 53, batch * 4)
+    y = oracle.fill(oracle.I64, oracle.SEED_B, 53, batch * 4)
+    assert tb.dot_sum(mctx.from_numpy(x, (4,), tb.SOA), mctx.from_numpy(y, (4,), tb.SOA)) == oracle.dot_sum(x, y, 4)
+    m = 32
+    a = oracle.fill(oracle.F64, oracle.SEED_A, 54, 999 * m * m)
+    b = oracle.fill(oracle.F64, oracle.SEED_B, 54, 999 * m * m)
+    got = tb.matmul(mctx.from_numpy(a, (m, m), tb.SOA), mctx.from_numpy(b, (m, m), tb.SOA))
+    assert np.array_equal(bits(got.to_numpy()), bits(oracle.matmul(a, b, m, m, m, threads=8)))
+
+
+def test_multi_device_buffers_may_outlive_shutdown():
+    import ctypes
+    n = ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.t5_init(None, 0, ctypes.byref(h)) == _lib.OK
+    b = ctypes.c_void_p()
+    assert L.t5_alloc(h, _lib.F32, 16, 1 << 20, _lib.AOS, ctypes.byref(b)) == _lib.OK
+    assert L.t5_fill_synthetic(b, 1, 1) == _lib.OK
+    assert L.t5_shutdown(h) == _lib.OK
+    assert L.t5_fill_synthetic(b, 1, 1) == _lib.ERR_INVALID
+    assert L.t5_free(b) == _lib.OK

@@ -222,8 +222,10 @@ def test_row_echelon_errors(ctx):
         tb.row_echelon_form(ctx.empty((9, 4), np.float64, 4))                    # rows <= 8
     with pytest.raises(tb.Unsupported):
         tb.row_echelon_form(ctx.empty((4, 17), np.float64, 4))                   # cols <= 16
-    with pytest.raises(tb.Unsupported):
-        tb.row_echelon_form(ctx.empty((5, 3), np.float64, 4, tb.SOA))            # SoA: the register-resident shapes only
+    a = oracle.fill(oracle.F64, oracle.SEED_A, 77, 4 * 15)
+    got, rank = tb.row_echelon_form(ctx.from_numpy(a, (5, 3), tb.SOA))          # SoA beyond the register-resident shapes:
+    want, wrank = oracle.row_echelon(a, 5, 3, 3)                                 # served through the AoS kernel (relayout detour)
+    assert got.layout == tb.SOA and np.array_equal(bits(got.to_numpy()), bits(want)) and np.array_equal(rank.to_numpy(), wrank)
     with pytest.raises(tb.WrongListLength):
         tb.row_echelon_form(ctx.empty((3, 3), np.float64, 4), 4)                 # more pivot columns than columns
     with pytest.raises(tb.WrongListLength):
