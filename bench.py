@@ -39,6 +39,18 @@ WORKLOADS = {
                               desc="64Mi pairs of 3x3 Double matrices, .*. (launch-amortised size, SURVEY H6)"),
     "inverse4_f64_64M": dict(op="inverse", dtype="f64", n=4, batch=1 << 26, bytes=257, bound="hbm",
                              desc="64Mi 4x4 Double inverse (configs[2] at a launch-amortised size, SURVEY H6)"),
+    "det16_f64_512K": dict(op="det", dtype="f64", n=16, batch=1 << 19, bytes=2056, bound="hbm",
+                           desc="512Ki 16x16 Double det (CTA per matrix, 2D-cyclic register tiles)"),
+    "inverse16_f64_512K": dict(op="inverse", dtype="f64", n=16, batch=1 << 19, bytes=4097, bound="hbm",
+                               desc="512Ki 16x16 Double inverse (CTA per matrix, 2D-cyclic register tiles)"),
+    "det32_f64_128K": dict(op="det", dtype="f64", n=32, batch=1 << 17, bytes=8200, bound="hbm",
+                           desc="128Ki 32x32 Double det (CTA per matrix, 2D-cyclic register tiles)"),
+    "inverse32_f64_128K": dict(op="inverse", dtype="f64", n=32, batch=1 << 17, bytes=16385, bound="hbm",
+                               desc="128Ki 32x32 Double inverse (CTA per matrix, 2D-cyclic register tiles)"),
+    "det128_f64_8K": dict(op="det", dtype="f64", n=128, batch=1 << 13, bytes=131080, bound="hbm",
+                          desc="8Ki 128x128 Double det (CTA per matrix, 2D-cyclic register tiles)"),
+    "inverse128_f64_8K": dict(op="inverse", dtype="f64", n=128, batch=1 << 13, bytes=262145, bound="hbm",
+                              desc="8Ki 128x128 Double inverse (CTA per matrix, 2D-cyclic register tiles)"),
     "transpose4x4_f32_16M": dict(op="transpose", dtype="f32", dims=(4, 4), batch=1 << 24, bytes=128, bound="hbm",
                                  desc="16Mi 4x4 Float transposes (configs[1])"),
     "matvec4_f32_16M": dict(op="matmul", dtype="f32", m=4, k=4, n=1, batch=1 << 24, bytes=96, bound="hbm",

@@ -145,7 +145,8 @@ static bool forward_eliminate(T* W, int n, int nrhs, int* swaps) {
 // singular -> exact +0.
 template <class T>
 static T det_item(const T* A, int n) {
-    T W[16 * 16];
+    std::vector<T> Wv((size_t)n * n);            // any n (the reference's shapes are unbounded unary naturals, MultiIndex.hs:46-48)
+    T* W = Wv.data();
     std::memcpy(W, A, sizeof(T) * n * n);
     int swaps;
     if (!forward_eliminate(W, n, 0, &swaps)) return T(0);
@@ -159,8 +160,9 @@ static T det_item(const T* A, int n) {
 // X[k,c] = (Y[k,c] - s) / U[k,k].   status 1 (and zero-filled X) when singular.
 template <class T>
 static uint8_t solve_item(const T* A, const T* B, T* X, int n, int nrhs) {
-    T W[16 * 32];
     const int w = n + nrhs;
+    std::vector<T> Wv((size_t)n * w);
+    T* W = Wv.data();
     for (int i = 0; i < n; ++i) {
         for (int j = 0; j < n; ++j) W[i * w + j] = A[i * n + j];
         for (int c = 0; c < nrhs; ++c) W[i * w + n + c] = B[i * nrhs + c];
@@ -184,7 +186,8 @@ static uint8_t solve_item(const T* A, const T* B, T* X, int n, int nrhs) {
 // structural zeros of I so that the GPU kernel can share one code path).
 template <class T>
 static uint8_t inverse_item(const T* A, T* X, int n) {
-    T I[16 * 16];
+    std::vector<T> Iv((size_t)n * n);
+    T* I = Iv.data();
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) I[i * n + j] = (i == j) ? T(1) : T(0);
     return solve_item(A, I, X, n, n);
@@ -461,7 +464,7 @@ int t5o_prod(int dtype, int rankA, const uint64_t* dimsA, int rankB, const uint6
 
 // ---- det / inverse / solve (a9-a11): Fractional element types only ---------
 int t5o_det(int dtype, int n, size_t batch, const void* A, void* OUT, int threads) {
-    if (n < 1 || n > 16) return 1;
+    if (n < 1 || n > 4096) return 1;
     if (dtype == 0) {
         const double* a = (const double*)A; double* o = (double*)OUT;
         par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) o[b] = det_item<double>(a + b * n * n, n); });
@@ -475,7 +478,7 @@ int t5o_det(int dtype, int n, size_t batch, const void* A, void* OUT, int thread
     return 2;
 }
 int t5o_inverse(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_t* status, int threads) {
-    if (n < 1 || n > 16) return 1;
+    if (n < 1 || n > 4096) return 1;
     if (dtype == 0) {
         const double* a = (const double*)A; double* o = (double*)OUT;
         par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = inverse_item<double>(a + b * n * n, o + b * n * n, n); });
@@ -489,7 +492,7 @@ int t5o_inverse(int dtype, int n, size_t batch, const void* A, void* OUT, uint8_
     return 2;
 }
 int t5o_solve(int dtype, int n, int nrhs, size_t batch, const void* A, const void* B, void* X, uint8_t* status, int threads) {
-    if (n < 1 || n > 16 || nrhs < 1 || nrhs > 16) return 1;
+    if (n < 1 || n > 4096 || nrhs < 1 || nrhs > 4096) return 1;
     if (dtype == 0) {
         const double* a = (const double*)A; const double* bb = (const double*)B; double* x = (double*)X;
         par_chunks(batch, threads, [=](size_t b0, size_t b1) { for (size_t b = b0; b < b1; ++b) status[b] = solve_item<double>(a + b * n * n, bb + b * n * nrhs, x + b * n * nrhs, n, nrhs); });

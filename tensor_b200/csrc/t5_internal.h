@@ -97,6 +97,12 @@ int rowlane_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int rowlane_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
 int rowlane_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
 
+// ---- t5_lu.cu: CTA-per-matrix elimination for 9 <= n <= 128, the matrix 2D-cyclic in the CTA's registers (AoS);
+// bit-identical to the oracle like every other elimination kernel
+int lu_det(const Shard& s, int dtype, int n, const void* A, void* O);
+int lu_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
+int lu_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
+
 // ---- t5_xgemm.cu: exact (oracle-order, bit-identical) register-tiled product for shapes without a
 // faster specialisation: large Float / Int64 matrices, Double shapes off the DMMA tile grid
 int exact_blocked_matmul(const Shard& s, int dtype, int P, int K, int Q, const void* A, const void* B, void* C);

@@ -1,0 +1,375 @@
+// Gaussian elimination for 9 <= n <= 128: ONE CTA PER MATRIX, the working matrix distributed over the CTA's
+// registers 2D-cyclically (SquareMatrix det / inverse, LinearSystem solve of SURVEY.md §8a a9-a11 for the sizes the
+// record-per-thread and row-per-lane kernels do not reach; the reference's shapes are unbounded unary naturals,
+// src/Data/MultiIndex.hs:46-48).
+//
+// Layout.  The CTA is a TG x TG grid of threads (TG = 8: n <= 32, TG = 16: n <= 128).  Thread (ty, tx) owns the
+// elements w[i][j] with i = ty (mod TG), j = tx (mod TG): an NB x NB register tile, NB = ceil(n / TG).  Cyclic,
+// not blocked: as the elimination front k advances every thread keeps about the same share of the trailing
+// matrix.  All register indices are compile-time (the run-time front only appears in predicates), so the
+// matrix never touches local memory.
+//
+// One elimination step k (two CTA barriers):
+// One elimination step k (ONE CTA barrier; row k and the raw column k were published by step k - 1):
+//   1. pivot = row[k]; exactly zero -> slow path: first row p > k with a non-zero entry in column k (atomicMin),
+//      swap rows k and p WHOLE (stored multipliers included), republish; none -> singular
+//   2. every thread divides for ITS rows: f(i) = column[i] / pivot for i > k (exact division through the pivot's
+//      hoisted reciprocal; solve / inverse also keep f(i) in the shared factor array, where the zero would go)
+//   3. every thread: w[i][j] = w[i][j] - f(i) * row[j] for its i > k, j > k  (2 NB shared loads per NB^2 updates)
+//   4. the owners of row k + 1 and of column k + 1 publish them (double-buffered by the parity of k)   -- barrier
+// (A first version let only the TG owners of column k divide, behind a second barrier: 15/16 of the CTA idled through
+// the FP64 division latency every step - 3.5x slower at n = 128.)
+// The tile index of the front, k / TG, is CTA-uniform: each of the three parts is a `switch` over it into code whose
+// register indices and loop bounds are compile-time constants (the first version selected tile rows with
+// run-time select chains: 57 % of its executed instructions were FSEL / ISETP / LOP3, ncu).  Register columns the
+// front has passed are dead - nothing reads them again - so they take part in the update unconditionally (garbage in,
+// garbage out, column by column) instead of costing a predicate per element.
+// Per element the operations and their order are the oracle's (oracle/t5_oracle.cpp forward_eliminate): updates
+// in ascending k, multiply-round-subtract-round (this TU is compiled with -fmad=false -prec-div=true), pivot =
+// FIRST non-zero, so det, the factors and everything derived from them are BIT-IDENTICAL to the oracle.
+//
+// det = (+-) fold_k (acc * pivot_k) from 1, singular -> +0.
+// solve / inverse: the factors (U above, the kept multipliers below the diagonal) are dumped to shared memory
+// once.  Because a swap moves whole rows - multipliers included - the interleaved swap / update sequence the
+// oracle applies to the right-hand sides equals: permute the rows of B by the composed permutation, then
+// y[i] -= f(i,k) * y[k] for k ascending with NO further swaps (the same values meet in the same order).  So the
+// right-hand sides are loaded already permuted (inverse: the permuted identity, integer bookkeeping), 2D-cyclic
+// like the matrix, and take one barrier per step (pivot row of Y published, f(i,k) read straight from the shared
+// factors).  Back-substitution is a sequential recurrence per column whose order the specification fixes
+// (s = fold_{j>k ascending}(s + u[k,j] x[j]) from 0, x[k] = (y[k] - s) / u[k,k]): Y goes to shared memory and
+// thread c runs column c, reading u[k,j] as a broadcast.  Singular: status 1, item zero-filled.
+#include <type_traits>
+
+#include "t5_device.cuh"
+#include "t5_internal.h"
+#include "t5_recip.cuh"
+
+namespace t5 {
+namespace lu {
+
+struct Args {
+    const void* A;
+    const void* B;          // n x nrhs per item (solve); unused for det / inverse
+    void* X;                // determinant / solution / inverse
+    unsigned char* status;  // unused for det
+    unsigned long long count;
+    int n, nrhs;
+    int ldl, ldy;           // row pitches (elements) of the shared factors and of the shared right-hand sides
+    int chunk;              // right-hand-side columns processed per pass (multiple of TG, <= TG * NB)
+};
+
+// CTA-uniform dispatch on a tile index: fn(std::integral_constant<int, A>) with A == a_rt
+template <int NB, int A = 0, class F>
+__device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
+    if constexpr (A < NB) {
+        if (a_rt == A) fn(std::integral_constant<int, A>{});
+        else with_tile_index<NB, A + 1>(a_rt, fn);
+    }
+}
+
+// MODE 0: det, 1: solve (rhs from B), 2: inverse (rhs = identity, nrhs == n)
+template <class T, int TG, int NB, int MODE>
+__global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
+    constexpr int THREADS = TG * TG;
+    constexpr int NMAX = TG * NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* prow = reinterpret_cast<T*>(smem_raw);          // [2][NMAX]   published pivot row (double-buffered)
+    T* fcol = prow + 2 * NMAX;                          // [2][NMAX]   published raw column of the step (the numerators of the multipliers)
+    T* xrow = fcol + 2 * NMAX;                          // [2][NMAX]   row exchange for swaps
+    int* perm = reinterpret_cast<int*>(xrow + 2 * NMAX);   // [NMAX] row i of the permuted system = row perm[i] of the input
+    int* ctl = perm + NMAX;                             // [4] pivot search result, swap count
+    T* LU = reinterpret_cast<T*>(ctl + 4);              // [n][ldl]  (MODE != 0): U on and above the diagonal, multipliers below
+    T* Y = LU + (MODE != 0 ? (size_t)p.n * p.ldl : 0);  // [n][ldy]  (MODE != 0)
+
+    const int tid = threadIdx.x, ty = tid / TG, tx = tid % TG;
+    const int n = p.n;
+    const T* gA = (const T*)p.A;
+    // number of this thread's tile rows / columns that lie inside the matrix
+    const int a_end = ty < n ? (n - ty + TG - 1) / TG : 0;
+
+    for (unsigned long long item = blockIdx.x; item < p.count; item += gridDim.x) {
+        // ---- load: thread (ty, tx) takes A[ty + TG a][tx + TG b]; TG consecutive threads read TG consecutive elements
+        T w[NB][NB];
+        const T* a_item = gA + item * (unsigned long long)n * n;
+        #pragma unroll
+        for (int a = 0; a < NB; ++a)
+            #pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int i = ty + TG * a, j = tx + TG * b;
+                w[a][b] = (i < n && j < n) ? __ldg(a_item + (size_t)i * n + j) : T(0);
+            }
+        if (tid < NMAX) perm[tid] = tid;
+        if (tid == 0) ctl[1] = 0;
+        T acc = T(1);                                   // thread 0: running product of the pivots
+        bool singular = false;
+        __syncthreads();
+
+        // ---- elimination of A: ONE barrier per step.  At the top of step k the pivot row and the raw column k (both as
+        // left by step k - 1) are already published.  Every thread divides for its own NB rows (f = column / pivot with
+        // the pivot's reciprocal hoisted, t5_recip.cuh: bit-identical to `/`) - redundantly across the TG threads of a
+        // thread-row, but in parallel, instead of TG owner threads dividing while the other 15/16 of the CTA wait at a
+        // second barrier - updates its tile, and the owners of row / column k + 1 publish them for the next step.
+        auto publish = [&](int k1) {                    // row k1 and column k1 of the CURRENT registers -> buffer k1 & 1
+            const int r1 = k1 % TG, a1 = k1 / TG;
+            T* pr1 = prow + (k1 & 1) * NMAX;
+            T* cr1 = fcol + (k1 & 1) * NMAX;
+            if (ty == r1)
+                with_tile_index<NB>(a1, [&](auto A_) {
+                    constexpr int A = decltype(A_)::value;
+                    #pragma unroll
+                    for (int b = A; b < NB; ++b) pr1[tx + TG * b] = w[A][b];      // (columns before the front are dead)
+                });
+            if (tx == r1)
+                with_tile_index<NB>(a1, [&](auto A_) {
+                    constexpr int A = decltype(A_)::value;
+                    #pragma unroll
+                    for (int a = A; a < NB; ++a) cr1[ty + TG * a] = w[a][A];
+                });
+        };
+        publish(0);
+        __syncthreads();
+        for (int k = 0; k < n; ++k) {
+            const int rk = k % TG, ak = k / TG;         // owner thread-row (= thread-column) and tile index of row / column k
+            const T* pr = prow + (k & 1) * NMAX;
+            const T* cr = fcol + (k & 1) * NMAX;
+            T piv = pr[k];
+            if (piv == T(0)) {
+                // slow path (rare: planted zeros, exactly singular items): first row p > k with a non-zero in column k
+                if (tid == 0) ctl[0] = n;
+                __syncthreads();
+                for (int i = k + 1 + tid; i < n; i += THREADS)
+                    if (cr[i] != T(0)) atomicMin(&ctl[0], i);
+                __syncthreads();
+                const int pidx = ctl[0];
+                if (pidx >= n) { singular = true; break; }           // uniform: every thread reads the same word
+                const int rp = pidx % TG, ap = pidx / TG;
+                // exchange rows k and pidx: the live part in registers, the kept multipliers (columns < k) in the shared factors
+                if (ty == rk)
+                    with_tile_index<NB>(ak, [&](auto A_) {
+                        constexpr int A = decltype(A_)::value;
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) xrow[tx + TG * b] = w[A][b];
+                    });
+                if (ty == rp)
+                    with_tile_index<NB>(ap, [&](auto A_) {
+                        constexpr int A = decltype(A_)::value;
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) xrow[NMAX + tx + TG * b] = w[A][b];
+                    });
+                __syncthreads();
+                if (ty == rk)
+                    with_tile_index<NB>(ak, [&](auto A_) {
+                        constexpr int A = decltype(A_)::value;
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) w[A][b] = xrow[NMAX + tx + TG * b];
+                    });
+                if (ty == rp)                                         // (k != pidx: when one thread owns both rows they are different tile rows)
+                    with_tile_index<NB>(ap, [&](auto A_) {
+                        constexpr int A = decltype(A_)::value;
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) w[A][b] = xrow[tx + TG * b];
+                    });
+                if (MODE != 0)
+                    for (int j = tid; j < k; j += THREADS) {
+                        const T t = LU[(size_t)k * p.ldl + j];
+                        LU[(size_t)k * p.ldl + j] = LU[(size_t)pidx * p.ldl + j];
+                        LU[(size_t)pidx * p.ldl + j] = t;
+                    }
+                if (tid == 0) { const int t = perm[k]; perm[k] = perm[pidx]; perm[pidx] = t; ctl[1] += 1; }
+                publish(k);                                           // (same buffer: every thread is inside this branch)
+                __syncthreads();
+                piv = pr[k];
+            }
+            if (tid == 0) acc = acc * piv;
+            const Recip<T> rc(piv);
+            with_tile_index<NB>(ak, [&](auto A_) {
+                constexpr int A = decltype(A_)::value;
+                T prj[NB];
+                #pragma unroll
+                for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
+                #pragma unroll
+                for (int a = A; a < NB; ++a) {
+                    // rows of tile row A are past the front only for ty > rk; later tile rows are, whole; rows >= n do not exist
+                    if ((a > A || ty > rk) && a < a_end) {
+                        const T f = rc.div(cr[ty + TG * a]);
+                        if (MODE != 0 && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f;   // the multiplier goes where the zero would go
+                        #pragma unroll
+                        for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f * prj[b];
+                    }
+                }
+            });
+            if (k + 1 < n) publish(k + 1);
+            __syncthreads();
+        }
+
+        if (MODE == 0) {
+            if (tid == 0) {
+                T d = singular ? T(0) : ((ctl[1] & 1) ? -acc : acc);
+                ((T*)p.X)[item] = d;
+            }
+            __syncthreads();                            // perm / ctl are rewritten by the next item
+            continue;
+        }
+
+        // ---- solve / inverse
+        const int nrhs = p.nrhs;
+        T* gX = (T*)p.X + item * (unsigned long long)n * nrhs;
+        if (tid == 0) p.status[item] = singular ? 1 : 0;
+        if (singular) {
+            for (int e = tid; e < n * nrhs; e += THREADS) gX[e] = T(0);
+            __syncthreads();
+            continue;
+        }
+        // U (row i, columns j >= i) is final in the registers of its owners
+        #pragma unroll
+        for (int a = 0; a < NB; ++a)
+            #pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int i = ty + TG * a, j = tx + TG * b;
+                if (i < n && j < n && j >= i) LU[(size_t)i * p.ldl + j] = w[a][b];
+            }
+        __syncthreads();
+        const T* gB = MODE == 1 ? (const T*)p.B + item * (unsigned long long)n * nrhs : nullptr;
+        for (int c0 = 0; c0 < nrhs; c0 += p.chunk) {
+            // right-hand sides of this pass, rows already permuted; same cyclic distribution (NB x NB tile, columns c0 + tx + TG b)
+            T y[NB][NB];
+            #pragma unroll
+            for (int a = 0; a < NB; ++a)
+                #pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const int i = ty + TG * a, c = c0 + tx + TG * b;
+                    T v = T(0);
+                    if (i < n && c < nrhs && TG * b < p.chunk) {
+                        const int src = perm[i];
+                        v = MODE == 2 ? (src == c ? T(1) : T(0)) : __ldg(gB + (size_t)src * nrhs + c);
+                    }
+                    y[a][b] = v;
+                }
+            for (int k = 0; k < n; ++k) {
+                const int rk = k % TG, ak = k / TG;
+                T* pr = prow + (k & 1) * NMAX;
+                if (ty == rk)
+                    with_tile_index<NB>(ak, [&](auto A_) {
+                    constexpr int A = decltype(A_)::value;
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) pr[tx + TG * b] = y[A][b];
+                    });
+                __syncthreads();
+                with_tile_index<NB>(ak, [&](auto A_) {
+                    constexpr int A = decltype(A_)::value;
+                    T prj[NB];
+                    #pragma unroll
+                    for (int b = 0; b < NB; ++b) prj[b] = pr[tx + TG * b];
+                    #pragma unroll
+                    for (int a = A; a < NB; ++a) {
+                        if ((a > A || ty > rk) && a < a_end) {
+                            const T f = LU[(size_t)(ty + TG * a) * p.ldl + k];
+                            #pragma unroll
+                            for (int b = 0; b < NB; ++b) y[a][b] = y[a][b] - f * prj[b];
+                        }
+                    }
+                });
+            }
+            #pragma unroll
+            for (int a = 0; a < NB; ++a)
+                #pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const int i = ty + TG * a, cc = tx + TG * b;
+                    if (i < n && cc < p.chunk) Y[(size_t)i * p.ldy + cc] = y[a][b];
+                }
+            __syncthreads();
+            // back-substitution: thread cc owns column c0 + cc; u[k][j] is a broadcast read
+            for (int cc = tid; cc < p.chunk && c0 + cc < nrhs; cc += THREADS) {
+                for (int k = n - 1; k >= 0; --k) {
+                    T s = T(0);
+                    const T* urow = LU + (size_t)k * p.ldl;
+                    for (int j = k + 1; j < n; ++j) s = s + urow[j] * Y[(size_t)j * p.ldy + cc];
+                    Y[(size_t)k * p.ldy + cc] = (Y[(size_t)k * p.ldy + cc] - s) / urow[k];
+                }
+            }
+            __syncthreads();
+            const int width = (nrhs - c0) < p.chunk ? (nrhs - c0) : p.chunk;
+            for (int e = tid; e < n * width; e += THREADS) {
+                const int i = e / width, cc = e - i * width;
+                gX[(size_t)i * nrhs + c0 + cc] = Y[(size_t)i * p.ldy + cc];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+        else n = T5_SM_COUNT_FALLBACK;
+    }
+    return n;
+}
+
+template <class T, int TG, int NB, int MODE>
+static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
+    constexpr int NMAX = TG * NB;
+    Args p;
+    p.A = A; p.B = B; p.X = X; p.status = (unsigned char*)status; p.count = s.count; p.n = n; p.nrhs = nrhs;
+    p.ldl = n | 1;                                           // odd pitch: rows a thread-row apart land in different banks
+    size_t smem = sizeof(T) * 6 * NMAX + sizeof(int) * (NMAX + 4);
+    p.chunk = TG; p.ldy = 1;
+    if (MODE != 0) {
+        // as many right-hand-side columns per pass as the tile holds and shared memory allows (the factors stay resident)
+        const size_t budget = 200 * 1024;
+        int chunk = ((nrhs + TG - 1) / TG) * TG;
+        if (chunk > NMAX) chunk = NMAX;
+        while (chunk > TG && smem + sizeof(T) * ((size_t)n * p.ldl + (size_t)n * (chunk | 1)) > budget) chunk -= TG;
+        p.chunk = chunk;
+        p.ldy = chunk | 1;
+        smem += sizeof(T) * ((size_t)n * p.ldl + (size_t)n * p.ldy);
+        if (smem > 227 * 1024) return T5I_UNSUPPORTED;
+    }
+    auto kern = lu_kernel<T, TG, NB, MODE>;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return T5I_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TG * TG, smem) != cudaSuccess || per_sm < 1) return T5I_CUDA;
+    const unsigned long long slots = (unsigned long long)per_sm * sm_count();
+    const int grid = (int)(s.count < slots ? s.count : slots);
+    kern<<<grid, TG * TG, smem, s.stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
+}
+
+template <class T, int MODE>
+static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
+    if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
+    if (n < 9 || n > 128) return T5I_NOT_SPECIALISED;
+    if (s.count == 0) return T5I_OK;
+    if (n <= 16) return launch<T, 8, 2, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 24) return launch<T, 8, 3, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 32) return launch<T, 8, 4, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 48) return launch<T, 16, 3, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 64) return launch<T, 16, 4, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 80) return launch<T, 16, 5, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 96) return launch<T, 16, 6, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 112) return launch<T, 16, 7, MODE>(s, n, nrhs, A, B, X, status);
+    return launch<T, 16, 8, MODE>(s, n, nrhs, A, B, X, status);
+}
+
+}  // namespace lu
+
+int lu_det(const Shard& s, int dtype, int n, const void* A, void* O) {
+    if (dtype == T5D_F64) return lu::dispatch<double, 0>(s, n, 0, A, nullptr, O, nullptr);
+    if (dtype == T5D_F32) return lu::dispatch<float, 0>(s, n, 0, A, nullptr, O, nullptr);
+    return T5I_NOT_SPECIALISED;
+}
+int lu_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status) {
+    if (dtype == T5D_F64) return lu::dispatch<double, 2>(s, n, n, A, nullptr, O, status);
+    if (dtype == T5D_F32) return lu::dispatch<float, 2>(s, n, n, A, nullptr, O, status);
+    return T5I_NOT_SPECIALISED;
+}
+int lu_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
+    if (nrhs < 1) return T5I_NOT_SPECIALISED;
+    if (dtype == T5D_F64) return lu::dispatch<double, 1>(s, n, nrhs, A, B, X, status);
+    if (dtype == T5D_F32) return lu::dispatch<float, 1>(s, n, nrhs, A, B, X, status);
+    return T5I_NOT_SPECIALISED;
+}
+
+}  // namespace t5

@@ -4,6 +4,7 @@
 // compiled with -fmad=false (multiply-round-add-round, bit-identical to the oracle).
 #pragma once
 #include "t5_tile.cuh"
+#include "t5_recip.cuh"
 
 namespace t5 {
 
@@ -36,54 +37,6 @@ struct TransposeOp {
         for (int i = 0; i < R_; ++i)
             #pragma unroll
             for (int j = 0; j < C_; ++j) o[j * R_ + i] = a[i * C_ + j];
-    }
-};
-
-// ---- exact division with a shared reciprocal ---------------------------------------------
-// Elimination divides many numerators by the same pivot (n-1-k multipliers going down, one
-// quotient per right-hand side coming back up).  IEEE division is correctly rounded, so any
-// algorithm that is correctly rounded is bit-identical to the oracle's `/`; the one used here
-// is the sequence the compiler itself emits for `n / d` (cuobjdump of a plain double
-// division, sm_100a): r0 = {MUFU.RCP64H(hi(d)), lo = 1}; two Newton steps in DFMA give r;
-// q0 = n*r; rem = fma(-d, q0, n); q = fma(r, rem, q0); the result stands when
-// |float(hi(n))| >= 2^-73ish (0x03600000) and 0*float(hi(d)) + float(hi(q)) is a normal
-// non-NaN float, else the compiler's full division runs.  Only the d-dependent half (the
-// MUFU and five DFMAs) is hoisted and shared; every step and the validity test are kept, so
-// the quotient equals the compiler's `/` bit for bit in all cases (tested against the
-// oracle incl. denormal, huge, zero, Inf and NaN operands).
-template <class T>
-struct Recip {  // element types without a hoistable reciprocal: the plain IEEE division
-    T d;
-    __device__ __forceinline__ Recip() : d(T(1)) {}
-    __device__ __forceinline__ explicit Recip(T d_) : d(d_) {}
-    __device__ __forceinline__ T div(T n) const { return n / d; }
-};
-
-static __device__ __noinline__ double full_ddiv(double n, double d) { return n / d; }   // out of line (cold)
-
-template <>
-struct Recip<double> {
-    double d, r;
-    __device__ __forceinline__ Recip() : d(1.0), r(1.0) {}
-    __device__ __forceinline__ explicit Recip(double d_) : d(d_) {
-        double g;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(g) : "d"(d_));       // MUFU.RCP64H
-        const double r0 = __hiloint2double(__double2hiint(g), 1);
-        double e = __fma_rn(-d_, r0, 1.0);
-        e = __fma_rn(e, e, e);
-        const double r1 = __fma_rn(r0, e, r0);
-        const double e2 = __fma_rn(-d_, r1, 1.0);
-        r = __fma_rn(r1, e2, r1);
-    }
-    __device__ __forceinline__ double div(double n) const {
-        const double q0 = __dmul_rn(n, r);
-        const double rem = __fma_rn(-d, q0, n);
-        double q = __fma_rn(r, rem, q0);
-        const float t = __fmaf_rn(0.0f, __int_as_float(__double2hiint(d)), __int_as_float(__double2hiint(q)));
-        const bool fast = (fabsf(t) > __int_as_float(0x00100000)) &&
-                          (fabsf(__int_as_float(__double2hiint(n))) >= __int_as_float(0x03600000));
-        if (!fast) q = full_ddiv(n, d);
-        return q;
     }
 };
 

@@ -113,7 +113,10 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     auto tfull_bar = [&](unsigned a) { return bar0 + 8 * (3 * STAGES + a); };
     auto tempty_bar = [&](unsigned a) { return bar0 + 8 * (3 * STAGES + 2 + a); };
 
-    const int tiles_m = p.M / BM, tiles_n = p.N / BN, kch = p.K / BK;
+    // ragged shapes: the tensor maps carry the item as their own (outermost) dimension, so the part of a box that lies
+    // beyond an item's M rows, N columns or K depth is out of bounds for TMA and arrives as ZEROS (never the next item's
+    // data); zero rows / columns / k-slices add nothing, and the epilogue stores only what exists
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN, kch = (p.K + BK - 1) / BK;
     const unsigned long long tiles_per_item = (unsigned long long)tiles_m * tiles_n;
     const unsigned long long n_tiles = p.count * tiles_per_item;
 
@@ -148,14 +151,12 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 const unsigned long long item = tile / tiles_per_item;
                 const int rem = (int)(tile - item * tiles_per_item);
                 const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
-                const int a_row = (int)(item * p.M) + tm * BM;
-                const int b_row = (int)(item * p.K);
                 for (int kc = 0; kc < kch; ++kc, ++it) {
                     const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), TILE_A + TILE_B);
-                    tma_load_2d(ring + s * STAGE, &mapA, full_bar(s), kc * BK, a_row);
-                    tma_load_3d(ring + s * STAGE + TILE_A, &mapB, full_bar(s), 0, b_row + kc * BK, tn * (BN / 32));
+                    mbar_expect_tx(full_bar(s), TILE_A + TILE_B);                 // out-of-bounds parts are zero-filled and counted
+                    tma_load_3d(ring + s * STAGE, &mapA, full_bar(s), kc * BK, tm * BM, (int)item);
+                    tma_load_4d(ring + s * STAGE + TILE_A, &mapB, full_bar(s), 0, kc * BK, tn * (BN / 32), (int)item);
                 }
             }
         }
@@ -231,11 +232,13 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             tc_fence_after();
             float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * RPW) * p.N + tn * BN;   // this warp's rows
             float* crow = cblk + (size_t)lane * p.N;
+            const int rows_here = p.M - (tm * BM + q * RPW);                  // rows of this warp's block that exist (may be <= 0)
+            const int cols_here = p.N - tn * BN;                              // columns of the tile that exist (multiple of 32)
             if (*(volatile unsigned*)&special_tile[tl & 7] == tl + 1) {
                 // exact sequential fold for this thread's row (multiply, round, add, round; k ascending)
                 const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + q * RPW + lane) * p.K;
                 const float* bcol = p.B + item * (size_t)p.K * p.N + tn * BN;
-                for (int j = 0; j < BN && lane < RPW; ++j) {
+                for (int j = 0; j < BN && j < cols_here && lane < RPW && lane < rows_here; ++j) {
                     float acc_x = 0.0f;
                     for (int kk = 0; kk < p.K; ++kk) acc_x = __fadd_rn(acc_x, __fmul_rn(__ldg(arow + kk), __ldg(bcol + (size_t)kk * p.N + j)));
                     crow[j] = acc_x;
@@ -247,6 +250,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
             #pragma unroll
             for (int cc = 0; cc < BN / 32; ++cc) {
+                if (cc * 32 >= cols_here) break;                              // (warp-uniform)
                 unsigned r[32];
                 const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + cc * 32;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -272,7 +276,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     uint4 v;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                                  : "r"(stage_w + rr * EPI_PITCH + c4 * 16));
-                    st_global_stream16(cblk + (size_t)rr * p.N + cc * 32 + c4 * 4, v);
+                    if (rr < rows_here) st_global_stream16(cblk + (size_t)rr * p.N + cc * 32 + c4 * 4, v);
                 }
             }
             tc_fence_before();
@@ -293,41 +297,48 @@ static int launch(const Shard& s, int m, int k, int n, const float* A, const flo
     constexpr int BM = G::BM, BN = G::BN;
     TensorMapEncodeFn enc = tensor_map_encoder();
     if (!enc) return T5I_CUDA;
-    const size_t per = (size_t)0x7fffffff / (size_t)(m > k ? m : k);      // TMA coordinates are int32
-    for (size_t off = 0; off < s.count; off += per) {
-        const size_t cnt = s.count - off < per ? s.count - off : per;
-        CUtensorMap ma, mb;
-        {   // A: [cnt*m rows][k] floats, box 32 floats x 128 rows, K-major
-            const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)cnt * m};
-            const cuuint64_t strides[1] = {(cuuint64_t)k * 4};
-            const cuuint32_t box[2] = {BK, BM}, estr[2] = {1, 1};
-            if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A + off * (size_t)m * k), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
-        }
-        {   // B: [cnt*k rows][n] floats viewed as {32, rows, n/32}; box {32, 32 k-rows, 4 column blocks}
-            const cuuint64_t dims[3] = {32, (cuuint64_t)cnt * k, (cuuint64_t)(n / 32)};
-            const cuuint64_t strides[2] = {(cuuint64_t)n * 4, 128};
-            const cuuint32_t box[3] = {32, BK, BN / 32}, estr[3] = {1, 1, 1};
-            if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(B + off * (size_t)k * n), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
-        }
-        const unsigned long long tiles = (unsigned long long)cnt * (m / BM) * (n / BN);
-        const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
-        Args a{A + off * (size_t)m * k, B + off * (size_t)k * n, C + off * (size_t)m * n, m, n, k, (unsigned long long)cnt};
-        tf32x3_kernel<G><<<grid, THREADS, G::SMEM, s.stream>>>(ma, mb, a);
-        if (cudaGetLastError() != cudaSuccess) return T5I_CUDA;
+    if (s.count > 0x7fffffffull) return T5I_UNSUPPORTED;                  // TMA coordinates are int32
+    CUtensorMap ma, mb;
+    {   // A: {k, m, count} floats, box 32 floats x BM rows x 1 item, K-major.  Rows >= m / depth >= k: zero fill.
+        const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)m, (cuuint64_t)s.count};
+        const cuuint64_t strides[2] = {(cuuint64_t)k * 4, (cuuint64_t)m * k * 4};
+        const cuuint32_t box[3] = {BK, BM, 1}, estr[3] = {1, 1, 1};
+        if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
     }
-    return T5I_OK;
+    {   // B: [k rows][n] floats per item viewed as {32, k, n/32, count}; box {32, 32 k-rows, BN/32 column blocks, 1 item}
+        const cuuint64_t dims[4] = {32, (cuuint64_t)k, (cuuint64_t)(n / 32), (cuuint64_t)s.count};
+        const cuuint64_t strides[3] = {(cuuint64_t)n * 4, 128, (cuuint64_t)k * n * 4};
+        const cuuint32_t box[4] = {32, BK, BN / 32, 1}, estr[4] = {1, 1, 1, 1};
+        if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(B), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
+    }
+    const unsigned long long tiles = (unsigned long long)s.count * ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+    const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
+    Args a{A, B, C, m, n, k, (unsigned long long)s.count};
+    tf32x3_kernel<G><<<grid, THREADS, G::SMEM, s.stream>>>(ma, mb, a);
+    return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
 
 }  // namespace tf
 
+// padded tile area over useful area for a square tiling of edge T
+static inline double tf_waste(int m, int n, int T) {
+    return (double)((m + T - 1) / T * T) * (double)((n + T - 1) / T * T) / ((double)m * n);
+}
+
 int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    if (m % 64 || n % 64 || k % tf::BK || k < tf::BK) return T5I_NOT_SPECIALISED;
-    const bool big = m % 128 == 0 && n % 128 == 0;
+    // TMA: row pitches must be whole 16-byte units (k % 4), B is viewed in 32-column blocks (n % 32); m is free.
+    // Items of at least 48 x 64 x 32: smaller ones are served better by the exact kernels before this one in the chain.
+    if (n % 32 || k % 4 || k < tf::BK || m < 48 || n < 64) return T5I_NOT_SPECIALISED;
+    // the tensor pipe is ~1/3 busy on full tiles (the kernel is HBM-bound), so up to 2x padded tile area is affordable;
+    // between the two geometries the one with less padding wins, the larger tile on a tie (operands read once)
+    const double w128 = tf_waste(m, n, 128), w64 = tf_waste(m, n, 64);
+    if (w128 > 2.0 && w64 > 2.0) return T5I_NOT_SPECIALISED;
+    const bool big = w128 <= w64 * 1.3;
     static bool configured[T5_MAX_DEVICES] = {false};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;

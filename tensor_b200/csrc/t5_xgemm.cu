@@ -20,11 +20,87 @@
 #include "t5_device.cuh"
 #include "t5_internal.h"
 #include <mutex>
+#include <type_traits>
 
 namespace t5 {
 namespace xg {
 
 constexpr int BK = 16, THREADS = 64;
+
+// The thread's TM x TN accumulators and the one operation on them: acc[i][j] = acc[i][j] + a[i] * b[j], the multiply
+// rounded, then the add rounded (never fused).
+template <class T, int TM, int TN>
+struct Acc {
+    using R = Arith<T>;
+    T v[TM][TN];
+    __device__ __forceinline__ void zero() {
+        #pragma unroll
+        for (int i = 0; i < TM; ++i)
+            #pragma unroll
+            for (int j = 0; j < TN; ++j) v[i][j] = R::zero();
+    }
+    __device__ __forceinline__ void step(const T (&a)[TM], const T (&b)[TN], unsigned long long, unsigned long long) {
+        #pragma unroll
+        for (int i = 0; i < TM; ++i)
+            #pragma unroll
+            for (int j = 0; j < TN; ++j) v[i][j] = R::add(v[i][j], R::mul(a[i], b[j]));
+    }
+    __device__ __forceinline__ uint4 vec16(int i, int h) const {      // elements [i][h * VE .. h * VE + VE)
+        constexpr int VE = 16 / (int)sizeof(T);
+        uint4 r;
+        #pragma unroll
+        for (int e = 0; e < VE; ++e) reinterpret_cast<T*>(&r)[e] = v[i][h * VE + e];
+        return r;
+    }
+    __device__ __forceinline__ T get(int i, int j) const { return v[i][j]; }
+};
+
+// Float: Blackwell's packed FP32 pairs (SASS FFMA2: two FP32 lanes per register pair, one issue slot).  ptxas CONTRACTS
+// a mul.rn.f32x2 feeding an add.rn.f32x2 into one fused FFMA2 even under -fmad=false (seen in the SASS: a * b + acc with
+// a single rounding - not the oracle's arithmetic), so the two roundings are spelled as two packed FMAs that cannot be
+// merged:  t = fma(a, b, -0.0)  is the correctly rounded product (x + -0.0 = x for every x, signed zeros included),
+// acc = fma(t, 1.0, acc)  the correctly rounded sum.  With literal constants ptxas folds the pair back into ONE fused
+// FFMA2 (x * 1 -> x, y + -0 -> y, then the same contraction), so 1.0 and -0.0 arrive as kernel parameters whose values
+// it cannot know.  Bit-identical to FMUL + FADD (tested against the oracle, specials included), but one issue slot now
+// carries two multiplies (or two adds): the scalar version was ISSUE-bound (ncu: issue active 72 %, FMUL + FADD + LDS +
+// addressing sharing the slots, 0.43 of the FP32 lanes).
+template <int TM, int TN>
+struct Acc<float, TM, TN> {
+    static_assert(TN % 2 == 0, "pairs along the row");
+    unsigned long long v[TM][TN / 2];               // {acc[i][2j] (low half), acc[i][2j+1] (high half)}
+    __device__ __forceinline__ void zero() {
+        #pragma unroll
+        for (int i = 0; i < TM; ++i)
+            #pragma unroll
+            for (int j = 0; j < TN / 2; ++j) v[i][j] = 0ull;        // (+0.0f, +0.0f)
+    }
+    __device__ __forceinline__ void step(const float (&a)[TM], const float (&b)[TN], unsigned long long one2, unsigned long long negzero2) {
+        unsigned long long bp[TN / 2];
+        #pragma unroll
+        for (int j = 0; j < TN / 2; ++j)
+            asm("mov.b64 %0, {%1, %2};" : "=l"(bp[j]) : "r"(__float_as_uint(b[2 * j])), "r"(__float_as_uint(b[2 * j + 1])));
+        #pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            unsigned long long aa, t;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "r"(__float_as_uint(a[i])));
+            #pragma unroll
+            for (int j = 0; j < TN / 2; ++j) {
+                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(aa), "l"(bp[j]), "l"(negzero2));        // a * b, rounded
+                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v[i][j]) : "l"(t), "l"(one2), "l"(v[i][j]));   // + acc, rounded
+            }
+        }
+    }
+    __device__ __forceinline__ uint4 vec16(int i, int h) const {
+        uint4 r;
+        r.x = (unsigned)v[i][2 * h]; r.y = (unsigned)(v[i][2 * h] >> 32);
+        r.z = (unsigned)v[i][2 * h + 1]; r.w = (unsigned)(v[i][2 * h + 1] >> 32);
+        return r;
+    }
+    __device__ __forceinline__ float get(int i, int j) const {
+        const unsigned long long x = v[i][j / 2];
+        return __uint_as_float((j & 1) ? (unsigned)(x >> 32) : (unsigned)x);
+    }
+};
 
 struct Args {
     const void* A;
@@ -32,6 +108,7 @@ struct Args {
     void* C;
     int P, K, Q;
     unsigned long long count;
+    unsigned long long one2, negzero2;   // packed (1.0f, 1.0f) and (-0.0f, -0.0f): kernel PARAMETERS, so that ptxas cannot fold them (below)
 };
 
 template <class T, int TM, int TN>
@@ -49,7 +126,6 @@ struct Cfg {
 template <class T, int TM, int TN>
 __global__ void __launch_bounds__(THREADS, 6) xgemm_kernel(Args p) {
     using C = Cfg<T, TM, TN>;
-    using R = Arith<T>;
     constexpr int VE = C::VE, BM = C::BM, BN = C::BN, A_LD = C::A_LD;
     __shared__ __align__(16) T smem[2 * (C::A_ELEMS + C::B_ELEMS)];
 
@@ -97,11 +173,8 @@ __global__ void __launch_bounds__(THREADS, 6) xgemm_kernel(Args p) {
             }
         };
 
-        alignas(16) T acc[TM][TN];
-        #pragma unroll
-        for (int i = 0; i < TM; ++i)
-            #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = R::zero();
+        Acc<T, TM, TN> acc;
+        acc.zero();
 
         __syncthreads();                    // the previous tile's readers are done with both buffers
         fetch(0);
@@ -121,10 +194,7 @@ __global__ void __launch_bounds__(THREADS, 6) xgemm_kernel(Args p) {
                 #pragma unroll
                 for (int g = 0; g < TN / VE; ++g)
                     *reinterpret_cast<uint4*>(b + g * VE) = *reinterpret_cast<const uint4*>(Bs + k * BN + g * (8 * VE) + tx * VE);
-                #pragma unroll
-                for (int i = 0; i < TM; ++i)
-                    #pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = R::add(acc[i][j], R::mul(a[i], b[j]));
+                acc.step(a, b, p.one2, p.negzero2);
             };
             if (kleft >= BK) {
                 #pragma unroll 4
@@ -148,11 +218,11 @@ __global__ void __launch_bounds__(THREADS, 6) xgemm_kernel(Args p) {
                 const int c = c0 + h * (8 * VE) + tx * VE;
                 T* dst = gC + (size_t)r * p.Q + c;
                 if (vec_store && c + VE <= p.Q) {
-                    st_global_stream16(dst, *reinterpret_cast<const uint4*>(&acc[i][h * VE]));
+                    st_global_stream16(dst, acc.vec16(i, h));
                 } else {
                     #pragma unroll
                     for (int v = 0; v < VE; ++v)
-                        if (c + v < p.Q) dst[v] = acc[i][h * VE + v];
+                        if (c + v < p.Q) dst[v] = acc.get(i, h * VE + v);
                 }
             }
         }
@@ -174,7 +244,7 @@ static int launch(const Shard& s, int P, int K, int Q, const void* A, const void
     }
     const unsigned long long tiles = (unsigned long long)s.count * ((P + C::BM - 1) / C::BM) * ((Q + C::BN - 1) / C::BN);
     const int grid = (int)(tiles < (unsigned long long)cap[dev] ? tiles : (unsigned long long)cap[dev]);
-    Args a{A, B, Cc, P, K, Q, (unsigned long long)s.count};
+    Args a{A, B, Cc, P, K, Q, (unsigned long long)s.count, 0x3f8000003f800000ull, 0x8000000080000000ull};
     kern<<<grid, THREADS, 0, s.stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }

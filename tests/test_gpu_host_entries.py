@@ -92,7 +92,7 @@ def test_host_entries_edge_cases_and_errors(ctx):
     with pytest.raises(tb.Unsupported):
         host.det(ctx, np.zeros(9, dtype=np.int64), 3)                    # needs Fractional
     with pytest.raises(tb.Unsupported):
-        host.inverse(ctx, np.zeros(81 * 4), 9)                           # n > 8: no kernel, no CPU fallback
+        host.inverse(ctx, np.zeros(129 * 129 * 2), 129)                  # n > 128: no kernel, no CPU fallback
     with pytest.raises(TypeError):
         host.matmul(ctx, np.zeros(9, dtype=np.int32), np.zeros(9, dtype=np.int32), 3, 3, 3)
 

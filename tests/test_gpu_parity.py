@@ -676,7 +676,11 @@ def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
 
 # ---- Float on tcgen05 (3xTF32, TMEM accumulators): tolerance stated by north_star for Float ----
 @pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 32, 128), (256, 64, 128), (128, 96, 256), (256, 160, 256),
-                                 (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64)])
+                                 (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64),
+                                 # ragged against the 128 / 64 tiles and the 32-deep K chunks: the tensor maps carry the item as
+                                 # a dimension, so the missing rows / columns / k-slices of a box arrive as zeros
+                                 (96, 96, 96), (100, 64, 96), (48, 32, 64), (130, 36, 160), (65, 128, 64), (200, 100, 96),
+                                 (127, 44, 224), (257, 32, 64)])
 def test_tf32x3_matmul_within_tolerance(ctx, mkn):
     m, k, n = mkn
     for batch in (1, 7, 150, 301):          # > 148 tiles: every CTA works, some take several tiles (both TMEM accumulators)
@@ -690,6 +694,30 @@ def test_tf32x3_matmul_within_tolerance(ctx, mkn):
         assert np.all(err <= bound), f"max excess {np.max(err / bound)} at {np.unravel_index(np.argmax(err / bound), err.shape)}"
         # and far better than a single TF32 pass would be (~1e-3): the split terms are really there
         assert np.max(err / bound) < 0.5
+
+
+def test_tf32x3_ragged_specials_and_neighbours(ctx):
+    """A ragged shape (96 x 100 . 100 x 96: one 128-tile, K tail of 4): items with inf / NaN are recomputed exactly,
+    and the zero-filled part of a box must really be zeros - an item of huge values next to an item of tiny ones
+    would show up at once if a box ever read its neighbour's rows."""
+    m, k, n, batch = 96, 100, 96, 6
+    a, b = inputs(oracle.F32, 25, batch, m * k, k * n)
+    a = a.copy(); b = b.copy()
+    a[1 * m * k: 2 * m * k] *= np.float32(1e30)                 # neighbours of very different magnitude
+    a[2 * m * k: 3 * m * k] *= np.float32(1e-30)
+    a[4 * m * k + 5] = np.inf
+    b[5 * k * n + 77] = np.nan
+    C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy().reshape(batch, m, n)
+    want = oracle.matmul(a, b, m, k, n).reshape(batch, m, n)
+    for item in (4, 5):
+        nan = np.isnan(want[item])
+        assert np.array_equal(np.isnan(C[item]), nan), item
+        assert_bits_equal(np.where(nan, 0, C[item]), np.where(nan, 0, want[item]), f"special item {item}")
+    a3 = a.reshape(batch, m, k).astype(np.float64)
+    b3 = b.reshape(batch, k, n).astype(np.float64)
+    for item in (0, 1, 2, 3):
+        err = np.abs(C[item].astype(np.float64) - a3[item] @ b3[item])
+        assert np.all(err <= 1e-5 * (np.abs(a3[item]) @ np.abs(b3[item]))), item
 
 
 @pytest.mark.parametrize("n", [128, 64])
