@@ -118,12 +118,16 @@ int t5_buf_layout(const t5_buf* buf);
  * reference checkout — CHANGELOG.md:24-25; specified in SURVEY.md §8a a6.)
  * Results are bit-identical to that fold for every element type and shape, with two
  * exceptions that run on the tensor cores and meet the stated tolerance instead
- * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|): Double with m, n multiples of 64 and k a
- * multiple of 32 (FP64 DMMA, tol 1e-12), Float with m, n multiples of 64 and k a
- * multiple of 32 (tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with
- * the exact fold).  The tensor-core kernels take AoS batches; in SoA those shapes run the
- * thread-per-item contraction (exact fold, bit-identical), as does every other shape
- * without an SoA tile kernel. */
+ * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|):
+ *   Double, m and n multiples of 64 and k a multiple of 32: FP64 DMMA, tol 1e-12;
+ *   Float, m >= 48, n >= 64 a multiple of 32, k >= 32 a multiple of 4, and a 64- or 128-tiling
+ *   of the m x n result that is at least half full (m = n = 96 is; 48 x 64 is; 200 x 32 is
+ *   not): tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with the exact fold.
+ * Layout: the tile pipeline (records up to 8 x 8), outer products and contractions whose B fits
+ * in shared memory read SoA directly.  Every other shape has AoS kernels only; given SoA
+ * operands the library re-lays the shard out into stream-ordered AoS temporaries, runs the AoS
+ * kernel and re-lays the result out (one extra read + write pass per operand).  SoA is the
+ * tiny-record layout: for records of more than ~64 elements prefer AoS buffers. */
 int t5_matmul(t5_ctx* ctx, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C);
 
 /* DotProduct (dot): OUT[b] = fold_{i ascending} (acc + X[b,i]*Y[b,i]).  §8a a7. */
@@ -153,7 +157,14 @@ int t5_transpose(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, const t
  * with the first-non-zero pivot rule of SURVEY.md §8a (a9-a11).  Double and
  * Float only (T5_I64 -> T5_ERR_UNSUPPORTED: needs Fractional).  STATUS is a
  * T5_U8 buffer with one byte per item: 0 = Just, 1 = Nothing (singular; the
- * item's output is zero-filled). */
+ * item's output is zero-filled).
+ * Sizes: 1 <= n <= 128, 1 <= nrhs (any count; beyond 128 columns they are processed in
+ * passes); n > 128 is T5_ERR_UNSUPPORTED.  n <= 4: one record per thread in registers;
+ * 5 <= n <= 8: record per thread with streamed results (nrhs in {1, 2, 3, 4, n}) or one row
+ * per lane (other nrhs); 9 <= n <= 128: one CTA per matrix, the matrix 2D-cyclic in the
+ * CTA's registers.  Every size keeps the oracle's operation order: results are bit-identical
+ * to oracle/t5_oracle.cpp, not merely within tolerance.  SoA: n <= 8 (nrhs in {1, 2, 3, 4, n})
+ * directly, everything else through the AoS detour described at t5_matmul. */
 int t5_det(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
 int t5_inverse(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_buf* STATUS);
 int t5_solve(t5_ctx* ctx, int dtype, int n, int nrhs, const t5_buf* A, const t5_buf* B, t5_buf* X, t5_buf* STATUS);
@@ -169,7 +180,9 @@ int t5_solve(t5_ctx* ctx, int dtype, int n, int nrhs, const t5_buf* A, const t5_
  *                first, OUT[n] = 1 (Faddeev-LeVerrier).  Double / Float.
  *   t5_min_poly  OUT as for t5_char_poly, zero above the degree; DEGREE (T5_U8) receives the
  *                degree: the first exact linear dependency among I, A, A^2, ..; degree n
- *                returns the characteristic polynomial.  Double / Float, n <= 6; SoA for n <= 4. */
+ *                returns the characteristic polynomial.  Double / Float, n <= 6.
+ * Sizes: t5_trace, t5_poly_eval, t5_char_poly n <= 8 (n <= 4 in registers, any ncoef); t5_min_poly n <= 6;
+ * larger n is T5_ERR_UNSUPPORTED.  SoA: n <= 4 directly, else through the AoS detour (t5_matmul). */
 int t5_trace(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
 int t5_poly_eval(t5_ctx* ctx, int dtype, int n, const void* coeffs, int ncoef, const t5_buf* A, t5_buf* OUT);
 int t5_char_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT);
@@ -183,8 +196,9 @@ int t5_min_poly(t5_ctx* ctx, int dtype, int n, const t5_buf* A, t5_buf* OUT, t5_
  * the pivot column cleared in every other row, then the pivot row divided by its pivot.  Pivots are searched in the first pivot_cols columns only: pivot_cols = cols
  * is rowEchelonForm; on an augmented [A | B] item with pivot_cols = cols(A) it is
  * triangularSolve (A reduced, B carried along).  RANK (T5_U8) receives the number of pivots.
- * Double / Float, rows <= 8, cols <= 16; SoA for n x n and n x (n+1) with n <= 8 and n x 2n with
- * n <= 4 (the register-resident kernels). */
+ * Double / Float, rows <= 8, cols <= 16 (else T5_ERR_UNSUPPORTED); n x n and n x (n+1) with n <= 8 and
+ * n x 2n with n <= 4 run in registers (AoS and SoA), other shapes in a shared-memory kernel (AoS; SoA
+ * through the AoS detour). */
 int t5_row_echelon(t5_ctx* ctx, int dtype, int rows, int cols, int pivot_cols, const t5_buf* A, t5_buf* OUT, t5_buf* RANK);
 
 /* Element-wise vector-space operations (Functor/Applicative instances,

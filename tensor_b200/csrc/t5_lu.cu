@@ -184,17 +184,36 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
             const Recip<T> rc(piv);
             with_tile_index<NB>(ak, [&](auto A_) {
                 constexpr int A = decltype(A_)::value;
-                T prj[NB];
+                T prj[NB], f[NB];
                 #pragma unroll
                 for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
+                // the multipliers of all this thread's tile rows first, as one batch of independent exact divisions with one
+                // fallback branch for the whole batch (rows that are not past the front divide stale values: unused, and kept
+                // out of the fallback test - stale zeros / denormals would send every step down the slow division)
+                // (worth it only where a thread has many rows and few warps cover for it: 16 x 16 threads, NB = 8:
+                // n = 128 det 7.8 -> 5.9 ms; smaller tiles lost 5-50 % to the divisions of rows that are not past the front)
+                constexpr bool BATCH = TG == 16 && NB == 8;
+                if constexpr (BATCH) {
+                    bool all_fast = true;
+                    #pragma unroll
+                    for (int a = A; a < NB; ++a) {
+                        bool ok = true;
+                        f[a] = rc.div_try(cr[ty + TG * a], ok);
+                        all_fast = all_fast && (ok || !((a > A || ty > rk) && a < a_end));
+                    }
+                    if (!all_fast) {
+                        #pragma unroll
+                        for (int a = A; a < NB; ++a) f[a] = rc.div_fix(cr[ty + TG * a], f[a]);
+                    }
+                }
                 #pragma unroll
                 for (int a = A; a < NB; ++a) {
                     // rows of tile row A are past the front only for ty > rk; later tile rows are, whole; rows >= n do not exist
                     if ((a > A || ty > rk) && a < a_end) {
-                        const T f = rc.div(cr[ty + TG * a]);
-                        if (MODE != 0 && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f;   // the multiplier goes where the zero would go
+                        if constexpr (!BATCH) f[a] = rc.div(cr[ty + TG * a]);
+                        if (MODE != 0 && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f[a];   // the multiplier goes where the zero would go
                         #pragma unroll
-                        for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f * prj[b];
+                        for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f[a] * prj[b];
                     }
                 }
             });
@@ -283,8 +302,18 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                 for (int k = n - 1; k >= 0; --k) {
                     T s = T(0);
                     const T* urow = LU + (size_t)k * p.ldl;
-                    for (int j = k + 1; j < n; ++j) s = s + urow[j] * Y[(size_t)j * p.ldy + cc];
-                    Y[(size_t)k * p.ldy + cc] = (Y[(size_t)k * p.ldy + cc] - s) / urow[k];
+                    const T* ycol = Y + cc;
+                    int j = k + 1;
+                    // the sum is one dependent chain (its order is the specification's), but the operands are not: four
+                    // products are formed ahead of the adds that consume them, so the chain runs at the add latency
+                    // instead of shared-load + multiply + add per term
+                    for (; j + 4 <= n; j += 4) {
+                        const T p0 = urow[j] * ycol[(size_t)j * p.ldy], p1 = urow[j + 1] * ycol[(size_t)(j + 1) * p.ldy];
+                        const T p2 = urow[j + 2] * ycol[(size_t)(j + 2) * p.ldy], p3 = urow[j + 3] * ycol[(size_t)(j + 3) * p.ldy];
+                        s = s + p0; s = s + p1; s = s + p2; s = s + p3;
+                    }
+                    for (; j < n; ++j) s = s + urow[j] * ycol[(size_t)j * p.ldy];
+                    Y[(size_t)k * p.ldy + cc] = (ycol[(size_t)k * p.ldy] - s) / urow[k];
                 }
             }
             __syncthreads();
@@ -340,13 +369,19 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
 template <class T, int MODE>
 static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    if (n < 9 || n > 128) return T5I_NOT_SPECIALISED;
+    if (n < 1 || n > 128) return T5I_NOT_SPECIALISED;     // (n <= 8 only gets here for column counts without a faster kernel)
     if (s.count == 0) return T5I_OK;
+    // Geometry from tools/time_lu.py sweeps (profiles/r02i_lu_geometry.txt): an 8 x 8 thread grid as far as its tile fits in
+    // registers (n <= 64: 64 doubles per thread) - two-warp CTAs whose barriers are cheap and of which many are resident,
+    // each thread amortising the per-step overhead over NB^2 updates: n = 48 det 3.34 ms (16 x 16 threads) -> 2.03 ms,
+    // n = 64 3.34 -> 2.49 ms; beyond that 16 x 16 threads.
     if (n <= 16) return launch<T, 8, 2, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 24) return launch<T, 8, 3, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 32) return launch<T, 8, 4, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 48) return launch<T, 16, 3, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 64) return launch<T, 16, 4, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 40) return launch<T, 8, 5, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 48) return launch<T, 8, 6, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 56) return launch<T, 8, 7, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 64) return launch<T, 8, 8, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 80) return launch<T, 16, 5, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 96) return launch<T, 16, 6, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 112) return launch<T, 16, 7, MODE>(s, n, nrhs, A, B, X, status);

@@ -414,38 +414,75 @@ __device__ __forceinline__ void lu_solve_block(const T (&w)[N][N], const Recip<T
     });
 }
 
+// (3) for `inverse`: the factors leave the registers.  After (1) the thread writes L and U back over its own
+// input record in shared memory (`scratch_in0`) and the registers are free for ALL N columns of the permuted
+// identity at once; the replay then reads each factor entry once (one LDS per N multiply-subtracts) and runs N
+// independent recurrences instead of two.  The earlier two-columns-at-a-time version kept the factors in
+// registers (255 of them, two warps per scheduler) and stalled on the FP64 latency of the back-substitution
+// chains, whose order the specification fixes: ncu showed 49 % of the stall samples as fixed-latency `wait` and
+// the FP64 pipe 26 % busy.  Finished row k of the inverse overwrites row k of the factors, which nothing reads
+// any more (L row k was consumed by the forward sweep, U row k by back-substitution step k), so in the AoS
+// pipeline the result still leaves through the thread's input slot.
 template <class T, int N>
 struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
     static constexpr bool streams_out0 = true;
-    static constexpr int CB = 2;   // wider blocks (N/2, N) measured no faster for Double and slower for Float (registers)
+    static constexpr bool scratch_in0 = true;
     using In0 = Rec<T, N * N>; using In1 = NoRec;
     using Out0 = Rec<T, N * N>; using Out1 = Rec<unsigned char, 1>;
-    template <class W>
-    __device__ __forceinline__ static void run_stream(const T* a, const unsigned char*, const W& out, unsigned char* status) {
-        T w[N][N];
-        #pragma unroll
-        for (int i = 0; i < N; ++i)
-            #pragma unroll
-            for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+    template <class W, class S>
+    __device__ __forceinline__ static void run_stream(const T* a, const unsigned char*, const W& out, unsigned char* status, const S& scr) {
         int piv[N];
         Recip<T> rc[N];
-        const bool ok = lu_factor<T, N>(w, piv, rc);
-        static_for<0, (N + CB - 1) / CB>([&](auto blk_) {
-            constexpr int c0 = decltype(blk_)::value * CB;
-            constexpr int cb = (N - c0 < CB) ? N - c0 : CB;
-            // a row keeps its right-hand side through every swap, so column c0+c of the identity starts as
-            // e_pos with the 1 wherever original row c0+c ended up
-            T x[N][cb];
+        bool ok;
+        {
+            T w[N][N];
             #pragma unroll
-            for (int c = 0; c < cb; ++c) {
-                int pos = c0 + c;
+            for (int i = 0; i < N; ++i)
                 #pragma unroll
-                for (int k = 0; k < N; ++k) pos = (pos == k) ? piv[k] : ((pos == piv[k]) ? k : pos);
+                for (int j = 0; j < N; ++j) w[i][j] = a[i * N + j];
+            ok = lu_factor<T, N>(w, piv, rc);
+            static_for<0, N>([&](auto i_) {
+                static_for<0, N>([&](auto j_) {
+                    constexpr int i = decltype(i_)::value, j = decltype(j_)::value;
+                    if (i != j) scr.template put<i * N + j>(w[i][j]);       // (the diagonal lives on in rc[])
+                });
+            });
+        }
+        // a row keeps its right-hand side through every swap, so column c of the identity starts as e_pos with the 1
+        // wherever original row c ended up
+        T x[N][N];
+        #pragma unroll
+        for (int c = 0; c < N; ++c) {
+            int pos = c;
+            #pragma unroll
+            for (int k = 0; k < N; ++k) pos = (pos == k) ? piv[k] : ((pos == piv[k]) ? k : pos);
+            #pragma unroll
+            for (int i = 0; i < N; ++i) x[i][c] = (i == pos) ? T(1) : T(0);
+        }
+        static_for<0, N>([&](auto k_) {
+            constexpr int k = decltype(k_)::value;
+            static_for<k + 1, N>([&](auto i_) {
+                constexpr int i = decltype(i_)::value;
+                const T l = scr.template get<i * N + k>();
                 #pragma unroll
-                for (int i = 0; i < N; ++i) x[i][c] = (i == pos) ? T(1) : T(0);
-            }
-            lu_solve_block<T, N, cb>(w, rc, x, [&](auto k_, auto c_, T v) {
-                out.template put<decltype(k_)::value * N + c0 + decltype(c_)::value>(ok ? v : T(0));
+                for (int c = 0; c < N; ++c) x[i][c] = x[i][c] - l * x[k][c];
+            });
+        });
+        static_for<0, N>([&](auto kk_) {
+            constexpr int k = N - 1 - decltype(kk_)::value;
+            T s[N];
+            #pragma unroll
+            for (int c = 0; c < N; ++c) s[c] = T(0);
+            static_for<k + 1, N>([&](auto j_) {
+                constexpr int j = decltype(j_)::value;
+                const T u = scr.template get<k * N + j>();
+                #pragma unroll
+                for (int c = 0; c < N; ++c) s[c] = s[c] + u * x[j][c];
+            });
+            static_for<0, N>([&](auto c_) {
+                constexpr int c = decltype(c_)::value;
+                x[k][c] = rc[k].div(x[k][c] - s[c]);
+                out.template put<k * N + c>(ok ? x[k][c] : T(0));
             });
         });
         status[0] = ok ? 0 : 1;

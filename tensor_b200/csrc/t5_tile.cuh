@@ -145,6 +145,30 @@ struct SoaWriter {
     __device__ __forceinline__ void put(T v) const { base[(size_t)E * stride] = v; }
 };
 
+// Ops that park part of their working set in the thread's own (already loaded) In0 staging area declare
+// `scratch_in0` and take a fifth run_stream argument with compile-time-indexed get<E>() / put<E>(v): the thread's
+// input slot in the AoS pipeline (the SAME bytes the streamed results go to when the result record replaces In0:
+// the op must only overwrite what it no longer reads), its column of the staged tile in the SoA one.
+template <class Op, class = void> struct ScratchIn0 : std::false_type {};
+template <class Op> struct ScratchIn0<Op, std::void_t<decltype(Op::scratch_in0)>> : std::true_type {};
+template <class R>
+struct SlotScratch {
+    unsigned char* stage;
+    int item;
+    template <int E> __device__ __forceinline__ typename R::type get() const {
+        return *reinterpret_cast<const typename R::type*>(stage + R::elem_off(item, E));
+    }
+    template <int E> __device__ __forceinline__ void put(typename R::type v) const {
+        *reinterpret_cast<typename R::type*>(stage + R::elem_off(item, E)) = v;
+    }
+};
+template <class T, int PITCH>
+struct SoaScratch {
+    T* base;                        // this item's column of the staged [element][item] tile
+    template <int E> __device__ __forceinline__ T get() const { return base[E * PITCH]; }
+    template <int E> __device__ __forceinline__ void put(T v) const { base[E * PITCH] = v; }
+};
+
 struct TileArgs {
     const void* in0;
     const void* in1;
@@ -319,6 +343,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel(TileArgs a) {
                     if constexpr (LazyIn1<Op>::value) {
                         SlotReader<I1> rd{s1, it};
                         Op::run_stream(r0.v, rd, wr, w1.v);
+                    } else if constexpr (ScratchIn0<Op>::value) {
+                        SlotScratch<I0> scr{s0, it};
+                        Op::run_stream(r0.v, r1.v, wr, w1.v, scr);
                     } else {
                         Op::run_stream(r0.v, r1.v, wr, w1.v);
                     }
@@ -409,6 +436,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) tile_kernel_1s(TileArgs a
                     if constexpr (LazyIn1<Op>::value) {
                         SlotReader<I1> rd{s1, it};
                         Op::run_stream(r0.v, rd, wr, w1.v);
+                    } else if constexpr (ScratchIn0<Op>::value) {
+                        SlotScratch<I0> scr{s0, it};
+                        Op::run_stream(r0.v, r1.v, wr, w1.v, scr);
                     } else {
                         Op::run_stream(r0.v, r1.v, wr, w1.v);
                     }
@@ -556,6 +586,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) soa_tile_kernel(SoaArgs a
                     if constexpr (LazyIn1<Op>::value) {
                         SoaReader<T1> rd{s1 + it, TILE};
                         Op::run_stream(r0.v, rd, wr, w1.v);
+                    } else if constexpr (ScratchIn0<Op>::value) {
+                        SoaScratch<T0, TILE> scr{const_cast<T0*>(s0) + it};
+                        Op::run_stream(r0.v, r1.v, wr, w1.v, scr);
                     } else {
                         Op::run_stream(r0.v, r1.v, wr, w1.v);
                     }

@@ -89,6 +89,17 @@ def test_large_solve_wide_rhs_and_host_entry(ctx):
     assert np.array_equal(bits(host.det(ctx, a, n)), bits(oracle.det(a, n)))
 
 
+def test_small_n_with_many_right_hand_sides(ctx):
+    """n <= 8 with a column count that has no record-per-thread / row-per-lane kernel lands on the CTA-per-matrix kernel."""
+    for n, nrhs in [(4, 20), (3, 9), (8, 13), (1, 5), (2, 130)]:
+        batch = 203
+        a = inputs(oracle.F64, n, batch, 74) if n >= 3 else oracle.fill(oracle.F64, oracle.SEED_A, 74, batch * n * n).reshape(batch, n, n)
+        b = oracle.fill(oracle.F64, oracle.SEED_B, 74, batch * n * nrhs)
+        X, st = tb.solve(ctx.from_numpy(a, (n, n)), ctx.from_numpy(b, (n, nrhs)))
+        ox, ost = oracle.solve(a, b, n, nrhs, threads=8)
+        assert np.array_equal(st.to_numpy(), ost) and np.array_equal(bits(X.to_numpy()), bits(ox)), (n, nrhs)
+
+
 def test_large_elimination_soa_and_limits(ctx):
     n, batch = 12, 100
     a = inputs(oracle.F32, n, batch, 73)
