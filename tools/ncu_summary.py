@@ -1,5 +1,10 @@
 """Summarise an .ncu-rep (one kernel launch) into the handful of numbers DESIGN.md and
-bench.py's roofline.traffic cite.  Usage: python tools/ncu_summary.py rep [rep...]"""
+bench.py's roofline.traffic cite.
+Usage: python tools/ncu_summary.py rep [rep...]                       -> JSON summary on stdout
+       python tools/ncu_summary.py --traffic SHA rep [rep...]        -> also rewrites profiles/traffic.json: the DRAM
+           bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every capture whose file name is
+           <prefix>prof_<bench workload name>.ncu-rep, stamped with SHA (the git revision of the build that was
+           profiled) and the date; entries of workloads that were not re-captured are kept and listed as older."""
 import csv
 import json
 import subprocess
@@ -46,5 +51,32 @@ def summarise(path):
 
 
 if __name__ == "__main__":
-    res = {p: summarise(p) for p in sys.argv[1:]}
+    import datetime
+    import os
+    import re
+    args = sys.argv[1:]
+    sha = None
+    if args and args[0] == "--traffic":
+        sha, args = args[1], args[2:]
+    res = {p: summarise(p) for p in args}
     print(json.dumps(res, indent=1))
+    if sha:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        path = os.path.join(root, "profiles", "traffic.json")
+        try:
+            with open(path) as f:
+                traffic = json.load(f)
+        except Exception:
+            traffic = {}
+        old_src = traffic.pop("_source", None)
+        fresh = []
+        for p_, d in res.items():
+            m = re.search(r"prof_(.+)\.ncu-rep$", os.path.basename(p_))
+            if m and "dram_traffic_bytes" in d:
+                traffic[m.group(1)] = d["dram_traffic_bytes"]
+                fresh.append(m.group(1))
+        traffic["_source"] = {"git_sha": sha, "date": datetime.date.today().isoformat(),
+                              "how": "ncu --set full --clock-control none, one launch per workload, dram__bytes_read.sum + dram__bytes_write.sum",
+                              "captured_at_this_sha": sorted(fresh), "older_entries_from": old_src}
+        with open(path, "w") as f:
+            json.dump(traffic, f, indent=1)

@@ -145,6 +145,20 @@ def main():
             add(f"pure 4x4 {tag}", B * 16 * es, lambda: tb.pure(ctx, 1.5, (4, 4), dt, B))
             for x in (B8, v8, v64a, v64b, v4a, v4b, A2, B2, A16, B16, A12, B12, I8, B44):
                 x.free()
+            # round 2: eliminations beyond n = 8 (CTA per matrix), the SoA detour of an AoS-only kernel, a ragged Float product
+            for nn in (16, 32, 64, 128):
+                Bn = max(256, (B * 16) // (nn * nn))
+                An = ctx.synthetic((nn, nn), dt, Bn, SEED, 40).plant_specials(1024, 65536)
+                add(f"det {nn}x{nn} (CTA per matrix) {tag}", Bn * (nn * nn + 1) * es, lambda: tb.det(An))
+                add(f"inverse {nn}x{nn} (CTA per matrix) {tag}", Bn * (2 * nn * nn * es + 1), lambda: tb.inverse(An))
+                An.free()
+            A32s, B32s = A32.relayout(tb.SOA), B32.relayout(tb.SOA)
+            add(f"SoA matmul 32x32 (detour: relayout in, AoS kernel, relayout out) {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(A32s, B32s))
+            A32s.free(); B32s.free()
+            if es == 4:
+                A96, B96 = ctx.synthetic((96, 96), dt, B // 64, SEED, 41), ctx.synthetic((96, 96), dt, B // 64, SEED + 1, 41)
+                add(f"matmul 96x96 (ragged tcgen05 tiles) {tag}", (B // 64) * 3 * 9216 * es, lambda: tb.matmul(A96, B96))
+                A96.free(); B96.free()
             for x in (A3, A4, B4, v3, A6, b6, A8, T234, A5, B5, A32, B32):
                 x.free()
 
