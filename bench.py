@@ -115,8 +115,10 @@ WORKLOADS = {
                               desc="64Ki 128x128 Float .*. on tcgen05 tensor cores (3xTF32 split, TMEM accumulators; 21 flop/B: HBM-bound)"),
     "matmul64_f32_256K": dict(op="matmul", dtype="f32", m=64, k=64, n=64, batch=1 << 18, bytes=49152, flops=524288, bound="hbm",
                               desc="256Ki 64x64 Float .*. on tcgen05 tensor cores (3xTF32, UMMA M = N = 64; 10.7 flop/B: HBM-bound)"),
-    "matmul96_f32_64K": dict(op="matmul", dtype="f32", m=96, k=96, n=96, batch=1 << 16, bytes=110592, flops=1769472, bound="fp32",
-                             desc="64Ki 96x96 Float .*. (off the tensor-core tile grid: exact blocked SIMT product, unfused multiply+add)"),
+    "matmul96_f32_64K": dict(op="matmul", dtype="f32", m=96, k=96, n=96, batch=1 << 16, bytes=110592, flops=1769472, bound="hbm",
+                             desc="64Ki 96x96 Float .*. on tcgen05 tensor cores (3xTF32; ragged against the 128-tile: the item is a tensor-map dimension, boxes zero-filled)"),
+    "matmul100x20x36_f32_256K": dict(op="matmul", dtype="f32", m=100, k=20, n=36, batch=1 << 18, bytes=(2000 + 720 + 3600) * 4, flops=144000, bound="fp32",
+                                     desc="256Ki 100x20 . 20x36 Float (no tensor-core tiling fits: exact blocked SIMT product, packed FFMA2 multiply then add)"),
     "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
                               desc="256Ki 64x64 Double .*. on FP64 tensor cores (smallest DMMA shape; 5.3 flop/B, HBM floor ~= tensor floor)"),
 }

@@ -12,6 +12,8 @@
 // |delta| <= 1e-12 * sum_j |a_ij||b_jk|, the tolerance north_star states for Double.
 // History (numbers in DESIGN.md §5.9): a cp.async ring issued by the DMMA warps with a CTA barrier
 // per K chunk kept the DMMA pipe 74 % busy (9.49 ms for 64Ki x 128^3); this kernel 96 % (7.73 ms).
+#include <atomic>
+
 #include "t5_async.cuh"
 #include "t5_device.cuh"
 #include "t5_internal.h"
@@ -216,7 +218,7 @@ int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* 
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
     if (m % 64 || n % 64 || k % dt::BK || k < dt::BK) return T5I_NOT_SPECIALISED;
     const bool big = m % 128 == 0 && n % 128 == 0;
-    static bool configured[T5_MAX_DEVICES] = {false};
+    static std::atomic<bool> configured[T5_MAX_DEVICES];   // zero-initialised; entries of different contexts / pipeline threads may race here (idempotent work)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
     if (!configured[dev]) {

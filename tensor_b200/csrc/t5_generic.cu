@@ -1233,130 +1233,6 @@ int generic_replicate(const Shard& s, int elem_bytes, size_t d, const void* rec_
 }
 
 // =====================================================================================
-// rowEchelonForm / triangularSolve (specification: oracle/t5_oracle.cpp
-// row_echelon_item): reduced row echelon form of any rows x cols matrix, rows <= 8, cols <= 16.
-// The pivot ROW is a run-time quantity here (a column without a pivot does not advance it), so a
-// register-resident working matrix is not possible; local memory (3 MB per SM of L1/L2 traffic)
-// is what made the first any-n elimination kernels slow.  Instead a CTA stages TPB consecutive
-// records into shared memory TRANSPOSED - element e of the CTA's item t at w[e * (TPB+1) + t] -
-// with coalesced global reads, every thread reduces its own column of that array in place
-// (stride-1 across the warp: conflict-free LDS/STS for any run-time index), and the CTA writes the
-// tile back coalesced.  Same operations in the same order as the oracle: bit-identical.
-// =====================================================================================
-constexpr int ECH_MAX_ROWS = 8, ECH_MAX_COLS = 16;
-
-template <class T, int TPB>
-__global__ void __launch_bounds__(TPB)
-row_echelon_kernel(const T* __restrict__ A, T* __restrict__ OUT, unsigned char* __restrict__ RANK, int m, int n, int pivot_cols,
-                   unsigned long long count) {
-    extern __shared__ __align__(16) unsigned char ech_smem[];
-    T* w = reinterpret_cast<T*>(ech_smem);
-    constexpr int P = TPB + 1;
-    const int L = m * n;
-    const int tid = threadIdx.x;
-    const unsigned long long n_tiles = (count + TPB - 1) / TPB;
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long first = tile * TPB;
-        const int nv = (count - first < (unsigned long long)TPB) ? (int)(count - first) : TPB;
-        const int total = nv * L;
-        const T* g = A + first * (size_t)L;
-        {
-            // asynchronous element copies: a CTA is only 2-4 warps, and with register-staged loads (4 in flight per
-            // thread) the kernel ran at the latency, not the bandwidth, of HBM (1.5 TB/s for Float and Double alike)
-            int item = tid / L, e = tid - item * L;
-            for (int idx = tid; idx < total; idx += TPB) {
-                cp_async_small<(int)sizeof(T)>(w + e * P + item, g + idx);
-                e += TPB;
-                while (e >= L) { e -= L; ++item; }
-            }
-            cp_async_commit();
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        if (tid < nv) {
-            T* x = w + tid;                                     // element (i, j) of this item: x[(i * n + j) * P]
-            int rank = 0;
-            for (int c = 0; c < pivot_cols && rank < m; ++c) {
-                int p = rank;
-                while (p < m && x[(p * n + c) * P] == T(0)) ++p;
-                if (p == m) continue;
-                if (p != rank)
-                    for (int j = 0; j < n; ++j) {
-                        const T t = x[(p * n + j) * P];
-                        x[(p * n + j) * P] = x[(rank * n + j) * P];
-                        x[(rank * n + j) * P] = t;
-                    }
-                T* pr = x + (rank * n) * P;
-                const T d = pr[c * P];
-                // m - 1 multipliers and up to n - 1 normalisations divide by this pivot: the exact division with its
-                // reciprocal hoisted (t5_recip.cuh; bit-identical to `/`) turns ~25 FP64 instructions per quotient into ~8
-                const Recip<T> rc(d);
-                // the pivot row and each target row pass through registers (compile-time unrolled over the 16 possible
-                // columns, predicated): with both rows addressed through shared-memory pointers the compiler must keep
-                // every load behind the previous store, and the updates ran one shared-memory latency at a time
-                T prow[ECH_MAX_COLS];
-                #pragma unroll
-                for (int j = 0; j < ECH_MAX_COLS; ++j) prow[j] = (j > c && j < n) ? pr[j * P] : T(0);
-                for (int i = 0; i < m; ++i) {
-                    if (i == rank) continue;
-                    T* ri = x + (i * n) * P;
-                    const T f = rc.div(ri[c * P]);
-                    T rrow[ECH_MAX_COLS];
-                    #pragma unroll
-                    for (int j = 0; j < ECH_MAX_COLS; ++j)
-                        if (j > c && j < n) rrow[j] = ri[j * P];
-                    #pragma unroll
-                    for (int j = 0; j < ECH_MAX_COLS; ++j)
-                        if (j > c && j < n) ri[j * P] = rrow[j] - f * prow[j];
-                    ri[c * P] = T(0);
-                }
-                #pragma unroll
-                for (int j = 0; j < ECH_MAX_COLS; ++j)
-                    if (j > c && j < n) pr[j * P] = rc.div(prow[j]);
-                pr[c * P] = T(1);
-                ++rank;
-            }
-            RANK[first + tid] = (unsigned char)rank;
-        }
-        __syncthreads();
-        {
-            T* o = OUT + first * (size_t)L;
-            int item = tid / L, e = tid - item * L;
-            #pragma unroll 4
-            for (int idx = tid; idx < total; idx += TPB) {
-                o[idx] = w[e * P + item];
-                e += TPB;
-                while (e >= L) { e -= L; ++item; }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-template <class T, int TPB>
-static int launch_row_echelon(const Shard& s, int m, int n, int pivot_cols, const void* A, void* O, void* rank) {
-    auto kern = row_echelon_kernel<T, TPB>;
-    const int smem = m * n * (TPB + 1) * (int)sizeof(T);
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return T5I_CUDA;
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
-    const size_t tiles = (s.count + TPB - 1) / TPB, cap = (size_t)occ * sm_count();
-    const int grid = (int)(tiles < cap ? tiles : cap);
-    kern<<<grid, TPB, smem, s.stream>>>((const T*)A, (T*)O, (unsigned char*)rank, m, n, pivot_cols, (unsigned long long)s.count);
-    return ok();
-}
-
-int generic_row_echelon(const Shard& s, int dtype, int m, int n, int pivot_cols, const void* A, void* O, void* rank) {
-    if (s.layout != T5L_AOS || m < 1 || n < 1 || m > ECH_MAX_ROWS || n > ECH_MAX_COLS || pivot_cols < 0 || pivot_cols > n) return T5I_UNSUPPORTED;
-    if (s.count == 0) return T5I_OK;
-    // small records: 128 items per CTA (more bytes in flight per CTA); large ones: 64, so that several CTAs fit an SM
-    const bool small = (size_t)m * n * (dtype == T5D_F64 ? 8 : 4) <= 192;
-    if (dtype == T5D_F64) return small ? launch_row_echelon<double, 128>(s, m, n, pivot_cols, A, O, rank) : launch_row_echelon<double, 64>(s, m, n, pivot_cols, A, O, rank);
-    if (dtype == T5D_F32) return small ? launch_row_echelon<float, 128>(s, m, n, pivot_cols, A, O, rank) : launch_row_echelon<float, 64>(s, m, n, pivot_cols, A, O, rank);
-    return T5I_UNSUPPORTED;
-}
-
-// =====================================================================================
 // Element-wise vector-space operations (Functor/Applicative, Vector.hs:180-190,
 // :250-251).  Layout-agnostic: they act on the flat element array of a shard.
 // =====================================================================================
@@ -1570,6 +1446,8 @@ static void dot_sum_launch(const Shard& s, size_t elems, size_t row_stride, size
     dot_sum_stage2<Acc><<<1, DS_THREADS, 0, s.stream>>>((const Acc*)scratch, grid, (Acc*)partial);
 }
 
+// (A single-kernel version - the last block to finish folds the partials - measured SLOWER: 16Mi 4-vectors Float
+// 99.8 -> 104.6 us per call; the extra code costs the streaming kernel more than the second launch does.)
 // scratch_dev: >= DS_MAX_BLOCKS * 8 bytes.  AoS: elems = count*d, row_stride = 0.  SoA: elems = stride*d, rows of
 // row_stride items of which the first row_valid are data (the rest is padding and is skipped).
 int dot_sum_partial(const Shard& s, int dtype, size_t elems, size_t row_stride, size_t row_valid, const void* X, const void* Y, void* scratch, void* partial) {

@@ -22,6 +22,8 @@
 //
 // The hardware reads the FP32 bit patterns of the "hi" tiles and ignores the 13 low mantissa bits,
 // so the raw operands serve as a_hi / b_hi and only the lo tiles are computed.
+#include <atomic>
+
 #include "t5_async.cuh"
 #include "t5_device.cuh"
 #include "t5_internal.h"
@@ -339,7 +341,7 @@ int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void
     const double w128 = tf_waste(m, n, 128), w64 = tf_waste(m, n, 64);
     if (w128 > 2.0 && w64 > 2.0) return T5I_NOT_SPECIALISED;
     const bool big = w128 <= w64 * 1.3;
-    static bool configured[T5_MAX_DEVICES] = {false};
+    static std::atomic<bool> configured[T5_MAX_DEVICES];   // zero-initialised; entries of different contexts / pipeline threads may race here (idempotent work)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
     if (!configured[dev]) {
