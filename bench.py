@@ -70,7 +70,7 @@ WORKLOADS = {
     "tensorprod8x8_f64_soa_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=0, batch=1 << 20, bytes=33792, bound="hbm", layout="soa",
                                      desc="1Mi 8x8 (x) 8x8 -> 8^4 Double on SoA buffers (16 bytes of consecutive items per thread, B staged in shared memory)"),
     "prod1_8x8_f64_soa_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=1, batch=1 << 20, bytes=1536, bound="hbm", layout="soa",
-                                 desc="1Mi 8x8 . 8x8 Double (prod 1) on SoA buffers (B staged in shared memory, A row in registers)"),
+                                 desc="1Mi 8x8 . 8x8 Double (prod 1) on SoA buffers (B in registers, rows of A streamed through a two-deep register pipeline)"),
     "matmul4x4_f32_soa_16M": dict(op="matmul", dtype="f32", m=4, k=4, n=4, batch=1 << 24, bytes=192, bound="hbm", layout="soa",
                                   desc="16Mi pairs of 4x4 Float matrices, .*., SoA device layout"),
     "inverse4_f64_soa_4M": dict(op="inverse", dtype="f64", n=4, batch=1 << 22, bytes=257, bound="hbm", layout="soa",

@@ -855,6 +855,62 @@ static int soa_outer_launch(const Shard& s, int P, int Q, const void* A, const v
     return ok();
 }
 
+// SoA contraction with B IN REGISTERS (K x Q <= 64 elements, compile-time): thread per item.  All of B is requested up
+// front (K * Q independent coalesced loads in flight per thread), the rows of A stream through a two-deep register
+// pipeline (row i + 1 is in flight while row i is multiplied), results leave as coalesced streaming stores - no shared
+// memory, no barrier.  The staged-B kernel above waited for its cp.async copies, then paid one exposed global round trip
+// per row of A and read every B element from shared memory P times: 1Mi 8x8 Double 0.453 ms (0.54 of the HBM peak).
+// Same fold as everywhere: acc = 0; k ascending; multiply, round, add, round.
+template <class T, int K, int Q>
+__global__ void __launch_bounds__(128)
+soa_prod_reg_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, unsigned long long count, unsigned long long stride) {
+    using R = Arith<T>;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < count; b += step) {
+        T breg[K * Q];
+        #pragma unroll
+        for (int e = 0; e < K * Q; ++e) breg[e] = __ldg(B + (size_t)e * stride + b);
+        const T* a = A + b;
+        T* c = C + b;
+        T nxt[K];
+        #pragma unroll
+        for (int k = 0; k < K; ++k) nxt[k] = __ldg(a + (size_t)k * stride);
+        for (int i = 0; i < P; ++i) {
+            T arow[K];
+            #pragma unroll
+            for (int k = 0; k < K; ++k) arow[k] = nxt[k];
+            if (i + 1 < P) {
+                #pragma unroll
+                for (int k = 0; k < K; ++k) nxt[k] = __ldg(a + ((size_t)(i + 1) * K + k) * stride);
+            }
+            #pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                T acc = R::zero();
+                #pragma unroll
+                for (int k = 0; k < K; ++k) acc = R::add(acc, R::mul(arow[k], breg[k * Q + q]));
+                __stcs(c + ((size_t)i * Q + q) * stride, acc);
+            }
+        }
+    }
+}
+template <class T, int K, int Q>
+static int soa_prod_reg_launch(const Shard& s, int P, const void* A, const void* B, void* C) {
+    auto kern = soa_prod_reg_kernel<T, K, Q>;
+    const size_t tiles = (s.count + 127) / 128;
+    kern<<<resident_grid((const void*)kern, 128, tiles), 128, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, (unsigned long long)s.count, s.soa_stride);
+    return ok();
+}
+template <class T>
+static int soa_prod_reg(const Shard& s, int P, int K, int Q, const void* A, const void* B, void* C) {
+    if (K == 8 && Q == 8) return soa_prod_reg_launch<T, 8, 8>(s, P, A, B, C);
+    if (K == 7 && Q == 7) return soa_prod_reg_launch<T, 7, 7>(s, P, A, B, C);
+    if (K == 6 && Q == 6) return soa_prod_reg_launch<T, 6, 6>(s, P, A, B, C);
+    if (K == 5 && Q == 5) return soa_prod_reg_launch<T, 5, 5>(s, P, A, B, C);
+    if (K == 8 && Q == 4) return soa_prod_reg_launch<T, 8, 4>(s, P, A, B, C);
+    if (K == 4 && Q == 8) return soa_prod_reg_launch<T, 4, 8>(s, P, A, B, C);
+    return T5I_NOT_SPECIALISED;
+}
+
 template <class T>
 static int soa_prod_staged_launch(const Shard& s, int P, int K, int Q, const void* A, const void* B, void* C) {
     constexpr int THREADS = 128;
@@ -877,6 +933,15 @@ int generic_soa_prod(const Shard& s, int dtype, int P, int K, int Q, int nc, con
             case T5D_F32: return soa_outer_launch<float>(s, P, Q, A, B, C);
             case T5D_I64: return soa_outer_launch<long long>(s, P, Q, A, B, C);
         }
+    }
+    if (nc != 0 && P > 1) {                                  // B of <= 64 elements, common shapes: B in registers
+        int r = T5I_NOT_SPECIALISED;
+        switch (dtype) {
+            case T5D_F64: r = soa_prod_reg<double>(s, P, K, Q, A, B, C); break;
+            case T5D_F32: r = soa_prod_reg<float>(s, P, K, Q, A, B, C); break;
+            case T5D_I64: r = soa_prod_reg<long long>(s, P, K, Q, A, B, C); break;
+        }
+        if (r != T5I_NOT_SPECIALISED) return r;
     }
     // B of 16..200 elements and more than one result row: stage B (<= 200 KB of shared memory per 128 items)
     if (nc != 0 && P > 1 && (long long)K * Q >= 16 && (long long)K * Q * 128 * (dtype == T5D_F32 ? 4 : 8) <= 200 * 1024) {

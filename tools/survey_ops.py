@@ -129,7 +129,7 @@ def main():
             add(f"SoA append 3x3|3 {tag}", B * 24 * es, lambda: st.append(2, A3s, v3s))
             # SoA: a slice copies 8 whole rows; the 16 rows it does not select are never read (AoS reads every sector of the item)
             add(f"SoA slice 2x3x4 [_,2,_] {tag}", B * (8 + 8) * es, lambda: st.slice_(T234s, [None, 2, None]))
-            add(f"SoA matmul 8x8 (B staged in shared memory) {tag}", (B // 4) * 192 * es, lambda: tb.matmul(A8s, B8s))
+            add(f"SoA matmul 8x8 (B in registers, A rows streamed) {tag}", (B // 4) * 192 * es, lambda: tb.matmul(A8s, B8s))
             for x in (T234s, A3s, v3s, A8s, B8s):
                 x.free()
             b3s, b4s = ctx.synthetic((3,), dt, B, SEED + 1, 28), ctx.synthetic((4,), dt, B, SEED + 1, 29)
