@@ -56,6 +56,7 @@ struct Args {
     int n, nrhs;
     int ldl, ldy;           // row pitches (elements) of the shared factors and of the shared right-hand sides
     int chunk;              // right-hand-side columns processed per pass (multiple of TG, <= TG * NB)
+    unsigned group_smem;    // shared-memory bytes of one group (a CTA holds G groups)
 };
 
 // CTA-uniform dispatch on a tile index: fn(std::integral_constant<int, A>) with A == a_rt
@@ -68,11 +69,21 @@ __device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
 }
 
 // MODE 0: det, 1: solve (rhs from B), 2: inverse (rhs = identity, nrhs == n)
-template <class T, int TG, int NB, int MODE>
-__global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
-    constexpr int THREADS = TG * TG;
+// G groups of TG x TG threads per CTA, one matrix per group.  Groups never interact: each has its own slice of shared
+// memory and its own barrier - the CTA barrier when the CTA is one group, a masked __syncwarp when a group is part of a
+// warp (TG = 4: two matrices per warp, every warp independent of the others - no CTA-wide barrier anywhere).
+template <class T, int TG, int NB, int MODE, int G>
+__global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
+    constexpr int THREADS = TG * TG;                   // threads of ONE group
     constexpr int NMAX = TG * NB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(G == 1 || THREADS <= 32, "several groups per CTA only when a group fits in a warp");
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    const int gid = threadIdx.x / THREADS;
+    unsigned char* smem_raw = smem_all + (size_t)gid * p.group_smem;
+    const unsigned gmask = THREADS >= 32 ? 0xffffffffu : (((1u << THREADS) - 1u) << ((threadIdx.x & 31) / THREADS * THREADS));
+    auto group_sync = [&]() {
+        if constexpr (THREADS >= 32) __syncthreads(); else __syncwarp(gmask);
+    };
     T* prow = reinterpret_cast<T*>(smem_raw);          // [2][NMAX]   published pivot row (double-buffered)
     T* fcol = prow + 2 * NMAX;                          // [2][NMAX]   published raw column of the step (the numerators of the multipliers)
     T* xrow = fcol + 2 * NMAX;                          // [2][NMAX]   row exchange for swaps
@@ -81,13 +92,13 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
     T* LU = reinterpret_cast<T*>(ctl + 4);              // [n][ldl]  (MODE != 0): U on and above the diagonal, multipliers below
     T* Y = LU + (MODE != 0 ? (size_t)p.n * p.ldl : 0);  // [n][ldy]  (MODE != 0)
 
-    const int tid = threadIdx.x, ty = tid / TG, tx = tid % TG;
+    const int tid = threadIdx.x % THREADS, ty = tid / TG, tx = tid % TG;
     const int n = p.n;
     const T* gA = (const T*)p.A;
     // number of this thread's tile rows / columns that lie inside the matrix
     const int a_end = ty < n ? (n - ty + TG - 1) / TG : 0;
 
-    for (unsigned long long item = blockIdx.x; item < p.count; item += gridDim.x) {
+    for (unsigned long long item = (unsigned long long)blockIdx.x * G + gid; item < p.count; item += (unsigned long long)gridDim.x * G) {
         // ---- load: thread (ty, tx) takes A[ty + TG a][tx + TG b]; TG consecutive threads read TG consecutive elements
         T w[NB][NB];
         const T* a_item = gA + item * (unsigned long long)n * n;
@@ -98,11 +109,11 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                 const int i = ty + TG * a, j = tx + TG * b;
                 w[a][b] = (i < n && j < n) ? __ldg(a_item + (size_t)i * n + j) : T(0);
             }
-        if (tid < NMAX) perm[tid] = tid;
+        for (int i = tid; i < NMAX; i += THREADS) perm[i] = i;     // (a 4 x 4 group has fewer threads than rows)
         if (tid == 0) ctl[1] = 0;
         T acc = T(1);                                   // thread 0: running product of the pivots
         bool singular = false;
-        __syncthreads();
+        group_sync();
 
         // ---- elimination of A: ONE barrier per step.  At the top of step k the pivot row and the raw column k (both as
         // left by step k - 1) are already published.  Every thread divides for its own NB rows (f = column / pivot with
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                 });
         };
         publish(0);
-        __syncthreads();
+        group_sync();
         for (int k = 0; k < n; ++k) {
             const int rk = k % TG, ak = k / TG;         // owner thread-row (= thread-column) and tile index of row / column k
             const T* pr = prow + (k & 1) * NMAX;
@@ -136,10 +147,10 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
             if (piv == T(0)) {
                 // slow path (rare: planted zeros, exactly singular items): first row p > k with a non-zero in column k
                 if (tid == 0) ctl[0] = n;
-                __syncthreads();
+                group_sync();
                 for (int i = k + 1 + tid; i < n; i += THREADS)
                     if (cr[i] != T(0)) atomicMin(&ctl[0], i);
-                __syncthreads();
+                group_sync();
                 const int pidx = ctl[0];
                 if (pidx >= n) { singular = true; break; }           // uniform: every thread reads the same word
                 const int rp = pidx % TG, ap = pidx / TG;
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) xrow[NMAX + tx + TG * b] = w[A][b];
                     });
-                __syncthreads();
+                group_sync();
                 if (ty == rk)
                     with_tile_index<NB>(ak, [&](auto A_) {
                         constexpr int A = decltype(A_)::value;
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                     }
                 if (tid == 0) { const int t = perm[k]; perm[k] = perm[pidx]; perm[pidx] = t; ctl[1] += 1; }
                 publish(k);                                           // (same buffer: every thread is inside this branch)
-                __syncthreads();
+                group_sync();
                 piv = pr[k];
             }
             if (tid == 0) acc = acc * piv;
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                 }
             });
             if (k + 1 < n) publish(k + 1);
-            __syncthreads();
+            group_sync();
         }
 
         if (MODE == 0) {
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                 T d = singular ? T(0) : ((ctl[1] & 1) ? -acc : acc);
                 ((T*)p.X)[item] = d;
             }
-            __syncthreads();                            // perm / ctl are rewritten by the next item
+            group_sync();                            // perm / ctl are rewritten by the next item
             continue;
         }
 
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
         if (tid == 0) p.status[item] = singular ? 1 : 0;
         if (singular) {
             for (int e = tid; e < n * nrhs; e += THREADS) gX[e] = T(0);
-            __syncthreads();
+            group_sync();
             continue;
         }
         // U (row i, columns j >= i) is final in the registers of its owners
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                 const int i = ty + TG * a, j = tx + TG * b;
                 if (i < n && j < n && j >= i) LU[(size_t)i * p.ldl + j] = w[a][b];
             }
-        __syncthreads();
+        group_sync();
         const T* gB = MODE == 1 ? (const T*)p.B + item * (unsigned long long)n * nrhs : nullptr;
         for (int c0 = 0; c0 < nrhs; c0 += p.chunk) {
             // right-hand sides of this pass, rows already permuted; same cyclic distribution (NB x NB tile, columns c0 + tx + TG b)
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) pr[tx + TG * b] = y[A][b];
                     });
-                __syncthreads();
+                group_sync();
                 with_tile_index<NB>(ak, [&](auto A_) {
                     constexpr int A = decltype(A_)::value;
                     T prj[NB];
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                     const int i = ty + TG * a, cc = tx + TG * b;
                     if (i < n && cc < p.chunk) Y[(size_t)i * p.ldy + cc] = y[a][b];
                 }
-            __syncthreads();
+            group_sync();
             // back-substitution: thread cc owns column c0 + cc; u[k][j] is a broadcast read
             for (int cc = tid; cc < p.chunk && c0 + cc < nrhs; cc += THREADS) {
                 for (int k = n - 1; k >= 0; --k) {
@@ -316,13 +327,13 @@ __global__ void __launch_bounds__(TG * TG) lu_kernel(Args p) {
                     Y[(size_t)k * p.ldy + cc] = (ycol[(size_t)k * p.ldy] - s) / urow[k];
                 }
             }
-            __syncthreads();
+            group_sync();
             const int width = (nrhs - c0) < p.chunk ? (nrhs - c0) : p.chunk;
             for (int e = tid; e < n * width; e += THREADS) {
                 const int i = e / width, cc = e - i * width;
                 gX[(size_t)i * nrhs + c0 + cc] = Y[(size_t)i * p.ldy + cc];
             }
-            __syncthreads();
+            group_sync();
         }
     }
 }
@@ -337,7 +348,7 @@ static int sm_count() {
     return n;
 }
 
-template <class T, int TG, int NB, int MODE>
+template <class T, int TG, int NB, int MODE, int G = 1>
 static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
     constexpr int NMAX = TG * NB;
     Args p;
@@ -347,22 +358,26 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
     p.chunk = TG; p.ldy = 1;
     if (MODE != 0) {
         // as many right-hand-side columns per pass as the tile holds and shared memory allows (the factors stay resident)
-        const size_t budget = 200 * 1024;
+        const size_t budget = 200 * 1024 / G;
         int chunk = ((nrhs + TG - 1) / TG) * TG;
         if (chunk > NMAX) chunk = NMAX;
         while (chunk > TG && smem + sizeof(T) * ((size_t)n * p.ldl + (size_t)n * (chunk | 1)) > budget) chunk -= TG;
         p.chunk = chunk;
         p.ldy = chunk | 1;
         smem += sizeof(T) * ((size_t)n * p.ldl + (size_t)n * p.ldy);
-        if (smem > 227 * 1024) return T5I_UNSUPPORTED;
     }
-    auto kern = lu_kernel<T, TG, NB, MODE>;
+    smem = (smem + 15) / 16 * 16;
+    p.group_smem = (unsigned)smem;
+    smem *= G;
+    if (smem > 227 * 1024) return T5I_UNSUPPORTED;
+    auto kern = lu_kernel<T, TG, NB, MODE, G>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return T5I_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TG * TG, smem) != cudaSuccess || per_sm < 1) return T5I_CUDA;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TG * TG * G, smem) != cudaSuccess || per_sm < 1) return T5I_CUDA;
     const unsigned long long slots = (unsigned long long)per_sm * sm_count();
-    const int grid = (int)(s.count < slots ? s.count : slots);
-    kern<<<grid, TG * TG, smem, s.stream>>>(p);
+    const unsigned long long want = (s.count + G - 1) / G;
+    const int grid = (int)(want < slots ? want : slots);
+    kern<<<grid, TG * TG * G, smem, s.stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? T5I_OK : T5I_CUDA;
 }
 
@@ -375,6 +390,15 @@ static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* 
     // registers (n <= 64: 64 doubles per thread) - two-warp CTAs whose barriers are cheap and of which many are resident,
     // each thread amortising the per-step overhead over NB^2 updates: n = 48 det 3.34 ms (16 x 16 threads) -> 2.03 ms,
     // n = 64 3.34 -> 2.49 ms; beyond that 16 x 16 threads.
+    // n <= 16 (and the light operations up to 32): 4 x 4 threads per matrix, EIGHT matrices per 128-thread CTA, two per
+    // warp - a group synchronises with a masked __syncwarp, so no warp ever waits for another: det 16x16 Double
+    // 1.85 -> 0.95 ms (1.13 TB/s), inverse 5.29 -> 2.72 ms, 9x9 det 2.17 -> 1.08 ms (tools/time_lu.py, profiles/r02m_*).
+    // Heavier tiles (inverse from n = 17, everything dense from n = 25) do better spread over 64 threads.
+    const bool light = MODE == 0 || (MODE == 1 && nrhs <= 4);
+    if (n <= 8) return launch<T, 4, 2, MODE, 8>(s, n, nrhs, A, B, X, status);
+    if (n <= 16) return launch<T, 4, 4, MODE, 8>(s, n, nrhs, A, B, X, status);
+    if (n <= 24 && light) return launch<T, 4, 6, MODE, 8>(s, n, nrhs, A, B, X, status);
+    if (n <= 32 && MODE == 1 && nrhs <= 4) return launch<T, 4, 8, MODE, 8>(s, n, nrhs, A, B, X, status);
     if (n <= 16) return launch<T, 8, 2, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 24) return launch<T, 8, 3, MODE>(s, n, nrhs, A, B, X, status);
     if (n <= 32) return launch<T, 8, 4, MODE>(s, n, nrhs, A, B, X, status);
