@@ -423,6 +423,10 @@ __device__ __forceinline__ void lu_solve_block(const T (&w)[N][N], const Recip<T
 // the FP64 pipe 26 % busy.  Finished row k of the inverse overwrites row k of the factors, which nothing reads
 // any more (L row k was consumed by the forward sweep, U row k by back-substitution step k), so in the AoS
 // pipeline the result still leaves through the thread's input slot.
+// (Tried and dropped for 8x8 Double in the AoS pipeline: streaming the result rows straight to global memory so that
+// nothing aliases the factors, two passes of four columns and a 168-register cap for a third warp per scheduler -
+// 0.340 -> 0.526 ms with the cap (256 B of spills), 0.457 ms without: a thread's 32-byte row pieces 512 B apart cost
+// more than the in-place slot + coalesced tile store saves.  Float fits the cap without spilling: 0.202 -> 0.165 ms.)
 template <class T, int N>
 struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
     static constexpr bool streams_out0 = true;
@@ -448,41 +452,48 @@ struct InverseOp<T, N, std::enable_if_t<(N >= 5)>> {
                 });
             });
         }
-        // a row keeps its right-hand side through every swap, so column c of the identity starts as e_pos with the 1
-        // wherever original row c ended up
-        T x[N][N];
-        #pragma unroll
-        for (int c = 0; c < N; ++c) {
-            int pos = c;
+        // All N columns of the permuted identity at once: in the in-place AoS pipeline a finished row may only overwrite
+        // factor rows nothing reads any more, which rules out a second pass over the factors.
+        constexpr int CB = N;
+        static_for<0, (N + CB - 1) / CB>([&](auto blk_) {
+            constexpr int c0 = decltype(blk_)::value * CB;
+            constexpr int cb = (N - c0 < CB) ? N - c0 : CB;
+            // a row keeps its right-hand side through every swap, so column c of the identity starts as e_pos with the 1
+            // wherever original row c ended up
+            T x[N][cb];
             #pragma unroll
-            for (int k = 0; k < N; ++k) pos = (pos == k) ? piv[k] : ((pos == piv[k]) ? k : pos);
-            #pragma unroll
-            for (int i = 0; i < N; ++i) x[i][c] = (i == pos) ? T(1) : T(0);
-        }
-        static_for<0, N>([&](auto k_) {
-            constexpr int k = decltype(k_)::value;
-            static_for<k + 1, N>([&](auto i_) {
-                constexpr int i = decltype(i_)::value;
-                const T l = scr.template get<i * N + k>();
+            for (int c = 0; c < cb; ++c) {
+                int pos = c0 + c;
                 #pragma unroll
-                for (int c = 0; c < N; ++c) x[i][c] = x[i][c] - l * x[k][c];
-            });
-        });
-        static_for<0, N>([&](auto kk_) {
-            constexpr int k = N - 1 - decltype(kk_)::value;
-            T s[N];
-            #pragma unroll
-            for (int c = 0; c < N; ++c) s[c] = T(0);
-            static_for<k + 1, N>([&](auto j_) {
-                constexpr int j = decltype(j_)::value;
-                const T u = scr.template get<k * N + j>();
+                for (int k = 0; k < N; ++k) pos = (pos == k) ? piv[k] : ((pos == piv[k]) ? k : pos);
                 #pragma unroll
-                for (int c = 0; c < N; ++c) s[c] = s[c] + u * x[j][c];
+                for (int i = 0; i < N; ++i) x[i][c] = (i == pos) ? T(1) : T(0);
+            }
+            static_for<0, N>([&](auto k_) {
+                constexpr int k = decltype(k_)::value;
+                static_for<k + 1, N>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    const T l = scr.template get<i * N + k>();
+                    #pragma unroll
+                    for (int c = 0; c < cb; ++c) x[i][c] = x[i][c] - l * x[k][c];
+                });
             });
-            static_for<0, N>([&](auto c_) {
-                constexpr int c = decltype(c_)::value;
-                x[k][c] = rc[k].div(x[k][c] - s[c]);
-                out.template put<k * N + c>(ok ? x[k][c] : T(0));
+            static_for<0, N>([&](auto kk_) {
+                constexpr int k = N - 1 - decltype(kk_)::value;
+                T s[cb];
+                #pragma unroll
+                for (int c = 0; c < cb; ++c) s[c] = T(0);
+                static_for<k + 1, N>([&](auto j_) {
+                    constexpr int j = decltype(j_)::value;
+                    const T u = scr.template get<k * N + j>();
+                    #pragma unroll
+                    for (int c = 0; c < cb; ++c) s[c] = s[c] + u * x[j][c];
+                });
+                static_for<0, cb>([&](auto c_) {
+                    constexpr int c = decltype(c_)::value;
+                    x[k][c] = rc[k].div(x[k][c] - s[c]);
+                    out.template put<k * N + c0 + c>(ok ? x[k][c] : T(0));
+                });
             });
         });
         status[0] = ok ? 0 : 1;

@@ -130,6 +130,7 @@ struct SoaReader {
 
 template <class R>
 struct SlotWriter {
+    static constexpr bool in_place = true;          // the results replace the thread's input record in shared memory
     unsigned char* stage;
     int item;
     template <int E>
@@ -139,11 +140,13 @@ struct SlotWriter {
 };
 template <class T>
 struct SoaWriter {
+    static constexpr bool in_place = false;
     T* base;                        // row 0 of this item
     unsigned long long stride;
     template <int E>
     __device__ __forceinline__ void put(T v) const { base[(size_t)E * stride] = v; }
 };
+
 
 // Ops that park part of their working set in the thread's own (already loaded) In0 staging area declare
 // `scratch_in0` and take a fifth run_stream argument with compile-time-indexed get<E>() / put<E>(v): the thread's
