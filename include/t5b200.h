@@ -118,17 +118,24 @@ int t5_buf_layout(const t5_buf* buf);
  * reference checkout — CHANGELOG.md:24-25; specified in SURVEY.md §8a a6.)
  * Results are bit-identical to that fold for every element type and shape, with two
  * exceptions that run on the tensor cores and meet the stated tolerance instead
- * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|):
- *   Double, m and n multiples of 64 and k a multiple of 32: FP64 DMMA, tol 1e-12;
+ * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|); t5_matmul_is_exact answers for a given shape:
+ *   Double, m >= 17, n >= 24, k >= 8, n and k multiples of 8, and a 32- / 48- / 64- / 96- / 128-tiling of
+ *   the m x n result that is at least a quarter full (24 x 24 and 32 x 32 items, four to a tile, are;
+ *   72 x 72 is; 17 x 136 is not): FP64 DMMA, tol 1e-12;
  *   Float, m >= 48, n >= 64 a multiple of 32, k >= 32 a multiple of 4, and a 64- or 128-tiling
  *   of the m x n result that is at least half full (m = n = 96 is; 48 x 64 is; 200 x 32 is
  *   not): tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with the exact fold.
+ * The class depends on dtype and shape only, never on layout, batch size or device count.
  * Layout: the tile pipeline (records up to 8 x 8), outer products and contractions whose B fits
  * in shared memory read SoA directly.  Every other shape has AoS kernels only; given SoA
  * operands the library re-lays the shard out into stream-ordered AoS temporaries, runs the AoS
  * kernel and re-lays the result out (one extra read + write pass per operand).  SoA is the
  * tiny-record layout: for records of more than ~64 elements prefer AoS buffers. */
 int t5_matmul(t5_ctx* ctx, int dtype, int m, int k, int n, const t5_buf* A, const t5_buf* B, t5_buf* C);
+/* 1 when t5_matmul / t5_prod / t5_matmul_host on an (m x k).(k x n) view of this dtype is bit-identical to the
+ * fold above, 0 when it runs on the tensor cores (tolerance class above); a negated T5_ERR_* (-T5_ERR_SHAPE,
+ * -T5_ERR_UNSUPPORTED) for arguments t5_matmul would reject.  Pure: no context, no GPU. */
+int t5_matmul_is_exact(int dtype, int m, int k, int n);
 
 /* DotProduct (dot): OUT[b] = fold_{i ascending} (acc + X[b,i]*Y[b,i]).  §8a a7. */
 int t5_dot(t5_ctx* ctx, int dtype, int n, const t5_buf* X, const t5_buf* Y, t5_buf* OUT);

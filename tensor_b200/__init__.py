@@ -7,7 +7,7 @@ what the tests and bench drive.  There is no CPU implementation in this package.
 from ._lib import AOS, SOA, F64, F32, I64, U8, LibraryMissing, partition  # noqa: F401
 from .device import (Batch, Context, DeviceError, PinnedArray, TensorException,  # noqa: F401
                      Unsupported, WrongListLength)
-from .linear_algebra import (char_poly, det, dot, dot_sum, inverse, matmul, matmul_host, min_poly,  # noqa: F401
+from .linear_algebra import (char_poly, det, dot, dot_sum, inverse, matmul, matmul_host, matmul_is_exact, min_poly,  # noqa: F401
                              poly_eval, prod, pure, replicate, row_echelon_form, scale, solve, tensor_product, tr, transpose,
                              triangular_solve, unit, zip_with)
 from . import host, structure, synthetic  # noqa: F401

@@ -48,6 +48,7 @@ SIGNATURES = {
     "t5_dot": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_dot_sum": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "t5_dot_sum_used_nccl": (_i, [_vp]),
+    "t5_matmul_is_exact": (_i, [_i, _i, _i, _i]),
     "t5_prod": (_i, [_vp, _i, _i, _u64p, _i, _u64p, _i, _vp, _vp, _vp]),
     "t5_transpose": (_i, [_vp, _i, _i, _u64p, _vp, _vp]),
     "t5_det": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -472,12 +472,14 @@ static Shard shard_of(const t5_ctx* c, const t5_buf* b, int g) {
 // the host-buffer pipeline
 static int product_shard(const Shard& s, int dtype, int P, int K, int Q, int nc, const void* A, const void* B, void* C) {
     int r = T5I_NOT_SPECIALISED;
-    if (nc != 0) r = small_matmul(s, dtype, P, K, Q, A, B, C);
+    // the tensor-core kernels first: their shape rules (dmma_takes / tf32x3_takes - exactly what t5_matmul_is_exact reports)
+    // exclude everything the exact thread-per-item kernels are good at
+    if (s.layout == T5L_AOS && dtype == T5D_F64 && nc != 0) r = dmma_matmul(s, P, K, Q, A, B, C);
+    if (s.layout == T5L_AOS && dtype == T5D_F32 && nc != 0) r = tf32x3_matmul(s, P, K, Q, A, B, C);
+    if (r == T5I_NOT_SPECIALISED && nc != 0) r = small_matmul(s, dtype, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0) r = mid_matmul(s, dtype, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0 && P == 1 && Q == 1 && K > 4) r = generic_longdot(s, dtype, K, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0 && s.layout == T5L_AOS) r = generic_stagedprod(s, dtype, P, K, Q, A, B, C);
-    if (r == T5I_NOT_SPECIALISED && s.layout == T5L_AOS && dtype == T5D_F64 && nc != 0) r = dmma_matmul(s, P, K, Q, A, B, C);
-    if (r == T5I_NOT_SPECIALISED && s.layout == T5L_AOS && dtype == T5D_F32 && nc != 0) r = tf32x3_matmul(s, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0) r = exact_blocked_matmul(s, dtype, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED) r = generic_prod(s, dtype, P, K, Q, nc, A, B, C);
     return r;
@@ -548,6 +550,8 @@ static int run_shard(t5_ctx* c, int g, const t5_buf* const* ins, int nin, t5_buf
 // memory (t5_generic.cu generic_soa_prod): run the AoS kernels through the detour instead
 static bool soa_product_detours(int dtype, int P, int K, int Q, int nc) {
     if (nc == 0) return (long long)Q * 64 * 16 > 200 * 1024;
+    // tensor-core shapes behave the same in both layouts (t5_matmul_is_exact depends on dtype and shape only)
+    if ((dtype == T5_F64 && dmma_takes(P, K, Q)) || (dtype == T5_F32 && tf32x3_takes(P, K, Q))) return true;
     if (P == 1 && Q == 1) return false;                              // long dot: its own SoA-capable kernel
     const long long es = dtype == T5_F32 ? 4 : 8;
     return (long long)K * Q * 128 * es > 200 * 1024;
@@ -622,6 +626,14 @@ static bool ensure_nccl(t5_ctx* c) {
 }
 
 int t5_dot_sum_used_nccl(t5_ctx* c) { return c && c->used_nccl ? 1 : 0; }
+
+int t5_matmul_is_exact(int dtype, int m, int k, int n) {
+    if (dtype != T5_F64 && dtype != T5_F32 && dtype != T5_I64) return -T5_ERR_UNSUPPORTED;
+    if (m < 1 || k < 1 || n < 1) return -T5_ERR_SHAPE;
+    if (dtype == T5_F64) return dmma_takes(m, k, n) ? 0 : 1;
+    if (dtype == T5_F32) return tf32x3_takes(m, k, n) ? 0 : 1;
+    return 1;
+}
 
 int t5_dot_sum(t5_ctx* c, int dtype, int n, const t5_buf* X, const t5_buf* Y, void* host_scalar) {
     if (!c || !host_scalar) return T5_ERR_INVALID;

@@ -84,12 +84,14 @@ int plant_specials(const Shard& s, int dtype, int n, uint64_t swap_every, uint64
 // AoS [count][d] <-> SoA [d][stride]
 int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst);
 
-// ---- t5_dgemm.cu: FP64 tensor-core (DMMA) batched product for large squares -------
-// returns T5I_NOT_SPECIALISED unless (m,k,n) is a supported multiple-of-tile shape
+// ---- t5_dgemm.cu: FP64 tensor-core (DMMA) batched product: items from 17 x 24 up with k, n multiples of 8 -------
+// returns T5I_NOT_SPECIALISED unless dmma_takes(m, k, n); within north_star's 1e-12 Double tolerance, not bit-exact
+bool dmma_takes(int m, int k, int n, int* geo_out = nullptr);
 int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
 
 // ---- t5_tf32x3.cu: Float products on tcgen05 tensor cores (3xTF32 split, TMEM accumulators) for shapes
 // on the 128 x 128 x 32 tile grid; within north_star's 1e-5 Float tolerance, not bit-exact
+bool tf32x3_takes(int m, int k, int n, bool* big_out = nullptr);
 int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
 
 // ---- t5_rowelim.cu: row-per-lane (8 lanes per matrix, warp shuffles) elimination for 5 <= n <= 8 -----

@@ -331,16 +331,23 @@ static inline double tf_waste(int m, int n, int T) {
     return (double)((m + T - 1) / T * T) * (double)((n + T - 1) / T * T) / ((double)m * n);
 }
 
+// Shape rule of the tcgen05 Float product (also what t5_matmul_is_exact reports); *big = the 128 x 128 geometry.
+// TMA: row pitches must be whole 16-byte units (k % 4), B is viewed in 32-column blocks (n % 32); m is free.
+// Items of at least 48 x 64 x 32: smaller ones are served better by the exact kernels.
+// The tensor pipe is ~1/3 busy on full tiles (the kernel is HBM-bound), so up to 2x padded tile area is affordable;
+// between the two geometries the one with less padding wins, the larger tile on a tie (operands read once).
+bool tf32x3_takes(int m, int k, int n, bool* big_out) {
+    if (n % 32 || k % 4 || k < tf::BK || m < 48 || n < 64) return false;
+    const double w128 = tf_waste(m, n, 128), w64 = tf_waste(m, n, 64);
+    if (w128 > 2.0 && w64 > 2.0) return false;
+    if (big_out) *big_out = w128 <= w64 * 1.3;
+    return true;
+}
+
 int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    // TMA: row pitches must be whole 16-byte units (k % 4), B is viewed in 32-column blocks (n % 32); m is free.
-    // Items of at least 48 x 64 x 32: smaller ones are served better by the exact kernels before this one in the chain.
-    if (n % 32 || k % 4 || k < tf::BK || m < 48 || n < 64) return T5I_NOT_SPECIALISED;
-    // the tensor pipe is ~1/3 busy on full tiles (the kernel is HBM-bound), so up to 2x padded tile area is affordable;
-    // between the two geometries the one with less padding wins, the larger tile on a tie (operands read once)
-    const double w128 = tf_waste(m, n, 128), w64 = tf_waste(m, n, 64);
-    if (w128 > 2.0 && w64 > 2.0) return T5I_NOT_SPECIALISED;
-    const bool big = w128 <= w64 * 1.3;
+    bool big = false;
+    if (!tf32x3_takes(m, k, n, &big)) return T5I_NOT_SPECIALISED;
     static std::atomic<bool> configured[T5_MAX_DEVICES];   // zero-initialised; entries of different contexts / pipeline threads may race here (idempotent work)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;

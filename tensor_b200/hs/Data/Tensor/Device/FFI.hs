@@ -67,6 +67,7 @@ foreign import ccall safe "t5_dot"
 foreign import ccall safe "t5_dot_sum"
   c_dot_sum :: Ptr Ctx -> CInt -> CInt -> Ptr Buf -> Ptr Buf -> Ptr () -> IO CInt
 foreign import ccall safe "t5_dot_sum_used_nccl" c_dot_sum_used_nccl :: Ptr Ctx -> IO CInt
+foreign import ccall safe "t5_matmul_is_exact" c_matmul_is_exact :: CInt -> CInt -> CInt -> CInt -> IO CInt
 foreign import ccall safe "t5_prod"
   c_prod :: Ptr Ctx -> CInt -> CInt -> Ptr Word64 -> CInt -> Ptr Word64 -> CInt
          -> Ptr Buf -> Ptr Buf -> Ptr Buf -> IO CInt

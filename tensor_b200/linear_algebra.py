@@ -53,6 +53,15 @@ def matmul(a: Batch, b: Batch) -> Batch:
     return out
 
 
+def matmul_is_exact(dtype: int, m: int, k: int, n: int) -> bool:
+    """True when ``(m x k) .*. (k x n)`` of this element type is bit-identical to the sequential fold, False when the
+    library runs it on the tensor cores (Double: |delta| <= 1e-12 sum|a||b|, Float: 1e-5; include/t5b200.h t5_matmul)."""
+    r = _lib.lib().t5_matmul_is_exact(dtype, m, k, n)
+    if r < 0:
+        check(-r, None)
+    return bool(r)
+
+
 def dot(x: Batch, y: Batch) -> Batch:
     """``dot``: one scalar per pair (§8a a7)."""
     ctx = _same_ctx(x, y)

@@ -106,8 +106,31 @@ def test_haskell_ffi_module_binds_every_declared_symbol():
     helpers = {"t5_timer_begin", "t5_timer_end", "t5_timer_per_device", "t5_flush_l2", "t5_fill_synthetic", "t5_plant_specials",
                "t5_launch_count", "t5_version", "t5_strerror", "t5_sync", "t5_free", "t5_partition", "t5_relayout",
                "t5_pinned_alloc", "t5_pinned_free", "t5_buf_batch", "t5_buf_elems", "t5_buf_dtype", "t5_buf_layout",
-               "t5_dot_sum_used_nccl", "t5_structural_table"}
+               "t5_dot_sum_used_nccl", "t5_structural_table", "t5_matmul_is_exact"}
     for n in declared_symbols():
         if n in helpers:
             continue
         assert "c_" + n[3:] in used, f"no Haskell caller for {n}"
+
+
+def test_matmul_is_exact_reports_the_tensor_core_shape_rules():
+    """Pure shape logic behind include/t5b200.h's t5_matmul contract (no GPU): which products are the bit-exact fold."""
+    import tensor_b200 as tb
+    ex = tb.matmul_is_exact
+    for dt in (tb.F64, tb.F32, tb.I64):
+        for mkn in ((3, 3, 3), (4, 4, 4), (8, 8, 8), (16, 16, 16), (4, 4, 1), (1, 64, 1), (20, 20, 20), (65, 17, 63)):
+            assert ex(dt, *mkn), (dt, mkn)
+    for mkn in ((128, 128, 128), (64, 64, 64), (32, 32, 32), (24, 24, 24), (48, 48, 48), (96, 96, 96), (17, 8, 24), (72, 72, 72)):
+        assert not ex(tb.F64, *mkn), mkn
+        assert ex(tb.I64, *mkn), mkn
+    for mkn in ((16, 32, 32), (32, 32, 16), (32, 12, 32), (32, 32, 20), (17, 32, 136), (8, 64, 64)):
+        assert ex(tb.F64, *mkn), mkn
+    for mkn in ((128, 128, 128), (64, 64, 64), (96, 96, 96), (48, 32, 64)):
+        assert not ex(tb.F32, *mkn), mkn
+    for mkn in ((32, 32, 32), (48, 48, 48), (200, 32, 32), (64, 30, 64)):
+        assert ex(tb.F32, *mkn), mkn
+    import pytest
+    with pytest.raises(tb.WrongListLength):
+        ex(tb.F64, 0, 3, 3)
+    with pytest.raises(tb.Unsupported):
+        ex(tb.U8, 3, 3, 3)

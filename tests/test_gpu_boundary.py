@@ -93,8 +93,7 @@ def test_soa_large_items_take_the_aos_kernels(ctx, dt):
         soa = tb.matmul(ctx.from_numpy(a, (m, k), tb.SOA), ctx.from_numpy(b, (k, n), tb.SOA))
         assert soa.layout == tb.SOA
         assert np.array_equal(bits(soa.to_numpy()), bits(aos)), (m, k, n)
-        tensor_core = dt != np.int64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0
-        if not tensor_core:
+        if tb.matmul_is_exact(code, m, k, n):
             assert np.array_equal(bits(aos), bits(oracle.matmul(a, b, m, k, n, threads=8))), (m, k, n)
 
 

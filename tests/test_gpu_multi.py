@@ -142,11 +142,16 @@ def test_soa_dot_sum_and_detour_multi_device(mctx):
     x = oracle.fill(oracle.I64, oracle.SEED_A, 53, batch * 4)
     y = oracle.fill(oracle.I64, oracle.SEED_B, 53, batch * 4)
     assert tb.dot_sum(mctx.from_numpy(x, (4,), tb.SOA), mctx.from_numpy(y, (4,), tb.SOA)) == oracle.dot_sum(x, y, 4)
-    m = 32
-    a = oracle.fill(oracle.F64, oracle.SEED_A, 54, 999 * m * m)
-    b = oracle.fill(oracle.F64, oracle.SEED_B, 54, 999 * m * m)
+    m = 32                                                            # Int64: the detour's kernel is the exact blocked product
+    a = oracle.fill(oracle.I64, oracle.SEED_A, 54, 999 * m * m)
+    b = oracle.fill(oracle.I64, oracle.SEED_B, 54, 999 * m * m)
     got = tb.matmul(mctx.from_numpy(a, (m, m), tb.SOA), mctx.from_numpy(b, (m, m), tb.SOA))
     assert np.array_equal(bits(got.to_numpy()), bits(oracle.matmul(a, b, m, m, m, threads=8)))
+    ad = oracle.fill(oracle.F64, oracle.SEED_A, 54, 999 * m * m)      # Double 32 x 32: four items to a DMMA tile on every device
+    bd = oracle.fill(oracle.F64, oracle.SEED_B, 54, 999 * m * m)
+    got = tb.matmul(mctx.from_numpy(ad, (m, m), tb.SOA), mctx.from_numpy(bd, (m, m), tb.SOA)).to_numpy().reshape(999, m, m)
+    want = oracle.matmul(ad, bd, m, m, m, threads=8).reshape(999, m, m)
+    assert np.all(np.abs(got - want) <= 1e-12 * np.einsum("bij,bjk->bik", np.abs(ad.reshape(999, m, m)), np.abs(bd.reshape(999, m, m))))
 
 
 def test_multi_device_buffers_may_outlive_shutdown():

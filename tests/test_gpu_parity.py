@@ -11,6 +11,7 @@ import pytest
 
 import oracle
 import tensor_b200 as tb
+from _parity import assert_matmul_matches, matmul_is_exact
 
 pytestmark = pytest.mark.gpu
 
@@ -58,7 +59,8 @@ def test_matmul_bit_exact(ctx, dc, mkn, layout):
         C = tb.matmul(A, B)                  # SoA: the tile kernels where they exist, the thread-per-item SoA contraction otherwise
         assert C.layout == layout
         assert C.shape == (m, n)
-        assert_bits_equal(C.to_numpy(), oracle.matmul(a, b, m, k, n), f"matmul {mkn} dt{dc} batch{batch}")
+        # bit-exact, except the Double shapes the FP64 tensor pipe takes (24^3, 32^3, 48^3 here): stated tolerance
+        assert_matmul_matches(C.to_numpy(), a, b, m, k, n, dc, f"matmul {mkn} dt{dc} batch{batch}")
 
 
 @pytest.mark.parametrize("batch", RAGGED)
@@ -633,10 +635,19 @@ def test_full_size_float128_tcgen05_properties(ctx):
 
 # ---- FP64 tensor-core (DMMA) product: tolerance stated by north_star -------------------
 @pytest.mark.parametrize("mkn", [(128, 128, 128), (128, 64, 128), (256, 32, 128), (128, 96, 256),
-                                 (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64)])
+                                 (64, 64, 64), (64, 32, 192), (192, 96, 64), (128, 160, 64),
+                                 # ragged against the 128 / 64 tiles and the 32-deep K chunks (round 2: the item is a tensor-map
+                                 # dimension, so the missing rows / columns / k-slices of a box arrive as zeros)
+                                 (96, 96, 96), (100, 64, 104), (48, 32, 56), (130, 40, 160), (65, 128, 64), (200, 104, 96),
+                                 (127, 48, 224), (257, 32, 64),
+                                 # items of at most 32 x 32 (four to a tile) and 48 x 48 (two to a tile), the 96 tile, K tails
+                                 # of 8 / 16 / 24 (skipped k-steps), K shorter than one chunk
+                                 (32, 32, 32), (24, 24, 24), (17, 8, 24), (25, 40, 32), (32, 16, 32), (31, 56, 24),
+                                 (48, 48, 48), (40, 40, 40), (33, 24, 48), (72, 72, 72), (80, 88, 80), (160, 48, 160), (192, 72, 96)])
 def test_dmma_matmul_within_tolerance(ctx, mkn):
     m, k, n = mkn
-    for batch in (1, 7, 150):     # 150 tiles > 148 SMs: every CTA takes work, some take two
+    assert not matmul_is_exact(oracle.F64, m, k, n)
+    for batch in (1, 2, 3, 7, 150, 601):     # > 148 tiles: every CTA takes work, some take two; 1 / 2 / 3 / 7: part-filled item tiles
         a, b = inputs(oracle.F64, 15, batch, m * k, k * n)
         C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
         want = oracle.matmul(a, b, m, k, n, threads=8)
@@ -653,8 +664,8 @@ def test_mid_size_matmul_generic_is_bit_exact(ctx):
             batch = 9
             a, b = inputs(dc, 16, batch, m * k, k * n)
             C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
-            if dc != oracle.I64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
-                continue        # Double / Float 64-multiples take the tensor-core paths (tolerance tests)
+            if not matmul_is_exact(dc, m, k, n):
+                continue        # tensor-core shapes (tolerance tests)
             assert_bits_equal(C, oracle.matmul(a, b, m, k, n), f"generic {m}x{k}x{n}")
 
 
@@ -664,10 +675,8 @@ def test_mid_size_matmul_generic_is_bit_exact(ctx):
                                  (16, 16, 17), (200, 9, 40), (24, 31, 130), (48, 48, 48), (1, 64, 300), (300, 64, 1)])
 def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
     m, k, n = mkn
-    if dc == oracle.F64 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
-        pytest.skip("Double 64-multiples take the tensor-core path")
-    if dc == oracle.F32 and m % 64 == 0 and n % 64 == 0 and k % 32 == 0:
-        pytest.skip("Float 64-multiples take the tcgen05 3xTF32 path (tolerance test below)")
+    if not matmul_is_exact(dc, m, k, n):
+        pytest.skip("this shape takes a tensor-core path for this element type (tolerance tests)")
     for batch in (1, 5, 37):
         a, b = inputs(dc, 21, batch, m * k, k * n)
         C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
@@ -747,7 +756,8 @@ def test_tf32x3_identity_and_specials(ctx, n):
 def test_exact_blocked_matmul_specials_and_k_tail(ctx):
     """inf / nan / signed zeros in the operands and a K that is not a multiple of the chunk: the K
     tail must be a loop bound, not zero padding (0 * inf would poison sums the oracle never forms)."""
-    m, k, n, batch = 40, 19, 24, 3
+    m, k, n, batch = 40, 19, 24, 3           # (k = 19: no tensor-core kernel takes it)
+    assert matmul_is_exact(oracle.F64, m, k, n) and matmul_is_exact(oracle.F32, m, k, n)
     rng = np.random.default_rng(5)
     a = rng.standard_normal(batch * m * k)
     b = rng.standard_normal(batch * k * n)
@@ -764,6 +774,27 @@ def test_exact_blocked_matmul_specials_and_k_tail(ctx):
     af, bf = a.astype(np.float32), b.astype(np.float32)
     Cf = tb.matmul(ctx.from_numpy(af, (m, k)), ctx.from_numpy(bf, (k, n))).to_numpy()
     same(Cf.ravel(), oracle.matmul(af, bf, m, k, n).ravel(), "specials f32")
+
+
+def test_dmma_ragged_neighbours_and_specials(ctx):
+    """A ragged Double shape (96 x 104 . 104 x 96: one 128-tile, K tail of 8): neighbouring items of very different
+    magnitude (a box that read its neighbour's rows instead of zeros would show at once) and inf / NaN operands, which
+    the FP64 tensor pipe propagates like the sequential fold does (same inf / NaN pattern as the oracle)."""
+    m, k, n, batch = 96, 104, 96, 6
+    a, b = inputs(oracle.F64, 26, batch, m * k, k * n)
+    a = a.copy(); b = b.copy()
+    a[1 * m * k: 2 * m * k] *= 1e200
+    a[2 * m * k: 3 * m * k] *= 1e-200
+    a[4 * m * k + 5] = np.inf
+    b[5 * k * n + 77] = np.nan
+    C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy().reshape(batch, m, n)
+    want = oracle.matmul(a, b, m, k, n).reshape(batch, m, n)
+    for item in (4, 5):
+        assert np.array_equal(np.isnan(C[item]), np.isnan(want[item])), item
+        assert np.array_equal(np.isinf(C[item]), np.isinf(want[item])), item
+    a3, b3 = np.abs(a.reshape(batch, m, k)), np.abs(b.reshape(batch, k, n))
+    for item in (0, 1, 2, 3):
+        assert np.all(np.abs(C[item] - want[item]) <= 1e-12 * (a3[item] @ b3[item])), item
 
 
 def test_dmma_identity_and_linearity(ctx):
