@@ -124,7 +124,8 @@ int t5_buf_layout(const t5_buf* buf);
  *   72 x 72 is; 17 x 136 is not): FP64 DMMA, tol 1e-12;
  *   Float, m >= 48, n >= 64 a multiple of 32, k >= 32 a multiple of 4, and a 64- or 128-tiling
  *   of the m x n result that is at least half full (m = n = 96 is; 48 x 64 is; 200 x 32 is
- *   not): tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with the exact fold.
+ *   not), or 17 <= m <= 32 with n = 32 and k >= 8 a multiple of 4 (four items to a tile):
+ *   tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with the exact fold.
  * The class depends on dtype and shape only, never on layout, batch size or device count.
  * Layout: the tile pipeline (records up to 8 x 8), outer products and contractions whose B fits
  * in shared memory read SoA directly.  Every other shape has AoS kernels only; given SoA

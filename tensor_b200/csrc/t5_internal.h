@@ -91,7 +91,7 @@ int dmma_matmul(const Shard& s, int m, int k, int n, const void* A, const void* 
 
 // ---- t5_tf32x3.cu: Float products on tcgen05 tensor cores (3xTF32 split, TMEM accumulators) for shapes
 // on the 128 x 128 x 32 tile grid; within north_star's 1e-5 Float tolerance, not bit-exact
-bool tf32x3_takes(int m, int k, int n, bool* big_out = nullptr);
+bool tf32x3_takes(int m, int k, int n, int* geo_out = nullptr);
 int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C);
 
 // ---- t5_rowelim.cu: row-per-lane (8 lanes per matrix, warp shuffles) elimination for 5 <= n <= 8 -----

@@ -37,9 +37,15 @@ constexpr int EPI_PITCH = 36 * 4;                                   // staging r
 constexpr int EPI_WARP = 32 * EPI_PITCH;                            // one (<= 32) x 32 block per epilogue warp
 
 // Square tiles of 128 (3 stages of 64 KB) or 64 (6 stages of 16 KB) - the UMMA shapes M = N = 128 / 64.
-template <int TILE_, int STAGES_>
+// ITEMS = 4 (round 2): items of at most 32 rows and exactly 32 columns, FOUR to a 128 x 128 tile.  The tensor maps carry
+// the item as a dimension, so one box {32 k, 32 rows, 4 items} lands as the A image of a 128-row tile (item q = rows
+// 32q..32q+31) and one box {32, 32 k-rows, 1 block, 4 items} as the B image of a 128-column tile (item q = column block
+// q): the MMA stream is the 128 tile's, and only the four diagonal 32 x 32 blocks of the accumulator are read back.
+// Per byte of HBM traffic that is exactly the tensor / split / epilogue work of a 128^3 item (one K chunk per 48 KB).
+template <int TILE_, int STAGES_, int ITEMS_ = 1>
 struct Geo {
-    static constexpr int BM = TILE_, BN = TILE_, STAGES = STAGES_;
+    static constexpr int BM = TILE_, BN = TILE_, STAGES = STAGES_, ITEMS = ITEMS_;
+    static_assert(ITEMS == 1 || (ITEMS == 4 && TILE_ == 128), "item packing: four 32-row items on the 128 tile");
     static constexpr int TILE_A = BM * BK * 4, TILE_B = BK * BN * 4;
     static constexpr int STAGE = 2 * (TILE_A + TILE_B);             // hi + lo tiles
     static constexpr int SMEM = STAGES * STAGE + 1024 + 4 * EPI_WARP;
@@ -52,6 +58,7 @@ struct Geo {
 };
 using Geo128 = Geo<128, 3>;
 using Geo64 = Geo<64, 6>;
+using Geo32x4 = Geo<128, 3, 4>;
 
 constexpr float FLT_MAX_F = 3.4028234664e38f;
 
@@ -96,7 +103,7 @@ template <class G>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Args p) {
     constexpr int BM = G::BM, BN = G::BN, STAGES = G::STAGES, TILE_A = G::TILE_A, TILE_B = G::TILE_B, STAGE = G::STAGE;
-    constexpr int TMEM_COLS = G::TMEM_COLS, RPW = G::ROWS_PER_WARP;
+    constexpr int TMEM_COLS = G::TMEM_COLS, RPW = G::ROWS_PER_WARP, ITEMS = G::ITEMS;
     constexpr unsigned IDESC = G::IDESC;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bars[3 * STAGES + 4];   // full, conv, empty, tmem_full[2], tmem_empty[2]
@@ -119,8 +126,8 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     // beyond an item's M rows, N columns or K depth is out of bounds for TMA and arrives as ZEROS (never the next item's
     // data); zero rows / columns / k-slices add nothing, and the epilogue stores only what exists
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN, kch = (p.K + BK - 1) / BK;
-    const unsigned long long tiles_per_item = (unsigned long long)tiles_m * tiles_n;
-    const unsigned long long n_tiles = p.count * tiles_per_item;
+    const unsigned long long tiles_per_item = (unsigned long long)tiles_m * tiles_n;      // 1 when ITEMS > 1 (host checks)
+    const unsigned long long n_tiles = ITEMS > 1 ? (p.count + ITEMS - 1) / ITEMS : p.count * tiles_per_item;
 
     if (tid < 8) special_tile[tid] = 0;
     if (tid == 0) {
@@ -150,8 +157,8 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (lane == 0) {
             unsigned it = 0;
             for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const unsigned long long item = tile / tiles_per_item;
-                const int rem = (int)(tile - item * tiles_per_item);
+                const unsigned long long item = ITEMS > 1 ? tile * ITEMS : tile / tiles_per_item;   // (items past the batch: zeros)
+                const int rem = ITEMS > 1 ? 0 : (int)(tile - item * tiles_per_item);
                 const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
                 for (int kc = 0; kc < kch; ++kc, ++it) {
                     const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
@@ -179,6 +186,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     const unsigned a_lo = b_hi + TILE_B, b_lo = a_lo + TILE_A;
                     #pragma unroll
                     for (int k8 = 0; k8 < BK / 8; ++k8) {
+                        if (k8 && kc * BK + k8 * 8 >= p.K) break;           // K tail: nothing but zeros beyond
                         // A (K-major): 32 bytes further along the 128-byte swizzled rows; 8-row groups 1024 B apart
                         const unsigned long long da_hi = umma_desc(a_hi + k8 * 32, 1, 64, 2);
                         const unsigned long long da_lo = umma_desc(a_lo + k8 * 32, 1, 64, 2);
@@ -227,18 +235,19 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         unsigned tl = 0;
         for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             const unsigned acc = tl & 1;
-            const unsigned long long item = tile / tiles_per_item;
-            const int rem = (int)(tile - item * tiles_per_item);
+            const unsigned long long item = ITEMS > 1 ? tile * ITEMS + q : tile / tiles_per_item;   // packed: warp q = item q of the tile
+            const int rem = ITEMS > 1 ? 0 : (int)(tile - item * tiles_per_item);
             const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
             mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
             tc_fence_after();
-            float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)(tm * BM + q * RPW) * p.N + tn * BN;   // this warp's rows
+            const int row_base = ITEMS > 1 ? 0 : tm * BM + q * RPW;           // first row (within the item) of this warp's block
+            float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)row_base * p.N + tn * BN;   // this warp's rows
             float* crow = cblk + (size_t)lane * p.N;
-            const int rows_here = p.M - (tm * BM + q * RPW);                  // rows of this warp's block that exist (may be <= 0)
+            const int rows_here = (ITEMS > 1 && item >= p.count) ? 0 : p.M - row_base;   // rows of this warp's block that exist (may be <= 0)
             const int cols_here = p.N - tn * BN;                              // columns of the tile that exist (multiple of 32)
             if (*(volatile unsigned*)&special_tile[tl & 7] == tl + 1) {
                 // exact sequential fold for this thread's row (multiply, round, add, round; k ascending)
-                const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(tm * BM + q * RPW + lane) * p.K;
+                const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(row_base + lane) * p.K;
                 const float* bcol = p.B + item * (size_t)p.K * p.N + tn * BN;
                 for (int j = 0; j < BN && j < cols_here && lane < RPW && lane < rows_here; ++j) {
                     float acc_x = 0.0f;
@@ -251,10 +260,11 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 continue;
             }
             #pragma unroll
-            for (int cc = 0; cc < BN / 32; ++cc) {
-                if (cc * 32 >= cols_here) break;                              // (warp-uniform)
-                unsigned r[32];
-                const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + cc * 32;
+            for (int cb = 0; cb < (ITEMS > 1 ? 1 : BN / 32); ++cb) {
+                if (cb * 32 >= cols_here) break;                              // (warp-uniform)
+                const int cc = ITEMS > 1 ? 0 : cb;                            // column block of C; packed: the item's only one,
+                unsigned r[32];                                               // found in the DIAGONAL block q of the accumulator
+                const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + (ITEMS > 1 ? q : cb) * 32;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -304,7 +314,7 @@ static int launch(const Shard& s, int m, int k, int n, const float* A, const flo
     {   // A: {k, m, count} floats, box 32 floats x BM rows x 1 item, K-major.  Rows >= m / depth >= k: zero fill.
         const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)m, (cuuint64_t)s.count};
         const cuuint64_t strides[2] = {(cuuint64_t)k * 4, (cuuint64_t)m * k * 4};
-        const cuuint32_t box[3] = {BK, BM, 1}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {BK, G::ITEMS > 1 ? 32u : (cuuint32_t)BM, (cuuint32_t)G::ITEMS}, estr[3] = {1, 1, 1};
         if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
@@ -312,12 +322,13 @@ static int launch(const Shard& s, int m, int k, int n, const float* A, const flo
     {   // B: [k rows][n] floats per item viewed as {32, k, n/32, count}; box {32, 32 k-rows, BN/32 column blocks, 1 item}
         const cuuint64_t dims[4] = {32, (cuuint64_t)k, (cuuint64_t)(n / 32), (cuuint64_t)s.count};
         const cuuint64_t strides[3] = {(cuuint64_t)n * 4, 128, (cuuint64_t)k * n * 4};
-        const cuuint32_t box[4] = {32, BK, BN / 32, 1}, estr[4] = {1, 1, 1, 1};
+        const cuuint32_t box[4] = {32, BK, G::ITEMS > 1 ? 1u : (cuuint32_t)(BN / 32), (cuuint32_t)G::ITEMS}, estr[4] = {1, 1, 1, 1};
         if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(B), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
     }
-    const unsigned long long tiles = (unsigned long long)s.count * ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+    const unsigned long long tiles = G::ITEMS > 1 ? ((unsigned long long)s.count + G::ITEMS - 1) / G::ITEMS
+                                                  : (unsigned long long)s.count * ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
     Args a{A, B, C, m, n, k, (unsigned long long)s.count};
     tf32x3_kernel<G><<<grid, THREADS, G::SMEM, s.stream>>>(ma, mb, a);
@@ -331,36 +342,40 @@ static inline double tf_waste(int m, int n, int T) {
     return (double)((m + T - 1) / T * T) * (double)((n + T - 1) / T * T) / ((double)m * n);
 }
 
-// Shape rule of the tcgen05 Float product (also what t5_matmul_is_exact reports); *big = the 128 x 128 geometry.
+// Shape rule of the tcgen05 Float product (also what t5_matmul_is_exact reports); *geo = tile edge (32: four items per tile).
 // TMA: row pitches must be whole 16-byte units (k % 4), B is viewed in 32-column blocks (n % 32); m is free.
 // Items of at least 48 x 64 x 32: smaller ones are served better by the exact kernels.
 // The tensor pipe is ~1/3 busy on full tiles (the kernel is HBM-bound), so up to 2x padded tile area is affordable;
 // between the two geometries the one with less padding wins, the larger tile on a tie (operands read once).
-bool tf32x3_takes(int m, int k, int n, bool* big_out) {
+// Items of 17..32 rows and exactly 32 columns (k >= 8) go four to a 128 tile (*geo = 32).
+bool tf32x3_takes(int m, int k, int n, int* geo_out) {
+    if (n == 32 && m >= 17 && m <= 32 && k % 4 == 0 && k >= 8) { if (geo_out) *geo_out = 32; return true; }
     if (n % 32 || k % 4 || k < tf::BK || m < 48 || n < 64) return false;
     const double w128 = tf_waste(m, n, 128), w64 = tf_waste(m, n, 64);
     if (w128 > 2.0 && w64 > 2.0) return false;
-    if (big_out) *big_out = w128 <= w64 * 1.3;
+    if (geo_out) *geo_out = w128 <= w64 * 1.3 ? 128 : 64;
     return true;
 }
 
 int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    bool big = false;
-    if (!tf32x3_takes(m, k, n, &big)) return T5I_NOT_SPECIALISED;
+    int geo = 0;
+    if (!tf32x3_takes(m, k, n, &geo)) return T5I_NOT_SPECIALISED;
     static std::atomic<bool> configured[T5_MAX_DEVICES];   // zero-initialised; entries of different contexts / pipeline threads may race here (idempotent work)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
     if (!configured[dev]) {
         if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo128::SMEM) != cudaSuccess) return T5I_CUDA;
         if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo64::SMEM) != cudaSuccess) return T5I_CUDA;
+        if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo32x4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo32x4::SMEM) != cudaSuccess) return T5I_CUDA;
         configured[dev] = true;
     }
     if (s.count == 0) return T5I_OK;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
-    return big ? tf::launch<tf::Geo128>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms)
+    if (geo == 32) return tf::launch<tf::Geo32x4>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
+    return geo == 128 ? tf::launch<tf::Geo128>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms)
                : tf::launch<tf::Geo64>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
 }
 

@@ -689,10 +689,13 @@ def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
                                  # ragged against the 128 / 64 tiles and the 32-deep K chunks: the tensor maps carry the item as
                                  # a dimension, so the missing rows / columns / k-slices of a box arrive as zeros
                                  (96, 96, 96), (100, 64, 96), (48, 32, 64), (130, 36, 160), (65, 128, 64), (200, 100, 96),
-                                 (127, 44, 224), (257, 32, 64)])
+                                 (127, 44, 224), (257, 32, 64),
+                                 # items of at most 32 x 32, four to a 128 tile (diagonal accumulator blocks), short and ragged K
+                                 (32, 32, 32), (17, 8, 32), (25, 44, 32), (32, 64, 32), (31, 12, 32)])
 def test_tf32x3_matmul_within_tolerance(ctx, mkn):
     m, k, n = mkn
-    for batch in (1, 7, 150, 301):          # > 148 tiles: every CTA works, some take several tiles (both TMEM accumulators)
+    assert not matmul_is_exact(oracle.F32, m, k, n)
+    for batch in (1, 2, 3, 7, 150, 301, 1201):          # > 148 tiles: every CTA works, some take several tiles (both TMEM accumulators)
         a, b = inputs(oracle.F32, 22, batch, m * k, k * n)
         C = tb.matmul(ctx.from_numpy(a, (m, k)), ctx.from_numpy(b, (k, n))).to_numpy()
         a3 = a.reshape(batch, m, k).astype(np.float64)
@@ -705,11 +708,14 @@ def test_tf32x3_matmul_within_tolerance(ctx, mkn):
         assert np.max(err / bound) < 0.5
 
 
-def test_tf32x3_ragged_specials_and_neighbours(ctx):
-    """A ragged shape (96 x 100 . 100 x 96: one 128-tile, K tail of 4): items with inf / NaN are recomputed exactly,
-    and the zero-filled part of a box must really be zeros - an item of huge values next to an item of tiny ones
-    would show up at once if a box ever read its neighbour's rows."""
-    m, k, n, batch = 96, 100, 96, 6
+@pytest.mark.parametrize("mkn", [(96, 100, 96), (30, 20, 32)])
+def test_tf32x3_ragged_specials_and_neighbours(ctx, mkn):
+    """A ragged shape (96 x 100 . 100 x 96: one 128-tile, K tail of 4) and a packed one (30 x 20 . 20 x 32: four items to
+    a tile, the last tile half empty): items with inf / NaN are recomputed exactly, and the zero-filled part of a box
+    must really be zeros - an item of huge values next to an item of tiny ones would show up at once if a box ever read
+    its neighbour's rows (or, packed, if an epilogue warp read an off-diagonal accumulator block)."""
+    (m, k, n), batch = mkn, 6
+    assert not matmul_is_exact(oracle.F32, m, k, n)
     a, b = inputs(oracle.F32, 25, batch, m * k, k * n)
     a = a.copy(); b = b.copy()
     a[1 * m * k: 2 * m * k] *= np.float32(1e30)                 # neighbours of very different magnitude
