@@ -59,6 +59,14 @@ struct Args {
     unsigned group_smem;    // shared-memory bytes of one group (a CTA holds G groups)
 };
 
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
 // CTA-uniform dispatch on a tile index: fn(std::integral_constant<int, A>) with A == a_rt
 template <int NB, int A = 0, class F>
 __device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
@@ -72,7 +80,7 @@ __device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
 // G groups of TG x TG threads per CTA, one matrix per group.  Groups never interact: each has its own slice of shared
 // memory and its own barrier - the CTA barrier when the CTA is one group, a masked __syncwarp when a group is part of a
 // warp (TG = 4: two matrices per warp, every warp independent of the others - no CTA-wide barrier anywhere).
-template <class T, int TG, int NB, int MODE, int G>
+template <class T, int TG, int NB, int MODE, int G, bool ONEDIV>
 __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
     constexpr int THREADS = TG * TG;                   // threads of ONE group
     constexpr int NMAX = TG * NB;
@@ -80,14 +88,16 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
     extern __shared__ __align__(16) unsigned char smem_all[];
     const int gid = threadIdx.x / THREADS;
     unsigned char* smem_raw = smem_all + (size_t)gid * p.group_smem;
-    const unsigned gmask = THREADS >= 32 ? 0xffffffffu : (((1u << THREADS) - 1u) << ((threadIdx.x & 31) / THREADS * THREADS));
+    // (the groups of a warp run in lockstep - same n, same trip counts, the pivot slow path entered warp-wide - so a group
+    // barrier is the plain full-mask __syncwarp; a run-time member mask costs MATCH / REDUX / VOTE per barrier)
     auto group_sync = [&]() {
-        if constexpr (THREADS >= 32) __syncthreads(); else __syncwarp(gmask);
+        if constexpr (THREADS >= 32) __syncthreads(); else __syncwarp();
     };
     T* prow = reinterpret_cast<T*>(smem_raw);          // [2][NMAX]   published pivot row (double-buffered)
     T* fcol = prow + 2 * NMAX;                          // [2][NMAX]   published raw column of the step (the numerators of the multipliers)
     T* xrow = fcol + 2 * NMAX;                          // [2][NMAX]   row exchange for swaps
-    int* perm = reinterpret_cast<int*>(xrow + 2 * NMAX);   // [NMAX] row i of the permuted system = row perm[i] of the input
+    T* fmul = xrow + 2 * NMAX;                          // [NMAX]      (ONEDIV) multipliers f(i, k) of the current step, one division per thread
+    int* perm = reinterpret_cast<int*>(fmul + NMAX);    // [NMAX] row i of the permuted system = row perm[i] of the input
     int* ctl = perm + NMAX;                             // [4] pivot search result, swap count
     T* LU = reinterpret_cast<T*>(ctl + 4);              // [n][ldl]  (MODE != 0): U on and above the diagonal, multipliers below
     T* Y = LU + (MODE != 0 ? (size_t)p.n * p.ldl : 0);  // [n][ldy]  (MODE != 0)
@@ -98,7 +108,10 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
     // number of this thread's tile rows / columns that lie inside the matrix
     const int a_end = ty < n ? (n - ty + TG - 1) / TG : 0;
 
-    for (unsigned long long item = (unsigned long long)blockIdx.x * G + gid; item < p.count; item += (unsigned long long)gridDim.x * G) {
+    // (groups of one warp stay in lockstep: a group past the end of the batch recomputes the last item and stores nothing)
+    for (unsigned long long base = (unsigned long long)blockIdx.x * G; base < p.count; base += (unsigned long long)gridDim.x * G) {
+        const bool live = base + gid < p.count;
+        const unsigned long long item = live ? base + gid : p.count - 1;
         // ---- load: thread (ty, tx) takes A[ty + TG a][tx + TG b]; TG consecutive threads read TG consecutive elements
         T w[NB][NB];
         const T* a_item = gA + item * (unsigned long long)n * n;
@@ -120,120 +133,156 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
         // the pivot's reciprocal hoisted, t5_recip.cuh: bit-identical to `/`) - redundantly across the TG threads of a
         // thread-row, but in parallel, instead of TG owner threads dividing while the other 15/16 of the CTA wait at a
         // second barrier - updates its tile, and the owners of row / column k + 1 publish them for the next step.
-        auto publish = [&](int k1) {                    // row k1 and column k1 of the CURRENT registers -> buffer k1 & 1
-            const int r1 = k1 % TG, a1 = k1 / TG;
-            T* pr1 = prow + (k1 & 1) * NMAX;
-            T* cr1 = fcol + (k1 & 1) * NMAX;
-            if (ty == r1)
-                with_tile_index<NB>(a1, [&](auto A_) {
-                    constexpr int A = decltype(A_)::value;
+        // Row k1 and column k1 of the CURRENT registers -> buffer k1 & 1.  A1 = k1 / TG is a compile-time tile index.
+        auto publish = [&](auto A1_, int k1) {
+            constexpr int A1 = decltype(A1_)::value;
+            if constexpr (A1 < NB) {
+                const int r1 = k1 - A1 * TG;
+                T* pr1 = prow + (k1 & 1) * NMAX;
+                T* cr1 = fcol + (k1 & 1) * NMAX;
+                if (ty == r1) {
                     #pragma unroll
-                    for (int b = A; b < NB; ++b) pr1[tx + TG * b] = w[A][b];      // (columns before the front are dead)
-                });
-            if (tx == r1)
-                with_tile_index<NB>(a1, [&](auto A_) {
-                    constexpr int A = decltype(A_)::value;
+                    for (int b = A1; b < NB; ++b) pr1[tx + TG * b] = w[A1][b];     // (columns before the front are dead)
+                }
+                if (tx == r1) {
                     #pragma unroll
-                    for (int a = A; a < NB; ++a) cr1[ty + TG * a] = w[a][A];
-                });
+                    for (int a = A1; a < NB; ++a) cr1[ty + TG * a] = w[a][A1];
+                }
+            }
         };
-        publish(0);
+        publish(std::integral_constant<int, 0>{}, 0);
         group_sync();
-        for (int k = 0; k < n; ++k) {
-            const int rk = k % TG, ak = k / TG;         // owner thread-row (= thread-column) and tile index of row / column k
-            const T* pr = prow + (k & 1) * NMAX;
-            const T* cr = fcol + (k & 1) * NMAX;
-            T piv = pr[k];
-            if (piv == T(0)) {
-                // slow path (rare: planted zeros, exactly singular items): first row p > k with a non-zero in column k
-                if (tid == 0) ctl[0] = n;
-                group_sync();
-                for (int i = k + 1 + tid; i < n; i += THREADS)
-                    if (cr[i] != T(0)) atomicMin(&ctl[0], i);
-                group_sync();
-                const int pidx = ctl[0];
-                if (pidx >= n) { singular = true; break; }           // uniform: every thread reads the same word
-                const int rp = pidx % TG, ap = pidx / TG;
-                // exchange rows k and pidx: the live part in registers, the kept multipliers (columns < k) in the shared factors
-                if (ty == rk)
-                    with_tile_index<NB>(ak, [&](auto A_) {
-                        constexpr int A = decltype(A_)::value;
+        // The tile index of the front, A = k / TG, is the OUTER, compile-time loop; the owner index rk = k mod TG the inner
+        // run-time one: every register index below is a constant without any per-step dispatch.  (The first version looped
+        // over k and switched on k / TG three times per step - update, row publish, column publish: indirect branches whose
+        // targets the front end had to fetch, 10 % of the issued instructions and the largest stall sites in ncu.)
+        static_for<0, NB>([&](auto A_) {
+            constexpr int A = decltype(A_)::value;
+            const int rk_end = (THREADS >= 32 && singular) ? 0 : (n - A * TG < TG ? n - A * TG : TG);
+            for (int rk = 0; rk < rk_end; ++rk) {
+                const int k = A * TG + rk;                  // row / column k: owner thread-row (= thread-column) rk, tile index A
+                const T* pr = prow + (k & 1) * NMAX;
+                const T* cr = fcol + (k & 1) * NMAX;
+                T piv = pr[k];
+                const bool need = piv == T(0);
+                // several groups per warp: the slow path is entered by the whole warp (a group that does not need it runs it
+                // as a no-op with pidx = k), so every barrier below is a plain full-mask __syncwarp
+                const bool enter = THREADS >= 32 ? need : __any_sync(0xffffffffu, need);
+                if (enter) {
+                    // slow path (rare: planted zeros, exactly singular items): first row p > k with a non-zero in column k
+                    if (tid == 0) ctl[0] = n;
+                    group_sync();
+                    if (need)
+                        for (int i = k + 1 + tid; i < n; i += THREADS)
+                            if (cr[i] != T(0)) atomicMin(&ctl[0], i);
+                    group_sync();
+                    int pidx = need ? ctl[0] : k;
+                    if (pidx >= n) {                                      // no pivot: singular (uniform within the group)
+                        singular = true;
+                        if constexpr (THREADS >= 32) break;               // the CTA is one group: stop here
+                        pidx = k;                                         // part of a warp: keep in step with the other group, results are discarded
+                    }
+                    const int ap = pidx / TG, rp = pidx - ap * TG;
+                    // exchange rows k and pidx: the live part in registers, the kept multipliers (columns < k) in the shared factors
+                    if (ty == rk) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) xrow[tx + TG * b] = w[A][b];
-                    });
-                if (ty == rp)
-                    with_tile_index<NB>(ap, [&](auto A_) {
-                        constexpr int A = decltype(A_)::value;
-                        #pragma unroll
-                        for (int b = 0; b < NB; ++b) xrow[NMAX + tx + TG * b] = w[A][b];
-                    });
-                group_sync();
-                if (ty == rk)
-                    with_tile_index<NB>(ak, [&](auto A_) {
-                        constexpr int A = decltype(A_)::value;
+                    }
+                    if (ty == rp)
+                        with_tile_index<NB>(ap, [&](auto P_) {
+                            constexpr int P = decltype(P_)::value;
+                            #pragma unroll
+                            for (int b = 0; b < NB; ++b) xrow[NMAX + tx + TG * b] = w[P][b];
+                        });
+                    group_sync();
+                    if (ty == rp && pidx != k)                            // first: when one thread owns both rows they are different tile rows
+                        with_tile_index<NB>(ap, [&](auto P_) {
+                            constexpr int P = decltype(P_)::value;
+                            #pragma unroll
+                            for (int b = 0; b < NB; ++b) w[P][b] = xrow[tx + TG * b];
+                        });
+                    if (ty == rk) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) w[A][b] = xrow[NMAX + tx + TG * b];
-                    });
-                if (ty == rp)                                         // (k != pidx: when one thread owns both rows they are different tile rows)
-                    with_tile_index<NB>(ap, [&](auto A_) {
-                        constexpr int A = decltype(A_)::value;
-                        #pragma unroll
-                        for (int b = 0; b < NB; ++b) w[A][b] = xrow[tx + TG * b];
-                    });
-                if (MODE != 0)
-                    for (int j = tid; j < k; j += THREADS) {
-                        const T t = LU[(size_t)k * p.ldl + j];
-                        LU[(size_t)k * p.ldl + j] = LU[(size_t)pidx * p.ldl + j];
-                        LU[(size_t)pidx * p.ldl + j] = t;
                     }
-                if (tid == 0) { const int t = perm[k]; perm[k] = perm[pidx]; perm[pidx] = t; ctl[1] += 1; }
-                publish(k);                                           // (same buffer: every thread is inside this branch)
-                group_sync();
-                piv = pr[k];
-            }
-            if (tid == 0) acc = acc * piv;
-            const Recip<T> rc(piv);
-            with_tile_index<NB>(ak, [&](auto A_) {
-                constexpr int A = decltype(A_)::value;
-                T prj[NB], f[NB];
-                #pragma unroll
-                for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
-                // the multipliers of all this thread's tile rows first, as one batch of independent exact divisions with one
-                // fallback branch for the whole batch (rows that are not past the front divide stale values: unused, and kept
-                // out of the fallback test - stale zeros / denormals would send every step down the slow division)
-                // (worth it only where a thread has many rows and few warps cover for it: 16 x 16 threads, NB = 8:
-                // n = 128 det 7.8 -> 5.9 ms; smaller tiles lost 5-50 % to the divisions of rows that are not past the front)
-                constexpr bool BATCH = TG == 16 && NB == 8;
-                if constexpr (BATCH) {
-                    bool all_fast = true;
+                    if (MODE != 0 && pidx != k)
+                        for (int j = tid; j < k; j += THREADS) {
+                            const T t = LU[(size_t)k * p.ldl + j];
+                            LU[(size_t)k * p.ldl + j] = LU[(size_t)pidx * p.ldl + j];
+                            LU[(size_t)pidx * p.ldl + j] = t;
+                        }
+                    if (tid == 0 && pidx != k) { const int t = perm[k]; perm[k] = perm[pidx]; perm[pidx] = t; ctl[1] += 1; }
+                    publish(A_, k);                                       // (same buffer: every thread of the group is inside this branch)
+                    group_sync();
+                    piv = pr[k];
+                }
+                acc = acc * piv;                                          // (every thread: cheaper than a predicate; thread 0's copy is used)
+                if constexpr (ONEDIV) {
+                    // One division per ROW, not per (row, thread of the thread-row): thread t divides for row t (a group has at
+                    // least as many threads as rows except 4 x 4 groups with NB > 4), the multipliers go through shared memory
+                    // and the update below is loads + multiply-subtract only.
+                    for (int i = k + 1 + tid; i < n; i += THREADS) {
+                        const T f = cr[i] / piv;
+                        fmul[i] = f;
+                        if (MODE != 0) LU[(size_t)i * p.ldl + k] = f;             // the multiplier goes where the zero would go
+                    }
+                    group_sync();
+                    T prj[NB];
+                    #pragma unroll
+                    for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
                     #pragma unroll
                     for (int a = A; a < NB; ++a) {
-                        bool ok = true;
-                        f[a] = rc.div_try(cr[ty + TG * a], ok);
-                        all_fast = all_fast && (ok || !((a > A || ty > rk) && a < a_end));
+                        // rows of tile row A are past the front only for ty > rk; later tile rows are, whole; rows >= n do not exist
+                        if ((a > A || ty > rk) && a < a_end) {
+                            const T f = fmul[ty + TG * a];
+                            #pragma unroll
+                            for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f * prj[b];
+                        }
                     }
-                    if (!all_fast) {
+                } else {
+                    const Recip<T> rc(piv);
+                    T prj[NB], f[NB];
+                    #pragma unroll
+                    for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
+                    // the multipliers of all this thread's tile rows first, as one batch of independent exact divisions with one
+                    // fallback branch for the whole batch (rows that are not past the front divide stale values: unused, and kept
+                    // out of the fallback test - stale zeros / denormals would send every step down the slow division)
+                    // (worth it only where a thread has many rows and few warps cover for it: 16 x 16 threads, NB = 8:
+                    // n = 128 det 7.8 -> 5.9 ms; smaller tiles lost 5-50 % to the divisions of rows that are not past the front)
+                    constexpr bool BATCH = TG == 16 && NB == 8;
+                    if constexpr (BATCH) {
+                        bool all_fast = true;
                         #pragma unroll
-                        for (int a = A; a < NB; ++a) f[a] = rc.div_fix(cr[ty + TG * a], f[a]);
+                        for (int a = A; a < NB; ++a) {
+                            bool ok = true;
+                            f[a] = rc.div_try(cr[ty + TG * a], ok);
+                            all_fast = all_fast && (ok || !((a > A || ty > rk) && a < a_end));
+                        }
+                        if (!all_fast) {
+                            #pragma unroll
+                            for (int a = A; a < NB; ++a) f[a] = rc.div_fix(cr[ty + TG * a], f[a]);
+                        }
+                    }
+                    #pragma unroll
+                    for (int a = A; a < NB; ++a) {
+                        if ((a > A || ty > rk) && a < a_end) {
+                            if constexpr (!BATCH) f[a] = rc.div(cr[ty + TG * a]);
+                            if (MODE != 0 && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f[a];   // the multiplier goes where the zero would go
+                            #pragma unroll
+                            for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f[a] * prj[b];
+                        }
                     }
                 }
-                #pragma unroll
-                for (int a = A; a < NB; ++a) {
-                    // rows of tile row A are past the front only for ty > rk; later tile rows are, whole; rows >= n do not exist
-                    if ((a > A || ty > rk) && a < a_end) {
-                        if constexpr (!BATCH) f[a] = rc.div(cr[ty + TG * a]);
-                        if (MODE != 0 && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f[a];   // the multiplier goes where the zero would go
-                        #pragma unroll
-                        for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f[a] * prj[b];
-                    }
+                if (k + 1 < n) {
+                    if (rk + 1 < TG) publish(A_, k + 1);
+                    else publish(std::integral_constant<int, A + 1>{}, k + 1);
                 }
-            });
-            if (k + 1 < n) publish(k + 1);
-            group_sync();
-        }
+                group_sync();
+            }
+        });
 
         if (MODE == 0) {
-            if (tid == 0) {
+            if (tid == 0 && live) {
                 T d = singular ? T(0) : ((ctl[1] & 1) ? -acc : acc);
                 ((T*)p.X)[item] = d;
             }
@@ -244,8 +293,8 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
         // ---- solve / inverse
         const int nrhs = p.nrhs;
         T* gX = (T*)p.X + item * (unsigned long long)n * nrhs;
-        if (tid == 0) p.status[item] = singular ? 1 : 0;
-        if (singular) {
+        if (tid == 0 && live) p.status[item] = singular ? 1 : 0;
+        if (THREADS >= 32 && singular) {                 // (a group that shares its warp runs on in step and zero-fills at the end)
             for (int e = tid; e < n * nrhs; e += THREADS) gX[e] = T(0);
             group_sync();
             continue;
@@ -275,31 +324,33 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
                     }
                     y[a][b] = v;
                 }
-            for (int k = 0; k < n; ++k) {
-                const int rk = k % TG, ak = k / TG;
-                T* pr = prow + (k & 1) * NMAX;
-                if (ty == rk)
-                    with_tile_index<NB>(ak, [&](auto A_) {
-                    constexpr int A = decltype(A_)::value;
+            const int nbl = p.chunk / TG;                 // column tiles of this pass that hold right-hand sides (1 for a single vector)
+            static_for<0, NB>([&](auto A_) {              // tile index of row k outside, owner index inside: no per-step dispatch
+                constexpr int A = decltype(A_)::value;
+                const int rk_end = n - A * TG < TG ? n - A * TG : TG;
+                for (int rk = 0; rk < rk_end; ++rk) {
+                    const int k = A * TG + rk;
+                    T* pr = prow + (k & 1) * NMAX;
+                    if (ty == rk) {
                         #pragma unroll
-                        for (int b = 0; b < NB; ++b) pr[tx + TG * b] = y[A][b];
-                    });
-                group_sync();
-                with_tile_index<NB>(ak, [&](auto A_) {
-                    constexpr int A = decltype(A_)::value;
+                        for (int b = 0; b < NB; ++b)
+                            if (b < nbl) pr[tx + TG * b] = y[A][b];
+                    }
+                    group_sync();
                     T prj[NB];
                     #pragma unroll
-                    for (int b = 0; b < NB; ++b) prj[b] = pr[tx + TG * b];
+                    for (int b = 0; b < NB; ++b) prj[b] = b < nbl ? pr[tx + TG * b] : T(0);
                     #pragma unroll
                     for (int a = A; a < NB; ++a) {
                         if ((a > A || ty > rk) && a < a_end) {
                             const T f = LU[(size_t)(ty + TG * a) * p.ldl + k];
                             #pragma unroll
-                            for (int b = 0; b < NB; ++b) y[a][b] = y[a][b] - f * prj[b];
+                            for (int b = 0; b < NB; ++b)
+                                if (b < nbl) y[a][b] = y[a][b] - f * prj[b];
                         }
                     }
-                });
-            }
+                }
+            });
             #pragma unroll
             for (int a = 0; a < NB; ++a)
                 #pragma unroll
@@ -329,9 +380,9 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
             }
             group_sync();
             const int width = (nrhs - c0) < p.chunk ? (nrhs - c0) : p.chunk;
-            for (int e = tid; e < n * width; e += THREADS) {
+            for (int e = tid; e < n * width && live; e += THREADS) {
                 const int i = e / width, cc = e - i * width;
-                gX[(size_t)i * nrhs + c0 + cc] = Y[(size_t)i * p.ldy + cc];
+                gX[(size_t)i * nrhs + c0 + cc] = singular ? T(0) : Y[(size_t)i * p.ldy + cc];
             }
             group_sync();
         }
@@ -348,13 +399,13 @@ static int sm_count() {
     return n;
 }
 
-template <class T, int TG, int NB, int MODE, int G = 1>
+template <class T, int TG, int NB, int MODE, int G = 1, bool ONEDIV = (TG <= 8)>
 static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
     constexpr int NMAX = TG * NB;
     Args p;
     p.A = A; p.B = B; p.X = X; p.status = (unsigned char*)status; p.count = s.count; p.n = n; p.nrhs = nrhs;
     p.ldl = n | 1;                                           // odd pitch: rows a thread-row apart land in different banks
-    size_t smem = sizeof(T) * 6 * NMAX + sizeof(int) * (NMAX + 4);
+    size_t smem = sizeof(T) * 7 * NMAX + sizeof(int) * (NMAX + 4);
     p.chunk = TG; p.ldy = 1;
     if (MODE != 0) {
         // as many right-hand-side columns per pass as the tile holds and shared memory allows (the factors stay resident)
@@ -370,7 +421,7 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
     p.group_smem = (unsigned)smem;
     smem *= G;
     if (smem > 227 * 1024) return T5I_UNSUPPORTED;
-    auto kern = lu_kernel<T, TG, NB, MODE, G>;
+    auto kern = lu_kernel<T, TG, NB, MODE, G, ONEDIV>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return T5I_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TG * TG * G, smem) != cudaSuccess || per_sm < 1) return T5I_CUDA;
@@ -394,22 +445,24 @@ static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* 
     // warp - a group synchronises with a masked __syncwarp, so no warp ever waits for another: det 16x16 Double
     // 1.85 -> 0.95 ms (1.13 TB/s), inverse 5.29 -> 2.72 ms, 9x9 det 2.17 -> 1.08 ms (tools/time_lu.py, profiles/r02m_*).
     // Heavier tiles (inverse from n = 17, everything dense from n = 25) do better spread over 64 threads.
+#define LU_LAUNCH(TG_, NB_, G_) return launch<T, TG_, NB_, MODE, G_>(s, n, nrhs, A, B, X, status)
     const bool light = MODE == 0 || (MODE == 1 && nrhs <= 4);
-    if (n <= 8) return launch<T, 4, 2, MODE, 8>(s, n, nrhs, A, B, X, status);
-    if (n <= 16) return launch<T, 4, 4, MODE, 8>(s, n, nrhs, A, B, X, status);
-    if (n <= 24 && light) return launch<T, 4, 6, MODE, 8>(s, n, nrhs, A, B, X, status);
-    if (n <= 32 && MODE == 1 && nrhs <= 4) return launch<T, 4, 8, MODE, 8>(s, n, nrhs, A, B, X, status);
-    if (n <= 16) return launch<T, 8, 2, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 24) return launch<T, 8, 3, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 32) return launch<T, 8, 4, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 40) return launch<T, 8, 5, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 48) return launch<T, 8, 6, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 56) return launch<T, 8, 7, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 64) return launch<T, 8, 8, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 80) return launch<T, 16, 5, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 96) return launch<T, 16, 6, MODE>(s, n, nrhs, A, B, X, status);
-    if (n <= 112) return launch<T, 16, 7, MODE>(s, n, nrhs, A, B, X, status);
-    return launch<T, 16, 8, MODE>(s, n, nrhs, A, B, X, status);
+    if (n <= 8) LU_LAUNCH(4, 2, 8);
+    if (n <= 16) LU_LAUNCH(4, 4, 8);
+    if (n <= 24 && light) LU_LAUNCH(4, 6, 8);
+    if (n <= 32 && MODE == 1 && nrhs <= 4) LU_LAUNCH(4, 8, 8);
+    if (n <= 16) LU_LAUNCH(8, 2, 1);
+    if (n <= 24) LU_LAUNCH(8, 3, 1);
+    if (n <= 32) LU_LAUNCH(8, 4, 1);
+    if (n <= 40) LU_LAUNCH(8, 5, 1);
+    if (n <= 48) LU_LAUNCH(8, 6, 1);
+    if (n <= 56) LU_LAUNCH(8, 7, 1);
+    if (n <= 64) LU_LAUNCH(8, 8, 1);
+    if (n <= 80) LU_LAUNCH(16, 5, 1);
+    if (n <= 96) LU_LAUNCH(16, 6, 1);
+    if (n <= 112) LU_LAUNCH(16, 7, 1);
+    LU_LAUNCH(16, 8, 1);
+#undef LU_LAUNCH
 }
 
 }  // namespace lu
