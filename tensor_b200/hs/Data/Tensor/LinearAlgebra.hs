@@ -49,6 +49,7 @@ module Data.Tensor.LinearAlgebra
     , type (++), Drop, Take
       -- * Pure forms of the remaining operations
     , dotSum', tr', polyEval', charPoly', minPoly', rowEchelonForm', triangularSolve'
+    , productIsExact
     , (.+.), (.-.), (.*), hadamard
       -- * The IO layer, re-exported for callers that sequence device work themselves
     , module Data.Tensor.LinearAlgebra.Device
@@ -62,6 +63,7 @@ import           System.IO.Unsafe                 (unsafePerformIO)
 import           Data.Indexable                   (ReverseI)
 import           Data.MultiIndex                  (PI (..), fromPI)
 import           Data.Tensor.Device
+import           Data.Tensor.Device.FFI            (c_matmul_is_exact)
 import           Data.Tensor.LinearAlgebra.Device
 
 infixl 7 .*.
@@ -168,6 +170,16 @@ transposeB' a = pure1 transposeB a
 -- | Sum over the batch of 'dot' - the only operation with a cross-GPU exchange (SURVEY.md §8e).
 dotSum' :: (SingI i, DeviceElt e) => Batch '[i] e -> Batch '[i] e -> e
 dotSum' x y = pure2 dotSum x y
+
+-- | Is @(.*.)@ of an @m x k@ by a @k x n@ matrix of this element type the bit-exact sequential fold ('True'), or
+-- does the library run it on the tensor cores within BASELINE.json's tolerance (Double 1e-12, Float 1e-5 of
+-- @sum_j |a_ij||b_jc|@; include/t5b200.h, t5_matmul)?  Depends on element type and shape only.  The C entry is a
+-- pure function of its arguments (no context, no device), hence the plain 'unsafePerformIO'.
+productIsExact :: forall e. DeviceElt e => Proxy e -> Int -> Int -> Int -> Bool
+productIsExact pe m k n = unsafePerformIO $ do
+    r <- c_matmul_is_exact (dtypeCode pe) (fromIntegral m) (fromIntegral k) (fromIntegral n)
+    return (r /= 0)        -- (negative = rejected arguments: (.*.) itself throws for those)
+{-# NOINLINE productIsExact #-}
 
 tr' :: (SingI i, DeviceElt e) => Batch '[i, i] e -> Batch '[] e
 tr' a = pure1 tr a
