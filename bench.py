@@ -121,6 +121,14 @@ WORKLOADS = {
                                      desc="256Ki 100x20 . 20x36 Float (no tensor-core tiling fits: exact blocked SIMT product, packed FFMA2 multiply then add)"),
     "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
                               desc="256Ki 64x64 Double .*. on FP64 tensor cores (smallest DMMA shape; 5.3 flop/B, HBM floor ~= tensor floor)"),
+    "matmul32_f64_1M": dict(op="matmul", dtype="f64", m=32, k=32, n=32, batch=1 << 20, bytes=24576, flops=65536, bound="hbm",
+                            desc="1Mi 32x32 Double .*. on FP64 tensor cores (four items per DMMA tile through item-dimension tensor maps; 2.7 flop/B: HBM-bound)"),
+    "matmul48_f64_512K": dict(op="matmul", dtype="f64", m=48, k=48, n=48, batch=1 << 19, bytes=55296, flops=221184, bound="hbm",
+                              desc="512Ki 48x48 Double .*. on FP64 tensor cores (two items per DMMA tile; 4 flop/B: HBM-bound)"),
+    "matmul96_f64_64K": dict(op="matmul", dtype="f64", m=96, k=96, n=96, batch=1 << 16, bytes=221184, flops=1769472, bound="tensor",
+                             desc="64Ki 96x96 Double .*. on FP64 tensor cores (96 x 96 tile; 8 flop/B: bound by the FP64 tensor pipe)"),
+    "matmul32_f32_1M": dict(op="matmul", dtype="f32", m=32, k=32, n=32, batch=1 << 20, bytes=12288, flops=65536, bound="hbm",
+                            desc="1Mi 32x32 Float .*. on tcgen05 tensor cores (3xTF32; four items per 128 tile, diagonal accumulator blocks read back)"),
 }
 HEADLINE = "matmul4x4_f32_16M"
 EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpose4x4_f32_16M", "matvec4_f32_16M",
@@ -128,7 +136,7 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M", "tensorprod8x8_f64_soa_1M", "prod1_8x8_f64_soa_1M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
           "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
-          "inverse6_f64_1M", "inverse8_f64_1M", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M", "echelon7x9_f64_1M"]
+          "inverse6_f64_1M", "inverse8_f64_1M", "matmul32_f64_1M", "matmul32_f32_1M", "det16_f64_512K", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M", "echelon7x9_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
 
@@ -776,7 +784,7 @@ def ours(args):
     # ---- the other BASELINE configs (explanatory; not the headline) ----------------------------------
     others = {}
     if args.all and world == 1:
-        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K", "matmul128_f32_64K", "matmul64_f32_256K", "matmul96_f32_64K"] if args.big else []):
+        for name in EXTRAS + (["matmul128_f64_64K", "matmul64_f64_256K", "matmul96_f64_64K", "matmul48_f64_512K", "matmul128_f32_64K", "matmul64_f32_256K", "matmul96_f32_64K"] if args.big else []):
             ww = WORKLOADS[name]
             try:
                 st = StepRing(ctx, tb, ww)

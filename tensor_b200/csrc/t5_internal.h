@@ -99,7 +99,7 @@ int rowlane_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int rowlane_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
 int rowlane_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);
 
-// ---- t5_lu.cu: CTA-per-matrix elimination for 9 <= n <= 128, the matrix 2D-cyclic in the CTA's registers (AoS);
+// ---- t5_lu.cuh (t5_lu_det.cu / t5_lu_solve.cu / t5_lu_inverse.cu): CTA-per-matrix elimination for 9 <= n <= 128, the matrix 2D-cyclic in the CTA's registers (AoS);
 // bit-identical to the oracle like every other elimination kernel
 int lu_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int lu_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);

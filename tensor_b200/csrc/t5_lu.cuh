@@ -1,3 +1,5 @@
+// (kernel + launch templates; instantiated per operation by t5_lu_det.cu / t5_lu_solve.cu / t5_lu_inverse.cu so that the
+// three operations compile in parallel)
 // Gaussian elimination for 9 <= n <= 128: ONE CTA PER MATRIX, the working matrix distributed over the CTA's
 // registers 2D-cyclically (SquareMatrix det / inverse, LinearSystem solve of SURVEY.md §8a a9-a11 for the sizes the
 // record-per-thread and row-per-lane kernels do not reach; the reference's shapes are unbounded unary naturals,
@@ -38,6 +40,7 @@
 // factors).  Back-substitution is a sequential recurrence per column whose order the specification fixes
 // (s = fold_{j>k ascending}(s + u[k,j] x[j]) from 0, x[k] = (y[k] - s) / u[k,k]): Y goes to shared memory and
 // thread c runs column c, reading u[k,j] as a broadcast.  Singular: status 1, item zero-filled.
+#pragma once
 #include <type_traits>
 
 #include "t5_device.cuh"
@@ -466,22 +469,5 @@ static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* 
 }
 
 }  // namespace lu
-
-int lu_det(const Shard& s, int dtype, int n, const void* A, void* O) {
-    if (dtype == T5D_F64) return lu::dispatch<double, 0>(s, n, 0, A, nullptr, O, nullptr);
-    if (dtype == T5D_F32) return lu::dispatch<float, 0>(s, n, 0, A, nullptr, O, nullptr);
-    return T5I_NOT_SPECIALISED;
-}
-int lu_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status) {
-    if (dtype == T5D_F64) return lu::dispatch<double, 2>(s, n, n, A, nullptr, O, status);
-    if (dtype == T5D_F32) return lu::dispatch<float, 2>(s, n, n, A, nullptr, O, status);
-    return T5I_NOT_SPECIALISED;
-}
-int lu_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
-    if (nrhs < 1) return T5I_NOT_SPECIALISED;
-    if (dtype == T5D_F64) return lu::dispatch<double, 1>(s, n, nrhs, A, B, X, status);
-    if (dtype == T5D_F32) return lu::dispatch<float, 1>(s, n, nrhs, A, B, X, status);
-    return T5I_NOT_SPECIALISED;
-}
 
 }  // namespace t5

@@ -1,4 +1,4 @@
-"""det / inverse / solve for 9 <= n <= 128 (t5_lu.cu: one CTA per matrix, the matrix 2D-cyclic in registers).
+"""det / inverse / solve for 9 <= n <= 128 (t5_lu.cuh: one CTA per matrix, the matrix 2D-cyclic in registers).
 The kernels keep the oracle's operation order element for element, so every result - the determinant, the status
 bytes and every entry of the inverse / solution - is compared BIT FOR BIT, with planted zero pivots (row swaps,
 including swaps between rows of the same owner thread) and exactly singular items in every batch."""

@@ -155,10 +155,15 @@ def main():
             A32s, B32s = A32.relayout(tb.SOA), B32.relayout(tb.SOA)
             add(f"SoA matmul 32x32 (detour: relayout in, AoS kernel, relayout out) {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(A32s, B32s))
             A32s.free(); B32s.free()
-            if es == 4:
-                A96, B96 = ctx.synthetic((96, 96), dt, B // 64, SEED, 41), ctx.synthetic((96, 96), dt, B // 64, SEED + 1, 41)
-                add(f"matmul 96x96 (ragged tcgen05 tiles) {tag}", (B // 64) * 3 * 9216 * es, lambda: tb.matmul(A96, B96))
-                A96.free(); B96.free()
+            A96, B96 = ctx.synthetic((96, 96), dt, B // 64, SEED, 41), ctx.synthetic((96, 96), dt, B // 64, SEED + 1, 41)
+            add(f"matmul 96x96 ({'ragged tcgen05 tiles' if es == 4 else 'DMMA 96 tile'}) {tag}", (B // 64) * 3 * 9216 * es, lambda: tb.matmul(A96, B96))
+            A96.free(); B96.free()
+            for nn in (24, 48, 64):
+                Bn = max(256, (B * 16 * 3) // (3 * nn * nn))
+                An, Bm = ctx.synthetic((nn, nn), dt, Bn, SEED, 42), ctx.synthetic((nn, nn), dt, Bn, SEED + 1, 42)
+                cls = "exact" if tb.matmul_is_exact(tb.device.DTYPE_OF[np.dtype(dt)], nn, nn, nn) else "tensor cores"
+                add(f"matmul {nn}x{nn} ({cls}) {tag}", Bn * 3 * nn * nn * es, lambda: tb.matmul(An, Bm))
+                An.free(); Bm.free()
             for x in (A3, A4, B4, v3, A6, b6, A8, T234, A5, B5, A32, B32):
                 x.free()
 
