@@ -38,17 +38,50 @@ struct RowEchelonOp {
         }
         if (w[R][C] != T(0)) {
             const Recip<T> rc(w[R][C]);
-            static_for<0, M>([&](auto i_) {
-                constexpr int i = decltype(i_)::value;
-                if constexpr (i != R) {
-                    const T f = rc.div(w[i][C]);
+            if constexpr (kBatchDiv<T>) {
+                // Double: the M - 1 multipliers, then the N - C - 1 entries of the pivot row, each as one batch of independent
+                // exact divisions with a single fallback test (t5_recip.cuh)
+                T f[M];
+                bool all_fast = true;
+                #pragma unroll
+                for (int i = 0; i < M; ++i)
+                    if (i != R) f[i] = rc.div_try(w[i][C], all_fast);
+                if (!all_fast) {
                     #pragma unroll
-                    for (int j = C + 1; j < N; ++j) w[i][j] = w[i][j] - f * w[R][j];
-                    w[i][C] = T(0);
+                    for (int i = 0; i < M; ++i)
+                        if (i != R) f[i] = rc.div_fix(w[i][C], f[i]);
                 }
-            });
-            #pragma unroll
-            for (int j = C + 1; j < N; ++j) w[R][j] = rc.div(w[R][j]);
+                static_for<0, M>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    if constexpr (i != R) {
+                        #pragma unroll
+                        for (int j = C + 1; j < N; ++j) w[i][j] = w[i][j] - f[i] * w[R][j];
+                        w[i][C] = T(0);
+                    }
+                });
+                T q[N];
+                all_fast = true;
+                #pragma unroll
+                for (int j = C + 1; j < N; ++j) q[j] = rc.div_try(w[R][j], all_fast);
+                if (!all_fast) {
+                    #pragma unroll
+                    for (int j = C + 1; j < N; ++j) q[j] = rc.div_fix(w[R][j], q[j]);
+                }
+                #pragma unroll
+                for (int j = C + 1; j < N; ++j) w[R][j] = q[j];
+            } else {
+                static_for<0, M>([&](auto i_) {
+                    constexpr int i = decltype(i_)::value;
+                    if constexpr (i != R) {
+                        const T f = rc.div(w[i][C]);
+                        #pragma unroll
+                        for (int j = C + 1; j < N; ++j) w[i][j] = w[i][j] - f * w[R][j];
+                        w[i][C] = T(0);
+                    }
+                });
+                #pragma unroll
+                for (int j = C + 1; j < N; ++j) w[R][j] = rc.div(w[R][j]);
+            }
             w[R][C] = T(1);
             rank = R + 1;
         }
