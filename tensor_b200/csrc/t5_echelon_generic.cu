@@ -101,10 +101,28 @@ row_echelon_kernel(const T* __restrict__ A, T* __restrict__ OUT, unsigned char* 
                     T prow[NC];
                     #pragma unroll
                     for (int j = C + 1; j < NC; ++j) prow[j] = pr[j * P];
-                    for (int i = 0; i < m; ++i) {
-                        if (i == rank) continue;
+                    // (Double: all multipliers of the column as one batch of independent exact divisions, one fallback test)
+                    T fb[ECH_MAX_ROWS];
+                    (void)fb;
+                    if constexpr (kBatchDiv<T>) {
+                        T cv[ECH_MAX_ROWS];
+                        bool all_fast = true;
+                        #pragma unroll
+                        for (int i = 0; i < ECH_MAX_ROWS; ++i) {
+                            cv[i] = (i < m && i != rank) ? x[(i * n + C) * P] : T(1);
+                            fb[i] = rc.div_try(cv[i], all_fast);
+                        }
+                        if (!all_fast) {
+                            #pragma unroll
+                            for (int i = 0; i < ECH_MAX_ROWS; ++i) fb[i] = rc.div_fix(cv[i], fb[i]);
+                        }
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < ECH_MAX_ROWS; ++i) {
+                        if (i >= m || i == rank) continue;
                         T* ri = x + (i * n) * P;
-                        const T f = rc.div(ri[C * P]);
+                        T f;
+                        if constexpr (kBatchDiv<T>) f = fb[i]; else f = rc.div(ri[C * P]);
                         T rrow[NC];
                         #pragma unroll
                         for (int j = C + 1; j < NC; ++j) rrow[j] = ri[j * P];
@@ -112,8 +130,21 @@ row_echelon_kernel(const T* __restrict__ A, T* __restrict__ OUT, unsigned char* 
                         for (int j = C + 1; j < NC; ++j) ri[j * P] = rrow[j] - f * prow[j];
                         ri[C * P] = T(0);
                     }
-                    #pragma unroll
-                    for (int j = C + 1; j < NC; ++j) pr[j * P] = rc.div(prow[j]);
+                    if constexpr (kBatchDiv<T>) {
+                        T q[NC];
+                        bool all_fast = true;
+                        #pragma unroll
+                        for (int j = C + 1; j < NC; ++j) q[j] = rc.div_try(prow[j], all_fast);
+                        if (!all_fast) {
+                            #pragma unroll
+                            for (int j = C + 1; j < NC; ++j) q[j] = rc.div_fix(prow[j], q[j]);
+                        }
+                        #pragma unroll
+                        for (int j = C + 1; j < NC; ++j) pr[j * P] = q[j];
+                    } else {
+                        #pragma unroll
+                        for (int j = C + 1; j < NC; ++j) pr[j * P] = rc.div(prow[j]);
+                    }
                     pr[C * P] = T(1);
                 });
                 ++rank;

@@ -42,10 +42,6 @@ struct TransposeOp {
 
 template <int K> using k_of = std::integral_constant<int, K>;
 
-// Quotients that share a divisor as ONE batch without a branch between them (Recip::div_try / div_fix, t5_recip.cuh):
-// worth it where the hoisted-reciprocal division exists (Double: 8x8 inverse 0.327 -> 0.289 ms, solve 0.135 -> 0.120);
-// Float divides with the hardware instruction sequence and only paid registers for the batch (8x8 det 0.048 -> 0.058).
-template <class T> constexpr bool kBatchDiv = std::is_same<T, double>::value;
 
 template <int B, int E, class F>
 __device__ __forceinline__ void static_for(F&& f) {
