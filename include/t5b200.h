@@ -122,10 +122,11 @@ int t5_buf_layout(const t5_buf* buf);
  *   Double, m >= 17, n >= 24, k >= 8, n and k multiples of 8, and a 32- / 48- / 64- / 96- / 128-tiling of
  *   the m x n result that is at least a quarter full (24 x 24 and 32 x 32 items, four to a tile, are;
  *   72 x 72 is; 17 x 136 is not): FP64 DMMA, tol 1e-12;
- *   Float, m >= 48, n >= 64 a multiple of 32, k >= 32 a multiple of 4, and a 64- or 128-tiling
- *   of the m x n result that is at least half full (m = n = 96 is; 48 x 64 is; 200 x 32 is
- *   not), or 17 <= m <= 32 with n = 32 and k >= 8 a multiple of 4 (four items to a tile):
- *   tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are computed with the exact fold.
+ *   Float, k and n multiples of 4: items of at least 33 x 36 with k >= 32 whose 64- or 128-tiling of the m x n
+ *   result is at least 2/7 full (every item up to 64 x 64 is: two to a tile; m = n = 96 is; 200 x 36 is not), and
+ *   items of 17..32 rows and 20..32 columns with k >= 8 that hold at least 2048 elements in A, B and C together
+ *   (32 x 32 is, 24 x 24 is not; four to a tile): tcgen05 3xTF32, tol 1e-5; items containing inf / NaN are
+ *   computed with the exact fold.
  * The class depends on dtype and shape only, never on layout, batch size or device count.
  * Layout: the tile pipeline (records up to 8 x 8), outer products and contractions whose B fits
  * in shared memory read SoA directly.  Every other shape has AoS kernels only; given SoA

@@ -10,7 +10,8 @@
 //
 //   warp 0 (1 lane)   TMA producer: A chunk 128 x 32 (K-major, SWIZZLE_128B), B chunk 32 x 128
 //                     (MN-major: [4 n-blocks][32 k-rows][32 floats], SWIZZLE_128B_ATOM_32B - the
-//                     only layout tcgen05 accepts for MN-major 32-bit operands)      --full[s]-->
+//                     only layout tcgen05 accepts for MN-major 32-bit operands; one box per
+//                     128-byte column block, so n need not be a multiple of 32)       --full[s]-->
 //   warps 4-7         split: x_lo = x - trunc_tf32(x) for both chunks into twin tiles of the same
 //                     (swizzled) layout; fence.proxy.async                            --conv[s]-->
 //   warp 1 (1 lane)   tcgen05.mma cta_group::1 kind::tf32, M=128 N=128 K=8: per K step
@@ -45,7 +46,9 @@ constexpr int EPI_WARP = 32 * EPI_PITCH;                            // one (<= 3
 template <int TILE_, int STAGES_, int ITEMS_ = 1>
 struct Geo {
     static constexpr int BM = TILE_, BN = TILE_, STAGES = STAGES_, ITEMS = ITEMS_;
-    static_assert(ITEMS == 1 || (ITEMS == 4 && TILE_ == 128), "item packing: four 32-row items on the 128 tile");
+    static_assert(ITEMS == 1 || ((ITEMS == 4 || ITEMS == 2) && TILE_ == 128), "item packing: four 32-row or two 64-row items on the 128 tile");
+    static constexpr int ITEM_ROWS = BM / ITEMS;                     // rows (and columns) of the tile one packed item owns
+    static constexpr int ITEM_BLOCKS = BN / 32 / ITEMS;              // 128-byte column blocks per packed item
     static constexpr int TILE_A = BM * BK * 4, TILE_B = BK * BN * 4;
     static constexpr int STAGE = 2 * (TILE_A + TILE_B);             // hi + lo tiles
     static constexpr int SMEM = STAGES * STAGE + 1024 + 4 * EPI_WARP;
@@ -59,6 +62,7 @@ struct Geo {
 using Geo128 = Geo<128, 3>;
 using Geo64 = Geo<64, 6>;
 using Geo32x4 = Geo<128, 3, 4>;
+using Geo64x2 = Geo<128, 3, 2>;                                       // two items of at most 64 x 64 per tile (rows 64q.., column blocks 2q, 2q + 1)
 
 constexpr float FLT_MAX_F = 3.4028234664e38f;
 
@@ -165,7 +169,12 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), TILE_A + TILE_B);                 // out-of-bounds parts are zero-filled and counted
                     tma_load_3d(ring + s * STAGE, &mapA, full_bar(s), kc * BK, tm * BM, (int)item);
-                    tma_load_4d(ring + s * STAGE + TILE_A, &mapB, full_bar(s), 0, kc * BK, tn * (BN / 32), (int)item);
+                    // B: one box of 32 columns x 32 k-rows per 128-byte column block (columns / items beyond the operand: zeros)
+                    #pragma unroll
+                    for (int blk = 0; blk < BN / 32; ++blk)
+                        tma_load_3d(ring + s * STAGE + TILE_A + blk * 4096, &mapB, full_bar(s),
+                                    ITEMS > 1 ? (blk % G::ITEM_BLOCKS) * 32 : tn * BN + blk * 32, kc * BK,
+                                    ITEMS > 1 ? (int)item + blk / G::ITEM_BLOCKS : (int)item);
                 }
             }
         }
@@ -235,16 +244,18 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         unsigned tl = 0;
         for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
             const unsigned acc = tl & 1;
-            const unsigned long long item = ITEMS > 1 ? tile * ITEMS + q : tile / tiles_per_item;   // packed: warp q = item q of the tile
+            constexpr int WPI = 4 / ITEMS;                                    // epilogue warps per packed item
+            const int qi = q / WPI, qr = q % WPI;                             // packed: item of the tile, 32-row block within the item
+            const unsigned long long item = ITEMS > 1 ? tile * ITEMS + qi : tile / tiles_per_item;
             const int rem = ITEMS > 1 ? 0 : (int)(tile - item * tiles_per_item);
             const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
             mbar_wait(tfull_bar(acc), (tl >> 1) & 1);
             tc_fence_after();
-            const int row_base = ITEMS > 1 ? 0 : tm * BM + q * RPW;           // first row (within the item) of this warp's block
+            const int row_base = ITEMS > 1 ? qr * 32 : tm * BM + q * RPW;     // first row (within the item) of this warp's block
             float* cblk = p.C + item * (size_t)p.M * p.N + (size_t)row_base * p.N + tn * BN;   // this warp's rows
             float* crow = cblk + (size_t)lane * p.N;
             const int rows_here = (ITEMS > 1 && item >= p.count) ? 0 : p.M - row_base;   // rows of this warp's block that exist (may be <= 0)
-            const int cols_here = p.N - tn * BN;                              // columns of the tile that exist (multiple of 32)
+            const int cols_here = p.N - tn * BN;                              // columns of the tile that exist (multiple of 4)
             if (*(volatile unsigned*)&special_tile[tl & 7] == tl + 1) {
                 // exact sequential fold for this thread's row (multiply, round, add, round; k ascending)
                 const float* arow = p.A + item * (size_t)p.M * p.K + (size_t)(row_base + lane) * p.K;
@@ -260,11 +271,11 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 continue;
             }
             #pragma unroll
-            for (int cb = 0; cb < (ITEMS > 1 ? 1 : BN / 32); ++cb) {
+            for (int cb = 0; cb < (ITEMS > 1 ? G::ITEM_BLOCKS : BN / 32); ++cb) {
                 if (cb * 32 >= cols_here) break;                              // (warp-uniform)
-                const int cc = ITEMS > 1 ? 0 : cb;                            // column block of C; packed: the item's only one,
-                unsigned r[32];                                               // found in the DIAGONAL block q of the accumulator
-                const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + (ITEMS > 1 ? q : cb) * 32;
+                const int cc = cb;                                            // column block of C; packed: the item's blocks are
+                unsigned r[32];                                               // found in the DIAGONAL part of the accumulator
+                const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + acc * BN + (ITEMS > 1 ? qi * G::ITEM_BLOCKS + cb : cb) * 32;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -288,7 +299,7 @@ tf32x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     uint4 v;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                                  : "r"(stage_w + rr * EPI_PITCH + c4 * 16));
-                    if (rr < rows_here) st_global_stream16(cblk + (size_t)rr * p.N + cc * 32 + c4 * 4, v);
+                    if (rr < rows_here && cb * 32 + c4 * 4 < cols_here) st_global_stream16(cblk + (size_t)rr * p.N + cc * 32 + c4 * 4, v);
                 }
             }
             tc_fence_before();
@@ -314,16 +325,17 @@ static int launch(const Shard& s, int m, int k, int n, const float* A, const flo
     {   // A: {k, m, count} floats, box 32 floats x BM rows x 1 item, K-major.  Rows >= m / depth >= k: zero fill.
         const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)m, (cuuint64_t)s.count};
         const cuuint64_t strides[2] = {(cuuint64_t)k * 4, (cuuint64_t)m * k * 4};
-        const cuuint32_t box[3] = {BK, G::ITEMS > 1 ? 32u : (cuuint32_t)BM, (cuuint32_t)G::ITEMS}, estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {BK, (cuuint32_t)(BM / G::ITEMS), (cuuint32_t)G::ITEMS}, estr[3] = {1, 1, 1};
         if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(A), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
     }
-    {   // B: [k rows][n] floats per item viewed as {32, k, n/32, count}; box {32, 32 k-rows, BN/32 column blocks, 1 item}
-        const cuuint64_t dims[4] = {32, (cuuint64_t)k, (cuuint64_t)(n / 32), (cuuint64_t)s.count};
-        const cuuint64_t strides[3] = {(cuuint64_t)n * 4, 128, (cuuint64_t)k * n * 4};
-        const cuuint32_t box[4] = {32, BK, G::ITEMS > 1 ? 1u : (cuuint32_t)(BN / 32), (cuuint32_t)G::ITEMS}, estr[4] = {1, 1, 1, 1};
-        if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(B), dims, strides, box, estr,
+    {   // B: [k rows][n] floats per item, {n, k, count}; box = one 128-byte column block: 32 columns x 32 k-rows x 1 item
+        // (one copy per block: n only has to keep the row pitch a multiple of 16 bytes, columns past n arrive as zeros)
+        const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)k, (cuuint64_t)s.count};
+        const cuuint64_t strides[2] = {(cuuint64_t)n * 4, (cuuint64_t)k * n * 4};
+        const cuuint32_t box[3] = {32, BK, 1}, estr[3] = {1, 1, 1};
+        if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(B), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return T5I_CUDA;
     }
@@ -343,16 +355,24 @@ static inline double tf_waste(int m, int n, int T) {
 }
 
 // Shape rule of the tcgen05 Float product (also what t5_matmul_is_exact reports); *geo = tile edge (32: four items per tile).
-// TMA: row pitches must be whole 16-byte units (k % 4), B is viewed in 32-column blocks (n % 32); m is free.
-// Items of at least 48 x 64 x 32: smaller ones are served better by the exact kernels.
+// TMA: row pitches must be whole 16-byte units (k % 4, n % 4); m is free.
+// Items of at least 33 x 36 x 32 (smaller ones: the packed geometry below, or the exact kernels).
 // The tensor pipe is ~1/3 busy on full tiles (the kernel is HBM-bound), so up to 2x padded tile area is affordable;
 // between the two geometries the one with less padding wins, the larger tile on a tie (operands read once).
-// Items of 17..32 rows and exactly 32 columns (k >= 8) go four to a 128 tile (*geo = 32).
+// Items of at most 32 x 32 go four to a 128 tile (*geo = 32) once they carry ~8 KB (below that the per-tile pipeline cost,
+// not HBM, bounds the kernel and the exact kernels tie: 24^3 3.9 TB/s either way, 20^3 2.6 against 4.7), items of at most
+// 64 x 64 two to a tile (*geo = 2; 48^3: 2.0 TB/s exact, 3.1 one per 64 tile, 3.7 two per 128 tile; 64^3: 4.8 -> 5.7).
 bool tf32x3_takes(int m, int k, int n, int* geo_out) {
-    if (n == 32 && m >= 17 && m <= 32 && k % 4 == 0 && k >= 8) { if (geo_out) *geo_out = 32; return true; }
-    if (n % 32 || k % 4 || k < tf::BK || m < 48 || n < 64) return false;
+    if (n % 4 || k % 4 || k < 8) return false;
+    if (m <= 32 && n <= 32) {
+        if (m < 17 || n < 20 || m * k + k * n + m * n < 2048) return false;
+        if (geo_out) *geo_out = 32;
+        return true;
+    }
+    if (k < tf::BK || m < 33 || n < 36) return false;
+    if (m <= 64 && n <= 64) { if (geo_out) *geo_out = 2; return true; }
     const double w128 = tf_waste(m, n, 128), w64 = tf_waste(m, n, 64);
-    if (w128 > 2.0 && w64 > 2.0) return false;
+    if (w128 > 3.5 && w64 > 3.5) return false;
     if (geo_out) *geo_out = w128 <= w64 * 1.3 ? 128 : 64;
     return true;
 }
@@ -368,6 +388,7 @@ int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void
         if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo128::SMEM) != cudaSuccess) return T5I_CUDA;
         if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo64::SMEM) != cudaSuccess) return T5I_CUDA;
         if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo32x4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo32x4::SMEM) != cudaSuccess) return T5I_CUDA;
+        if (cudaFuncSetAttribute(tf::tf32x3_kernel<tf::Geo64x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tf::Geo64x2::SMEM) != cudaSuccess) return T5I_CUDA;
         configured[dev] = true;
     }
     if (s.count == 0) return T5I_OK;
@@ -375,6 +396,7 @@ int tf32x3_matmul(const Shard& s, int m, int k, int n, const void* A, const void
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < 1) sms = T5_SM_COUNT_FALLBACK;
     if (geo == 32) return tf::launch<tf::Geo32x4>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
+    if (geo == 2) return tf::launch<tf::Geo64x2>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
     return geo == 128 ? tf::launch<tf::Geo128>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms)
                : tf::launch<tf::Geo64>(s, m, k, n, (const float*)A, (const float*)B, (float*)C, sms);
 }

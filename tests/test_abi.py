@@ -125,9 +125,9 @@ def test_matmul_is_exact_reports_the_tensor_core_shape_rules():
         assert ex(tb.I64, *mkn), mkn
     for mkn in ((16, 32, 32), (32, 32, 16), (32, 12, 32), (32, 32, 20), (17, 32, 136), (8, 64, 64)):
         assert ex(tb.F64, *mkn), mkn
-    for mkn in ((128, 128, 128), (64, 64, 64), (96, 96, 96), (48, 32, 64), (32, 32, 32), (17, 8, 32)):
+    for mkn in ((128, 128, 128), (64, 64, 64), (96, 96, 96), (48, 32, 64), (32, 32, 32), (17, 40, 32), (48, 48, 48), (32, 32, 24), (28, 28, 28), (36, 32, 36)):
         assert not ex(tb.F32, *mkn), mkn
-    for mkn in ((16, 32, 32), (32, 32, 24), (48, 48, 48), (200, 32, 32), (64, 30, 64), (32, 6, 32)):
+    for mkn in ((16, 32, 32), (32, 32, 16), (17, 8, 32), (24, 24, 24), (24, 24, 22), (200, 32, 32), (64, 30, 64), (32, 6, 32), (100, 20, 36)):
         assert ex(tb.F32, *mkn), mkn
     import pytest
     with pytest.raises(tb.WrongListLength):

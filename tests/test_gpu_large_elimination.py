@@ -58,6 +58,25 @@ def test_large_det_inverse_solve_bit_exact(ctx, dc, n):
         assert np.array_equal(bits(X.to_numpy().reshape(batch, n, nrhs)), bits(ox)), f"solve {n} x {nrhs}"
 
 
+@pytest.mark.parametrize("n,batch", [(12, 9001), (24, 7919), (40, 2999)])
+def test_large_elimination_batches_beyond_one_wave(ctx, n, batch):
+    """More items than the grid holds at once (888 CTAs x 8 groups for the 4 x 4-thread geometry): every CTA loops, the
+    last pass is part empty - groups that share a warp with a group past the end of the batch recompute the last item
+    and must store nothing - and zero-pivot / singular items sit next to ordinary ones in the same warp."""
+    a = inputs(oracle.F64, n, batch, 80 + n)
+    A = ctx.from_numpy(a, (n, n))
+    assert np.array_equal(bits(tb.det(A).to_numpy()), bits(oracle.det(a, n, threads=8))), f"det {n}"
+    inv, st = tb.inverse(A)
+    oinv, ost = oracle.inverse(a, n, threads=8)
+    assert np.array_equal(st.to_numpy(), ost)
+    assert np.array_equal(bits(inv.to_numpy()), bits(oinv)), f"inverse {n}"
+    b = oracle.fill(oracle.F64, oracle.SEED_B, 80 + n, batch * n)
+    X, st = tb.solve(A, ctx.from_numpy(b, (n,)))
+    ox, ost2 = oracle.solve(a, b, n, 1, threads=8)
+    assert np.array_equal(st.to_numpy(), ost2)
+    assert np.array_equal(bits(X.to_numpy().reshape(batch, n, 1)), bits(ox)), f"solve {n}"
+
+
 @pytest.mark.parametrize("n", [16, 64])
 def test_large_inverse_is_an_inverse(ctx, n):
     """Independent of the oracle: A . A^-1 is the identity to rounding for well-conditioned items (diagonally dominant)."""

@@ -691,7 +691,11 @@ def test_exact_blocked_matmul_bit_exact(ctx, dc, mkn):
                                  (96, 96, 96), (100, 64, 96), (48, 32, 64), (130, 36, 160), (65, 128, 64), (200, 100, 96),
                                  (127, 44, 224), (257, 32, 64),
                                  # items of at most 32 x 32, four to a 128 tile (diagonal accumulator blocks), short and ragged K
-                                 (32, 32, 32), (17, 8, 32), (25, 44, 32), (32, 64, 32), (31, 12, 32)])
+                                 (32, 32, 32), (17, 40, 32), (25, 44, 32), (32, 64, 32), (31, 20, 32),
+                                 # column counts that are not multiples of 32 (one TMA box per 128-byte column block, columns past
+                                 # n zero-filled, the last block stored in part): packed and unpacked geometries
+                                 (28, 28, 28), (26, 32, 28), (32, 24, 28), (48, 48, 48), (40, 40, 40), (56, 64, 44), (36, 32, 36), (100, 32, 100),
+                                 (130, 36, 68), (64, 32, 36)])
 def test_tf32x3_matmul_within_tolerance(ctx, mkn):
     m, k, n = mkn
     assert not matmul_is_exact(oracle.F32, m, k, n)
