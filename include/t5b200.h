@@ -119,7 +119,7 @@ int t5_buf_layout(const t5_buf* buf);
  * Results are bit-identical to that fold for every element type and shape, with two
  * exceptions that run on the tensor cores and meet the stated tolerance instead
  * (|delta| <= tol * sum_j |A[i,j]||B[j,c]|); t5_matmul_is_exact answers for a given shape:
- *   Double, m >= 17, n >= 24, k >= 8, n and k multiples of 8, and a 32- / 48- / 64- / 96- / 128-tiling of
+ *   Double, m >= 17, n >= 24, k >= 8, n and k even, and a 32- / 48- / 64- / 96- / 128-tiling of
  *   the m x n result that is at least a quarter full (24 x 24 and 32 x 32 items, four to a tile, are;
  *   72 x 72 is; 17 x 136 is not): FP64 DMMA, tol 1e-12;
  *   Float, k and n multiples of 4: items of at least 33 x 36 with k >= 32 whose 64- or 128-tiling of the m x n

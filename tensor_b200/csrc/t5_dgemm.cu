@@ -35,12 +35,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // accumulators while the other keeps the FP64 tensor pipe busy, and no DMMA-warp issue slot
 // or register goes to address generation for the copies.
 //
-//   A map: dims {8, M, K/8, count}, box {8, BM, 4, 1}     -> shared [4][BM rows][8 doubles]
-//   B map: dims {8, K, N/8, count}, box {8, 32, BN/8, 1}  -> shared [BN/8][32 k-rows][8 doubles]
+//   A map: dims {K, M, count}, one box {8, BM, ITEMS} per group of 8 k    -> shared [4 k-groups][item][BM rows][8 doubles]
+//   B map: dims {N, K, count}, one box {8, 32, ITEMS} per group of 8 n    -> shared [BN/8 n-groups][item][32 k-rows][8 doubles]
 //   (64-byte rows, 16-B chunks XOR-ed with (row >> 1) & 3 by the TMA unit; stage bases 1024-B aligned)
 // The ITEM is its own outermost dimension (round 2): the part of a box beyond an item's M rows, N columns or K depth is
 // out of bounds for TMA and arrives as ZEROS, never as the next item's data, so shapes that are not multiples of the
-// tile run too - zero rows / columns / k-slices add nothing, and the epilogue stores only what exists.
+// tile run too - zero rows / columns / k-slices add nothing, and the epilogue stores only what exists.  One box per
+// 64-byte group (not one 4-D box over a {8, rows, cols/8} view): K and N only have to be EVEN (16-byte row pitch).
 //
 // The four k of a DMMA step are free to be any four k of the chunk as long as A and B agree.
 // Lane (g, t) of step s uses k = (t&1) + 2(s&1) + 4(t>>1) + 8((s>>1)&1) + 16(s>>2): with the
@@ -62,13 +63,13 @@ template <int BM_, int BN_, int STAGES_, int ITEMS_ = 1, int WM_ = 2, int WN_ = 
 struct Geo {
     static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_, ITEMS = ITEMS_, WM = WM_, WN = WN_;
     static constexpr int WTM = BM / WM, WTN = BN / WN, FI = WTM / 8, FJ = WTN / 8;
-    static constexpr int A_ITEM = BM * BK * 8, B_ITEM = BK * BN * 8;
-    static constexpr int A_STAGE = ITEMS * A_ITEM, B_STAGE = ITEMS * B_ITEM, STAGE = A_STAGE + B_STAGE;
+    static constexpr int A_GROUP = ITEMS * BM * 64, B_GROUP = ITEMS * BK * 64;       // one TMA box: 8 doubles x rows x items
+    static constexpr int A_STAGE = (BK / 8) * A_GROUP, B_STAGE = (BN / 8) * B_GROUP, STAGE = A_STAGE + B_STAGE;
     static constexpr int SMEM = STAGES * STAGE + 1024;     // + slack to align the ring to 1024 B
     static_assert(SMEM <= 227 * 1024, "ring does not fit");
     static_assert(WTN % 8 == 0 && WTM % 8 == 0, "warp tile must be whole 8x8 DMMA fragments");
     static_assert(ITEMS * WM * WN == CONSUMER_WARPS, "eight DMMA warps");
-    static_assert(A_ITEM % 1024 == 0 && B_ITEM % 1024 == 0, "item bases keep the swizzle phase");
+    static_assert(A_GROUP % 512 == 0 && B_GROUP % 512 == 0 && (BM * 64) % 512 == 0, "box and item bases keep the swizzle phase");
 };
 using Geo128 = Geo<128, 128, 3>;
 using Geo64 = Geo<64, 64, 6>;
@@ -128,8 +129,12 @@ dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(bar0 + 8 * (STAGES + s), ph ^ 1);              // stage released by all 8 warps
                 const unsigned full = bar0 + 8 * s;
                 mbar_expect_tx(full, STAGE);                              // (zero-filled parts of a box count too)
-                tma_load_4d(ring + s * STAGE, &mapA, full, 0, tm * BM, kc * (BK / 8), (int)item);
-                tma_load_4d(ring + s * STAGE + A_STAGE, &mapB, full, 0, kc * BK, tn * (BN / 8), (int)item);
+                #pragma unroll
+                for (int g8 = 0; g8 < BK / 8; ++g8)
+                    tma_load_3d(ring + s * STAGE + g8 * G::A_GROUP, &mapA, full, kc * BK + g8 * 8, tm * BM, (int)item);
+                #pragma unroll
+                for (int g8 = 0; g8 < BN / 8; ++g8)
+                    tma_load_3d(ring + s * STAGE + A_STAGE + g8 * G::B_GROUP, &mapB, full, tn * BN + g8 * 8, kc * BK, (int)item);
             }
         }
         return;
@@ -140,8 +145,8 @@ dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int g = lane >> 2, t = lane & 3, t0 = t & 1, t1 = t >> 1;
     const int wq = warp / (G::WM * G::WN), wm = (warp / G::WN) % G::WM, wn = warp % G::WN;   // item of the tile, warp row, warp column
     // runtime parts of the swizzled fragment addresses (see the header comment)
-    const unsigned a_thr = (unsigned)wq * G::A_ITEM + (unsigned)(wm * WTM + g) * 64u + (unsigned)t0 * 8u;
-    const unsigned b_thr = (unsigned)wq * G::B_ITEM + (unsigned)(wn * (WTN / 8)) * 2048u + (unsigned)(t0 + 4 * t1) * 64u + (unsigned)(g & 1) * 8u;
+    const unsigned a_thr = (unsigned)wq * (BM * 64) + (unsigned)(wm * WTM + g) * 64u + (unsigned)t0 * 8u;
+    const unsigned b_thr = (unsigned)wq * 2048u + (unsigned)(wn * (WTN / 8)) * G::B_GROUP + (unsigned)(t0 + 4 * t1) * 64u + (unsigned)(g & 1) * 8u;
     const unsigned x_thr = (unsigned)((g >> 1) ^ (2 * t1));                      // 16-B chunk = x_thr ^ (s & 1), both operands
 
     double acc[FI][FJ][2];
@@ -156,18 +161,18 @@ dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const unsigned s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(bar0 + 8 * s, ph);                                 // TMA bytes have landed
             const unsigned As = ring + s * STAGE + a_thr, Bs = ring + s * STAGE + A_STAGE + b_thr;
-            const int ksteps = (p.K - kc * BK) >> 2;                     // steps 0..s-1 hold exactly k < 4s when K % 8 == 0 (see the k order above)
+            const int ksteps = ((p.K - kc * BK + 7) >> 3) << 1;          // steps 0..s-1 (s even) hold exactly k < 4s (see the k order above)
             #pragma unroll
             for (int st = 0; st < BK / 4; ++st) {
                 if (st >= 2 && st >= ksteps) break;                       // K tail: nothing but zeros beyond
                 const unsigned chunk = (x_thr ^ (unsigned)(st & 1)) << 4;
-                const unsigned a_off = (unsigned)(st >> 1) * (unsigned)(BM * 64) + chunk;
+                const unsigned a_off = (unsigned)(st >> 1) * (unsigned)G::A_GROUP + chunk;
                 const unsigned b_off = (unsigned)(2 * (st & 1) + 8 * ((st >> 1) & 1) + 16 * (st >> 2)) * 64u + chunk;
                 double a[FI], b[FJ];
                 #pragma unroll
                 for (int i = 0; i < FI; ++i) a[i] = lds_f64(As + a_off + (unsigned)i * 512u);
                 #pragma unroll
-                for (int j = 0; j < FJ; ++j) b[j] = lds_f64(Bs + b_off + (unsigned)j * 2048u);
+                for (int j = 0; j < FJ; ++j) b[j] = lds_f64(Bs + b_off + (unsigned)j * (unsigned)G::B_GROUP);
                 #pragma unroll
                 for (int i = 0; i < FI; ++i)
                     #pragma unroll
@@ -196,15 +201,15 @@ dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
 }
 
-// `count` items of rows x cols doubles, row-major, viewed as {8, rows, cols/8, count}; box {8, box_rows, box_grp, box_items}
-static bool make_map(CUtensorMap* map, const void* base, unsigned long long count, int rows, int cols, int box_rows, int box_grp, int box_items) {
+// `count` items of rows x cols doubles, row-major: {cols, rows, count}; box {8 doubles, box_rows, box_items}
+static bool make_map(CUtensorMap* map, const void* base, unsigned long long count, int rows, int cols, int box_rows, int box_items) {
     TensorMapEncodeFn enc = tensor_map_encoder();
     if (!enc) return false;
-    const cuuint64_t dims[4] = {8, (cuuint64_t)rows, (cuuint64_t)(cols / 8), count};
-    const cuuint64_t strides[3] = {(cuuint64_t)cols * 8, 64, (cuuint64_t)rows * cols * 8};
-    const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_grp, (cuuint32_t)box_items};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, estr,
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, count};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)rows * cols * 8};
+    const cuuint32_t box[3] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_items};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -214,8 +219,8 @@ static int launch(const Shard& s, int m, int k, int n, const double* A, const do
     constexpr int BM = G::BM, BN = G::BN;
     if (s.count > 0x7fffffffull) return T5I_UNSUPPORTED;                  // TMA coordinates are int32
     CUtensorMap ma, mb;
-    if (!make_map(&ma, A, (unsigned long long)s.count, m, k, BM, BK / 8, G::ITEMS)) return T5I_CUDA;
-    if (!make_map(&mb, B, (unsigned long long)s.count, k, n, BK, BN / 8, G::ITEMS)) return T5I_CUDA;
+    if (!make_map(&ma, A, (unsigned long long)s.count, m, k, BM, G::ITEMS)) return T5I_CUDA;
+    if (!make_map(&mb, B, (unsigned long long)s.count, k, n, BK, G::ITEMS)) return T5I_CUDA;
     const unsigned long long tiles = G::ITEMS > 1 ? ((unsigned long long)s.count + G::ITEMS - 1) / G::ITEMS
                                                   : (unsigned long long)s.count * ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     const int grid = (int)(tiles < (unsigned long long)sms ? tiles : (unsigned long long)sms);
@@ -227,13 +232,13 @@ static int launch(const Shard& s, int m, int k, int n, const double* A, const do
 
 
 // Shape rule of the FP64 tensor-core product (also what t5_matmul_is_exact reports); *geo = tile edge chosen.
-// TMA views rows in groups of 8 doubles (k % 8 for A, n % 8 for B); m is free.
+// TMA needs 16-byte row pitches: k and n even; m is free.
 // Geometry = the least padded tile area (ties and near-ties go to the larger tile: more operand reuse per byte of
 // shared-memory traffic).  Measured against the exact kernels (profiles/r02r_dmma_small_items.txt): the tensor pipe wins
 // from 17 x 24 items on (24^3: 4.2 -> 6.7 TB/s, 32^3: 3.6 -> 6.0, 48^3: 1.9 -> 4.1) and still by 1.8x when two thirds of
 // the tile are padding (72^3 on the 128 tile), so only thin items stay on the SIMT kernels.
 bool dmma_takes(int m, int k, int n, int* geo_out) {
-    if (n % 8 || k % 8 || k < 8 || m < 17 || n < 24) return false;
+    if (n % 2 || k % 2 || k < 8 || m < 17 || n < 24) return false;
     const double area = (double)m * n;
     auto padded = [&](int T) { return (double)((m + T - 1) / T * T) * (double)((n + T - 1) / T * T) / area; };
     int geo = 128; double best = padded(128);

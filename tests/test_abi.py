@@ -120,10 +120,10 @@ def test_matmul_is_exact_reports_the_tensor_core_shape_rules():
     for dt in (tb.F64, tb.F32, tb.I64):
         for mkn in ((3, 3, 3), (4, 4, 4), (8, 8, 8), (16, 16, 16), (4, 4, 1), (1, 64, 1), (20, 20, 20), (65, 17, 63)):
             assert ex(dt, *mkn), (dt, mkn)
-    for mkn in ((128, 128, 128), (64, 64, 64), (32, 32, 32), (24, 24, 24), (48, 48, 48), (96, 96, 96), (17, 8, 24), (72, 72, 72)):
+    for mkn in ((128, 128, 128), (64, 64, 64), (32, 32, 32), (24, 24, 24), (48, 48, 48), (96, 96, 96), (17, 8, 24), (72, 72, 72), (32, 12, 32), (100, 100, 100), (50, 10, 26)):
         assert not ex(tb.F64, *mkn), mkn
         assert ex(tb.I64, *mkn), mkn
-    for mkn in ((16, 32, 32), (32, 32, 16), (32, 12, 32), (32, 32, 20), (17, 32, 136), (8, 64, 64)):
+    for mkn in ((16, 32, 32), (32, 32, 16), (32, 13, 32), (32, 32, 25), (32, 32, 20), (17, 32, 136), (8, 64, 64)):
         assert ex(tb.F64, *mkn), mkn
     for mkn in ((128, 128, 128), (64, 64, 64), (96, 96, 96), (48, 32, 64), (32, 32, 32), (17, 40, 32), (48, 48, 48), (32, 32, 24), (28, 28, 28), (36, 32, 36)):
         assert not ex(tb.F32, *mkn), mkn

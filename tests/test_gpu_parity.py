@@ -643,7 +643,9 @@ def test_full_size_float128_tcgen05_properties(ctx):
                                  # items of at most 32 x 32 (four to a tile) and 48 x 48 (two to a tile), the 96 tile, K tails
                                  # of 8 / 16 / 24 (skipped k-steps), K shorter than one chunk
                                  (32, 32, 32), (24, 24, 24), (17, 8, 24), (25, 40, 32), (32, 16, 32), (31, 56, 24),
-                                 (48, 48, 48), (40, 40, 40), (33, 24, 48), (72, 72, 72), (80, 88, 80), (160, 48, 160), (192, 72, 96)])
+                                 (48, 48, 48), (40, 40, 40), (33, 24, 48), (72, 72, 72), (80, 88, 80), (160, 48, 160), (192, 72, 96),
+                                 # k and n that are only EVEN (one TMA box per 64-byte group, partial groups zero-filled, odd k-step counts)
+                                 (100, 100, 100), (50, 50, 50), (30, 10, 26), (18, 22, 24), (66, 34, 70), (129, 14, 130), (32, 12, 30)])
 def test_dmma_matmul_within_tolerance(ctx, mkn):
     m, k, n = mkn
     assert not matmul_is_exact(oracle.F64, m, k, n)
