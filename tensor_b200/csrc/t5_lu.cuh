@@ -11,21 +11,25 @@
 // matrix.  All register indices are compile-time (the run-time front only appears in predicates), so the
 // matrix never touches local memory.
 //
-// One elimination step k (two CTA barriers):
-// One elimination step k (ONE CTA barrier; row k and the raw column k were published by step k - 1):
+// One elimination step k (row k and the raw column k were published by step k - 1):
 //   1. pivot = row[k]; exactly zero -> slow path: first row p > k with a non-zero entry in column k (atomicMin),
 //      swap rows k and p WHOLE (stored multipliers included), republish; none -> singular
-//   2. every thread divides for ITS rows: f(i) = column[i] / pivot for i > k (exact division through the pivot's
-//      hoisted reciprocal; solve / inverse also keep f(i) in the shared factor array, where the zero would go)
+//   2. the multipliers f(i) = column[i] / pivot for i > k.  n <= 64 (TG <= 8): ONE division per row - thread t divides
+//      for row t and the quotients travel through shared memory (one more group barrier).  TG = 16: every thread divides
+//      for ITS rows through the pivot's hoisted reciprocal, as one batch (no second barrier: with only the TG owners of
+//      column k dividing, 15/16 of a 256-thread CTA idled through the division latency every step - 3.5x slower at
+//      n = 128).  solve / inverse also keep f(i) in the shared factor array, where the zero would go.
 //   3. every thread: w[i][j] = w[i][j] - f(i) * row[j] for its i > k, j > k  (2 NB shared loads per NB^2 updates)
 //   4. the owners of row k + 1 and of column k + 1 publish them (double-buffered by the parity of k)   -- barrier
-// (A first version let only the TG owners of column k divide, behind a second barrier: 15/16 of the CTA idled through
-// the FP64 division latency every step - 3.5x slower at n = 128.)
-// The tile index of the front, k / TG, is CTA-uniform: each of the three parts is a `switch` over it into code whose
-// register indices and loop bounds are compile-time constants (the first version selected tile rows with
-// run-time select chains: 57 % of its executed instructions were FSEL / ISETP / LOP3, ncu).  Register columns the
-// front has passed are dead - nothing reads them again - so they take part in the update unconditionally (garbage in,
-// garbage out, column by column) instead of costing a predicate per element.
+// The tile index of the front, A = k / TG, is the OUTER compile-time loop (static_for) and the owner index k mod TG the
+// inner run-time one, so every register index and loop bound in the step is a constant with no per-step dispatch.
+// (History: run-time select chains over the tile rows - 57 % FSEL / ISETP / LOP3; then a `switch` on k / TG three
+// times per step - indirect branches, 10 % of the issued instructions and the largest stall sites; ncu.)  Register
+// columns the front has passed are dead - nothing reads them again - so they take part in the update unconditionally
+// (garbage in, garbage out, column by column) instead of costing a predicate per element.
+// Groups that share a warp (4 x 4 threads, two matrices per warp) run in lockstep: same trip counts (a group past the
+// end of the batch recomputes the last item and stores nothing), the pivot slow path entered warp-wide, a singular
+// group computing on and zero-filling at the end - so their barrier is the plain full-mask __syncwarp.
 // Per element the operations and their order are the oracle's (oracle/t5_oracle.cpp forward_eliminate): updates
 // in ascending k, multiply-round-subtract-round (this TU is compiled with -fmad=false -prec-div=true), pivot =
 // FIRST non-zero, so det, the factors and everything derived from them are BIT-IDENTICAL to the oracle.
@@ -84,7 +88,7 @@ __device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
 // memory and its own barrier - the CTA barrier when the CTA is one group, a masked __syncwarp when a group is part of a
 // warp (TG = 4: two matrices per warp, every warp independent of the others - no CTA-wide barrier anywhere).
 template <class T, int TG, int NB, int MODE, int G, bool ONEDIV>
-__global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {
+__global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-register cap for 8 CTAs per SM spilled: det 16x16 0.665 -> 0.729 ms)
     constexpr int THREADS = TG * TG;                   // threads of ONE group
     constexpr int NMAX = TG * NB;
     static_assert(G == 1 || THREADS <= 32, "several groups per CTA only when a group fits in a warp");
