@@ -103,7 +103,7 @@ int rowlane_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, con
 // bit-identical to the oracle like every other elimination kernel
 int lu_det(const Shard& s, int dtype, int n, const void* A, void* O);
 // ---- t5_warp_lu.cuh (t5_warp_lu_det.cu / _solve.cu / _inverse.cu): a matrix row per lane, shuffles only (AoS): Float
-// 9 <= n <= 16 and 30 <= n <= 32, Double solve with <= 4 right-hand sides for 9 <= n <= 16; T5I_NOT_SPECIALISED otherwise
+// 9 <= n <= 16 and 30 <= n <= 32; T5I_NOT_SPECIALISED otherwise (Double, other sizes)
 int warp_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int warp_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
 int warp_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);

@@ -87,7 +87,7 @@ __device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
 // G groups of TG x TG threads per CTA, one matrix per group.  Groups never interact: each has its own slice of shared
 // memory and its own barrier - the CTA barrier when the CTA is one group, a masked __syncwarp when a group is part of a
 // warp (TG = 4: two matrices per warp, every warp independent of the others - no CTA-wide barrier anywhere).
-template <class T, int TG, int NB, int MODE, int G, bool ONEDIV>
+template <class T, int TG, int NB, int MODE, int G, bool ONEDIV, bool RIDE>
 __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-register cap for 8 CTAs per SM spilled: det 16x16 0.665 -> 0.729 ms)
     constexpr int THREADS = TG * TG;                   // threads of ONE group
     constexpr int NMAX = TG * NB;
@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
     T* fcol = prow + 2 * NMAX;                          // [2][NMAX]   published raw column of the step (the numerators of the multipliers)
     T* xrow = fcol + 2 * NMAX;                          // [2][NMAX]   row exchange for swaps
     T* fmul = xrow + 2 * NMAX;                          // [NMAX]      (ONEDIV) multipliers f(i, k) of the current step, one division per thread
-    int* perm = reinterpret_cast<int*>(fmul + NMAX);    // [NMAX] row i of the permuted system = row perm[i] of the input
+    T* prb = fmul + NMAX;                               // [2][TG]     (RIDE) right-hand-side entries of the published pivot row
+    T* xrb = prb + 2 * TG;                              // [2][TG]     (RIDE) right-hand-side entries of the rows exchanged by a swap
+    int* perm = reinterpret_cast<int*>(xrb + 2 * TG);    // [NMAX] row i of the permuted system = row perm[i] of the input
     int* ctl = perm + NMAX;                             // [4] pivot search result, swap count
     T* LU = reinterpret_cast<T*>(ctl + 4);              // [n][ldl]  (MODE != 0): U on and above the diagonal, multipliers below
     T* Y = LU + (MODE != 0 ? (size_t)p.n * p.ldl : 0);  // [n][ldy]  (MODE != 0)
@@ -129,6 +131,19 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                 const int i = ty + TG * a, j = tx + TG * b;
                 w[a][b] = (i < n && j < n) ? __ldg(a_item + (size_t)i * n + j) : T(0);
             }
+        // RIDE (solve with at most TG right-hand sides): the right-hand sides ride along as one more tile column of the
+        // working matrix - row i of B next to row i of A, column c in thread column c - and take every swap and update
+        // together with their row, exactly as the oracle eliminates [A | B]; the separate forward substitution (n more
+        // barriers) is gone (profiles/r02ap_time_lu.txt).
+        T wb[RIDE ? NB : 1];
+        if constexpr (RIDE) {
+            const T* b_item = (const T*)p.B + item * (unsigned long long)n * p.nrhs;
+            #pragma unroll
+            for (int a = 0; a < NB; ++a) {
+                const int i = ty + TG * a;
+                wb[a] = (i < n && tx < p.nrhs) ? __ldg(b_item + (size_t)i * p.nrhs + tx) : T(0);
+            }
+        }
         for (int i = tid; i < NMAX; i += THREADS) perm[i] = i;     // (a 4 x 4 group has fewer threads than rows)
         if (tid == 0) ctl[1] = 0;
         T acc = T(1);                                   // thread 0: running product of the pivots
@@ -150,6 +165,7 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                 if (ty == r1) {
                     #pragma unroll
                     for (int b = A1; b < NB; ++b) pr1[tx + TG * b] = w[A1][b];     // (columns before the front are dead)
+                    if constexpr (RIDE) prb[(k1 & 1) * TG + tx] = wb[A1];
                 }
                 if (tx == r1) {
                     #pragma unroll
@@ -194,12 +210,14 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                     if (ty == rk) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) xrow[tx + TG * b] = w[A][b];
+                        if constexpr (RIDE) xrb[tx] = wb[A];
                     }
                     if (ty == rp)
                         with_tile_index<NB>(ap, [&](auto P_) {
                             constexpr int P = decltype(P_)::value;
                             #pragma unroll
                             for (int b = 0; b < NB; ++b) xrow[NMAX + tx + TG * b] = w[P][b];
+                            if constexpr (RIDE) xrb[TG + tx] = wb[P];
                         });
                     group_sync();
                     if (ty == rp && pidx != k)                            // first: when one thread owns both rows they are different tile rows
@@ -207,12 +225,14 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                             constexpr int P = decltype(P_)::value;
                             #pragma unroll
                             for (int b = 0; b < NB; ++b) w[P][b] = xrow[tx + TG * b];
+                            if constexpr (RIDE) wb[P] = xrb[tx];
                         });
                     if (ty == rk) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) w[A][b] = xrow[NMAX + tx + TG * b];
+                        if constexpr (RIDE) wb[A] = xrb[TG + tx];
                     }
-                    if (MODE != 0 && pidx != k)
+                    if (MODE != 0 && !RIDE && pidx != k)
                         for (int j = tid; j < k; j += THREADS) {
                             const T t = LU[(size_t)k * p.ldl + j];
                             LU[(size_t)k * p.ldl + j] = LU[(size_t)pidx * p.ldl + j];
@@ -231,12 +251,14 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                     for (int i = k + 1 + tid; i < n; i += THREADS) {
                         const T f = cr[i] / piv;
                         fmul[i] = f;
-                        if (MODE != 0) LU[(size_t)i * p.ldl + k] = f;             // the multiplier goes where the zero would go
+                        if (MODE != 0 && !RIDE) LU[(size_t)i * p.ldl + k] = f;    // the multiplier goes where the zero would go (RIDE: nothing replays it)
                     }
                     group_sync();
                     T prj[NB];
                     #pragma unroll
                     for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
+                    const T prbj = RIDE ? prb[(k & 1) * TG + tx] : T(0);
+                    (void)prbj;
                     #pragma unroll
                     for (int a = A; a < NB; ++a) {
                         // rows of tile row A are past the front only for ty > rk; later tile rows are, whole; rows >= n do not exist
@@ -244,6 +266,7 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                             const T f = fmul[ty + TG * a];
                             #pragma unroll
                             for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f * prj[b];
+                            if constexpr (RIDE) wb[a] = wb[a] - f * prbj;
                         }
                     }
                 } else {
@@ -274,9 +297,10 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                     for (int a = A; a < NB; ++a) {
                         if ((a > A || ty > rk) && a < a_end) {
                             if constexpr (!BATCH) f[a] = rc.div(cr[ty + TG * a]);
-                            if (MODE != 0 && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f[a];   // the multiplier goes where the zero would go
+                            if (MODE != 0 && !RIDE && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f[a];   // the multiplier goes where the zero would go
                             #pragma unroll
                             for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f[a] * prj[b];
+                            if constexpr (RIDE) wb[a] = wb[a] - f[a] * prb[(k & 1) * TG + tx];
                         }
                     }
                 }
@@ -319,45 +343,53 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
         for (int c0 = 0; c0 < nrhs; c0 += p.chunk) {
             // right-hand sides of this pass, rows already permuted; same cyclic distribution (NB x NB tile, columns c0 + tx + TG b)
             T y[NB][NB];
-            #pragma unroll
-            for (int a = 0; a < NB; ++a)
+            if constexpr (RIDE) {
+                // the right-hand sides were eliminated together with A (one pass: nrhs <= TG = chunk)
                 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const int i = ty + TG * a, c = c0 + tx + TG * b;
-                    T v = T(0);
-                    if (i < n && c < nrhs && TG * b < p.chunk) {
-                        const int src = perm[i];
-                        v = MODE == 2 ? (src == c ? T(1) : T(0)) : __ldg(gB + (size_t)src * nrhs + c);
-                    }
-                    y[a][b] = v;
-                }
-            const int nbl = p.chunk / TG;                 // column tiles of this pass that hold right-hand sides (1 for a single vector)
-            static_for<0, NB>([&](auto A_) {              // tile index of row k outside, owner index inside: no per-step dispatch
-                constexpr int A = decltype(A_)::value;
-                const int rk_end = n - A * TG < TG ? n - A * TG : TG;
-                for (int rk = 0; rk < rk_end; ++rk) {
-                    const int k = A * TG + rk;
-                    T* pr = prow + (k & 1) * NMAX;
-                    if (ty == rk) {
-                        #pragma unroll
-                        for (int b = 0; b < NB; ++b)
-                            if (b < nbl) pr[tx + TG * b] = y[A][b];
-                    }
-                    group_sync();
-                    T prj[NB];
+                for (int a = 0; a < NB; ++a)
                     #pragma unroll
-                    for (int b = 0; b < NB; ++b) prj[b] = b < nbl ? pr[tx + TG * b] : T(0);
+                    for (int b = 0; b < NB; ++b) y[a][b] = b == 0 ? wb[a] : T(0);
+            } else {
+                #pragma unroll
+                for (int a = 0; a < NB; ++a)
                     #pragma unroll
-                    for (int a = A; a < NB; ++a) {
-                        if ((a > A || ty > rk) && a < a_end) {
-                            const T f = LU[(size_t)(ty + TG * a) * p.ldl + k];
+                    for (int b = 0; b < NB; ++b) {
+                        const int i = ty + TG * a, c = c0 + tx + TG * b;
+                        T v = T(0);
+                        if (i < n && c < nrhs && TG * b < p.chunk) {
+                            const int src = perm[i];
+                            v = MODE == 2 ? (src == c ? T(1) : T(0)) : __ldg(gB + (size_t)src * nrhs + c);
+                        }
+                        y[a][b] = v;
+                    }
+                const int nbl = p.chunk / TG;                 // column tiles of this pass that hold right-hand sides (1 for a single vector)
+                static_for<0, NB>([&](auto A_) {              // tile index of row k outside, owner index inside: no per-step dispatch
+                    constexpr int A = decltype(A_)::value;
+                    const int rk_end = n - A * TG < TG ? n - A * TG : TG;
+                    for (int rk = 0; rk < rk_end; ++rk) {
+                        const int k = A * TG + rk;
+                        T* pr = prow + (k & 1) * NMAX;
+                        if (ty == rk) {
                             #pragma unroll
                             for (int b = 0; b < NB; ++b)
-                                if (b < nbl) y[a][b] = y[a][b] - f * prj[b];
+                                if (b < nbl) pr[tx + TG * b] = y[A][b];
+                        }
+                        group_sync();
+                        T prj[NB];
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) prj[b] = b < nbl ? pr[tx + TG * b] : T(0);
+                        #pragma unroll
+                        for (int a = A; a < NB; ++a) {
+                            if ((a > A || ty > rk) && a < a_end) {
+                                const T f = LU[(size_t)(ty + TG * a) * p.ldl + k];
+                                #pragma unroll
+                                for (int b = 0; b < NB; ++b)
+                                    if (b < nbl) y[a][b] = y[a][b] - f * prj[b];
+                            }
                         }
                     }
-                }
-            });
+                });
+            }
             #pragma unroll
             for (int a = 0; a < NB; ++a)
                 #pragma unroll
@@ -406,13 +438,13 @@ static int sm_count() {
     return n;
 }
 
-template <class T, int TG, int NB, int MODE, int G = 1, bool ONEDIV = (TG <= 8)>
+template <class T, int TG, int NB, int MODE, int G = 1, bool RIDE = false, bool ONEDIV = (TG <= 8)>
 static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
     constexpr int NMAX = TG * NB;
     Args p;
     p.A = A; p.B = B; p.X = X; p.status = (unsigned char*)status; p.count = s.count; p.n = n; p.nrhs = nrhs;
     p.ldl = n | 1;                                           // odd pitch: rows a thread-row apart land in different banks
-    size_t smem = sizeof(T) * 7 * NMAX + sizeof(int) * (NMAX + 4);
+    size_t smem = sizeof(T) * (7 * NMAX + 4 * TG) + sizeof(int) * (NMAX + 4);
     p.chunk = TG; p.ldy = 1;
     if (MODE != 0) {
         // as many right-hand-side columns per pass as the tile holds and shared memory allows (the factors stay resident)
@@ -428,7 +460,7 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
     p.group_smem = (unsigned)smem;
     smem *= G;
     if (smem > 227 * 1024) return T5I_UNSUPPORTED;
-    auto kern = lu_kernel<T, TG, NB, MODE, G, ONEDIV>;
+    auto kern = lu_kernel<T, TG, NB, MODE, G, ONEDIV, RIDE>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return T5I_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TG * TG * G, smem) != cudaSuccess || per_sm < 1) return T5I_CUDA;
@@ -452,7 +484,8 @@ static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* 
     // warp - a group synchronises with a masked __syncwarp, so no warp ever waits for another: det 16x16 Double
     // 1.85 -> 0.95 ms (1.13 TB/s), inverse 5.29 -> 2.72 ms, 9x9 det 2.17 -> 1.08 ms (tools/time_lu.py, profiles/r02m_*).
     // Heavier tiles (inverse from n = 17, everything dense from n = 25) do better spread over 64 threads.
-#define LU_LAUNCH(TG_, NB_, G_) return launch<T, TG_, NB_, MODE, G_>(s, n, nrhs, A, B, X, status)
+#define LU_LAUNCH(TG_, NB_, G_) do { if (MODE == 1 && nrhs <= TG_) return launch<T, TG_, NB_, MODE, G_, MODE == 1>(s, n, nrhs, A, B, X, status); \
+        return launch<T, TG_, NB_, MODE, G_>(s, n, nrhs, A, B, X, status); } while (0)
     const bool light = MODE == 0 || (MODE == 1 && nrhs <= 4);
     if (n <= 8) LU_LAUNCH(4, 2, 8);
     if (n <= 16) LU_LAUNCH(4, 4, 8);

@@ -7,10 +7,11 @@
 // Scope, from measurements (tools/time_lu.py, profiles/r02am_warp_lu.txt).  The kernel is bound by the shuffle /
 // shared-memory data path (ncu of det 16x16 Double: 82 % of the LSU wavefront peak, `mio_throttle` the top stall): an
 // entry of the pivot row costs one SHFL per 32 bits against the multiply + subtract it feeds.  So it serves
-//   Float,  9 <= n <= 16 and 30 <= n <= 32: det, inverse, solve  (16x16: solve 3.17 -> 1.46 ms, inverse 3.48 -> 2.29)
-//   Double, 9 <= n <= 16: solve with at most 4 right-hand sides   (16x16: 2.10 -> 1.52 ms)
-// and everything else stays on t5_lu.cuh (Double det / inverse: two SHFL per entry lose to its shared-memory tiles;
-// 17 <= n <= 29: too many idle lanes in a 32-lane frame).  Two variants that were tried and dropped: publishing the
+//   Float,  9 <= n <= 16: det, inverse, solve        (16x16: solve 2.39 -> 1.46 ms, inverse 3.48 -> 2.29)
+//   Float, 30 <= n <= 32: det, inverse, solve with more than 8 right-hand sides   (32x32 inverse 8.04 -> 6.34)
+// and everything else stays on t5_lu.cuh (Double: two SHFL per entry lose to its shared-memory tiles, so the
+// kernel is instantiated for Float only; 17 <= n <= 29: too many idle lanes in a
+// 32-lane frame; few right-hand sides at n >= 30: t5_lu.cuh eliminates them together with A).  Two variants that were tried and dropped: publishing the
 // pivot row through shared memory with 16-byte broadcast loads and a zero row for the lanes above the front (no per-element
 // select), and shuffling the next pivot out early to overlap its reciprocal - neither beat the plain version.
 //
@@ -228,33 +229,22 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
 // Sizes and element types of the scope table above; T5I_NOT_SPECIALISED otherwise (the caller goes on to t5_lu.cuh).
 template <class T, int MODE>
 static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
+    static_assert(sizeof(T) == 4, "instantiated for Float only: with two SHFL per entry Double loses to t5_lu.cuh at every size");
     if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
     const bool small = n >= 9 && n <= 16, wide = n >= 30 && n <= 32;
-    if (sizeof(T) == 8) {
-        if (!(MODE == 1 && small && nrhs >= 1 && nrhs <= 4)) return T5I_NOT_SPECIALISED;
-    } else {
-        if (!small && !wide) return T5I_NOT_SPECIALISED;
-        if (MODE == 1 && (nrhs < 1 || nrhs > (small ? 16 : 32))) return T5I_NOT_SPECIALISED;
-    }
+    if (!small && !wide) return T5I_NOT_SPECIALISED;
+    if (MODE == 1 && (nrhs < 1 || nrhs > (small ? 16 : 32))) return T5I_NOT_SPECIALISED;
+    if (MODE == 1 && wide && nrhs <= 8) return T5I_NOT_SPECIALISED;   // t5_lu.cuh with the right-hand sides riding along: 2.67 vs 2.90 ms
     if (s.count == 0) return T5I_OK;
     if constexpr (MODE == 0) {
-        if constexpr (sizeof(T) == 8) return T5I_NOT_SPECIALISED;
-        else return small ? launch<T, 16, 0, 0>(s, n, 0, A, B, X, status) : launch<T, 32, 0, 0>(s, n, 0, A, B, X, status);
+        return small ? launch<T, 16, 0, 0>(s, n, 0, A, B, X, status) : launch<T, 32, 0, 0>(s, n, 0, A, B, X, status);
     } else if constexpr (MODE == 2) {
-        if constexpr (sizeof(T) == 8) return T5I_NOT_SPECIALISED;
-        else return small ? launch<T, 16, 2, 16>(s, n, n, A, B, X, status) : launch<T, 32, 2, 32>(s, n, n, A, B, X, status);
+        return small ? launch<T, 16, 2, 16>(s, n, n, A, B, X, status) : launch<T, 32, 2, 32>(s, n, n, A, B, X, status);
     } else {
-        if (small) {
-            if (nrhs == 1) return launch<T, 16, 1, 1>(s, n, nrhs, A, B, X, status);
-            if (nrhs <= 4) return launch<T, 16, 1, 4>(s, n, nrhs, A, B, X, status);
-            if constexpr (sizeof(T) == 4) return launch<T, 16, 1, 16>(s, n, nrhs, A, B, X, status);
-        }
-        if constexpr (sizeof(T) == 4) {
-            if (nrhs == 1) return launch<T, 32, 1, 1>(s, n, nrhs, A, B, X, status);
-            if (nrhs <= 4) return launch<T, 32, 1, 4>(s, n, nrhs, A, B, X, status);
-            return launch<T, 32, 1, 32>(s, n, nrhs, A, B, X, status);
-        }
-        return T5I_NOT_SPECIALISED;
+        if (!small) return launch<T, 32, 1, 32>(s, n, nrhs, A, B, X, status);
+        if (nrhs == 1) return launch<T, 16, 1, 1>(s, n, nrhs, A, B, X, status);
+        if (nrhs <= 4) return launch<T, 16, 1, 4>(s, n, nrhs, A, B, X, status);
+        return launch<T, 16, 1, 16>(s, n, nrhs, A, B, X, status);
     }
 }
 

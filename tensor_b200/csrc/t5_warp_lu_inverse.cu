@@ -1,9 +1,8 @@
-// inverse for 9 <= n <= 32, a matrix row per lane (t5_warp_lu.cuh, MODE 2).  One operation per TU so that they compile in parallel.
+// inverse Float, 9 <= n <= 16 and 30 <= n <= 32, a matrix row per lane (t5_warp_lu.cuh, MODE 2).  One operation per TU so that they compile in parallel.
 #include "t5_warp_lu.cuh"
 
 namespace t5 {
 int warp_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status) {
-    if (dtype == T5D_F64) return wlu::dispatch<double, 2>(s, n, n, A, nullptr, O, status);
     if (dtype == T5D_F32) return wlu::dispatch<float, 2>(s, n, n, A, nullptr, O, status);
     return T5I_NOT_SPECIALISED;
 }
