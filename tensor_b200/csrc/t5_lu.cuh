@@ -87,7 +87,7 @@ __device__ __forceinline__ void with_tile_index(int a_rt, F&& fn) {
 // G groups of TG x TG threads per CTA, one matrix per group.  Groups never interact: each has its own slice of shared
 // memory and its own barrier - the CTA barrier when the CTA is one group, a masked __syncwarp when a group is part of a
 // warp (TG = 4: two matrices per warp, every warp independent of the others - no CTA-wide barrier anywhere).
-template <class T, int TG, int NB, int MODE, int G, bool ONEDIV, bool RIDE>
+template <class T, int TG, int NB, int MODE, int G, bool ONEDIV, int NBR>
 __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-register cap for 8 CTAs per SM spilled: det 16x16 0.665 -> 0.729 ms)
     constexpr int THREADS = TG * TG;                   // threads of ONE group
     constexpr int NMAX = TG * NB;
@@ -104,9 +104,11 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
     T* fcol = prow + 2 * NMAX;                          // [2][NMAX]   published raw column of the step (the numerators of the multipliers)
     T* xrow = fcol + 2 * NMAX;                          // [2][NMAX]   row exchange for swaps
     T* fmul = xrow + 2 * NMAX;                          // [NMAX]      (ONEDIV) multipliers f(i, k) of the current step, one division per thread
-    T* prb = fmul + NMAX;                               // [2][TG]     (RIDE) right-hand-side entries of the published pivot row
-    T* xrb = prb + 2 * TG;                              // [2][TG]     (RIDE) right-hand-side entries of the rows exchanged by a swap
-    int* perm = reinterpret_cast<int*>(xrb + 2 * TG);    // [NMAX] row i of the permuted system = row perm[i] of the input
+    constexpr bool RIDE = NBR > 0;                      // right-hand sides eliminated together with A, NBR tile columns of them
+    constexpr int RW = TG * (NBR > 0 ? NBR : 1);
+    T* prb = fmul + NMAX;                               // [2][RW]     (RIDE) right-hand-side entries of the published pivot row
+    T* xrb = prb + 2 * RW;                              // [2][RW]     (RIDE) right-hand-side entries of the rows exchanged by a swap
+    int* perm = reinterpret_cast<int*>(xrb + 2 * RW);    // [NMAX] row i of the permuted system = row perm[i] of the input
     int* ctl = perm + NMAX;                             // [4] pivot search result, swap count
     T* LU = reinterpret_cast<T*>(ctl + 4);              // [n][ldl]  (MODE != 0): U on and above the diagonal, multipliers below
     T* Y = LU + (MODE != 0 ? (size_t)p.n * p.ldl : 0);  // [n][ldy]  (MODE != 0)
@@ -131,18 +133,21 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                 const int i = ty + TG * a, j = tx + TG * b;
                 w[a][b] = (i < n && j < n) ? __ldg(a_item + (size_t)i * n + j) : T(0);
             }
-        // RIDE (solve with at most TG right-hand sides): the right-hand sides ride along as one more tile column of the
-        // working matrix - row i of B next to row i of A, column c in thread column c - and take every swap and update
-        // together with their row, exactly as the oracle eliminates [A | B]; the separate forward substitution (n more
-        // barriers) is gone (profiles/r02ap_time_lu.txt).
-        T wb[RIDE ? NB : 1];
+        // RIDE (solve with at most TG * NBR right-hand sides; inverse for NB <= 4): the right-hand sides ride along as NBR
+        // more tile columns of the working matrix - row i of B next to row i of A, column c in thread column c mod TG - and
+        // take every swap and update together with their row, exactly as the oracle eliminates [A | B]; the separate
+        // forward substitution (n more barriers) is gone (profiles/r02ar_time_lu.txt, r02as_time_lu.txt).
+        T wb[RIDE ? NB : 1][RIDE ? NBR : 1];
         if constexpr (RIDE) {
-            const T* b_item = (const T*)p.B + item * (unsigned long long)n * p.nrhs;
+            const T* b_item = MODE == 1 ? (const T*)p.B + item * (unsigned long long)n * p.nrhs : nullptr;
             #pragma unroll
-            for (int a = 0; a < NB; ++a) {
-                const int i = ty + TG * a;
-                wb[a] = (i < n && tx < p.nrhs) ? __ldg(b_item + (size_t)i * p.nrhs + tx) : T(0);
-            }
+            for (int a = 0; a < NB; ++a)
+                #pragma unroll
+                for (int b = 0; b < NBR; ++b) {
+                    const int i = ty + TG * a, c = tx + TG * b;
+                    if constexpr (MODE == 2) wb[a][b] = (i < n && i == c) ? T(1) : T(0);
+                    else wb[a][b] = (i < n && c < p.nrhs) ? __ldg(b_item + (size_t)i * p.nrhs + c) : T(0);
+                }
         }
         for (int i = tid; i < NMAX; i += THREADS) perm[i] = i;     // (a 4 x 4 group has fewer threads than rows)
         if (tid == 0) ctl[1] = 0;
@@ -165,7 +170,10 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                 if (ty == r1) {
                     #pragma unroll
                     for (int b = A1; b < NB; ++b) pr1[tx + TG * b] = w[A1][b];     // (columns before the front are dead)
-                    if constexpr (RIDE) prb[(k1 & 1) * TG + tx] = wb[A1];
+                    if constexpr (RIDE) {
+                        #pragma unroll
+                        for (int b = 0; b < NBR; ++b) prb[(k1 & 1) * RW + tx + TG * b] = wb[A1][b];
+                    }
                 }
                 if (tx == r1) {
                     #pragma unroll
@@ -210,14 +218,20 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                     if (ty == rk) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) xrow[tx + TG * b] = w[A][b];
-                        if constexpr (RIDE) xrb[tx] = wb[A];
+                        if constexpr (RIDE) {
+                            #pragma unroll
+                            for (int b = 0; b < NBR; ++b) xrb[tx + TG * b] = wb[A][b];
+                        }
                     }
                     if (ty == rp)
                         with_tile_index<NB>(ap, [&](auto P_) {
                             constexpr int P = decltype(P_)::value;
                             #pragma unroll
                             for (int b = 0; b < NB; ++b) xrow[NMAX + tx + TG * b] = w[P][b];
-                            if constexpr (RIDE) xrb[TG + tx] = wb[P];
+                            if constexpr (RIDE) {
+                                #pragma unroll
+                                for (int b = 0; b < NBR; ++b) xrb[RW + tx + TG * b] = wb[P][b];
+                            }
                         });
                     group_sync();
                     if (ty == rp && pidx != k)                            // first: when one thread owns both rows they are different tile rows
@@ -225,12 +239,18 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                             constexpr int P = decltype(P_)::value;
                             #pragma unroll
                             for (int b = 0; b < NB; ++b) w[P][b] = xrow[tx + TG * b];
-                            if constexpr (RIDE) wb[P] = xrb[tx];
+                            if constexpr (RIDE) {
+                                #pragma unroll
+                                for (int b = 0; b < NBR; ++b) wb[P][b] = xrb[tx + TG * b];
+                            }
                         });
                     if (ty == rk) {
                         #pragma unroll
                         for (int b = 0; b < NB; ++b) w[A][b] = xrow[NMAX + tx + TG * b];
-                        if constexpr (RIDE) wb[A] = xrb[TG + tx];
+                        if constexpr (RIDE) {
+                            #pragma unroll
+                            for (int b = 0; b < NBR; ++b) wb[A][b] = xrb[RW + tx + TG * b];
+                        }
                     }
                     if (MODE != 0 && !RIDE && pidx != k)
                         for (int j = tid; j < k; j += THREADS) {
@@ -257,7 +277,9 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                     T prj[NB];
                     #pragma unroll
                     for (int b = A; b < NB; ++b) prj[b] = pr[tx + TG * b];
-                    const T prbj = RIDE ? prb[(k & 1) * TG + tx] : T(0);
+                    T prbj[RIDE ? NBR : 1];
+                    #pragma unroll
+                    for (int b = 0; b < (RIDE ? NBR : 1); ++b) prbj[b] = RIDE ? prb[(k & 1) * RW + tx + TG * b] : T(0);
                     (void)prbj;
                     #pragma unroll
                     for (int a = A; a < NB; ++a) {
@@ -266,7 +288,10 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                             const T f = fmul[ty + TG * a];
                             #pragma unroll
                             for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f * prj[b];
-                            if constexpr (RIDE) wb[a] = wb[a] - f * prbj;
+                            if constexpr (RIDE) {
+                                #pragma unroll
+                                for (int b = 0; b < NBR; ++b) wb[a][b] = wb[a][b] - f * prbj[b];
+                            }
                         }
                     }
                 } else {
@@ -300,7 +325,10 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
                             if (MODE != 0 && !RIDE && tx == rk) LU[(size_t)(ty + TG * a) * p.ldl + k] = f[a];   // the multiplier goes where the zero would go
                             #pragma unroll
                             for (int b = A; b < NB; ++b) w[a][b] = w[a][b] - f[a] * prj[b];
-                            if constexpr (RIDE) wb[a] = wb[a] - f[a] * prb[(k & 1) * TG + tx];
+                            if constexpr (RIDE) {
+                                #pragma unroll
+                                for (int b = 0; b < NBR; ++b) wb[a][b] = wb[a][b] - f[a] * prb[(k & 1) * RW + tx + TG * b];
+                            }
                         }
                     }
                 }
@@ -344,11 +372,11 @@ __global__ void __launch_bounds__(TG * TG * G) lu_kernel(Args p) {   // (a 64-re
             // right-hand sides of this pass, rows already permuted; same cyclic distribution (NB x NB tile, columns c0 + tx + TG b)
             T y[NB][NB];
             if constexpr (RIDE) {
-                // the right-hand sides were eliminated together with A (one pass: nrhs <= TG = chunk)
+                // the right-hand sides were eliminated together with A (one pass: nrhs <= TG * NBR = chunk)
                 #pragma unroll
                 for (int a = 0; a < NB; ++a)
                     #pragma unroll
-                    for (int b = 0; b < NB; ++b) y[a][b] = b == 0 ? wb[a] : T(0);
+                    for (int b = 0; b < NB; ++b) y[a][b] = b < NBR ? wb[a][b < NBR ? b : 0] : T(0);
             } else {
                 #pragma unroll
                 for (int a = 0; a < NB; ++a)
@@ -438,13 +466,13 @@ static int sm_count() {
     return n;
 }
 
-template <class T, int TG, int NB, int MODE, int G = 1, bool RIDE = false, bool ONEDIV = (TG <= 8)>
+template <class T, int TG, int NB, int MODE, int G = 1, int NBR = 0, bool ONEDIV = (TG <= 8)>
 static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
     constexpr int NMAX = TG * NB;
     Args p;
     p.A = A; p.B = B; p.X = X; p.status = (unsigned char*)status; p.count = s.count; p.n = n; p.nrhs = nrhs;
     p.ldl = n | 1;                                           // odd pitch: rows a thread-row apart land in different banks
-    size_t smem = sizeof(T) * (7 * NMAX + 4 * TG) + sizeof(int) * (NMAX + 4);
+    size_t smem = sizeof(T) * (7 * NMAX + 4 * TG * (NBR > 0 ? NBR : 1)) + sizeof(int) * (NMAX + 4);
     p.chunk = TG; p.ldy = 1;
     if (MODE != 0) {
         // as many right-hand-side columns per pass as the tile holds and shared memory allows (the factors stay resident)
@@ -452,6 +480,7 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
         int chunk = ((nrhs + TG - 1) / TG) * TG;
         if (chunk > NMAX) chunk = NMAX;
         while (chunk > TG && smem + sizeof(T) * ((size_t)n * p.ldl + (size_t)n * (chunk | 1)) > budget) chunk -= TG;
+        if (NBR > 0 && chunk < nrhs) return launch<T, TG, NB, MODE, G, 0, ONEDIV>(s, n, nrhs, A, B, X, status);   // (does not fit one pass)
         p.chunk = chunk;
         p.ldy = chunk | 1;
         smem += sizeof(T) * ((size_t)n * p.ldl + (size_t)n * p.ldy);
@@ -460,7 +489,7 @@ static int launch(const Shard& s, int n, int nrhs, const void* A, const void* B,
     p.group_smem = (unsigned)smem;
     smem *= G;
     if (smem > 227 * 1024) return T5I_UNSUPPORTED;
-    auto kern = lu_kernel<T, TG, NB, MODE, G, ONEDIV, RIDE>;
+    auto kern = lu_kernel<T, TG, NB, MODE, G, ONEDIV, NBR>;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return T5I_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TG * TG * G, smem) != cudaSuccess || per_sm < 1) return T5I_CUDA;
@@ -484,7 +513,15 @@ static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* 
     // warp - a group synchronises with a masked __syncwarp, so no warp ever waits for another: det 16x16 Double
     // 1.85 -> 0.95 ms (1.13 TB/s), inverse 5.29 -> 2.72 ms, 9x9 det 2.17 -> 1.08 ms (tools/time_lu.py, profiles/r02m_*).
     // Heavier tiles (inverse from n = 17, everything dense from n = 25) do better spread over 64 threads.
-#define LU_LAUNCH(TG_, NB_, G_) do { if (MODE == 1 && nrhs <= TG_) return launch<T, TG_, NB_, MODE, G_, MODE == 1>(s, n, nrhs, A, B, X, status); \
+    // right-hand sides that ride along with the elimination (NBR tile columns): one column tile for solves with at most TG
+    // right-hand sides at any n; up to n right-hand sides while the tile is small (NB <= 4); the whole identity of `inverse`
+    // for 17 <= n <= 32 (8 x 8 threads: 32x32 Double 4.84 -> 4.05 ms, 24x24 4.60 -> 3.95; with 4 x 4 threads per matrix the
+    // doubled register tile cost more than the forward pass it saves: 16x16 2.27 -> 2.46)
+#define LU_LAUNCH(TG_, NB_, G_) do { \
+        constexpr int FULL_ = (NB_ <= 4) ? NB_ : 0; \
+        if (MODE == 2 && FULL_ > 0 && TG_ == 8) return launch<T, TG_, NB_, MODE, G_, (MODE == 2 && TG_ == 8 ? FULL_ : 0)>(s, n, nrhs, A, B, X, status); \
+        if (MODE == 1 && nrhs <= TG_) return launch<T, TG_, NB_, MODE, G_, (MODE == 1 ? 1 : 0)>(s, n, nrhs, A, B, X, status); \
+        if (MODE == 1 && FULL_ > 1 && nrhs <= TG_ * NB_) return launch<T, TG_, NB_, MODE, G_, (MODE == 1 ? FULL_ : 0)>(s, n, nrhs, A, B, X, status); \
         return launch<T, TG_, NB_, MODE, G_>(s, n, nrhs, A, B, X, status); } while (0)
     const bool light = MODE == 0 || (MODE == 1 && nrhs <= 4);
     if (n <= 8) LU_LAUNCH(4, 2, 8);
