@@ -121,6 +121,8 @@ WORKLOADS = {
                                      desc="256Ki 100x20 . 20x36 Float (no tensor-core tiling fits: exact blocked SIMT product, packed FFMA2 multiply then add)"),
     "matmul64_f64_256K": dict(op="matmul", dtype="f64", m=64, k=64, n=64, batch=1 << 18, bytes=98304, flops=524288, bound="tensor",
                               desc="256Ki 64x64 Double .*. on FP64 tensor cores (smallest DMMA shape; 5.3 flop/B, HBM floor ~= tensor floor)"),
+    "solve32_f64_128K": dict(op="solve", dtype="f64", n=32, batch=1 << 17, bytes=8705, bound="hbm",
+                             desc="128Ki 32x32 Double solve, one right-hand side (CTA per matrix; the right-hand side rides along with the elimination)"),
     "matmul32_f64_1M": dict(op="matmul", dtype="f64", m=32, k=32, n=32, batch=1 << 20, bytes=24576, flops=65536, bound="hbm",
                             desc="1Mi 32x32 Double .*. on FP64 tensor cores (four items per DMMA tile through item-dimension tensor maps; 2.7 flop/B: HBM-bound)"),
     "matmul48_f64_512K": dict(op="matmul", dtype="f64", m=48, k=48, n=48, batch=1 << 19, bytes=55296, flops=221184, bound="hbm",

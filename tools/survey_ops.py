@@ -145,13 +145,16 @@ def main():
             add(f"pure 4x4 {tag}", B * 16 * es, lambda: tb.pure(ctx, 1.5, (4, 4), dt, B))
             for x in (B8, v8, v64a, v64b, v4a, v4b, A2, B2, A16, B16, A12, B12, I8, B44):
                 x.free()
-            # round 2: eliminations beyond n = 8 (CTA per matrix), the SoA detour of an AoS-only kernel, a ragged Float product
+            # round 2: eliminations beyond n = 8 (a CTA, or for Float 9..16 / 30..32 a half-warp / warp, per matrix), the SoA detour
+            # of an AoS-only kernel, ragged and item-packed tensor-core products
             for nn in (16, 32, 64, 128):
                 Bn = max(256, (B * 16) // (nn * nn))
                 An = ctx.synthetic((nn, nn), dt, Bn, SEED, 40).plant_specials(1024, 65536)
-                add(f"det {nn}x{nn} (CTA per matrix) {tag}", Bn * (nn * nn + 1) * es, lambda: tb.det(An))
-                add(f"inverse {nn}x{nn} (CTA per matrix) {tag}", Bn * (2 * nn * nn * es + 1), lambda: tb.inverse(An))
-                An.free()
+                bn = ctx.synthetic((nn,), dt, Bn, SEED + 1, 40)
+                add(f"det {nn}x{nn} (n > 8 kernels) {tag}", Bn * (nn * nn + 1) * es, lambda: tb.det(An))
+                add(f"solve {nn}x{nn}, 1 rhs (n > 8 kernels) {tag}", Bn * ((nn * nn + 2 * nn) * es + 1), lambda: tb.solve(An, bn))
+                add(f"inverse {nn}x{nn} (n > 8 kernels) {tag}", Bn * (2 * nn * nn * es + 1), lambda: tb.inverse(An))
+                An.free(); bn.free()
             A32s, B32s = A32.relayout(tb.SOA), B32.relayout(tb.SOA)
             add(f"SoA matmul 32x32 (detour: relayout in, AoS kernel, relayout out) {tag}", (B // 64) * 3072 * es, lambda: tb.matmul(A32s, B32s))
             A32s.free(); B32s.free()
