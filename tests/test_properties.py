@@ -6,6 +6,8 @@ tests/MultiIndex.hs), restated with hypothesis over RANDOM shapes:
   the same equalities the reference checks, but on shapes hypothesis chooses;
 * GPU (marked): the same round trips and the linear-algebra metamorphic identities through the C ABI
   on random small shapes, every result compared with the oracle bit for bit."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
@@ -18,7 +20,8 @@ from tensor_b200 import _lib
 
 dims_st = st.lists(st.integers(1, 4), min_size=1, max_size=4)
 CPU = settings(max_examples=60, deadline=None)
-GPU = settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+GPU = settings(max_examples=int(os.environ.get("T5_HYP_EXAMPLES", "40")), deadline=None,
+               suppress_health_check=[HealthCheck.function_scoped_fixture])   # (T5_HYP_EXAMPLES=400 for a soak run)
 
 
 def flat(dims, start=0):
