@@ -181,7 +181,8 @@ def test_transpose_golden(ctx):
 
 @pytest.mark.parametrize("dc", ALL)
 @pytest.mark.parametrize("dims", [(4, 4), (3, 3), (2, 3), (4, 1), (5,), (2, 3, 4), (8, 8), (3, 1, 2, 2), (16, 16),
-                                  (17, 33), (32, 32), (20, 40), (64, 16), (16, 1, 31), (15, 40), (128, 128), (100, 130)])
+                                  (17, 33), (32, 32), (20, 40), (64, 16), (16, 1, 31), (15, 40), (128, 128), (100, 130),
+                                  (48, 50), (66, 190), (64, 64), (130, 48)])      # (4-byte elements, even extents >= 48: 64 x 64 tiles, 8-byte accesses)
 @pytest.mark.parametrize("layout", [tb.AOS, tb.SOA])
 def test_transpose_bit_exact_and_involution(ctx, dc, dims, layout):
     d = int(np.prod(dims))
