@@ -109,6 +109,11 @@ class Batch {
     std::shared_ptr<t5_buf> buf_;
 };
 
+// Is (.*.) of an I x J by a J x K matrix of this element type the bit-exact sequential fold (true), or does the library run it
+// on the tensor cores within BASELINE.json's tolerance (include/t5b200.h, t5_matmul)?  Pure: shape and element type only.
+template <class T, size_t I, size_t J, size_t K>
+inline bool product_is_exact() { return t5_matmul_is_exact(dtype_of<T>::value, (int)I, (int)J, (int)K) == 1; }
+
 template <class T, size_t I, size_t J, size_t K>
 Batch<T, I, K> operator*(const Batch<T, I, J>& a, const Batch<T, J, K>& b) {     // (.*.) matrix . matrix
     Batch<T, I, K> c(a.ctx(), a.count());

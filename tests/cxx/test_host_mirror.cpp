@@ -200,6 +200,12 @@ int main() {
         expect_bits("t `at` [3] (column 3)", col3.to_list(), wc);
         expect_bits("slice [Nothing, Just 3] == at [3]", slice<2>(A, {0, 3}).to_list(), wc);
 
+        // the numerical contract is queryable without a device: tiny products are the exact fold, large Double / Float ones are not
+        if (!product_is_exact<double, 3, 3, 3>() || !product_is_exact<int64_t, 128, 128, 128>() ||
+            product_is_exact<double, 128, 128, 128>() || product_is_exact<float, 64, 64, 64>()) {
+            std::printf("FAIL product_is_exact\n");
+            ++failures;
+        }
         std::vector<double> hc(n * 8), hinv(n * 16), hi_want(n * 16);
         matmul_host<double, 2, 3, 4>(ctx, n, a.data(), b.data(), hc.data());
         expect_bits("matmul_host (host arrays, one call)", hc, wp);
