@@ -528,7 +528,6 @@ static int dispatch(const Shard& s, int n, int nrhs, const void* A, const void* 
     if (n <= 16) LU_LAUNCH(4, 4, 8);
     if (n <= 24 && light) LU_LAUNCH(4, 6, 8);
     if (n <= 32 && MODE == 1 && nrhs <= 4) LU_LAUNCH(4, 8, 8);
-    if (n <= 16) LU_LAUNCH(8, 2, 1);
     if (n <= 24) LU_LAUNCH(8, 3, 1);
     if (n <= 32) LU_LAUNCH(8, 4, 1);
     if (n <= 40) LU_LAUNCH(8, 5, 1);
