@@ -477,6 +477,7 @@ static int product_shard(const Shard& s, int dtype, int P, int K, int Q, int nc,
     if (s.layout == T5L_AOS && dtype == T5D_F64 && nc != 0) r = dmma_matmul(s, P, K, Q, A, B, C);
     if (s.layout == T5L_AOS && dtype == T5D_F32 && nc != 0) r = tf32x3_matmul(s, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0) r = small_matmul(s, dtype, P, K, Q, A, B, C);
+    if (r == T5I_NOT_SPECIALISED && nc == 0) r = small_outer(s, dtype, P, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0) r = mid_matmul(s, dtype, P, K, Q, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0 && P == 1 && Q == 1 && K > 4) r = generic_longdot(s, dtype, K, A, B, C);
     if (r == T5I_NOT_SPECIALISED && nc != 0 && s.layout == T5L_AOS) r = generic_stagedprod(s, dtype, P, K, Q, A, B, C);

@@ -35,6 +35,7 @@ struct Shard {
 
 // ---- t5_small_ops.cu: register-resident thread-per-item kernels -----------------
 int small_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, const void* B, void* C);
+int small_outer(const Shard& s, int dtype, int p, int q, const void* A, const void* B, void* C);   // tiny outer products (tile pipeline)
 int small_transpose(const Shard& s, int elem_bytes, int r, int c, const void* A, void* O);
 int small_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int small_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);

@@ -45,6 +45,11 @@ template <class T, int N, int R> struct Geo<SolveOp<T, N, R>> {
                                     std::conditional_t<(N <= 3), G<128, 1, 2, 6>, G<64, 1, 2, 8>>>;
 };
 
+template <class T, int P, int Q> struct Geo<OuterOp<T, P, Q>> {     // by the size of the result record
+    using type = std::conditional_t<(P * Q * sizeof(T) >= 512), G<64, 1, 1>,
+                 std::conditional_t<(P * Q * sizeof(T) >= 128), G<64, 1, 2>, G<128, 1, 2>>>;
+};
+
 template <class T>
 static int matmul_t(const Shard& s, int m, int k, int n, const void* A, const void* B, void* C) {
 #define T5_MM(M_, K_, N_) \
@@ -66,6 +71,30 @@ int small_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, 
         case T5D_F64: return matmul_t<double>(s, m, k, n, A, B, C);
         case T5D_F32: return matmul_t<float>(s, m, k, n, A, B, C);
         case T5D_I64: return matmul_t<long long>(s, m, k, n, A, B, C);
+    }
+    return T5I_NOT_SPECIALISED;
+}
+
+// Tiny outer products (rank-1 (x) rank-1 up to 4 (x) 4, and 3x3 (x) 3x3 / 4x4 (x) 4x4 seen as 9 (x) 9 / 16 (x) 16) in the tile
+// pipeline: a record per thread, the P * Q results leave as whole 16-byte chunks of the tile (the coalesced-run kernel
+// of t5_generic.cu writes one element per thread: 3x3 (x) 3x3 Float 3.2 -> 5.6 TB/s, 4x4 (x) 4x4 Float 2.9 -> 6.2,
+// 4 (x) 4 Double 4.3 -> 5.6; tools/survey_ops.py).
+template <class T>
+static int outer_t(const Shard& s, int p, int q, const void* A, const void* B, void* C) {
+#define T5_OUT(P_, Q_) \
+    if (p == P_ && q == Q_) return launch_op<OuterOp<T, P_, Q_>>(s, A, B, C, nullptr);
+    T5_OUT(2, 2) T5_OUT(3, 3) T5_OUT(4, 4) T5_OUT(2, 3) T5_OUT(3, 2) T5_OUT(2, 4) T5_OUT(4, 2) T5_OUT(3, 4) T5_OUT(4, 3)
+    T5_OUT(9, 9) T5_OUT(4, 9) T5_OUT(9, 4) T5_OUT(3, 9) T5_OUT(9, 3)
+    if constexpr (sizeof(T) == 4) { T5_OUT(16, 16) T5_OUT(4, 16) T5_OUT(16, 4) }     // (8-byte 16 (x) 16 = 2 KB of results per thread: the streaming kernel's)
+#undef T5_OUT
+    return T5I_NOT_SPECIALISED;
+}
+int small_outer(const Shard& s, int dtype, int p, int q, const void* A, const void* B, void* C) {
+    if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;      // SoA: the vectorised SoA outer product of t5_generic.cu
+    switch (dtype) {
+        case T5D_F64: return outer_t<double>(s, p, q, A, B, C);
+        case T5D_F32: return outer_t<float>(s, p, q, A, B, C);
+        case T5D_I64: return outer_t<long long>(s, p, q, A, B, C);
     }
     return T5I_NOT_SPECIALISED;
 }

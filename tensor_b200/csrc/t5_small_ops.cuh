@@ -27,6 +27,21 @@ struct MatmulOp {
     }
 };
 
+// ---- outer product (prod 0 / tensor product of tiny tensors): C[p,q] = A[p] * B[q], ONE multiply per output
+// (no `0 +`: the sign of a zero product is the multiply's; §8a a8) ------------------------
+template <class T, int P, int Q>
+struct OuterOp {
+    using In0 = Rec<T, P>; using In1 = Rec<T, Q>;
+    using Out0 = Rec<T, P * Q>; using Out1 = NoRec;
+    __device__ __forceinline__ static void run(const T* a, const T* b, T* c, unsigned char*) {
+        using R = Arith<T>;
+        #pragma unroll
+        for (int i = 0; i < P; ++i)
+            #pragma unroll
+            for (int j = 0; j < Q; ++j) c[i * Q + j] = R::mul(a[i], b[j]);
+    }
+};
+
 // ---- transpose of an R x C matrix: pure register renaming (§8a a4) -----------------
 template <class T, int R_, int C_>
 struct TransposeOp {
