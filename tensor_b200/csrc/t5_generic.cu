@@ -5,6 +5,7 @@
 #include "t5_device.cuh"
 #include "t5_internal.h"
 #include "t5_recip.cuh"
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -449,6 +450,115 @@ gather2_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__
     }
 }
 
+// Staged form of the gathers above for records of up to a few KB (append / split / at / ta / slice / axis permutations of
+// tiny tensors): the direct kernels move one element per lane and instruction - 128-byte warp accesses for Float, and source
+// reads that follow the table - and reached 0.55-0.83 of the HBM peak.  Here G consecutive items arrive as ONE contiguous
+// run per operand (16-byte cp.async), the index tables sit in shared memory, and every result leaves as 16-byte vectors of
+// its own contiguous run, each lane collecting its 2 / 4 elements from the staged records.  Up to two sources (table value
+// v < dA: A[v], else B[v - dA]) and two results (split: both halves from one read of the input).
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+staged_gather_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ O1, T* __restrict__ O2,
+                     const uint32_t* __restrict__ t1, const uint32_t* __restrict__ t2, unsigned dA, unsigned dB, unsigned d1, unsigned d2,
+                     unsigned long long count, unsigned G, unsigned offB, unsigned offT) {
+    constexpr unsigned V = 16 / sizeof(T);
+    struct alignas(16) Vec { T v[V]; };
+    extern __shared__ __align__(16) unsigned char sg_smem[];
+    T* sA = reinterpret_cast<T*>(sg_smem);
+    T* sB = sA + offB;
+    uint32_t* sT1 = reinterpret_cast<uint32_t*>(sA + offT);
+    uint32_t* sT2 = sT1 + d1;
+    for (unsigned i = threadIdx.x; i < d1; i += THREADS) sT1[i] = __ldg(t1 + i);
+    for (unsigned i = threadIdx.x; i < d2; i += THREADS) sT2[i] = __ldg(t2 + i);
+    for (unsigned long long g0 = (unsigned long long)blockIdx.x * G; g0 < count; g0 += (unsigned long long)gridDim.x * G) {
+        const unsigned long long left = count - g0;
+        const unsigned gc = left < (unsigned long long)G ? (unsigned)left : G;
+        __syncthreads();                                     // the previous group has left shared memory (and the tables are in)
+        #pragma unroll
+        for (int op = 0; op < 2; ++op) {
+            const unsigned dd = op ? dB : dA;
+            if (dd == 0) continue;
+            const T* src = (op ? B : A) + (size_t)g0 * dd;   // g0 % V == 0: 16-byte aligned
+            T* dst = op ? sB : sA;
+            const unsigned total = gc * dd, nvec = total / V;
+            for (unsigned l = threadIdx.x; l < nvec; l += THREADS) cp_async16(dst + l * V, src + l * V);
+            for (unsigned l = nvec * V + threadIdx.x; l < total; l += THREADS) dst[l] = __ldg(src + l);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        #pragma unroll
+        for (int res = 0; res < 2; ++res) {
+            const unsigned dd = res ? d2 : d1;
+            if (dd == 0) continue;
+            const uint32_t* tab = res ? sT2 : sT1;
+            T* out = (res ? O2 : O1) + (size_t)g0 * dd;
+            const unsigned total = gc * dd, nvec = total / V;
+            const unsigned step_q = (THREADS * V) / dd, step_r = THREADS * V - step_q * dd;
+            unsigned il = (threadIdx.x * V) / dd, i = threadIdx.x * V - il * dd;
+            for (unsigned lv = threadIdx.x; lv < nvec; lv += THREADS) {
+                Vec o;
+                unsigned il2 = il, i2 = i;
+                #pragma unroll
+                for (unsigned u = 0; u < V; ++u) {
+                    const unsigned v = tab[i2];
+                    o.v[u] = v < dA ? sA[il2 * dA + v] : sB[il2 * dB + (v - dA)];
+                    if (++i2 == dd) { i2 = 0; ++il2; }
+                }
+                *reinterpret_cast<Vec*>(out + (size_t)lv * V) = o;
+                il += step_q; i += step_r;
+                if (i >= dd) { i -= dd; ++il; }
+            }
+            for (unsigned l = nvec * V + threadIdx.x; l < total; l += THREADS) {      // (< V elements: the last group of an odd batch)
+                const unsigned il2 = l / dd, v = tab[l - il2 * dd];
+                out[l] = v < dA ? sA[il2 * dA + v] : sB[il2 * dB + (v - dA)];
+            }
+        }
+    }
+}
+
+// Records that can be staged: V of them in 24 KB, tables of at most 2048 entries.  Measured on 4Mi items (TB/s, direct ->
+// staged): Float append 3x3|3 4.4 -> 5.4, split 4x4 3.7 -> 5.2, split 8x8 3.8 -> 5.0, permutations of 2x3x4 5.1 -> 5.3; Double
+// split 4x4 3.9 -> 5.4, split 8x8 3.7 -> 5.3 - but Double append 5.4 -> 5.3, permutations 5.9 -> 5.7, transpose 8x8 6.4 -> 5.5, and
+// picks of a third or a quarter of the record (at / ta / slice) 2-6 % slower in both types: the direct gather reads only the
+// sectors it needs.  So: 4-byte elements when the results are at least half the record, 8-byte elements for the split only.
+bool staged_gather_fits(int elem_bytes, size_t d_in_total, size_t d_out_total, bool two_results) {
+    if (elem_bytes != 4 && elem_bytes != 8) return false;
+    if (elem_bytes == 8 && !two_results) return false;
+    const size_t V = 16 / elem_bytes;
+    return d_in_total > 0 && d_out_total <= 2048 && d_in_total * elem_bytes * V <= 24 * 1024 && d_out_total * 2 >= d_in_total;
+}
+
+// T5I_NOT_SPECIALISED when the records are too large to stage (the direct kernels take them)
+int staged_gather(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d1, size_t d2, const uint32_t* t1, const uint32_t* t2,
+                  const void* A, const void* B, void* O1, void* O2) {
+    constexpr int THREADS = 256;
+    static const bool off = getenv("T5_NO_STAGED_GATHER") != nullptr;       // tuning hook
+    if (off || s.layout != T5L_AOS || !staged_gather_fits(elem_bytes, dA + dB, d1 + d2, d1 && d2)) return T5I_NOT_SPECIALISED;
+    if (s.count == 0 || d1 + d2 == 0) return T5I_OK;
+    const size_t V = 16 / elem_bytes, item = (dA + dB) * elem_bytes;
+    if ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)O1 | (uintptr_t)O2) & 15) != 0) return T5I_NOT_SPECIALISED;
+    size_t G = (24 * 1024) / item / V * V;
+    const size_t want = (size_t)THREADS * V * 4;                       // ~4 result vectors per thread and group are plenty
+    const size_t dmin = d1 == 0 ? d2 : d2 == 0 ? d1 : (d2 < d1 ? d2 : d1);
+    if (G * dmin > want) G = ((want + dmin - 1) / dmin + V - 1) / V * V;
+    if (G < V) G = V;
+    const size_t offB = (G * dA + V - 1) / V * V, offT = offB + (G * dB + V - 1) / V * V;
+    const size_t smem = offT * elem_bytes + (d1 + d2) * 4;
+    const void* kern = elem_bytes == 8 ? (const void*)staged_gather_kernel<unsigned long long, THREADS> : (const void*)staged_gather_kernel<unsigned, THREADS>;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const size_t groups = (s.count + G - 1) / G, cap = (size_t)occ * sm_count();
+    const int grid = (int)(groups < cap ? groups : cap);
+    if (elem_bytes == 8)
+        staged_gather_kernel<unsigned long long, THREADS><<<grid, THREADS, smem, s.stream>>>((const unsigned long long*)A, (const unsigned long long*)B,
+            (unsigned long long*)O1, (unsigned long long*)O2, t1, t2, (unsigned)dA, (unsigned)dB, (unsigned)d1, (unsigned)d2, s.count, (unsigned)G, (unsigned)offB, (unsigned)offT);
+    else
+        staged_gather_kernel<unsigned, THREADS><<<grid, THREADS, smem, s.stream>>>((const unsigned*)A, (const unsigned*)B,
+            (unsigned*)O1, (unsigned*)O2, t1, t2, (unsigned)dA, (unsigned)dB, (unsigned)d1, (unsigned)d2, s.count, (unsigned)G, (unsigned)offB, (unsigned)offT);
+    return ok();
+}
+
 static int gather_geometry(const void* kern, size_t count, size_t d_out, int threads, int* G) {
     int g = (int)((threads * 16 + d_out - 1) / d_out);
     if (g < 1) g = 1;
@@ -461,6 +571,10 @@ int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, co
     if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
     if (s.count == 0 || d_out == 0) return T5I_OK;
     if (d_in > (1u << 28) || d_out > (1u << 28)) return T5I_UNSUPPORTED;
+    {
+        const int r = staged_gather(s, elem_bytes, d_in, 0, d_out, 0, table_dev, nullptr, A, nullptr, O, nullptr);
+        if (r != T5I_NOT_SPECIALISED) return r;
+    }
     int G;
     const int grid = gather_geometry(elem_bytes == 8 ? (const void*)gather_kernel<unsigned long long, THREADS>
                                                      : (const void*)gather_kernel<unsigned, THREADS>, s.count, d_out, THREADS, &G);
@@ -479,6 +593,10 @@ int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t
     if (s.layout != T5L_AOS) return T5I_UNSUPPORTED;
     if (s.count == 0 || d_out == 0) return T5I_OK;
     if (dA + dB > (1u << 28) || d_out > (1u << 28)) return T5I_UNSUPPORTED;
+    {
+        const int r = staged_gather(s, elem_bytes, dA, dB, d_out, 0, table_dev, nullptr, A, B, O, nullptr);
+        if (r != T5I_NOT_SPECIALISED) return r;
+    }
     int G;
     const int grid = gather_geometry(elem_bytes == 8 ? (const void*)gather2_kernel<unsigned long long, THREADS>
                                                      : (const void*)gather2_kernel<unsigned, THREADS>, s.count, d_out, THREADS, &G);
@@ -949,6 +1067,66 @@ soa_prod_reg_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restr
         }
     }
 }
+// The same contraction with the result COLUMNS split over QS warps of the CTA (warp w: items of group w / QS, columns
+// [h * Q/QS, (h + 1) * Q/QS) with h = w % QS).  A thread keeps K * Q/QS elements of B instead of K * Q - 8x8 Double: 192
+// registers and 8 warps per SM become ~128 and 16 - and the rows of A run DEPTH ahead; the QS warps of a group read
+// the same rows of A, the second time from L1.  Per result element nothing changes (acc = 0; k ascending).
+template <class T, int K, int Q, int QS, int DEPTH>
+__global__ void __launch_bounds__(128, 4)
+soa_prod_split_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int P, unsigned long long count, unsigned long long stride) {
+    using R = Arith<T>;
+    constexpr int QH = Q / QS, GROUP = 128 / QS;              // items per CTA
+    static_assert(Q % QS == 0 && (128 / 32) % QS == 0, "column blocks are whole warps");
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned h = warp % QS;
+    const unsigned long long step = (unsigned long long)gridDim.x * GROUP;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * GROUP + (warp / QS) * 32 + lane; b < count; b += step) {
+        T breg[K * QH];
+        #pragma unroll
+        for (int k = 0; k < K; ++k)
+            #pragma unroll
+            for (int q = 0; q < QH; ++q) breg[k * QH + q] = __ldg(B + (size_t)(k * Q + h * QH + q) * stride + b);
+        const T* a = A + b;
+        T* c = C + (size_t)(h * QH) * stride + b;
+        T pre[DEPTH][K];
+        #pragma unroll
+        for (int u = 0; u < DEPTH; ++u)
+            if (u < P) {
+                #pragma unroll
+                for (int k = 0; k < K; ++k) pre[u][k] = __ldg(a + ((size_t)u * K + k) * stride);
+            }
+        for (int i0 = 0; i0 < P; i0 += DEPTH) {
+            #pragma unroll
+            for (int u = 0; u < DEPTH; ++u) {
+                const int i = i0 + u;
+                if (i < P) {
+                    T arow[K];
+                    #pragma unroll
+                    for (int k = 0; k < K; ++k) arow[k] = pre[u][k];
+                    if (i + DEPTH < P) {
+                        #pragma unroll
+                        for (int k = 0; k < K; ++k) pre[u][k] = __ldg(a + ((size_t)(i + DEPTH) * K + k) * stride);
+                    }
+                    #pragma unroll
+                    for (int q = 0; q < QH; ++q) {
+                        T acc = R::zero();
+                        #pragma unroll
+                        for (int k = 0; k < K; ++k) acc = R::add(acc, R::mul(arow[k], breg[k * QH + q]));
+                        __stcs(c + ((size_t)i * Q + q) * stride, acc);
+                    }
+                }
+            }
+        }
+    }
+}
+template <class T, int K, int Q, int QS, int DEPTH>
+static int soa_prod_split_launch(const Shard& s, int P, const void* A, const void* B, void* C) {
+    auto kern = soa_prod_split_kernel<T, K, Q, QS, DEPTH>;
+    const size_t tiles = (s.count + 128 / QS - 1) / (128 / QS);
+    kern<<<resident_grid((const void*)kern, 128, tiles), 128, 0, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, (unsigned long long)s.count, s.soa_stride);
+    return ok();
+}
+
 template <class T, int K, int Q>
 static int soa_prod_reg_launch(const Shard& s, int P, const void* A, const void* B, void* C) {
     auto kern = soa_prod_reg_kernel<T, K, Q>;
@@ -958,6 +1136,9 @@ static int soa_prod_reg_launch(const Shard& s, int P, const void* A, const void*
 }
 template <class T>
 static int soa_prod_reg(const Shard& s, int P, int K, int Q, const void* A, const void* B, void* C) {
+    // 8x8 with 8-byte elements: two column blocks, rows of A two ahead (1Mi items, Double: 0.319 ms all of B per thread; 0.308
+    // two blocks, one row ahead; 0.290 two ahead; 0.307 three ahead (spills); 0.347 four blocks.  Int64: 0.357 -> 0.301)
+    if constexpr (sizeof(T) == 8) if (K == 8 && Q == 8) return soa_prod_split_launch<T, 8, 8, 2, 2>(s, P, A, B, C);
     if (K == 8 && Q == 8) return soa_prod_reg_launch<T, 8, 8>(s, P, A, B, C);
     if (K == 7 && Q == 7) return soa_prod_reg_launch<T, 7, 7>(s, P, A, B, C);
     if (K == 6 && Q == 6) return soa_prod_reg_launch<T, 6, 6>(s, P, A, B, C);
@@ -1675,9 +1856,9 @@ relayout_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long lo
 // accesses; the SoA side moves as d row segments of TI elements.  In between the tile sits in
 // shared memory as [item][element] with an odd pitch, which makes the column reads / writes of the
 // SoA phase conflict-free.  No index division in either loop.
-constexpr int RL_TI = 128, RL_THREADS = 256;
+constexpr int RL_THREADS = 256;
 
-template <class T>
+template <class T, int TI>
 __global__ void __launch_bounds__(RL_THREADS)
 relayout_small_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long long count, unsigned d,
                       unsigned long long stride, int to_soa) {
@@ -1686,10 +1867,10 @@ relayout_small_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned l
     const unsigned pitch = d | 1u;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned step_q = RL_THREADS / d, step_r = RL_THREADS - step_q * d;
-    const unsigned long long n_tiles = (count + RL_TI - 1) / RL_TI;
+    const unsigned long long n_tiles = (count + TI - 1) / TI;
     for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const unsigned long long b0 = t * RL_TI;
-        const unsigned nv = count - b0 < (unsigned long long)RL_TI ? (unsigned)(count - b0) : (unsigned)RL_TI;
+        const unsigned long long b0 = t * TI;
+        const unsigned nv = count - b0 < (unsigned long long)TI ? (unsigned)(count - b0) : (unsigned)TI;
         const unsigned total = nv * d;
         __syncthreads();                                    // the previous tile has left shared memory
         if (to_soa) {
@@ -1704,7 +1885,7 @@ relayout_small_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned l
             for (unsigned r = warp; r < d; r += RL_THREADS / 32) {
                 T* row = dst + (unsigned long long)r * stride + b0;
                 #pragma unroll
-                for (unsigned j = 0; j < RL_TI / 32; ++j) {
+                for (unsigned j = 0; j < TI / 32; ++j) {
                     const unsigned it = lane + 32 * j;
                     if (it < nv) row[it] = tile[it * pitch + r];
                 }
@@ -1713,7 +1894,7 @@ relayout_small_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned l
             for (unsigned r = warp; r < d; r += RL_THREADS / 32) {
                 const T* row = src + (unsigned long long)r * stride + b0;
                 #pragma unroll
-                for (unsigned j = 0; j < RL_TI / 32; ++j) {
+                for (unsigned j = 0; j < TI / 32; ++j) {
                     const unsigned it = lane + 32 * j;
                     if (it < nv) tile[it * pitch + r] = row[it];
                 }
@@ -1730,30 +1911,278 @@ relayout_small_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned l
     }
 }
 
-template <class T>
-static int relayout_small(cudaStream_t st, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
-    const size_t smem = (size_t)RL_TI * (d | 1) * sizeof(T);
-    auto kern = relayout_small_kernel<T>;
-    static bool configured[T5_MAX_DEVICES] = {false};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev >= T5_MAX_DEVICES) return T5I_CUDA;
-    if (!configured[dev]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_TI * 65 * (int)sizeof(T)) != cudaSuccess) return T5I_CUDA;
-        configured[dev] = true;
+// 4-byte elements: the same tile, but every global access is an 8-byte PAIR, so that a warp instruction moves 256
+// contiguous bytes as the 8-byte kernel's does (1-element accesses left the 4x4 Float relayout at 0.82 of the HBM peak
+// against 0.96 for 3x3 Double).  SoA side: two consecutive items of one element row (rows are padded to 32 items: the
+// partner of the last item of an odd count is padding, written as zero).  AoS side: two consecutive elements of the
+// tile's contiguous AoS image - for even d a pair lies inside one item (pitch d + 1), for odd d the pitch IS d, the tile is
+// the linear image and a pair that straddles two items still lands on consecutive words.
+template <int TI>
+__global__ void __launch_bounds__(RL_THREADS)
+relayout_small_pair_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, unsigned long long count, unsigned d,
+                           unsigned long long stride, int to_soa) {
+    extern __shared__ __align__(16) unsigned char rl_smem[];
+    unsigned* tile = reinterpret_cast<unsigned*>(rl_smem);
+    const unsigned pitch = d | 1u;
+    const bool linear = d & 1u;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned dp = d / 2;                              // pairs per item (even d)
+    const unsigned step_q = dp ? RL_THREADS / dp : 0, step_r = dp ? RL_THREADS - step_q * dp : 0;
+    const unsigned long long n_tiles = (count + TI - 1) / TI;
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const unsigned long long b0 = t * TI;
+        const unsigned nv = count - b0 < (unsigned long long)TI ? (unsigned)(count - b0) : (unsigned)TI;
+        const unsigned total = nv * d, totalp = total / 2;
+        __syncthreads();                                    // the previous tile has left shared memory
+        if (to_soa) {
+            const uint2* a = reinterpret_cast<const uint2*>(src + b0 * d);
+            if (linear) {
+                for (unsigned l = tid; l < totalp; l += RL_THREADS) {
+                    const uint2 v = __ldg(a + l);
+                    tile[2 * l] = v.x;
+                    tile[2 * l + 1] = v.y;
+                }
+                if ((total & 1u) && tid == 0) tile[total - 1] = __ldg(src + b0 * d + total - 1);
+            } else {
+                unsigned i = tid / dp, e = tid - i * dp;
+                for (unsigned l = tid; l < totalp; l += RL_THREADS) {
+                    const uint2 v = __ldg(a + l);
+                    tile[i * pitch + 2 * e] = v.x;
+                    tile[i * pitch + 2 * e + 1] = v.y;
+                    i += step_q; e += step_r;
+                    if (e >= dp) { e -= dp; ++i; }
+                }
+            }
+            if (nv < (unsigned)TI && (nv & 1u))             // the partner of the last item: padding, must read as zero
+                for (unsigned e2 = tid; e2 < d; e2 += RL_THREADS) tile[nv * pitch + e2] = 0u;
+            __syncthreads();
+            for (unsigned r = warp; r < d; r += RL_THREADS / 32) {
+                uint2* row = reinterpret_cast<uint2*>(dst + (unsigned long long)r * stride + b0);
+                #pragma unroll
+                for (unsigned j = 0; j < TI / 64; ++j) {
+                    const unsigned it = 2 * (lane + 32 * j);
+                    if (it < nv) row[lane + 32 * j] = make_uint2(tile[it * pitch + r], tile[(it + 1) * pitch + r]);
+                }
+            }
+        } else {
+            for (unsigned r = warp; r < d; r += RL_THREADS / 32) {
+                const uint2* row = reinterpret_cast<const uint2*>(src + (unsigned long long)r * stride + b0);
+                #pragma unroll
+                for (unsigned j = 0; j < TI / 64; ++j) {
+                    const unsigned it = 2 * (lane + 32 * j);
+                    if (it < nv) {
+                        const uint2 v = __ldg(row + lane + 32 * j);
+                        tile[it * pitch + r] = v.x;
+                        tile[(it + 1) * pitch + r] = v.y;     // (item nv of an odd tail: padding, staged but never stored)
+                    }
+                }
+            }
+            __syncthreads();
+            uint2* a = reinterpret_cast<uint2*>(dst + b0 * d);
+            if (linear) {
+                for (unsigned l = tid; l < totalp; l += RL_THREADS) a[l] = make_uint2(tile[2 * l], tile[2 * l + 1]);
+                if ((total & 1u) && tid == 0) dst[b0 * d + total - 1] = tile[total - 1];
+            } else {
+                unsigned i = tid / dp, e = tid - i * dp;
+                for (unsigned l = tid; l < totalp; l += RL_THREADS) {
+                    a[l] = make_uint2(tile[i * pitch + 2 * e], tile[i * pitch + 2 * e + 1]);
+                    i += step_q; e += step_r;
+                    if (e >= dp) { e -= dp; ++i; }
+                }
+            }
+        }
     }
+}
+
+// Records beyond the staging limit: 64 x 64 (items x elements) tiles with 8-byte accesses on both sides.  4-byte elements
+// (d even) move as pairs like the kernel above - the 32 x 32 tile with 1-element accesses ran the 32x32 Float relayout at
+// 0.43 of the HBM peak, this one at 0.97 - 8-byte elements one per lane and two column halves per row (0.73 -> 0.9).
+template <class T>
+__global__ void __launch_bounds__(256)
+relayout_tile64_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long long count, unsigned d,
+                       unsigned long long stride, int to_soa) {
+    __shared__ T tile[64][65];
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 lanes x 8 rows
+    const unsigned long long n_bt = (count + 63) / 64;
+    const unsigned n_dt = (d + 63) / 64;
+    for (unsigned long long t = blockIdx.x; t < n_bt * n_dt; t += gridDim.x) {
+        const unsigned long long b0 = (t / n_dt) * 64;
+        const unsigned e0 = (unsigned)(t % n_dt) * 64;
+        __syncthreads();
+        if constexpr (sizeof(T) == 4) {
+            if (to_soa) {
+                // tile[item][element]: AoS rows, pairs of elements
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8) {
+                    uint2 v = make_uint2(0u, 0u);                   // items past count: the SoA padding reads as zero
+                    if (b0 + r < count && e0 + 2 * tx < d) v = __ldg(reinterpret_cast<const uint2*>(src + (b0 + r) * d + e0 + 2 * tx));
+                    tile[r][2 * tx] = v.x;
+                    tile[r][2 * tx + 1] = v.y;
+                }
+                __syncthreads();
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    if (e0 + r < d && b0 + 2 * tx < count)
+                        *reinterpret_cast<uint2*>(dst + (unsigned long long)(e0 + r) * stride + b0 + 2 * tx) = make_uint2(tile[2 * tx][r], tile[2 * tx + 1][r]);
+            } else {
+                // tile[element][item]: SoA rows, pairs of items
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    if (e0 + r < d && b0 + 2 * tx < count) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(src + (unsigned long long)(e0 + r) * stride + b0 + 2 * tx));
+                        tile[r][2 * tx] = v.x;
+                        tile[r][2 * tx + 1] = v.y;
+                    }
+                __syncthreads();
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    if (b0 + r < count && e0 + 2 * tx < d)
+                        *reinterpret_cast<uint2*>(dst + (b0 + r) * d + e0 + 2 * tx) = make_uint2(tile[2 * tx][r], tile[2 * tx + 1][r]);
+            }
+        } else {
+            if (to_soa) {
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    #pragma unroll
+                    for (unsigned c = tx; c < 64; c += 32)
+                        if (b0 + r < count && e0 + c < d) tile[r][c] = __ldg(src + (b0 + r) * d + e0 + c);
+                __syncthreads();
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    #pragma unroll
+                    for (unsigned c = tx; c < 64; c += 32)
+                        if (e0 + r < d && b0 + c < count) dst[(unsigned long long)(e0 + r) * stride + b0 + c] = tile[c][r];
+            } else {
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    #pragma unroll
+                    for (unsigned c = tx; c < 64; c += 32)
+                        if (e0 + r < d && b0 + c < count) tile[r][c] = __ldg(src + (unsigned long long)(e0 + r) * stride + b0 + c);
+                __syncthreads();
+                #pragma unroll
+                for (unsigned r = ty; r < 64; r += 8)
+                    #pragma unroll
+                    for (unsigned c = tx; c < 64; c += 32)
+                        if (b0 + r < count && e0 + c < d) dst[(b0 + r) * d + e0 + c] = tile[c][r];
+            }
+        }
+    }
+}
+
+// 8-byte elements towards SoA: the same 64 x 64 tile written with one body for both directions (run-time pitches, staged
+// elements always written, zero where the source ends) measured 5.76 TB/s on 32x32 Double against 4.94 for the branch of
+// the kernel above - and 5.95 against 6.15 the other way, so each direction keeps its faster form.
+template <class T>
+__global__ void __launch_bounds__(256)
+relayout_tile64_uniform_kernel(const T* __restrict__ src, T* __restrict__ dst, unsigned long long count, unsigned d,
+                               unsigned long long stride, int to_soa) {
+    __shared__ T tile[64][65];
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned long long n_bt = (count + 63) / 64;
+    const unsigned n_dt = (d + 63) / 64;
+    for (unsigned long long t = blockIdx.x; t < n_bt * n_dt; t += gridDim.x) {
+        const unsigned long long b0 = (t / n_dt) * 64;
+        const unsigned e0 = (unsigned)(t % n_dt) * 64;
+        // first index of the tile = the side being read; rd_* describe it, wr_* the other one
+        const unsigned long long rd_rows = to_soa ? count - b0 : d - e0, rd_cols = to_soa ? d - e0 : count - b0;
+        const T* rd = to_soa ? src + b0 * d + e0 : src + (unsigned long long)e0 * stride + b0;
+        const unsigned long long rd_pitch = to_soa ? d : stride;
+        T* wr = to_soa ? dst + (unsigned long long)e0 * stride + b0 : dst + b0 * d + e0;
+        const unsigned long long wr_pitch = to_soa ? stride : d;
+        __syncthreads();
+        #pragma unroll
+        for (unsigned r = ty; r < 64; r += 8)
+            #pragma unroll
+            for (unsigned c = tx; c < 64; c += 32) {
+                T v = T(0);
+                if (r < rd_rows && c < rd_cols) v = rd[r * rd_pitch + c];
+                tile[r][c] = v;
+            }
+        __syncthreads();
+        #pragma unroll
+        for (unsigned r = ty; r < 64; r += 8)
+            #pragma unroll
+            for (unsigned c = tx; c < 64; c += 32)
+                if (r < rd_cols && c < rd_rows) wr[r * wr_pitch + c] = tile[c][r];
+    }
+}
+
+static int relayout_ti_override() {          // tuning hook: T5_RL_TI = items per staged tile
+    static const int v = [] { const char* e = getenv("T5_RL_TI"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
+template <class P>
+static int relayout_small_launch(void (*kern)(const P*, P*, unsigned long long, unsigned, unsigned long long, int), cudaStream_t st, int ti,
+                                 size_t pitch, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
+    const size_t smem = (size_t)ti * pitch * sizeof(P);
+    // (an attribute call per launch costs ~1 us on the host; the limit only has to cover this launch)
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return T5I_CUDA;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RL_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
-    const size_t tiles = (count + RL_TI - 1) / RL_TI;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RL_THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const size_t tiles = (count + ti - 1) / ti;
     const size_t cap = (size_t)sm_count() * occ;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    kern<<<grid, RL_THREADS, smem, st>>>((const T*)src, (T*)dst, count, (unsigned)d, soa_stride, to_soa ? 1 : 0);
+    kern<<<grid, RL_THREADS, smem, st>>>((const P*)src, (P*)dst, count, (unsigned)d, soa_stride, to_soa ? 1 : 0);
     return ok();
+}
+
+template <class P>
+static int relayout_small(cudaStream_t st, int ti, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
+    const size_t pitch = d | 1;
+    switch (ti) {
+        case 64:  return relayout_small_launch<P>(relayout_small_kernel<P, 64>, st, ti, pitch, d, count, soa_stride, to_soa, src, dst);
+        case 256: return relayout_small_launch<P>(relayout_small_kernel<P, 256>, st, ti, pitch, d, count, soa_stride, to_soa, src, dst);
+        default:  return relayout_small_launch<P>(relayout_small_kernel<P, 128>, st, 128, pitch, d, count, soa_stride, to_soa, src, dst);
+    }
+}
+
+static int relayout_small_pair(cudaStream_t st, int ti, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
+    const size_t pitch = d | 1;
+    switch (ti) {
+        case 64:  return relayout_small_launch<unsigned>(relayout_small_pair_kernel<64>, st, ti, pitch, d, count, soa_stride, to_soa, src, dst);
+        case 256: return relayout_small_launch<unsigned>(relayout_small_pair_kernel<256>, st, ti, pitch, d, count, soa_stride, to_soa, src, dst);
+        case 512: return relayout_small_launch<unsigned>(relayout_small_pair_kernel<512>, st, ti, pitch, d, count, soa_stride, to_soa, src, dst);
+        default:  return relayout_small_launch<unsigned>(relayout_small_pair_kernel<128>, st, 128, pitch, d, count, soa_stride, to_soa, src, dst);
+    }
 }
 
 int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
     if (count == 0 || d == 0) return T5I_OK;
-    if (d <= 64 && elem_bytes == 8) return relayout_small<unsigned long long>(st, d, count, soa_stride, to_soa, src, dst);
-    if (d <= 64 && elem_bytes == 4) return relayout_small<unsigned>(st, d, count, soa_stride, to_soa, src, dst);
+    // 8-byte accesses need rows padded to an even number of items and 8-byte aligned bases (cudaMalloc gives 256)
+    const bool wide = soa_stride % 2 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 7) == 0;
+    static const int small_max = [] { const char* e = getenv("T5_RL_SMALL_MAX"); return e ? atoi(e) : 64; }();   // tuning hook
+    // Items per staged tile: row segments of 1 KB (256 four-byte / 128 eight-byte items), twice that while the tile stays
+    // under 8 KB (records of a few elements), halved while it exceeds 33 KB (measured: 4x4 Float 5.2 / 4.0 TB/s to / from SoA
+    // with 128 items, 6.1 / 6.3 with 256; 2x3 Double 5.4 -> 6.3 with 256; 8x8 Float 5.5 / 6.4 with 128, 5.2 / 5.5 with 256).
+    // 8-byte records of more than 32 elements go to the 64 x 64 tiles (8x8 Double 5.3 / 5.6 -> 5.7 / 6.0 TB/s).
+    int ti = elem_bytes == 4 ? 256 : 128;
+    const size_t item_tile = (d | 1) * elem_bytes;
+    if (ti * item_tile < 8 * 1024) ti *= 2;
+    while (ti > 64 && ti * item_tile > 33 * 1024) ti /= 2;
+    if (elem_bytes == 4 && !wide) ti = 128;
+    if (relayout_ti_override()) ti = relayout_ti_override();
+    if (d <= (size_t)small_max && d <= 64 && !(elem_bytes == 8 && d > 32)) {
+        if (elem_bytes == 8) return relayout_small<unsigned long long>(st, ti, d, count, soa_stride, to_soa, src, dst);
+        if (elem_bytes == 4 && wide) return relayout_small_pair(st, ti, d, count, soa_stride, to_soa, src, dst);
+        if (elem_bytes == 4) return relayout_small<unsigned>(st, ti, d, count, soa_stride, to_soa, src, dst);
+    }
+    const size_t tiles64 = ((count + 63) / 64) * ((d + 63) / 64);
+    if (elem_bytes == 8 && to_soa) {
+        relayout_tile64_uniform_kernel<unsigned long long><<<resident_grid((const void*)relayout_tile64_uniform_kernel<unsigned long long>, 256, tiles64), 256, 0, st>>>(
+            (const unsigned long long*)src, (unsigned long long*)dst, count, (unsigned)d, soa_stride, 1);
+        return ok();
+    }
+    if (elem_bytes == 8) {
+        relayout_tile64_kernel<unsigned long long><<<resident_grid((const void*)relayout_tile64_kernel<unsigned long long>, 256, tiles64), 256, 0, st>>>(
+            (const unsigned long long*)src, (unsigned long long*)dst, count, (unsigned)d, soa_stride, to_soa);
+        return ok();
+    }
+    if (elem_bytes == 4 && wide && d % 2 == 0) {
+        relayout_tile64_kernel<unsigned><<<resident_grid((const void*)relayout_tile64_kernel<unsigned>, 256, tiles64), 256, 0, st>>>(
+            (const unsigned*)src, (unsigned*)dst, count, (unsigned)d, soa_stride, to_soa);
+        return ok();
+    }
     const size_t tiles = ((count + 31) / 32) * ((d + 31) / 32);
     const void* kern = elem_bytes == 8 ? (const void*)relayout_kernel<unsigned long long>
                      : elem_bytes == 4 ? (const void*)relayout_kernel<unsigned> : (const void*)relayout_kernel<unsigned char>;

@@ -1608,12 +1608,52 @@ static int split_locked(t5_ctx* c, int dtype, int axis, int rank, const uint64_t
     return T5_OK;
 }
 
+// AoS records small enough to stage: both halves from one read of the input, 16-byte accesses on every side
+// (4Mi 4x4 -> 4x3 | 4x1: the two Float gathers ran at 0.55 of the HBM peak, the Double scatter at 0.78)
+static int split_staged(t5_ctx* c, int dtype, int axis, int rank, const uint64_t* dims, uint64_t first_extent,
+                        const t5_buf* IN, t5_buf* OUT1, t5_buf* OUT2, bool* done) {
+    *done = false;
+    const int es = dtype_size(dtype);
+    std::vector<uint64_t> dv(dims, dims + rank), prm{(uint64_t)axis, first_extent};
+    LOCKED(c);
+    size_t d1 = 0, d2 = 0;
+    CHECK(structural_table_dev(c, -1, 1, dv, prm, nullptr, &d1, nullptr));
+    CHECK(structural_table_dev(c, -1, 2, dv, prm, nullptr, &d2, nullptr));
+    const size_t d_in = prod_of(dv);
+    if (!staged_gather_fits(es, d_in, d1 + d2, d1 && d2)) return T5_OK;
+    CHECK(check(c, IN, dtype, d_in, nullptr));
+    CHECK(check(c, OUT1, dtype, d1, IN));
+    CHECK(check(c, OUT2, dtype, d2, IN));
+    for (int g = 0; g < c->ndev; ++g) {
+        if (!IN->count[g]) continue;
+        CU(c, cudaSetDevice(c->dev[g]));
+        const uint32_t *tab1, *tab2; size_t n;
+        CHECK(structural_table_dev(c, g, 1, dv, prm, &tab1, &n, nullptr));
+        CHECK(structural_table_dev(c, g, 2, dv, prm, &tab2, &n, nullptr));
+        const Shard s = shard_of(c, IN, g);
+        int r = staged_gather(s, es, d_in, 0, d1, d2, tab1, tab2, IN->ptr[g], nullptr, OUT1->ptr[g], OUT2->ptr[g]);
+        if (r == T5I_NOT_SPECIALISED) {                       // (a misaligned shard: never with the library's own allocations)
+            r = generic_gather(s, es, d_in, d1, tab1, IN->ptr[g], OUT1->ptr[g]);
+            if (r == T5I_OK) r = generic_gather(s, es, d_in, d2, tab2, IN->ptr[g], OUT2->ptr[g]);
+        }
+        if (r != T5I_OK) return map_internal(c, r, "t5_split");
+        c->launches++;
+    }
+    *done = true;
+    return T5_OK;
+}
+
 int t5_split(t5_ctx* c, int dtype, int axis, int rank, const uint64_t* dims, uint64_t first_extent,
              const t5_buf* IN, t5_buf* OUT1, t5_buf* OUT2) try {
     if (!c || !IN || rank < 0 || rank > 16 || (rank && !dims)) return T5_ERR_INVALID;
     if (OUT1 == OUT2 || OUT1 == IN || OUT2 == IN) return T5_ERR_INVALID;
     const int es = dtype_size(dtype);
     if (es != 4 && es != 8) return T5_ERR_UNSUPPORTED;
+    if (IN->layout != T5_SOA && OUT1 && OUT2 && OUT1->layout != T5_SOA && OUT2->layout != T5_SOA) {
+        bool done = false;
+        const int rc = split_staged(c, dtype, axis, rank, dims, first_extent, IN, OUT1, OUT2, &done);
+        if (rc != T5_OK || done) return rc;
+    }
     if (es == 4 || IN->layout == T5_SOA) {      // (SoA: each half is a copy of whole rows)
         // 4-byte elements: the scatter's short store runs cost more than the second read saves
         // (4Mi 4x4 -> 4x3 | 4x1: Float 0.145 ms as two gathers vs 0.160 ms; Double 0.278 vs 0.211 ms)

@@ -65,6 +65,11 @@ int generic_permute(const Shard& s, int elem_bytes, size_t d, const uint32_t* pe
 // out[b][i] = in[b][table[i]] with d_in != d_out allowed (structural gathers); gather2: two sources (append)
 int generic_gather(const Shard& s, int elem_bytes, size_t d_in, size_t d_out, const uint32_t* table_dev, const void* A, void* O);
 int generic_gather2(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d_out, const uint32_t* table_dev, const void* A, const void* B, void* O);
+// gathers of staged records, up to two sources and two results (t2 / O2 may be null with d2 = 0); T5I_NOT_SPECIALISED when the
+// records are too large to stage
+bool staged_gather_fits(int elem_bytes, size_t d_in_total, size_t d_out_total, bool two_results);
+int staged_gather(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d1, size_t d2, const uint32_t* t1, const uint32_t* t2,
+                  const void* A, const void* B, void* O1, void* O2);
 int generic_scatter2(const Shard& s, int elem_bytes, size_t d_in, size_t d1, size_t d2, const uint32_t* table_dev, const void* A, void* O1, void* O2);
 int generic_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int generic_solve(const Shard& s, int dtype, int n, int nrhs, bool identity_rhs, const void* A, const void* B, void* X, void* status);

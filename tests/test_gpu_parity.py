@@ -156,6 +156,10 @@ def test_prod_and_tensor_product_soa(ctx, dc):
         a3, b3 = inputs(dc, 6, batch, 2 * 3 * 4, 4 * 5)
         P = tb.prod(ctx.from_numpy(a3, (2, 3, 4), tb.SOA), ctx.from_numpy(b3, (4, 5), tb.SOA), 1)
         assert_bits_equal(P.to_numpy(), oracle.prod(a3, [2, 3, 4], b3, [4, 5], 1), "SoA rank3.rank2")
+        for rows in (2, 3, 5):              # row counts of A that end inside the prefetch ring of the column-split 8x8 kernel
+            a5, b5 = inputs(dc, 8, batch, rows * 8, 64)
+            P = tb.prod(ctx.from_numpy(a5, (rows, 8), tb.SOA), ctx.from_numpy(b5, (8, 8), tb.SOA), 1)
+            assert_bits_equal(P.to_numpy(), oracle.prod(a5, [rows, 8], b5, [8, 8], 1), "SoA %dx8 . 8x8" % rows)
 
 
 def test_prod_shape_mismatch_is_wrong_list_length(ctx):
@@ -425,12 +429,23 @@ def test_from_list_length_check(ctx):
 
 @pytest.mark.parametrize("dc", ALL)
 def test_relayout_roundtrip(ctx, dc):
-    for batch, shape in ((1, (3, 3)), (1000, (4, 4)), (4099, (3,)), (77, (8, 8, 2))):
+    # odd and even counts either side of the 128-item tile, d even / odd, d <= 64 and beyond (4-byte elements with even d move
+    # as 8-byte pairs: two elements of an item on the AoS side, two items of a row on the SoA side)
+    for batch, shape in ((1, (3, 3)), (1000, (4, 4)), (4099, (3,)), (77, (8, 8, 2)), (1, (4, 4)), (129, (4, 4)), (255, (2, 3)),
+                         (4097, (8, 8)), (127, (2,)), (65, (10, 13)), (193, (33, 2)), (64, (32, 32))):
         a, _ = inputs(dc, 12, batch, int(np.prod(shape)))
         A = ctx.from_numpy(a, shape)
         S = A.relayout(tb.SOA)
         assert_bits_equal(S.to_numpy().ravel(), a, "soa download")
         assert_bits_equal(S.relayout(tb.AOS).to_numpy().ravel(), a, "aos roundtrip")
+        S.free(); A.free()
+    # the SoA image is the one the SoA kernels read: a product of relayouted operands = the AoS product
+    for batch in (1, 129, 1023):
+        a, b = inputs(dc, 13, batch, 16, 16)
+        A, B = ctx.from_numpy(a, (4, 4)), ctx.from_numpy(b, (4, 4))
+        want = tb.matmul(A, B).to_numpy()
+        As, Bs = A.relayout(tb.SOA), B.relayout(tb.SOA)
+        assert_bits_equal(tb.matmul(As, Bs).to_numpy().ravel(), want.ravel(), "product of relayouted operands")
 
 
 @pytest.mark.parametrize("dc", ALL)
