@@ -88,9 +88,9 @@ def test_int64_wraparound(ctx):
 
 # ---- dot / dot_sum ---------------------------------------------------------------
 @pytest.mark.parametrize("dc", ALL)
-@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 16, 33, 64, 100])    # n > 4: the staged long-dot kernel (chunk tails at 33, 100)
-def test_dot_bit_exact(ctx, dc, n):
-    for batch in (1, 1000, 4099):
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 7, 16, 33, 36, 64, 100, 200, 260])    # n > 4: the staged long-dot kernels (chunk tails at 33, 36, 100, 200;
+def test_dot_bit_exact(ctx, dc, n):                                          # whole 16-byte groups per vector take the pipelined one)
+    for batch in (1, 1000, 4099) + ((300001,) if n in (16, 36, 64) else ()):  # 300001: several tiles per CTA, the prefetch runs across tiles
         x, y = inputs(dc, 3, batch, n, n)
         D = tb.dot(ctx.from_numpy(x, (n,)), ctx.from_numpy(y, (n,)))
         assert D.shape == ()

@@ -1,6 +1,6 @@
 """Developer timing: t5_relayout in both directions over record sizes either side of the 64-element staging limit, and
 the SoA 8x8 contraction (T5_SOA_PROD_VARIANT picks the kernel while it is being tuned).  Device-resident, CUDA events on
-the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct]"""
+the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct | dot]"""
 import os
 import sys
 
@@ -65,6 +65,15 @@ def main():
     with tb.Context([0]) as ctx:
         if "struct" in sys.argv[1:]:
             return structural(ctx)
+        if "dot" in sys.argv[1:]:
+            for dt, es in ((np.float32, 4), (np.float64, 8), (np.int64, 8)):
+                for n, batch in ((64, 1 << 20), (16, 1 << 22), (256, 1 << 18), (100, 1 << 20)):
+                    x, y = ctx.synthetic((n,), dt, batch, SEED, 7), ctx.synthetic((n,), dt, batch, SEED + 1, 7)
+                    ms = timed(ctx, lambda: tb.dot(x, y))
+                    print("dot %4d %-8s x %8d %7.3f ms %6.0f GB/s%s" % (n, np.dtype(dt).name, batch, ms, batch * (2 * n + 1) * es / ms / 1e6,
+                                                                       "  (one element per lane)" if os.environ.get("T5_NO_LONGDOT_ROWS") else ""), flush=True)
+                    x.free(); y.free()
+            return
         for dt, es in ((np.float32, 4), (np.float64, 8)) if "prod" not in sys.argv[1:] else ():
             tag = "f32" if es == 4 else "f64"
             for shape, batch in (((4, 4), 1 << 24), ((3, 3), 1 << 24), ((2, 3), 1 << 24), ((8, 8), 1 << 22), ((32, 32), 1 << 18),
