@@ -57,6 +57,14 @@ WORKLOADS = {
                             desc="16Mi 4x4 . 4-vector Float (configs[1])"),
     "dot4_f32_16M": dict(op="dot", dtype="f32", n=4, batch=1 << 24, bytes=36, bound="hbm",
                          desc="16Mi 4-vector Float dot (configs[1])"),
+    "dot64_f32_1M": dict(op="dot", dtype="f32", n=64, batch=1 << 20, bytes=516, bound="hbm",
+                         desc="1Mi 64-vector Float dot (whole rows by 16-byte cp.async, folded from shared memory)"),
+    "dot64_f64_1M": dict(op="dot", dtype="f64", n=64, batch=1 << 20, bytes=1032, bound="hbm",
+                         desc="1Mi 64-vector Double dot (whole rows by 16-byte cp.async, folded from shared memory)"),
+    "prod2_8x8_f64_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=2, batch=1 << 20, bytes=1032, bound="hbm",
+                             desc="1Mi 8x8 : 8x8 -> scalar Double contractions (configs[3], n=2)"),
+    "relayout_32x32_f32_256K": dict(op="relayout", dtype="f32", dims=(32, 32), batch=1 << 18, bytes=8192, bound="hbm",
+                                    desc="256Ki 32x32 Float items, AoS -> SoA (64 x 64 tiles, 8-byte pairs: one leg of the SoA detour of an AoS-only kernel)"),
     "det3_f64_4M": dict(op="det", dtype="f64", n=3, batch=1 << 22, bytes=80, bound="hbm", desc="4Mi 3x3 Double det (configs[2])"),
     "det4_f64_4M": dict(op="det", dtype="f64", n=4, batch=1 << 22, bytes=136, bound="hbm", desc="4Mi 4x4 Double det (configs[2])"),
     "inverse3_f64_4M": dict(op="inverse", dtype="f64", n=3, batch=1 << 22, bytes=145, bound="hbm", desc="4Mi 3x3 Double inverse (configs[2])"),
@@ -70,7 +78,7 @@ WORKLOADS = {
     "tensorprod8x8_f64_soa_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=0, batch=1 << 20, bytes=33792, bound="hbm", layout="soa",
                                      desc="1Mi 8x8 (x) 8x8 -> 8^4 Double on SoA buffers (16 bytes of consecutive items per thread, B staged in shared memory)"),
     "prod1_8x8_f64_soa_1M": dict(op="prod", dtype="f64", dims_a=(8, 8), dims_b=(8, 8), nc=1, batch=1 << 20, bytes=1536, bound="hbm", layout="soa",
-                                 desc="1Mi 8x8 . 8x8 Double (prod 1) on SoA buffers (B in registers, rows of A streamed through a two-deep register pipeline)"),
+                                 desc="1Mi 8x8 . 8x8 Double (prod 1) on SoA buffers (B in registers, result columns split over two warps, rows of A streamed two ahead)"),
     "matmul4x4_f32_soa_16M": dict(op="matmul", dtype="f32", m=4, k=4, n=4, batch=1 << 24, bytes=192, bound="hbm", layout="soa",
                                   desc="16Mi pairs of 4x4 Float matrices, .*., SoA device layout"),
     "inverse4_f64_soa_4M": dict(op="inverse", dtype="f64", n=4, batch=1 << 22, bytes=257, bound="hbm", layout="soa",
@@ -137,7 +145,7 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M", "tensorprod8x8_f64_soa_1M", "prod1_8x8_f64_soa_1M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
-          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
+          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "relayout_32x32_f32_256K", "dot64_f32_1M", "dot64_f64_1M", "prod2_8x8_f64_1M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
           "inverse6_f64_1M", "inverse8_f64_1M", "matmul32_f64_1M", "matmul32_f32_1M", "det16_f64_512K", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M", "echelon7x9_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 
