@@ -35,6 +35,12 @@ static inline int ech_sm_count() {
 // 19 % ISETP, 17 % branch / reconvergence instructions, 15 % FP64 - 9 800 instructions per
 // 32 items of which 1 500 were arithmetic.  The quotients by a pivot use its hoisted exact
 // reciprocal (t5_recip.cuh).
+//
+// Tried and dropped (profiles/r02m_time_echelon_pair_vs_single.txt): two lanes per item (lanes l and l + 16 of a warp own the
+// columns of parity 0 and 1, two __syncwarp over the pair per step, multipliers computed by both) to double the warps the
+// staged records allow per SM - bit-identical, but the duplicated divisions and boundary predicates cost more than the
+// residency bought: 7x9 Double 0.354 -> 0.559 ms, 5x7 0.151 -> 0.323, Float 7x9 0.229 -> 0.362; only 8x16 Double gained
+// (0.499 -> 0.422).
 // =====================================================================================
 constexpr int ECH_MAX_ROWS = 8, ECH_MAX_COLS = 16;
 

@@ -182,6 +182,17 @@ def test_row_echelon_special_values(ctx):
     g, w = got.to_numpy(), want
     assert np.array_equal(np.isnan(g), np.isnan(w))
     assert np.array_equal(bits(np.where(np.isnan(g), 0.0, g)), bits(np.where(np.isnan(w), 0.0, w)))
+    # the any-shape kernel (two lanes per item, columns split by parity): odd and even column counts
+    for m, n in ((6, 5), (5, 8), (7, 9)):
+        a = rng.standard_normal((777, m, n))
+        idx = rng.integers(0, a.size, size=1500)
+        a.ravel()[idx] = specials[rng.integers(0, len(specials), size=1500)]
+        got, rank = tb.row_echelon_form(ctx.from_numpy(a, (m, n)))
+        want, wrank = oracle.row_echelon(a, m, n)
+        assert np.array_equal(rank.to_numpy(), wrank), (m, n)
+        g, w = got.to_numpy(), want
+        assert np.array_equal(np.isnan(g), np.isnan(w)), (m, n)
+        assert np.array_equal(bits(np.where(np.isnan(g), 0.0, g)), bits(np.where(np.isnan(w), 0.0, w))), (m, n)
 
 
 @pytest.mark.gpu

@@ -1,6 +1,6 @@
 """Developer timing: t5_relayout in both directions over record sizes either side of the 64-element staging limit, and
 the SoA 8x8 contraction (T5_SOA_PROD_VARIANT picks the kernel while it is being tuned).  Device-resident, CUDA events on
-the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct | dot]"""
+the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct | dot | echelon]"""
 import os
 import sys
 
@@ -65,6 +65,14 @@ def main():
     with tb.Context([0]) as ctx:
         if "struct" in sys.argv[1:]:
             return structural(ctx)
+        if "echelon" in sys.argv[1:]:
+            for dt, es in ((np.float64, 8), (np.float32, 4)):
+                for (m, n), batch in (((7, 9), 1 << 20), ((5, 7), 1 << 20), ((8, 12), 1 << 19), ((3, 7), 1 << 21), ((8, 16), 1 << 19)):
+                    a = ctx.synthetic((m, n), dt, batch, SEED, 9)
+                    ms = timed(ctx, lambda: tb.row_echelon_form(a))
+                    print("rowEchelonForm %dx%-2d %-8s x %8d %7.3f ms %6.0f GB/s" % (m, n, np.dtype(dt).name, batch, ms, batch * (2 * m * n * es + 1) / ms / 1e6), flush=True)
+                    a.free()
+            return
         if "dot" in sys.argv[1:]:
             for dt, es in ((np.float32, 4), (np.float64, 8), (np.int64, 8)):
                 for n, batch in ((64, 1 << 20), (16, 1 << 22), (256, 1 << 18), (100, 1 << 20)):
