@@ -1101,9 +1101,8 @@ soa_outer_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict
     }
 }
 
-template <class T>
-static int soa_outer_launch(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
-    constexpr int THREADS = 64;
+template <class T, int THREADS>
+static int soa_outer_launch_t(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
     auto kern = soa_outer_kernel<T, THREADS>;
     const int smem = Q * THREADS * 16;
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return T5I_CUDA;
@@ -1113,6 +1112,12 @@ static int soa_outer_launch(const Shard& s, int P, int Q, const void* A, const v
     const size_t tiles = ((s.count + VEC - 1) / VEC + THREADS - 1) / THREADS, cap = (size_t)occ * sm_count();
     kern<<<(int)(tiles < cap ? tiles : cap), THREADS, smem, s.stream>>>((const T*)A, (const T*)B, (T*)C, P, Q, (unsigned long long)s.count, s.soa_stride);
     return ok();
+}
+// (CTA width measured on 256Ki 8x8 (x) 8x8, Double / Float: 32 threads = 512-byte row segments 5.31 / 5.35 TB/s, 64 = 1 KB
+// 5.34 / 5.32, 128 = 2 KB 5.60 / 5.28 at one CTA per SM: the segment length is not what holds the 4096-row scatter at 0.82.)
+template <class T>
+static int soa_outer_launch(const Shard& s, int P, int Q, const void* A, const void* B, void* C) {
+    return soa_outer_launch_t<T, 64>(s, P, Q, A, B, C);
 }
 
 // SoA contraction with B IN REGISTERS (K x Q <= 64 elements, compile-time): thread per item.  All of B is requested up

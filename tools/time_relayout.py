@@ -1,6 +1,6 @@
 """Developer timing: t5_relayout in both directions over record sizes either side of the 64-element staging limit, and
 the SoA 8x8 contraction (T5_SOA_PROD_VARIANT picks the kernel while it is being tuned).  Device-resident, CUDA events on
-the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct | dot | echelon]"""
+the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct | dot | echelon | outer]"""
 import os
 import sys
 
@@ -65,6 +65,16 @@ def main():
     with tb.Context([0]) as ctx:
         if "struct" in sys.argv[1:]:
             return structural(ctx)
+        if "outer" in sys.argv[1:]:
+            for dt, es in ((np.float64, 8), (np.float32, 4)):
+                batch = 1 << 18
+                A = ctx.synthetic((8, 8), dt, batch, SEED, 5, tb.SOA)
+                B = ctx.synthetic((8, 8), dt, batch, SEED + 1, 17, tb.SOA)
+                ms = timed(ctx, lambda: tb.tensor_product(A, B), reps=4)
+                print("SoA 8x8 (x) 8x8 %-8s x %d  T5_SOA_OUTER_THREADS=%s: %7.3f ms %6.0f GB/s" % (np.dtype(dt).name, batch, os.environ.get("T5_SOA_OUTER_THREADS", "64"),
+                                                                                              ms, batch * (4096 + 128) * es / ms / 1e6), flush=True)
+                A.free(); B.free()
+            return
         if "echelon" in sys.argv[1:]:
             for dt, es in ((np.float64, 8), (np.float32, 4)):
                 for (m, n), batch in (((7, 9), 1 << 20), ((5, 7), 1 << 20), ((8, 12), 1 << 19), ((3, 7), 1 << 21), ((8, 16), 1 << 19)):
