@@ -844,6 +844,7 @@ int t5_transpose(t5_ctx* c, int dtype, int rank, const uint64_t* dims, const t5_
 // Kernel chains, fastest applicable first; shared by the device-buffer entries and the host-array pipeline.
 static int det_chain(const Shard& s, int dtype, int n, const void* A, void* O) {
     int r = small_det(s, dtype, n, A, O);
+    if (r == T5I_NOT_SPECIALISED) r = reg9_det(s, dtype, n, A, O);
     if (r == T5I_NOT_SPECIALISED) r = rowlane_det(s, dtype, n, A, O);
     if (r == T5I_NOT_SPECIALISED) r = warp_det(s, dtype, n, A, O);
     if (r == T5I_NOT_SPECIALISED) r = lu_det(s, dtype, n, A, O);
@@ -852,6 +853,7 @@ static int det_chain(const Shard& s, int dtype, int n, const void* A, void* O) {
 }
 static int inverse_chain(const Shard& s, int dtype, int n, const void* A, void* O, void* st) {
     int r = small_inverse(s, dtype, n, A, O, st);
+    if (r == T5I_NOT_SPECIALISED) r = reg9_inverse(s, dtype, n, A, O, st);
     if (r == T5I_NOT_SPECIALISED) r = rowlane_inverse(s, dtype, n, A, O, st);
     if (r == T5I_NOT_SPECIALISED) r = warp_inverse(s, dtype, n, A, O, st);
     if (r == T5I_NOT_SPECIALISED) r = lu_inverse(s, dtype, n, A, O, st);
@@ -860,6 +862,7 @@ static int inverse_chain(const Shard& s, int dtype, int n, const void* A, void* 
 }
 static int solve_chain(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* st) {
     int r = small_solve(s, dtype, n, nrhs, A, B, X, st);
+    if (r == T5I_NOT_SPECIALISED) r = reg9_solve(s, dtype, n, nrhs, A, B, X, st);
     if (r == T5I_NOT_SPECIALISED) r = many_solve(s, dtype, n, nrhs, A, B, X, st);
     if (r == T5I_NOT_SPECIALISED) r = rowlane_solve(s, dtype, n, nrhs, A, B, X, st);
     if (r == T5I_NOT_SPECIALISED) r = warp_solve(s, dtype, n, nrhs, A, B, X, st);

@@ -36,7 +36,7 @@ def inputs(dc, n, batch, seed_op):
 
 
 @pytest.mark.parametrize("dc", FRAC)
-@pytest.mark.parametrize("n", [9, 12, 16, 17, 24, 25, 32, 33, 48, 64, 65, 100, 128])
+@pytest.mark.parametrize("n", [9, 10, 11, 12, 13, 14, 15, 16, 17, 24, 25, 32, 33, 48, 64, 65, 100, 128])   # 9..14: the record-per-thread kernels of t5_small_ops_9.cu
 def test_large_det_inverse_solve_bit_exact(ctx, dc, n):
     batch = 67 if n <= 32 else (35 if n <= 64 else 23)
     a = inputs(dc, n, batch, 60 + n)
@@ -58,7 +58,7 @@ def test_large_det_inverse_solve_bit_exact(ctx, dc, n):
         assert np.array_equal(bits(X.to_numpy().reshape(batch, n, nrhs)), bits(ox)), f"solve {n} x {nrhs}"
 
 
-@pytest.mark.parametrize("n,batch", [(12, 9001), (24, 7919), (40, 2999)])
+@pytest.mark.parametrize("n,batch", [(9, 70001), (10, 40001), (12, 9001), (24, 7919), (40, 2999)])
 def test_large_elimination_batches_beyond_one_wave(ctx, n, batch):
     """More items than the grid holds at once (888 CTAs x 8 groups for the 4 x 4-thread geometry): every CTA loops, the
     last pass is part empty - groups that share a warp with a group past the end of the batch recompute the last item
