@@ -65,6 +65,9 @@ WORKLOADS = {
                              desc="1Mi 8x8 : 8x8 -> scalar Double contractions (configs[3], n=2)"),
     "relayout_32x32_f32_256K": dict(op="relayout", dtype="f32", dims=(32, 32), batch=1 << 18, bytes=8192, bound="hbm",
                                     desc="256Ki 32x32 Float items, AoS -> SoA (64 x 64 tiles, 8-byte pairs: one leg of the SoA detour of an AoS-only kernel)"),
+    "det9_f64_1M": dict(op="det", dtype="f64", n=9, batch=1 << 20, bytes=656, bound="hbm", desc="1Mi 9x9 Double det (record per thread, one-stage tile pipeline)"),
+    "solve9_f64_1M": dict(op="solve", dtype="f64", n=9, batch=1 << 20, bytes=793, bound="hbm", desc="1Mi 9x9 Double solve (record per thread, one-stage tile pipeline)"),
+    "inverse9_f64_1M": dict(op="inverse", dtype="f64", n=9, batch=1 << 20, bytes=1297, bound="hbm", desc="1Mi 9x9 Double inverse (record per thread; factors parked in shared memory for the replay)"),
     "det3_f64_4M": dict(op="det", dtype="f64", n=3, batch=1 << 22, bytes=80, bound="hbm", desc="4Mi 3x3 Double det (configs[2])"),
     "det4_f64_4M": dict(op="det", dtype="f64", n=4, batch=1 << 22, bytes=136, bound="hbm", desc="4Mi 4x4 Double det (configs[2])"),
     "inverse3_f64_4M": dict(op="inverse", dtype="f64", n=3, batch=1 << 22, bytes=145, bound="hbm", desc="4Mi 3x3 Double inverse (configs[2])"),
@@ -145,7 +148,7 @@ EXTRAS = ["matmul3x3_f64_1M", "matmul3x3_i64_1M", "matmul3x3_f64_64M", "transpos
           "dot4_f32_16M", "det3_f64_4M", "det4_f64_4M", "inverse3_f64_4M", "inverse4_f64_4M", "solve3_f64_4M",
           "solve4_f64_4M", "tensorprod8x8_f64_1M", "prod1_8x8_f64_1M", "matmul4x4_f32_soa_16M", "inverse4_f64_soa_4M", "tensorprod8x8_f64_soa_1M", "prod1_8x8_f64_soa_1M",
           "append_3x3_3x1_f64_4M", "transpose8x8x8_f64_1M", "dotsum4_f32_16M", "dotsum4_f32_soa_16M",
-          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "relayout_32x32_f32_256K", "dot64_f32_1M", "dot64_f64_1M", "prod2_8x8_f64_1M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M",
+          "relayout_4x4_f32_16M", "relayout_3x3_f64_soa_4M", "relayout_32x32_f32_256K", "dot64_f32_1M", "dot64_f64_1M", "prod2_8x8_f64_1M", "matmul5x5_f64_4M", "det8_f64_1M", "solve8_f64_1M", "det9_f64_1M", "solve9_f64_1M", "inverse9_f64_1M",
           "inverse6_f64_1M", "inverse8_f64_1M", "matmul32_f64_1M", "matmul32_f32_1M", "det16_f64_512K", "minpoly4_f64_4M", "echelon4x4_f64_4M", "echelon4x5_f64_4M", "echelon6x7_f64_1M", "echelon7x9_f64_1M"]
 NPD = {"f64": np.float64, "f32": np.float32, "i64": np.int64}
 

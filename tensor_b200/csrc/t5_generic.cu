@@ -332,9 +332,8 @@ int generic_longdot(const Shard& s, int dtype, int K, const void* X, const void*
     if (s.layout != T5L_AOS || K < 1) return T5I_NOT_SPECIALISED;
     if (s.count == 0) return T5I_OK;
     const size_t tiles = (s.count + TPB - 1) / TPB;
-    static const bool no_rows = getenv("T5_NO_LONGDOT_ROWS") != nullptr;    // tuning hook
     const size_t row_bytes = (size_t)K * (dtype == T5D_F32 ? 4 : 8);
-    if (!no_rows && row_bytes % 16 == 0 && (((uintptr_t)X | (uintptr_t)Y) & 15) == 0) {
+    if (row_bytes % 16 == 0 && (((uintptr_t)X | (uintptr_t)Y) & 15) == 0) {
         switch (dtype) {
             case T5D_F64: return longdot_rows_launch<double>(s, K, X, Y, O);
             case T5D_F32: return longdot_rows_launch<float>(s, K, X, Y, O);
@@ -619,8 +618,7 @@ bool staged_gather_fits(int elem_bytes, size_t d_in_total, size_t d_out_total, b
 int staged_gather(const Shard& s, int elem_bytes, size_t dA, size_t dB, size_t d1, size_t d2, const uint32_t* t1, const uint32_t* t2,
                   const void* A, const void* B, void* O1, void* O2) {
     constexpr int THREADS = 256;
-    static const bool off = getenv("T5_NO_STAGED_GATHER") != nullptr;       // tuning hook
-    if (off || s.layout != T5L_AOS || !staged_gather_fits(elem_bytes, dA + dB, d1 + d2, d1 && d2)) return T5I_NOT_SPECIALISED;
+    if (s.layout != T5L_AOS || !staged_gather_fits(elem_bytes, dA + dB, d1 + d2, d1 && d2)) return T5I_NOT_SPECIALISED;
     if (s.count == 0 || d1 + d2 == 0) return T5I_OK;
     const size_t V = 16 / elem_bytes, item = (dA + dB) * elem_bytes;
     if ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)O1 | (uintptr_t)O2) & 15) != 0) return T5I_NOT_SPECIALISED;
@@ -2268,11 +2266,6 @@ relayout_tile64_uniform_kernel(const T* __restrict__ src, T* __restrict__ dst, u
     }
 }
 
-static int relayout_ti_override() {          // tuning hook: T5_RL_TI = items per staged tile
-    static const int v = [] { const char* e = getenv("T5_RL_TI"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
 template <class P>
 static int relayout_small_launch(void (*kern)(const P*, P*, unsigned long long, unsigned, unsigned long long, int), cudaStream_t st, int ti,
                                  size_t pitch, size_t d, size_t count, size_t soa_stride, bool to_soa, const void* src, void* dst) {
@@ -2312,7 +2305,6 @@ int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa
     if (count == 0 || d == 0) return T5I_OK;
     // 8-byte accesses need rows padded to an even number of items and 8-byte aligned bases (cudaMalloc gives 256)
     const bool wide = soa_stride % 2 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 7) == 0;
-    static const int small_max = [] { const char* e = getenv("T5_RL_SMALL_MAX"); return e ? atoi(e) : 64; }();   // tuning hook
     // Items per staged tile: row segments of 1 KB (256 four-byte / 128 eight-byte items), twice that while the tile stays
     // under 8 KB (records of a few elements), halved while it exceeds 33 KB (measured: 4x4 Float 5.2 / 4.0 TB/s to / from SoA
     // with 128 items, 6.1 / 6.3 with 256; 2x3 Double 5.4 -> 6.3 with 256; 8x8 Float 5.5 / 6.4 with 128, 5.2 / 5.5 with 256).
@@ -2322,8 +2314,7 @@ int relayout(cudaStream_t st, int elem_bytes, size_t d, size_t count, size_t soa
     if (ti * item_tile < 8 * 1024) ti *= 2;
     while (ti > 64 && ti * item_tile > 33 * 1024) ti /= 2;
     if (elem_bytes == 4 && !wide) ti = 128;
-    if (relayout_ti_override()) ti = relayout_ti_override();
-    if (d <= (size_t)small_max && d <= 64 && !(elem_bytes == 8 && d > 32)) {
+    if (d <= 64 && !(elem_bytes == 8 && d > 32)) {
         if (elem_bytes == 8) return relayout_small<unsigned long long>(st, ti, d, count, soa_stride, to_soa, src, dst);
         if (elem_bytes == 4 && wide) return relayout_small_pair(st, ti, d, count, soa_stride, to_soa, src, dst);
         if (elem_bytes == 4) return relayout_small<unsigned>(st, ti, d, count, soa_stride, to_soa, src, dst);

@@ -1,5 +1,7 @@
 """Developer timing: t5_relayout in both directions over record sizes either side of the 64-element staging limit, and
-the SoA 8x8 contraction (T5_SOA_PROD_VARIANT picks the kernel while it is being tuned).  Device-resident, CUDA events on
+the SoA 8x8 contraction, the structural gathers, long dots, the any-shape echelon kernel and the SoA outer product.  (The
+environment variables some labels mention selected kernel variants while these were tuned - the A/B files under profiles/
+r02f .. r02q - and no longer exist in the library.)  Device-resident, CUDA events on
 the library's stream, GB/s against read + written bytes.  Usage (GPU box): python tools/time_relayout.py [prod | struct | dot | echelon | outer]"""
 import os
 import sys
