@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
                 for (int ch = tid; ch < nchB; ch += THREADS)
                     cp_async16(sB + (ch / C::B_CPI) * C::B_ITEM + (ch % C::B_CPI) * 16, srcB + (size_t)ch * 16);
             } else {
+                // (Tried and dropped, profiles/r02r_sweep_matmul_vector_staging.txt: reading these contiguous runs as 16-byte
+                // vectors into registers and scattering the elements to their padded places from there - the copy is no longer
+                // asynchronous and every size lost: 9x9 Double 3.8 -> 3.2 TB/s, 19x19 2.8 -> 2.0, 16x16 . 16 Float 4.3 -> 3.6.)
                 constexpr int ES = (int)sizeof(T);
                 const int neA = nv * P * K, neB = nv * K * Q;
                 for (int e = tid; e < neA; e += THREADS)
