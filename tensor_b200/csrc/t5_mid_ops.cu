@@ -36,6 +36,9 @@ struct Cfg {
     // rows that are whole 16-byte chunks are copied chunk-wise and B items stay packed; other extents (odd n for
     // 8-byte elements, n % 4 != 0 for Float) are copied element-wise into rows padded to the next chunk
     static constexpr bool ALIGNED = A_ROW % 16 == 0 && B_ROW % 16 == 0;
+    // matrix . vector (Q = 1) can never have chunk-sized B rows, but its A - K times the data - may: A alone is then copied
+    // chunk-wise (16x16 . 16 Float: every A element was a 4-byte asynchronous copy of its own)
+    static constexpr bool A_CHUNKS = A_ROW % 16 == 0;
     static constexpr int A_CPR = up16(A_ROW) / 16;              // chunks per (padded) A row
     static constexpr int A_RS = up16(A_ROW) + ((A_CPR % 2 == 0) ? 16 : 0);
     static constexpr int A_STAGE = G * P * A_RS;
@@ -79,6 +82,15 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
                     cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
                 for (int ch = tid; ch < nchB; ch += THREADS)
                     cp_async16(sB + (ch / C::B_CPI) * C::B_ITEM + (ch % C::B_CPI) * 16, srcB + (size_t)ch * 16);
+            } else if constexpr (C::A_CHUNKS) {
+                constexpr int ES = (int)sizeof(T);
+                const int nchA = nv * P * C::A_CPR, neB = nv * K * Q;
+                for (int ch = tid; ch < nchA; ch += THREADS)
+                    cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
+                for (int e = tid; e < neB; e += THREADS) {
+                    const int item = e / (K * Q), rem = e - item * (K * Q);
+                    cp_async_small<ES>(sB + item * C::B_ITEM + (rem / Q) * C::B_RS + (rem % Q) * ES, srcB + (size_t)e * ES);
+                }
             } else {
                 // (Tried and dropped, profiles/r02r_sweep_matmul_vector_staging.txt: reading these contiguous runs as 16-byte
                 // vectors into registers and scattering the elements to their padded places from there - the copy is no longer
