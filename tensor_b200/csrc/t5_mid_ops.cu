@@ -36,9 +36,6 @@ struct Cfg {
     // rows that are whole 16-byte chunks are copied chunk-wise and B items stay packed; other extents (odd n for
     // 8-byte elements, n % 4 != 0 for Float) are copied element-wise into rows padded to the next chunk
     static constexpr bool ALIGNED = A_ROW % 16 == 0 && B_ROW % 16 == 0;
-    // matrix . vector (Q = 1) can never have chunk-sized B rows, but its A - K times the data - may: A alone is then copied
-    // chunk-wise (16x16 . 16 Float: every A element was a 4-byte asynchronous copy of its own)
-    static constexpr bool A_CHUNKS = A_ROW % 16 == 0;
     static constexpr int A_CPR = up16(A_ROW) / 16;              // chunks per (padded) A row
     static constexpr int A_RS = up16(A_ROW) + ((A_CPR % 2 == 0) ? 16 : 0);
     static constexpr int A_STAGE = G * P * A_RS;
@@ -51,6 +48,12 @@ struct Cfg {
     static constexpr int SMEM = STAGES * STAGE;
     static_assert(THREADS % 32 == 0 && G >= 1, "bad thread count");
 };
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_unit(void* smem_dst, const void* gsrc) {
+    if constexpr (BYTES == 16) cp_async16(smem_dst, gsrc);
+    else cp_async_small<BYTES>(smem_dst, gsrc);
+}
 
 template <class T, int P, int K, int Q, int THREADS, int STAGES>
 __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
@@ -82,26 +85,22 @@ __global__ void __launch_bounds__(THREADS) rowprod_kernel(Args a) {
                     cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
                 for (int ch = tid; ch < nchB; ch += THREADS)
                     cp_async16(sB + (ch / C::B_CPI) * C::B_ITEM + (ch % C::B_CPI) * 16, srcB + (size_t)ch * 16);
-            } else if constexpr (C::A_CHUNKS) {
-                constexpr int ES = (int)sizeof(T);
-                const int nchA = nv * P * C::A_CPR, neB = nv * K * Q;
-                for (int ch = tid; ch < nchA; ch += THREADS)
-                    cp_async16(sA + (ch / C::A_CPR) * C::A_RS + (ch % C::A_CPR) * 16, srcA + (size_t)ch * 16);
-                for (int e = tid; e < neB; e += THREADS) {
-                    const int item = e / (K * Q), rem = e - item * (K * Q);
-                    cp_async_small<ES>(sB + item * C::B_ITEM + (rem / Q) * C::B_RS + (rem % Q) * ES, srcB + (size_t)e * ES);
-                }
             } else {
+                // Rows that are not whole chunks: each operand moves in the largest unit its OWN row length allows - 16 bytes
+                // (matrix . vector: A's rows may be whole chunks although a one-element B row never is), 8 bytes (Float rows
+                // of an even length), else one element per asynchronous copy.
                 // (Tried and dropped, profiles/r02r_sweep_matmul_vector_staging.txt: reading these contiguous runs as 16-byte
                 // vectors into registers and scattering the elements to their padded places from there - the copy is no longer
                 // asynchronous and every size lost: 9x9 Double 3.8 -> 3.2 TB/s, 19x19 2.8 -> 2.0, 16x16 . 16 Float 4.3 -> 3.6.)
                 constexpr int ES = (int)sizeof(T);
-                const int neA = nv * P * K, neB = nv * K * Q;
-                for (int e = tid; e < neA; e += THREADS)
-                    cp_async_small<ES>(sA + (e / K) * C::A_RS + (e % K) * ES, srcA + (size_t)e * ES);
-                for (int e = tid; e < neB; e += THREADS) {
-                    const int item = e / (K * Q), rem = e - item * (K * Q);
-                    cp_async_small<ES>(sB + item * C::B_ITEM + (rem / Q) * C::B_RS + (rem % Q) * ES, srcB + (size_t)e * ES);
+                constexpr int AU = C::A_ROW % 16 == 0 ? 16 : (C::A_ROW % 8 == 0 ? 8 : ES), UA = C::A_ROW / AU;
+                constexpr int BU = C::B_ROW % 16 == 0 ? 16 : (C::B_ROW % 8 == 0 ? 8 : ES), UB = C::B_ROW / BU;
+                const int nuA = nv * P * UA, nuB = nv * K * UB;
+                for (int u = tid; u < nuA; u += THREADS)
+                    cp_async_unit<AU>(sA + (u / UA) * C::A_RS + (u % UA) * AU, srcA + (size_t)u * AU);
+                for (int u = tid; u < nuB; u += THREADS) {
+                    const int item = u / (K * UB), rem = u - item * (K * UB);
+                    cp_async_unit<BU>(sB + item * C::B_ITEM + (rem / UB) * C::B_RS + (rem % UB) * BU, srcB + (size_t)u * BU);
                 }
             }
         }
