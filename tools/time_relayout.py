@@ -67,6 +67,16 @@ def main():
     with tb.Context([0]) as ctx:
         if "struct" in sys.argv[1:]:
             return structural(ctx)
+        if "staged" in sys.argv[1:]:
+            for dt, es in ((np.float32, 4), (np.float64, 8), (np.int64, 8)):
+                for (m, k, n) in ((21, 21, 21), (23, 23, 23), (22, 22, 22), (13, 7, 19), (5, 24, 9), (23, 5, 6), (9, 9, 5)):
+                    batch = max(256, (256 << 20) // ((m * k + k * n + m * n) * es))
+                    A, B = ctx.synthetic((m, k), dt, batch, SEED, 1), ctx.synthetic((k, n), dt, batch, SEED + 1, 1)
+                    ms = timed(ctx, lambda: tb.matmul(A, B))
+                    print("matmul %2dx%2dx%2d %-8s x %8d %7.3f ms %6.0f GB/s%s" % (m, k, n, np.dtype(dt).name, batch, ms, batch * (m * k + k * n + m * n) * es / ms / 1e6,
+                          "  (one element per lane)" if os.environ.get("T5_STAGED_SCALAR") else ""), flush=True)
+                    A.free(); B.free()
+            return
         if "outer" in sys.argv[1:]:
             for dt, es in ((np.float64, 8), (np.float32, 4)):
                 batch = 1 << 18
