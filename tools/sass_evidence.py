@@ -26,6 +26,11 @@ FAMILIES = {
     "xgemm_exact": "xgemm_kernel",
     "lu_cta_per_matrix": "lu_kernel",
     "inverse8_f64": "InverseOp<double, 8>",
+    "det9_reg_f64": "DetOp<double, 9>",
+    "longdot_rows": "longdot_rows_kernel",
+    "relayout": "relayout_",
+    "soa_prod_split": "soa_prod_split",
+    "staged_gather": "staged_gather_kernel",
 }
 
 
