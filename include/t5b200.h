@@ -171,7 +171,7 @@ int t5_transpose(t5_ctx* ctx, int dtype, int rank, const uint64_t* dims, const t
  * passes); n > 128 is T5_ERR_UNSUPPORTED.  n <= 4: one record per thread in registers;
  * 5 <= n <= 8: record per thread with streamed results (nrhs in {1, 2, 3, 4, n}) or one row
  * per lane (other nrhs); just beyond that still a record per thread (det / solve with one
- * right-hand side / inverse: Double up to n = 12 / 13 / 11, Float up to 18 / 18 / 14);
+ * right-hand side / inverse: Double up to n = 12 / 13 / 11, Float up to 18 / 20 / 14);
  * otherwise up to n = 128: one CTA per matrix, the matrix 2D-cyclic in the CTA's registers.  Every size keeps the oracle's operation order: results are bit-identical
  * to oracle/t5_oracle.cpp, not merely within tolerance.  SoA: n <= 8 (nrhs in {1, 2, 3, 4, n})
  * directly, everything else through the AoS detour described at t5_matmul. */

@@ -38,7 +38,7 @@ int small_matmul(const Shard& s, int dtype, int m, int k, int n, const void* A, 
 int small_outer(const Shard& s, int dtype, int p, int q, const void* A, const void* B, void* C);   // tiny outer products (tile pipeline)
 int small_transpose(const Shard& s, int elem_bytes, int r, int c, const void* A, void* O);
 int small_det(const Shard& s, int dtype, int n, const void* A, void* O);
-// record-per-thread eliminations just beyond 8x8 (t5_small_ops_9.cu): Double up to 12 / 13 / 11 (det / solve / inverse), Float 18 / 18 / 14; AoS
+// record-per-thread eliminations just beyond 8x8 (t5_small_ops_9.cu): Double up to 12 / 13 / 11 (det / solve / inverse), Float 18 / 20 / 14; AoS
 int reg9_det(const Shard& s, int dtype, int n, const void* A, void* O);
 int reg9_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status);
 int reg9_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status);

@@ -13,6 +13,7 @@
 //   Double inverse 9: 2.475 -> 0.441   10: 2.714 -> 0.906   11: 2.971 -> 1.628   (12: 2.854 -> 3.125, not taken)
 //   Float det   9: 0.517 -> 0.059  10: 0.069  11: 0.095  12: 0.686 -> 0.148  14: 0.821 -> 0.188  16: 0.934 -> 0.407  17: 1.709 -> 0.554  18: 1.632 -> 1.083
 //   Float solve 9: 1.186 -> 0.071  12: 1.301 -> 0.176  14: 1.467 -> 0.226  16: 1.462 -> 0.573  17: 4.071 -> 1.069  18: 3.963 -> 1.433
+//               19: 1.680 and 20: 2.240 (743Ki / 671Ki items; the CTA-per-matrix kernel needs ~3.9 ms at these sizes)
 //   Float inverse 9: 1.717 -> 0.265  10: 1.769 -> 0.324  11: 1.950 -> 0.597  12: 2.040 -> 0.965  13: 2.133 -> 1.216  14: 2.326 -> 1.586  (15, 16 slower)
 // Registers / spills (ptxas): Double det 9 254 / 0, 10 255 / 348 B, 12 255 / 2.6 KB; Float det 14 226 / 0, 16 255 / 256 B.
 // AoS only (SoA operands arrive through the host layer's relayout detour).  Compiled with -fmad=false like every exact TU.
@@ -66,6 +67,8 @@ int reg9_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const 
         if (n == 16) return launch_reg<SolveOp<float, 16, 1>>(s, A, B, X, status);
         if (n == 17) return launch_reg<SolveOp<float, 17, 1>>(s, A, B, X, status);
         if (n == 18) return launch_reg<SolveOp<float, 18, 1>>(s, A, B, X, status);
+        if (n == 19) return launch_reg<SolveOp<float, 19, 1>>(s, A, B, X, status);
+        if (n == 20) return launch_reg<SolveOp<float, 20, 1>>(s, A, B, X, status);
     }
     return T5I_NOT_SPECIALISED;
 }

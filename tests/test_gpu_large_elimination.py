@@ -36,7 +36,7 @@ def inputs(dc, n, batch, seed_op):
 
 
 @pytest.mark.parametrize("dc", FRAC)
-@pytest.mark.parametrize("n", [9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 24, 25, 32, 33, 48, 64, 65, 100, 128])   # 9..14: the record-per-thread kernels of t5_small_ops_9.cu
+@pytest.mark.parametrize("n", [9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 24, 25, 32, 33, 48, 64, 65, 100, 128])   # 9..14: the record-per-thread kernels of t5_small_ops_9.cu
 def test_large_det_inverse_solve_bit_exact(ctx, dc, n):
     batch = 67 if n <= 32 else (35 if n <= 64 else 23)
     a = inputs(dc, n, batch, 60 + n)
