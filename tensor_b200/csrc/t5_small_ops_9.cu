@@ -17,6 +17,7 @@
 //   Float inverse 9: 1.717 -> 0.265  10: 1.769 -> 0.324  11: 1.950 -> 0.597  12: 2.040 -> 0.965  13: 2.133 -> 1.216  14: 2.326 -> 1.586  (15, 16 slower)
 // Registers / spills (ptxas): Double det 9 254 / 0, 10 255 / 348 B, 12 255 / 2.6 KB; Float det 14 226 / 0, 16 255 / 256 B.
 // AoS only (SoA operands arrive through the host layer's relayout detour).  Compiled with -fmad=false like every exact TU.
+// This file holds the `det` instances; `solve` and `inverse` are t5_small_ops_9_solve.cu / _inverse.cu (parallel builds).
 #include "t5_tile_launch.cuh"
 
 namespace t5 {
@@ -44,48 +45,6 @@ int reg9_det(const Shard& s, int dtype, int n, const void* A, void* O) {
         if (n == 16) return launch_reg<DetOp<float, 16>>(s, A, nullptr, O, nullptr);
         if (n == 17) return launch_reg<DetOp<float, 17>>(s, A, nullptr, O, nullptr);
         if (n == 18) return launch_reg<DetOp<float, 18>>(s, A, nullptr, O, nullptr);
-    }
-    return T5I_NOT_SPECIALISED;
-}
-
-int reg9_solve(const Shard& s, int dtype, int n, int nrhs, const void* A, const void* B, void* X, void* status) {
-    if (s.layout != T5L_AOS || nrhs != 1) return T5I_NOT_SPECIALISED;
-    if (dtype == T5D_F64) {
-        if (n == 9) return launch_reg<SolveOp<double, 9, 1>>(s, A, B, X, status);
-        if (n == 10) return launch_reg<SolveOp<double, 10, 1>>(s, A, B, X, status);
-        if (n == 11) return launch_reg<SolveOp<double, 11, 1>>(s, A, B, X, status);
-        if (n == 12) return launch_reg<SolveOp<double, 12, 1>>(s, A, B, X, status);
-        if (n == 13) return launch_reg<SolveOp<double, 13, 1>>(s, A, B, X, status);
-    } else if (dtype == T5D_F32) {
-        if (n == 9) return launch_reg<SolveOp<float, 9, 1>>(s, A, B, X, status);
-        if (n == 10) return launch_reg<SolveOp<float, 10, 1>>(s, A, B, X, status);
-        if (n == 11) return launch_reg<SolveOp<float, 11, 1>>(s, A, B, X, status);
-        if (n == 12) return launch_reg<SolveOp<float, 12, 1>>(s, A, B, X, status);
-        if (n == 13) return launch_reg<SolveOp<float, 13, 1>>(s, A, B, X, status);
-        if (n == 14) return launch_reg<SolveOp<float, 14, 1>>(s, A, B, X, status);
-        if (n == 15) return launch_reg<SolveOp<float, 15, 1>>(s, A, B, X, status);
-        if (n == 16) return launch_reg<SolveOp<float, 16, 1>>(s, A, B, X, status);
-        if (n == 17) return launch_reg<SolveOp<float, 17, 1>>(s, A, B, X, status);
-        if (n == 18) return launch_reg<SolveOp<float, 18, 1>>(s, A, B, X, status);
-        if (n == 19) return launch_reg<SolveOp<float, 19, 1>>(s, A, B, X, status);
-        if (n == 20) return launch_reg<SolveOp<float, 20, 1>>(s, A, B, X, status);
-    }
-    return T5I_NOT_SPECIALISED;
-}
-
-int reg9_inverse(const Shard& s, int dtype, int n, const void* A, void* O, void* status) {
-    if (s.layout != T5L_AOS) return T5I_NOT_SPECIALISED;
-    if (dtype == T5D_F64) {
-        if (n == 9) return launch_reg<InverseOp<double, 9>>(s, A, nullptr, O, status);
-        if (n == 10) return launch_reg<InverseOp<double, 10>>(s, A, nullptr, O, status);
-        if (n == 11) return launch_reg<InverseOp<double, 11>>(s, A, nullptr, O, status);
-    } else if (dtype == T5D_F32) {
-        if (n == 9) return launch_reg<InverseOp<float, 9>>(s, A, nullptr, O, status);
-        if (n == 10) return launch_reg<InverseOp<float, 10>>(s, A, nullptr, O, status);
-        if (n == 11) return launch_reg<InverseOp<float, 11>>(s, A, nullptr, O, status);
-        if (n == 12) return launch_reg<InverseOp<float, 12>>(s, A, nullptr, O, status);
-        if (n == 13) return launch_reg<InverseOp<float, 13>>(s, A, nullptr, O, status);
-        if (n == 14) return launch_reg<InverseOp<float, 14>>(s, A, nullptr, O, status);
     }
     return T5I_NOT_SPECIALISED;
 }
